@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- pose-beam likelihood evaluations per second of the brute-force scan matcher.
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): one laser scan of 1081
+beams scored under the candidate set of BruteForcePoseEnumerator(+-1 m @0.02, +-0.5 rad @0.01)
+= 101 x 101 x 100 = 1 020 100 poses on a 2000 x 2000 grid at 0.05 m, obstacle OOPE, even
+weights.  A "step" is one full pass: trig table -> cell-index tables -> scoring kernel ->
+arg-max (-> 32-byte all-gather when N > 1).  Synthetic data (numpy, seeded).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); candidates are sharded by contiguous rows.
+`value` is device-timed with inputs resident in HBM; `e2e` goes through the host-buffer C-ABI
+call (scan + axes H2D, best index/score D2H).  The cpu_baseline / --impl reference legs time
+the UNMODIFIED reference (oracle/_ref/libslamref.so) on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAP_SIZE, MAP_SCALE, N_BEAMS = 2000, 0.05, 1081
+BF = dict(x=(-1.0, 1.0, 0.02), y=(-1.0, 1.0, 0.02), t=(-0.5, 0.5, 0.01))
+BYTES_PER_EVAL = 32  # one 32-byte sector per map gather
+L2_FLUSH = True
+
+
+# ---------------------------------------------------------------- synthetic inputs (numpy only)
+def room_ranges(rng, n, fov, half_w, half_h, pose, noise):
+    ang = np.linspace(-fov / 2, fov / 2, n, endpoint=False)
+    th = ang + pose[2]
+    c, s = np.cos(th), np.sin(th)
+    with np.errstate(divide="ignore"):
+        tx = np.where(c > 0, (half_w - pose[0]) / c, np.where(c < 0, (-half_w - pose[0]) / c, np.inf))
+        ty = np.where(s > 0, (half_h - pose[1]) / s, np.where(s < 0, (-half_h - pose[1]) / s, np.inf))
+    return np.minimum(tx, ty) + rng.normal(0, noise, n), ang
+
+
+def synth_map(rng, size, scale, half_w, half_h):
+    """MeanProbabilityCell records {p, n}: a walled room with clutter, free interior, unknown outside"""
+    cells = np.zeros((size, size, 2))
+    cells[..., 0] = 0.5
+    c = (np.arange(size) - size // 2 + 0.5) * scale
+    X, Y = np.meshgrid(c, c)
+    inside = (np.abs(X) < half_w) & (np.abs(Y) < half_h)
+    wall = (np.abs(X) < half_w + 3 * scale) & (np.abs(Y) < half_h + 3 * scale) & ~inside
+    n_obs = rng.integers(1, 30, (size, size)).astype(float)
+    p_free = np.clip(rng.normal(0.03, 0.02, (size, size)), 0.005, 0.3)
+    p_wall = np.clip(rng.normal(0.9, 0.05, (size, size)), 0.5, 0.99)
+    cells[..., 0] = np.where(inside, p_free, np.where(wall, p_wall, 0.5))
+    cells[..., 1] = np.where(inside | wall, n_obs, 0.0)
+    for _ in range(60):  # clutter boxes
+        bx, by = rng.uniform(-half_w, half_w), rng.uniform(-half_h, half_h)
+        bw, bh = rng.uniform(0.2, 1.5, 2)
+        box = (np.abs(X - bx) < bw) & (np.abs(Y - by) < bh) & inside
+        cells[..., 0] = np.where(box, p_wall, cells[..., 0])
+    return cells
+
+
+def bf_axis(base, lo, hi, step, inclusive_le):
+    """value list of BruteForcePoseEnumerator for one axis: FP accumulation with the reference's
+    per-axis stop rule (brute_force_scan_matcher.h:23-54): x/y emit, then step while v < to;
+    theta is emitted while t <= to"""
+    vals, v = [], lo
+    if inclusive_le:
+        while v <= hi:
+            vals.append(base + v)
+            v += step
+    else:
+        while True:
+            vals.append(base + v)
+            if not (v < hi):
+                break
+            v += step
+    return np.array(vals)
+
+
+def make_workload(seed=42):
+    rng = np.random.default_rng(seed)
+    half_w, half_h = 30.0, 22.0
+    cells = synth_map(rng, MAP_SIZE, MAP_SCALE, half_w, half_h)
+    true_pose = np.array([1.3, -2.1, 0.4])
+    r, a = room_ranges(rng, N_BEAMS, np.deg2rad(270), half_w, half_h, true_pose, 0.01)
+    base = true_pose + np.array([0.04, -0.03, 0.01])
+    xs = bf_axis(base[0], *BF["x"], False)
+    ys = bf_axis(base[1], *BF["y"], False)
+    ts = bf_axis(base[2], *BF["t"], True)
+    return dict(cells=cells, r=r, a=a, base=base, xs=xs, ys=ys, ts=ts)
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, gpu_index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        mhz, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                clk = float(f[0]); mx = float(f[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                mhz.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not mhz:  # the timed region was shorter than one sample: use every sample
+            for ts, line in self.rows:
+                try:
+                    mhz.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+# ---------------------------------------------------------------- reference (CPU) arm
+class ReferenceScorer:
+    """the unmodified reference (oracle/_ref, else the oracle port) scoring candidates of the workload
+    on the host cores: the checker / baseline, never on the product path"""
+
+    def __init__(self, wl):
+        from oracle import binding as ob
+        self.ob, self.wl = ob, wl
+        self.kind = "reference" if ob.ref is not None else "port"
+        self.P = np.stack(np.meshgrid(wl["ts"], wl["ys"], wl["xs"], indexing="ij"), -1).reshape(-1, 3)[:, ::-1]
+        self.r, self.a = ob.f64(wl["r"]), ob.f64(wl["a"])
+        self.occ = np.ones(N_BEAMS, np.uint8)
+        self.params = ob.spe_params()
+        if self.kind == "reference":
+            self.map = ob.RefMap(MAP_SIZE, MAP_SIZE, MAP_SCALE, ob.CELL_MEAN, ob.GROW_NONE)
+            self.map.set_cells(wl["cells"])
+        else:
+            self.map = ob.OracleMap(MAP_SIZE, MAP_SIZE, MAP_SCALE, ob.CELL_MEAN)
+            self.map.set_cells(wl["cells"])
+            self.scan = ob.OracleScan(self.r, self.a)
+
+    def sample(self, n_poses, seed=7):
+        n_poses = min(n_poses, len(self.P) - 1)
+        start = int(np.random.default_rng(seed).integers(0, len(self.P) - n_poses))
+        return np.ascontiguousarray(self.P[start:start + n_poses])
+
+    def score(self, poses, threads):
+        """returns (seconds, scores, threads used)"""
+        ob, wl = self.ob, self.wl
+        out = np.empty(len(poses))
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            ob.ref.ref_score_poses_mt(self.map.h_, N_BEAMS, ob.dptr(self.r), ob.dptr(self.a), ob.u8ptr(self.occ),
+                                      ob.SPW_EVEN, self.params, wl["base"][0], wl["base"][1], wl["base"][2],
+                                      ob.dptr(poses), len(poses), threads, ob.dptr(out))
+        else:
+            threads = 1
+            out = self.map.score(self.scan, self.params, poses)
+        return time.perf_counter() - t0, out, threads
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, cfg):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    wl = make_workload()
+    cores = host_cores()
+    ref = ReferenceScorer(wl)
+    poses = ref.sample(10000 * cores)  # bounded sample: roughly a second of work per step on all host threads
+    for _ in range(args.warmup):
+        ref.score(poses[:max(200, len(poses) // 10)], cores)
+    total, thr = 0.0, cores
+    for _ in range(args.steps):
+        dt, _, thr = ref.score(poses, cores)
+        total += dt
+    value = args.steps * len(poses) * N_BEAMS / total
+    sample = "%d consecutive candidates x %d beams per step of the same workload" % (len(poses), N_BEAMS)
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
+            "cpu_baseline": {"value": value, "unit": cfg["unit"], "cores": thr, "kind": ref.kind, "sample": sample},
+            "e2e": {"value": value, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = {"metric": "pose-beam likelihood evaluations/sec (brute-force scan matcher)", "unit": "evals/s",
+           "config": {"workload": "configs[2]: brute-force matcher, +-1 m @0.02 / +-0.5 rad @0.01 = 101x101x100 = 1020100 "
+                                  "candidate poses x 1081 beams, 2000x2000 grid @0.05 m, obstacle OOPE, even weights, "
+                                  "MeanProbabilityCell map",
+                      "candidates": 1020100, "beams": N_BEAMS, "grid": [MAP_SIZE, MAP_SIZE],
+                      "sharding": "candidate rows (theta, y) split contiguously over ranks, map replicated",
+                      "l2": "flushed (256 MB write) before every timed step" if L2_FLUSH else "not flushed"}}
+    if args.impl == "reference":
+        return run_reference_arm(args, cfg)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N > 1 with torchrun: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+
+    import slam_constructor_b200 as sg
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [sg.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    ctx = sg.Context(local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+
+    wl = make_workload()
+    P = len(wl["xs"]) * len(wl["ys"]) * len(wl["ts"])
+    gmap = sg.GridMap(ctx, MAP_SIZE, MAP_SIZE, MAP_SCALE, sg.CELL_MEAN)
+    gmap.upload(wl["cells"])
+    scan = sg.Scan(ctx, wl["r"], wl["a"])
+    params = sg.spe_params(sg.OOPE_OBSTACLE, sg.OIE_DISCREPANCY, trig=sg.TRIG_DEVICE)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    # ---- device-timed steps, inputs resident in HBM
+    ctx.stage_grid(scan, params, wl["xs"], wl["ys"], wl["ts"])
+    for _ in range(args.warmup):
+        ctx.score_launch(gmap)
+    _, idx0, best0 = ctx.score_fetch()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    launches0 = ctx.launch_count()
+    t_wall0 = time.time()
+    total_ms, kern_ms = 0.0, 0.0
+    for _ in range(args.steps):
+        if L2_FLUSH:
+            ctx.flush_l2()
+        ctx.timer_begin()
+        ctx.score_launch(gmap)
+        total_ms += ctx.timer_end()
+        kern_ms += ctx.last_kernel_ms()
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    _, idx1, best1 = ctx.score_fetch()
+    assert (idx1, best1) == (idx0, best0), "result changed between launches"
+    st = ctx.score_stats()
+
+    # ---- end to end through the host-buffer C-ABI call (what a GridScanMatcher adapter calls)
+    e2e_steps = args.steps
+    for _ in range(2):
+        scan.upload(wl["r"], wl["a"])
+        ctx.score_grid(gmap, scan, params, wl["xs"], wl["ys"], wl["ts"], want_scores=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        scan.upload(wl["r"], wl["a"])
+        _, idx2, best2 = ctx.score_grid(gmap, scan, params, wl["xs"], wl["ys"], wl["ts"], want_scores=False)
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    assert (idx2, best2) == (idx0, best0)
+    h2d = N_BEAMS * (6 * 8 + 1) + 8 * (len(wl["xs"]) + len(wl["ys"]) + len(wl["ts"])) + 16 * ((len(wl["ys"]) + 7) // 8) * len(wl["ts"])
+    d2h = 32
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, kern_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms, e2e_s = (float(v) for v in t.tolist())
+        ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln.item())
+
+    if rank == 0:
+        evals = P * N_BEAMS
+        value = evals * args.steps / (total_ms * 1e-3)
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (OSError, KeyError, ValueError):
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # dominant kernel: k_score_grid; algorithmic bytes = 32 B per pose-beam evaluation of this rank's slice
+        k_evals = st["evals"]
+        achieved = k_evals * BYTES_PER_EVAL / (kern_ms / args.steps * 1e-3) / 1e9
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get("k_score_grid_dram_bytes_per_launch")
+            except ValueError:
+                traffic = None
+        line = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
+                "e2e": {"value": evals * e2e_steps / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_score_grid", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "kernel_ms": kern_ms / args.steps,
+                             "note": "algorithmic bytes = 32 B (one sector) per pose-beam evaluation; the map is L2/L1 "
+                                     "resident so frac > 1 means sector reuse, not an error"},
+                "result": {"best_idx": idx0, "best_score": best0, "guard_hits": st["guard_hits"]}}
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            ref = ReferenceScorer(wl)
+            ref_poses = ref.sample(30000 * cores)
+            best_dt, ref_scores, thr = min((ref.score(ref_poses, cores) for _ in range(3)), key=lambda r: r[0])
+            got, _, _ = ctx.score_poses(gmap, scan, sg.spe_params(trig=sg.TRIG_DEVICE), ref_poses)
+            line["cpu_baseline"] = {"value": len(ref_poses) * N_BEAMS / best_dt, "unit": cfg["unit"], "cores": thr,
+                                    "kind": ref.kind,
+                                    "sample": "%d consecutive candidates x %d beams of the same workload, best of 3; GPU "
+                                              "scores on the sample bit-equal to the reference: %s"
+                                              % (len(ref_poses), N_BEAMS, bool(np.array_equal(got, ref_scores)))}
+        print(json.dumps(line))
+    gmap.close(); scan.close(); ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

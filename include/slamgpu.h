@@ -1,0 +1,263 @@
+/*
+ * slamgpu.h -- C ABI of libslamgpu.so: the B200 (sm_100a) scan-scoring, grid-update
+ * and max-pyramid engine for slam-constructor.
+ *
+ * This is the drop-in boundary.  Everything above it (the C++ plugin adapters in
+ * slam_constructor_b200/host/, the ctypes binding in slam_constructor_b200/capi.py,
+ * or a binding a maintainer adds to the reference) talks to the
+ * GPU only through these entry points: plain pointers and sizes, caller-owned host
+ * arrays, no C++ or torch types.  There is NO CPU fallback behind it: every compute
+ * entry point runs hand-written CUDA kernels or fails with a negative status.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * upstream repository root, OSLL/slam-constructor).
+ *
+ * Conventions
+ *   - return value: 0 = ok, negative = SLAMGPU_E_*; slamgpu_last_error(ctx) gives
+ *     a message.  Nothing throws or aborts across the boundary (the reference uses
+ *     assert / std::exit, src/utils/init_scan_matching.h:39-43).
+ *   - one slamgpu_ctx per world (or per GPU rank), externally serialised: the
+ *     reference core is single-threaded and not re-entrant.
+ *   - calls are synchronous unless named *_launch (then slamgpu_*_fetch / slamgpu_sync).
+ *   - a grid map is a dense row-major array cells[h][w][stride] of doubles plus
+ *     (w, h, scale, origin): internal index = external cell + origin
+ *     (src/core/maps/regular_squares_grid.h:120-143, plain_grid_map.h:40-44).
+ *   - all floating point on the parity-critical path is IEEE double without FMA
+ *     contraction, in the reference's operation order.
+ */
+#ifndef SLAMGPU_H
+#define SLAMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAMGPU_ABI_VERSION 1
+
+enum {
+  SLAMGPU_OK = 0,
+  SLAMGPU_E_INVALID = -1, /* bad argument */
+  SLAMGPU_E_CUDA = -2,    /* CUDA runtime / driver error (message has the code) */
+  SLAMGPU_E_NOMEM = -3,
+  SLAMGPU_E_NCCL = -4,
+  SLAMGPU_E_STATE = -5,   /* call order (e.g. fetch without launch) */
+  SLAMGPU_E_NODEVICE = -6 /* no usable sm_100 device: there is no CPU fallback */
+};
+
+/* ---- cell models: record layouts (doubles), same as the reference's cell classes ----
+ * LWW      {p, q, known}            GridCell base          src/core/maps/grid_cell.h:9-57
+ * AFFINE   {p, known}               AffineQualityMergeCell src/core/maps/naive_grid_cells.h:6-21
+ * MEAN     {p, n}                   MeanProbabilityCell    src/core/maps/naive_grid_cells.h:25-44
+ * TBM_*    {p, q, u, e, o, known}   TbmBaseCell            src/core/maps/tbm_grid_cells.h:8-79
+ * GMAPPING {p, ox, oy, hits, tries} GmappingBaseCell       src/slams/gmapping/gmapping_grid_cell.h:9-43
+ */
+enum {
+  SLAMGPU_CELL_LWW = 0,
+  SLAMGPU_CELL_AFFINE = 1,
+  SLAMGPU_CELL_MEAN = 2,
+  SLAMGPU_CELL_TBM_CONSISTENT = 3,
+  SLAMGPU_CELL_TBM_UNKNOWN_EVEN = 4,
+  SLAMGPU_CELL_GMAPPING = 5,
+  SLAMGPU_CELL_MODELS = 6
+};
+#define SLAMGPU_MAX_STRIDE 8
+
+/* ObservationImpactEstimator: src/core/scan_matchers/observation_impact_estimators.h:14-28 */
+enum { SLAMGPU_OIE_DISCREPANCY = 0, SLAMGPU_OIE_OCCUPANCY = 1 };
+/* OccupancyObservationProbabilityEstimator: src/core/scan_matchers/occupancy_observation_probability.h:12-99,
+ * src/slams/gmapping/gmapping_occupancy_observation_pe.h:11-45 */
+enum {
+  SLAMGPU_OOPE_OBSTACLE = 0,
+  SLAMGPU_OOPE_MAX = 1,
+  SLAMGPU_OOPE_MEAN = 2,
+  SLAMGPU_OOPE_OVERLAP = 3,
+  SLAMGPU_OOPE_GMAPPING = 4
+};
+/* map growth rule on update: PlainGridMap (bounded), UnboundedPlainGridMap (x1.2,
+ * src/core/maps/plain_grid_map.h:133-173), UnboundedLazyTiledGridMap (128-cell tiles,
+ * src/core/maps/lazy_tiled_grid_map.h:151-181) */
+enum { SLAMGPU_GROW_NONE = 0, SLAMGPU_GROW_PLAIN = 1, SLAMGPU_GROW_TILED = 2 };
+/* CellOccupancyEstimator: src/core/maps/const_occupancy_estimator.h:6-17, area_occupancy_estimator.h:27-240 */
+enum { SLAMGPU_EST_CONST = 0, SLAMGPU_EST_AREA = 1 };
+/* how beam trigonometry cos/sin(theta + angle) is produced for a candidate set:
+ *   HOST   : libm on the host, once per distinct theta -- bit-identical to the reference
+ *   DEVICE : CUDA sincos, once per distinct theta, with a boundary guard: any world
+ *            point that lands within a guard band of a cell border is recomputed with
+ *            HOST trig before the result is returned, so cell indices stay bit-exact */
+enum { SLAMGPU_TRIG_DEVICE = 0, SLAMGPU_TRIG_HOST = 1 };
+
+typedef struct slamgpu_ctx slamgpu_ctx;
+typedef struct slamgpu_map slamgpu_map;
+typedef struct slamgpu_scan slamgpu_scan;
+typedef struct slamgpu_pyramid slamgpu_pyramid;
+
+/* SPEParams + the OOPE/OIE choice: src/core/scan_matchers/grid_scan_matcher.h:105-136 */
+typedef struct slamgpu_spe_params {
+  int32_t oope;          /* SLAMGPU_OOPE_* */
+  int32_t oie;           /* SLAMGPU_OIE_* */
+  double win_v, win_h;   /* sp_analysis_area side lengths (vside, hside), metres */
+  int32_t prerotated;    /* SPEParams::scan_is_prerotated (scan must be Cartesian) */
+  int32_t trig_mode;     /* SLAMGPU_TRIG_* */
+  double gm_fullness_th; /* GMapping OOPE fullness threshold */
+  int32_t gm_window;     /* GMapping OOPE half window, cells */
+  int32_t reserved;
+} slamgpu_spe_params;
+
+/* CellOccupancyEstimator parameters (both kinds), src/utils/init_occupancy_mapping.h:42-80 */
+typedef struct slamgpu_estimator {
+  int32_t type; /* SLAMGPU_EST_* */
+  int32_t reserved;
+  double occ_p, occ_q;     /* base_occupied */
+  double empty_p, empty_q; /* base_empty */
+  double low_qual, unknown_qual;
+  double shift_amount; /* area estimator's function-static Shift_Amount
+                          (area_occupancy_estimator.h:71); <0: low_qual * cell side */
+} slamgpu_estimator;
+
+/* ------------------------------------------------------------------ context */
+int slamgpu_abi_version(void);
+/* number of visible CUDA devices with compute capability 10.x (0 on a CPU box) */
+int slamgpu_device_count(void);
+int slamgpu_ctx_create(int device, slamgpu_ctx **out);
+/* one rank of an n-rank job (one process per GPU).  `nccl_id` is the 128-byte
+ * ncclUniqueId made by slamgpu_nccl_unique_id on rank 0 and shipped to the others by
+ * the launcher.  Candidate sets are sharded over ranks by contiguous index range and
+ * merged by one 16-byte-per-rank all-gather. */
+int slamgpu_nccl_unique_id(void *id128);
+int slamgpu_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id128, slamgpu_ctx **out);
+void slamgpu_ctx_destroy(slamgpu_ctx *ctx);
+const char *slamgpu_last_error(const slamgpu_ctx *ctx); /* ctx may be NULL: last create error */
+int slamgpu_sync(slamgpu_ctx *ctx);
+/* device-side stop watch on the ctx stream (CUDA events) for bench.py */
+int slamgpu_timer_begin(slamgpu_ctx *ctx);
+int slamgpu_timer_end(slamgpu_ctx *ctx, float *ms);
+/* device time of the dominant kernel of the last compute call (the scoring kernel of K1, the
+ * apply kernel of K3, ...), from CUDA events recorded around that one launch */
+int slamgpu_last_kernel_ms(slamgpu_ctx *ctx, float *ms);
+/* kernels launched by this ctx since creation (bench.py's gpu_launches) */
+int64_t slamgpu_launch_count(const slamgpu_ctx *ctx);
+/* write (and discard) a buffer larger than L2 on the ctx stream */
+int slamgpu_flush_l2(slamgpu_ctx *ctx);
+
+/* ------------------------------------------------------------------ grid map
+ * replaces GridMap / PlainGridMap / UnboundedPlainGridMap / UnboundedLazyTiledGridMap storage
+ * (src/core/maps/grid_map.h:22-74, plain_grid_map.h:13-190, lazy_tiled_grid_map.h:18-187) */
+int slamgpu_model_stride(int model);
+void slamgpu_default_unknown(int model, double *rec /* SLAMGPU_MAX_STRIDE */);
+int slamgpu_map_create(slamgpu_ctx *ctx, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
+                       const double *unknown_rec /* NULL: the model's default prototype */, slamgpu_map **out);
+void slamgpu_map_destroy(slamgpu_map *m);
+int slamgpu_map_info(const slamgpu_map *m, int32_t *w, int32_t *h, double *scale, int32_t *ox, int32_t *oy,
+                     int32_t *stride);
+/* replace the whole content (dims and origin may change); cells = h*w*stride doubles */
+int slamgpu_map_upload(slamgpu_map *m, const double *cells, int32_t w, int32_t h, int32_t ox, int32_t oy);
+int slamgpu_map_download(slamgpu_map *m, double *cells /* h*w*stride */);
+/* GridMap::operator[] / update / reset for single cells (host mirror plumbing;
+ * src/core/maps/grid_map.h:41-57).  (x, y) are external cell coordinates. */
+int slamgpu_map_read_cell(slamgpu_map *m, int32_t x, int32_t y, double *rec);
+int slamgpu_map_reset_cell(slamgpu_map *m, int32_t x, int32_t y, const double *rec);
+int slamgpu_map_update_cell(slamgpu_map *m, int32_t x, int32_t y, int32_t aoo_is_occ, double aoo_p, double aoo_q,
+                            double obst_x, double obst_y, double quality);
+/* the per-cell observation impact ("score LUT") the scoring kernels gather:
+ * OIE(cell, obstacle AOO {true,{1,1},.,1}), grid_scan_matcher.h:44-46 */
+int slamgpu_map_lut_download(slamgpu_map *m, int32_t oie, double *lut /* h*w */, double *unknown_value);
+
+/* ------------------------------------------------------------------ laser scan
+ * replaces LaserScan2D / ScanPoint2D (src/core/states/sensor_data.h:14-208) as the
+ * kernels see it: filtered points with their pose-independent weights (the output of
+ * WeightedMeanPointProbabilitySPE::filter_scan + ScanPointWeighting,
+ * weighted_mean_point_probability_spe.h:21-95). */
+int slamgpu_scan_create(slamgpu_ctx *ctx, slamgpu_scan **out);
+void slamgpu_scan_destroy(slamgpu_scan *s);
+int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian, const double *a /* range | x */,
+                        const double *b /* angle | y */, const uint8_t *occ /* NULL: all occupied */,
+                        const double *factor /* NULL: 1.0 */, const double *weight /* NULL: 1/n */);
+
+/* ------------------------------------------------------------------ K1: batched scan likelihood
+ * replaces the candidate loop of PoseEnumerationScanMatcher::process_scan
+ * (src/core/scan_matchers/pose_enumeration_scan_matcher.h:48-65) around
+ * WeightedMeanPointProbabilitySPE::estimate_scan_probability
+ * (weighted_mean_point_probability_spe.h:97-133): scores[k] = scan probability under
+ * poses[k]; (best_idx, best_score) = the sequential strict-'<' accept loop started from
+ * init_score, i.e. the lowest index among the maxima that beat init_score, or -1.
+ * Under a dist ctx every rank passes the same full candidate set, scores its own
+ * contiguous slice (out_scores is filled for that slice only) and gets the global best. */
+int slamgpu_score_poses(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                        const double *poses /* 3*P: x, y, theta */, int64_t P, double init_score,
+                        double *out_scores /* P or NULL */, int64_t *best_idx, double *best_score);
+/* the same for the candidate set of BruteForcePoseEnumerator
+ * (src/core/scan_matchers/brute_force_scan_matcher.h:10-64): the Cartesian product
+ * thetas x ys x xs in the enumerator's order, index = (t*ny + y)*nx + x.  The axis
+ * value lists are the enumerator's own accumulated values (base pose included). */
+int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                       const double *xs, int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt,
+                       double init_score, double *out_scores /* nt*ny*nx or NULL */, int64_t *best_idx,
+                       double *best_score);
+/* split form used by bench.py to time the device part with inputs resident in HBM:
+ * stage a candidate set once, launch any number of times, fetch the last result */
+int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *poses,
+                        int64_t P);
+int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *xs,
+                       int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt);
+int slamgpu_score_launch(slamgpu_ctx *ctx, slamgpu_map *map, double init_score);
+int slamgpu_score_fetch(slamgpu_ctx *ctx, double *out_scores /* NULL ok */, int64_t *best_idx, double *best_score);
+/* counters of the last scoring call: [0] guard hits (points re-done with host trig),
+ * [1] kernel variant used (0 list, 1 grid-tiled), [2] evaluations (poses*points) on this rank,
+ * [3] first candidate index of this rank's slice, [4] slice length */
+int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]);
+
+/* ------------------------------------------------------------------ K2: ray casting
+ * replaces RegularSquaresGrid::world_to_cells (src/core/maps/regular_squares_grid.h:56-101,
+ * fail-over DiscreteSegment2D src/core/geometry_discrete_primitives.h:55-104) for every
+ * beam of a scan seen from `pose`.  out_offsets[n+1] are prefix sums; out_cells holds
+ * (x, y) pairs, external coordinates, in the reference's order.  Pass out_cells = NULL
+ * (cap 0) to get only the offsets/total.  Bit-exact. */
+int slamgpu_raycast(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
+                    int64_t *out_offsets /* n+1 */, int32_t *out_cells /* 2*cap */, int64_t cap, int64_t *total);
+
+/* ------------------------------------------------------------------ K2+K3: scan insertion
+ * replaces GridMapScanAdder::append_scan + WallDistanceBlurringScanAdder::handle_scan_point
+ * (src/core/maps/grid_map_scan_adders.h:54-75, 138-189), the const/area occupancy estimators
+ * and the cell models' operator+= with the reference's update order (beam index, then the
+ * obstacle cell first).  `point_quality` (NULL: 1.0) is the per-point factor of the
+ * ObservationMappingQualityEstimator (grid_map_scan_adders.h:22-46), a host precompute.
+ * The scan here is the RAW scan (all points, occupied flags).  *cells_updated counts
+ * ray-cast cells. */
+int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
+                        double scan_quality, int32_t scan_margin, const slamgpu_estimator *est, double blur,
+                        double max_range, const double *point_quality, int64_t *cells_updated);
+
+/* ------------------------------------------------------------------ K4/K5: max-pyramid
+ * replaces RescalableCachingGridMap + M3RSMRescalableGridMap
+ * (src/core/maps/rescalable_caching_grid_map.h:16-200, src/core/scan_matchers/m3rsm_engine.h:17-131)
+ * and the Match upper bound (m3rsm_engine.h:156-180). */
+int slamgpu_pyramid_create(slamgpu_ctx *ctx, slamgpu_map *fine, int32_t oie, slamgpu_pyramid **out);
+void slamgpu_pyramid_destroy(slamgpu_pyramid *p);
+int slamgpu_pyramid_levels(slamgpu_pyramid *p);
+int slamgpu_pyramid_level_info(slamgpu_pyramid *p, int32_t level, int32_t *w, int32_t *h, double *scale, int32_t *ox,
+                               int32_t *oy);
+/* rebuild every coarse level from the fine map (what the reference's incremental rule
+ * yields for a map whose cells were each written once, or whose impacts only grew) */
+int slamgpu_pyramid_build(slamgpu_pyramid *p);
+int slamgpu_pyramid_level_download(slamgpu_pyramid *p, int32_t level, double *cells /* h*w*stride */,
+                                   double *impact /* h*w or NULL */);
+int slamgpu_pyramid_rescale(slamgpu_pyramid *p, double target_scale); /* level id, rescale :79-91 */
+/* scan insertion through the pyramid (update :100-105 -> update_coarser_maps :101-126) */
+int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const double pose[3], double scan_quality,
+                                int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
+                                const double *point_quality, int64_t *cells_updated);
+/* batched Match bounds: M windows, each over one of the pre-rotated scans.  windows =
+ * {bot, top, left, right} per match (metres, relative to pose); bound[m] = scan probability
+ * of scans[scan_id[m]] at the window centre on the level rescale(max side) with the `max`
+ * OOPE over the window re-centred at each point. */
+int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *scans, int32_t n_scans, const int32_t *scan_id,
+                          const double *windows /* 4*M */, int64_t M, const double pose[3],
+                          const slamgpu_spe_params *spe, double *out_bounds /* M */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMGPU_H */

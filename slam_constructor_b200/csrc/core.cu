@@ -1,0 +1,444 @@
+// core.cu -- context, device grid map, scan upload, score-LUT kernels, timers.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "dev_math.cuh"
+#include "internal.h"
+
+// ------------------------------------------------------------------ errors
+static std::string g_last_error;
+void sg_set_global_error(const char *msg) { g_last_error = msg; }
+int sg_fail(slamgpu_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  g_last_error = buf;
+  return code;
+}
+
+int DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return SLAMGPU_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  size_t want = std::max<size_t>(bytes + bytes / 4, 256);
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); return SLAMGPU_E_NOMEM; }
+    want = bytes;
+  }
+  cap = want;
+  return SLAMGPU_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+}
+
+int sg_pinned(slamgpu_ctx *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->h_pinned_cap) {
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr; ctx->h_pinned_cap = 0;
+    size_t want = std::max<size_t>(bytes * 2, 4096);
+    SG_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, want));
+    ctx->h_pinned_cap = want;
+  }
+  *out = ctx->h_pinned;
+  return SLAMGPU_OK;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int slamgpu_abi_version(void) { return SLAMGPU_ABI_VERSION; }
+
+extern "C" int slamgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ++ok;
+  }
+  return ok;
+}
+
+static int ctx_create_common(int device, slamgpu_ctx **out) {
+  if (!out) return sg_fail(nullptr, SLAMGPU_E_INVALID, "slamgpu_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return sg_fail(nullptr, SLAMGPU_E_NODEVICE, "no CUDA device visible: libslamgpu has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return sg_fail(nullptr, SLAMGPU_E_INVALID, "device %d out of range (%d visible)", device, n);
+  cudaDeviceProp pr;
+  if (cudaGetDeviceProperties(&pr, device) != cudaSuccess)
+    return sg_fail(nullptr, SLAMGPU_E_CUDA, "cudaGetDeviceProperties(%d) failed", device);
+  if (pr.major != 10)
+    return sg_fail(nullptr, SLAMGPU_E_NODEVICE, "device %d is sm_%d%d; libslamgpu is built for sm_100a only", device,
+                   pr.major, pr.minor);
+  slamgpu_ctx *ctx = new slamgpu_ctx();
+  ctx->device = device;
+  ctx->sm_count = pr.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess) {
+    int r = sg_fail(nullptr, SLAMGPU_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return r;
+  }
+  *out = ctx;
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_ctx_create(int device, slamgpu_ctx **out) { return ctx_create_common(device, out); }
+
+extern "C" int slamgpu_nccl_unique_id(void *id128) {
+  std::string err;
+  int r = sg_nccl_unique_id(id128, &err);
+  if (r != SLAMGPU_OK) return sg_fail(nullptr, r, "%s", err.c_str());
+  return r;
+}
+
+extern "C" int slamgpu_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id128, slamgpu_ctx **out) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return sg_fail(nullptr, SLAMGPU_E_INVALID, "bad rank %d / %d", rank, nranks);
+  SG_TRY(ctx_create_common(device, out));
+  slamgpu_ctx *ctx = *out;
+  ctx->rank = rank; ctx->nranks = nranks;
+  if (nranks > 1) {
+    if (!nccl_id128) { slamgpu_ctx_destroy(ctx); *out = nullptr; return sg_fail(nullptr, SLAMGPU_E_INVALID, "nccl id is NULL"); }
+    std::string err;
+    int r = sg_nccl_init(nranks, rank, nccl_id128, &ctx->comm, &err);
+    if (r != SLAMGPU_OK) { slamgpu_ctx_destroy(ctx); *out = nullptr; return sg_fail(nullptr, r, "%s", err.c_str()); }
+  }
+  return SLAMGPU_OK;
+}
+
+extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) sg_nccl_destroy(ctx->comm);
+  Candidates &c = ctx->cand;
+  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.trc, &c.trs,
+                    &c.scores, &c.blk_best, &c.result, &ctx->flush, &ctx->gather};
+  for (DevBuf *b : bufs) b->release();
+  for (DevBuf &b : ctx->scratch) b.release();
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->evk0);
+  cudaEventDestroy(ctx->evk1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *slamgpu_last_error(const slamgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int slamgpu_sync(slamgpu_ctx *ctx) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+extern "C" int slamgpu_timer_begin(slamgpu_ctx *ctx) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  SG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return SLAMGPU_OK;
+}
+extern "C" int slamgpu_timer_end(slamgpu_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return SLAMGPU_E_INVALID;
+  SG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  SG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  SG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return SLAMGPU_OK;
+}
+extern "C" int slamgpu_last_kernel_ms(slamgpu_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return SLAMGPU_E_INVALID;
+  if (!ctx->evk_valid) return sg_fail(ctx, SLAMGPU_E_STATE, "no dominant-kernel timing recorded yet");
+  SG_CUDA(ctx, cudaEventSynchronize(ctx->evk1));
+  SG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->evk0, ctx->evk1));
+  return SLAMGPU_OK;
+}
+extern "C" int64_t slamgpu_launch_count(const slamgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+__global__ void k_flush_l2(float4 *p, size_t n, float v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) p[i] = make_float4(v, v, v, v);
+}
+extern "C" int slamgpu_flush_l2(slamgpu_ctx *ctx) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  const size_t bytes = 256u << 20;  // > 126 MB L2
+  if (ctx->flush.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "flush buffer");
+  k_flush_l2<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->flush.as<float4>(), bytes / 16, 1.0f);
+  SG_CUDA(ctx, cudaGetLastError());
+  return SLAMGPU_OK;
+}
+
+int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv) {
+  std::string err;
+  int r = sg_nccl_allgather(ctx->comm, d_send16, d_recv, 16, ctx->stream, &err);
+  if (r != SLAMGPU_OK) return sg_fail(ctx, r, "%s", err.c_str());
+  return SLAMGPU_OK;
+}
+
+// ------------------------------------------------------------------ map
+extern "C" int slamgpu_model_stride(int model) { return sg::model_stride(model); }
+
+// prototypes: test/core/mock_grid_cell.h:10-11, naive_grid_cells.h:8,27, tbm_grid_cells.h:10,
+// slams/gmapping/gmapping_grid_cell.h:14
+extern "C" void slamgpu_default_unknown(int model, double *r) {
+  memset(r, 0, sizeof(double) * SLAMGPU_MAX_STRIDE);
+  switch (model) {
+    case SLAMGPU_CELL_LWW:
+    case SLAMGPU_CELL_AFFINE:
+    case SLAMGPU_CELL_MEAN: r[0] = 0.5; break;
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: r[0] = 0.5; r[1] = 1; r[2] = 1; break;
+    case SLAMGPU_CELL_GMAPPING: r[0] = -1; break;
+  }
+}
+
+struct RecParam { double v[SLAMGPU_MAX_STRIDE]; };
+
+__global__ void k_fill_cells(double *cells, size_t n_cells, int stride, RecParam rec) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  size_t n = n_cells * stride;
+  for (; i < n; i += st) cells[i] = rec.v[i % stride];
+}
+
+int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h) {
+  slamgpu_ctx *ctx = m->ctx;
+  size_t need = (size_t)w * h * m->stride;
+  if (need > m->cells_cap) {
+    if (m->d_cells) cudaFree(m->d_cells);
+    m->d_cells = nullptr; m->cells_cap = 0;
+    SG_CUDA(ctx, cudaMalloc(&m->d_cells, std::max<size_t>(need, 1) * sizeof(double)));
+    m->cells_cap = need;
+  }
+  m->w = w; m->h = h;
+  m->pitch = (w + 2 * SG_LUT_PAD + 1) & ~1;
+  sg_map_invalidate_lut(m);
+  return SLAMGPU_OK;
+}
+
+void sg_map_invalidate_lut(slamgpu_map *m) { m->lut_valid[0] = m->lut_valid[1] = false; }
+
+extern "C" int slamgpu_map_create(slamgpu_ctx *ctx, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
+                                  const double *unknown_rec, slamgpu_map **out) {
+  if (!ctx || !out) return SLAMGPU_E_INVALID;
+  *out = nullptr;
+  if (w < 0 || h < 0 || !(scale > 0) || model < 0 || model >= SLAMGPU_CELL_MODELS || grow < 0 || grow > SLAMGPU_GROW_TILED)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "slamgpu_map_create: bad arguments (w=%d h=%d scale=%g model=%d grow=%d)", w, h,
+                   scale, model, grow);
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  slamgpu_map *m = new slamgpu_map();
+  m->ctx = ctx; m->scale = scale; m->model = model; m->grow = grow;
+  m->stride = sg::model_stride(model);
+  m->ox = w / 2; m->oy = h / 2;  // regular_squares_grid.h:120-122
+  if (unknown_rec) memcpy(m->unknown, unknown_rec, sizeof(double) * m->stride);
+  else slamgpu_default_unknown(model, m->unknown);
+  int r = sg_map_realloc(m, w, h);
+  if (r != SLAMGPU_OK) { slamgpu_map_destroy(m); return r; }
+  RecParam rp;
+  memcpy(rp.v, m->unknown, sizeof rp.v);
+  if ((size_t)w * h > 0) {
+    k_fill_cells<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(m->d_cells, (size_t)w * h, m->stride, rp);
+    SG_LAUNCHED(ctx);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { slamgpu_map_destroy(m); return sg_fail(ctx, SLAMGPU_E_CUDA, "k_fill_cells: %s", cudaGetErrorString(e)); }
+  }
+  *out = m;
+  return SLAMGPU_OK;
+}
+
+extern "C" void slamgpu_map_destroy(slamgpu_map *m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  if (m->d_cells) cudaFree(m->d_cells);
+  for (int i = 0; i < 2; ++i)
+    if (m->d_lut[i]) cudaFree(m->d_lut[i]);
+  delete m;
+}
+
+extern "C" int slamgpu_map_info(const slamgpu_map *m, int32_t *w, int32_t *h, double *scale, int32_t *ox, int32_t *oy,
+                                int32_t *stride) {
+  if (!m) return SLAMGPU_E_INVALID;
+  if (w) *w = m->w;
+  if (h) *h = m->h;
+  if (scale) *scale = m->scale;
+  if (ox) *ox = m->ox;
+  if (oy) *oy = m->oy;
+  if (stride) *stride = m->stride;
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_map_upload(slamgpu_map *m, const double *cells, int32_t w, int32_t h, int32_t ox, int32_t oy) {
+  if (!m || !cells || w < 0 || h < 0) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  SG_TRY(sg_map_realloc(m, w, h));
+  m->ox = ox; m->oy = oy;
+  size_t bytes = (size_t)w * h * m->stride * sizeof(double);
+  SG_CUDA(ctx, cudaMemcpyAsync(m->d_cells, cells, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_map_download(slamgpu_map *m, double *cells) {
+  if (!m || !cells) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  size_t bytes = (size_t)m->w * m->h * m->stride * sizeof(double);
+  SG_CUDA(ctx, cudaMemcpyAsync(cells, m->d_cells, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_map_read_cell(slamgpu_map *m, int32_t x, int32_t y, double *rec) {
+  if (!m || !rec) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  int ix = x + m->ox, iy = y + m->oy;
+  if (ix < 0 || ix >= m->w || iy < 0 || iy >= m->h) {  // plain_grid_map.h:69-73: the unknown cell outside
+    memcpy(rec, m->unknown, sizeof(double) * m->stride);
+    return SLAMGPU_OK;
+  }
+  SG_CUDA(ctx, cudaMemcpyAsync(rec, m->d_cells + ((size_t)iy * m->w + ix) * m->stride, sizeof(double) * m->stride,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+
+// ------------------------------------------------------------------ score LUT
+__global__ void k_build_lut(const double *__restrict__ cells, int w, int h, int stride, int model, int oie,
+                            double *__restrict__ lut, int pitch, double unknown_value) {
+  int px = blockIdx.x * blockDim.x + threadIdx.x;  // padded coordinates
+  int py = blockIdx.y * blockDim.y + threadIdx.y;
+  if (px >= pitch || py >= h + 2 * SG_LUT_PAD) return;
+  int x = px - SG_LUT_PAD, y = py - SG_LUT_PAD;
+  double v = unknown_value;
+  if (x >= 0 && x < w && y >= 0 && y < h) {
+    double r[SLAMGPU_MAX_STRIDE];
+    const double *src = cells + ((size_t)y * w + x) * stride;
+    for (int k = 0; k < stride; ++k) r[k] = src[k];
+    v = sg::cell_impact(model, oie, r, 0.0, 0.0);
+  }
+  lut[(size_t)py * pitch + px] = v;
+}
+
+__global__ void k_unknown_impact(int model, int oie, RecParam rec, double *out) {
+  *out = sg::cell_impact(model, oie, rec.v, 0.0, 0.0);
+}
+
+int sg_map_ensure_lut(slamgpu_map *m, int oie) {
+  slamgpu_ctx *ctx = m->ctx;
+  if (oie < 0 || oie > 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oie %d", oie);
+  if (m->lut_valid[oie]) return SLAMGPU_OK;
+  size_t need = (size_t)m->pitch * (m->h + 2 * SG_LUT_PAD);
+  if (need > m->lut_cap[oie]) {
+    if (m->d_lut[oie]) cudaFree(m->d_lut[oie]);
+    m->d_lut[oie] = nullptr; m->lut_cap[oie] = 0;
+    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], need * sizeof(double)));
+    m->lut_cap[oie] = need;
+  }
+  // the unknown cell's impact, computed by the same device code as every other cell
+  double *d_tmp = nullptr;
+  SG_TRY(ctx->scratch[7].reserve(64));
+  d_tmp = ctx->scratch[7].as<double>();
+  RecParam rp;
+  memcpy(rp.v, m->unknown, sizeof rp.v);
+  k_unknown_impact<<<1, 1, 0, ctx->stream>>>(m->model, oie, rp, d_tmp);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaMemcpyAsync(&m->unknown_lut[oie], d_tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  dim3 blk(32, 8), grd((m->pitch + 31) / 32, (m->h + 2 * SG_LUT_PAD + 7) / 8);
+  k_build_lut<<<grd, blk, 0, ctx->stream>>>(m->d_cells, m->w, m->h, m->stride, m->model, oie, m->d_lut[oie], m->pitch,
+                                             m->unknown_lut[oie]);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  m->lut_valid[oie] = true;
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_map_lut_download(slamgpu_map *m, int32_t oie, double *lut, double *unknown_value) {
+  if (!m) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  SG_TRY(sg_map_ensure_lut(m, oie));
+  if (lut && m->w > 0 && m->h > 0)
+    SG_CUDA(ctx, cudaMemcpy2DAsync(lut, (size_t)m->w * sizeof(double),
+                                   m->d_lut[oie] + (size_t)SG_LUT_PAD * m->pitch + SG_LUT_PAD,
+                                   (size_t)m->pitch * sizeof(double), (size_t)m->w * sizeof(double), m->h,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (unknown_value) *unknown_value = m->unknown_lut[oie];
+  return SLAMGPU_OK;
+}
+
+// ------------------------------------------------------------------ scan
+extern "C" int slamgpu_scan_create(slamgpu_ctx *ctx, slamgpu_scan **out) {
+  if (!ctx || !out) return SLAMGPU_E_INVALID;
+  slamgpu_scan *s = new slamgpu_scan();
+  s->ctx = ctx;
+  *out = s;
+  return SLAMGPU_OK;
+}
+extern "C" void slamgpu_scan_destroy(slamgpu_scan *s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  if (s->ctx->cand.scan == s) { s->ctx->cand.scan = nullptr; s->ctx->cand.kind = -1; }
+  s->d.release();
+  delete s;
+}
+
+extern "C" int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian, const double *a, const double *b,
+                                   const uint8_t *occ, const double *factor, const double *weight) {
+  if (!s || n < 0 || (n > 0 && (!a || !b))) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = s->ctx;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  s->n = n; s->cartesian = cartesian; s->has_factor = factor != nullptr;
+  s->range.resize(n); s->angle.resize(n); s->x.resize(n); s->y.resize(n); s->weight.resize(n); s->factor.resize(n);
+  s->occ.resize(n);
+  // ScanPoint2D accessors, src/core/states/sensor_data.h:47-70: the representation that was
+  // not given is derived with libm on the host (bit-identical to the reference's own calls)
+  for (int i = 0; i < n; ++i) {
+    if (cartesian) {
+      s->x[i] = a[i]; s->y[i] = b[i];
+      s->range[i] = std::sqrt(a[i] * a[i] + b[i] * b[i]);
+      s->angle[i] = std::atan2(b[i], a[i]);
+    } else {
+      s->range[i] = a[i]; s->angle[i] = b[i];
+      s->x[i] = a[i] * std::cos(b[i]);
+      s->y[i] = a[i] * std::sin(b[i]);
+    }
+    s->weight[i] = weight ? weight[i] : 1.0 / n;
+    s->factor[i] = factor ? factor[i] : 1.0;
+    s->occ[i] = occ ? occ[i] : 1;
+  }
+  double ws = 0;
+  for (int i = 0; i < n; ++i) ws += s->weight[i];  // weighted_mean_point_probability_spe.h:125
+  s->wsum = ws;
+  size_t nn = std::max(n, 1);
+  size_t bytes = nn * 6 * sizeof(double) + nn;
+  if (s->d.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "scan buffer");
+  void *hp;
+  SG_TRY(sg_pinned(ctx, bytes, &hp));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging may still be in flight
+  double *h = (double *)hp;
+  memcpy(h + 0 * nn, s->range.data(), n * sizeof(double));
+  memcpy(h + 1 * nn, s->angle.data(), n * sizeof(double));
+  memcpy(h + 2 * nn, s->x.data(), n * sizeof(double));
+  memcpy(h + 3 * nn, s->y.data(), n * sizeof(double));
+  memcpy(h + 4 * nn, s->weight.data(), n * sizeof(double));
+  memcpy(h + 5 * nn, s->factor.data(), n * sizeof(double));
+  memcpy(h + 6 * nn, s->occ.data(), n);
+  double *d = s->d.as<double>();
+  s->d_range = d; s->d_angle = d + nn; s->d_x = d + 2 * nn; s->d_y = d + 3 * nn; s->d_w = d + 4 * nn; s->d_f = d + 5 * nn;
+  s->d_occ = (uint8_t *)(d + 6 * nn);
+  SG_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->cand.scan == s) ctx->cand.kind = -1;  // staged candidates depend on the scan
+  return SLAMGPU_OK;
+}

@@ -1,0 +1,187 @@
+// dev_math.cuh -- device-side arithmetic shared by the kernels.
+//
+// Everything here is IEEE double in the reference's operation order.  The library is
+// compiled with -fmad=false, and the parity-critical expressions additionally use the
+// explicit round-to-nearest intrinsics so no FMA contraction can ever be introduced.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/slamgpu.h"
+
+#define SG_DEV __device__ __forceinline__
+#define SG_HD __host__ __device__ __forceinline__
+
+namespace sg {
+
+SG_DEV double add(double a, double b) { return __dadd_rn(a, b); }
+SG_DEV double sub(double a, double b) { return __dsub_rn(a, b); }
+SG_DEV double mul(double a, double b) { return __dmul_rn(a, b); }
+SG_DEV double div(double a, double b) { return __ddiv_rn(a, b); }
+SG_DEV double maxd(double a, double b) { return (a < b) ? b : a; }  // std::max(a, b)
+SG_DEV double mind(double a, double b) { return (b < a) ? b : a; }  // std::min(a, b)
+
+// src/core/math_utils.h:10-51
+SG_DEV bool are_equal(double a, double b) {
+  double sc = maxd(1.0, maxd(fabs(a), fabs(b)));
+  return fabs(sub(a, b)) <= mul(1e-7, sc);
+}
+SG_DEV bool less(double a, double b) { return a < add(b, 2.220446049250313e-16); }
+SG_DEV bool less_or_equal(double a, double b) { return are_equal(a, b) || less(a, b); }
+SG_DEV bool are_ordered(double a, double b, double c) { return less_or_equal(a, b) && less_or_equal(b, c); }
+
+// RegularSquaresGrid::world_to_cell, src/core/maps/regular_squares_grid.h:40-46
+SG_DEV int world_to_cell(double v, double scale) { return (int)floor(div(v, scale)); }
+
+// world_to_cell plus the trig guard: `slack` is an upper bound of |v - v_reference|
+// when v was built from device trigonometry; returns true if the cell could differ.
+SG_DEV int world_to_cell_guard(double v, double scale, double slack, bool *unsafe) {
+  double q = div(v, scale);
+  double f = floor(q);
+  double lo = q - f;           // distance to the lower border, in cells
+  double hi = (f + 1.0) - q;   // distance to the upper border
+  double tol = slack / scale + 4.0 * 2.220446049250313e-16 * fabs(q);
+  *unsafe = (lo <= tol) || (hi <= tol);
+  f = f < -1e9 ? -1e9 : (f > 1e9 ? 1e9 : f);
+  return (int)f;
+}
+
+// ---------------------------------------------------------------- cell models
+SG_HD int model_stride(int model) {
+  switch (model) {
+    case SLAMGPU_CELL_LWW: return 3;
+    case SLAMGPU_CELL_AFFINE: return 2;
+    case SLAMGPU_CELL_MEAN: return 2;
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: return 6;
+    case SLAMGPU_CELL_GMAPPING: return 5;
+  }
+  return 0;
+}
+
+SG_DEV bool rec_is_unknown(int model, const double *r) {
+  switch (model) {
+    case SLAMGPU_CELL_LWW: return r[2] == 0;
+    case SLAMGPU_CELL_AFFINE: return r[1] == 0;
+    case SLAMGPU_CELL_MEAN: return r[1] == 0;
+    case SLAMGPU_CELL_GMAPPING: return r[4] == 0;
+    default: return r[5] == 0;
+  }
+}
+
+// TBM belief {unknown, empty, occupied, conflict}: src/core/maps/transferable_belief_model.h:63-143
+struct Tbm { double u, e, o, c; };
+SG_DEV Tbm tbm_conj(const Tbm &l, const Tbm &r) {
+  // t[i|j] += l[i]*r[j] over i, j in {0:u, 1:e, 2:o, 3:c}, accumulated in (i, j) order
+  double lb[4] = {l.u, l.e, l.o, l.c}, rb[4] = {r.u, r.e, r.o, r.c};
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[i | j] = add(t[i | j], mul(lb[i], rb[j]));
+  double tot = add(add(add(t[0], t[1]), t[2]), t[3]);
+  Tbm out;
+  if (tot == 0.0) { out.u = 1.0; out.e = out.o = out.c = 0.0; return out; }
+  out.u = div(t[0], tot); out.e = div(t[1], tot); out.o = div(t[2], tot); out.c = div(t[3], tot);
+  return out;
+}
+SG_DEV void tbm_norm_conflict(Tbm &t) {
+  double w = add(add(t.u, t.e), t.o);
+  if (w == 0.0) { t.u = 1.0; t.e = t.o = t.c = 0.0; return; }
+  t.u = div(t.u, w); t.e = div(t.e, w); t.o = div(t.o, w); t.c = 0.0;
+}
+// aoo2tbm, src/core/maps/tbm_grid_cells.h:57-66
+SG_DEV Tbm aoo2tbm(double p, double q, double quality) {
+  Tbm t;
+  if (isnan(p) || isnan(q)) { t.u = 1.0; t.e = t.o = t.c = 0.0; return t; }
+  double est = mul(q, quality);
+  double occupied = mul(p, est), empty = mul(sub(1.0, p), est);
+  t.u = sub(sub(1.0, occupied), empty); t.e = empty; t.o = occupied; t.c = 0.0;
+  return t;
+}
+
+// operator+= of each cell model: grid_cell.h:27-30, naive_grid_cells.h:14-20,33-40,
+// tbm_grid_cells.h:12-19,93-106, slams/gmapping/gmapping_grid_cell.h:20-33
+SG_DEV void cell_update(int model, double *r, double p, double q, double obx, double oby, double quality) {
+  bool valid = !isnan(p) && !isnan(q);
+  switch (model) {
+    case SLAMGPU_CELL_LWW: r[0] = p; r[1] = q; r[2] = 1; break;
+    case SLAMGPU_CELL_AFFINE:
+      if (!valid) return;
+      r[0] = add(mul(sub(1.0, quality), r[0]), mul(quality, p));
+      r[1] = 1;
+      break;
+    case SLAMGPU_CELL_MEAN: {
+      if (!valid) return;
+      r[1] = add(r[1], 1.0);
+      double that_p = add(0.5, mul(sub(p, 0.5), quality));
+      r[0] = div(add(mul(r[0], sub(r[1], 1.0)), that_p), r[1]);
+      break;
+    }
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: {
+      if (!valid) return;
+      Tbm b = {r[2], r[3], r[4], 0.0}, m = aoo2tbm(p, q, quality);
+      b = tbm_conj(b, m);
+      tbm_norm_conflict(b);
+      r[2] = b.u; r[3] = b.e; r[4] = b.o;
+      if (model == SLAMGPU_CELL_TBM_CONSISTENT) {
+        double qual = add(b.o, b.e);
+        r[0] = div(b.o, qual); r[1] = qual;
+      } else {
+        r[0] = add(b.o, mul(0.5, b.u)); r[1] = 1.0;
+      }
+      r[5] = 1;
+      break;
+    }
+    case SLAMGPU_CELL_GMAPPING: {
+      if (!valid) return;
+      r[4] = add(r[4], 1.0);  // tries
+      bool free_ = p <= 0.5;
+      double aoo_p = free_ ? 0.0 : p;
+      r[0] = div(add(mul(r[0], sub(r[4], 1.0)), aoo_p), r[4]);
+      if (free_) return;
+      r[3] = add(r[3], 1.0);  // hits
+      r[1] = div(add(mul(r[1], sub(r[3], 1.0)), obx), r[3]);
+      r[2] = div(add(mul(r[2], sub(r[3], 1.0)), oby), r[3]);
+      break;
+    }
+  }
+}
+
+// discrepancy against the obstacle AOO {true, {1, 1}, obst, 1}:
+// grid_cell.h:33-35, tbm_grid_cells.h:21-35, gmapping_grid_cell.h:35-38
+SG_DEV double cell_discrepancy_obstacle(int model, const double *r, double obx, double oby) {
+  switch (model) {
+    case SLAMGPU_CELL_LWW:
+    case SLAMGPU_CELL_AFFINE:
+    case SLAMGPU_CELL_MEAN: return fabs(sub(r[0], 1.0));
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: {
+      Tbm that = aoo2tbm(1.0, 1.0, 1.0), b = {r[2], r[3], r[4], 0.0};
+      double total_unknown = add(that.u, b.u);
+      double d_occ = fabs(sub(that.o, b.o));
+      Tbm comb = tbm_conj(that, b);
+      double unknown = div(total_unknown, 2.0);
+      double known = sub(1.0, unknown);
+      double known_disc = div(mul(known, add(comb.c, d_occ)), 2.0);
+      return add(div(unknown, 2.0), known_disc);
+    }
+    case SLAMGPU_CELL_GMAPPING: {
+      double dx = sub(r[1], obx), dy = sub(r[2], oby);
+      double d = add(mul(dx, dx), mul(dy, dy));
+      double sim = exp(div(-d, 0.05));
+      return sub(1.0, sim);
+    }
+  }
+  return 0;
+}
+
+// observation_impact_estimators.h:14-28
+SG_DEV double cell_impact(int model, int oie, const double *r, double obx, double oby) {
+  if (oie == SLAMGPU_OIE_OCCUPANCY) return r[0];
+  return sub(1.0, cell_discrepancy_obstacle(model, r, obx, oby));
+}
+
+}  // namespace sg

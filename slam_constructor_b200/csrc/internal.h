@@ -1,0 +1,132 @@
+// internal.h -- host-side structures of libslamgpu.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/slamgpu.h"
+
+#define SG_LUT_PAD 1  // ring of "unknown" cells around the padded score LUT
+
+struct DevBuf {  // grow-only device scratch buffer
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+  template <class T> T *as() const { return (T *)p; }
+};
+
+struct NcclApi;  // nccl_dyn.cc
+
+struct Candidates {  // a staged candidate set (device resident)
+  int kind = -1;     // 0 list, 1 grid
+  int64_t P = 0;     // global candidate count
+  int64_t p0 = 0, p1 = 0;  // this rank's slice [p0, p1)
+  slamgpu_spe_params spe{};
+  slamgpu_scan *scan = nullptr;
+  // list
+  DevBuf poses;      // 3*Ploc doubles (slice only)
+  DevBuf theta_id;   // int32 per local pose
+  int32_t T = 0;     // distinct thetas
+  std::vector<double> h_thetas;  // distinct theta values (host)
+  DevBuf d_thetas;
+  // grid
+  int32_t nx = 0, ny = 0, nt = 0, nyp = 0;
+  std::vector<double> h_xs, h_ys, h_ts;
+  DevBuf d_xs, d_ys;
+  DevBuf groups;     // int32 {t, k0, cnt, pad} per row group of this rank
+  int32_t n_groups = 0, rows_per_group = 0;
+  int32_t t_lo = 0, t_hi = 0;  // theta planes touched by this rank
+  DevBuf cxp, cyp;   // int32 index tables
+  // trig tables (device), layout given by strides
+  DevBuf trc, trs;
+  bool trig_is_host = false;
+  // results
+  DevBuf scores;     // Ploc doubles
+  DevBuf blk_best;   // per block {double score; int64 idx}
+  DevBuf result;     // {double score; int64 idx; int64 guard}
+  bool launched = false;
+  slamgpu_map *last_map = nullptr;  // map of the last launch (a guard-triggered redo needs it)
+  double init_score = 0;
+  int64_t stats[8] = {0};
+};
+
+struct slamgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // around the dominant kernel of the last call
+  bool evk_valid = false;
+  int rank = 0, nranks = 1;
+  void *comm = nullptr;  // ncclComm_t
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+  Candidates cand;
+  DevBuf flush;      // L2 flush target
+  DevBuf gather;     // all-gather staging: nranks * 16 B
+  void *h_pinned = nullptr;  // small pinned staging (results)
+  size_t h_pinned_cap = 0;
+  DevBuf scratch[8];  // generic scratch (append_scan etc.)
+};
+
+struct slamgpu_map {
+  slamgpu_ctx *ctx = nullptr;
+  int32_t w = 0, h = 0, ox = 0, oy = 0;
+  double scale = 1;
+  int32_t model = 0, stride = 0, grow = 0;
+  double unknown[SLAMGPU_MAX_STRIDE] = {0};
+  double *d_cells = nullptr;  // h*w*stride
+  size_t cells_cap = 0;       // doubles
+  // padded score LUT per OIE: (h + 2*PAD) rows of `pitch` doubles
+  double *d_lut[2] = {nullptr, nullptr};
+  size_t lut_cap[2] = {0, 0};
+  bool lut_valid[2] = {false, false};
+  int32_t pitch = 0;
+  double unknown_lut[2] = {0, 0};
+  struct slamgpu_pyramid *pyr = nullptr;  // owning pyramid if this is its level 0
+};
+
+struct slamgpu_scan {
+  slamgpu_ctx *ctx = nullptr;
+  int32_t n = 0, cartesian = 0;
+  bool has_factor = false;
+  // host copies (libm-derived fields are computed on the host so they are bit-identical
+  // to the reference's: range/angle of Cartesian points, x/y of polar points)
+  std::vector<double> range, angle, x, y, weight, factor;
+  std::vector<uint8_t> occ;
+  double wsum = 0;  // sequential sum of weights (pose independent)
+  // device: one block of 6*n doubles + n bytes
+  DevBuf d;
+  double *d_range = nullptr, *d_angle = nullptr, *d_x = nullptr, *d_y = nullptr, *d_w = nullptr, *d_f = nullptr;
+  uint8_t *d_occ = nullptr;
+};
+
+// ---- error plumbing ----
+int sg_fail(slamgpu_ctx *ctx, int code, const char *fmt, ...);
+void sg_set_global_error(const char *msg);
+#define SG_CUDA(ctx, call)                                                                             \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return sg_fail(ctx, SLAMGPU_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+#define SG_TRY(call)             \
+  do {                           \
+    int r__ = (call);            \
+    if (r__ != SLAMGPU_OK) return r__; \
+  } while (0)
+#define SG_LAUNCHED(ctx) (++(ctx)->launches)
+
+int sg_pinned(slamgpu_ctx *ctx, size_t bytes, void **out);
+int sg_map_ensure_lut(slamgpu_map *m, int oie);
+void sg_map_invalidate_lut(slamgpu_map *m);
+int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h);
+int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv);
+
+// NCCL through dlopen (nccl_dyn.cc)
+int sg_nccl_unique_id(void *id128, std::string *err);
+int sg_nccl_init(int nranks, int rank, const void *id128, void **comm, std::string *err);
+int sg_nccl_allgather(void *comm, const void *send, void *recv, size_t bytes, cudaStream_t s, std::string *err);
+void sg_nccl_destroy(void *comm);

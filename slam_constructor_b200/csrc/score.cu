@@ -1,0 +1,759 @@
+// score.cu -- K1: batched likelihood of one laser scan under many candidate poses.
+//
+// Replaces the candidate loop of PoseEnumerationScanMatcher::process_scan
+// (src/core/scan_matchers/pose_enumeration_scan_matcher.h:48-65) around
+// WeightedMeanPointProbabilitySPE::estimate_scan_probability
+// (src/core/scan_matchers/weighted_mean_point_probability_spe.h:97-133).
+//
+// Two kernels:
+//   k_score_list  any pose list: one thread per pose walks the scan points in index order
+//                 (the reference's FP64 summation order), beam trig comes from a per-theta
+//                 table built once per candidate set;
+//   k_score_grid  the Cartesian candidate set of BruteForcePoseEnumerator
+//                 (brute_force_scan_matcher.h:10-64): cell indices are separable in
+//                 (theta, beam, x) and (theta, beam, y), so they are precomputed into two
+//                 small integer tables and the inner loop is gather + multiply + add.
+// Both end in a warp-shuffle arg-max whose tie-break is the lowest candidate index, which
+// is what the reference's sequential strict-'<' accept loop selects.
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <unordered_map>
+
+#include "dev_math.cuh"
+#include "internal.h"
+
+namespace {
+
+struct MapView {
+  const double *lut;    // padded score LUT (pitch doubles per row, ring of unknown)
+  const double *cells;  // dense records (GMapping OOPE gathers these)
+  int w, h, ox, oy, pitch, stride, model;
+  double scale;
+  double unknown_lut;
+  double unknown_rec[SLAMGPU_MAX_STRIDE];
+};
+
+struct Best {
+  double score;
+  long long idx;
+};
+struct Result {
+  double score;
+  long long idx;
+  long long guard;
+  long long pad;
+};
+
+// a beats b in the reference's accept loop: strictly larger, or equal with a lower index
+SG_DEV bool beats(double s, long long i, double bs, long long bi) { return (s > bs) || (s == bs && i < bi); }
+
+SG_DEV void warp_argmax(double &s, long long &i) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double os = __shfl_down_sync(0xffffffffu, s, off);
+    long long oi = __shfl_down_sync(0xffffffffu, i, off);
+    if (beats(os, oi, s, i)) { s = os; i = oi; }
+  }
+}
+
+// block arg-max -> *dst (written by thread 0); every thread of the block must call
+SG_DEV void block_argmax(double s, long long i, Best *dst) {
+  __shared__ double sh_s[32];
+  __shared__ long long sh_i[32];
+  warp_argmax(s, i);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { sh_s[wid] = s; sh_i[wid] = i; }
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < nw ? sh_s[lane] : -INFINITY;
+    i = lane < nw ? sh_i[lane] : LLONG_MAX;
+    warp_argmax(s, i);
+    if (lane == 0) { dst->score = s; dst->idx = i; }
+  }
+}
+
+__global__ void k_reduce_blocks(const Best *__restrict__ blk, int n, Result *out) {
+  double s = -INFINITY;
+  long long i = LLONG_MAX;
+  for (int k = threadIdx.x; k < n; k += blockDim.x)  // ascending k per thread keeps the lowest index on ties
+    if (beats(blk[k].score, blk[k].idx, s, i)) { s = blk[k].score; i = blk[k].idx; }
+  block_argmax(s, i, reinterpret_cast<Best *>(out));  // Result starts with {score, idx}
+}
+
+// merge the per-rank results (after the all-gather) and apply the accept rule against
+// init_score: the winner must be strictly better than the initial pose's score
+__global__ void k_finalize(const Result *__restrict__ per_rank, int nranks, double init_score, Result *out) {
+  double s = -INFINITY;
+  long long i = LLONG_MAX, guard = 0;
+  for (int r = 0; r < nranks; ++r) {
+    guard += per_rank[r].guard;
+    if (beats(per_rank[r].score, per_rank[r].idx, s, i)) { s = per_rank[r].score; i = per_rank[r].idx; }
+  }
+  if (!(init_score < s) || i == LLONG_MAX) { s = init_score; i = -1; }
+  out->score = s; out->idx = i; out->guard = guard; out->pad = 0;
+}
+
+// ------------------------------------------------------------------ trig table
+// ScanPoint2D::move_origin + RawTrigonometryProvider: src/core/states/sensor_data.h:83-87,
+// src/core/trigonometry_utils.h:21-27 -- r*cos(theta + a), r*sin(theta + a)
+__global__ void k_trig_table(const double *__restrict__ thetas, int T, const double *__restrict__ range,
+                             const double *__restrict__ angle, int N, long long st_t, long long st_i,
+                             double *__restrict__ trc, double *__restrict__ trs) {
+  long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (id >= (long long)T * N) return;
+  int t = (int)(id / N), i = (int)(id - (long long)t * N);
+  double s, c;
+  sincos(sg::add(thetas[t], angle[i]), &s, &c);
+  long long o = t * st_t + i * st_i;
+  trc[o] = sg::mul(range[i], c);
+  trs[o] = sg::mul(range[i], s);
+}
+
+// slack of a world coordinate built from device trig (see slamgpu.h, SLAMGPU_TRIG_DEVICE)
+SG_DEV double trig_slack(double rc, double X) { return 4e-15 * fabs(rc) + 1e-15 * fabs(X); }
+
+SG_DEV int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+SG_DEV int cell_of(double q_floor) {  // floor(q) -> int without overflow
+  q_floor = q_floor < -1e9 ? -1e9 : (q_floor > 1e9 ? 1e9 : q_floor);
+  return (int)q_floor;
+}
+
+SG_DEV double lut_at(const MapView &m, int cx, int cy) {  // external cell -> impact (unknown outside)
+  int ix = clampi(cx + m.ox, -1, m.w) + SG_LUT_PAD, iy = clampi(cy + m.oy, -1, m.h) + SG_LUT_PAD;
+  return __ldg(m.lut + (size_t)iy * m.pitch + ix);
+}
+
+// ---- window OOPEs: occupancy_observation_probability.h:29-99 over GridRasterizedRectangle
+// (src/core/maps/grid_rasterization.h:26-64) and LightWeightRectangle::overlap
+// (src/core/geometry_primitives.h:252-318)
+struct Lwr { double b, t, l, r; };
+SG_DEV bool lwr_contains(const Lwr &a, double x, double y) { return sg::are_ordered(a.l, x, a.r) && sg::are_ordered(a.b, y, a.t); }
+SG_DEV double lwr_area(const Lwr &a) { return sg::mul(sg::sub(a.t, a.b), sg::sub(a.r, a.l)); }
+SG_DEV Lwr lwr_intersect(const Lwr &a0, const Lwr &b0) {
+  for (int pass = 0; pass < 2; ++pass) {
+    const Lwr &a = pass ? b0 : a0;
+    const Lwr &that = pass ? a0 : b0;
+    unsigned nm = 0;
+    double cl = a.l, cr = a.r, ct = a.t, cb = a.b;
+    if (lwr_contains(a, that.l, that.b)) { ++nm; cl = that.l; cb = that.b; }
+    if (lwr_contains(a, that.r, that.b)) { ++nm; cr = that.r; cb = that.b; }
+    if (lwr_contains(a, that.l, that.t)) { ++nm; cl = that.l; ct = that.t; }
+    if (lwr_contains(a, that.r, that.t)) { ++nm; cr = that.r; ct = that.t; }
+    if (nm) return Lwr{cb, ct, cl, cr};
+  }
+  return Lwr{0, 0, 0, 0};
+}
+SG_DEV double lwr_overlap(const Lwr &a, const Lwr &b) {
+  if (lwr_area(a) != 0) {
+    Lwr i = lwr_intersect(a, b);
+    return sg::div(lwr_area(i), lwr_area(a));
+  }
+  if (lwr_area(b) != 0) return lwr_contains(b, a.l, a.b) ? 1.0 : 0.0;
+  return (sg::are_equal(a.t, b.t) && sg::are_equal(a.b, b.b) && sg::are_equal(a.l, b.l) && sg::are_equal(a.r, b.r)) ? 1.0 : 0.0;
+}
+
+template <int MODE>
+SG_DEV double window_probability(const MapView &m, double X, double Y, double win_v, double win_h) {
+  const double s = m.scale;
+  double half_v = sg::div(win_v, 2.0), half_h = sg::div(win_h, 2.0);
+  Lwr win{sg::sub(Y, half_v), sg::add(Y, half_v), sg::sub(X, half_h), sg::add(X, half_h)};
+  double area = lwr_area(win);
+  int lx, ly, rx, ry;
+  if (area == INFINITY) {
+    lx = -m.ox; ly = -m.oy; rx = m.w - 1 - m.ox; ry = m.h - 1 - m.oy;
+  } else if (area == 0) {
+    lx = rx = cell_of(floor(sg::div(win.l, s)));
+    ly = ry = cell_of(floor(sg::div(win.b, s)));
+  } else {
+    lx = cell_of(floor(sg::div(win.l, s))); ly = cell_of(floor(sg::div(win.b, s)));
+    rx = cell_of(floor(sg::div(win.r, s))); ry = cell_of(floor(sg::div(win.t, s)));
+  }
+  double acc = 0, wsum = 0;
+  unsigned nm = 0;
+  for (int x = lx; x <= rx; ++x)
+    for (int y = ly; y <= ry; ++y) {
+      double impact = lut_at(m, x, y);
+      if (MODE == SLAMGPU_OOPE_MAX) {
+        acc = sg::maxd(impact, acc);
+      } else if (MODE == SLAMGPU_OOPE_MEAN) {
+        acc = sg::add(acc, impact); nm += 1;
+      } else {
+        Lwr cell;  // world_cell_bounds, regular_squares_grid.h:108-118
+        if (s == INFINITY) cell = Lwr{-INFINITY, INFINITY, -INFINITY, INFINITY};
+        else cell = Lwr{sg::mul(s, (double)y), sg::mul(s, (double)(y + 1)), sg::mul(s, (double)x), sg::mul(s, (double)(x + 1))};
+        double wgt = lwr_overlap(win, cell);
+        acc = sg::add(acc, sg::mul(impact, wgt));
+        wsum = sg::add(wsum, wgt);
+      }
+    }
+  if (MODE == SLAMGPU_OOPE_MAX) return acc;
+  if (MODE == SLAMGPU_OOPE_MEAN) return nm ? sg::div(acc, (double)nm) : 0.5;
+  return wsum != 0 ? sg::div(acc, wsum) : 0.5;
+}
+
+// GmappingOccupancyObservationPE::probability, src/slams/gmapping/gmapping_occupancy_observation_pe.h:17-38
+SG_DEV double gmapping_probability(const MapView &m, int cx, int cy, double X, double Y, double th, int win) {
+  double best = 0;
+  for (int dx = -win; dx <= win; ++dx)
+    for (int dy = -win; dy <= win; ++dy) {
+      int ix = cx + dx + m.ox, iy = cy + dy + m.oy;
+      double r[SLAMGPU_MAX_STRIDE];
+      if (ix < 0 || ix >= m.w || iy < 0 || iy >= m.h) {
+#pragma unroll
+        for (int k = 0; k < SLAMGPU_MAX_STRIDE; ++k) r[k] = m.unknown_rec[k];
+      } else {
+        const double *src = m.cells + ((size_t)iy * m.w + ix) * m.stride;
+        for (int k = 0; k < m.stride; ++k) r[k] = __ldg(src + k);
+      }
+      if (r[0] < th) continue;
+      double v = sg::sub(1.0, sg::cell_discrepancy_obstacle(m.model, r, X, Y));
+      best = sg::maxd(best, v);
+    }
+  return best;
+}
+
+struct ListArgs {
+  MapView map;
+  const double *poses;      // 3*Ploc
+  const int *theta_id;      // Ploc (table column), unused when prerotated
+  const double *trc, *trs;  // [i*T + tid]
+  int T;
+  const double *sx, *sy, *w, *f;
+  int N;
+  long long Ploc, p0;  // local count, global index of local pose 0
+  double wsum, win_v, win_h, gm_th;
+  int gm_win, gm_cache;
+  double *scores;  // Ploc
+  Best *blk;
+  Result *result;  // guard counter lives here
+};
+
+template <int MODE, bool PREROT, bool GUARD, bool FACTOR>
+__global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  if (p < a.Ploc) {
+    const double px = a.poses[3 * p], py = a.poses[3 * p + 1];
+    const int tid = PREROT ? 0 : a.theta_id[p];
+    const double s = a.map.scale;
+    double total_probability = 0;
+    bool unsafe_any = false;
+    int cache_x = 0, cache_y = 0;
+    double cache_p = -1;
+    for (int i = 0; i < a.N; ++i) {
+      double X, Y, rc = 0, rs = 0;
+      if (PREROT) {  // sensor_data.h:103-105 -- point + pose offset
+        X = sg::add(__ldg(a.sx + i), px); Y = sg::add(__ldg(a.sy + i), py);
+      } else {
+        rc = __ldg(a.trc + (size_t)i * a.T + tid); rs = __ldg(a.trs + (size_t)i * a.T + tid);
+        X = sg::add(px, rc); Y = sg::add(py, rs);
+      }
+      double prob;
+      if (MODE == SLAMGPU_OOPE_OBSTACLE || MODE == SLAMGPU_OOPE_GMAPPING) {
+        int cx, cy;
+        if (GUARD) {
+          bool u1, u2;
+          cx = sg::world_to_cell_guard(X, s, trig_slack(rc, X), &u1);
+          cy = sg::world_to_cell_guard(Y, s, trig_slack(rs, Y), &u2);
+          unsafe_any |= u1 | u2;
+        } else {
+          cx = cell_of(floor(sg::div(X, s))); cy = cell_of(floor(sg::div(Y, s)));
+        }
+        if (MODE == SLAMGPU_OOPE_OBSTACLE) {
+          prob = lut_at(a.map, cx, cy);
+        } else {
+          if (a.gm_cache && cx == cache_x && cy == cache_y && cache_p != -1) {
+            prob = cache_p;
+          } else {
+            prob = gmapping_probability(a.map, cx, cy, X, Y, a.gm_th, a.gm_win);
+            cache_x = cx; cache_y = cy; cache_p = prob;
+          }
+        }
+      } else {
+        if (GUARD) {  // window corners depend on X, Y too: guard the four borders
+          double hv = sg::div(a.win_v, 2.0), hh = sg::div(a.win_h, 2.0);
+          bool u;
+          sg::world_to_cell_guard(sg::sub(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+          sg::world_to_cell_guard(sg::add(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+          sg::world_to_cell_guard(sg::sub(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+          sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+        }
+        prob = window_probability<MODE>(a.map, X, Y, a.win_v, a.win_h);
+      }
+      double term = sg::mul(prob, __ldg(a.w + i));
+      if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+      total_probability = sg::add(total_probability, term);
+    }
+    double score = a.wsum == 0 ? NAN : sg::div(total_probability, a.wsum);
+    a.scores[p] = score;
+    if (GUARD && unsafe_any) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
+    if (score == score) { best_s = score; best_i = a.p0 + p; }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+// ------------------------------------------------------------------ grid (brute force) path
+struct GridIdxArgs {
+  const double *trc, *trs;  // [t*N + i]
+  const double *xs, *ys;
+  int nx, ny, nyp, N, t_lo, nt_loc;
+  int w, h, ox, oy, pitch;
+  double scale;
+  int guard;
+  int *cxp;  // [(tl*N + i)*nx + j]   padded LUT column
+  int *cyp;  // [(tl*N + i)*nyp + k]  padded LUT row * pitch
+  Result *result;
+};
+
+// one thread per (theta, beam, axis value): the exact world_to_cell of the reference,
+// regular_squares_grid.h:40-46, applied to x_j + r*cos(theta+a) and y_k + r*sin(theta+a)
+__global__ void k_grid_indices(GridIdxArgs a) {
+  const int per = a.nx + a.nyp;
+  long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)a.nt_loc * a.N * per;
+  if (id >= total) return;
+  long long ti = id / per;  // tl*N + i
+  int c = (int)(id - ti * per);
+  int tl = (int)(ti / a.N), i = (int)(ti - (long long)tl * a.N);
+  long long src = (long long)(a.t_lo + tl) * a.N + i;
+  bool unsafe = false;
+  if (c < a.nx) {
+    double rc = a.trc[src];
+    double X = sg::add(a.xs[c], rc);
+    int cx = a.guard ? sg::world_to_cell_guard(X, a.scale, trig_slack(rc, X), &unsafe) : cell_of(floor(sg::div(X, a.scale)));
+    a.cxp[ti * a.nx + c] = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
+  } else {
+    int k = c - a.nx;
+    int out = 0;  // padding rows point at the ring row 0 (always valid memory)
+    if (k < a.ny) {
+      double rs = a.trs[src];
+      double Y = sg::add(a.ys[k], rs);
+      int cy = a.guard ? sg::world_to_cell_guard(Y, a.scale, trig_slack(rs, Y), &unsafe) : cell_of(floor(sg::div(Y, a.scale)));
+      out = (clampi(cy + a.oy, -1, a.h) + SG_LUT_PAD) * a.pitch;
+    }
+    a.cyp[ti * a.nyp + k] = out;
+  }
+  if (unsafe) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
+}
+
+struct GridArgs {
+  const double *lut;
+  const int *cxp, *cyp;
+  const int4 *groups;  // {t, k0, m_lo, m_hi}: rows k0+m for m in [m_lo, m_hi) belong to this rank
+  int n_groups, nx, ny, nyp, N, t_lo;
+  const double *w, *f;
+  double wsum;
+  long long p0;
+  double *scores;  // local slice
+  Best *blk;
+};
+
+#define SG_GRID_R 8
+
+template <bool FACTOR>
+__global__ void __launch_bounds__(128) k_score_grid(GridArgs a) {
+  long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int g = (int)(q0 / a.nx);
+  int j = (int)(q0 - (long long)g * a.nx);
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  if (g < a.n_groups) {
+    const int4 grp = __ldg(a.groups + g);
+    const int tl = grp.x - a.t_lo;
+    const int *pcx = a.cxp + (size_t)tl * a.N * a.nx + j;
+    const int4 *pcy = reinterpret_cast<const int4 *>(a.cyp + (size_t)tl * a.N * a.nyp + grp.y);
+    const int cy_step = a.nyp / 4;
+    double acc[SG_GRID_R];
+#pragma unroll
+    for (int m = 0; m < SG_GRID_R; ++m) acc[m] = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < a.N; ++i) {
+      const int cx = __ldg(pcx);
+      const int4 r0 = __ldg(pcy), r1 = __ldg(pcy + 1);
+      const double wi = __ldg(a.w + i);
+      const double fi = FACTOR ? __ldg(a.f + i) : 1.0;
+      const int row[SG_GRID_R] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      double v[SG_GRID_R];
+#pragma unroll
+      for (int m = 0; m < SG_GRID_R; ++m) v[m] = __ldg(a.lut + (row[m] + cx));
+#pragma unroll
+      for (int m = 0; m < SG_GRID_R; ++m) {
+        double term = sg::mul(v[m], wi);
+        if (FACTOR) term = sg::mul(term, fi);
+        acc[m] = sg::add(acc[m], term);
+      }
+      pcx += a.nx;
+      pcy += cy_step;
+    }
+#pragma unroll
+    for (int m = 0; m < SG_GRID_R; ++m) {
+      if (m < grp.z || m >= grp.w) continue;
+      double score = a.wsum == 0 ? NAN : sg::div(acc[m], a.wsum);
+      long long idx = ((long long)grp.x * a.ny + (grp.y + m)) * a.nx + j;
+      a.scores[idx - a.p0] = score;
+      if (score == score && beats(score, idx, best_s, best_i)) { best_s = score; best_i = idx; }
+    }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+// ------------------------------------------------------------------ host side
+void slice_of(const slamgpu_ctx *ctx, int64_t P, int64_t *p0, int64_t *p1) {
+  *p0 = (int64_t)((__int128)P * ctx->rank / ctx->nranks);
+  *p1 = (int64_t)((__int128)P * (ctx->rank + 1) / ctx->nranks);
+}
+
+MapView make_view(const slamgpu_map *m, int oie) {
+  MapView v;
+  v.lut = m->d_lut[oie]; v.cells = m->d_cells;
+  v.w = m->w; v.h = m->h; v.ox = m->ox; v.oy = m->oy; v.pitch = m->pitch; v.stride = m->stride; v.model = m->model;
+  v.scale = m->scale; v.unknown_lut = m->unknown_lut[oie];
+  memcpy(v.unknown_rec, m->unknown, sizeof v.unknown_rec);
+  return v;
+}
+
+int check_spe(slamgpu_ctx *ctx, const slamgpu_scan *scan, const slamgpu_spe_params *p) {
+  if (!scan || !p) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan/params is NULL");
+  if (scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan belongs to another ctx");
+  if (p->oope < 0 || p->oope > SLAMGPU_OOPE_GMAPPING) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oope %d", p->oope);
+  if (p->oie < 0 || p->oie > 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oie %d", p->oie);
+  if (p->trig_mode != SLAMGPU_TRIG_DEVICE && p->trig_mode != SLAMGPU_TRIG_HOST)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "bad trig_mode %d", p->trig_mode);
+  if (p->oope == SLAMGPU_OOPE_GMAPPING && (p->gm_window < 0 || p->gm_window > 8))
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "bad gm_window %d", p->gm_window);
+  return SLAMGPU_OK;
+}
+
+// host trig table with libm: bit-identical to the reference's std::cos/std::sin calls
+void host_trig(const slamgpu_scan *s, const std::vector<double> &thetas, int64_t st_t, int64_t st_i,
+               std::vector<double> &rc, std::vector<double> &rs) {
+  const int N = s->n;
+  const size_t T = thetas.size();
+  rc.resize(T * N); rs.resize(T * N);
+  for (size_t t = 0; t < T; ++t)
+    for (int i = 0; i < N; ++i) {
+      double ang = thetas[t] + s->angle[i];
+      rc[t * st_t + i * st_i] = s->range[i] * std::cos(ang);
+      rs[t * st_t + i * st_i] = s->range[i] * std::sin(ang);
+    }
+}
+
+int upload(slamgpu_ctx *ctx, DevBuf &dst, const void *src, size_t bytes) {
+  if (dst.reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "device buffer of %zu bytes", bytes);
+  if (bytes) SG_CUDA(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return SLAMGPU_OK;
+}
+
+int upload_host_trig(slamgpu_ctx *ctx, Candidates &c, const std::vector<double> &thetas, int64_t st_t, int64_t st_i) {
+  std::vector<double> rc, rs;
+  host_trig(c.scan, thetas, st_t, st_i, rc, rs);
+  SG_TRY(upload(ctx, c.trc, rc.data(), rc.size() * sizeof(double)));
+  SG_TRY(upload(ctx, c.trs, rs.data(), rs.size() * sizeof(double)));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rc/rs are stack-lifetime host vectors
+  c.trig_is_host = true;
+  return SLAMGPU_OK;
+}
+
+#define SG_LIST_MAX_TABLE_BYTES (1ull << 30)
+
+}  // namespace
+
+extern "C" int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *poses,
+                                   int64_t P) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  SG_TRY(check_spe(ctx, scan, p));
+  if (P < 0 || (P > 0 && !poses)) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad pose list");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  Candidates &c = ctx->cand;
+  c.kind = -1; c.launched = false;
+  c.P = P; c.spe = *p; c.scan = scan;
+  slice_of(ctx, P, &c.p0, &c.p1);
+  const int64_t Ploc = c.p1 - c.p0;
+  const int N = scan->n;
+  SG_TRY(upload(ctx, c.poses, poses + 3 * c.p0, (size_t)Ploc * 3 * sizeof(double)));
+  c.h_thetas.clear();
+  std::vector<int32_t> tid((size_t)Ploc);
+  if (!p->prerotated) {
+    // distinct thetas of this slice (bit patterns), in order of first appearance
+    std::unordered_map<uint64_t, int32_t> seen;
+    seen.reserve((size_t)std::min<int64_t>(Ploc, 1 << 16));
+    for (int64_t k = 0; k < Ploc; ++k) {
+      double th = poses[3 * (c.p0 + k) + 2];
+      uint64_t bits;
+      memcpy(&bits, &th, 8);
+      auto it = seen.find(bits);
+      if (it == seen.end()) {
+        it = seen.emplace(bits, (int32_t)c.h_thetas.size()).first;
+        c.h_thetas.push_back(th);
+      }
+      tid[k] = it->second;
+    }
+    if ((unsigned long long)c.h_thetas.size() * std::max(N, 1) * 16ull > SG_LIST_MAX_TABLE_BYTES)
+      return sg_fail(ctx, SLAMGPU_E_NOMEM, "%zu distinct thetas x %d points exceed the trig table budget; split the call",
+                     c.h_thetas.size(), N);
+  }
+  c.T = (int32_t)c.h_thetas.size();
+  SG_TRY(upload(ctx, c.theta_id, tid.data(), tid.size() * sizeof(int32_t)));
+  SG_TRY(upload(ctx, c.d_thetas, c.h_thetas.data(), c.h_thetas.size() * sizeof(double)));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tid is a local
+  size_t tb = std::max<size_t>((size_t)c.T * N, 1) * sizeof(double);
+  if (c.trc.reserve(tb) != SLAMGPU_OK || c.trs.reserve(tb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trig table");
+  c.trig_is_host = false;
+  if (!p->prerotated && p->trig_mode == SLAMGPU_TRIG_HOST && c.T > 0) SG_TRY(upload_host_trig(ctx, c, c.h_thetas, 1, c.T));
+  int nblk = (int)((Ploc + 127) / 128);
+  if (c.scores.reserve(std::max<size_t>(Ploc, 1) * sizeof(double)) != SLAMGPU_OK ||
+      c.blk_best.reserve(std::max(nblk, 1) * sizeof(Best)) != SLAMGPU_OK ||
+      c.result.reserve(sizeof(Result) * 2) != SLAMGPU_OK ||
+      ctx->gather.reserve(sizeof(Result) * std::max(ctx->nranks, 1)) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "score buffers");
+  c.kind = 0;
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *xs,
+                                  int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  SG_TRY(check_spe(ctx, scan, p));
+  if (nx <= 0 || ny <= 0 || nt <= 0 || !xs || !ys || !thetas) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad grid axes");
+  if (p->oope != SLAMGPU_OOPE_OBSTACLE || p->prerotated)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "slamgpu_stage_grid: only the obstacle OOPE on polar scans has a tiled kernel; "
+                                           "expand the grid and use slamgpu_stage_poses");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  Candidates &c = ctx->cand;
+  c.kind = -1; c.launched = false;
+  c.spe = *p; c.scan = scan;
+  c.nx = nx; c.ny = ny; c.nt = nt; c.nyp = (ny + SG_GRID_R - 1) / SG_GRID_R * SG_GRID_R;
+  c.P = (int64_t)nt * ny * nx;
+  c.h_xs.assign(xs, xs + nx); c.h_ys.assign(ys, ys + ny); c.h_ts.assign(thetas, thetas + nt);
+  // shard by rows (theta, y): contiguous candidate index ranges, whole rows per rank
+  const int64_t rows = (int64_t)nt * ny;
+  int64_t r0, r1;
+  slice_of(ctx, rows, &r0, &r1);
+  c.p0 = r0 * nx; c.p1 = r1 * nx;
+  std::vector<int32_t> groups;
+  c.t_lo = (int32_t)(r0 / ny);
+  c.t_hi = r1 > r0 ? (int32_t)((r1 - 1) / ny) : c.t_lo;
+  for (int32_t t = c.t_lo; t <= c.t_hi && r1 > r0; ++t) {
+    int64_t ka = std::max<int64_t>(r0 - (int64_t)t * ny, 0), kb = std::min<int64_t>(r1 - (int64_t)t * ny, ny);
+    for (int32_t k0 = (int32_t)(ka / SG_GRID_R * SG_GRID_R); k0 < kb; k0 += SG_GRID_R) {
+      int32_t lo = (int32_t)std::max<int64_t>(ka - k0, 0), hi = (int32_t)std::min<int64_t>(kb - k0, SG_GRID_R);
+      groups.push_back(t); groups.push_back(k0); groups.push_back(lo); groups.push_back(hi);
+    }
+  }
+  c.n_groups = (int32_t)(groups.size() / 4);
+  c.rows_per_group = SG_GRID_R;
+  const int N = scan->n;
+  const int nt_loc = c.t_hi - c.t_lo + 1;
+  SG_TRY(upload(ctx, c.groups, groups.data(), groups.size() * sizeof(int32_t)));
+  SG_TRY(upload(ctx, c.d_xs, c.h_xs.data(), nx * sizeof(double)));
+  SG_TRY(upload(ctx, c.d_ys, c.h_ys.data(), ny * sizeof(double)));
+  SG_TRY(upload(ctx, c.d_thetas, c.h_ts.data(), nt * sizeof(double)));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  size_t tb = std::max<size_t>((size_t)nt * N, 1) * sizeof(double);
+  if (c.trc.reserve(tb) != SLAMGPU_OK || c.trs.reserve(tb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trig table");
+  c.trig_is_host = false;
+  if (p->trig_mode == SLAMGPU_TRIG_HOST) SG_TRY(upload_host_trig(ctx, c, c.h_ts, N, 1));
+  const int64_t Ploc = c.p1 - c.p0;
+  long long threads = (long long)c.n_groups * nx;
+  int nblk = (int)((threads + 127) / 128);
+  if (c.cxp.reserve(std::max<size_t>((size_t)nt_loc * N * nx, 1) * sizeof(int)) != SLAMGPU_OK ||
+      c.cyp.reserve(std::max<size_t>((size_t)nt_loc * N * c.nyp, 1) * sizeof(int)) != SLAMGPU_OK ||
+      c.scores.reserve(std::max<size_t>(Ploc, 1) * sizeof(double)) != SLAMGPU_OK ||
+      c.blk_best.reserve(std::max(nblk, 1) * sizeof(Best)) != SLAMGPU_OK ||
+      c.result.reserve(sizeof(Result) * 2) != SLAMGPU_OK ||
+      ctx->gather.reserve(sizeof(Result) * std::max(ctx->nranks, 1)) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "grid score buffers");
+  c.kind = 1;
+  return SLAMGPU_OK;
+}
+
+namespace {
+
+template <int MODE, bool PREROT, bool GUARD>
+void launch_list_f(slamgpu_ctx *ctx, const ListArgs &a, int nblk, bool factor) {
+  if (factor) k_score_list<MODE, PREROT, GUARD, true><<<nblk, 128, 0, ctx->stream>>>(a);
+  else k_score_list<MODE, PREROT, GUARD, false><<<nblk, 128, 0, ctx->stream>>>(a);
+}
+template <int MODE>
+void launch_list_m(slamgpu_ctx *ctx, const ListArgs &a, int nblk, bool prerot, bool guard, bool factor) {
+  if (prerot) launch_list_f<MODE, true, false>(ctx, a, nblk, factor);
+  else if (guard) launch_list_f<MODE, false, true>(ctx, a, nblk, factor);
+  else launch_list_f<MODE, false, false>(ctx, a, nblk, factor);
+}
+
+int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
+  Candidates &c = ctx->cand;
+  if (c.kind < 0 || !c.scan) return sg_fail(ctx, SLAMGPU_E_STATE, "no staged candidate set (stage_* first; re-stage after a scan upload)");
+  if (!map || map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map is NULL or belongs to another ctx");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const slamgpu_scan *s = c.scan;
+  const int N = s->n;
+  const int oie = c.spe.oie;
+  if (c.spe.oope != SLAMGPU_OOPE_GMAPPING) SG_TRY(sg_map_ensure_lut(map, oie));
+  Result *res = c.result.as<Result>();
+  SG_CUDA(ctx, cudaMemsetAsync(res, 0, sizeof(Result) * 2, ctx->stream));
+  const int64_t Ploc = c.p1 - c.p0;
+  const bool device_trig = !c.trig_is_host && !c.spe.prerotated;
+  int nblk = 0;
+  memset(c.stats, 0, sizeof c.stats);
+  c.stats[1] = c.kind; c.stats[2] = Ploc * N; c.stats[3] = c.p0; c.stats[4] = Ploc;
+  if (c.kind == 0) {
+    if (device_trig && c.T > 0 && N > 0) {
+      long long tot = (long long)c.T * N;
+      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.d_thetas.as<double>(), c.T, s->d_range, s->d_angle,
+                                                                            N, 1, c.T, c.trc.as<double>(), c.trs.as<double>());
+      SG_LAUNCHED(ctx);
+    }
+    nblk = (int)((Ploc + 127) / 128);
+    if (nblk > 0) {
+      ListArgs a;
+      a.map = make_view(map, oie);
+      a.poses = c.poses.as<double>(); a.theta_id = c.theta_id.as<int>();
+      a.trc = c.trc.as<double>(); a.trs = c.trs.as<double>(); a.T = c.T;
+      a.sx = s->d_x; a.sy = s->d_y; a.w = s->d_w; a.f = s->d_f; a.N = N;
+      a.Ploc = Ploc; a.p0 = c.p0; a.wsum = s->wsum; a.win_v = c.spe.win_v; a.win_h = c.spe.win_h;
+      a.gm_th = c.spe.gm_fullness_th; a.gm_win = c.spe.gm_window; a.gm_cache = c.spe.reserved;
+      a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>(); a.result = res;
+      const bool pre = c.spe.prerotated != 0, fac = s->has_factor;
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      switch (c.spe.oope) {
+        case SLAMGPU_OOPE_OBSTACLE: launch_list_m<SLAMGPU_OOPE_OBSTACLE>(ctx, a, nblk, pre, device_trig, fac); break;
+        case SLAMGPU_OOPE_MAX: launch_list_m<SLAMGPU_OOPE_MAX>(ctx, a, nblk, pre, device_trig, fac); break;
+        case SLAMGPU_OOPE_MEAN: launch_list_m<SLAMGPU_OOPE_MEAN>(ctx, a, nblk, pre, device_trig, fac); break;
+        case SLAMGPU_OOPE_OVERLAP: launch_list_m<SLAMGPU_OOPE_OVERLAP>(ctx, a, nblk, pre, device_trig, fac); break;
+        default: launch_list_m<SLAMGPU_OOPE_GMAPPING>(ctx, a, nblk, pre, device_trig, fac); break;
+      }
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->evk_valid = true;
+      SG_LAUNCHED(ctx);
+    }
+  } else {
+    const int nt_loc = c.t_hi - c.t_lo + 1;
+    if (device_trig && N > 0) {
+      long long tot = (long long)c.nt * N;
+      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.d_thetas.as<double>(), c.nt, s->d_range, s->d_angle,
+                                                                            N, N, 1, c.trc.as<double>(), c.trs.as<double>());
+      SG_LAUNCHED(ctx);
+    }
+    long long threads = (long long)c.n_groups * c.nx;
+    nblk = (int)((threads + 127) / 128);
+    if (nblk > 0 && N > 0) {
+      GridIdxArgs ia;
+      ia.trc = c.trc.as<double>(); ia.trs = c.trs.as<double>(); ia.xs = c.d_xs.as<double>(); ia.ys = c.d_ys.as<double>();
+      ia.nx = c.nx; ia.ny = c.ny; ia.nyp = c.nyp; ia.N = N; ia.t_lo = c.t_lo; ia.nt_loc = nt_loc;
+      ia.w = map->w; ia.h = map->h; ia.ox = map->ox; ia.oy = map->oy; ia.pitch = map->pitch; ia.scale = map->scale;
+      ia.guard = device_trig ? 1 : 0;
+      ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
+      long long tot = (long long)nt_loc * N * (c.nx + c.nyp);
+      k_grid_indices<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ia);
+      SG_LAUNCHED(ctx);
+    }
+    if (nblk > 0) {
+      GridArgs a;
+      a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<int>(); a.cyp = c.cyp.as<int>(); a.groups = c.groups.as<int4>();
+      a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.nyp = c.nyp; a.N = N; a.t_lo = c.t_lo;
+      a.w = s->d_w; a.f = s->d_f; a.wsum = s->wsum; a.p0 = c.p0;
+      a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>();
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      if (s->has_factor) k_score_grid<true><<<nblk, 128, 0, ctx->stream>>>(a);
+      else k_score_grid<false><<<nblk, 128, 0, ctx->stream>>>(a);
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->evk_valid = true;
+      SG_LAUNCHED(ctx);
+    }
+  }
+  SG_CUDA(ctx, cudaGetLastError());
+  // per-rank best -> res[1] (keeps the guard counter accumulated in res[0].guard)
+  Result *local = res + 1;
+  if (nblk > 0) {
+    k_reduce_blocks<<<1, 1024, 0, ctx->stream>>>(c.blk_best.as<Best>(), nblk, res);
+    SG_LAUNCHED(ctx);
+  } else {
+    Result empty{-INFINITY, LLONG_MAX, 0, 0};
+    SG_CUDA(ctx, cudaMemcpyAsync(res, &empty, sizeof(Result), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const Result *per_rank = res;
+  if (ctx->nranks > 1) {
+    std::string err;
+    int r = sg_nccl_allgather(ctx->comm, res, ctx->gather.p, sizeof(Result), ctx->stream, &err);
+    if (r != SLAMGPU_OK) return sg_fail(ctx, r, "%s", err.c_str());
+    per_rank = ctx->gather.as<Result>();
+  }
+  k_finalize<<<1, 1, 0, ctx->stream>>>(per_rank, ctx->nranks, init_score, local);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  c.launched = true;
+  c.init_score = init_score;
+  c.last_map = map;
+  return SLAMGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int slamgpu_score_launch(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  return launch_staged(ctx, map, init_score);
+}
+
+static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, int64_t *best_idx, double *best_score) {
+  Candidates &c = ctx->cand;
+  if (!c.launched) return sg_fail(ctx, SLAMGPU_E_STATE, "slamgpu_score_fetch without a launch");
+  void *hp;
+  SG_TRY(sg_pinned(ctx, sizeof(Result), &hp));
+  Result *h = (Result *)hp;
+  SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h->guard > 0 && !c.trig_is_host && map) {
+    // some world point sits within the guard band of a cell border: redo with libm trig so the
+    // cell indices are the reference's by construction (every rank sees the same summed counter)
+    int64_t hits = h->guard;
+    if (c.kind == 0) SG_TRY(upload_host_trig(ctx, c, c.h_thetas, 1, c.T));
+    else SG_TRY(upload_host_trig(ctx, c, c.h_ts, c.scan->n, 1));
+    SG_TRY(launch_staged(ctx, map, c.init_score));
+    c.stats[0] = hits;
+    SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    c.trig_is_host = c.spe.trig_mode == SLAMGPU_TRIG_HOST;  // next launch of a DEVICE set uses device trig again
+  }
+  if (best_idx) *best_idx = h->idx;
+  if (best_score) *best_score = h->score;
+  if (out_scores && c.p1 > c.p0) {
+    SG_CUDA(ctx, cudaMemcpyAsync(out_scores + c.p0, c.scores.p, (size_t)(c.p1 - c.p0) * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_score_fetch(slamgpu_ctx *ctx, double *out_scores, int64_t *best_idx, double *best_score) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  return fetch_impl(ctx, ctx->cand.last_map, out_scores, best_idx, best_score);
+}
+
+extern "C" int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]) {
+  if (!ctx || !stats) return SLAMGPU_E_INVALID;
+  memcpy(stats, ctx->cand.stats, sizeof ctx->cand.stats);
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_score_poses(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                                   const double *poses, int64_t P, double init_score, double *out_scores, int64_t *best_idx,
+                                   double *best_score) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  SG_TRY(slamgpu_stage_poses(ctx, scan, p, poses, P));
+  SG_TRY(launch_staged(ctx, map, init_score));
+  return fetch_impl(ctx, map, out_scores, best_idx, best_score);
+}
+
+extern "C" int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                                  const double *xs, int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt,
+                                  double init_score, double *out_scores, int64_t *best_idx, double *best_score) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  SG_TRY(slamgpu_stage_grid(ctx, scan, p, xs, nx, ys, ny, thetas, nt));
+  SG_TRY(launch_staged(ctx, map, init_score));
+  return fetch_impl(ctx, map, out_scores, best_idx, best_score);
+}

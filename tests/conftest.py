@@ -25,3 +25,18 @@ def refso(oracle):
     # pin the function-static Shift_Amount of the reference's area estimator (quirk Q10)
     oracle.ref.ref_init_area_shift(0.01, 0.05)
     return oracle.ref
+
+
+@pytest.fixture(scope="session")
+def sg():
+    """the product package (ctypes over lib/libslamgpu.so); no fallback if it is missing"""
+    import slam_constructor_b200 as pkg
+    pkg.lib()
+    return pkg
+
+
+@pytest.fixture(scope="session")
+def gpu(sg):
+    ctx = sg.Context(0)
+    yield ctx
+    ctx.close()

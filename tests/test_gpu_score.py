@@ -1,0 +1,223 @@
+"""K1 parity on the GPU: libslamgpu.so (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): selected candidate index bit-exact; per-pose scores within
+1e-5 relative.  The kernels are written to be bit-exact for every mode built only from
++ - * / (obstacle, max, mean, overlap), so those are asserted with array_equal; the GMapping
+mode goes through exp() and is asserted at rtol 1e-5 (RTOL below).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import random_cells, room_map_cells, room_scan
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _setup(sg, gpu, rng, model, n_pts, size=200, scale=0.05, passes=3, spw=ob.SPW_EVEN, factor=False, fov=270):
+    cells = room_map_cells(rng, size, size, scale, model, passes=passes)
+    om = ob.OracleMap(size, size, scale, model, ob.GROW_NONE)
+    om.set_cells(cells)
+    gm = sg.GridMap(gpu, size, size, scale, model)
+    gm.upload(cells)
+    pose0 = np.array([0.2, -0.1, 0.3])
+    r, a = room_scan(rng, n_pts, np.deg2rad(fov), pose=pose0, noise=0.01)
+    w = np.empty(n_pts)
+    ob.orc.orc_point_weights(spw, n_pts, ob.dptr(ob.f64(r)), ob.dptr(ob.f64(a)), ob.dptr(w))
+    f = rng.uniform(0.5, 1.5, n_pts) if factor else None
+    osc = ob.OracleScan(r, a, weight=w, factor=f)
+    gsc = sg.Scan(gpu, r, a, weight=w, factor=f)
+    return om, gm, osc, gsc, pose0
+
+
+def _argbest(scores, init):
+    best = C.c_double()
+    idx = ob.orc.orc_argbest(ob.dptr(ob.f64(scores)), len(scores), init, C.byref(best))
+    return idx, best.value
+
+
+@pytest.mark.parametrize("model,oie", [(ob.CELL_LWW, 0), (ob.CELL_MEAN, 0), (ob.CELL_TBM_CONSISTENT, 0),
+                                       (ob.CELL_TBM_UNKNOWN_EVEN, 1), (ob.CELL_AFFINE, 1)])
+@pytest.mark.parametrize("trig", [0, 1])
+def test_list_obstacle_bit_exact(sg, gpu, model, oie, trig):
+    rng = np.random.default_rng(1000 + model * 3 + trig)
+    om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, model, 181, spw=[ob.SPW_EVEN, ob.SPW_VINY, ob.SPW_AHR][model % 3],
+                                  factor=(model == ob.CELL_MEAN))
+    poses = p0 + rng.normal(0, [0.2, 0.2, 0.1], (700, 3))
+    poses[::50] += [30.0, -30.0, 0.0]  # far outside the map: unknown cells
+    want = om.score(osc, ob.spe_params(ob.OOPE_OBSTACLE, oie), poses)
+    init = float(np.sort(want)[len(want) // 2])
+    got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(sg.OOPE_OBSTACLE, oie, trig=trig), poses, init_score=init)
+    lut, unk = gm.lut(oie)
+    olut, ounk = om.lut(oie)
+    assert np.array_equal(lut, olut) and unk == ounk
+    assert np.array_equal(got, want)
+    assert (idx, best) == _argbest(want, init)
+    gm.close(); gsc.close()
+
+
+@pytest.mark.parametrize("oope", [ob.OOPE_MAX, ob.OOPE_MEAN, ob.OOPE_OVERLAP])
+def test_list_window_modes_bit_exact(sg, gpu, oope):
+    rng = np.random.default_rng(1100 + oope)
+    om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_MEAN, 90, fov=240)
+    poses = p0 + rng.normal(0, [0.2, 0.2, 0.1], (130, 3))
+    for win in ((0.1, 0.1), (0.05, 0.2), (0.0, 0.0), (0.3, 0.0)):
+        want = om.score(osc, ob.spe_params(oope, 0, win_v=win[0], win_h=win[1]), poses)
+        for trig in (0, 1):
+            got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(oope, 0, win_v=win[0], win_h=win[1], trig=trig), poses)
+            assert np.array_equal(got, want), (win, trig)
+            assert (idx, best) == _argbest(want, -np.inf)
+    gm.close(); gsc.close()
+
+
+def test_list_prerotated_cartesian(sg, gpu):
+    rng = np.random.default_rng(1200)
+    om, gm, _, _, p0 = _setup(sg, gpu, rng, ob.CELL_MEAN, 50)
+    r, a = room_scan(rng, 150, np.deg2rad(270), pose=p0)
+    x, y = r * np.cos(a + p0[2]), r * np.sin(a + p0[2])
+    osc = ob.OracleScan(x, y, cartesian=True)
+    gsc = sg.Scan(gpu, x, y, cartesian=True)
+    poses = p0 + rng.normal(0, [0.3, 0.3, 0.0], (257, 3))
+    for oope, win in ((ob.OOPE_OBSTACLE, (0, 0)), (ob.OOPE_MAX, (0.2, 0.1))):
+        want = om.score(osc, ob.spe_params(oope, 0, win_v=win[0], win_h=win[1], prerotated=1), poses)
+        got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(oope, 0, win_v=win[0], win_h=win[1], prerotated=1), poses)
+        assert np.array_equal(got, want)
+        assert (idx, best) == _argbest(want, -np.inf)
+    # a Cartesian scan scored NOT pre-rotated goes through range/angle (sensor_data.h:47-70)
+    want = om.score(osc, ob.spe_params(ob.OOPE_OBSTACLE, 0), poses)
+    got, _, _ = gpu.score_poses(gm, gsc, sg.spe_params(sg.OOPE_OBSTACLE, 0, trig=sg.TRIG_HOST), poses)
+    assert np.array_equal(got, want)
+    gm.close(); gsc.close()
+
+
+def test_list_gmapping_oope(sg, gpu):
+    rng = np.random.default_rng(1300)
+    cells = room_map_cells(rng, 200, 200, 0.05, ob.CELL_GMAPPING, passes=4)
+    om = ob.OracleMap(200, 200, 0.05, ob.CELL_GMAPPING)
+    om.set_cells(cells)
+    gm = sg.GridMap(gpu, 200, 200, 0.05, sg.CELL_GMAPPING)
+    gm.upload(cells)
+    r, a = room_scan(rng, 360, 2 * np.pi, pose=(0.1, 0.1, 0.0), noise=0.005)
+    osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+    poses = np.array([0.1, 0.1, 0.0]) + rng.normal(0, [0.05, 0.05, 0.02], (300, 3))
+    want = om.score(osc, ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1), poses)
+    got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1), poses)
+    assert (want > 0).sum() > 250
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    # the reference's 1-entry cell cache (quirk Q7), restarted per pose
+    want_c = np.array([om.score(osc, ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1), p[None],
+                                cache=ob.GmCache(0, 0, -1.0))[0] for p in poses[:60]])
+    got_c, _, _ = gpu.score_poses(gm, gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=1), poses[:60])
+    np.testing.assert_allclose(got_c, want_c, rtol=RTOL, atol=0)
+    gm.close(); gsc.close()
+
+
+def _bf_axes(base, args):
+    xs, ys, ts = np.empty(4096), np.empty(4096), np.empty(4096)
+    nx, ny, nt = C.c_int32(), C.c_int32(), C.c_int32()
+    n = ob.orc.orc_bf_enumerate(*base, *args, None, 0, ob.dptr(xs), nx, ob.dptr(ys), ny, ob.dptr(ts), nt)
+    P = np.empty((n, 3))
+    ob.orc.orc_bf_enumerate(*base, *args, ob.dptr(P), n, None, None, None, None, None, None)
+    return xs[:nx.value].copy(), ys[:ny.value].copy(), ts[:nt.value].copy(), P
+
+
+@pytest.mark.parametrize("trig", [0, 1])
+@pytest.mark.parametrize("model,factor", [(ob.CELL_MEAN, False), (ob.CELL_TBM_CONSISTENT, True)])
+def test_grid_matches_oracle_and_list(sg, gpu, trig, model, factor):
+    rng = np.random.default_rng(1400 + trig + model)
+    om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, model, 121, factor=factor, spw=ob.SPW_VINY)
+    base = p0 + np.array([0.07, -0.04, 0.02])
+    xs, ys, ts, P = _bf_axes(base, (-0.5, 0.5, 0.05, -0.3, 0.3, 0.05, -0.1, 0.1, 0.02))
+    assert len(P) == len(xs) * len(ys) * len(ts) and len(ys) % 8 != 0
+    want = om.score(osc, ob.spe_params(), P)
+    init = om.score(osc, ob.spe_params(), base[None])[0]
+    got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(trig=trig), xs, ys, ts, init_score=init)
+    assert np.array_equal(got, want)
+    assert (idx, best) == _argbest(want, init)
+    got2, idx2, best2 = gpu.score_poses(gm, gsc, sg.spe_params(trig=trig), P, init_score=init)
+    assert np.array_equal(got2, want) and (idx2, best2) == (idx, best)
+    st = gpu.score_stats()
+    assert st["variant"] == 0 and st["evals"] == len(P) * 121
+    gm.close(); gsc.close()
+
+
+def test_argmax_ties_and_accept_rule(sg, gpu):
+    """constant map: every candidate ties -> the lowest index wins, and only if it beats init_score"""
+    cells = np.zeros((50, 50, 2))
+    cells[..., 0] = 0.7; cells[..., 1] = 3
+    gm = sg.GridMap(gpu, 50, 50, 0.1, sg.CELL_MEAN)
+    gm.upload(cells)
+    r = np.full(40, 1.0); a = np.linspace(-1, 1, 40)
+    gsc = sg.Scan(gpu, r, a)
+    xs = np.linspace(-0.5, 0.5, 33); ys = np.linspace(-0.5, 0.5, 19); ts = np.linspace(-0.2, 0.2, 5)
+    got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts, init_score=0.1)
+    assert len(set(got.tolist())) == 1 and idx == 0 and best == got[0]
+    _, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts, init_score=got[0])  # ties never accepted
+    assert idx == -1 and best == got[0]
+    # one better cell row makes a unique maximum somewhere in the middle; duplicates of it tie -> first wins
+    P = np.zeros((1000, 3)); P[:, 0] = np.linspace(-0.4, 0.4, 1000)
+    P[600:] = P[:400]
+    got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(), P, init_score=-1.0)
+    assert idx == 0
+    gm.close(); gsc.close()
+
+
+def test_empty_and_degenerate_inputs(sg, gpu):
+    gm = sg.GridMap(gpu, 20, 20, 0.1, sg.CELL_LWW)
+    gsc = sg.Scan(gpu, np.array([1.0, 2.0]), np.array([0.0, 0.5]))
+    got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(), np.zeros((0, 3)), init_score=0.25)
+    assert len(got) == 0 and idx == -1 and best == 0.25
+    # an empty scan has zero total weight: the reference returns NaN (unknown probability), never accepted
+    empty = sg.Scan(gpu, np.zeros(0), np.zeros(0))
+    got, idx, best = gpu.score_poses(gm, empty, sg.spe_params(), np.zeros((5, 3)), init_score=0.25)
+    assert np.isnan(got).all() and idx == -1 and best == 0.25
+    # all-unknown map: every point reads the prototype
+    got, idx, _ = gpu.score_poses(gm, gsc, sg.spe_params(), np.array([[0.0, 0.0, 0.0], [100.0, 5.0, 1.0]]))
+    assert got[0] == got[1] == 0.5 and idx == 0
+    with pytest.raises(sg.SlamGpuError):
+        gpu.score_grid(gm, gsc, sg.spe_params(sg.OOPE_MAX), [0.0], [0.0], [0.0])
+    gm.close(); gsc.close(); empty.close()
+
+
+def test_guard_forces_host_trig_on_cell_borders(sg, gpu):
+    """scan points that land exactly on cell borders must trip the device-trig guard and still be exact"""
+    rng = np.random.default_rng(1500)
+    cells = random_cells(rng, 80, 80, ob.CELL_MEAN, known_frac=1.0)
+    om = ob.OracleMap(80, 80, 0.1, ob.CELL_MEAN); om.set_cells(cells)
+    gm = sg.GridMap(gpu, 80, 80, 0.1, sg.CELL_MEAN); gm.upload(cells)
+    r = np.array([1.0, 2.0, 0.5, 1.5]); a = np.array([0.0, np.pi / 2, np.pi, 0.0])  # axis-aligned beams
+    osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+    poses = np.array([[0.1 * k, 0.1 * (k % 7), 0.0] for k in range(-20, 20)])  # multiples of the cell size
+    want = om.score(osc, ob.spe_params(), poses)
+    got, idx, best = gpu.score_poses(gm, gsc, sg.spe_params(trig=sg.TRIG_DEVICE), poses)
+    assert gpu.score_stats()["guard_hits"] > 0
+    assert np.array_equal(got, want) and (idx, best) == _argbest(want, -np.inf)
+    gm.close(); gsc.close()
+
+
+def test_full_size_bruteforce_properties(sg, gpu):
+    """BASELINE config 3 shape (2000x2000 grid, 1081 beams, 101x101x100 candidates): sampled scores against
+    the oracle, the arg-max against numpy over all GPU scores, and list-vs-grid agreement on a slice."""
+    rng = np.random.default_rng(1600)
+    size, scale, n = 2000, 0.05, 1081
+    cells = room_map_cells(rng, size, size, scale, ob.CELL_MEAN, half_w=30.0, half_h=22.0, passes=2)
+    om = ob.OracleMap(size, size, scale, ob.CELL_MEAN); om.set_cells(cells)
+    gm = sg.GridMap(gpu, size, size, scale, sg.CELL_MEAN); gm.upload(cells)
+    p0 = np.array([1.3, -2.1, 0.4])
+    r, a = room_scan(rng, n, np.deg2rad(270), half_w=30.0, half_h=22.0, pose=p0, noise=0.01)
+    osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+    xs, ys, ts, P = _bf_axes(p0 + [0.04, -0.03, 0.01], (-1, 1, 0.02, -1, 1, 0.02, -0.5, 0.5, 0.01))
+    assert (len(xs), len(ys), len(ts)) == (101, 101, 100)
+    got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+    assert not np.isnan(got).any()
+    assert idx == int(np.argmax(got)) and best == got[idx]  # np.argmax returns the first maximum
+    pick = rng.choice(len(P), 3000, replace=False)
+    want = om.score(osc, ob.spe_params(), P[pick])
+    assert np.array_equal(got[pick], want)
+    sl = slice(400000, 420000)
+    got_l, _, _ = gpu.score_poses(gm, gsc, sg.spe_params(), P[sl])
+    assert np.array_equal(got_l, got[sl])
+    gm.close(); gsc.close()
