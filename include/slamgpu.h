@@ -218,6 +218,16 @@ int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]);
 int slamgpu_raycast(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
                     int64_t *out_offsets /* n+1 */, int32_t *out_cells /* 2*cap */, int64_t cap, int64_t *total);
 
+/* the same for explicit world segments {bx, by, ex, ey} on a grid of cell size `scale`: the unit
+ * interface world_to_cells(Segment2D) itself (the reference's golden vectors are stated on it) */
+int slamgpu_raycast_segments(slamgpu_ctx *ctx, double scale, const double *segments /* 4*n */, int32_t n,
+                             int64_t *out_offsets /* n+1 */, int32_t *out_cells /* 2*cap */, int64_t cap, int64_t *total);
+/* batched CellOccupancyEstimator::estimate_occupancy(beam, cell_bounds, is_occupied) -> Occupancy
+ * (src/core/maps/cell_occupancy_estimator.h:13-15): beams {bx, by, ex, ey}, cell_bounds
+ * {bot, top, left, right}; out_pq {prob, quality}, (NaN, NaN) = Occupancy::invalid() */
+int slamgpu_estimate_occupancy(slamgpu_ctx *ctx, const slamgpu_estimator *est, int32_t n, const double *beams /* 4*n */,
+                               const double *cell_bounds /* 4*n */, const uint8_t *is_occ /* n */, double *out_pq /* 2*n */);
+
 /* ------------------------------------------------------------------ K2+K3: scan insertion
  * replaces GridMapScanAdder::append_scan + WallDistanceBlurringScanAdder::handle_scan_point
  * (src/core/maps/grid_map_scan_adders.h:54-75, 138-189), the const/area occupancy estimators

@@ -94,6 +94,8 @@ def _load_orc():
     L = C.CDLL(ORC_SO)
     L.orc_map_create.restype = C.c_void_p
     L.orc_map_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_dp]
+    L.orc_default_unknown.argtypes = [C.c_int, c_dp]
+    L.orc_default_unknown.restype = None
     L.orc_map_clone.restype = C.c_void_p
     L.orc_map_clone.argtypes = [C.c_void_p]
     L.orc_map_destroy.argtypes = [C.c_void_p]

@@ -65,7 +65,7 @@ SYMBOLS = [
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_scan_create",
     "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_stage_poses",
-    "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast",
+    "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
     "slamgpu_pyramid_append_scan", "slamgpu_score_windows",
@@ -125,6 +125,8 @@ def lib():
     L.slamgpu_score_stats.argtypes = [vp, c_lp]
     L.slamgpu_raycast.argtypes = [vp, vp, vp, c_dp, c_lp, c_ip, i64, c_lp]
     ep = C.POINTER(Estimator)
+    L.slamgpu_raycast_segments.argtypes = [vp, dbl, c_dp, i32, c_lp, c_ip, i64, c_lp]
+    L.slamgpu_estimate_occupancy.argtypes = [vp, ep, i32, c_dp, c_dp, c_u8p, c_dp]
     L.slamgpu_append_scan.argtypes = [vp, vp, vp, c_dp, dbl, i32, ep, dbl, dbl, c_dp, c_lp]
     L.slamgpu_pyramid_create.argtypes = [vp, vp, i32, pvp]
     L.slamgpu_pyramid_destroy.argtypes = [vp]
@@ -263,6 +265,26 @@ class Context:
         self.check(self.L.slamgpu_raycast(self.h, gmap.h, scan.h, _dp(pose), offs.ctypes.data_as(c_lp),
                                           cells.ctypes.data_as(c_ip), total.value, C.byref(total)))
         return offs, cells[:total.value]
+
+    def raycast_segments(self, scale, segments):
+        seg = _f64(segments).reshape(-1, 4)
+        n = len(seg)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        total = C.c_int64()
+        self.check(self.L.slamgpu_raycast_segments(self.h, scale, _dp(seg), n, offs.ctypes.data_as(c_lp), None, 0,
+                                                   C.byref(total)))
+        cells = np.zeros((max(total.value, 1), 2), dtype=np.int32)
+        self.check(self.L.slamgpu_raycast_segments(self.h, scale, _dp(seg), n, offs.ctypes.data_as(c_lp),
+                                                   cells.ctypes.data_as(c_ip), total.value, C.byref(total)))
+        return offs, cells[:total.value]
+
+    def estimate_occupancy(self, est, beams, bounds, is_occ):
+        beams, bounds = _f64(beams).reshape(-1, 4), _f64(bounds).reshape(-1, 4)
+        occ = np.ascontiguousarray(is_occ, dtype=np.uint8)
+        out = np.zeros((len(beams), 2))
+        self.check(self.L.slamgpu_estimate_occupancy(self.h, C.byref(est), len(beams), _dp(beams), _dp(bounds),
+                                                     occ.ctypes.data_as(c_u8p), _dp(out)))
+        return out
 
     def append_scan(self, gmap, scan, pose, quality=1.0, margin=0, est=None, blur=0.0, max_range=np.inf,
                     point_quality=None):

@@ -1,7 +1,744 @@
-// placeholder until K2/K3 land (same session): keeps every ABI symbol exported
-#include "internal.h"
-#define NOTYET(ctx) sg_fail(ctx, SLAMGPU_E_STATE, "%s: not implemented yet", __func__)
-extern "C" int slamgpu_map_reset_cell(slamgpu_map *m, int32_t, int32_t, const double *) { return NOTYET(m ? m->ctx : nullptr); }
-extern "C" int slamgpu_map_update_cell(slamgpu_map *m, int32_t, int32_t, int32_t, double, double, double, double, double) { return NOTYET(m ? m->ctx : nullptr); }
-extern "C" int slamgpu_raycast(slamgpu_ctx *ctx, slamgpu_map *, slamgpu_scan *, const double *, int64_t *, int32_t *, int64_t, int64_t *) { return NOTYET(ctx); }
-extern "C" int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *, slamgpu_scan *, const double *, double, int32_t, const slamgpu_estimator *, double, double, const double *, int64_t *) { return NOTYET(ctx); }
+// mapping.cu -- K2 (ray casting) and K3 (occupancy estimation + ordered cell update).
+//
+// Replaces GridMapScanAdder::append_scan + WallDistanceBlurringScanAdder::handle_scan_point
+// (src/core/maps/grid_map_scan_adders.h:54-75, 138-189), RegularSquaresGrid::world_to_cells
+// (src/core/maps/regular_squares_grid.h:56-101), the const / area occupancy estimators and the
+// cell models' operator+=.
+//
+// Pipeline of one scan insertion (all on the ctx stream, one host sync at the end):
+//   host   per-beam record: end point (libm trig, bit-identical to the reference), range gate,
+//          blur radius, slot offsets from the |dx|+|dy|+1 upper bound of each beam's cell count
+//   K2     k_raycast       one thread per beam walks its cells in the reference's order into the
+//                          beam's slot range and estimates the obstacle (last) cell
+//   K3a    k_estimate      one thread per (beam, cell) slot: occupancy estimate + wall blur -> AOO,
+//                          sort key = internal cell index
+//   sort   k_radix_*       stable LSD radix sort of (cell, slot): slots are generated in beam order,
+//                          so every cell's run comes out in the reference's update order
+//   K3b    k_apply         one thread per run walks it sequentially through the cell model's +=
+// The reference updates cells beam by beam (obstacle cell first, then along the beam); a cell
+// appears at most once per beam, so per-cell order == beam order, which the stable sort keeps.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "dev_geometry.cuh"
+#include "mapping.h"
+
+namespace {
+
+#define SG_INVALID_KEY 0xFFFFFFFFu
+
+// ---------------------------------------------------------------- K2
+struct RaycastArgs {
+  const BeamRec *beams;
+  const long long *offsets;  // slot offset of each beam (exclusive prefix of the upper bounds)
+  int N;
+  double px, py, scale;
+  slamgpu_estimator est;
+  double shift_amount;
+  int2 *cells;      // per slot
+  BeamOut *out;     // per beam
+};
+
+__global__ void k_raycast(RaycastArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  const BeamRec b = a.beams[i];
+  BeamOut o;
+  o.count = 0; o.base_p = 0; o.base_q = 0; o.lx = o.ly = 0;
+  if (b.active) {
+    int2 *dst = a.cells + a.offsets[i];
+    int lx = 0, ly = 0;
+    o.count = sg::raycast(a.px, a.py, b.wx, b.wy, a.scale, [&](int k, int x, int y) {
+      dst[k] = make_int2(x, y);
+      lx = x; ly = y;
+    });
+    o.lx = lx; o.ly = ly;
+    // the obstacle cell is estimated (and, in the reference, updated) first: grid_map_scan_adders.h:151-154
+    const double s = a.scale;
+    sg::estimate_occupancy(a.est, a.shift_amount, a.px, a.py, b.wx, b.wy, sg::mul(s, (double)ly), sg::mul(s, (double)(ly + 1)),
+                           sg::mul(s, (double)lx), sg::mul(s, (double)(lx + 1)), b.is_occ != 0, &o.base_p, &o.base_q);
+  }
+  a.out[i] = o;
+}
+
+// ---------------------------------------------------------------- K3a
+struct EstimateArgs {
+  const BeamRec *beams;
+  const BeamOut *bout;
+  const long long *offsets;  // N + 1
+  int N;
+  long long M;  // total slots
+  double px, py, scale;
+  slamgpu_estimator est;
+  double shift_amount;
+  const int2 *cells;
+  int w, h, ox, oy;
+  double *aoo_p, *aoo_q;  // per slot
+  unsigned *keys;         // per slot: internal cell index or SG_INVALID_KEY
+  unsigned *vals;         // per slot: slot id
+  int *slot_beam;         // per slot
+  unsigned long long *counters;  // [0] valid cells, [1] updates dropped outside a bounded map
+};
+
+__global__ void k_estimate(EstimateArgs a) {
+  long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (s >= a.M) return;
+  // beam of this slot: last i with offsets[i] <= s
+  int lo = 0, hi = a.N;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (a.offsets[mid] <= s) lo = mid; else hi = mid;
+  }
+  const int i = lo;
+  const int k = (int)(s - a.offsets[i]);
+  const BeamOut bo = a.bout[i];
+  a.vals[s] = (unsigned)s;
+  a.slot_beam[s] = i;
+  if (k >= bo.count) { a.keys[s] = SG_INVALID_KEY; return; }
+  const BeamRec b = a.beams[i];
+  const int2 c = a.cells[s];
+  double p, q;
+  if (k == bo.count - 1) {
+    p = bo.base_p; q = bo.base_q;
+  } else {
+    const double sc = a.scale;
+    sg::estimate_occupancy(a.est, a.shift_amount, a.px, a.py, b.wx, b.wy, sg::mul(sc, (double)c.y), sg::mul(sc, (double)(c.y + 1)),
+                           sg::mul(sc, (double)c.x), sg::mul(sc, (double)(c.x + 1)), false, &p, &q);
+    // wall blur ("hole"), grid_map_scan_adders.h:160-169; distances in cells, squared (exact in double)
+    double ddx = (double)(c.x - b.obx), ddy = (double)(c.y - b.oby);
+    double d_sq = sg::add(sg::mul(ddx, ddx), sg::mul(ddy, ddy));
+    if (d_sq < b.hole_sq && b.hole_sq < b.obst_sq) {
+      double prob_scale = sg::sub(1.0, sg::div(d_sq, b.hole_sq));
+      p = sg::mul(bo.base_p, prob_scale);
+    }
+  }
+  a.aoo_p[s] = p; a.aoo_q[s] = q;
+  int ix = c.x + a.ox, iy = c.y + a.oy;
+  if (ix < 0 || ix >= a.w || iy < 0 || iy >= a.h) {
+    a.keys[s] = SG_INVALID_KEY;
+    atomicAdd(a.counters + 1, 1ull);
+  } else {
+    a.keys[s] = (unsigned)iy * (unsigned)a.w + (unsigned)ix;
+  }
+  atomicAdd(a.counters, 1ull);
+}
+
+// ---------------------------------------------------------------- stable LSD radix sort (8-bit digits)
+#define SG_SORT_THREADS 256
+#define SG_SORT_ITEMS 8
+#define SG_SORT_TILE (SG_SORT_THREADS * SG_SORT_ITEMS)
+
+__global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_hist(const unsigned *__restrict__ keys, long long n, int shift,
+                                                                unsigned *__restrict__ ghist, int nb) {
+  __shared__ unsigned hist[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  long long base = (long long)blockIdx.x * SG_SORT_TILE;
+  for (int it = 0; it < SG_SORT_ITEMS; ++it) {
+    long long idx = base + it * SG_SORT_THREADS + threadIdx.x;
+    if (idx < n) atomicAdd(&hist[(keys[idx] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  ghist[(size_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) k_radix_scan(unsigned *data, int n) {  // exclusive scan, one block
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned v = i < n ? data[i] : 0, x = v;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned ws = warp_sums[lane], sx = ws;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, sx, off);
+        if (lane >= off) sx += y;
+      }
+      warp_sums[lane] = sx - ws;  // exclusive
+    }
+    __syncthreads();
+    unsigned excl = x - v + warp_sums[wid] + carry;
+    if (i < n) data[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigned *__restrict__ keys_in,
+                                                                   const unsigned *__restrict__ vals_in,
+                                                                   unsigned *__restrict__ keys_out,
+                                                                   unsigned *__restrict__ vals_out, long long n, int shift,
+                                                                   const unsigned *__restrict__ ghist, int nb) {
+  constexpr int NW = SG_SORT_THREADS / 32;
+  __shared__ unsigned wcount[NW][256];
+  __shared__ unsigned gbase[256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < NW * 256; k += SG_SORT_THREADS) (&wcount[0][0])[k] = 0;
+  gbase[threadIdx.x] = ghist[(size_t)threadIdx.x * nb + blockIdx.x];
+  __syncthreads();
+  // each warp owns a contiguous 256-element span of the tile and walks it in order, 32 at a time,
+  // so ranks within a digit follow the input order (stability)
+  const long long wbase = (long long)blockIdx.x * SG_SORT_TILE + (long long)w * (32 * SG_SORT_ITEMS);
+  unsigned key[SG_SORT_ITEMS], val[SG_SORT_ITEMS], rank[SG_SORT_ITEMS];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int c = 0; c < SG_SORT_ITEMS; ++c) {
+    long long idx = wbase + c * 32 + lane;
+    bool valid = idx < n;
+    key[c] = valid ? keys_in[idx] : 0u;
+    val[c] = valid ? vals_in[idx] : 0u;
+    unsigned digit = valid ? ((key[c] >> shift) & 255u) : 256u;
+    unsigned peers = __match_any_sync(0xffffffffu, digit);
+    unsigned r = __popc(peers & lt);
+    unsigned pre = valid ? wcount[w][digit] : 0u;
+    __syncwarp();
+    if (valid && r == 0) wcount[w][digit] = pre + __popc(peers);
+    __syncwarp();
+    rank[c] = pre + r;
+  }
+  __syncthreads();
+  {  // exclusive prefix over the warps of this block, per digit
+    unsigned run = 0;
+    const int d = threadIdx.x;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) {
+      unsigned t = wcount[ww][d];
+      wcount[ww][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < SG_SORT_ITEMS; ++c) {
+    long long idx = wbase + c * 32 + lane;
+    if (idx < n) {
+      unsigned digit = (key[c] >> shift) & 255u;
+      unsigned dst = gbase[digit] + wcount[w][digit] + rank[c];
+      keys_out[dst] = key[c];
+      vals_out[dst] = val[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K3b
+struct ApplyArgs {
+  const unsigned *keys, *vals;  // sorted
+  long long M;
+  const double *aoo_p, *aoo_q;
+  const int *slot_beam;
+  const BeamRec *beams;
+  double *cells;
+  int stride, model;
+  // optional trace for the pyramid: post-update impact of every applied slot (indexed by slot)
+  double *trace_impact;
+  int trace_oie;
+};
+
+__global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
+  long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= a.M) return;
+  const unsigned key = a.keys[j];
+  if (key == SG_INVALID_KEY) return;
+  if (j > 0 && a.keys[j - 1] == key) return;  // not the head of this cell's run
+  double r[SLAMGPU_MAX_STRIDE];
+  double *cell = a.cells + (size_t)key * a.stride;
+  for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
+  for (long long t = j; t < a.M && a.keys[t] == key; ++t) {
+    const unsigned s = a.vals[t];
+    const BeamRec &b = a.beams[a.slot_beam[s]];
+    sg::cell_update(a.model, r, a.aoo_p[s], a.aoo_q[s], b.wx, b.wy, b.quality);
+    if (a.trace_impact) a.trace_impact[s] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+  }
+  for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+}
+
+// ---------------------------------------------------------------- map growth (device side)
+__global__ void k_copy_block(const double *__restrict__ src, int sw, int sh, double *__restrict__ dst, int dw, int offx,
+                             int offy, int stride) {
+  size_t n = (size_t)sw * sh * stride;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    size_t cell = i / stride;
+    int k = (int)(i - cell * stride);
+    int y = (int)(cell / sw), x = (int)(cell - (size_t)y * sw);
+    dst[(((size_t)(y + offy)) * dw + (x + offx)) * stride + k] = src[i];
+  }
+}
+struct RecParam { double v[SLAMGPU_MAX_STRIDE]; };
+__global__ void k_fill(double *cells, size_t n_cells, int stride, RecParam rec) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  size_t n = n_cells * stride;
+  for (; i < n; i += st) cells[i] = rec.v[i % stride];
+}
+
+__global__ void k_reset_cell(double *cell, int stride, RecParam rec) {
+  for (int k = 0; k < stride; ++k) cell[k] = rec.v[k];
+}
+__global__ void k_update_cell(double *cell, int stride, int model, double p, double q, double obx, double oby, double quality) {
+  double r[SLAMGPU_MAX_STRIDE];
+  for (int k = 0; k < stride; ++k) r[k] = cell[k];
+  sg::cell_update(model, r, p, q, obx, oby, quality);
+  for (int k = 0; k < stride; ++k) cell[k] = r[k];
+}
+
+int host_world_to_cell(double v, double scale) { return (int)std::floor(v / scale); }
+
+}  // namespace
+
+// ---------------------------------------------------------------- growth rules (host logic)
+// UnboundedPlainGridMap::ensure_inside (src/core/maps/plain_grid_map.h:133-173, with its
+// unsigned/double conversions) and UnboundedLazyTiledGridMap::ensure_inside
+// (src/core/maps/lazy_tiled_grid_map.h:151-181)
+bool GrowState::ensure_inside(int x, int y) {
+  int cx = x + ox, cy = y + oy;
+  if (0 <= cx && cx < w && 0 <= cy && cy < h) return false;
+  if (grow == SLAMGPU_GROW_PLAIN) {
+    unsigned uw = w, uh = h, prep_x = 0, app_x = 0, prep_y = 0, app_y = 0;
+    if (cx < 0) prep_x = 0 - cx; else if ((int)uw <= cx) app_x = cx - uw + 1;
+    if (cy < 0) prep_y = 0 - cy; else if ((int)uh <= cy) app_y = cy - uh + 1;
+    unsigned new_w = prep_x + uw + app_x, new_h = prep_y + uh + app_y;
+    const double rate = 1.2;
+    if (uw < new_w && new_w < rate * uw) {
+      double sc = prep_x / (new_w - uw);  // unsigned division, as upstream
+      prep_x += (rate * uw - new_w) * sc;
+      new_w = rate * uw;
+    }
+    if (uh < new_h && new_h < rate * uh) {
+      double sc = prep_y / (new_h - uh);
+      prep_y += (rate * uh - new_h) * sc;
+      new_h = rate * uh;
+    }
+    w = (int)new_w; h = (int)new_h; ox += (int)prep_x; oy += (int)prep_y;
+    return true;
+  }
+  if (grow == SLAMGPU_GROW_TILED) {
+    const unsigned bits = 7, tile = 1u << bits;
+    unsigned tx = (w + tile - 1) / tile, ty = (h + tile - 1) / tile;
+    unsigned prep_x = 0, app_x = 0, prep_y = 0, app_y = 0;
+    if (cx < 0) prep_x = 1 + ((0 - cx) >> bits); else if (w <= cx) app_x = 1 + ((cx - w) >> bits);
+    if (cy < 0) prep_y = 1 + ((0 - cy) >> bits); else if (h <= cy) app_y = 1 + ((cy - h) >> bits);
+    unsigned ntx = prep_x + tx + app_x, nty = prep_y + ty + app_y;
+    w = (int)(ntx * tile); h = (int)(nty * tile); ox += (int)(prep_x * tile); oy += (int)(prep_y * tile);
+    return true;
+  }
+  return false;
+}
+
+// move the device map into a (larger) array laid out for `g`
+int sg_map_regrow(slamgpu_map *m, const GrowState &g) {
+  slamgpu_ctx *ctx = m->ctx;
+  if (g.w == m->w && g.h == m->h && g.ox == m->ox && g.oy == m->oy) return SLAMGPU_OK;
+  const int offx = g.ox - m->ox, offy = g.oy - m->oy;
+  if (offx < 0 || offy < 0 || offx + m->w > g.w || offy + m->h > g.h) return sg_fail(ctx, SLAMGPU_E_STATE, "map growth would shrink the map");
+  size_t need = (size_t)g.w * g.h * m->stride;
+  double *nc = nullptr;
+  SG_CUDA(ctx, cudaMalloc(&nc, std::max<size_t>(need, 1) * sizeof(double)));
+  RecParam rp;
+  memcpy(rp.v, m->unknown, sizeof rp.v);
+  k_fill<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(nc, (size_t)g.w * g.h, m->stride, rp);
+  SG_LAUNCHED(ctx);
+  if ((size_t)m->w * m->h > 0) {
+    k_copy_block<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(m->d_cells, m->w, m->h, nc, g.w, offx, offy, m->stride);
+    SG_LAUNCHED(ctx);
+  }
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (m->d_cells) cudaFree(m->d_cells);
+  m->d_cells = nc; m->cells_cap = need;
+  m->w = g.w; m->h = g.h; m->ox = g.ox; m->oy = g.oy;
+  m->pitch = (m->w + 2 * SG_LUT_PAD + 1) & ~1;
+  sg_map_invalidate_lut(m);
+  return SLAMGPU_OK;
+}
+
+// ---------------------------------------------------------------- single-cell plumbing
+extern "C" int slamgpu_map_reset_cell(slamgpu_map *m, int32_t x, int32_t y, const double *rec) {
+  if (!m || !rec) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  GrowState g{m->w, m->h, m->ox, m->oy, m->grow};
+  if (g.ensure_inside(x, y)) SG_TRY(sg_map_regrow(m, g));
+  int ix = x + m->ox, iy = y + m->oy;
+  if (ix < 0 || ix >= m->w || iy < 0 || iy >= m->h) return sg_fail(ctx, SLAMGPU_E_INVALID, "cell (%d, %d) is outside the bounded map", x, y);
+  RecParam rp;
+  memset(rp.v, 0, sizeof rp.v);
+  memcpy(rp.v, rec, sizeof(double) * m->stride);
+  k_reset_cell<<<1, 1, 0, ctx->stream>>>(m->d_cells + ((size_t)iy * m->w + ix) * m->stride, m->stride, rp);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  sg_map_invalidate_lut(m);
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_map_update_cell(slamgpu_map *m, int32_t x, int32_t y, int32_t aoo_is_occ, double aoo_p, double aoo_q,
+                                       double obst_x, double obst_y, double quality) {
+  (void)aoo_is_occ;
+  if (!m) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  GrowState g{m->w, m->h, m->ox, m->oy, m->grow};
+  if (g.ensure_inside(x, y)) SG_TRY(sg_map_regrow(m, g));
+  int ix = x + m->ox, iy = y + m->oy;
+  if (ix < 0 || ix >= m->w || iy < 0 || iy >= m->h) return sg_fail(ctx, SLAMGPU_E_INVALID, "cell (%d, %d) is outside the bounded map", x, y);
+  k_update_cell<<<1, 1, 0, ctx->stream>>>(m->d_cells + ((size_t)iy * m->w + ix) * m->stride, m->stride, m->model, aoo_p, aoo_q,
+                                         obst_x, obst_y, quality);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  sg_map_invalidate_lut(m);
+  return SLAMGPU_OK;
+}
+
+// ---------------------------------------------------------------- beam preparation (host, libm)
+// GridMapScanAdder::append_scan :54-75 + the per-beam part of handle_scan_point :138-150, 176-189
+int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double pose[3], double scan_quality, int scan_margin,
+                     double blur, double max_range, const double *point_quality, bool gate, BeamPlan *plan) {
+  const int N = s->n;
+  const double px = pose[0], py = pose[1], pth = pose[2], scale = m->scale;
+  plan->beams.assign(N, BeamRec{});
+  plan->offsets.assign(N + 1, 0);
+  plan->px = px; plan->py = py;
+  plan->rx = host_world_to_cell(px, scale); plan->ry = host_world_to_cell(py, scale);
+  const double max_range_sq = std::pow(max_range, 2);
+  long long total = 0;
+  const long long first = scan_margin, last = (long long)N - scan_margin - 1;  // grid_map_scan_adders.h:65-66
+  for (int i = 0; i < N; ++i) {
+    BeamRec &b = plan->beams[i];
+    plan->offsets[i] = total;
+    bool in_margin = i >= first && i <= last;
+    if (gate && !in_margin) continue;
+    const double r = s->range[i], a = s->angle[i];
+    b.wx = px + r * std::cos(pth + a);
+    b.wy = py + r * std::sin(pth + a);
+    b.quality = scan_quality * (point_quality ? point_quality[i] : 1.0);
+    b.is_occ = s->occ[i] ? 1 : 0;
+    const double len_sq = std::pow(b.wx - px, 2) + std::pow(b.wy - py, 2);
+    if (gate && max_range_sq < len_sq) continue;
+    if (!std::isfinite(b.wx) || !std::isfinite(b.wy)) continue;
+    b.obx = host_world_to_cell(b.wx, scale); b.oby = host_world_to_cell(b.wy, scale);
+    b.obst_sq = std::pow(plan->rx - b.obx, 2) + std::pow(plan->ry - b.oby, 2);
+    double blur_dist = 0;
+    if (b.is_occ) {
+      blur_dist = blur / scale;
+      if (blur_dist < 0) blur_dist *= -len_sq;
+    }
+    b.hole_sq = std::pow(blur_dist, 2);
+    b.active = 1;
+    long long ub = std::llabs((long long)b.obx - plan->rx) + std::llabs((long long)b.oby - plan->ry) + 1;
+    if (ub > (1ll << 26)) return SLAMGPU_E_INVALID;
+    total += ub;
+  }
+  plan->offsets[N] = total;
+  plan->M = total;
+  return SLAMGPU_OK;
+}
+
+namespace {
+
+int upload_async(slamgpu_ctx *ctx, DevBuf &dst, const void *src, size_t bytes) {
+  if (dst.reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "device buffer of %zu bytes", bytes);
+  if (bytes) SG_CUDA(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return SLAMGPU_OK;
+}
+
+double est_shift(const slamgpu_estimator &e, double scale, const BeamPlan &plan) {
+  // Shift_Amount is a function-static of the reference, fixed by the first cell it ever estimates
+  // (quirk Q10): the obstacle cell of the first inserted beam
+  if (e.shift_amount >= 0) return e.shift_amount;
+  int ly = plan.ry;
+  for (const BeamRec &b : plan.beams)
+    if (b.active) { ly = b.oby; break; }
+  return e.low_qual * (scale * (ly + 1) - scale * ly);
+}
+
+// K2 for a prepared plan: fills scratch[0] (beams), [1] (offsets), [2] (cells), [3] (BeamOut)
+int run_raycast(slamgpu_ctx *ctx, const slamgpu_map *m, const BeamPlan &plan, const slamgpu_estimator &est) {
+  const int N = (int)plan.beams.size();
+  SG_TRY(upload_async(ctx, ctx->scratch[0], plan.beams.data(), sizeof(BeamRec) * N));
+  SG_TRY(upload_async(ctx, ctx->scratch[1], plan.offsets.data(), sizeof(long long) * (N + 1)));
+  if (ctx->scratch[2].reserve(std::max<size_t>(plan.M, 1) * sizeof(int2)) != SLAMGPU_OK ||
+      ctx->scratch[3].reserve(std::max<size_t>(N, 1) * sizeof(BeamOut)) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast buffers (%lld slots)", plan.M);
+  if (N == 0) return SLAMGPU_OK;
+  RaycastArgs a;
+  a.beams = ctx->scratch[0].as<BeamRec>(); a.offsets = ctx->scratch[1].as<long long>(); a.N = N;
+  a.px = plan.px; a.py = plan.py; a.scale = m->scale; a.est = est;
+  a.shift_amount = est_shift(est, m->scale, plan);
+  a.cells = ctx->scratch[2].as<int2>(); a.out = ctx->scratch[3].as<BeamOut>();
+  cudaEventRecord(ctx->evk0, ctx->stream);
+  k_raycast<<<(N + 31) / 32, 32, 0, ctx->stream>>>(a);
+  cudaEventRecord(ctx->evk1, ctx->stream);
+  ctx->evk_valid = true;
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  return SLAMGPU_OK;
+}
+
+int radix_sort(slamgpu_ctx *ctx, unsigned *keys, unsigned *vals, unsigned *keys_tmp, unsigned *vals_tmp, long long n,
+               unsigned max_key, unsigned **keys_sorted, unsigned **vals_sorted) {
+  int bits = 1;
+  while (bits < 32 && (max_key >> bits) != 0) ++bits;
+  const int passes = (bits + 7) / 8;
+  const int nb = (int)((n + SG_SORT_TILE - 1) / SG_SORT_TILE);
+  if (ctx->scratch[6].reserve((size_t)256 * std::max(nb, 1) * sizeof(unsigned)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "sort histogram");
+  unsigned *ghist = ctx->scratch[6].as<unsigned>();
+  unsigned *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
+  for (int p = 0; p < passes && nb > 0; ++p) {
+    k_radix_hist<<<nb, SG_SORT_THREADS, 0, ctx->stream>>>(ki, n, 8 * p, ghist, nb);
+    k_radix_scan<<<1, 1024, 0, ctx->stream>>>(ghist, 256 * nb);
+    k_radix_scatter<<<nb, SG_SORT_THREADS, 0, ctx->stream>>>(ki, vi, ko, vo, n, 8 * p, ghist, nb);
+    ctx->launches += 3;
+    std::swap(ki, ko); std::swap(vi, vo);
+  }
+  SG_CUDA(ctx, cudaGetLastError());
+  *keys_sorted = ki; *vals_sorted = vi;
+  return SLAMGPU_OK;
+}
+
+}  // namespace
+
+// the whole insertion; `trace` (optional) receives what the pyramid needs
+int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,
+                        int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
+                        const double *point_quality, int64_t *cells_updated, AppendTrace *trace) {
+  if (!ctx || !map || !scan || !pose || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_scan: NULL argument");
+  if (map->ctx != ctx || scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map/scan belongs to another ctx");
+  if (est->type != SLAMGPU_EST_CONST && est->type != SLAMGPU_EST_AREA) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad estimator type");
+  if (scan_margin < 0) return sg_fail(ctx, SLAMGPU_E_INVALID, "negative scan margin");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (cells_updated) *cells_updated = 0;
+  if (trace) { trace->M = 0; trace->applied = 0; }
+  const int N = scan->n;
+  if (N == 0) return SLAMGPU_OK;  // grid_map_scan_adders.h:59
+  BeamPlan plan;
+  if (sg_prepare_beams(map, scan, pose, scan_quality, scan_margin, blur, max_range, point_quality, true, &plan) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "a beam spans more than 2^26 cells");
+  if (plan.M == 0) return SLAMGPU_OK;
+  if (plan.M >= (1ll << 31)) return sg_fail(ctx, SLAMGPU_E_NOMEM, "scan insertion needs %lld cell slots", plan.M);
+  SG_TRY(run_raycast(ctx, map, plan, *est));
+
+  // ---- map growth (Q9): only when some beam leaves the current bounds; replays the reference's
+  // ensure_inside sequence over the cells in update order
+  if (map->grow != SLAMGPU_GROW_NONE) {
+    auto outside = [&](int x, int y) { int ix = x + map->ox, iy = y + map->oy; return ix < 0 || ix >= map->w || iy < 0 || iy >= map->h; };
+    bool need = false;
+    for (int i = 0; i < N && !need; ++i)
+      if (plan.beams[i].active && (outside(plan.rx, plan.ry) || outside(plan.beams[i].obx, plan.beams[i].oby))) need = true;
+    if (need) {
+      std::vector<int2> cells((size_t)plan.M);
+      std::vector<BeamOut> bout(N);
+      SG_CUDA(ctx, cudaMemcpyAsync(cells.data(), ctx->scratch[2].p, sizeof(int2) * plan.M, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(ctx, cudaMemcpyAsync(bout.data(), ctx->scratch[3].p, sizeof(BeamOut) * N, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      GrowState g{map->w, map->h, map->ox, map->oy, map->grow};
+      for (int i = 0; i < N; ++i) {
+        if (!plan.beams[i].active) continue;
+        const int2 *c = cells.data() + plan.offsets[i];
+        const int n = bout[i].count;
+        g.ensure_inside(c[n - 1].x, c[n - 1].y);  // the obstacle cell is updated first
+        for (int k = 0; k < n - 1; ++k) g.ensure_inside(c[k].x, c[k].y);
+      }
+      SG_TRY(sg_map_regrow(map, g));
+    }
+  }
+  if ((long long)map->w * map->h >= 0xFFFFFFFFll) return sg_fail(ctx, SLAMGPU_E_NOMEM, "map too large for 32-bit cell keys");
+
+  // ---- K3a: per-slot AOO + sort keys
+  const long long M = plan.M;
+  DevBuf &slotbuf = ctx->scratch[4];
+  // layout: aoo_p[M] aoo_q[M] (double) | keys[M] vals[M] keys_tmp[M] vals_tmp[M] (u32) | slot_beam[M] (i32) | counters[2] (u64)
+  size_t bytes = (size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 64;
+  if (slotbuf.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "slot buffers (%lld slots)", M);
+  double *aoo_p = slotbuf.as<double>(), *aoo_q = aoo_p + M;
+  unsigned *keys = (unsigned *)(aoo_q + M), *vals = keys + M, *keys_tmp = vals + M, *vals_tmp = keys_tmp + M;
+  int *slot_beam = (int *)(vals_tmp + M);
+  size_t coff = ((size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 15) & ~(size_t)15;
+  unsigned long long *counters = (unsigned long long *)((char *)slotbuf.p + coff);
+  SG_CUDA(ctx, cudaMemsetAsync(counters, 0, 16, ctx->stream));
+  EstimateArgs ea;
+  ea.beams = ctx->scratch[0].as<BeamRec>(); ea.bout = ctx->scratch[3].as<BeamOut>(); ea.offsets = ctx->scratch[1].as<long long>();
+  ea.N = N; ea.M = M; ea.px = plan.px; ea.py = plan.py; ea.scale = map->scale; ea.est = *est;
+  ea.shift_amount = est_shift(*est, map->scale, plan);
+  ea.cells = ctx->scratch[2].as<int2>(); ea.w = map->w; ea.h = map->h; ea.ox = map->ox; ea.oy = map->oy;
+  ea.aoo_p = aoo_p; ea.aoo_q = aoo_q; ea.keys = keys; ea.vals = vals; ea.slot_beam = slot_beam; ea.counters = counters;
+  k_estimate<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+
+  // ---- sort by cell (stable), then apply each cell's run in order
+  unsigned *ks, *vs;
+  SG_TRY(radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)map->w * map->h), &ks, &vs));
+  ApplyArgs aa;
+  aa.keys = ks; aa.vals = vs; aa.M = M; aa.aoo_p = aoo_p; aa.aoo_q = aoo_q; aa.slot_beam = slot_beam;
+  aa.beams = ctx->scratch[0].as<BeamRec>(); aa.cells = map->d_cells; aa.stride = map->stride; aa.model = map->model;
+  aa.trace_impact = nullptr; aa.trace_oie = 0;
+  if (trace) {
+    if (ctx->scratch[5].reserve((size_t)M * sizeof(double)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
+    aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_oie = trace->oie;
+  }
+  cudaEventRecord(ctx->evk0, ctx->stream);
+  k_apply<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(aa);
+  cudaEventRecord(ctx->evk1, ctx->stream);
+  ctx->evk_valid = true;
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  sg_map_invalidate_lut(map);
+  unsigned long long h_counters[2];
+  SG_CUDA(ctx, cudaMemcpyAsync(h_counters, counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cells_updated) *cells_updated = (int64_t)h_counters[0];
+  if (trace) {
+    trace->M = M; trace->applied = (int64_t)h_counters[0];
+    trace->cells = ctx->scratch[2].as<int2>(); trace->keys_sorted = ks; trace->vals_sorted = vs;
+    trace->impact = aa.trace_impact; trace->slot_beam = slot_beam;
+    trace->d_bout = ctx->scratch[3].as<BeamOut>(); trace->d_offsets = ctx->scratch[1].as<long long>();
+  }
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
+                                   double scan_quality, int32_t scan_margin, const slamgpu_estimator *est, double blur,
+                                   double max_range, const double *point_quality, int64_t *cells_updated) {
+  if (!ctx) return SLAMGPU_E_INVALID;
+  if (map && map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_scan");
+  return sg_append_scan_impl(ctx, map, scan, pose, scan_quality, scan_margin, est, blur, max_range, point_quality,
+                             cells_updated, nullptr);
+}
+
+extern "C" int slamgpu_raycast(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
+                               int64_t *out_offsets, int32_t *out_cells, int64_t cap, int64_t *total) {
+  if (!ctx || !map || !scan || !pose || !out_offsets) return sg_fail(ctx, SLAMGPU_E_INVALID, "raycast: NULL argument");
+  if (map->ctx != ctx || scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map/scan belongs to another ctx");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int N = scan->n;
+  BeamPlan plan;
+  if (sg_prepare_beams(map, scan, pose, 1.0, 0, 0.0, INFINITY, nullptr, false, &plan) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "a beam spans more than 2^26 cells");
+  slamgpu_estimator est;
+  memset(&est, 0, sizeof est);
+  est.type = SLAMGPU_EST_CONST;
+  SG_TRY(run_raycast(ctx, map, plan, est));
+  std::vector<BeamOut> bout(std::max(N, 1));
+  if (N > 0) SG_CUDA(ctx, cudaMemcpyAsync(bout.data(), ctx->scratch[3].p, sizeof(BeamOut) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int64_t acc = 0;
+  for (int i = 0; i < N; ++i) { out_offsets[i] = acc; acc += bout[i].count; }
+  out_offsets[N] = acc;
+  if (total) *total = acc;
+  if (out_cells && cap > 0) {
+    std::vector<int2> cells((size_t)std::max<long long>(plan.M, 1));
+    if (plan.M > 0) SG_CUDA(ctx, cudaMemcpy(cells.data(), ctx->scratch[2].p, sizeof(int2) * plan.M, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < bout[i].count; ++k) {
+        int64_t o = out_offsets[i] + k;
+        if (o >= cap) break;
+        out_cells[2 * o] = cells[plan.offsets[i] + k].x;
+        out_cells[2 * o + 1] = cells[plan.offsets[i] + k].y;
+      }
+  }
+  return SLAMGPU_OK;
+}
+
+// ---------------------------------------------------------------- unit-level entry points
+// (the reference's own unit interfaces, used by the golden-vector tests and the C++ adapters)
+namespace {
+__global__ void k_raycast_segments(const double4 *__restrict__ segs, const long long *__restrict__ offsets, int n, double scale,
+                                   int2 *cells, int *counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 s = segs[i];
+  int2 *dst = cells + offsets[i];
+  counts[i] = sg::raycast(s.x, s.y, s.z, s.w, scale, [&](int k, int x, int y) { dst[k] = make_int2(x, y); });
+}
+__global__ void k_estimate_batch(slamgpu_estimator est, double shift, const double4 *__restrict__ beams,
+                                 const double4 *__restrict__ bounds, const unsigned char *__restrict__ is_occ, int n,
+                                 double2 *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 b = beams[i], c = bounds[i];
+  double p, q;
+  sg::estimate_occupancy(est, shift, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, is_occ[i] != 0, &p, &q);
+  out[i] = make_double2(p, q);
+}
+}  // namespace
+
+extern "C" int slamgpu_raycast_segments(slamgpu_ctx *ctx, double scale, const double *segments, int32_t n,
+                                        int64_t *out_offsets, int32_t *out_cells, int64_t cap, int64_t *total) {
+  if (!ctx || n < 0 || (n > 0 && !segments) || !out_offsets || !(scale > 0)) return sg_fail(ctx, SLAMGPU_E_INVALID, "raycast_segments: bad argument");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<long long> offs(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    const double *s = segments + 4 * i;
+    for (int k = 0; k < 4; ++k)
+      if (!std::isfinite(s[k])) return sg_fail(ctx, SLAMGPU_E_INVALID, "segment %d is not finite", i);
+    long long ub = std::llabs((long long)host_world_to_cell(s[2], scale) - host_world_to_cell(s[0], scale)) +
+                   std::llabs((long long)host_world_to_cell(s[3], scale) - host_world_to_cell(s[1], scale)) + 1;
+    if (ub > (1ll << 26)) return sg_fail(ctx, SLAMGPU_E_INVALID, "segment %d spans more than 2^26 cells", i);
+    offs[i + 1] = offs[i] + ub;
+  }
+  const long long M = offs[n];
+  SG_TRY(upload_async(ctx, ctx->scratch[0], segments, sizeof(double) * 4 * n));
+  SG_TRY(upload_async(ctx, ctx->scratch[1], offs.data(), sizeof(long long) * (n + 1)));
+  if (ctx->scratch[2].reserve(std::max<size_t>(M, 1) * sizeof(int2)) != SLAMGPU_OK ||
+      ctx->scratch[3].reserve(std::max<size_t>(n, 1) * sizeof(int)) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast buffers");
+  std::vector<int> counts(std::max(n, 1), 0);
+  std::vector<int2> cells((size_t)std::max<long long>(M, 1));
+  if (n > 0) {
+    k_raycast_segments<<<(n + 31) / 32, 32, 0, ctx->stream>>>(ctx->scratch[0].as<double4>(), ctx->scratch[1].as<long long>(), n,
+                                                              scale, ctx->scratch[2].as<int2>(), ctx->scratch[3].as<int>());
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaGetLastError());
+    SG_CUDA(ctx, cudaMemcpyAsync(counts.data(), ctx->scratch[3].p, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(cells.data(), ctx->scratch[2].p, sizeof(int2) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int64_t acc = 0;
+  for (int i = 0; i < n; ++i) { out_offsets[i] = acc; acc += counts[i]; }
+  out_offsets[n] = acc;
+  if (total) *total = acc;
+  if (out_cells)
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < counts[i]; ++k) {
+        int64_t o = out_offsets[i] + k;
+        if (o >= cap) break;
+        out_cells[2 * o] = cells[offs[i] + k].x;
+        out_cells[2 * o + 1] = cells[offs[i] + k].y;
+      }
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_estimate_occupancy(slamgpu_ctx *ctx, const slamgpu_estimator *est, int32_t n, const double *beams,
+                                          const double *cell_bounds, const uint8_t *is_occ, double *out_pq) {
+  if (!ctx || !est || n < 0 || (n > 0 && (!beams || !cell_bounds || !is_occ || !out_pq))) return sg_fail(ctx, SLAMGPU_E_INVALID, "estimate_occupancy: bad argument");
+  if (n == 0) return SLAMGPU_OK;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  SG_TRY(upload_async(ctx, ctx->scratch[0], beams, sizeof(double) * 4 * n));
+  SG_TRY(upload_async(ctx, ctx->scratch[1], cell_bounds, sizeof(double) * 4 * n));
+  SG_TRY(upload_async(ctx, ctx->scratch[2], is_occ, n));
+  if (ctx->scratch[3].reserve(sizeof(double2) * n) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "estimate buffers");
+  // Shift_Amount: explicit, or low_qual * side of the first cell (quirk Q10)
+  double shift = est->shift_amount >= 0 ? est->shift_amount : est->low_qual * (cell_bounds[1] - cell_bounds[0]);
+  k_estimate_batch<<<(n + 63) / 64, 64, 0, ctx->stream>>>(*est, shift, ctx->scratch[0].as<double4>(), ctx->scratch[1].as<double4>(),
+                                                         ctx->scratch[2].as<unsigned char>(), n, ctx->scratch[3].as<double2>());
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaMemcpyAsync(out_pq, ctx->scratch[3].p, sizeof(double2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}

@@ -1,0 +1,50 @@
+// mapping.h -- structures shared by mapping.cu (K2/K3) and pyramid.cu (K4/K5).
+#pragma once
+#include <vector>
+
+#include "internal.h"
+
+struct BeamRec {  // host-prepared, one per scan point
+  double wx, wy;      // beam end point in the world (libm trig on the host)
+  double quality;     // scan_quality * per-point mapping quality
+  double hole_sq;     // blur radius in cells, squared (0 for free points)
+  double obst_sq;     // squared cell distance robot -> obstacle cell
+  int obx, oby;       // obstacle cell
+  int is_occ, active; // active: inside the margin and the range gate
+};
+struct BeamOut {  // device-produced, one per scan point
+  int count;          // ray-cast cells of this beam
+  int lx, ly;         // last (obstacle) cell
+  int pad;
+  double base_p, base_q;  // occupancy estimate of the obstacle cell
+};
+struct BeamPlan {
+  std::vector<BeamRec> beams;
+  std::vector<long long> offsets;  // N + 1 slot offsets (upper bounds)
+  long long M = 0;
+  double px = 0, py = 0;
+  int rx = 0, ry = 0;  // robot cell
+};
+struct GrowState {
+  int w, h, ox, oy, grow;
+  bool ensure_inside(int x, int y);
+};
+struct AppendTrace {  // what a pyramid needs from a scan insertion (device pointers valid until the next call)
+  int oie = 0;
+  long long M = 0;
+  int64_t applied = 0;
+  const int2 *cells = nullptr;           // per slot: external cell
+  const unsigned *keys_sorted = nullptr; // per sorted position
+  const unsigned *vals_sorted = nullptr; // per sorted position: slot id
+  const double *impact = nullptr;        // per slot: impact of the cell right after this update
+  const int *slot_beam = nullptr;
+  const BeamOut *d_bout = nullptr;
+  const long long *d_offsets = nullptr;
+};
+
+int sg_map_regrow(slamgpu_map *m, const GrowState &g);
+int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double pose[3], double scan_quality, int scan_margin,
+                     double blur, double max_range, const double *point_quality, bool gate, BeamPlan *plan);
+int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,
+                        int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
+                        const double *point_quality, int64_t *cells_updated, AppendTrace *trace);

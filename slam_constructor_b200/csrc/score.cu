@@ -503,7 +503,10 @@ extern "C" int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const s
   size_t tb = std::max<size_t>((size_t)c.T * N, 1) * sizeof(double);
   if (c.trc.reserve(tb) != SLAMGPU_OK || c.trs.reserve(tb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trig table");
   c.trig_is_host = false;
-  if (!p->prerotated && p->trig_mode == SLAMGPU_TRIG_HOST && c.T > 0) SG_TRY(upload_host_trig(ctx, c, c.h_thetas, 1, c.T));
+  // the overlap OOPE depends continuously on the point position (not only on its cell), so device
+  // trig could move a score by an ulp: it always gets libm trig
+  if (p->oope == SLAMGPU_OOPE_OVERLAP) c.spe.trig_mode = SLAMGPU_TRIG_HOST;
+  if (!p->prerotated && c.spe.trig_mode == SLAMGPU_TRIG_HOST && c.T > 0) SG_TRY(upload_host_trig(ctx, c, c.h_thetas, 1, c.T));
   int nblk = (int)((Ploc + 127) / 128);
   if (c.scores.reserve(std::max<size_t>(Ploc, 1) * sizeof(double)) != SLAMGPU_OK ||
       c.blk_best.reserve(std::max(nblk, 1) * sizeof(Best)) != SLAMGPU_OK ||
