@@ -439,7 +439,9 @@ int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double p
     }
     b.hole_sq = std::pow(blur_dist, 2);
     b.active = 1;
-    long long ub = std::llabs((long long)b.obx - plan->rx) + std::llabs((long long)b.oby - plan->ry) + 1;
+    // |dx| + |dy| + 1 cells at most, plus the one extra cell the walk emits before it detects an
+    // overshoot and fails over to Bresenham (regular_squares_grid.h:84-86)
+    long long ub = std::llabs((long long)b.obx - plan->rx) + std::llabs((long long)b.oby - plan->ry) + 2;
     if (ub > (1ll << 26)) return SLAMGPU_E_INVALID;
     total += ub;
   }
@@ -687,7 +689,7 @@ extern "C" int slamgpu_raycast_segments(slamgpu_ctx *ctx, double scale, const do
     for (int k = 0; k < 4; ++k)
       if (!std::isfinite(s[k])) return sg_fail(ctx, SLAMGPU_E_INVALID, "segment %d is not finite", i);
     long long ub = std::llabs((long long)host_world_to_cell(s[2], scale) - host_world_to_cell(s[0], scale)) +
-                   std::llabs((long long)host_world_to_cell(s[3], scale) - host_world_to_cell(s[1], scale)) + 1;
+                   std::llabs((long long)host_world_to_cell(s[3], scale) - host_world_to_cell(s[1], scale)) + 2;
     if (ub > (1ll << 26)) return sg_fail(ctx, SLAMGPU_E_INVALID, "segment %d spans more than 2^26 cells", i);
     offs[i + 1] = offs[i] + ub;
   }

@@ -311,33 +311,32 @@ struct GridIdxArgs {
 
 // one thread per (theta, beam, axis value): the exact world_to_cell of the reference,
 // regular_squares_grid.h:40-46, applied to x_j + r*cos(theta+a) and y_k + r*sin(theta+a)
-__global__ void k_grid_indices(GridIdxArgs a) {
-  const int per = a.nx + a.nyp;
-  long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long total = (long long)a.nt_loc * a.N * per;
-  if (id >= total) return;
-  long long ti = id / per;  // tl*N + i
-  int c = (int)(id - ti * per);
-  int tl = (int)(ti / a.N), i = (int)(ti - (long long)tl * a.N);
-  long long src = (long long)(a.t_lo + tl) * a.N + i;
-  bool unsafe = false;
-  if (c < a.nx) {
-    double rc = a.trc[src];
-    double X = sg::add(a.xs[c], rc);
-    int cx = a.guard ? sg::world_to_cell_guard(X, a.scale, trig_slack(rc, X), &unsafe) : cell_of(floor(sg::div(X, a.scale)));
-    a.cxp[ti * a.nx + c] = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
-  } else {
-    int k = c - a.nx;
-    int out = 0;  // padding rows point at the ring row 0 (always valid memory)
-    if (k < a.ny) {
-      double rs = a.trs[src];
-      double Y = sg::add(a.ys[k], rs);
-      int cy = a.guard ? sg::world_to_cell_guard(Y, a.scale, trig_slack(rs, Y), &unsafe) : cell_of(floor(sg::div(Y, a.scale)));
-      out = (clampi(cy + a.oy, -1, a.h) + SG_LUT_PAD) * a.pitch;
+__global__ void __launch_bounds__(128) k_grid_indices(GridIdxArgs a) {
+  // blockIdx.x = tl * N + i (one (theta, beam) pair per block); threads cover the nx + nyp axis values
+  const long long ti = blockIdx.x;
+  const int tl = (int)(ti / a.N), i = (int)(ti - (long long)tl * a.N);
+  const long long src = (long long)(a.t_lo + tl) * a.N + i;
+  const double rc = a.trc[src], rs = a.trs[src];
+  bool unsafe_any = false;
+  for (int c = threadIdx.x; c < a.nx + a.nyp; c += blockDim.x) {
+    bool unsafe = false;
+    if (c < a.nx) {
+      double X = sg::add(a.xs[c], rc);
+      int cx = a.guard ? sg::world_to_cell_guard(X, a.scale, trig_slack(rc, X), &unsafe) : cell_of(floor(sg::div(X, a.scale)));
+      a.cxp[ti * a.nx + c] = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
+    } else {
+      int k = c - a.nx;
+      int out = 0;  // padding rows point at the ring row 0 (always valid memory)
+      if (k < a.ny) {
+        double Y = sg::add(a.ys[k], rs);
+        int cy = a.guard ? sg::world_to_cell_guard(Y, a.scale, trig_slack(rs, Y), &unsafe) : cell_of(floor(sg::div(Y, a.scale)));
+        out = (clampi(cy + a.oy, -1, a.h) + SG_LUT_PAD) * a.pitch;
+      }
+      a.cyp[ti * a.nyp + k] = out;
     }
-    a.cyp[ti * a.nyp + k] = out;
+    unsafe_any |= unsafe;
   }
-  if (unsafe) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
+  if (unsafe_any) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
 }
 
 struct GridArgs {
@@ -651,8 +650,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       ia.w = map->w; ia.h = map->h; ia.ox = map->ox; ia.oy = map->oy; ia.pitch = map->pitch; ia.scale = map->scale;
       ia.guard = device_trig ? 1 : 0;
       ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
-      long long tot = (long long)nt_loc * N * (c.nx + c.nyp);
-      k_grid_indices<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ia);
+      k_grid_indices<<<(unsigned)((long long)nt_loc * N), 128, 0, ctx->stream>>>(ia);
       SG_LAUNCHED(ctx);
     }
     if (nblk > 0) {
