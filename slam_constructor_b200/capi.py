@@ -379,3 +379,65 @@ class Scan:
         if getattr(self, "h", None):
             self.ctx.L.slamgpu_scan_destroy(self.h)
             self.h = None
+
+
+class Pyramid:
+    """slamgpu_pyramid: the max-pyramid over a fine GridMap (level 0)"""
+
+    def __init__(self, ctx, fine, oie=OIE_DISCREPANCY):
+        self.ctx, self.fine, self.oie = ctx, fine, oie
+        hnd = C.c_void_p()
+        ctx.check(ctx.L.slamgpu_pyramid_create(ctx.h, fine.h, oie, C.byref(hnd)))
+        self.h = hnd
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.slamgpu_pyramid_destroy(self.h)
+            self.h = None
+
+    def levels(self):
+        n = self.ctx.L.slamgpu_pyramid_levels(self.h)
+        if n < 0:
+            self.ctx.check(n)
+        return n
+
+    def level_info(self, level):
+        w, h, ox, oy = (C.c_int32() for _ in range(4))
+        sc = C.c_double()
+        self.ctx.check(self.ctx.L.slamgpu_pyramid_level_info(self.h, level, w, h, sc, ox, oy))
+        return dict(w=w.value, h=h.value, scale=sc.value, ox=ox.value, oy=oy.value, stride=STRIDE[self.fine.model])
+
+    def level(self, level, want_impact=False):
+        i = self.level_info(level)
+        cells = np.empty((i["h"], i["w"], i["stride"]))
+        imp = np.empty((i["h"], i["w"])) if want_impact else None
+        self.ctx.check(self.ctx.L.slamgpu_pyramid_level_download(self.h, level, _dp(cells), _dp(imp)))
+        return (cells, imp) if want_impact else cells
+
+    def build(self):
+        self.ctx.check(self.ctx.L.slamgpu_pyramid_build(self.h))
+
+    def rescale(self, target):
+        r = self.ctx.L.slamgpu_pyramid_rescale(self.h, target)
+        if r < 0:
+            self.ctx.check(r)
+        return r
+
+    def append_scan(self, scan, pose, quality=1.0, margin=0, est=None, blur=0.0, max_range=np.inf, point_quality=None):
+        est = est or estimator()
+        pose = _f64(pose)
+        pq = _f64(point_quality) if point_quality is not None else None
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.slamgpu_pyramid_append_scan(self.h, scan.h, _dp(pose), quality, margin, C.byref(est), blur,
+                                                              max_range, _dp(pq), C.byref(n)))
+        return n.value
+
+    def score_windows(self, scans, scan_id, windows, pose, params):
+        arr = (C.c_void_p * len(scans))(*[s.h for s in scans])
+        sid = np.ascontiguousarray(scan_id, dtype=np.int32)
+        win = _f64(windows).reshape(-1, 4)
+        pose = _f64(pose)
+        out = np.full(len(win), np.nan)
+        self.ctx.check(self.ctx.L.slamgpu_score_windows(self.h, arr, len(scans), sid.ctypes.data_as(c_ip), _dp(win), len(win),
+                                                        _dp(pose), C.byref(params), _dp(out)))
+        return out

@@ -247,6 +247,7 @@ struct ApplyArgs {
   int stride, model;
   // optional trace for the pyramid: post-update impact of every applied slot (indexed by slot)
   double *trace_impact;
+  double *trace_rec;  // per slot: the cell record right after this update (stride doubles)
   int trace_oie;
 };
 
@@ -263,7 +264,11 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
     const unsigned s = a.vals[t];
     const BeamRec &b = a.beams[a.slot_beam[s]];
     sg::cell_update(a.model, r, a.aoo_p[s], a.aoo_q[s], b.wx, b.wy, b.quality);
-    if (a.trace_impact) a.trace_impact[s] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+    if (a.trace_impact) {
+      a.trace_impact[s] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+      double *tr = a.trace_rec + (size_t)s * a.stride;
+      for (int k = 0; k < a.stride; ++k) tr[k] = r[k];
+    }
   }
   for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
 }
@@ -491,7 +496,9 @@ int run_raycast(slamgpu_ctx *ctx, const slamgpu_map *m, const BeamPlan &plan, co
   return SLAMGPU_OK;
 }
 
-int radix_sort(slamgpu_ctx *ctx, unsigned *keys, unsigned *vals, unsigned *keys_tmp, unsigned *vals_tmp, long long n,
+}  // namespace
+
+int sg_radix_sort(slamgpu_ctx *ctx, unsigned *keys, unsigned *vals, unsigned *keys_tmp, unsigned *vals_tmp, long long n,
                unsigned max_key, unsigned **keys_sorted, unsigned **vals_sorted) {
   int bits = 1;
   while (bits < 32 && (max_key >> bits) != 0) ++bits;
@@ -512,7 +519,6 @@ int radix_sort(slamgpu_ctx *ctx, unsigned *keys, unsigned *vals, unsigned *keys_
   return SLAMGPU_OK;
 }
 
-}  // namespace
 
 // the whole insertion; `trace` (optional) receives what the pyramid needs
 int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,
@@ -584,14 +590,14 @@ int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, 
 
   // ---- sort by cell (stable), then apply each cell's run in order
   unsigned *ks, *vs;
-  SG_TRY(radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)map->w * map->h), &ks, &vs));
+  SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)map->w * map->h), &ks, &vs));
   ApplyArgs aa;
   aa.keys = ks; aa.vals = vs; aa.M = M; aa.aoo_p = aoo_p; aa.aoo_q = aoo_q; aa.slot_beam = slot_beam;
   aa.beams = ctx->scratch[0].as<BeamRec>(); aa.cells = map->d_cells; aa.stride = map->stride; aa.model = map->model;
-  aa.trace_impact = nullptr; aa.trace_oie = 0;
+  aa.trace_impact = nullptr; aa.trace_rec = nullptr; aa.trace_oie = 0;
   if (trace) {
-    if (ctx->scratch[5].reserve((size_t)M * sizeof(double)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
-    aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_oie = trace->oie;
+    if (ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + map->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
+    aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_rec = aa.trace_impact + M; aa.trace_oie = trace->oie;
   }
   cudaEventRecord(ctx->evk0, ctx->stream);
   k_apply<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(aa);
@@ -607,7 +613,7 @@ int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, 
   if (trace) {
     trace->M = M; trace->applied = (int64_t)h_counters[0];
     trace->cells = ctx->scratch[2].as<int2>(); trace->keys_sorted = ks; trace->vals_sorted = vs;
-    trace->impact = aa.trace_impact; trace->slot_beam = slot_beam;
+    trace->impact = aa.trace_impact; trace->rec = aa.trace_rec; trace->slot_beam = slot_beam; trace->N = N;
     trace->d_bout = ctx->scratch[3].as<BeamOut>(); trace->d_offsets = ctx->scratch[1].as<long long>();
   }
   return SLAMGPU_OK;

@@ -37,6 +37,8 @@ struct AppendTrace {  // what a pyramid needs from a scan insertion (device poin
   const unsigned *keys_sorted = nullptr; // per sorted position
   const unsigned *vals_sorted = nullptr; // per sorted position: slot id
   const double *impact = nullptr;        // per slot: impact of the cell right after this update
+  const double *rec = nullptr;           // per slot: the cell record right after this update
+  int N = 0;                             // beams
   const int *slot_beam = nullptr;
   const BeamOut *d_bout = nullptr;
   const long long *d_offsets = nullptr;
@@ -48,3 +50,8 @@ int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double p
 int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,
                         int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
                         const double *point_quality, int64_t *cells_updated, AppendTrace *trace);
+
+// stable LSD radix sort of (key, value) pairs on the ctx stream; *_sorted point at whichever of the
+// two buffer pairs holds the result
+int sg_radix_sort(slamgpu_ctx *ctx, unsigned *keys, unsigned *vals, unsigned *keys_tmp, unsigned *vals_tmp, long long n,
+                  unsigned max_key, unsigned **keys_sorted, unsigned **vals_sorted);

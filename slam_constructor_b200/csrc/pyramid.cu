@@ -1,12 +1,530 @@
-// placeholder until K4/K5 land (same session): keeps every ABI symbol exported
-#include "internal.h"
-#define NOTYET(ctx) sg_fail(ctx, SLAMGPU_E_STATE, "%s: not implemented yet", __func__)
-extern "C" int slamgpu_pyramid_create(slamgpu_ctx *ctx, slamgpu_map *, int32_t, slamgpu_pyramid **) { return NOTYET(ctx); }
-extern "C" void slamgpu_pyramid_destroy(slamgpu_pyramid *) {}
-extern "C" int slamgpu_pyramid_levels(slamgpu_pyramid *) { return NOTYET(nullptr); }
-extern "C" int slamgpu_pyramid_level_info(slamgpu_pyramid *, int32_t, int32_t *, int32_t *, double *, int32_t *, int32_t *) { return NOTYET(nullptr); }
-extern "C" int slamgpu_pyramid_build(slamgpu_pyramid *) { return NOTYET(nullptr); }
-extern "C" int slamgpu_pyramid_level_download(slamgpu_pyramid *, int32_t, double *, double *) { return NOTYET(nullptr); }
-extern "C" int slamgpu_pyramid_rescale(slamgpu_pyramid *, double) { return NOTYET(nullptr); }
-extern "C" int slamgpu_pyramid_append_scan(slamgpu_pyramid *, slamgpu_scan *, const double *, double, int32_t, const slamgpu_estimator *, double, double, const double *, int64_t *) { return NOTYET(nullptr); }
-extern "C" int slamgpu_score_windows(slamgpu_pyramid *, slamgpu_scan *const *, int32_t, const int32_t *, const double *, int64_t, const double *, const slamgpu_spe_params *, double *) { return NOTYET(nullptr); }
+// pyramid.cu -- K4 (multi-resolution max-pyramid) and K5 (batched Match upper bounds).
+//
+// Replaces RescalableCachingGridMap (src/core/maps/rescalable_caching_grid_map.h:16-200),
+// M3RSMRescalableGridMap (src/core/scan_matchers/m3rsm_engine.h:17-131) and the scoring done by
+// Match::Match (m3rsm_engine.h:156-180).
+//
+// Level 0 is the caller's fine map; level k has cells of 2^k times the fine size and the last
+// level is a single cell of infinite size.  Every level is its own map with its own origin; all
+// levels share world alignment through floor(x / scale_k).
+//
+// The reference maintains coarse cells incrementally (update_coarser_maps :101-126): after each
+// fine cell update, walking up the levels, a coarse cell is replaced by a clone of the fine cell
+// iff it is still unknown or the fine cell's impact is not less_or_equal (eps compare) to the
+// coarse one, and the walk stops at the first level that did not change.  That is a sequential,
+// order dependent fold, reproduced here exactly for a whole scan insertion:
+//   per level:  k_level_coords  coarse cell of every still-alive update, in the reference's
+//                               update order (beam order, obstacle cell first)
+//               radix sort      stable, by coarse cell
+//               k_level_fold    one thread per coarse cell walks its run in order with the
+//                               reference's accept rule; updates that did not change the level
+//                               die, the others go on to the next level
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "dev_window.cuh"
+#include "mapping.h"
+
+struct slamgpu_pyramid {
+  slamgpu_ctx *ctx = nullptr;
+  int oie = 0;
+  std::vector<slamgpu_map *> lv;  // lv[0] is the caller's fine map (not owned)
+  DevBuf ent;                     // per-update working arrays of the incremental fold
+  DevBuf views, matches, scans, terms, bounds;  // K5 staging
+};
+
+namespace {
+
+#define SG_INVALID_KEY 0xFFFFFFFFu
+
+int ge_pow2(int i) {
+  int p = 1;
+  while (p < i) p *= 2;
+  return p;
+}
+
+// RescalableCachingGridMap::ensure_map_cache_is_continuous :171-194
+int ensure_continuous(slamgpu_pyramid *p) {
+  if (p->lv.size() < 2) return SLAMGPU_OK;
+  const slamgpu_map *pc = p->lv[p->lv.size() - 2];
+  int pc_w = pc->w, pc_h = pc->h;
+  double pc_scale = pc->scale;
+  if (pc_w <= 2 && pc_h <= 2) return SLAMGPU_OK;
+  pc_w = ge_pow2(pc_w); pc_h = ge_pow2(pc_h);
+  const slamgpu_map *fine = p->lv[0];
+  while (2 < pc_w || 2 < pc_h) {
+    // std::ceil(w / factor) with an unsigned factor upstream: integer division
+    pc_w = std::max(2, (int)std::ceil((double)((unsigned)pc_w / 2u)));
+    pc_h = std::max(2, (int)std::ceil((double)((unsigned)pc_h / 2u)));
+    pc_scale *= 2;
+    slamgpu_map *m = nullptr;
+    SG_TRY(slamgpu_map_create(p->ctx, pc_w, pc_h, pc_scale, fine->model, fine->grow, fine->unknown, &m));
+    p->lv.insert(p->lv.end() - 1, m);
+  }
+  return SLAMGPU_OK;
+}
+
+// ---------------------------------------------------------------- incremental update (exact)
+struct OrderArgs {
+  const long long *offsets;  // N + 1 slot offsets
+  const BeamOut *bout;
+  const int2 *cells;         // per slot
+  int N;
+  long long M;
+  int w, h, ox, oy;          // fine map bounds (updates outside a bounded map were dropped)
+  int *ent_slot;             // per position in update order: slot, or -1
+  unsigned char *alive;      // per position
+};
+
+// position pos of the reference's update sequence -> slot: within a beam the obstacle (last) cell
+// comes first, then cells 0 .. n-2 (grid_map_scan_adders.h:151-171)
+__global__ void k_order_entries(OrderArgs a) {
+  long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pos >= a.M) return;
+  int lo = 0, hi = a.N;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (a.offsets[mid] <= pos) lo = mid; else hi = mid;
+  }
+  const int j = (int)(pos - a.offsets[lo]);
+  const int count = a.bout[lo].count;
+  int slot = -1;
+  unsigned char alive = 0;
+  if (j < count) {
+    const int k = j == 0 ? count - 1 : j - 1;
+    slot = (int)(a.offsets[lo] + k);
+    const int2 c = a.cells[slot];
+    const int ix = c.x + a.ox, iy = c.y + a.oy;
+    alive = (ix >= 0 && ix < a.w && iy >= 0 && iy < a.h) ? 1 : 0;
+  }
+  a.ent_slot[pos] = slot;
+  a.alive[pos] = alive;
+}
+
+struct CoordArgs {
+  const int *ent_slot;
+  const unsigned char *alive;
+  const int2 *cells;
+  long long M;
+  double fine_scale, scale;  // fine cell size, this level's cell size
+  int w, h, ox, oy;          // this level's bounds
+  int2 *coords;              // per position: this level's (external) cell
+  unsigned long long *counters;  // [0] alive, [1] outside the level, [2] fine cell spans several coarse cells
+};
+
+// cells of this level covered by the fine cell: GridRasterizedRectangle(level, fine bounds, border excluded)
+// (grid_rasterization.h:26-47 with the 1e-9 inset)
+__global__ void k_level_coords(CoordArgs a) {
+  long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pos >= a.M) return;
+  if (!a.alive[pos]) return;
+  const int2 c = a.cells[a.ent_slot[pos]];
+  const double s = a.fine_scale;
+  const double bot = sg::mul(s, (double)c.y), top = sg::mul(s, (double)(c.y + 1));
+  const double left = sg::mul(s, (double)c.x), right = sg::mul(s, (double)(c.x + 1));
+  const double off = 1e-9;
+  const int lx = sg::world_to_cell(sg::add(left, off), a.scale), ly = sg::world_to_cell(sg::add(bot, off), a.scale);
+  const int rx = sg::world_to_cell(sg::sub(right, off), a.scale), ry = sg::world_to_cell(sg::sub(top, off), a.scale);
+  a.coords[pos] = make_int2(lx, ly);
+  atomicAdd(a.counters, 1ull);
+  if (lx != rx || ly != ry) atomicAdd(a.counters + 2, 1ull);
+  const int ix = lx + a.ox, iy = ly + a.oy;
+  if (ix < 0 || ix >= a.w || iy < 0 || iy >= a.h) atomicAdd(a.counters + 1, 1ull);
+}
+
+struct KeyArgs {
+  const unsigned char *alive;
+  const int2 *coords;
+  long long M;
+  int w, h, ox, oy;
+  unsigned *keys, *vals;
+  unsigned char *alive_next;
+};
+
+__global__ void k_level_keys(KeyArgs a) {
+  long long pos = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pos >= a.M) return;
+  unsigned key = SG_INVALID_KEY;
+  unsigned char next = 0;
+  if (a.alive[pos]) {
+    const int2 c = a.coords[pos];
+    const int ix = c.x + a.ox, iy = c.y + a.oy;
+    if (ix >= 0 && ix < a.w && iy >= 0 && iy < a.h) key = (unsigned)iy * (unsigned)a.w + (unsigned)ix;
+    else next = 1;  // outside a bounded level: reads as unknown, nothing is stored, the walk goes on
+  }
+  a.keys[pos] = key;
+  a.vals[pos] = (unsigned)pos;
+  a.alive_next[pos] = next;
+}
+
+struct FoldArgs {
+  const unsigned *keys, *vals;  // sorted by level cell; vals = positions in update order
+  long long M;
+  const int *ent_slot;
+  const double *impact;  // per slot: impact of the fine cell right after its update
+  const double *rec;     // per slot: fine cell record right after its update
+  double *cells;         // this level
+  int stride, model, oie;
+  unsigned char *alive_next;
+};
+
+// M3RSMRescalableGridMap::update_coarser_maps :101-126 for one level, one thread per level cell
+__global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
+  long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= a.M) return;
+  const unsigned key = a.keys[j];
+  if (key == SG_INVALID_KEY) return;
+  if (j > 0 && a.keys[j - 1] == key) return;
+  double cur[SLAMGPU_MAX_STRIDE];
+  double *cell = a.cells + (size_t)key * a.stride;
+  for (int k = 0; k < a.stride; ++k) cur[k] = cell[k];
+  bool cur_unknown = sg::rec_is_unknown(a.model, cur);
+  double cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
+  bool changed = false;
+  for (long long t = j; t < a.M && a.keys[t] == key; ++t) {
+    const unsigned pos = a.vals[t];
+    const int slot = a.ent_slot[pos];
+    const double x = a.impact[slot];
+    if (!cur_unknown && sg::less_or_equal(x, cur_impact)) { a.alive_next[pos] = 0; continue; }
+    const double *r = a.rec + (size_t)slot * a.stride;
+    for (int k = 0; k < a.stride; ++k) cur[k] = r[k];
+    cur_unknown = sg::rec_is_unknown(a.model, cur);
+    cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
+    changed = true;
+    a.alive_next[pos] = 1;
+  }
+  if (changed)
+    for (int k = 0; k < a.stride; ++k) cell[k] = cur[k];
+}
+
+// ---------------------------------------------------------------- from-scratch build
+struct BuildArgs {
+  const double *src;  // finer level
+  int sw, sh, sox, soy;
+  double *dst;        // this level
+  int dw, dh, dox, doy;
+  int stride, model, oie;
+  int last;           // this is the single infinite cell: reduce the whole finer level
+};
+
+SG_DEV void build_take(const BuildArgs &a, const double *r, double *cur, bool *cur_unknown, double *cur_impact) {
+  double rec[SLAMGPU_MAX_STRIDE];
+  for (int k = 0; k < a.stride; ++k) rec[k] = r[k];
+  if (sg::rec_is_unknown(a.model, rec)) return;  // a cell nobody wrote never propagated
+  double x = sg::cell_impact(a.model, a.oie, rec, 0.0, 0.0);
+  if (!*cur_unknown && sg::less_or_equal(x, *cur_impact)) return;
+  for (int k = 0; k < a.stride; ++k) cur[k] = rec[k];
+  *cur_unknown = false;
+  *cur_impact = x;
+}
+
+__global__ void k_build_level(BuildArgs a) {
+  int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (ix >= a.dw || iy >= a.dh) return;
+  double *cell = a.dst + ((size_t)iy * a.dw + ix) * a.stride;
+  double cur[SLAMGPU_MAX_STRIDE];
+  for (int k = 0; k < a.stride; ++k) cur[k] = cell[k];
+  bool cur_unknown = true;
+  double cur_impact = 0;
+  if (a.last) {
+    for (int sx = 0; sx < a.sw; ++sx)
+      for (int sy = 0; sy < a.sh; ++sy) build_take(a, a.src + ((size_t)sy * a.sw + sx) * a.stride, cur, &cur_unknown, &cur_impact);
+  } else {
+    const int X = ix - a.dox, Y = iy - a.doy;  // external cell of this level
+    for (int dx = 0; dx < 2; ++dx)
+      for (int dy = 0; dy < 2; ++dy) {
+        const int sx = 2 * X + dx + a.sox, sy = 2 * Y + dy + a.soy;
+        if (sx < 0 || sx >= a.sw || sy < 0 || sy >= a.sh) continue;
+        build_take(a, a.src + ((size_t)sy * a.sw + sx) * a.stride, cur, &cur_unknown, &cur_impact);
+      }
+  }
+  if (!cur_unknown)
+    for (int k = 0; k < a.stride; ++k) cell[k] = cur[k];
+}
+
+struct RecParam { double v[SLAMGPU_MAX_STRIDE]; };
+__global__ void k_fill_level(double *cells, size_t n_cells, int stride, RecParam rec) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  size_t n = n_cells * stride;
+  for (; i < n; i += st) cells[i] = rec.v[i % stride];
+}
+
+// ---------------------------------------------------------------- K5
+struct ScanView { const double *sx, *sy, *w, *f; int n, has_factor; double wsum; };
+struct MatchRec { double dx, dy, vside, hside; int scan_id, level; };
+
+// phase 1: one thread per (match, point): the `max` OOPE over the window re-centred at the point
+// (occupancy_observation_probability.h:35-48) on the level Match::Match picked (:176)
+__global__ void k_window_terms(const MatchRec *__restrict__ matches, const ScanView *__restrict__ scans,
+                               const MapView *__restrict__ views, int n_max, double *__restrict__ terms) {
+  const int m = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const MatchRec mr = matches[m];
+  const ScanView sv = scans[mr.scan_id];
+  if (i >= sv.n) return;
+  const MapView &mv = views[mr.level];
+  // pre-rotated scan: point + pose offset (sensor_data.h:103-105)
+  const double X = sg::add(sv.sx[i], mr.dx), Y = sg::add(sv.sy[i], mr.dy);
+  const double prob = window_probability<SLAMGPU_OOPE_MAX>(mv, X, Y, mr.vside, mr.hside);
+  double term = sg::mul(prob, sv.w[i]);
+  if (sv.has_factor) term = sg::mul(term, sv.f[i]);
+  terms[(size_t)m * n_max + i] = term;
+}
+
+// phase 2: the reference's sequential FP64 sum in point order (weighted_mean_point_probability_spe.h:107-132)
+__global__ void k_ordered_sums(const MatchRec *__restrict__ matches, const ScanView *__restrict__ scans, int n_max,
+                               const double *__restrict__ terms, long long M, double *__restrict__ out) {
+  long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const ScanView sv = scans[matches[m].scan_id];
+  double total = 0;
+  const double *t = terms + (size_t)m * n_max;
+  for (int i = 0; i < sv.n; ++i) total = sg::add(total, t[i]);
+  out[m] = sv.wsum == 0 ? NAN : sg::div(total, sv.wsum);
+}
+
+MapView level_view(const slamgpu_map *m, int oie) {
+  MapView v;
+  v.lut = m->d_lut[oie]; v.cells = m->d_cells;
+  v.w = m->w; v.h = m->h; v.ox = m->ox; v.oy = m->oy; v.pitch = m->pitch; v.stride = m->stride; v.model = m->model;
+  v.scale = m->scale; v.unknown_lut = m->unknown_lut[oie];
+  memcpy(v.unknown_rec, m->unknown, sizeof v.unknown_rec);
+  return v;
+}
+
+int rescale_id(slamgpu_pyramid *p, double target) {  // rescale :79-91
+  int id = 0;
+  while (id + 1 < (int)p->lv.size() && !(target <= p->lv[id]->scale)) ++id;
+  return id;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- ABI
+extern "C" int slamgpu_pyramid_create(slamgpu_ctx *ctx, slamgpu_map *fine, int32_t oie, slamgpu_pyramid **out) {
+  if (!ctx || !fine || !out) return sg_fail(ctx, SLAMGPU_E_INVALID, "pyramid_create: NULL argument");
+  if (fine->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
+  if (oie < 0 || oie > 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oie %d", oie);
+  if (fine->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map already is level 0 of a pyramid");
+  *out = nullptr;
+  slamgpu_pyramid *p = new slamgpu_pyramid();
+  p->ctx = ctx; p->oie = oie;
+  p->lv.push_back(fine);
+  slamgpu_map *top = nullptr;
+  int r = slamgpu_map_create(ctx, 1, 1, INFINITY, fine->model, fine->grow, fine->unknown, &top);
+  if (r != SLAMGPU_OK) { delete p; return r; }
+  p->lv.push_back(top);
+  r = ensure_continuous(p);
+  if (r != SLAMGPU_OK) { slamgpu_pyramid_destroy(p); return r; }
+  fine->pyr = p;
+  *out = p;
+  return SLAMGPU_OK;
+}
+
+extern "C" void slamgpu_pyramid_destroy(slamgpu_pyramid *p) {
+  if (!p) return;
+  if (!p->lv.empty() && p->lv[0]) p->lv[0]->pyr = nullptr;
+  for (size_t i = 1; i < p->lv.size(); ++i) slamgpu_map_destroy(p->lv[i]);
+  DevBuf *bufs[] = {&p->ent, &p->views, &p->matches, &p->scans, &p->terms, &p->bounds};
+  for (DevBuf *b : bufs) b->release();
+  delete p;
+}
+
+extern "C" int slamgpu_pyramid_levels(slamgpu_pyramid *p) {
+  if (!p) return SLAMGPU_E_INVALID;
+  if (ensure_continuous(p) != SLAMGPU_OK) return SLAMGPU_E_NOMEM;
+  return (int)p->lv.size();
+}
+
+extern "C" int slamgpu_pyramid_level_info(slamgpu_pyramid *p, int32_t level, int32_t *w, int32_t *h, double *scale,
+                                          int32_t *ox, int32_t *oy) {
+  if (!p || level < 0 || level >= (int)p->lv.size()) return SLAMGPU_E_INVALID;
+  return slamgpu_map_info(p->lv[level], w, h, scale, ox, oy, nullptr);
+}
+
+extern "C" int slamgpu_pyramid_rescale(slamgpu_pyramid *p, double target_scale) {
+  if (!p) return SLAMGPU_E_INVALID;
+  if (ensure_continuous(p) != SLAMGPU_OK) return SLAMGPU_E_NOMEM;
+  return rescale_id(p, target_scale);
+}
+
+extern "C" int slamgpu_pyramid_level_download(slamgpu_pyramid *p, int32_t level, double *cells, double *impact) {
+  if (!p || level < 0 || level >= (int)p->lv.size()) return SLAMGPU_E_INVALID;
+  if (cells) SG_TRY(slamgpu_map_download(p->lv[level], cells));
+  if (impact) SG_TRY(slamgpu_map_lut_download(p->lv[level], p->oie, impact, nullptr));
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_pyramid_build(slamgpu_pyramid *p) {
+  if (!p) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  SG_TRY(ensure_continuous(p));
+  for (size_t id = 1; id < p->lv.size(); ++id) {
+    slamgpu_map *src = p->lv[id - 1], *dst = p->lv[id];
+    const bool last = id + 1 == p->lv.size();
+    if (!last && dst->grow != SLAMGPU_GROW_NONE && src->w > 0 && src->h > 0) {
+      // make the level cover the finer one: the two extreme finer cells, halved toward -inf
+      GrowState g{dst->w, dst->h, dst->ox, dst->oy, dst->grow};
+      auto half = [](int v) { return (int)std::floor(v / 2.0); };
+      bool grew = g.ensure_inside(half(-src->ox), half(-src->oy));
+      grew |= g.ensure_inside(half(src->w - 1 - src->ox), half(src->h - 1 - src->oy));
+      if (grew) SG_TRY(sg_map_regrow(dst, g));
+    }
+    RecParam rp;
+    memcpy(rp.v, dst->unknown, sizeof rp.v);
+    k_fill_level<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dst->d_cells, (size_t)dst->w * dst->h, dst->stride, rp);
+    BuildArgs a;
+    a.src = src->d_cells; a.sw = src->w; a.sh = src->h; a.sox = src->ox; a.soy = src->oy;
+    a.dst = dst->d_cells; a.dw = dst->w; a.dh = dst->h; a.dox = dst->ox; a.doy = dst->oy;
+    a.stride = dst->stride; a.model = dst->model; a.oie = p->oie; a.last = last ? 1 : 0;
+    dim3 blk(32, 8), grd((dst->w + 31) / 32, (dst->h + 7) / 8);
+    if (id == 1) { cudaEventRecord(ctx->evk0, ctx->stream); }
+    k_build_level<<<grd, blk, 0, ctx->stream>>>(a);
+    if (id == 1) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->evk_valid = true; }
+    ctx->launches += 2;
+    SG_CUDA(ctx, cudaGetLastError());
+    sg_map_invalidate_lut(dst);
+    if (!last) SG_TRY(ensure_continuous(p));
+  }
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const double pose[3], double scan_quality,
+                                           int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
+                                           const double *point_quality, int64_t *cells_updated) {
+  if (!p) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  slamgpu_map *fine = p->lv[0];
+  SG_TRY(ensure_continuous(p));
+  AppendTrace tr;
+  tr.oie = p->oie;
+  SG_TRY(sg_append_scan_impl(ctx, fine, scan, pose, scan_quality, scan_margin, est, blur, max_range, point_quality,
+                             cells_updated, &tr));
+  const long long M = tr.M;
+  if (M == 0) return SLAMGPU_OK;
+  // per-position arrays: ent_slot (i32) coords (int2) keys vals keys_tmp vals_tmp (u32) alive alive_next (u8) counters
+  const size_t bytes = (size_t)M * (4 + 8 + 16 + 2) + 256;
+  if (p->ent.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "pyramid update buffers (%lld updates)", M);
+  int2 *coords = p->ent.as<int2>();
+  int *ent_slot = (int *)(coords + M);
+  unsigned *keys = (unsigned *)(ent_slot + M), *vals = keys + M, *keys_tmp = vals + M, *vals_tmp = keys_tmp + M;
+  unsigned char *alive = (unsigned char *)(vals_tmp + M), *alive_next = alive + M;
+  unsigned long long *counters = (unsigned long long *)(((uintptr_t)(alive_next + M) + 63) & ~(uintptr_t)63);
+  const unsigned nblk = (unsigned)((M + 127) / 128);
+  OrderArgs oa;
+  oa.offsets = tr.d_offsets; oa.bout = tr.d_bout; oa.cells = tr.cells; oa.N = tr.N; oa.M = M;
+  oa.w = fine->w; oa.h = fine->h; oa.ox = fine->ox; oa.oy = fine->oy; oa.ent_slot = ent_slot; oa.alive = alive;
+  k_order_entries<<<nblk, 128, 0, ctx->stream>>>(oa);
+  SG_LAUNCHED(ctx);
+  for (size_t id = 1; id < p->lv.size(); ++id) {
+    slamgpu_map *lvl = p->lv[id];
+    SG_CUDA(ctx, cudaMemsetAsync(counters, 0, 32, ctx->stream));
+    CoordArgs ca;
+    ca.ent_slot = ent_slot; ca.alive = alive; ca.cells = tr.cells; ca.M = M; ca.fine_scale = fine->scale; ca.scale = lvl->scale;
+    ca.w = lvl->w; ca.h = lvl->h; ca.ox = lvl->ox; ca.oy = lvl->oy; ca.coords = coords; ca.counters = counters;
+    k_level_coords<<<nblk, 128, 0, ctx->stream>>>(ca);
+    SG_LAUNCHED(ctx);
+    unsigned long long hc[4];
+    SG_CUDA(ctx, cudaMemcpyAsync(hc, counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hc[0] == 0) break;  // every update stopped below this level
+    if (hc[2] != 0) return sg_fail(ctx, SLAMGPU_E_STATE, "a fine cell spans several cells of level %zu (unsupported grid scale)", id);
+    if (hc[1] != 0 && lvl->grow != SLAMGPU_GROW_NONE) {
+      // the level grows exactly as the reference's would: replay ensure_inside over the updates in order
+      std::vector<int2> hcoords((size_t)M);
+      std::vector<unsigned char> halive((size_t)M);
+      SG_CUDA(ctx, cudaMemcpyAsync(hcoords.data(), coords, sizeof(int2) * M, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(ctx, cudaMemcpyAsync(halive.data(), alive, M, cudaMemcpyDeviceToHost, ctx->stream));
+      SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      GrowState g{lvl->w, lvl->h, lvl->ox, lvl->oy, lvl->grow};
+      for (long long pos = 0; pos < M; ++pos)
+        if (halive[pos]) g.ensure_inside(hcoords[pos].x, hcoords[pos].y);
+      SG_TRY(sg_map_regrow(lvl, g));
+    }
+    if ((long long)lvl->w * lvl->h >= 0xFFFFFFFFll) return sg_fail(ctx, SLAMGPU_E_NOMEM, "level too large for 32-bit cell keys");
+    KeyArgs ka;
+    ka.alive = alive; ka.coords = coords; ka.M = M; ka.w = lvl->w; ka.h = lvl->h; ka.ox = lvl->ox; ka.oy = lvl->oy;
+    ka.keys = keys; ka.vals = vals; ka.alive_next = alive_next;
+    k_level_keys<<<nblk, 128, 0, ctx->stream>>>(ka);
+    SG_LAUNCHED(ctx);
+    unsigned *ks, *vs;
+    SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)lvl->w * lvl->h), &ks, &vs));
+    FoldArgs fa;
+    fa.keys = ks; fa.vals = vs; fa.M = M; fa.ent_slot = ent_slot; fa.impact = tr.impact; fa.rec = tr.rec;
+    fa.cells = lvl->d_cells; fa.stride = lvl->stride; fa.model = lvl->model; fa.oie = p->oie; fa.alive_next = alive_next;
+    k_level_fold<<<nblk, 128, 0, ctx->stream>>>(fa);
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaGetLastError());
+    sg_map_invalidate_lut(lvl);
+    std::swap(alive, alive_next);
+    SG_TRY(ensure_continuous(p));  // a grown 2x2 level gets coarser levels above it
+  }
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *scans, int32_t n_scans, const int32_t *scan_id,
+                                     const double *windows, int64_t M, const double pose[3], const slamgpu_spe_params *spe,
+                                     double *out_bounds) {
+  if (!p) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  if (!scans || n_scans <= 0 || M < 0 || (M > 0 && (!scan_id || !windows || !out_bounds)) || !pose || !spe)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "score_windows: bad argument");
+  if (spe->oope != SLAMGPU_OOPE_MAX || !spe->prerotated)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "score_windows: the Match bound is defined for the max OOPE on pre-rotated scans");
+  if (M == 0) return SLAMGPU_OK;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  SG_TRY(ensure_continuous(p));
+  const int L = (int)p->lv.size();
+  std::vector<ScanView> sv(n_scans);
+  int n_max = 1;
+  for (int k = 0; k < n_scans; ++k) {
+    const slamgpu_scan *s = scans[k];
+    if (!s || s->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan %d is NULL or belongs to another ctx", k);
+    sv[k] = ScanView{s->d_x, s->d_y, s->d_w, s->d_f, s->n, s->has_factor ? 1 : 0, s->wsum};
+    n_max = std::max(n_max, s->n);
+  }
+  std::vector<MatchRec> mr((size_t)M);
+  std::vector<char> used(L, 0);
+  for (int64_t m = 0; m < M; ++m) {
+    const double bot = windows[4 * m], top = windows[4 * m + 1], left = windows[4 * m + 2], right = windows[4 * m + 3];
+    const double vside = top - bot, hside = right - left;  // LightWeightRectangle::vside/hside
+    const double cx = left + hside / 2, cy = bot + vside / 2;  // ::center, geometry_primitives.h:191-193
+    if (scan_id[m] < 0 || scan_id[m] >= n_scans) return sg_fail(ctx, SLAMGPU_E_INVALID, "match %lld: bad scan id", (long long)m);
+    MatchRec &r = mr[m];
+    r.dx = pose[0] + cx; r.dy = pose[1] + cy; r.vside = vside; r.hside = hside; r.scan_id = scan_id[m];
+    r.level = rescale_id(p, std::max(vside, hside));  // Match::Match :176
+    used[r.level] = 1;
+  }
+  std::vector<MapView> views(L);
+  for (int l = 0; l < L; ++l) {
+    if (used[l]) SG_TRY(sg_map_ensure_lut(p->lv[l], spe->oie));
+    views[l] = level_view(p->lv[l], spe->oie);
+  }
+  if (p->views.reserve(sizeof(MapView) * L) != SLAMGPU_OK || p->matches.reserve(sizeof(MatchRec) * M) != SLAMGPU_OK ||
+      p->scans.reserve(sizeof(ScanView) * n_scans) != SLAMGPU_OK || p->terms.reserve(sizeof(double) * M * n_max) != SLAMGPU_OK ||
+      p->bounds.reserve(sizeof(double) * M) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "score_windows buffers");
+  SG_CUDA(ctx, cudaMemcpyAsync(p->views.p, views.data(), sizeof(MapView) * L, cudaMemcpyHostToDevice, ctx->stream));
+  SG_CUDA(ctx, cudaMemcpyAsync(p->matches.p, mr.data(), sizeof(MatchRec) * M, cudaMemcpyHostToDevice, ctx->stream));
+  SG_CUDA(ctx, cudaMemcpyAsync(p->scans.p, sv.data(), sizeof(ScanView) * n_scans, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grd((n_max + 127) / 128, (unsigned)M);
+  cudaEventRecord(ctx->evk0, ctx->stream);
+  k_window_terms<<<grd, 128, 0, ctx->stream>>>(p->matches.as<MatchRec>(), p->scans.as<ScanView>(), p->views.as<MapView>(), n_max,
+                                                p->terms.as<double>());
+  cudaEventRecord(ctx->evk1, ctx->stream);
+  ctx->evk_valid = true;
+  k_ordered_sums<<<(unsigned)((M + 63) / 64), 64, 0, ctx->stream>>>(p->matches.as<MatchRec>(), p->scans.as<ScanView>(), n_max,
+                                                                   p->terms.as<double>(), M, p->bounds.as<double>());
+  ctx->launches += 2;
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaMemcpyAsync(out_bounds, p->bounds.p, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
