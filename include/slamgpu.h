@@ -165,6 +165,13 @@ int slamgpu_map_update_cell(slamgpu_map *m, int32_t x, int32_t y, int32_t aoo_is
  * OIE(cell, obstacle AOO {true,{1,1},.,1}), grid_scan_matcher.h:44-46 */
 int slamgpu_map_lut_download(slamgpu_map *m, int32_t oie, double *lut /* h*w */, double *unknown_value);
 
+/* score-only snapshot of a host-side map: `lut` holds ObservationImpactEstimator::estimate_obstacle_impact
+ * of every cell (h*w, row major), evaluated by the caller with the reference's own classes, so any
+ * GridCell / OIE type can be scored on the device; cell records are left unknown.  The next cell
+ * update or upload invalidates it. */
+int slamgpu_map_upload_lut(slamgpu_map *m, int32_t oie, const double *lut /* h*w */, double unknown_value, int32_t w,
+                           int32_t h, int32_t ox, int32_t oy);
+
 /* ------------------------------------------------------------------ laser scan
  * replaces LaserScan2D / ScanPoint2D (src/core/states/sensor_data.h:14-208) as the
  * kernels see it: filtered points with their pose-independent weights (the output of
@@ -239,6 +246,14 @@ int slamgpu_estimate_occupancy(slamgpu_ctx *ctx, const slamgpu_estimator *est, i
 int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
                         double scan_quality, int32_t scan_margin, const slamgpu_estimator *est, double blur,
                         double max_range, const double *point_quality, int64_t *cells_updated);
+
+/* the same for the beams of one scan given explicitly as world segments {bx, by, ex, ey} (all
+ * starting at the robot position), with per-beam is_occupied and quality: exactly the arguments of
+ * the pure virtual GridMapScanAdder::handle_scan_point(map, is_occ, scan_quality, beam)
+ * (grid_map_scan_adders.h:85-86), which a drop-in adder queues per point and flushes in one call */
+int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t n, const double *beams /* 4*n */,
+                         const uint8_t *is_occ /* n */, const double *quality /* n */, const slamgpu_estimator *est,
+                         double blur, double max_range, int64_t *cells_updated);
 
 /* ------------------------------------------------------------------ K4/K5: max-pyramid
  * replaces RescalableCachingGridMap + M3RSMRescalableGridMap

@@ -63,10 +63,10 @@ SYMBOLS = [
     "slamgpu_ctx_destroy", "slamgpu_last_error", "slamgpu_sync", "slamgpu_timer_begin", "slamgpu_timer_end",
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
-    "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_scan_create",
+    "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
     "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_stage_poses",
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
-    "slamgpu_append_scan", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
+    "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
     "slamgpu_pyramid_append_scan", "slamgpu_score_windows",
 ]
@@ -111,6 +111,7 @@ def lib():
     L.slamgpu_map_reset_cell.argtypes = [vp, i32, i32, c_dp]
     L.slamgpu_map_update_cell.argtypes = [vp, i32, i32, i32, dbl, dbl, dbl, dbl, dbl]
     L.slamgpu_map_lut_download.argtypes = [vp, i32, c_dp, c_dp]
+    L.slamgpu_map_upload_lut.argtypes = [vp, i32, c_dp, dbl, i32, i32, i32, i32]
     L.slamgpu_scan_create.argtypes = [vp, pvp]
     L.slamgpu_scan_destroy.argtypes = [vp]
     L.slamgpu_scan_destroy.restype = None
@@ -128,6 +129,7 @@ def lib():
     L.slamgpu_raycast_segments.argtypes = [vp, dbl, c_dp, i32, c_lp, c_ip, i64, c_lp]
     L.slamgpu_estimate_occupancy.argtypes = [vp, ep, i32, c_dp, c_dp, c_u8p, c_dp]
     L.slamgpu_append_scan.argtypes = [vp, vp, vp, c_dp, dbl, i32, ep, dbl, dbl, c_dp, c_lp]
+    L.slamgpu_append_beams.argtypes = [vp, vp, i32, c_dp, c_u8p, c_dp, ep, dbl, dbl, c_lp]
     L.slamgpu_pyramid_create.argtypes = [vp, vp, i32, pvp]
     L.slamgpu_pyramid_destroy.argtypes = [vp]
     L.slamgpu_pyramid_destroy.restype = None
@@ -337,6 +339,13 @@ class GridMap:
         unk = C.c_double()
         self.ctx.check(self.ctx.L.slamgpu_map_lut_download(self.h, oie, _dp(out), C.byref(unk)))
         return out, unk.value
+
+    def upload_lut(self, lut, unknown_value, oie=OIE_DISCREPANCY, ox=None, oy=None):
+        lut = _f64(lut)
+        h, w = lut.shape
+        ox = w // 2 if ox is None else ox
+        oy = h // 2 if oy is None else oy
+        self.ctx.check(self.ctx.L.slamgpu_map_upload_lut(self.h, oie, _dp(lut), unknown_value, w, h, ox, oy))
 
     def read_cell(self, x, y):
         rec = np.zeros(8)

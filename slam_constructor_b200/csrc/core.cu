@@ -442,3 +442,49 @@ extern "C" int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian
   if (ctx->cand.scan == s) ctx->cand.kind = -1;  // staged candidates depend on the scan
   return SLAMGPU_OK;
 }
+
+// a score-only snapshot of a host-side map: the caller evaluated its own ObservationImpactEstimator per
+// cell (any cell class works), the kernels only ever gather this LUT
+__global__ void k_pad_lut(const double *__restrict__ src, int w, int h, double *__restrict__ lut, int pitch, double unknown_value) {
+  int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+  if (px >= pitch || py >= h + 2 * SG_LUT_PAD) return;
+  int x = px - SG_LUT_PAD, y = py - SG_LUT_PAD;
+  lut[(size_t)py * pitch + px] = (x >= 0 && x < w && y >= 0 && y < h) ? src[(size_t)y * w + x] : unknown_value;
+}
+
+extern "C" int slamgpu_map_upload_lut(slamgpu_map *m, int32_t oie, const double *lut, double unknown_value, int32_t w, int32_t h,
+                                      int32_t ox, int32_t oy) {
+  if (!m || !lut || w < 0 || h < 0 || oie < 0 || oie > 1) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = m->ctx;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (w != m->w || h != m->h) {
+    SG_TRY(sg_map_realloc(m, w, h));
+    // cell records are not part of a score-only snapshot: keep them at the unknown prototype
+    RecParam rp;
+    memcpy(rp.v, m->unknown, sizeof rp.v);
+    if ((size_t)w * h > 0) {
+      k_fill_cells<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(m->d_cells, (size_t)w * h, m->stride, rp);
+      SG_LAUNCHED(ctx);
+    }
+  }
+  m->ox = ox; m->oy = oy;
+  size_t need = (size_t)m->pitch * (m->h + 2 * SG_LUT_PAD);
+  if (need > m->lut_cap[oie]) {
+    if (m->d_lut[oie]) cudaFree(m->d_lut[oie]);
+    m->d_lut[oie] = nullptr; m->lut_cap[oie] = 0;
+    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], need * sizeof(double)));
+    m->lut_cap[oie] = need;
+  }
+  size_t bytes = std::max<size_t>((size_t)w * h, 1) * sizeof(double);
+  if (ctx->scratch[7].reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "LUT staging");
+  SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[7].p, lut, (size_t)w * h * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 blk(32, 8), grd((m->pitch + 31) / 32, (m->h + 2 * SG_LUT_PAD + 7) / 8);
+  k_pad_lut<<<grd, blk, 0, ctx->stream>>>(ctx->scratch[7].as<double>(), w, h, m->d_lut[oie], m->pitch, unknown_value);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->unknown_lut[oie] = unknown_value;
+  m->lut_valid[oie] = true;
+  m->lut_valid[1 - oie] = false;
+  return SLAMGPU_OK;
+}

@@ -526,16 +526,25 @@ int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, 
                         const double *point_quality, int64_t *cells_updated, AppendTrace *trace) {
   if (!ctx || !map || !scan || !pose || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_scan: NULL argument");
   if (map->ctx != ctx || scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map/scan belongs to another ctx");
-  if (est->type != SLAMGPU_EST_CONST && est->type != SLAMGPU_EST_AREA) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad estimator type");
   if (scan_margin < 0) return sg_fail(ctx, SLAMGPU_E_INVALID, "negative scan margin");
-  SG_CUDA(ctx, cudaSetDevice(ctx->device));
   if (cells_updated) *cells_updated = 0;
   if (trace) { trace->M = 0; trace->applied = 0; }
-  const int N = scan->n;
-  if (N == 0) return SLAMGPU_OK;  // grid_map_scan_adders.h:59
+  if (scan->n == 0) return SLAMGPU_OK;  // grid_map_scan_adders.h:59
   BeamPlan plan;
   if (sg_prepare_beams(map, scan, pose, scan_quality, scan_margin, blur, max_range, point_quality, true, &plan) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_INVALID, "a beam spans more than 2^26 cells");
+  return sg_append_plan(ctx, map, plan, est, cells_updated, trace);
+}
+
+// K2 + K3 for prepared beams (all sharing the begin point plan.px, plan.py)
+int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, const slamgpu_estimator *est,
+                   int64_t *cells_updated, AppendTrace *trace) {
+  if (!ctx || !map || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append: NULL argument");
+  if (est->type != SLAMGPU_EST_CONST && est->type != SLAMGPU_EST_AREA) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad estimator type");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (cells_updated) *cells_updated = 0;
+  if (trace) { trace->M = 0; trace->applied = 0; }
+  const int N = (int)plan.beams.size();
   if (plan.M == 0) return SLAMGPU_OK;
   if (plan.M >= (1ll << 31)) return sg_fail(ctx, SLAMGPU_E_NOMEM, "scan insertion needs %lld cell slots", plan.M);
   SG_TRY(run_raycast(ctx, map, plan, *est));
@@ -626,6 +635,50 @@ extern "C" int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_s
   if (map && map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_scan");
   return sg_append_scan_impl(ctx, map, scan, pose, scan_quality, scan_margin, est, blur, max_range, point_quality,
                              cells_updated, nullptr);
+}
+
+extern "C" int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
+                                    const double *quality, const slamgpu_estimator *est, double blur, double max_range,
+                                    int64_t *cells_updated) {
+  if (!ctx || !map || n < 0 || (n > 0 && (!beams || !is_occ || !quality)) || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_beams: bad argument");
+  if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
+  if (map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_scan");
+  if (cells_updated) *cells_updated = 0;
+  if (n == 0) return SLAMGPU_OK;
+  BeamPlan plan;
+  const double scale = map->scale;
+  const double px = beams[0], py = beams[1];
+  plan.px = px; plan.py = py;
+  plan.rx = host_world_to_cell(px, scale); plan.ry = host_world_to_cell(py, scale);
+  plan.beams.assign(n, BeamRec{});
+  plan.offsets.assign(n + 1, 0);
+  const double max_range_sq = std::pow(max_range, 2);
+  long long total = 0;
+  for (int i = 0; i < n; ++i) {
+    const double *s = beams + 4 * i;
+    if (s[0] != px || s[1] != py) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_beams: beam %d starts elsewhere (one call = one scan)", i);
+    BeamRec &b = plan.beams[i];
+    plan.offsets[i] = total;
+    b.wx = s[2]; b.wy = s[3]; b.quality = quality[i]; b.is_occ = is_occ[i] ? 1 : 0;
+    const double len_sq = std::pow(b.wx - px, 2) + std::pow(b.wy - py, 2);  // Segment2D::length_sq
+    if (max_range_sq < len_sq) continue;
+    if (!std::isfinite(b.wx) || !std::isfinite(b.wy)) continue;
+    b.obx = host_world_to_cell(b.wx, scale); b.oby = host_world_to_cell(b.wy, scale);
+    b.obst_sq = std::pow(plan.rx - b.obx, 2) + std::pow(plan.ry - b.oby, 2);
+    double blur_dist = 0;
+    if (b.is_occ) {
+      blur_dist = blur / scale;
+      if (blur_dist < 0) blur_dist *= -len_sq;
+    }
+    b.hole_sq = std::pow(blur_dist, 2);
+    b.active = 1;
+    long long ub = std::llabs((long long)b.obx - plan.rx) + std::llabs((long long)b.oby - plan.ry) + 2;
+    if (ub > (1ll << 26)) return sg_fail(ctx, SLAMGPU_E_INVALID, "beam %d spans more than 2^26 cells", i);
+    total += ub;
+  }
+  plan.offsets[n] = total;
+  plan.M = total;
+  return sg_append_plan(ctx, map, plan, est, cells_updated, nullptr);
 }
 
 extern "C" int slamgpu_raycast(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],

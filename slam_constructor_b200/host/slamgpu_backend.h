@@ -1,0 +1,670 @@
+// slamgpu_backend.h -- the B200 back end as plug-ins for slam-constructor's own interfaces.
+//
+// Header-only C++14, compiled against the UNMODIFIED reference headers (add the reference's
+// root to the include path: -I<slam-constructor>); it talks to the GPU only through the C ABI
+// of include/slamgpu.h.  Nothing in here computes a score or a cell value on the CPU.
+//
+//   slamgpu::CudaGridMap            : GridMap            device-resident map (+ lazy host mirror)
+//   slamgpu::CudaScanAdder          : GridMapScanAdder   queues handle_scan_point, one K2/K3 launch per scan
+//   slamgpu::CudaBruteForceScanMatcher          : GridScanMatcher   BruteForceScanMatcher's candidate set on K1 (grid kernel)
+//   slamgpu::CudaPoseEnumerationScanMatcher<PE> : GridScanMatcher   any copyable PoseEnumerator (Monte-Carlo, hill climbing,
+//                                                 polar brute force) by speculative batches on K1 (list kernel)
+//   slamgpu::CudaMonteCarloScanMatcher, slamgpu::CudaHillClimbingScanMatcher   the two stock instances
+//
+// They drop into SingleStateHypothesisLSGWProperties{grid_map, gsm, gmsa}
+// (src/core/states/single_state_hypothesis_laser_scan_grid_world.h:13-21) and hence into the
+// tinySLAM / vinySLAM world and into GmappingWorld / GmappingParticleFilter
+// (src/slams/gmapping/gmapping_world.h:36-128) unchanged.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "src/core/maps/area_occupancy_estimator.h"
+#include "src/core/maps/const_occupancy_estimator.h"
+#include "src/core/maps/grid_map.h"
+#include "src/core/maps/grid_map_scan_adders.h"
+#include "src/core/maps/naive_grid_cells.h"
+#include "src/core/maps/tbm_grid_cells.h"
+#include "src/core/scan_matchers/brute_force_scan_matcher.h"
+#include "src/core/scan_matchers/grid_scan_matcher.h"
+#include "src/core/scan_matchers/hill_climbing_scan_matcher.h"
+#include "src/core/scan_matchers/monte_carlo_scan_matcher.h"
+#include "src/core/scan_matchers/observation_impact_estimators.h"
+#include "src/core/scan_matchers/occupancy_observation_probability.h"
+#include "src/core/scan_matchers/weighted_mean_point_probability_spe.h"
+#include "src/slams/gmapping/gmapping_grid_cell.h"
+#include "src/slams/gmapping/gmapping_occupancy_observation_pe.h"
+
+#include "slamgpu.h"
+
+namespace slamgpu {
+
+class Error : public std::runtime_error {
+public:
+  Error(int code, const std::string &msg) : std::runtime_error("slamgpu error " + std::to_string(code) + ": " + msg), code(code) {}
+  int code;
+};
+
+// one CUDA context (stream, scratch) per world; shared by the map, the adder and the matcher
+class Context {
+public:
+  explicit Context(int device = 0) {
+    int r = slamgpu_ctx_create(device, &_h);
+    if (r != SLAMGPU_OK) throw Error(r, slamgpu_last_error(nullptr));
+  }
+  ~Context() { slamgpu_ctx_destroy(_h); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  slamgpu_ctx *handle() const { return _h; }
+  void check(int r) const {
+    if (r != SLAMGPU_OK) throw Error(r, slamgpu_last_error(_h));
+  }
+private:
+  slamgpu_ctx *_h = nullptr;
+};
+
+// the cell model enum of a reference cell class
+inline int cell_model_of(const GridCell &proto) {
+  if (dynamic_cast<const MeanProbabilityCell *>(&proto)) return SLAMGPU_CELL_MEAN;
+  if (dynamic_cast<const AffineQualityMergeCell *>(&proto)) return SLAMGPU_CELL_AFFINE;
+  if (dynamic_cast<const TbmOccConsistentCell *>(&proto)) return SLAMGPU_CELL_TBM_CONSISTENT;
+  if (dynamic_cast<const TbmUnknownEvenOccCell *>(&proto)) return SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
+  if (dynamic_cast<const GmappingBaseCell *>(&proto)) return SLAMGPU_CELL_GMAPPING;
+  return SLAMGPU_CELL_LWW;  // GridCell itself (last write wins) and test doubles built on it
+}
+
+// Host view of one device cell record, handed out by CudaGridMap::operator[] (publishers, PGM dumps,
+// tests read occupancy()/is_unknown() from it; nothing on the hot path does).
+class MirrorCell : public GridCell {
+public:
+  MirrorCell() : GridCell{Occupancy{0.5, 1}}, _model{SLAMGPU_CELL_LWW} { std::memset(_rec, 0, sizeof _rec); }
+  MirrorCell(int model, const double *rec) : GridCell{occupancy_of(model, rec)}, _model{model} {
+    std::memcpy(_rec, rec, sizeof _rec);
+    if (!unknown_of(model, rec)) { on_update(); }
+  }
+  std::unique_ptr<GridCell> clone() const override { return std::make_unique<MirrorCell>(*this); }
+  void operator+=(const AreaOccupancyObservation &) override {
+    throw std::logic_error("MirrorCell is read-only: update the CudaGridMap, not the cell");
+  }
+  double discrepancy(const AreaOccupancyObservation &aoo) const override {
+    switch (_model) {
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: {
+      TbmOccConsistentCell probe;  // the formula only needs the belief, restored through the public deserializer
+      Serializer s(GridCell::serialize());
+      s << _rec[2] << _rec[3] << _rec[4] << 0.0;
+      probe.deserialize(s.result());
+      return probe.discrepancy(aoo);
+    }
+    case SLAMGPU_CELL_GMAPPING: {
+      auto d = std::pow(_rec[1] - aoo.obstacle.x, 2) + std::pow(_rec[2] - aoo.obstacle.y, 2);
+      return 1.0 - std::exp(-d / 0.05);
+    }
+    default: return GridCell::discrepancy(aoo);
+    }
+  }
+  int model() const { return _model; }
+  const double *record() const { return _rec; }
+
+  static Occupancy occupancy_of(int model, const double *r) {
+    switch (model) {
+    case SLAMGPU_CELL_LWW: return Occupancy{r[0], r[1]};
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: return Occupancy{r[0], r[1]};
+    default: return Occupancy{r[0], 1};
+    }
+  }
+  static bool unknown_of(int model, const double *r) {
+    switch (model) {
+    case SLAMGPU_CELL_LWW: return r[2] == 0;
+    case SLAMGPU_CELL_AFFINE: return r[1] == 0;
+    case SLAMGPU_CELL_MEAN: return r[1] == 0;
+    case SLAMGPU_CELL_GMAPPING: return r[4] == 0;
+    default: return r[5] == 0;
+    }
+  }
+private:
+  int _model;
+  double _rec[SLAMGPU_MAX_STRIDE];
+};
+
+// what a scan adder needs to hand to the device with each beam
+struct AdderParams {
+  slamgpu_estimator est;
+  double blur = 0;
+  double max_range = std::numeric_limits<double>::infinity();
+  bool operator==(const AdderParams &o) const {
+    return std::memcmp(&est, &o.est, sizeof est) == 0 && blur == o.blur && max_range == o.max_range;
+  }
+};
+
+//============================================================================//
+// CudaGridMap: GridMap whose cells live in HBM.  Growth follows the reference's unbounded maps
+// (SLAMGPU_GROW_PLAIN = UnboundedPlainGridMap, SLAMGPU_GROW_TILED = UnboundedLazyTiledGridMap,
+// SLAMGPU_GROW_NONE = PlainGridMap).
+class CudaGridMap : public GridMap {
+public:
+  CudaGridMap(std::shared_ptr<Context> ctx, std::shared_ptr<GridCell> prototype, const GridMapParams &params = MapValues::gmp,
+              int grow = SLAMGPU_GROW_PLAIN)
+    : GridMap{prototype, params}, _ctx{ctx}, _model{cell_model_of(*prototype)}, _grow{grow} {
+    _ctx->check(slamgpu_map_create(_ctx->handle(), params.width_cells, params.height_cells, params.meters_per_cell, _model, grow,
+                                   nullptr, &_map));
+    _stride = slamgpu_model_stride(_model);
+    slamgpu_default_unknown(_model, _unknown_rec);
+    _unknown_cell = MirrorCell(_model, _unknown_rec);
+    refresh_info();
+  }
+  ~CudaGridMap() override { slamgpu_map_destroy(_map); }
+  CudaGridMap(const CudaGridMap &) = delete;
+  CudaGridMap &operator=(const CudaGridMap &) = delete;
+
+  // ---- RegularSquaresGrid
+  int width() const override { flush(); return _w; }
+  int height() const override { flush(); return _h; }
+  DiscretePoint2D origin() const override { flush(); return DiscretePoint2D{_ox, _oy}; }
+  bool has_cell(const Coord &c) const override {
+    if (_grow != SLAMGPU_GROW_NONE) { return true; }  // unbounded maps: plain_grid_map.h:77
+    return GridMap::has_cell(c);
+  }
+
+  // ---- GridMap
+  const GridCell &operator[](const Coord &c) const override {
+    flush();
+    int ix = c.x + _ox, iy = c.y + _oy;
+    if (ix < 0 || ix >= _w || iy < 0 || iy >= _h) { return _unknown_cell; }
+    ensure_mirror();
+    MirrorCell &slot = _ring[_ring_next++ % _ring.size()];  // valid until kRing more lookups
+    slot = MirrorCell(_model, _mirror.data() + ((size_t)iy * _w + ix) * _stride);
+    return slot;
+  }
+  void update(const Coord &c, const AreaOccupancyObservation &aoo) override {
+    flush();
+    _ctx->check(slamgpu_map_update_cell(_map, c.x, c.y, aoo.is_occupied, aoo.occupancy.prob_occ, aoo.occupancy.estimation_quality,
+                                        aoo.obstacle.x, aoo.obstacle.y, aoo.quality));
+    touched();
+  }
+  void reset(const Coord &c, const GridCell &cell) override {
+    flush();
+    double rec[SLAMGPU_MAX_STRIDE];
+    record_of(cell, rec);
+    _ctx->check(slamgpu_map_reset_cell(_map, c.x, c.y, rec));
+    touched();
+  }
+
+  // ---- device side
+  std::shared_ptr<Context> context() const { return _ctx; }
+  slamgpu_map *device() const { flush(); return _map; }
+  int cell_model() const { return _model; }
+  // dense copy of the records, [h][w][stride]
+  const std::vector<double> &records() const { flush(); ensure_mirror(); return _mirror; }
+
+  // GridMapScanAdder::handle_scan_point arguments, queued until the map is next looked at
+  void queue_beam(bool is_occ, double quality, const Segment2D &beam, const AdderParams &p) {
+    if (!_q_occ.empty() && (!(p == _q_params) || beam.beg().x != _q_beams[0] || beam.beg().y != _q_beams[1])) { flush(); }
+    _q_params = p;
+    _q_beams.push_back(beam.beg().x); _q_beams.push_back(beam.beg().y);
+    _q_beams.push_back(beam.end().x); _q_beams.push_back(beam.end().y);
+    _q_occ.push_back(is_occ ? 1 : 0);
+    _q_quality.push_back(quality);
+  }
+  void flush() const {
+    if (_q_occ.empty()) { return; }
+    std::vector<double> beams;
+    std::vector<uint8_t> occ;
+    std::vector<double> quality;
+    beams.swap(_q_beams); occ.swap(_q_occ); quality.swap(_q_quality);  // re-entrancy: the queue is empty from here on
+    int64_t n = 0;
+    _ctx->check(slamgpu_append_beams(_ctx->handle(), _map, (int32_t)occ.size(), beams.data(), occ.data(), quality.data(),
+                                     &_q_params.est, _q_params.blur, _q_params.max_range, &n));
+    _cells_updated += n;
+    const_cast<CudaGridMap *>(this)->touched();
+  }
+  int64_t cells_updated() const { return _cells_updated; }
+
+private:
+  void touched() { _mirror_valid = false; refresh_info(); }
+  void refresh_info() const {
+    int32_t st;
+    double sc;
+    _ctx->check(slamgpu_map_info(_map, &_w, &_h, &sc, &_ox, &_oy, &st));
+  }
+  void ensure_mirror() const {
+    if (_mirror_valid) { return; }
+    _mirror.resize((size_t)_w * _h * _stride);
+    _ctx->check(slamgpu_map_download(_map, _mirror.data()));
+    _mirror_valid = true;
+  }
+  void record_of(const GridCell &cell, double *rec) const {
+    std::memcpy(rec, _unknown_rec, sizeof _unknown_rec);
+    if (auto m = dynamic_cast<const MirrorCell *>(&cell)) { std::memcpy(rec, m->record(), sizeof _unknown_rec); return; }
+    if (cell.is_unknown()) { return; }
+    const Occupancy &o = cell.occupancy();
+    switch (_model) {
+    case SLAMGPU_CELL_LWW: rec[0] = o.prob_occ; rec[1] = o.estimation_quality; rec[2] = 1; return;
+    case SLAMGPU_CELL_AFFINE: rec[0] = o.prob_occ; rec[1] = 1; return;
+    case SLAMGPU_CELL_TBM_CONSISTENT:
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN:
+      if (auto t = dynamic_cast<const TbmBaseCell *>(&cell)) {
+        rec[0] = o.prob_occ; rec[1] = o.estimation_quality;
+        rec[2] = t->belief().unknown(); rec[3] = t->belief().empty(); rec[4] = t->belief().occupied(); rec[5] = 1;
+        return;
+      }
+      break;
+    default: break;
+    }
+    // MeanProbabilityCell / GmappingBaseCell keep their counters private: a written cell of those
+    // classes cannot be moved onto the device through the public API
+    throw std::logic_error("CudaGridMap::reset: cannot take over a known cell of this class");
+  }
+
+private:
+  static constexpr std::size_t kRing = 4096;
+  std::shared_ptr<Context> _ctx;
+  slamgpu_map *_map = nullptr;
+  int _model, _grow, _stride = 0;
+  double _unknown_rec[SLAMGPU_MAX_STRIDE];
+  MirrorCell _unknown_cell;
+  mutable int32_t _w = 0, _h = 0, _ox = 0, _oy = 0;
+  mutable std::vector<double> _mirror;
+  mutable bool _mirror_valid = false;
+  mutable std::vector<MirrorCell> _ring = std::vector<MirrorCell>(kRing);
+  mutable std::size_t _ring_next = 0;
+  mutable std::vector<double> _q_beams, _q_quality;
+  mutable std::vector<uint8_t> _q_occ;
+  mutable AdderParams _q_params;
+  mutable int64_t _cells_updated = 0;
+};
+
+//============================================================================//
+// CudaScanAdder: WallDistanceBlurringScanAdder on the device.  GridMapScanAdder::append_scan is not
+// virtual (grid_map_scan_adders.h:54); it walks the scan on the host (libm trig, mapping quality) and
+// calls handle_scan_point per beam, which here only queues the beam on the CudaGridMap; the map
+// inserts the whole scan with one slamgpu_append_beams call the next time anybody looks at it.
+class CudaScanAdder : public GridMapScanAdder {
+public:
+  struct Properties {
+    int estimator = SLAMGPU_EST_CONST;  // SLAMGPU_EST_CONST | SLAMGPU_EST_AREA
+    Occupancy base_occupied{0.95, 1.0}, base_empty{0.01, 1.0};
+    double low_qual = 0.01, unknown_qual = 0.5;  // area estimator only
+    double blur_distance = 0;
+    double max_usable_range = std::numeric_limits<double>::infinity();
+    std::shared_ptr<ObservationMappingQualityEstimator> observation_quality_estimator = std::make_shared<IdleOMQE>();
+  };
+  explicit CudaScanAdder(const Properties &p) : GridMapScanAdder{make_estimator(p), p.observation_quality_estimator}, _props{p} {
+    std::memset(&_params.est, 0, sizeof _params.est);
+    _params.est.type = p.estimator;
+    _params.est.occ_p = p.base_occupied.prob_occ; _params.est.occ_q = p.base_occupied.estimation_quality;
+    _params.est.empty_p = p.base_empty.prob_occ; _params.est.empty_q = p.base_empty.estimation_quality;
+    _params.est.low_qual = p.low_qual; _params.est.unknown_qual = p.unknown_qual;
+    _params.est.shift_amount = -1;
+    _params.blur = p.blur_distance;
+    _params.max_range = p.max_usable_range;
+  }
+protected:
+  void handle_scan_point(GridMap &map, bool is_occ, double scan_quality, const Segment2D &beam) const override {
+    auto *cm = dynamic_cast<CudaGridMap *>(&map);
+    if (!cm) { throw std::logic_error("CudaScanAdder updates a CudaGridMap only (there is no CPU fallback)"); }
+    if (_params.est.type == SLAMGPU_EST_AREA && _params.est.shift_amount < 0) {
+      // AreaOccupancyEstimator::ensure_segment_not_on_edge keeps a function-static shift computed from
+      // the first cell it ever sees (area_occupancy_estimator.h:71): the obstacle cell of the first beam
+      auto c = map.world_to_cell(beam.end());
+      auto b = map.world_cell_bounds(c);
+      _params.est.shift_amount = area_shift_amount(_props.low_qual * b.side());
+    }
+    cm->queue_beam(is_occ, scan_quality, beam, _params);
+  }
+private:
+  static std::shared_ptr<CellOccupancyEstimator> make_estimator(const Properties &p) {
+    if (p.estimator == SLAMGPU_EST_AREA) {
+      return std::make_shared<AreaOccupancyEstimator>(p.base_occupied, p.base_empty, p.low_qual, p.unknown_qual);
+    }
+    return std::make_shared<ConstOccupancyEstimator>(p.base_occupied, p.base_empty);
+  }
+  static double area_shift_amount(double first) {
+    static double shift = first;  // process-wide and fixed by its first use, like the reference's static
+    return shift;
+  }
+  Properties _props;
+  mutable AdderParams _params;
+};
+
+//============================================================================//
+// scan scoring set-up shared by the matchers
+
+struct ScoreSetup {
+  int oope = SLAMGPU_OOPE_OBSTACLE, oie = SLAMGPU_OIE_DISCREPANCY;
+  double gm_fullness_th = 0.1;
+  int gm_window = 1;
+  bool generic_oie = false;  // an OIE class this header does not know: score through a host-built LUT
+};
+
+// which kernels reproduce this estimator chain (the GMapping OOPE keeps its parameters private:
+// pass a ScoreSetup explicitly for it)
+inline ScoreSetup detect_score_setup(const ScanProbabilityEstimator &spe) {
+  ScoreSetup s;
+  auto oope = spe.occupancy_observation_probability_estimator();
+  if (dynamic_cast<const ObstacleBasedOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_OBSTACLE;
+  else if (dynamic_cast<const MaxOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_MAX;
+  else if (dynamic_cast<const MeanOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_MEAN;
+  else if (dynamic_cast<const OverlapWeightedOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_OVERLAP;
+  else if (dynamic_cast<const GmappingOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_GMAPPING;
+  else throw std::logic_error("slamgpu: unknown OccupancyObservationProbabilityEstimator class");
+  auto oie = oope->impact_estimator();
+  if (dynamic_cast<const DiscrepancyOIE *>(oie.get())) s.oie = SLAMGPU_OIE_DISCREPANCY;
+  else if (dynamic_cast<const OccupancyOIE *>(oie.get())) s.oie = SLAMGPU_OIE_OCCUPANCY;
+  else if (s.oope != SLAMGPU_OOPE_GMAPPING) s.generic_oie = true;
+  return s;
+}
+
+// the device view of the map a matcher was given: a CudaGridMap is used in place; any other GridMap
+// is snapshotted as a score LUT evaluated with the reference's own OIE (slow: a host pass per call)
+class MapBinding {
+public:
+  explicit MapBinding(std::shared_ptr<Context> ctx) : _ctx{ctx} {}
+  ~MapBinding() { if (_snapshot) slamgpu_map_destroy(_snapshot); }
+  slamgpu_map *bind(const GridMap &map, const ScanProbabilityEstimator &spe, const ScoreSetup &setup) {
+    if (auto cm = dynamic_cast<const CudaGridMap *>(&map)) {
+      if (setup.generic_oie) throw std::logic_error("slamgpu: a custom ObservationImpactEstimator needs a host map");
+      return cm->device();
+    }
+    if (setup.oope == SLAMGPU_OOPE_GMAPPING) throw std::logic_error("slamgpu: the GMapping OOPE gathers cell records: use a CudaGridMap");
+    const int w = map.width(), h = map.height();
+    const auto org = map.origin();
+    if (!_snapshot) {
+      _ctx->check(slamgpu_map_create(_ctx->handle(), w, h, map.scale(), SLAMGPU_CELL_LWW, SLAMGPU_GROW_NONE, nullptr, &_snapshot));
+    }
+    auto oie = spe.occupancy_observation_probability_estimator()->impact_estimator();
+    _lut.resize((size_t)w * h);
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x)
+        _lut[(size_t)y * w + x] = oie->estimate_obstacle_impact(map[GridMap::Coord{x - org.x, y - org.y}]);
+    double unknown = oie->estimate_obstacle_impact(*map.new_cell());
+    _ctx->check(slamgpu_map_upload_lut(_snapshot, setup.generic_oie ? 0 : setup.oie, _lut.data(), unknown, w, h, org.x, org.y));
+    return _snapshot;
+  }
+private:
+  std::shared_ptr<Context> _ctx;
+  slamgpu_map *_snapshot = nullptr;
+  std::vector<double> _lut;
+};
+
+// filtered scan -> device (weights are the SPE's own ScanPointWeighting, evaluated once per scan)
+class ScanBinding {
+public:
+  explicit ScanBinding(std::shared_ptr<Context> ctx) : _ctx{ctx} { _ctx->check(slamgpu_scan_create(_ctx->handle(), &_scan)); }
+  ~ScanBinding() { slamgpu_scan_destroy(_scan); }
+  slamgpu_scan *upload(const LaserScan2D &scan, const ScanPointWeighting &spw) {
+    const auto &pts = scan.points();
+    const std::size_t n = pts.size();
+    _a.resize(n); _b.resize(n); _w.resize(n); _f.resize(n); _occ.resize(n);
+    bool factor = false;
+    for (std::size_t i = 0; i < n; ++i) {
+      _a[i] = pts[i].range(); _b[i] = pts[i].angle();
+      _w[i] = spw.weight(pts, i);
+      _f[i] = pts[i].factor(); factor |= _f[i] != 1.0;
+      _occ[i] = pts[i].is_occupied() ? 1 : 0;
+    }
+    _ctx->check(slamgpu_scan_upload(_scan, (int32_t)n, 0, _a.data(), _b.data(), _occ.data(), factor ? _f.data() : nullptr, _w.data()));
+    return _scan;
+  }
+private:
+  std::shared_ptr<Context> _ctx;
+  slamgpu_scan *_scan = nullptr;
+  std::vector<double> _a, _b, _w, _f;
+  std::vector<uint8_t> _occ;
+};
+
+inline slamgpu_spe_params make_spe_params(const ScoreSetup &s, int trig_mode) {
+  slamgpu_spe_params p;
+  std::memset(&p, 0, sizeof p);
+  p.oope = s.oope; p.oie = s.generic_oie ? 0 : s.oie;
+  p.trig_mode = trig_mode;
+  p.gm_fullness_th = s.gm_fullness_th; p.gm_window = s.gm_window;
+  return p;
+}
+
+//============================================================================//
+// Base of the CUDA matchers: PoseEnumerationScanMatcher::process_scan
+// (pose_enumeration_scan_matcher.h:31-77) with the candidate loop on the device.
+class CudaScanMatcherBase : public GridScanMatcher {
+public:
+  CudaScanMatcherBase(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
+                      std::shared_ptr<ScanPointWeighting> spw, int trig_mode = SLAMGPU_TRIG_DEVICE)
+    : GridScanMatcher{spe}, _ctx{ctx}, _spw{spw}, _setup{detect_score_setup(*spe)}, _trig_mode{trig_mode}
+    , _map_binding{ctx}, _scan_binding{ctx} {}
+
+  void set_score_setup(const ScoreSetup &s) { _setup = s; }
+  // candidates scored on the device by the last process_scan (the initial pose included)
+  std::size_t poses_tested() const { return _poses_tested; }
+
+protected:
+  struct Prepared { LaserScan2D scan; slamgpu_map *map; slamgpu_scan *dscan; slamgpu_spe_params params; };
+
+  Prepared prepare(const TransformedLaserScan &raw_scan, const RobotPose &init_pose, const GridMap &map) {
+    Prepared p;
+    // WeightedMeanPointProbabilitySPE::filter_scan (host): point filter + resets the shared SPW
+    p.scan = filter_scan(raw_scan.scan, init_pose, map);
+    p.map = _map_binding.bind(map, *scan_probability_estimator(), _setup);
+    p.dscan = _scan_binding.upload(p.scan, *_spw);
+    p.params = make_spe_params(_setup, _trig_mode);
+    return p;
+  }
+  // scores of a pose list, in order
+  std::vector<double> score(const Prepared &p, const std::vector<RobotPose> &poses) {
+    std::vector<double> flat(poses.size() * 3), out(poses.size());
+    for (std::size_t i = 0; i < poses.size(); ++i) { flat[3 * i] = poses[i].x; flat[3 * i + 1] = poses[i].y; flat[3 * i + 2] = poses[i].theta; }
+    int64_t idx; double best;
+    _ctx->check(slamgpu_score_poses(_ctx->handle(), p.map, p.dscan, &p.params, flat.data(), (int64_t)poses.size(),
+                                    -std::numeric_limits<double>::infinity(), out.data(), &idx, &best));
+    _poses_tested += poses.size();
+    return out;
+  }
+  bool has_observers() {
+    bool any = false;
+    do_for_each_observer([&any](ObsPtr) { any = true; });
+    return any;
+  }
+
+  std::shared_ptr<Context> _ctx;
+  std::shared_ptr<ScanPointWeighting> _spw;
+  ScoreSetup _setup;
+  int _trig_mode;
+  MapBinding _map_binding;
+  ScanBinding _scan_binding;
+  std::size_t _poses_tested = 0;
+};
+
+//============================================================================//
+// Any copyable PoseEnumerator, by speculation.  The enumerator decides the next candidate from the
+// current best pose and the accept/reject feedback, so candidates cannot be listed up front in
+// general.  A copy of the enumerator is run ahead as if every candidate were rejected, the whole
+// speculated list is scored in one launch, and the real enumerator is then replayed over the scores
+// up to (and including) the first accepted candidate, where speculation restarts.  The replay makes
+// exactly the calls the reference loop makes (next / feedback / observers, same order, same
+// arguments), so enumerator quirks are inherited rather than re-implemented.  Batches = accepts + 1.
+template <typename PE>
+class CudaPoseEnumerationScanMatcher : public CudaScanMatcherBase {
+public:
+  CudaPoseEnumerationScanMatcher(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
+                                 std::shared_ptr<ScanPointWeighting> spw, const PE &pe, int trig_mode = SLAMGPU_TRIG_DEVICE,
+                                 std::size_t max_batch = 1 << 16)
+    : CudaScanMatcherBase{ctx, spe, spw, trig_mode}, _pe{pe}, _max_batch{max_batch} {}
+
+  void set_pose_enumerator(const PE &pe) { _pe = pe; }
+  void reset_state() override { _pe.reset(); }
+
+  double process_scan(const TransformedLaserScan &raw_scan, const RobotPose &init_pose, const GridMap &map,
+                      RobotPoseDelta &pose_delta) override {
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_start(init_pose, raw_scan, map); });
+    _poses_tested = 0;
+    auto prep = prepare(raw_scan, init_pose, map);
+    const LaserScan2D &scan = prep.scan;
+    auto best_pose = init_pose;
+    double best_pose_prob = score(prep, {best_pose})[0];
+    do_for_each_observer([&](ObsPtr obs) {
+      obs->on_scan_test(best_pose, scan, best_pose_prob);
+      obs->on_pose_update(best_pose, scan, best_pose_prob);
+    });
+    _pe.reset();
+    std::vector<RobotPose> batch;
+    while (_pe.has_next()) {
+      // speculate: everything after the current state, assuming rejections only
+      PE ahead = _pe;
+      batch.clear();
+      while (ahead.has_next() && batch.size() < _max_batch) {
+        batch.push_back(ahead.next(best_pose));
+        ahead.feedback(false);
+      }
+      auto probs = score(prep, batch);
+      // replay on the real enumerator
+      for (std::size_t k = 0; k < batch.size(); ++k) {
+        auto sampled_pose = _pe.next(best_pose);
+        if (sampled_pose.x != batch[k].x || sampled_pose.y != batch[k].y || sampled_pose.theta != batch[k].theta) {
+          throw std::logic_error("slamgpu: the pose enumerator is not reproducible from a copy");
+        }
+        double sampled_scan_prob = probs[k];
+        do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(sampled_pose, scan, sampled_scan_prob); });
+        auto pose_is_acceptable = best_pose_prob < sampled_scan_prob;
+        _pe.feedback(pose_is_acceptable);
+        if (!pose_is_acceptable) { continue; }
+        best_pose_prob = sampled_scan_prob;
+        best_pose = sampled_pose;
+        do_for_each_observer([&](ObsPtr obs) { obs->on_pose_update(best_pose, scan, best_pose_prob); });
+        break;  // the speculation past this point assumed a rejection
+      }
+    }
+    pose_delta = best_pose - init_pose;
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(pose_delta, scan, best_pose_prob); });
+    return best_pose_prob;
+  }
+private:
+  PE _pe;
+  std::size_t _max_batch;
+};
+
+using HillClimbingPoseEnumerator = FailedRoundsLimitedPoseEnumerator<Distorsion1DPoseEnumerator>;
+
+// MonteCarloScanMatcher (monte_carlo_scan_matcher.h:84-100) on the device
+class CudaMonteCarloScanMatcher : public CudaPoseEnumerationScanMatcher<GaussianPoseEnumerator> {
+public:
+  CudaMonteCarloScanMatcher(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
+                            std::shared_ptr<ScanPointWeighting> spw, unsigned seed, double translation_dispersion,
+                            double rotation_dispersion, unsigned failed_attempts_per_dispersion, unsigned total_attempts)
+    : CudaPoseEnumerationScanMatcher{ctx, spe, spw,
+                                     GaussianPoseEnumerator{seed, translation_dispersion, rotation_dispersion,
+                                                            failed_attempts_per_dispersion, total_attempts}} {}
+};
+
+// HillClimbingScanMatcher (hill_climbing_scan_matcher.h:128-170) on the device
+class CudaHillClimbingScanMatcher : public CudaPoseEnumerationScanMatcher<HillClimbingPoseEnumerator> {
+public:
+  CudaHillClimbingScanMatcher(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
+                              std::shared_ptr<ScanPointWeighting> spw, unsigned max_lookup_failed_attempts,
+                              double translation_delta, double rotation_delta)
+    : CudaPoseEnumerationScanMatcher{ctx, spe, spw,
+                                     HillClimbingPoseEnumerator{max_lookup_failed_attempts, translation_delta, rotation_delta}} {}
+};
+
+//============================================================================//
+// BruteForceScanMatcher (brute_force_scan_matcher.h:68-80) on the device.  The candidate set of
+// BruteForcePoseEnumerator is the Cartesian product of three value lists, each built by FP
+// accumulation with its own stop rule (:42-54); it ignores the feedback, so the whole set is scored by
+// one launch of the grid kernel and the accept loop collapses to its arg-max (lowest index on ties).
+// Observers, if any, still get on_scan_test for every candidate in order.
+class CudaBruteForceScanMatcher : public CudaScanMatcherBase {
+public:
+  CudaBruteForceScanMatcher(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
+                            std::shared_ptr<ScanPointWeighting> spw, double from_x, double to_x, double step_x, double from_y,
+                            double to_y, double step_y, double from_t, double to_t, double step_t,
+                            int trig_mode = SLAMGPU_TRIG_DEVICE)
+    : CudaScanMatcherBase{ctx, spe, spw, trig_mode}
+    , _dx{axis(from_x, to_x, step_x, false)}, _dy{axis(from_y, to_y, step_y, false)}, _dt{axis(from_t, to_t, step_t, true)} {}
+
+  double process_scan(const TransformedLaserScan &raw_scan, const RobotPose &init_pose, const GridMap &map,
+                      RobotPoseDelta &pose_delta) override {
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_start(init_pose, raw_scan, map); });
+    _poses_tested = 0;
+    auto prep = prepare(raw_scan, init_pose, map);
+    const LaserScan2D &scan = prep.scan;
+    auto best_pose = init_pose;
+    double best_pose_prob = score(prep, {best_pose})[0];
+    do_for_each_observer([&](ObsPtr obs) {
+      obs->on_scan_test(best_pose, scan, best_pose_prob);
+      obs->on_pose_update(best_pose, scan, best_pose_prob);
+    });
+    // the enumerator keeps the base pose of its first ever use (reset() does not clear it)
+    if (!_base_pose_is_set) { _base_pose = init_pose; _base_pose_is_set = true; }
+    std::vector<double> xs(_dx.size()), ys(_dy.size()), ts(_dt.size());
+    for (std::size_t i = 0; i < xs.size(); ++i) xs[i] = _base_pose.x + _dx[i];
+    for (std::size_t i = 0; i < ys.size(); ++i) ys[i] = _base_pose.y + _dy[i];
+    for (std::size_t i = 0; i < ts.size(); ++i) ts[i] = _base_pose.theta + _dt[i];
+    const std::size_t P = xs.size() * ys.size() * ts.size();
+    const bool observed = has_observers();
+    std::vector<double> probs(observed ? P : 0);
+    int64_t idx = -1;
+    double best = best_pose_prob;
+    if (prep.params.oope == SLAMGPU_OOPE_OBSTACLE) {
+      _ctx->check(slamgpu_score_grid(_ctx->handle(), prep.map, prep.dscan, &prep.params, xs.data(), (int32_t)xs.size(), ys.data(),
+                                     (int32_t)ys.size(), ts.data(), (int32_t)ts.size(), best_pose_prob,
+                                     observed ? probs.data() : nullptr, &idx, &best));
+    } else {  // window / GMapping OOPEs: the list kernel over the expanded product
+      std::vector<double> flat(P * 3);
+      std::size_t k = 0;
+      for (double t : ts) for (double y : ys) for (double x : xs) { flat[k++] = x; flat[k++] = y; flat[k++] = t; }
+      _ctx->check(slamgpu_score_poses(_ctx->handle(), prep.map, prep.dscan, &prep.params, flat.data(), (int64_t)P, best_pose_prob,
+                                      observed ? probs.data() : nullptr, &idx, &best));
+    }
+    _poses_tested += P;
+    auto pose_at = [&](std::size_t i) {
+      const std::size_t nx = xs.size(), ny = ys.size();
+      return RobotPose{xs[i % nx], ys[(i / nx) % ny], ts[i / (nx * ny)]};
+    };
+    if (observed) {  // the reference's notifications, candidate by candidate
+      for (std::size_t i = 0; i < P; ++i) {
+        auto sampled_pose = pose_at(i);
+        double sampled_scan_prob = probs[i];
+        do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(sampled_pose, scan, sampled_scan_prob); });
+        if (!(best_pose_prob < sampled_scan_prob)) { continue; }
+        best_pose_prob = sampled_scan_prob;
+        best_pose = sampled_pose;
+        do_for_each_observer([&](ObsPtr obs) { obs->on_pose_update(best_pose, scan, best_pose_prob); });
+      }
+    } else if (idx >= 0) {
+      best_pose = pose_at((std::size_t)idx);
+      best_pose_prob = best;
+    }
+    pose_delta = best_pose - init_pose;
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(pose_delta, scan, best_pose_prob); });
+    return best_pose_prob;
+  }
+private:
+  // the values one axis of BruteForcePoseEnumerator takes: x / y are stepped while v < to (after the
+  // value was used), theta is used while t <= to
+  static std::vector<double> axis(double from, double to, double step, bool top_level) {
+    std::vector<double> v;
+    double cur = from;
+    if (top_level) {
+      while (cur <= to) { v.push_back(cur); cur += step; }
+    } else {
+      for (;;) {
+        v.push_back(cur);
+        if (!(cur < to)) { break; }
+        cur += step;
+      }
+    }
+    return v;
+  }
+  std::vector<double> _dx, _dy, _dt;
+  bool _base_pose_is_set = false;
+  RobotPose _base_pose;
+};
+
+}  // namespace slamgpu

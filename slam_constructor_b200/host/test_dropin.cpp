@@ -1,0 +1,226 @@
+// test_dropin.cpp -- the reference's own world classes with the CUDA plug-ins swapped in, run side
+// by side with the unmodified CPU classes on the same synthetic scans; every pose and every map cell
+// must be identical.  Built here against the reference headers (host/Makefile), run on the GPU box by
+// tests/test_gpu_dropin.py.
+#include <cstdio>
+#include <random>
+
+#include "slamgpu_backend.h"
+#include "src/core/maps/plain_grid_map.h"
+#include "src/core/states/single_state_hypothesis_laser_scan_grid_world.h"
+
+namespace {
+
+int g_failed = 0;
+#define CHECK(cond, ...)                                      \
+  do {                                                        \
+    if (!(cond)) {                                            \
+      ++g_failed;                                             \
+      std::printf("FAIL %s:%d %s | ", __FILE__, __LINE__, #cond); \
+      std::printf(__VA_ARGS__);                               \
+      std::printf("\n");                                      \
+    }                                                         \
+  } while (0)
+
+// a laser scan of a rectangular room (|x| < hw, |y| < hh) taken from `pose`
+LaserScan2D room_scan(const RobotPose &pose, int n, double fov, double hw, double hh, std::mt19937 &rng, double noise) {
+  LaserScan2D scan;
+  std::normal_distribution<double> nd(0.0, noise);
+  for (int i = 0; i < n; ++i) {
+    double a = -fov / 2 + fov * i / n;
+    double c = std::cos(a + pose.theta), s = std::sin(a + pose.theta);
+    double tx = c > 0 ? (hw - pose.x) / c : (c < 0 ? (-hw - pose.x) / c : 1e300);
+    double ty = s > 0 ? (hh - pose.y) / s : (s < 0 ? (-hh - pose.y) / s : 1e300);
+    double r = std::min(tx, ty) + nd(rng);
+    bool occ = (i % 37) != 5;  // a few "no return" beams
+    scan.points().push_back(ScanPoint2D::make_polar(r, a, occ));
+  }
+  return scan;
+}
+
+struct Config {
+  const char *name;
+  int map_cells; double scale;
+  std::shared_ptr<GridCell> proto;
+  int estimator; Occupancy occ, empty;
+  double blur;
+  int matcher;  // 0 MC, 1 HC, 2 BF
+  int weighting; // 0 even, 1 viny
+  int beams; double fov;
+  int steps;
+  double loc_q, raw_q;
+};
+
+std::shared_ptr<ScanPointWeighting> make_spw(int kind) {
+  if (kind == 1) return std::make_shared<VinySlamSPW>();
+  return std::make_shared<EvenSPW>();
+}
+
+std::shared_ptr<ScanProbabilityEstimator> make_spe(std::shared_ptr<ScanPointWeighting> spw) {
+  auto oope = std::make_shared<ObstacleBasedOccupancyObservationPE>(std::make_shared<DiscrepancyOIE>());
+  return std::make_shared<WeightedMeanPointProbabilitySPE>(oope, spw);
+}
+
+bool same_cells(const GridMap &a, const GridMap &b, const char *what) {
+  bool ok = a.width() == b.width() && a.height() == b.height() && a.origin().x == b.origin().x && a.origin().y == b.origin().y;
+  CHECK(ok, "%s: geometry %dx%d@(%d,%d) vs %dx%d@(%d,%d)", what, a.width(), a.height(), a.origin().x, a.origin().y, b.width(),
+        b.height(), b.origin().x, b.origin().y);
+  if (!ok) return false;
+  long bad = 0, known = 0;
+  auto org = a.origin();
+  for (int y = 0; y < a.height(); ++y)
+    for (int x = 0; x < a.width(); ++x) {
+      GridMap::Coord c{x - org.x, y - org.y};
+      const auto &ca = a[c];
+      Occupancy oa = ca.occupancy();
+      bool ua = ca.is_unknown();
+      const auto &cb = b[c];
+      Occupancy obb = cb.occupancy();
+      known += !ua;
+      if (ua != cb.is_unknown() || oa.prob_occ != obb.prob_occ || oa.estimation_quality != obb.estimation_quality) {
+        if (bad++ < 3) std::printf("  cell (%d,%d): %.17g/%.17g/%d vs %.17g/%.17g/%d\n", c.x, c.y, oa.prob_occ, oa.estimation_quality,
+                                   (int)ua, obb.prob_occ, obb.estimation_quality, (int)cb.is_unknown());
+      }
+    }
+  CHECK(bad == 0, "%s: %ld cells differ", what, bad);
+  CHECK(known > 100, "%s: only %ld known cells", what, known);
+  return bad == 0;
+}
+
+struct CountingObserver : GridScanMatcherObserver {
+  long tests = 0, updates = 0;
+  double last = 0;
+  void on_scan_test(const RobotPose &, const LaserScan2D &, double s) override { ++tests; last = s; }
+  void on_pose_update(const RobotPose &, const LaserScan2D &, double) override { ++updates; }
+};
+
+void run_world_pair(const Config &cfg, std::shared_ptr<slamgpu::Context> ctx) {
+  std::printf("== %s\n", cfg.name);
+  GridMapParams gmp{cfg.map_cells, cfg.map_cells, cfg.scale};
+  // ---- the reference, unmodified
+  auto spw_ref = make_spw(cfg.weighting);
+  auto spe_ref = make_spe(spw_ref);
+  SingleStateHypothesisLSGWProperties pr;
+  pr.localized_scan_quality = cfg.loc_q; pr.raw_scan_quality = cfg.raw_q;
+  pr.grid_map = std::make_shared<UnboundedPlainGridMap>(cfg.proto, gmp);
+  if (cfg.matcher == 0) pr.gsm = std::make_shared<MonteCarloScanMatcher>(spe_ref, 42, 0.2, 0.1, 20, 100);
+  else if (cfg.matcher == 1) pr.gsm = std::make_shared<HillClimbingScanMatcher>(spe_ref, 6, 0.1, 0.1);
+  else pr.gsm = std::make_shared<BruteForceScanMatcher>(spe_ref, -0.3, 0.3, 0.05, -0.3, 0.3, 0.05, -0.1, 0.1, 0.02);
+  std::shared_ptr<CellOccupancyEstimator> est;
+  if (cfg.estimator == SLAMGPU_EST_AREA) est = std::make_shared<AreaOccupancyEstimator>(cfg.occ, cfg.empty);
+  else est = std::make_shared<ConstOccupancyEstimator>(cfg.occ, cfg.empty);
+  pr.gmsa = WallDistanceBlurringScanAdder::builder().set_blur_distance(cfg.blur).set_occupancy_estimator(est)
+              .set_observation_quality_estimator(std::make_shared<IdleOMQE>()).set_max_usable_range(25.0).build();
+  SingleStateHypothesisLaserScanGridWorld ref_world{pr};
+  // ---- the same world class with the CUDA plug-ins
+  auto spw_gpu = make_spw(cfg.weighting);
+  auto spe_gpu = make_spe(spw_gpu);
+  SingleStateHypothesisLSGWProperties pg;
+  pg.localized_scan_quality = cfg.loc_q; pg.raw_scan_quality = cfg.raw_q;
+  pg.grid_map = std::make_shared<slamgpu::CudaGridMap>(ctx, cfg.proto, gmp, SLAMGPU_GROW_PLAIN);
+  if (cfg.matcher == 0) pg.gsm = std::make_shared<slamgpu::CudaMonteCarloScanMatcher>(ctx, spe_gpu, spw_gpu, 42, 0.2, 0.1, 20, 100);
+  else if (cfg.matcher == 1) pg.gsm = std::make_shared<slamgpu::CudaHillClimbingScanMatcher>(ctx, spe_gpu, spw_gpu, 6, 0.1, 0.1);
+  else pg.gsm = std::make_shared<slamgpu::CudaBruteForceScanMatcher>(ctx, spe_gpu, spw_gpu, -0.3, 0.3, 0.05, -0.3, 0.3, 0.05, -0.1, 0.1, 0.02);
+  slamgpu::CudaScanAdder::Properties ap;
+  ap.estimator = cfg.estimator; ap.base_occupied = cfg.occ; ap.base_empty = cfg.empty; ap.blur_distance = cfg.blur;
+  ap.max_usable_range = 25.0;
+  pg.gmsa = std::make_shared<slamgpu::CudaScanAdder>(ap);
+  SingleStateHypothesisLaserScanGridWorld gpu_world{pg};
+
+  auto obs_ref = std::make_shared<CountingObserver>(), obs_gpu = std::make_shared<CountingObserver>();
+  ref_world.add_sm_observer(obs_ref);
+  gpu_world.add_sm_observer(obs_gpu);
+
+  std::mt19937 rng(7);
+  std::normal_distribution<double> odo(0.0, 0.02), odo_t(0.0, 0.01);
+  RobotPose truth{0.3, -0.2, 0.1};
+  // both worlds start at the origin; the first scan is matched against an empty map
+  RobotPose prev = truth;
+  for (int step = 0; step < cfg.steps; ++step) {
+    RobotPoseDelta motion = step == 0 ? RobotPoseDelta{truth.x, truth.y, truth.theta}
+                                      : RobotPoseDelta{0.08 * std::cos(0.3 * step), 0.06 * std::sin(0.2 * step), 0.03};
+    if (step > 0) { truth += motion; }
+    RobotPoseDelta odom = step == 0 ? motion : RobotPoseDelta{motion.x + odo(rng), motion.y + odo(rng), motion.theta + odo_t(rng)};
+    auto scan = room_scan(truth, cfg.beams, cfg.fov, 4.0, 3.0, rng, 0.01);
+    TransformedLaserScan a{odom, scan, 1.0}, b{odom, scan, 1.0};
+    b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();  // no shared mutable state between the two worlds
+    ref_world.handle_sensor_data(a);
+    gpu_world.handle_sensor_data(b);
+    const RobotPose &p1 = ref_world.pose(), &p2 = gpu_world.pose();
+    CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "%s step %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)", cfg.name,
+          step, p1.x, p1.y, p1.theta, p2.x, p2.y, p2.theta);
+    CHECK(obs_ref->tests == obs_gpu->tests && obs_ref->updates == obs_gpu->updates && obs_ref->last == obs_gpu->last,
+          "%s step %d: observers saw %ld/%ld tests, %ld/%ld updates", cfg.name, step, obs_ref->tests, obs_gpu->tests, obs_ref->updates,
+          obs_gpu->updates);
+    if (step == 1 || step + 1 == cfg.steps) same_cells(ref_world.map(), gpu_world.map(), cfg.name);
+    if (g_failed > 5) return;
+    prev = truth;
+  }
+  std::printf("   %d scans, %ld candidate poses scored on the device, final pose %.6f %.6f %.6f\n", cfg.steps, obs_gpu->tests,
+              gpu_world.pose().x, gpu_world.pose().y, gpu_world.pose().theta);
+}
+
+// a CUDA matcher handed a plain host map of the reference (score-LUT snapshot path)
+void run_host_map(std::shared_ptr<slamgpu::Context> ctx) {
+  std::printf("== CUDA matchers on a reference UnboundedPlainGridMap\n");
+  GridMapParams gmp{200, 200, 0.05};
+  auto map = std::make_shared<UnboundedPlainGridMap>(std::make_shared<TbmUnknownEvenOccCell>(), gmp);
+  auto est = std::make_shared<ConstOccupancyEstimator>(Occupancy{0.95, 0.3}, Occupancy{0.01, 0.1});
+  auto adder = WallDistanceBlurringScanAdder::builder().set_blur_distance(0.2).set_occupancy_estimator(est)
+                 .set_observation_quality_estimator(std::make_shared<IdleOMQE>()).build();
+  std::mt19937 rng(11);
+  RobotPose truth{0.2, 0.1, -0.2};
+  for (int k = 0; k < 3; ++k) {
+    auto s = room_scan(truth, 360, 2 * M_PI, 4.0, 3.0, rng, 0.01);
+    adder->append_scan(*map, truth, s, 1.0);
+  }
+  auto scan = room_scan(truth, 181, 1.5 * M_PI, 4.0, 3.0, rng, 0.005);
+  RobotPose init{truth.x + 0.07, truth.y - 0.05, truth.theta + 0.03};
+  for (int which = 0; which < 3; ++which) {
+    auto spw1 = make_spw(1), spw2 = make_spw(1);
+    auto spe1 = make_spe(spw1), spe2 = make_spe(spw2);
+    std::shared_ptr<GridScanMatcher> m1, m2;
+    if (which == 0) { m1 = std::make_shared<MonteCarloScanMatcher>(spe1, 3, 0.2, 0.1, 20, 100); m2 = std::make_shared<slamgpu::CudaMonteCarloScanMatcher>(ctx, spe2, spw2, 3, 0.2, 0.1, 20, 100); }
+    if (which == 1) { m1 = std::make_shared<HillClimbingScanMatcher>(spe1, 6, 0.1, 0.1); m2 = std::make_shared<slamgpu::CudaHillClimbingScanMatcher>(ctx, spe2, spw2, 6, 0.1, 0.1); }
+    if (which == 2) { m1 = std::make_shared<BruteForceScanMatcher>(spe1, -0.2, 0.2, 0.02, -0.2, 0.2, 0.02, -0.06, 0.06, 0.01); m2 = std::make_shared<slamgpu::CudaBruteForceScanMatcher>(ctx, spe2, spw2, -0.2, 0.2, 0.02, -0.2, 0.2, 0.02, -0.06, 0.06, 0.01); }
+    TransformedLaserScan a{RobotPoseDelta{}, scan, 1.0}, b{RobotPoseDelta{}, scan, 1.0};
+    b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+    RobotPoseDelta d1, d2;
+    double s1 = m1->process_scan(a, init, *map, d1), s2 = m2->process_scan(b, init, *map, d2);
+    CHECK(s1 == s2 && d1.x == d2.x && d1.y == d2.y && d1.theta == d2.theta, "matcher %d: %.17g (%.17g %.17g %.17g) vs %.17g (%.17g %.17g %.17g)",
+          which, s1, d1.x, d1.y, d1.theta, s2, d2.x, d2.y, d2.theta);
+    std::printf("   matcher %d: best %.9f, delta %.4f %.4f %.4f\n", which, s2, d2.x, d2.y, d2.theta);
+  }
+}
+
+}  // namespace
+
+int main() {
+  std::shared_ptr<slamgpu::Context> ctx;
+  try {
+    ctx = std::make_shared<slamgpu::Context>(0);
+  } catch (const slamgpu::Error &e) {
+    std::printf("NO-DEVICE %s\n", e.what());
+    return e.code == SLAMGPU_E_NODEVICE ? 77 : 1;
+  }
+  try {
+    Config tiny{"tinySLAM: mean cell, const estimator, blur 0.5, MC(42, 0.2/0.1, 20, 100), even weights, 360 beams", 100, 0.1,
+                std::make_shared<MeanProbabilityCell>(), SLAMGPU_EST_CONST, {0.95, 1.0}, {0.01, 1.0}, 0.5, 0, 0, 360, 2 * M_PI, 25, 0.9, 0.6};
+    Config viny{"vinySLAM: tbm_consistent cell, const 0.95/0.04 0.01/0.003, blur 0.3, MC, viny weights, 361 beams over 270 deg", 100, 0.1,
+                std::make_shared<TbmOccConsistentCell>(), SLAMGPU_EST_CONST, {0.95, 0.04}, {0.01, 0.003}, 0.3, 0, 1, 361, 1.5 * M_PI, 25, 0.9, 0.6};
+    Config hc{"hill climbing + area estimator: tbm_unknown_even cell, HC(6, 0.1, 0.1), 0.05 m cells, 541 beams", 200, 0.05,
+              std::make_shared<TbmUnknownEvenOccCell>(), SLAMGPU_EST_AREA, {0.95, 0.3}, {0.01, 0.1}, 0.3, 1, 1, 541, 1.5 * M_PI, 15, 0.9, 0.6};
+    Config bf{"brute force: affine cell, area estimator, BF(+-0.3 @0.05, +-0.1 rad @0.02)", 160, 0.05,
+              std::make_shared<AffineQualityMergeCell>(), SLAMGPU_EST_AREA, {0.95, 1.0}, {0.01, 1.0}, 0.2, 2, 0, 181, 1.5 * M_PI, 6, 0.9, 0.6};
+    run_world_pair(tiny, ctx);
+    run_world_pair(viny, ctx);
+    run_world_pair(hc, ctx);
+    run_world_pair(bf, ctx);
+    run_host_map(ctx);
+  } catch (const std::exception &e) {
+    std::printf("FAIL exception: %s\n", e.what());
+    return 1;
+  }
+  std::printf(g_failed ? "RESULT: %d FAILED\n" : "RESULT: ALL PASSED\n", g_failed);
+  return g_failed ? 1 : 0;
+}
