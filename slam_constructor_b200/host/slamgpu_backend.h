@@ -514,10 +514,18 @@ public:
       obs->on_pose_update(best_pose, scan, best_pose_prob);
     });
     _pe.reset();
+    // A copy of an enumerator is only state-identical when it is taken right after reset(): the
+    // Gaussian enumerator clones its random variables without their cached second variate
+    // (random_utils.h:23-25).  So the run-ahead twin is always rebuilt from that clean snapshot by
+    // replaying the calls the real enumerator has received since.
+    const PE clean = _pe;
+    struct Call { RobotPose best; bool accepted; };
+    std::vector<Call> history;
     std::vector<RobotPose> batch;
     while (_pe.has_next()) {
+      PE ahead = clean;
+      for (const Call &c : history) { ahead.next(c.best); ahead.feedback(c.accepted); }
       // speculate: everything after the current state, assuming rejections only
-      PE ahead = _pe;
       batch.clear();
       while (ahead.has_next() && batch.size() < _max_batch) {
         batch.push_back(ahead.next(best_pose));
@@ -526,14 +534,16 @@ public:
       auto probs = score(prep, batch);
       // replay on the real enumerator
       for (std::size_t k = 0; k < batch.size(); ++k) {
-        auto sampled_pose = _pe.next(best_pose);
+        const RobotPose arg = best_pose;
+        auto sampled_pose = _pe.next(arg);
         if (sampled_pose.x != batch[k].x || sampled_pose.y != batch[k].y || sampled_pose.theta != batch[k].theta) {
-          throw std::logic_error("slamgpu: the pose enumerator is not reproducible from a copy");
+          throw std::logic_error("slamgpu: the pose enumerator is not reproducible from a copy taken after reset()");
         }
         double sampled_scan_prob = probs[k];
         do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(sampled_pose, scan, sampled_scan_prob); });
         auto pose_is_acceptable = best_pose_prob < sampled_scan_prob;
         _pe.feedback(pose_is_acceptable);
+        history.push_back(Call{arg, pose_is_acceptable});
         if (!pose_is_acceptable) { continue; }
         best_pose_prob = sampled_scan_prob;
         best_pose = sampled_pose;
