@@ -83,7 +83,7 @@ def bf_axis(base, lo, hi, step, inclusive_le):
     return np.array(vals)
 
 
-def make_workload(seed=42):
+def make_workload(seed=42, theta_blocks=1):
     rng = np.random.default_rng(seed)
     half_w, half_h = 30.0, 22.0
     cells = synth_map(rng, MAP_SIZE, MAP_SCALE, half_w, half_h)
@@ -93,6 +93,12 @@ def make_workload(seed=42):
     xs = bf_axis(base[0], *BF["x"], False)
     ys = bf_axis(base[1], *BF["y"], False)
     ts = bf_axis(base[2], *BF["t"], True)
+    if theta_blocks > 1:  # weak scaling: the theta sweep goes on with the same step, 100 more values per extra GPU
+        vals, v = [], BF["t"][0]
+        while len(vals) < len(ts) * theta_blocks:
+            vals.append(base[2] + v)
+            v += BF["t"][2]
+        ts = np.array(vals)
     return dict(cells=cells, r=r, a=a, base=base, xs=xs, ys=ys, ts=ts)
 
 
@@ -210,7 +216,7 @@ def run_reference_arm(args, cfg):
     sample = "%d consecutive candidates x %d beams per step of the same workload" % (len(poses), N_BEAMS)
     line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
             "cpu_baseline": {"value": value, "unit": cfg["unit"], "cores": thr, "kind": ref.kind, "sample": sample},
             "e2e": {"value": value, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -226,6 +232,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 100 more theta values (1 020 100 more candidates) per extra GPU; strong = the fixed "
+                         "1 020 100 candidates split N ways")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = {"metric": "pose-beam likelihood evaluations/sec (brute-force scan matcher)", "unit": "evals/s",
@@ -233,7 +242,10 @@ def main():
                                   "candidate poses x 1081 beams, 2000x2000 grid @0.05 m, obstacle OOPE, even weights, "
                                   "MeanProbabilityCell map",
                       "candidates": 1020100, "beams": N_BEAMS, "grid": [MAP_SIZE, MAP_SIZE],
-                      "sharding": "candidate rows (theta, y) split contiguously over ranks, map replicated",
+                      "sharding": "candidate rows (theta, y) split contiguously over ranks, map replicated; one 32-byte "
+                                  "all-gather merges the per-rank arg-max",
+                      "scaling_mode": "weak: the theta sweep is extended by 100 values (1020100 candidates) per extra GPU"
+                                      if args.scaling == "weak" else "strong: fixed 1020100 candidates split over ranks",
                       "l2": "flushed (256 MB write) before every timed step" if L2_FLUSH else "not flushed"}}
     if args.impl == "reference":
         return run_reference_arm(args, cfg)
@@ -259,8 +271,9 @@ def main():
         nccl_id = box[0]
     ctx = sg.Context(local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
 
-    wl = make_workload()
+    wl = make_workload(theta_blocks=world if args.scaling == "weak" else 1)
     P = len(wl["xs"]) * len(wl["ys"]) * len(wl["ts"])
+    cfg["config"]["candidates"] = P
     gmap = sg.GridMap(ctx, MAP_SIZE, MAP_SIZE, MAP_SCALE, sg.CELL_MEAN)
     gmap.upload(wl["cells"])
     scan = sg.Scan(ctx, wl["r"], wl["a"])
@@ -342,7 +355,7 @@ def main():
             except ValueError:
                 traffic = None
         line = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
                 "e2e": {"value": evals * e2e_steps / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / e2e_steps},

@@ -34,6 +34,18 @@ SG_DEV bool are_ordered(double a, double b, double c) { return less_or_equal(a, 
 // RegularSquaresGrid::world_to_cell, src/core/maps/regular_squares_grid.h:40-46
 SG_DEV int world_to_cell(double v, double scale) { return (int)floor(div(v, scale)); }
 
+// floor(v / scale) with the reference's rounding (a correctly rounded division, then floor), without
+// paying for the division: floor(v * (1/scale)) is checked against both cell borders with exact FMA
+// residuals, and only a point within a few ulps of a border takes the real division.
+SG_DEV double floor_div(double v, double scale, double inv_scale) {
+  double f = floor(v * inv_scale);
+  const double lo = fma(-f, scale, v);        // v - f*scale, one rounding
+  const double hi = fma(f + 1.0, scale, -v);  // (f+1)*scale - v
+  const double margin = fabs(v) * 8.9e-16 + 1e-300;  // 4 ulp(v): RN(v/scale) cannot cross a border farther than this
+  if (!(lo >= margin && hi >= margin)) f = floor(div(v, scale));
+  return f;
+}
+
 // world_to_cell plus the trig guard: `slack` is an upper bound of |v - v_reference|
 // when v was built from device trigonometry; returns true if the cell could differ.
 SG_DEV int world_to_cell_guard(double v, double scale, double slack, bool *unsafe) {

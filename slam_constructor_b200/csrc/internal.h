@@ -39,6 +39,10 @@ struct Candidates {  // a staged candidate set (device resident)
   int32_t n_groups = 0, rows_per_group = 0;
   int32_t t_lo = 0, t_hi = 0;  // theta planes touched by this rank
   DevBuf cxp, cyp;   // int32 index tables
+  DevBuf cyw;        // v2: packed row words, one per (theta, beam, y-group)
+  int32_t grid_R = 8, ngy = 0;  // rows per thread of the grid kernel, y-groups per (theta, beam)
+  bool grid_v2 = true, force_v1 = false;
+  bool uniform_w = false;
   // trig tables (device), layout given by strides
   DevBuf trc, trs;
   bool trig_is_host = false;

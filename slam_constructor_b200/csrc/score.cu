@@ -78,13 +78,14 @@ __global__ void k_reduce_blocks(const Best *__restrict__ blk, int n, Result *out
 // init_score: the winner must be strictly better than the initial pose's score
 __global__ void k_finalize(const Result *__restrict__ per_rank, int nranks, double init_score, Result *out) {
   double s = -INFINITY;
-  long long i = LLONG_MAX, guard = 0;
+  long long i = LLONG_MAX, guard = 0, enc = 0;
   for (int r = 0; r < nranks; ++r) {
     guard += per_rank[r].guard;
+    enc += per_rank[r].pad;
     if (beats(per_rank[r].score, per_rank[r].idx, s, i)) { s = per_rank[r].score; i = per_rank[r].idx; }
   }
   if (!(init_score < s) || i == LLONG_MAX) { s = init_score; i = -1; }
-  out->score = s; out->idx = i; out->guard = guard; out->pad = 0;
+  out->score = s; out->idx = i; out->guard = guard; out->pad = enc;
 }
 
 // ------------------------------------------------------------------ trig table
@@ -127,6 +128,17 @@ SG_DEV double gmapping_probability(const MapView &m, int cx, int cy, double X, d
   return best;
 }
 
+// exact cell of a world coordinate (+ the device-trig border guard; the tolerance itself need not be exact)
+SG_DEV int grid_cell(double v, double rc, double scale, double inv_scale, int guard, bool *unsafe) {
+  const double f = sg::floor_div(v, scale, inv_scale);
+  if (guard) {
+    const double q = v * inv_scale;
+    const double tol = trig_slack(rc, v) * inv_scale + 8.0 * 2.220446049250313e-16 * fabs(q);
+    if ((q - f) <= tol || ((f + 1.0) - q) <= tol) *unsafe = true;
+  }
+  return cell_of(f);
+}
+
 struct ListArgs {
   MapView map;
   const double *poses;      // 3*Ploc
@@ -151,7 +163,7 @@ __global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
   if (p < a.Ploc) {
     const double px = a.poses[3 * p], py = a.poses[3 * p + 1];
     const int tid = PREROT ? 0 : a.theta_id[p];
-    const double s = a.map.scale;
+    const double s = a.map.scale, inv_s = 1.0 / a.map.scale;
     double total_probability = 0;
     bool unsafe_any = false;
     int cache_x = 0, cache_y = 0;
@@ -167,14 +179,8 @@ __global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
       double prob;
       if (MODE == SLAMGPU_OOPE_OBSTACLE || MODE == SLAMGPU_OOPE_GMAPPING) {
         int cx, cy;
-        if (GUARD) {
-          bool u1, u2;
-          cx = sg::world_to_cell_guard(X, s, trig_slack(rc, X), &u1);
-          cy = sg::world_to_cell_guard(Y, s, trig_slack(rs, Y), &u2);
-          unsafe_any |= u1 | u2;
-        } else {
-          cx = cell_of(floor(sg::div(X, s))); cy = cell_of(floor(sg::div(Y, s)));
-        }
+        cx = grid_cell(X, rc, s, inv_s, GUARD ? 1 : 0, &unsafe_any);
+        cy = grid_cell(Y, rs, s, inv_s, GUARD ? 1 : 0, &unsafe_any);
         if (MODE == SLAMGPU_OOPE_OBSTACLE) {
           prob = lut_at(a.map, cx, cy);
         } else {
@@ -217,36 +223,106 @@ struct GridIdxArgs {
   double scale;
   int guard;
   int *cxp;  // [(tl*N + i)*nx + j]   padded LUT column
-  int *cyp;  // [(tl*N + i)*nyp + k]  padded LUT row * pitch
+  int *cyp;  // [(tl*N + i)*nyp + k]  padded LUT row * pitch            (v1 kernel)
+  unsigned long long *cyw;  // [(tl*N + i)*ngy + gy] packed rows of one y-group (v2 kernel)
+  int v2, R, ngy;
   Result *result;
 };
 
+// v2 row word: low 32 bits = padded LUT row offset of the group's first y, then one signed nibble per
+// further y = (cell row of y_m) - (cell row of y_{m-1}); 0 means "same cell row: reuse the gathered value"
+SG_DEV int nib_sext(unsigned long long w, int m) {  // m in 1..7
+  int v = (int)((w >> (32 + 4 * (m - 1))) & 15ull);
+  return (v ^ 8) - 8;
+}
+
 // one thread per (theta, beam, axis value): the exact world_to_cell of the reference,
 // regular_squares_grid.h:40-46, applied to x_j + r*cos(theta+a) and y_k + r*sin(theta+a)
-__global__ void __launch_bounds__(128) k_grid_indices(GridIdxArgs a) {
-  // blockIdx.x = tl * N + i (one (theta, beam) pair per block); threads cover the nx + nyp axis values
-  const long long ti = blockIdx.x;
-  const int tl = (int)(ti / a.N), i = (int)(ti - (long long)tl * a.N);
-  const long long src = (long long)(a.t_lo + tl) * a.N + i;
-  const double rc = a.trc[src], rs = a.trs[src];
-  bool unsafe_any = false;
-  for (int c = threadIdx.x; c < a.nx + a.nyp; c += blockDim.x) {
-    bool unsafe = false;
-    if (c < a.nx) {
-      double X = sg::add(a.xs[c], rc);
-      int cx = a.guard ? sg::world_to_cell_guard(X, a.scale, trig_slack(rc, X), &unsafe) : cell_of(floor(sg::div(X, a.scale)));
-      a.cxp[ti * a.nx + c] = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
-    } else {
-      int k = c - a.nx;
-      int out = 0;  // padding rows point at the ring row 0 (always valid memory)
-      if (k < a.ny) {
-        double Y = sg::add(a.ys[k], rs);
-        int cy = a.guard ? sg::world_to_cell_guard(Y, a.scale, trig_slack(rs, Y), &unsafe) : cell_of(floor(sg::div(Y, a.scale)));
-        out = (clampi(cy + a.oy, -1, a.h) + SG_LUT_PAD) * a.pitch;
-      }
-      a.cyp[ti * a.nyp + k] = out;
+#define SG_IDX_PAIRS 8     // beams per block of the index kernel
+#define SG_IDX_THREADS 128
+
+// cell of one axis value for the index tables: floor(RN(v / scale)) like the reference, computed as
+// floor(v * (1/scale)) and verified against both cell borders with exact FMA residuals; only a value
+// within `margin` of a border (a few ulps, or the device-trig slack when the guard is on) takes the
+// real division, and with the guard on such a value also flags the call for a libm-trig redo.
+SG_DEV int grid_axis_cell(double v, double rc, double scale, double inv_scale, int guard, bool *unsafe) {
+  int c = __double2int_rd(v * inv_scale);  // saturating
+  const double f = (double)c;
+  const double lo = fma(-f, scale, v);        // v - f*scale
+  const double hi = fma(f + 1.0, scale, -v);  // (f+1)*scale - v
+  double margin = fabs(v) * 8.9e-16 + 1e-300;
+  if (guard) margin += trig_slack(rc, v);
+  if (!(lo >= margin && hi >= margin)) {
+    c = cell_of(floor(sg::div(v, scale)));
+    if (guard) {
+      const double q = v * inv_scale, fl = floor(q);
+      const double tol = trig_slack(rc, v) * inv_scale + 8.0 * 2.220446049250313e-16 * fabs(q);
+      if ((q - fl) <= tol || ((fl + 1.0) - q) <= tol) *unsafe = true;
     }
-    unsafe_any |= unsafe;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) {
+  // grid = (ceil(N / SG_IDX_PAIRS), nt_loc): each block handles SG_IDX_PAIRS beams of one theta; a thread
+  // owns one axis value (an x or a y) and walks the beams, so the axis value is loaded once
+  extern __shared__ int sh_rows[];  // [SG_IDX_PAIRS][ny] padded LUT rows (v2 packing)
+  __shared__ double sh_rc[SG_IDX_PAIRS], sh_rs[SG_IDX_PAIRS];
+  const int tl = blockIdx.y;
+  const int i0 = blockIdx.x * SG_IDX_PAIRS;
+  const int np = min(SG_IDX_PAIRS, a.N - i0);
+  const double inv_scale = 1.0 / a.scale;
+  if (threadIdx.x < np) {
+    const long long src = (long long)(a.t_lo + tl) * a.N + i0 + threadIdx.x;
+    sh_rc[threadIdx.x] = a.trc[src];
+    sh_rs[threadIdx.x] = a.trs[src];
+  }
+  __syncthreads();
+  bool unsafe_any = false;
+  const long long ti0 = (long long)tl * a.N + i0;
+  const int ny_items = a.v2 ? a.ny : a.nyp;
+  for (int c = threadIdx.x; c < a.nx + ny_items; c += blockDim.x) {
+    if (c < a.nx) {
+      const double x = a.xs[c];
+      int *dst = a.cxp + ti0 * a.nx + c;
+      for (int pr = 0; pr < np; ++pr) {
+        const double rc = sh_rc[pr];
+        const int cx = grid_axis_cell(sg::add(x, rc), rc, a.scale, inv_scale, a.guard, &unsafe_any);
+        dst[(size_t)pr * a.nx] = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
+      }
+    } else {
+      const int k = c - a.nx;
+      const double y = k < a.ny ? a.ys[k] : 0.0;
+      for (int pr = 0; pr < np; ++pr) {
+        int prow = 0;  // v1 padding rows point at the ring row 0 (always valid memory)
+        if (k < a.ny) {
+          const double rs = sh_rs[pr];
+          const int cy = grid_axis_cell(sg::add(y, rs), rs, a.scale, inv_scale, a.guard, &unsafe_any);
+          prow = clampi(cy + a.oy, -1, a.h) + SG_LUT_PAD;
+        }
+        if (a.v2) sh_rows[pr * a.ny + k] = prow;
+        else a.cyp[(ti0 + pr) * a.nyp + k] = prow * a.pitch;
+      }
+    }
+  }
+  if (a.v2) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < np * a.ngy; e += blockDim.x) {
+      const int pr = e / a.ngy, gy = e - pr * a.ngy;
+      const int *rows = sh_rows + pr * a.ny;
+      const int k0 = gy * a.R;
+      unsigned long long word = (unsigned)(rows[k0] * a.pitch);
+      int prev = rows[k0];
+      for (int m = 1; m < a.R; ++m) {
+        const int k = k0 + m;
+        const int prow = k < a.ny ? rows[k] : prev;  // rows past the end repeat the last one (delta 0)
+        int d = prow - prev;
+        if (d < -8 || d > 7) { atomicAdd((unsigned long long *)&a.result->pad, 1ull); d = 0; }
+        word |= (unsigned long long)(d & 15) << (32 + 4 * (m - 1));
+        prev = prow;
+      }
+      a.cyw[(ti0 + pr) * a.ngy + gy] = word;
+    }
   }
   if (unsafe_any) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
 }
@@ -310,6 +386,103 @@ __global__ void __launch_bounds__(128) k_score_grid(GridArgs a) {
     }
   }
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+// v2 of the grid kernel.  Same arithmetic and summation order; what changes is the data movement:
+//  * the R consecutive y of a thread usually fall into ~R*step/scale+1 distinct cell rows; the packed row
+//    word says (warp-uniformly) where the row changes, so a repeated row re-uses the value already in a
+//    register instead of gathering (and multiplying) again;
+//  * the row table shrinks to one 64-bit uniform load per beam (was two LDG.128);
+//  * the per-beam index loads run PF beams ahead of the gathers that depend on them;
+//  * equal point weights (EvenSPW) come from a kernel parameter instead of a load.
+struct GridArgs2 {
+  const double *lut;
+  const int *cxp;
+  const unsigned long long *cyw;
+  const int4 *groups;  // {t, k0, m_lo, m_hi}
+  int n_groups, nx, ny, ngy, N, t_lo, pitch;
+  const double *w, *f;
+  double w0, wsum;
+  long long p0;
+  double *scores;
+  Best *blk;
+};
+
+template <int R, bool FACTOR, bool UNIW>
+__global__ void __launch_bounds__(128) k_score_grid2(GridArgs2 a) {
+  long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int g = (int)(q0 / a.nx);
+  int j = (int)(q0 - (long long)g * a.nx);
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  if (g < a.n_groups) {
+    const int4 grp = __ldg(a.groups + g);
+    const int tl = grp.x - a.t_lo;
+    const int *pcx = a.cxp + (size_t)tl * a.N * a.nx + j;
+    const unsigned long long *pcw = a.cyw + (size_t)tl * a.N * a.ngy + grp.y / R;
+    double acc[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) acc[m] = 0.0;
+    // software pipeline: indices run two beams ahead, gathers one beam ahead of the adds
+    int cx1 = 0, cx2 = 0;
+    unsigned long long cw1 = 0, cw2 = 0;
+    double v[R];
+    {
+      int cx0 = a.N > 0 ? __ldg(pcx) : 0;
+      unsigned long long cw0 = a.N > 0 ? __ldg(pcw) : 0ull;
+      if (a.N > 1) { cx1 = __ldg(pcx + a.nx); cw1 = __ldg(pcw + a.ngy); }
+      if (a.N > 2) { cx2 = __ldg(pcx + 2 * (size_t)a.nx); cw2 = __ldg(pcw + 2 * (size_t)a.ngy); }
+      int off = (int)(unsigned)(cw0 & 0xffffffffull) + cx0;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (m > 0) off += nib_sext(cw0, m) * a.pitch;
+        v[m] = a.N > 0 ? __ldg(a.lut + off) : 0.0;
+      }
+    }
+    for (int i = 0; i < a.N; ++i) {
+      // gathers of beam i+1 (indices already in registers)
+      double vn[R];
+      {
+        int off = (int)(unsigned)(cw1 & 0xffffffffull) + cx1;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          if (m > 0) off += nib_sext(cw1, m) * a.pitch;
+          vn[m] = (i + 1 < a.N) ? __ldg(a.lut + off) : 0.0;
+        }
+      }
+      cx1 = cx2; cw1 = cw2;
+      if (i + 3 < a.N) { cx2 = __ldg(pcx + (size_t)(i + 3) * a.nx); cw2 = __ldg(pcw + (size_t)(i + 3) * a.ngy); }
+      const double wi = UNIW ? a.w0 : __ldg(a.w + i);
+      const double fi = FACTOR ? __ldg(a.f + i) : 1.0;
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        double term = sg::mul(v[m], wi);
+        if (FACTOR) term = sg::mul(term, fi);
+        acc[m] = sg::add(acc[m], term);
+        v[m] = vn[m];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m < grp.z || m >= grp.w) continue;
+      double score = a.wsum == 0 ? NAN : sg::div(acc[m], a.wsum);
+      long long idx = ((long long)grp.x * a.ny + (grp.y + m)) * a.nx + j;
+      a.scores[idx - a.p0] = score;
+      if (score == score && beats(score, idx, best_s, best_i)) { best_s = score; best_i = idx; }
+    }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+template <int R>
+void launch_grid2(slamgpu_ctx *ctx, const GridArgs2 &a, int nblk, bool factor, bool uniw) {
+  if (factor) {
+    if (uniw) k_score_grid2<R, true, true><<<nblk, 128, 0, ctx->stream>>>(a);
+    else k_score_grid2<R, true, false><<<nblk, 128, 0, ctx->stream>>>(a);
+  } else {
+    if (uniw) k_score_grid2<R, false, true><<<nblk, 128, 0, ctx->stream>>>(a);
+    else k_score_grid2<R, false, false><<<nblk, 128, 0, ctx->stream>>>(a);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -442,6 +615,20 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   c.spe = *p; c.scan = scan;
   c.nx = nx; c.ny = ny; c.nt = nt; c.nyp = (ny + SG_GRID_R - 1) / SG_GRID_R * SG_GRID_R;
   c.P = (int64_t)nt * ny * nx;
+  c.grid_v2 = !c.force_v1 && (size_t)ny * SG_IDX_PAIRS * sizeof(int) <= 40 * 1024;  // index kernel stages the rows in smem
+  {
+    // rows per thread: as many as keep the device full (one resident thread per pose column and y-group)
+    int64_t r0_, r1_;
+    slice_of(ctx, (int64_t)nt * ny, &r0_, &r1_);
+    const int64_t want_threads = (int64_t)ctx->sm_count * 768;
+    int R = 8;
+    while (c.grid_v2 && R > 2 && ((r1_ - r0_ + R - 1) / R) * nx < want_threads) R /= 2;
+    c.grid_R = c.grid_v2 ? R : SG_GRID_R;
+    c.ngy = (ny + c.grid_R - 1) / c.grid_R;
+  }
+  const int GR = c.grid_R;
+  c.uniform_w = scan->n > 0;
+  for (int i = 1; i < scan->n && c.uniform_w; ++i) c.uniform_w = scan->weight[i] == scan->weight[0];
   c.h_xs.assign(xs, xs + nx); c.h_ys.assign(ys, ys + ny); c.h_ts.assign(thetas, thetas + nt);
   // shard by rows (theta, y): contiguous candidate index ranges, whole rows per rank
   const int64_t rows = (int64_t)nt * ny;
@@ -453,13 +640,13 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   c.t_hi = r1 > r0 ? (int32_t)((r1 - 1) / ny) : c.t_lo;
   for (int32_t t = c.t_lo; t <= c.t_hi && r1 > r0; ++t) {
     int64_t ka = std::max<int64_t>(r0 - (int64_t)t * ny, 0), kb = std::min<int64_t>(r1 - (int64_t)t * ny, ny);
-    for (int32_t k0 = (int32_t)(ka / SG_GRID_R * SG_GRID_R); k0 < kb; k0 += SG_GRID_R) {
-      int32_t lo = (int32_t)std::max<int64_t>(ka - k0, 0), hi = (int32_t)std::min<int64_t>(kb - k0, SG_GRID_R);
+    for (int32_t k0 = (int32_t)(ka / GR * GR); k0 < kb; k0 += GR) {
+      int32_t lo = (int32_t)std::max<int64_t>(ka - k0, 0), hi = (int32_t)std::min<int64_t>(kb - k0, GR);
       groups.push_back(t); groups.push_back(k0); groups.push_back(lo); groups.push_back(hi);
     }
   }
   c.n_groups = (int32_t)(groups.size() / 4);
-  c.rows_per_group = SG_GRID_R;
+  c.rows_per_group = GR;
   const int N = scan->n;
   const int nt_loc = c.t_hi - c.t_lo + 1;
   SG_TRY(upload(ctx, c.groups, groups.data(), groups.size() * sizeof(int32_t)));
@@ -475,7 +662,8 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   long long threads = (long long)c.n_groups * nx;
   int nblk = (int)((threads + 127) / 128);
   if (c.cxp.reserve(std::max<size_t>((size_t)nt_loc * N * nx, 1) * sizeof(int)) != SLAMGPU_OK ||
-      c.cyp.reserve(std::max<size_t>((size_t)nt_loc * N * c.nyp, 1) * sizeof(int)) != SLAMGPU_OK ||
+      c.cyp.reserve(std::max<size_t>(c.grid_v2 ? 1 : (size_t)nt_loc * N * c.nyp, 1) * sizeof(int)) != SLAMGPU_OK ||
+      c.cyw.reserve(std::max<size_t>(c.grid_v2 ? (size_t)nt_loc * N * c.ngy : 1, 1) * sizeof(unsigned long long)) != SLAMGPU_OK ||
       c.scores.reserve(std::max<size_t>(Ploc, 1) * sizeof(double)) != SLAMGPU_OK ||
       c.blk_best.reserve(std::max(nblk, 1) * sizeof(Best)) != SLAMGPU_OK ||
       c.result.reserve(sizeof(Result) * 2) != SLAMGPU_OK ||
@@ -514,7 +702,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   const bool device_trig = !c.trig_is_host && !c.spe.prerotated;
   int nblk = 0;
   memset(c.stats, 0, sizeof c.stats);
-  c.stats[1] = c.kind; c.stats[2] = Ploc * N; c.stats[3] = c.p0; c.stats[4] = Ploc;
+  c.stats[1] = c.kind == 1 ? (c.grid_v2 ? 2 : 1) : 0; c.stats[2] = Ploc * N; c.stats[5] = c.grid_R; c.stats[3] = c.p0; c.stats[4] = Ploc;
   if (c.kind == 0) {
     if (device_trig && c.T > 0 && N > 0) {
       long long tot = (long long)c.T * N;
@@ -562,10 +750,28 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       ia.w = map->w; ia.h = map->h; ia.ox = map->ox; ia.oy = map->oy; ia.pitch = map->pitch; ia.scale = map->scale;
       ia.guard = device_trig ? 1 : 0;
       ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
-      k_grid_indices<<<(unsigned)((long long)nt_loc * N), 128, 0, ctx->stream>>>(ia);
+      ia.cyw = c.cyw.as<unsigned long long>(); ia.v2 = c.grid_v2 ? 1 : 0; ia.R = c.grid_R; ia.ngy = c.ngy;
+      {
+        const size_t shm = c.grid_v2 ? sizeof(int) * SG_IDX_PAIRS * (size_t)c.ny : 0;
+        dim3 grd((unsigned)((N + SG_IDX_PAIRS - 1) / SG_IDX_PAIRS), (unsigned)nt_loc);
+        k_grid_indices<<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia);
+      }
       SG_LAUNCHED(ctx);
     }
-    if (nblk > 0) {
+    if (nblk > 0 && c.grid_v2) {
+      GridArgs2 a;
+      a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<int>(); a.cyw = c.cyw.as<unsigned long long>(); a.groups = c.groups.as<int4>();
+      a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.N = N; a.t_lo = c.t_lo; a.pitch = map->pitch;
+      a.w = s->d_w; a.f = s->d_f; a.w0 = N > 0 ? s->weight[0] : 0.0; a.wsum = s->wsum; a.p0 = c.p0;
+      a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>();
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      if (c.grid_R == 8) launch_grid2<8>(ctx, a, nblk, s->has_factor, c.uniform_w);
+      else if (c.grid_R == 4) launch_grid2<4>(ctx, a, nblk, s->has_factor, c.uniform_w);
+      else launch_grid2<2>(ctx, a, nblk, s->has_factor, c.uniform_w);
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->evk_valid = true;
+      SG_LAUNCHED(ctx);
+    } else if (nblk > 0) {
       GridArgs a;
       a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<int>(); a.cyp = c.cyp.as<int>(); a.groups = c.groups.as<int4>();
       a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.nyp = c.nyp; a.N = N; a.t_lo = c.t_lo;
@@ -620,6 +826,21 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
   Result *h = (Result *)hp;
   SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h->pad > 0 && c.kind == 1 && c.grid_v2 && map) {
+    // some pair of neighbouring y values is more than 7 cell rows apart: the packed row word cannot
+    // hold it; redo with the explicit row table (v1 kernel)
+    c.force_v1 = true;
+    slamgpu_spe_params spe = c.spe;
+    std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
+    double init = c.init_score;
+    int r = slamgpu_stage_grid(ctx, c.scan, &spe, xs.data(), (int32_t)xs.size(), ys.data(), (int32_t)ys.size(), ts.data(),
+                               (int32_t)ts.size());
+    c.force_v1 = false;
+    SG_TRY(r);
+    SG_TRY(launch_staged(ctx, map, init));
+    SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if (h->guard > 0 && !c.trig_is_host && map) {
     // some world point sits within the guard band of a cell border: redo with libm trig so the
     // cell indices are the reference's by construction (every rank sees the same summed counter)
