@@ -93,6 +93,7 @@ typedef struct slamgpu_ctx slamgpu_ctx;
 typedef struct slamgpu_map slamgpu_map;
 typedef struct slamgpu_scan slamgpu_scan;
 typedef struct slamgpu_pyramid slamgpu_pyramid;
+typedef struct slamgpu_particles slamgpu_particles;
 
 /* SPEParams + the OOPE/OIE choice: src/core/scan_matchers/grid_scan_matcher.h:105-136 */
 typedef struct slamgpu_spe_params {
@@ -281,6 +282,36 @@ int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const do
 int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *scans, int32_t n_scans, const int32_t *scan_id,
                           const double *windows /* 4*M */, int64_t M, const double pose[3],
                           const slamgpu_spe_params *spe, double *out_bounds /* M */);
+
+/* ------------------------------------------------------------------ K6: GMapping particles
+ * replaces the per-particle loop of GmappingParticleFilter::handle_observation
+ * (src/slams/gmapping/gmapping_particle_filter.h:70-85): n particles, each with its OWN device map.
+ * Pose noise, weights, N_eff and the resampling draw stay on the host (libstdc++ <random>,
+ * src/slams/gmapping/gmapping_world.h:81-85, src/core/particle_filter.h:34-106). */
+int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
+                             const double *unknown_rec, slamgpu_particles **out);
+void slamgpu_particles_destroy(slamgpu_particles *p);
+int slamgpu_particles_count(const slamgpu_particles *p);
+/* borrowed handle of particle i's map: valid for every slamgpu_map_* call until the next resample */
+slamgpu_map *slamgpu_particles_map(slamgpu_particles *p, int32_t i);
+/* scores[i*c + k] = scan probability of poses[i*c + k] on particle i's map; one launch for all particles */
+int slamgpu_particles_score(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
+                            const double *poses /* 3*n*c */, int32_t per_particle /* c */, double *out_scores /* n*c */);
+/* HillClimbingScanMatcher::process_scan (src/core/scan_matchers/hill_climbing_scan_matcher.h:128-170) for
+ * every active particle from its own initial pose against its own map, all particles in lock step
+ * (one launch per hill-climbing round).  out_poses = best poses, out_probs = their probabilities,
+ * out_tested = poses scored per particle (initial pose included). */
+int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
+                               const double *init_poses /* 3*n */, const uint8_t *active /* n or NULL */,
+                               uint32_t max_failed_rounds, double translation_delta, double rotation_delta,
+                               double *out_poses /* 3*n */, double *out_probs /* n */, int64_t *out_tested /* n or NULL */);
+/* GridMapScanAdder::append_scan into every particle's own map from its own pose (do_update NULL: all) */
+int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses /* 3*n */,
+                                  const uint8_t *do_update /* n or NULL */, double scan_quality, int32_t scan_margin,
+                                  const slamgpu_estimator *est, double blur, double max_range, const double *point_quality,
+                                  int64_t *cells_updated /* n or NULL */);
+/* the copy step of ParticleFilter::try_resample (src/core/particle_filter.h:92-98): particle i := particle src[i] */
+int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src /* n */);
 
 #ifdef __cplusplus
 }

@@ -68,7 +68,9 @@ SYMBOLS = [
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
-    "slamgpu_pyramid_append_scan", "slamgpu_score_windows",
+    "slamgpu_pyramid_append_scan", "slamgpu_score_windows", "slamgpu_particles_create", "slamgpu_particles_destroy",
+    "slamgpu_particles_count", "slamgpu_particles_map", "slamgpu_particles_score", "slamgpu_particles_match_hc",
+    "slamgpu_particles_append_scan", "slamgpu_particles_resample",
 ]
 
 
@@ -140,6 +142,16 @@ def lib():
     L.slamgpu_pyramid_rescale.argtypes = [vp, dbl]
     L.slamgpu_pyramid_append_scan.argtypes = [vp, vp, c_dp, dbl, i32, ep, dbl, dbl, c_dp, c_lp]
     L.slamgpu_score_windows.argtypes = [vp, pvp, i32, c_ip, c_dp, i64, c_dp, sp, c_dp]
+    L.slamgpu_particles_create.argtypes = [vp, i32, i32, i32, dbl, i32, i32, c_dp, pvp]
+    L.slamgpu_particles_destroy.argtypes = [vp]
+    L.slamgpu_particles_destroy.restype = None
+    L.slamgpu_particles_count.argtypes = [vp]
+    L.slamgpu_particles_map.argtypes = [vp, i32]
+    L.slamgpu_particles_map.restype = vp
+    L.slamgpu_particles_score.argtypes = [vp, vp, sp, c_dp, i32, c_dp]
+    L.slamgpu_particles_match_hc.argtypes = [vp, vp, sp, c_dp, c_u8p, C.c_uint32, dbl, dbl, c_dp, c_dp, c_lp]
+    L.slamgpu_particles_append_scan.argtypes = [vp, vp, c_dp, c_u8p, dbl, i32, ep, dbl, dbl, c_dp, c_lp]
+    L.slamgpu_particles_resample.argtypes = [vp, c_ip]
     _lib = L
     return L
 
@@ -450,3 +462,63 @@ class Pyramid:
         self.ctx.check(self.ctx.L.slamgpu_score_windows(self.h, arr, len(scans), sid.ctypes.data_as(c_ip), _dp(win), len(win),
                                                         _dp(pose), C.byref(params), _dp(out)))
         return out
+
+
+class _BorrowedMap(GridMap):
+    """a particle's map: same methods as GridMap, owned by the Particles object"""
+
+    def __init__(self, ctx, handle, model):
+        self.ctx, self.model, self.h = ctx, model, C.c_void_p(handle)
+
+    def close(self):
+        self.h = None
+
+
+class Particles:
+    """slamgpu_particles: n GMapping particles, each with its own device map"""
+
+    def __init__(self, ctx, n, w, h, scale, model=CELL_GMAPPING, grow=GROW_TILED):
+        self.ctx, self.n, self.model = ctx, n, model
+        hnd = C.c_void_p()
+        ctx.check(ctx.L.slamgpu_particles_create(ctx.h, n, w, h, scale, model, grow, None, C.byref(hnd)))
+        self.h = hnd
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.slamgpu_particles_destroy(self.h)
+            self.h = None
+
+    def map(self, i):
+        return _BorrowedMap(self.ctx, self.ctx.L.slamgpu_particles_map(self.h, i), self.model)
+
+    def score(self, scan, params, poses):
+        poses = _f64(poses).reshape(self.n, -1, 3)
+        c = poses.shape[1]
+        out = np.full((self.n, c), np.nan)
+        self.ctx.check(self.ctx.L.slamgpu_particles_score(self.h, scan.h, C.byref(params), _dp(poses), c, _dp(out)))
+        return out
+
+    def match_hc(self, scan, params, init_poses, max_failed_rounds=6, tr=0.1, rot=0.1, active=None):
+        init = _f64(init_poses).reshape(self.n, 3)
+        act = np.ascontiguousarray(active, dtype=np.uint8) if active is not None else None
+        poses, probs, tested = np.zeros((self.n, 3)), np.zeros(self.n), np.zeros(self.n, dtype=np.int64)
+        self.ctx.check(self.ctx.L.slamgpu_particles_match_hc(self.h, scan.h, C.byref(params), _dp(init),
+                                                             act.ctypes.data_as(c_u8p) if act is not None else None,
+                                                             max_failed_rounds, tr, rot, _dp(poses), _dp(probs),
+                                                             tested.ctypes.data_as(c_lp)))
+        return poses, probs, tested
+
+    def append_scan(self, scan, poses, do_update=None, quality=1.0, margin=0, est=None, blur=0.0, max_range=np.inf):
+        est = est or estimator()
+        poses = _f64(poses).reshape(self.n, 3)
+        upd = np.ascontiguousarray(do_update, dtype=np.uint8) if do_update is not None else None
+        cells = np.zeros(self.n, dtype=np.int64)
+        self.ctx.check(self.ctx.L.slamgpu_particles_append_scan(self.h, scan.h, _dp(poses),
+                                                                upd.ctypes.data_as(c_u8p) if upd is not None else None, quality,
+                                                                margin, C.byref(est), blur, max_range, None,
+                                                                cells.ctypes.data_as(c_lp)))
+        return cells
+
+    def resample(self, src):
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        self.ctx.check(self.ctx.L.slamgpu_particles_resample(self.h, src.ctypes.data_as(c_ip)))

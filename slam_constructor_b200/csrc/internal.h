@@ -43,6 +43,9 @@ struct Candidates {  // a staged candidate set (device resident)
   int32_t grid_R = 8, ngy = 0;  // rows per thread of the grid kernel, y-groups per (theta, beam)
   bool grid_v2 = true, force_v1 = false;
   bool uniform_w = false;
+  // K6: every pose scored against its own particle's map
+  bool multi = false;
+  DevBuf views, view_id;
   // trig tables (device), layout given by strides
   DevBuf trc, trs;
   bool trig_is_host = false;
@@ -127,6 +130,9 @@ int sg_pinned(slamgpu_ctx *ctx, size_t bytes, void **out);
 int sg_map_ensure_lut(slamgpu_map *m, int oie);
 void sg_map_invalidate_lut(slamgpu_map *m);
 int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h);
+// K6 (score.cu): poses[k] is scored against maps[view_id[k]]; out_scores may be NULL
+int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
+                         const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores);
 int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv);
 
 // NCCL through dlopen (nccl_dyn.cc)

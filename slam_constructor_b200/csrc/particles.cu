@@ -1,0 +1,247 @@
+// particles.cu -- K6: the GMapping particle step batched over particles.
+//
+// Replaces the per-particle loop of GmappingParticleFilter::handle_observation
+// (src/slams/gmapping/gmapping_particle_filter.h:70-85) around GmappingWorld::handle_observation
+// (src/slams/gmapping/gmapping_world.h:73-101): every particle hill-climbs from its own pose against
+// its OWN map (HillClimbingScanMatcher(6, 0.1, 0.1) upstream, src/slams/gmapping/init_gmapping.h:58-60),
+// then inserts the scan into its own map.  Here all particles advance in lock step: one K1 launch
+// scores the current hill-climbing round of every particle (6 candidates each, each against its
+// particle's map), the accept logic of the round runs on the host, repeat until every particle has
+// exhausted its failed-rounds budget.  Resampling copies maps on the device.
+//
+// Each particle owns a dense device map (the reference shares copy-on-write 128x128 tiles between
+// particles, src/core/maps/lazy_tiled_grid_map.h:18-118; tile sharing on the device is future work --
+// resampling here copies whole maps, device to device).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "mapping.h"
+
+struct slamgpu_particles {
+  slamgpu_ctx *ctx = nullptr;
+  std::vector<slamgpu_map *> maps;
+};
+
+extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, int32_t h, double scale, int32_t model,
+                                        int32_t grow, const double *unknown_rec, slamgpu_particles **out) {
+  if (!ctx || !out || n <= 0) return sg_fail(ctx, SLAMGPU_E_INVALID, "particles_create: bad argument");
+  *out = nullptr;
+  slamgpu_particles *p = new slamgpu_particles();
+  p->ctx = ctx;
+  for (int i = 0; i < n; ++i) {
+    slamgpu_map *m = nullptr;
+    int r = slamgpu_map_create(ctx, w, h, scale, model, grow, unknown_rec, &m);
+    if (r != SLAMGPU_OK) { slamgpu_particles_destroy(p); return r; }
+    p->maps.push_back(m);
+  }
+  *out = p;
+  return SLAMGPU_OK;
+}
+
+extern "C" void slamgpu_particles_destroy(slamgpu_particles *p) {
+  if (!p) return;
+  for (slamgpu_map *m : p->maps) slamgpu_map_destroy(m);
+  delete p;
+}
+
+extern "C" int slamgpu_particles_count(const slamgpu_particles *p) { return p ? (int)p->maps.size() : SLAMGPU_E_INVALID; }
+
+extern "C" slamgpu_map *slamgpu_particles_map(slamgpu_particles *p, int32_t i) {
+  if (!p || i < 0 || i >= (int)p->maps.size()) return nullptr;
+  return p->maps[i];
+}
+
+extern "C" int slamgpu_particles_score(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
+                                       const double *poses, int32_t per_particle, double *out_scores) {
+  if (!p || !spe || per_particle < 0 || (per_particle > 0 && (!poses || !out_scores))) return SLAMGPU_E_INVALID;
+  const int n = (int)p->maps.size();
+  const int64_t P = (int64_t)n * per_particle;
+  std::vector<int32_t> vid((size_t)P);
+  for (int64_t k = 0; k < P; ++k) vid[k] = (int32_t)(k / per_particle);
+  return sg_score_poses_multi(p->ctx, p->maps.data(), n, vid.data(), scan, spe, poses, P, out_scores);
+}
+
+namespace {
+
+// FailedRoundsLimitedPoseEnumerator<Distorsion1DPoseEnumerator> + the accept loop of
+// PoseEnumerationScanMatcher, one instance per particle (hill_climbing_scan_matcher.h:10-126,
+// pose_enumeration_scan_matcher.h:48-65); frame rotation is always 0 upstream (quirk Q5)
+struct HillClimb {
+  double bx, by, bt, best;     // best pose so far and its probability
+  double rbx, rby, rbt;        // base of the current round
+  double tr, rot;
+  unsigned failed_rounds = 0, action = 0;
+  bool base_set = false, round_failed = true, done = false;
+  int64_t tested = 1;
+
+  // candidates the reference would test next, up to the end of the current round
+  int next_round(unsigned max_failed_rounds, double out[6][3]) {
+    int k = 0;
+    unsigned fr = failed_rounds, act = action;
+    bool bs = base_set, rf = round_failed;
+    double t_tr = tr, t_rot = rot, x0 = rbx, y0 = rby, t0 = rbt;
+    while (fr < max_failed_rounds && k < 6) {
+      if (!(act < 6)) {
+        if (k > 0) break;  // the next round depends on this round's accepts: stop here
+        if (rf) { t_tr *= 0.5; t_rot *= 0.5; ++fr; }
+        act = 0; bs = false; rf = true;
+      }
+      if (!bs) { x0 = bx; y0 = by; t0 = bt; bs = true; }
+      double x = x0, y = y0, t = t0;
+      const double dir = act % 2 ? -1 : 1;
+      switch (act % 3) {
+        case 0: x += 1.0 * dir * t_tr; y += 0.0 * dir * t_tr; break;
+        case 1: x += -0.0 * dir * t_tr; y += 1.0 * dir * t_tr; break;
+        case 2: t += dir * t_rot; break;
+      }
+      ++act;
+      out[k][0] = x; out[k][1] = y; out[k][2] = t;
+      ++k;
+    }
+    return k;
+  }
+  // replay the same steps with the scores known
+  void apply(unsigned max_failed_rounds, const double cand[6][3], const double *scores, int k) {
+    for (int j = 0; j < k; ++j) {
+      if (!(action < 6)) {
+        if (round_failed) { tr *= 0.5; rot *= 0.5; ++failed_rounds; }
+        action = 0; base_set = false; round_failed = true;
+      }
+      if (!base_set) { rbx = bx; rby = by; rbt = bt; base_set = true; }
+      ++action;
+      ++tested;
+      const bool ok = best < scores[j];
+      round_failed &= !ok;
+      if (ok) { best = scores[j]; bx = cand[j][0]; by = cand[j][1]; bt = cand[j][2]; }
+    }
+    done = !(failed_rounds < max_failed_rounds);
+    (void)max_failed_rounds;
+  }
+};
+
+}  // namespace
+
+extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
+                                          const double *init_poses, const uint8_t *active, uint32_t max_failed_rounds,
+                                          double translation_delta, double rotation_delta, double *out_poses, double *out_probs,
+                                          int64_t *out_tested) {
+  if (!p || !scan || !spe || !init_poses || !out_poses || !out_probs) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  const int n = (int)p->maps.size();
+  std::vector<HillClimb> hc(n);
+  std::vector<double> poses;
+  std::vector<int32_t> vid;
+  std::vector<double> scores;
+  // probability of the initial poses (pose_enumeration_scan_matcher.h:40)
+  for (int i = 0; i < n; ++i) {
+    if (active && !active[i]) continue;
+    poses.insert(poses.end(), init_poses + 3 * i, init_poses + 3 * i + 3);
+    vid.push_back(i);
+  }
+  scores.resize(vid.size());
+  if (!vid.empty())
+    SG_TRY(sg_score_poses_multi(ctx, p->maps.data(), n, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
+  size_t q = 0;
+  for (int i = 0; i < n; ++i) {
+    HillClimb &h = hc[i];
+    h.bx = init_poses[3 * i]; h.by = init_poses[3 * i + 1]; h.bt = init_poses[3 * i + 2];
+    h.tr = translation_delta; h.rot = rotation_delta;
+    if (active && !active[i]) { h.done = true; h.best = NAN; h.tested = 0; continue; }
+    h.best = scores[q++];
+    h.done = !(0 < max_failed_rounds);
+  }
+  std::vector<int> who, cnt;
+  std::vector<double> cands;  // per entry of `who`: 6 x 3
+  for (;;) {
+    poses.clear(); vid.clear(); who.clear(); cnt.clear(); cands.clear();
+    for (int i = 0; i < n; ++i) {
+      if (hc[i].done) continue;
+      double c6[6][3];
+      int k = hc[i].next_round(max_failed_rounds, c6);
+      if (k == 0) { hc[i].done = true; continue; }
+      who.push_back(i); cnt.push_back(k);
+      cands.insert(cands.end(), &c6[0][0], &c6[0][0] + 18);
+      for (int j = 0; j < k; ++j) {
+        poses.push_back(c6[j][0]); poses.push_back(c6[j][1]); poses.push_back(c6[j][2]);
+        vid.push_back(i);
+      }
+    }
+    if (who.empty()) break;
+    scores.resize(vid.size());
+    SG_TRY(sg_score_poses_multi(ctx, p->maps.data(), n, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
+    size_t off = 0;
+    for (size_t e = 0; e < who.size(); ++e) {
+      double c6[6][3];
+      memcpy(c6, cands.data() + 18 * e, sizeof c6);
+      hc[who[e]].apply(max_failed_rounds, c6, scores.data() + off, cnt[e]);
+      off += cnt[e];
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    out_poses[3 * i] = hc[i].bx; out_poses[3 * i + 1] = hc[i].by; out_poses[3 * i + 2] = hc[i].bt;
+    out_probs[i] = hc[i].best;
+    if (out_tested) out_tested[i] = hc[i].tested;
+  }
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses,
+                                             const uint8_t *do_update, double scan_quality, int32_t scan_margin,
+                                             const slamgpu_estimator *est, double blur, double max_range,
+                                             const double *point_quality, int64_t *cells_updated) {
+  if (!p || !scan || !poses || !est) return SLAMGPU_E_INVALID;
+  const int n = (int)p->maps.size();
+  for (int i = 0; i < n; ++i) {
+    int64_t cells = 0;
+    if (!do_update || do_update[i])
+      SG_TRY(sg_append_scan_impl(p->ctx, p->maps[i], scan, poses + 3 * i, scan_quality, scan_margin, est, blur, max_range,
+                                 point_quality, &cells, nullptr));
+    if (cells_updated) cells_updated[i] = cells;
+  }
+  return SLAMGPU_OK;
+}
+
+// ParticleFilter::try_resample's copy step (src/core/particle_filter.h:92-98): particle i becomes a
+// copy of particle src[i].  A source that survives exactly once is moved, the others are copied on
+// the device.
+extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src) {
+  if (!p || !src) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  const int n = (int)p->maps.size();
+  for (int i = 0; i < n; ++i)
+    if (src[i] < 0 || src[i] >= n) return sg_fail(ctx, SLAMGPU_E_INVALID, "resample: bad source index %d", src[i]);
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<slamgpu_map *> next(n, nullptr);
+  std::vector<char> taken(n, 0);
+  // keep a surviving particle in place when it can be (no copy at all for the common "i -> i")
+  for (int i = 0; i < n; ++i)
+    if (src[i] == i) { next[i] = p->maps[i]; taken[i] = 1; }
+  // first other use of a source whose own slot is not reused takes the object itself
+  for (int i = 0; i < n; ++i) {
+    if (next[i]) continue;
+    if (!taken[src[i]]) { next[i] = p->maps[src[i]]; taken[src[i]] = 1; }
+  }
+  // the rest are copies into the maps nobody kept
+  std::vector<slamgpu_map *> spare;
+  for (int i = 0; i < n; ++i)
+    if (!taken[i]) spare.push_back(p->maps[i]);
+  for (int i = 0; i < n; ++i) {
+    if (next[i]) continue;
+    slamgpu_map *from = p->maps[src[i]];
+    slamgpu_map *to = spare.back();
+    spare.pop_back();
+    SG_TRY(sg_map_realloc(to, from->w, from->h));
+    to->ox = from->ox; to->oy = from->oy;
+    SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, from->d_cells, (size_t)from->w * from->h * from->stride * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    sg_map_invalidate_lut(to);
+    next[i] = to;
+  }
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  p->maps.swap(next);
+  return SLAMGPU_OK;
+}

@@ -141,6 +141,8 @@ SG_DEV int grid_cell(double v, double rc, double scale, double inv_scale, int gu
 
 struct ListArgs {
   MapView map;
+  const MapView *views;  // K6: per-particle maps (NULL: every pose against `map`)
+  const int *view_id;    // K6: per local pose
   const double *poses;      // 3*Ploc
   const int *theta_id;      // Ploc (table column), unused when prerotated
   const double *trc, *trs;  // [i*T + tid]
@@ -163,7 +165,8 @@ __global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
   if (p < a.Ploc) {
     const double px = a.poses[3 * p], py = a.poses[3 * p + 1];
     const int tid = PREROT ? 0 : a.theta_id[p];
-    const double s = a.map.scale, inv_s = 1.0 / a.map.scale;
+    const MapView &mv = a.views ? a.views[a.view_id[p]] : a.map;
+    const double s = mv.scale, inv_s = 1.0 / mv.scale;
     double total_probability = 0;
     bool unsafe_any = false;
     int cache_x = 0, cache_y = 0;
@@ -182,12 +185,12 @@ __global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
         cx = grid_cell(X, rc, s, inv_s, GUARD ? 1 : 0, &unsafe_any);
         cy = grid_cell(Y, rs, s, inv_s, GUARD ? 1 : 0, &unsafe_any);
         if (MODE == SLAMGPU_OOPE_OBSTACLE) {
-          prob = lut_at(a.map, cx, cy);
+          prob = lut_at(mv, cx, cy);
         } else {
           if (a.gm_cache && cx == cache_x && cy == cache_y && cache_p != -1) {
             prob = cache_p;
           } else {
-            prob = gmapping_probability(a.map, cx, cy, X, Y, a.gm_th, a.gm_win);
+            prob = gmapping_probability(mv, cx, cy, X, Y, a.gm_th, a.gm_win);
             cache_x = cx; cache_y = cy; cache_p = prob;
           }
         }
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
           sg::world_to_cell_guard(sg::sub(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
           sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
         }
-        prob = window_probability<MODE>(a.map, X, Y, a.win_v, a.win_h);
+        prob = window_probability<MODE>(mv, X, Y, a.win_v, a.win_h);
       }
       double term = sg::mul(prob, __ldg(a.w + i));
       if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
@@ -695,7 +698,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   const slamgpu_scan *s = c.scan;
   const int N = s->n;
   const int oie = c.spe.oie;
-  if (c.spe.oope != SLAMGPU_OOPE_GMAPPING) SG_TRY(sg_map_ensure_lut(map, oie));
+  if (c.spe.oope != SLAMGPU_OOPE_GMAPPING && !c.multi) SG_TRY(sg_map_ensure_lut(map, oie));
   Result *res = c.result.as<Result>();
   SG_CUDA(ctx, cudaMemsetAsync(res, 0, sizeof(Result) * 2, ctx->stream));
   const int64_t Ploc = c.p1 - c.p0;
@@ -714,6 +717,8 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
     if (nblk > 0) {
       ListArgs a;
       a.map = make_view(map, oie);
+      a.views = c.multi ? c.views.as<MapView>() : nullptr;
+      a.view_id = c.multi ? c.view_id.as<int>() : nullptr;
       a.poses = c.poses.as<double>(); a.theta_id = c.theta_id.as<int>();
       a.trc = c.trc.as<double>(); a.trs = c.trs.as<double>(); a.T = c.T;
       a.sx = s->d_x; a.sy = s->d_y; a.w = s->d_w; a.f = s->d_f; a.N = N;
@@ -890,4 +895,28 @@ extern "C" int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_sc
   SG_TRY(slamgpu_stage_grid(ctx, scan, p, xs, nx, ys, ny, thetas, nt));
   SG_TRY(launch_staged(ctx, map, init_score));
   return fetch_impl(ctx, map, out_scores, best_idx, best_score);
+}
+
+// K6: one launch scores every particle's candidates against that particle's own map
+int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
+                         const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores) {
+  if (!ctx || !maps || n_maps <= 0 || (P > 0 && !view_id)) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_multi: bad argument");
+  SG_TRY(slamgpu_stage_poses(ctx, scan, p, poses, P));
+  Candidates &c = ctx->cand;
+  std::vector<MapView> views(n_maps);
+  for (int k = 0; k < n_maps; ++k) {
+    if (!maps[k] || maps[k]->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "particle map %d is NULL or belongs to another ctx", k);
+    if (p->oope != SLAMGPU_OOPE_GMAPPING) SG_TRY(sg_map_ensure_lut(maps[k], p->oie));
+    views[k] = make_view(maps[k], p->oie);
+  }
+  for (int64_t k = 0; k < P; ++k)
+    if (view_id[k] < 0 || view_id[k] >= n_maps) return sg_fail(ctx, SLAMGPU_E_INVALID, "pose %lld: bad particle id", (long long)k);
+  SG_TRY(upload(ctx, c.views, views.data(), sizeof(MapView) * n_maps));
+  SG_TRY(upload(ctx, c.view_id, view_id + c.p0, sizeof(int32_t) * (size_t)(c.p1 - c.p0)));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  c.multi = true;
+  int r = launch_staged(ctx, maps[0], -INFINITY);
+  if (r == SLAMGPU_OK) r = fetch_impl(ctx, maps[0], out_scores, nullptr, nullptr);
+  c.multi = false;
+  return r;
 }

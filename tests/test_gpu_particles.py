@@ -1,0 +1,108 @@
+"""K6 parity on the GPU: the GMapping particle step batched over particles, against the oracle run particle by
+particle.  Obstacle-OOPE runs are bit-exact (scores, poses, number of poses tested); the GMapping OOPE goes
+through exp(), so its scores are compared at rtol 1e-5 and the climbed poses must still coincide."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import room_scan
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _build(sg, gpu, rng, n, model, size=160, scale=0.05, scans=3):
+    """n particles with slightly different pose histories -> n different maps, mirrored in the oracle"""
+    parts = sg.Particles(gpu, n, size, size, scale, model, sg.GROW_TILED)
+    omaps = [ob.OracleMap(size, size, scale, model, ob.GROW_TILED) for _ in range(n)]
+    oest, gest = ob.estimator(ob.EST_CONST), sg.estimator(sg.EST_CONST)
+    truth = np.array([0.2, -0.1, 0.3])
+    for k in range(scans):
+        r, a = room_scan(rng, 181, 2 * np.pi, half_w=3.0, half_h=2.5, pose=truth, noise=0.01)
+        poses = truth + rng.normal(0, [0.03, 0.03, 0.01], (n, 3))
+        gsc = sg.Scan(gpu, r, a)
+        upd = np.ones(n, np.uint8)
+        if k == 1:
+            upd[::3] = 0  # some particles skip an update (scan probability 0 upstream)
+        cells = parts.append_scan(gsc, poses, do_update=upd, est=gest)
+        for i in range(n):
+            if upd[i]:
+                c, _ = omaps[i].append_scan(ob.OracleScan(r, a), poses[i], 1.0, 0, oest)
+                assert c == cells[i]
+            else:
+                assert cells[i] == 0
+        gsc.close()
+        truth = truth + [0.05, 0.02, 0.02]
+    return parts, omaps, truth
+
+
+def _check_maps(parts, omaps):
+    for i, om in enumerate(omaps):
+        pm = parts.map(i)
+        assert pm.info() == om.info(), i
+        assert np.array_equal(pm.download(), om.cells(), equal_nan=True), i
+
+
+@pytest.mark.parametrize("model", [ob.CELL_MEAN, ob.CELL_GMAPPING])
+def test_particle_maps_scores_and_hill_climbing(sg, gpu, model):
+    rng = np.random.default_rng(4000 + model)
+    n = 12
+    parts, omaps, truth = _build(sg, gpu, rng, n, model)
+    _check_maps(parts, omaps)
+    r, a = room_scan(rng, 121, 2 * np.pi, half_w=3.0, half_h=2.5, pose=truth, noise=0.005)
+    gsc, osc = sg.Scan(gpu, r, a), ob.OracleScan(r, a)
+    gm_mode = model == ob.CELL_GMAPPING
+    if gm_mode:
+        gparams = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1)
+        oparams = ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1)
+    else:
+        gparams, oparams = sg.spe_params(), ob.spe_params()
+    # per-particle candidate scoring, one launch
+    cand = truth + rng.normal(0, [0.05, 0.05, 0.02], (n, 7, 3))
+    got = parts.score(gsc, gparams, cand)
+    want = np.stack([omaps[i].score(osc, oparams, cand[i]) for i in range(n)])
+    if gm_mode:
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    else:
+        assert np.array_equal(got, want)
+    assert len(set(np.round(want[:, 0], 12))) > 1  # the maps really differ
+    # lock-step hill climbing
+    init = truth + rng.normal(0, [0.04, 0.04, 0.02], (n, 3))
+    active = np.ones(n, np.uint8); active[5] = 0
+    poses, probs, tested = parts.match_hc(gsc, gparams, init, 6, 0.1, 0.1, active=active)
+    for i in range(n):
+        if not active[i]:
+            assert tested[i] == 0 and np.array_equal(poses[i], init[i])
+            continue
+        m = ob.MatchResult()
+        ob.orc.orc_match_hill_climbing(omaps[i].h_, C.byref(osc.s), C.byref(oparams), *init[i], 6, 0.1, 0.1, C.byref(m), None)
+        assert tested[i] == m.poses_tested, i
+        assert np.array_equal(poses[i] - init[i], [m.dx, m.dy, m.dth]), i
+        if gm_mode:
+            assert abs(probs[i] - m.best_prob) <= RTOL * abs(m.best_prob)
+        else:
+            assert probs[i] == m.best_prob
+    assert tested[active > 0].min() > 30
+    gsc.close(); parts.close()
+
+
+def test_resample_copies_maps_on_device(sg, gpu):
+    rng = np.random.default_rng(4100)
+    n = 8
+    parts, omaps, truth = _build(sg, gpu, rng, n, ob.CELL_GMAPPING, size=96, scans=2)
+    src = np.array([3, 3, 2, 7, 3, 5, 0, 7], np.int32)   # multinomial draw: duplicates, a kept-in-place particle, dropped ones
+    parts.resample(src)
+    after = [omaps[s] for s in src]
+    _check_maps(parts, after)
+    # copies are independent: updating one does not touch its siblings
+    r, a = room_scan(rng, 91, 2 * np.pi, half_w=3.0, half_h=2.5, pose=truth)
+    gsc = sg.Scan(gpu, r, a)
+    upd = np.zeros(n, np.uint8); upd[1] = 1
+    parts.append_scan(gsc, np.tile(truth, (n, 1)), do_update=upd)
+    clone = ob.OracleMap(model=ob.CELL_GMAPPING, handle=ob.orc.orc_map_clone(omaps[3].h_), owner=True)
+    clone.append_scan(ob.OracleScan(r, a), truth, 1.0, 0, ob.estimator())
+    after[1] = clone
+    _check_maps(parts, after)
+    gsc.close(); parts.close()
