@@ -283,6 +283,17 @@ int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *scans, int32_
                           const double *windows /* 4*M */, int64_t M, const double pose[3],
                           const slamgpu_spe_params *spe, double *out_bounds /* M */);
 
+/* BruteForceMultiResolutionScanMatcher::process_scan (src/core/scan_matchers/bf_multi_res_scan_matcher.h:24-66)
+ * over M3RSMEngine (m3rsm_engine.h:252-365): best-first branch and bound over (rotation, translation
+ * window).  The scan is the FILTERED polar scan (output of the SPE's filter_scan) with one weight per
+ * point (NULL: 1/n); it is pre-rotated per rotation hypothesis on the host (libm) like upstream.
+ * out_delta = {dx, dy, dtheta} of the first finest match popped, *out_prob its probability.
+ * stats: [0] matches scored, [1] K5 calls, [2] branches, [3] rotation hypotheses. */
+int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *range, const double *angle, const double *weight,
+                        const double pose[3], const slamgpu_spe_params *spe, double x_limit, double y_limit, double rot_limit,
+                        double ang_step, double transl_step, double max_finest_prob_diff, double out_delta[3],
+                        double *out_prob, int64_t stats[4]);
+
 /* ------------------------------------------------------------------ K6: GMapping particles
  * replaces the per-particle loop of GmappingParticleFilter::handle_observation
  * (src/slams/gmapping/gmapping_particle_filter.h:70-85): n particles, each with its OWN device map.

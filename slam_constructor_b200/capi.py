@@ -68,7 +68,7 @@ SYMBOLS = [
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
-    "slamgpu_pyramid_append_scan", "slamgpu_score_windows", "slamgpu_particles_create", "slamgpu_particles_destroy",
+    "slamgpu_pyramid_append_scan", "slamgpu_score_windows", "slamgpu_match_m3rsm", "slamgpu_particles_create", "slamgpu_particles_destroy",
     "slamgpu_particles_count", "slamgpu_particles_map", "slamgpu_particles_score", "slamgpu_particles_match_hc",
     "slamgpu_particles_append_scan", "slamgpu_particles_resample",
 ]
@@ -142,6 +142,7 @@ def lib():
     L.slamgpu_pyramid_rescale.argtypes = [vp, dbl]
     L.slamgpu_pyramid_append_scan.argtypes = [vp, vp, c_dp, dbl, i32, ep, dbl, dbl, c_dp, c_lp]
     L.slamgpu_score_windows.argtypes = [vp, pvp, i32, c_ip, c_dp, i64, c_dp, sp, c_dp]
+    L.slamgpu_match_m3rsm.argtypes = [vp, i32, c_dp, c_dp, c_dp, c_dp, sp, dbl, dbl, dbl, dbl, dbl, dbl, c_dp, c_dp, c_lp]
     L.slamgpu_particles_create.argtypes = [vp, i32, i32, i32, dbl, i32, i32, c_dp, pvp]
     L.slamgpu_particles_destroy.argtypes = [vp]
     L.slamgpu_particles_destroy.restype = None
@@ -452,6 +453,16 @@ class Pyramid:
         self.ctx.check(self.ctx.L.slamgpu_pyramid_append_scan(self.h, scan.h, _dp(pose), quality, margin, C.byref(est), blur,
                                                               max_range, _dp(pq), C.byref(n)))
         return n.value
+
+    def match_m3rsm(self, r, a, pose, params, x_limit=1.0, y_limit=1.0, rot_limit=np.deg2rad(5), ang_step=np.deg2rad(0.1),
+                    transl_step=0.05, max_finest_prob_diff=0.0, weight=None):
+        r, a, pose = _f64(r), _f64(a), _f64(pose)
+        w = _f64(weight) if weight is not None else None
+        delta, prob, st = np.zeros(3), C.c_double(), np.zeros(4, dtype=np.int64)
+        self.ctx.check(self.ctx.L.slamgpu_match_m3rsm(self.h, len(r), _dp(r), _dp(a), _dp(w), _dp(pose), C.byref(params), x_limit,
+                                                      y_limit, rot_limit, ang_step, transl_step, max_finest_prob_diff, _dp(delta),
+                                                      C.byref(prob), st.ctypes.data_as(c_lp)))
+        return delta, prob.value, dict(scored=int(st[0]), calls=int(st[1]), branches=int(st[2]), rotations=int(st[3]))
 
     def score_windows(self, scans, scan_id, windows, pose, params):
         arr = (C.c_void_p * len(scans))(*[s.h for s in scans])

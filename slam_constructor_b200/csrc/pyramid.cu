@@ -528,3 +528,158 @@ extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *sc
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
 }
+
+// ---------------------------------------------------------------- BF-M3RSM matcher (host engine over K5)
+// BruteForceMultiResolutionScanMatcher::process_scan (src/core/scan_matchers/bf_multi_res_scan_matcher.h:24-66)
+// over M3RSMEngine (m3rsm_engine.h:252-365): a best-first branch and bound over (rotation, translation
+// window) matches.  The engine logic (priority queue with the reference's eps comparator, pruning,
+// branching order) runs on the host exactly as upstream; every batch of new matches -- all roots at
+// once, then the 2/4 children of a branch or the 5 point hypotheses of a leaf -- is scored by one K5 call.
+namespace {
+
+bool h_are_equal(double a, double b) {
+  double sc = std::max(1.0, std::max(std::fabs(a), std::fabs(b)));
+  return std::fabs(a - b) <= 1e-7 * sc;
+}
+bool h_less(double a, double b) { return a < b + 2.220446049250313e-16; }
+bool h_less_or_equal(double a, double b) { return h_are_equal(a, b) || h_less(a, b); }
+
+struct HMatch {
+  double bound, rotation, bot, top, left, right;
+  int scan_id;
+  double abs_rotation, drift_amount;
+  double hside() const { return right - left; }
+  double vside() const { return top - bot; }
+  bool is_finest() const { return drift_amount <= 0; }
+  // Match::operator< (m3rsm_engine.h:192-203): true if *this is less preferable
+  bool operator<(const HMatch &that) const {
+    if (!h_are_equal(bound, that.bound)) return h_less(bound, that.bound);
+    if (!h_are_equal(drift_amount, that.drift_amount)) return drift_amount > that.drift_amount;
+    return abs_rotation > that.abs_rotation;
+  }
+};
+
+HMatch make_match(double rot, double bot, double top, double left, double right, int scan_id) {
+  HMatch m;
+  m.bound = 0; m.rotation = rot; m.bot = bot; m.top = top; m.left = left; m.right = right; m.scan_id = scan_id;
+  m.abs_rotation = std::fabs(rot);
+  m.drift_amount = (right - left) + (top - bot);  // hside_len() + vside_len()
+  return m;
+}
+
+}  // namespace
+
+#include <queue>
+#include <set>
+
+extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *range, const double *angle,
+                                   const double *weight, const double pose[3], const slamgpu_spe_params *spe, double x_limit,
+                                   double y_limit, double rot_limit, double ang_step, double transl_step,
+                                   double max_finest_prob_diff, double out_delta[3], double *out_prob, int64_t stats[4]) {
+  if (!p) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  if (n < 0 || (n > 0 && (!range || !angle)) || !pose || !spe || !out_delta || !out_prob || !(ang_step > 0))
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "match_m3rsm: bad argument");
+  slamgpu_spe_params sp = *spe;
+  sp.oope = SLAMGPU_OOPE_MAX; sp.prerotated = 1;
+  // ---- rotations in the engine's order (add_scan_matching_request :291-316)
+  struct Rot { double rot; int scan_id; };
+  std::vector<Rot> rots;
+  const double sector = 2 * rot_limit;
+  for (double rd = 0; h_less_or_equal(2 * rd, sector); rd += ang_step)
+    for (double rot : std::set<double>{rd, -rd}) rots.push_back(Rot{rot, (int)rots.size()});
+  // ---- pre-rotated Cartesian copies of the scan: LaserScan2D::to_cartesian(rot + pose.theta)
+  // (src/core/states/sensor_data.h:156-167, RawTrigonometryProvider: cos(base + angle))
+  static thread_local std::vector<slamgpu_scan *> pool;
+  while (pool.size() < rots.size()) {
+    slamgpu_scan *s = nullptr;
+    SG_TRY(slamgpu_scan_create(ctx, &s));
+    pool.push_back(s);
+  }
+  for (slamgpu_scan *s : pool)
+    if (s->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_STATE, "match_m3rsm: one ctx per thread");
+  std::vector<double> xs(std::max(n, 1)), ys(std::max(n, 1));
+  for (size_t k = 0; k < rots.size(); ++k) {
+    const double base = rots[k].rot + pose[2];
+    for (int i = 0; i < n; ++i) {
+      xs[i] = 0 + range[i] * std::cos(base + angle[i]);
+      ys[i] = 0 + range[i] * std::sin(base + angle[i]);
+    }
+    SG_TRY(slamgpu_scan_upload(pool[k], n, 1, xs.data(), ys.data(), nullptr, nullptr, weight));
+  }
+  int64_t n_scored = 0, n_calls = 0, n_branches = 0;
+  std::vector<int32_t> sid;
+  std::vector<double> win, bounds;
+  auto score = [&](std::vector<HMatch> &ms) -> int {
+    if (ms.empty()) return SLAMGPU_OK;
+    sid.clear(); win.clear();
+    for (const HMatch &m : ms) {
+      sid.push_back(m.scan_id);
+      win.push_back(m.bot); win.push_back(m.top); win.push_back(m.left); win.push_back(m.right);
+    }
+    bounds.resize(ms.size());
+    SG_TRY(slamgpu_score_windows(p, pool.data(), (int32_t)rots.size(), sid.data(), win.data(), (int64_t)ms.size(), pose, &sp,
+                                 bounds.data()));
+    for (size_t k = 0; k < ms.size(); ++k) ms[k].bound = bounds[k];
+    n_scored += (int64_t)ms.size(); ++n_calls;
+    return SLAMGPU_OK;
+  };
+  // ---- engine state (M3RSMEngine :252-289)
+  std::priority_queue<HMatch> queue;
+  double best_finest = 0.0;
+  auto add_match = [&](const HMatch &m) {
+    if (m.bound < best_finest) return;
+    if (m.is_finest()) best_finest = std::max(best_finest, m.bound - max_finest_prob_diff);
+    queue.push(m);
+  };
+  std::vector<HMatch> batch;
+  for (const Rot &r : rots) {
+    batch.push_back(make_match(r.rot, 0, 0, 0, 0, r.scan_id));
+    batch.push_back(make_match(r.rot, -y_limit, y_limit, -x_limit, x_limit, r.scan_id));
+  }
+  SG_TRY(score(batch));
+  for (const HMatch &m : batch) add_match(m);
+  // ---- best-first search (bf_multi_res_scan_matcher.h:44-65, next_best_match :318-333, branch :337-357)
+  for (;;) {
+    HMatch best;
+    bool found = false;
+    while (!queue.empty()) {
+      best = queue.top();
+      queue.pop();
+      const bool horz = h_less(transl_step, best.hside()), vert = h_less(transl_step, best.vside());
+      if (!horz && !vert) { found = true; break; }
+      ++n_branches;
+      const double cx = best.left + best.hside() / 2, cy = best.bot + best.vside() / 2;  // center()
+      batch.clear();
+      auto child = [&](double b, double t, double l, double r) { batch.push_back(make_match(best.rotation, b, t, l, r, best.scan_id)); };
+      if (horz && vert) {  // split4_evenly: left-bot, left-top, right-bot, right-top
+        child(best.bot, cy, best.left, cx); child(cy, best.top, best.left, cx);
+        child(best.bot, cy, cx, best.right); child(cy, best.top, cx, best.right);
+      } else if (horz) {   // split_horz
+        child(best.bot, best.top, best.left, cx); child(best.bot, best.top, cx, best.right);
+      } else {             // split_vert
+        child(best.bot, cy, best.left, best.right); child(cy, best.top, best.left, best.right);
+      }
+      SG_TRY(score(batch));
+      for (const HMatch &m : batch) add_match(m);
+    }
+    if (!found) return sg_fail(ctx, SLAMGPU_E_STATE, "match_m3rsm: the match queue ran empty");
+    if (best.is_finest()) {
+      out_delta[0] = best.left + best.hside() / 2;
+      out_delta[1] = best.bot + best.vside() / 2;
+      out_delta[2] = best.rotation;
+      *out_prob = best.bound;
+      break;
+    }
+    // exact translation hypotheses: the four corners and the centre as point windows
+    const double cx = best.left + best.hside() / 2, cy = best.bot + best.vside() / 2;
+    const double px[5] = {best.left, best.left, best.right, best.right, cx};
+    const double py[5] = {best.bot, best.top, best.bot, best.top, cy};
+    batch.clear();
+    for (int k = 0; k < 5; ++k) batch.push_back(make_match(best.rotation, py[k], py[k], px[k], px[k], best.scan_id));
+    SG_TRY(score(batch));
+    for (const HMatch &m : batch) add_match(m);
+  }
+  if (stats) { stats[0] = n_scored; stats[1] = n_calls; stats[2] = n_branches; stats[3] = (int64_t)rots.size(); }
+  return SLAMGPU_OK;
+}

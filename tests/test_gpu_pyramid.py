@@ -143,3 +143,44 @@ def test_match_bounds_bit_exact(sg, gpu):
     finally:
         ob.orc.orc_pyramid_destroy(op)
         pyr.close(); gm.close()
+
+
+@pytest.mark.parametrize("seed,lims", [(3300, (0.5, 0.5, 3.0, 0.5, 0.05)), (3301, (1.0, 0.6, 2.0, 1.0, 0.1)), (3302, (0.3, 0.3, 0.0, 0.5, 0.02))])
+def test_m3rsm_matcher_matches_reference(sg, gpu, refso, seed, lims):
+    """BruteForceMultiResolutionScanMatcher of the unmodified reference (libslamref.so) vs the host engine over K5:
+    same pose delta, same probability"""
+    rng = np.random.default_rng(seed)
+    w = h = 256
+    model = ob.CELL_MEAN
+    rm = ob.RefMap(w, h, 0.05, model, ob.GROW_PLAIN, pyramid_oie=ob.OIE_DISCREPANCY)
+    gm = sg.GridMap(gpu, w, h, 0.05, model, sg.GROW_PLAIN)
+    pyr = sg.Pyramid(gpu, gm, sg.OIE_DISCREPANCY)
+    oest, gest = ob.estimator(ob.EST_CONST), sg.estimator(sg.EST_CONST)
+    truth = np.array([0.3, -0.2, 0.1])
+    try:
+        for k in range(3):
+            pose = truth + rng.normal(0, [0.1, 0.1, 0.05])
+            r, a = room_scan(rng, 200, 2 * np.pi, pose=pose)
+            occ = np.ones(200, np.uint8)
+            refso.ref_append_scan(rm.h_, 200, ob.dptr(ob.f64(r)), ob.dptr(ob.f64(a)), ob.u8ptr(occ), pose[0], pose[1], pose[2], 1.0, 0,
+                                  C.byref(oest), 0.3, np.inf, 0)
+            gsc = sg.Scan(gpu, r, a)
+            pyr.append_scan(gsc, pose, 1.0, 0, gest, blur=0.3)
+            gsc.close()
+        for lv in range(pyr.levels()):
+            assert np.array_equal(pyr.level(lv), rm.export(lv)), lv
+        xlim, ylim, rot_deg, ang_deg, tstep = lims
+        r, a = room_scan(rng, 120, np.deg2rad(270), pose=truth, noise=0.003)
+        init = truth + np.array([0.11, -0.07, np.deg2rad(0.8)])
+        oparams = ob.spe_params(ob.OOPE_MAX, ob.OIE_DISCREPANCY)
+        m = ob.MatchResult()
+        occ = np.ones(len(r), np.uint8)
+        refso.ref_match_bf_m3rsm(rm.h_, len(r), ob.dptr(ob.f64(r)), ob.dptr(ob.f64(a)), ob.u8ptr(occ), ob.SPW_EVEN, C.byref(oparams),
+                                 *init, xlim, ylim, np.deg2rad(rot_deg), np.deg2rad(ang_deg), tstep, C.byref(m))
+        delta, prob, st = pyr.match_m3rsm(r, a, init, sg.spe_params(sg.OOPE_MAX, sg.OIE_DISCREPANCY, prerotated=1), xlim, ylim,
+                                          np.deg2rad(rot_deg), np.deg2rad(ang_deg), tstep)
+        assert np.array_equal(delta, [m.dx, m.dy, m.dth]), (delta, (m.dx, m.dy, m.dth), st)
+        assert prob == m.best_prob
+        assert st["scored"] > 2 * st["rotations"] and st["branches"] > 3
+    finally:
+        pyr.close(); gm.close()
