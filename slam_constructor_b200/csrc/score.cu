@@ -217,6 +217,106 @@ __global__ void __launch_bounds__(128) k_score_list(ListArgs a) {
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
 }
 
+// ---- small candidate sets (Monte-Carlo batches, hill-climbing rounds, particle rounds): latency, not
+// throughput, is what matters, and one thread per pose would walk its ~1000 dependent gathers alone.
+// Phase 1 spreads the (pose, point) pairs over the whole device -- trig computed in place, no table;
+// phase 2 adds each pose's terms in point order (the reference's FP64 summation order) and feeds the
+// same arg-max.
+struct PointArgs {
+  ListArgs l;
+  const double *thetas;   // distinct thetas (indexed by theta_id)
+  const double *range, *angle;
+  int trig_is_table;      // 1: l.trc/l.trs hold a host (libm) table, 0: sincos here
+  double *terms;          // [Ploc][N]
+  int2 *cellids;          // [Ploc][N] (GMapping cache emulation only)
+};
+
+template <int MODE, bool PREROT, bool GUARD, bool FACTOR>
+__global__ void __launch_bounds__(128) k_point_terms(PointArgs pa) {
+  const ListArgs &a = pa.l;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long p = blockIdx.y;
+  if (i >= a.N) return;
+  const double px = a.poses[3 * p], py = a.poses[3 * p + 1];
+  const MapView &mv = a.views ? a.views[a.view_id[p]] : a.map;
+  const double s = mv.scale, inv_s = 1.0 / mv.scale;
+  double X, Y, rc = 0, rs = 0;
+  bool unsafe_any = false;
+  if (PREROT) {
+    X = sg::add(__ldg(a.sx + i), px); Y = sg::add(__ldg(a.sy + i), py);
+  } else {
+    const int tid = a.theta_id[p];
+    if (pa.trig_is_table) {
+      rc = __ldg(a.trc + (size_t)i * a.T + tid); rs = __ldg(a.trs + (size_t)i * a.T + tid);
+    } else {
+      double sn, cs;
+      sincos(sg::add(pa.thetas[tid], pa.angle[i]), &sn, &cs);
+      rc = sg::mul(pa.range[i], cs); rs = sg::mul(pa.range[i], sn);
+    }
+    X = sg::add(px, rc); Y = sg::add(py, rs);
+  }
+  double prob;
+  if (MODE == SLAMGPU_OOPE_OBSTACLE || MODE == SLAMGPU_OOPE_GMAPPING) {
+    const int cx = grid_cell(X, rc, s, inv_s, GUARD ? 1 : 0, &unsafe_any);
+    const int cy = grid_cell(Y, rs, s, inv_s, GUARD ? 1 : 0, &unsafe_any);
+    if (MODE == SLAMGPU_OOPE_OBSTACLE) {
+      prob = lut_at(mv, cx, cy);
+    } else {
+      prob = gmapping_probability(mv, cx, cy, X, Y, a.gm_th, a.gm_win);
+      if (a.gm_cache) pa.cellids[(size_t)p * a.N + i] = make_int2(cx, cy);
+    }
+  } else {
+    if (GUARD) {
+      double hv = sg::div(a.win_v, 2.0), hh = sg::div(a.win_h, 2.0);
+      bool u;
+      sg::world_to_cell_guard(sg::sub(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+      sg::world_to_cell_guard(sg::add(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+      sg::world_to_cell_guard(sg::sub(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+      sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+    }
+    prob = window_probability<MODE>(mv, X, Y, a.win_v, a.win_h);
+  }
+  // GMapping cache emulation needs the raw probability in phase 2 (the cached value replaces it)
+  double term = prob;
+  if (!(MODE == SLAMGPU_OOPE_GMAPPING && a.gm_cache)) {
+    term = sg::mul(prob, __ldg(a.w + i));
+    if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+  }
+  pa.terms[(size_t)p * a.N + i] = term;
+  if (GUARD && unsafe_any) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
+}
+
+template <bool GMCACHE, bool FACTOR>
+__global__ void __launch_bounds__(128) k_pose_sums(PointArgs pa) {
+  const ListArgs &a = pa.l;
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  if (p < a.Ploc) {
+    const double *t = pa.terms + (size_t)p * a.N;
+    double total = 0;
+    if (GMCACHE) {  // GmappingOccupancyObservationPE's 1-entry cell cache, restarted per pose (quirk Q7)
+      const int2 *c = pa.cellids + (size_t)p * a.N;
+      int cache_x = 0, cache_y = 0;
+      double cache_p = -1;
+      for (int i = 0; i < a.N; ++i) {
+        double prob = t[i];
+        if (c[i].x == cache_x && c[i].y == cache_y && cache_p != -1) prob = cache_p;
+        else { cache_x = c[i].x; cache_y = c[i].y; cache_p = prob; }
+        double term = sg::mul(prob, __ldg(a.w + i));
+        if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+        total = sg::add(total, term);
+      }
+    } else {
+      for (int i = 0; i < a.N; ++i) total = sg::add(total, t[i]);
+    }
+    double score = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
+    a.scores[p] = score;
+    if (score == score) { best_s = score; best_i = a.p0 + p; }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
 // ------------------------------------------------------------------ grid (brute force) path
 struct GridIdxArgs {
   const double *trc, *trs;  // [t*N + i]
@@ -690,6 +790,21 @@ void launch_list_m(slamgpu_ctx *ctx, const ListArgs &a, int nblk, bool prerot, b
   else launch_list_f<MODE, false, false>(ctx, a, nblk, factor);
 }
 
+template <int MODE, bool PREROT, bool GUARD>
+void launch_terms_f(slamgpu_ctx *ctx, const PointArgs &a, dim3 grd, bool factor) {
+  if (factor) k_point_terms<MODE, PREROT, GUARD, true><<<grd, 128, 0, ctx->stream>>>(a);
+  else k_point_terms<MODE, PREROT, GUARD, false><<<grd, 128, 0, ctx->stream>>>(a);
+}
+template <int MODE>
+void launch_terms_m(slamgpu_ctx *ctx, const PointArgs &a, dim3 grd, bool prerot, bool guard, bool factor) {
+  if (prerot) launch_terms_f<MODE, true, false>(ctx, a, grd, factor);
+  else if (guard) launch_terms_f<MODE, false, true>(ctx, a, grd, factor);
+  else launch_terms_f<MODE, false, false>(ctx, a, grd, factor);
+}
+
+#define SG_SMALL_MAX_POSES 8192
+#define SG_SMALL_MAX_TERMS (4ll << 20)
+
 int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   Candidates &c = ctx->cand;
   if (c.kind < 0 || !c.scan) return sg_fail(ctx, SLAMGPU_E_STATE, "no staged candidate set (stage_* first; re-stage after a scan upload)");
@@ -707,7 +822,8 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   memset(c.stats, 0, sizeof c.stats);
   c.stats[1] = c.kind == 1 ? (c.grid_v2 ? 2 : 1) : 0; c.stats[2] = Ploc * N; c.stats[5] = c.grid_R; c.stats[3] = c.p0; c.stats[4] = Ploc;
   if (c.kind == 0) {
-    if (device_trig && c.T > 0 && N > 0) {
+    const bool small = Ploc > 0 && Ploc <= SG_SMALL_MAX_POSES && Ploc * (long long)N <= SG_SMALL_MAX_TERMS && N > 0;
+    if (!small && device_trig && c.T > 0 && N > 0) {
       long long tot = (long long)c.T * N;
       k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.d_thetas.as<double>(), c.T, s->d_range, s->d_angle,
                                                                             N, 1, c.T, c.trc.as<double>(), c.trs.as<double>());
@@ -726,17 +842,46 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       a.gm_th = c.spe.gm_fullness_th; a.gm_win = c.spe.gm_window; a.gm_cache = c.spe.reserved;
       a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>(); a.result = res;
       const bool pre = c.spe.prerotated != 0, fac = s->has_factor;
-      cudaEventRecord(ctx->evk0, ctx->stream);
-      switch (c.spe.oope) {
-        case SLAMGPU_OOPE_OBSTACLE: launch_list_m<SLAMGPU_OOPE_OBSTACLE>(ctx, a, nblk, pre, device_trig, fac); break;
-        case SLAMGPU_OOPE_MAX: launch_list_m<SLAMGPU_OOPE_MAX>(ctx, a, nblk, pre, device_trig, fac); break;
-        case SLAMGPU_OOPE_MEAN: launch_list_m<SLAMGPU_OOPE_MEAN>(ctx, a, nblk, pre, device_trig, fac); break;
-        case SLAMGPU_OOPE_OVERLAP: launch_list_m<SLAMGPU_OOPE_OVERLAP>(ctx, a, nblk, pre, device_trig, fac); break;
-        default: launch_list_m<SLAMGPU_OOPE_GMAPPING>(ctx, a, nblk, pre, device_trig, fac); break;
+      if (small) {
+        c.stats[1] = 3;
+        const bool gmc = c.spe.oope == SLAMGPU_OOPE_GMAPPING && c.spe.reserved != 0;
+        size_t tb = (size_t)Ploc * N * sizeof(double), cb = gmc ? (size_t)Ploc * N * sizeof(int2) : 0;
+        if (ctx->scratch[7].reserve(tb + cb + 64) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "term buffer");
+        PointArgs pa;
+        pa.l = a; pa.thetas = c.d_thetas.as<double>(); pa.range = s->d_range; pa.angle = s->d_angle;
+        pa.trig_is_table = c.trig_is_host ? 1 : 0;
+        pa.terms = ctx->scratch[7].as<double>(); pa.cellids = (int2 *)((char *)ctx->scratch[7].p + tb);
+        dim3 grd((N + 127) / 128, (unsigned)Ploc);
+        cudaEventRecord(ctx->evk0, ctx->stream);
+        switch (c.spe.oope) {
+          case SLAMGPU_OOPE_OBSTACLE: launch_terms_m<SLAMGPU_OOPE_OBSTACLE>(ctx, pa, grd, pre, device_trig, fac); break;
+          case SLAMGPU_OOPE_MAX: launch_terms_m<SLAMGPU_OOPE_MAX>(ctx, pa, grd, pre, device_trig, fac); break;
+          case SLAMGPU_OOPE_MEAN: launch_terms_m<SLAMGPU_OOPE_MEAN>(ctx, pa, grd, pre, device_trig, fac); break;
+          case SLAMGPU_OOPE_OVERLAP: launch_terms_m<SLAMGPU_OOPE_OVERLAP>(ctx, pa, grd, pre, device_trig, fac); break;
+          default: launch_terms_m<SLAMGPU_OOPE_GMAPPING>(ctx, pa, grd, pre, device_trig, fac); break;
+        }
+        cudaEventRecord(ctx->evk1, ctx->stream);
+        ctx->evk_valid = true;
+        if (gmc) {
+          if (fac) k_pose_sums<true, true><<<nblk, 128, 0, ctx->stream>>>(pa);
+          else k_pose_sums<true, false><<<nblk, 128, 0, ctx->stream>>>(pa);
+        } else {
+          k_pose_sums<false, false><<<nblk, 128, 0, ctx->stream>>>(pa);
+        }
+        ctx->launches += 2;
+      } else {
+        cudaEventRecord(ctx->evk0, ctx->stream);
+        switch (c.spe.oope) {
+          case SLAMGPU_OOPE_OBSTACLE: launch_list_m<SLAMGPU_OOPE_OBSTACLE>(ctx, a, nblk, pre, device_trig, fac); break;
+          case SLAMGPU_OOPE_MAX: launch_list_m<SLAMGPU_OOPE_MAX>(ctx, a, nblk, pre, device_trig, fac); break;
+          case SLAMGPU_OOPE_MEAN: launch_list_m<SLAMGPU_OOPE_MEAN>(ctx, a, nblk, pre, device_trig, fac); break;
+          case SLAMGPU_OOPE_OVERLAP: launch_list_m<SLAMGPU_OOPE_OVERLAP>(ctx, a, nblk, pre, device_trig, fac); break;
+          default: launch_list_m<SLAMGPU_OOPE_GMAPPING>(ctx, a, nblk, pre, device_trig, fac); break;
+        }
+        cudaEventRecord(ctx->evk1, ctx->stream);
+        ctx->evk_valid = true;
+        SG_LAUNCHED(ctx);
       }
-      cudaEventRecord(ctx->evk1, ctx->stream);
-      ctx->evk_valid = true;
-      SG_LAUNCHED(ctx);
     }
   } else {
     const int nt_loc = c.t_hi - c.t_lo + 1;

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Per-call latency of the small-batch paths (BASELINE configs[0] and configs[1] shapes): one Monte-Carlo
+batch (100 poses x 360 beams, 100x100 map @0.1) and one hill-climbing round (6 poses x 1081 beams,
+800x800 @0.05), scan insertion (const / area) and the world-level loop; prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import slam_constructor_b200 as sg  # noqa: E402
+
+
+def timeit(fn, n=200, warm=20):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    return (time.perf_counter() - t0) / n * 1e6
+
+
+def main():
+    ctx = sg.Context(0)
+    rng = np.random.default_rng(1)
+    out = {}
+    for name, size, scale, beams, fov, P, model, est_kind in (
+            ("tiny_mc_batch", 100, 0.1, 360, 2 * np.pi, 100, sg.CELL_MEAN, sg.EST_CONST),
+            ("viny_hc_round", 800, 0.05, 1081, 1.5 * np.pi, 6, sg.CELL_TBM_CONSISTENT, sg.EST_AREA)):
+        hw, hh = size * scale * 0.35, size * scale * 0.3
+        gm = sg.GridMap(ctx, size, size, scale, model, sg.GROW_PLAIN)
+        pose = np.array([0.3, -0.2, 0.1])
+        r, a = bench.room_ranges(rng, beams, fov, hw, hh, pose, 0.01)
+        scan = sg.Scan(ctx, r, a)
+        tbm = model == sg.CELL_TBM_CONSISTENT
+        est = sg.estimator(est_kind, occ=(0.95, 0.04) if tbm else (0.95, 1.0), empty=(0.01, 0.003) if tbm else (0.01, 1.0), shift=0.01 * scale)
+        for _ in range(5):
+            cells = ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3)
+        poses = pose + rng.normal(0, [0.1, 0.1, 0.05], (P, 3))
+        params = sg.spe_params()
+        e2e = timeit(lambda: ctx.score_poses(gm, scan, params, poses, want_scores=True))
+        ctx.stage_poses(scan, params, poses)
+
+        def dev():
+            ctx.timer_begin(); ctx.score_launch(gm); return ctx.timer_end()
+        for _ in range(20):
+            dev()
+        dev_us = float(np.median([dev() for _ in range(200)])) * 1e3
+        upd = timeit(lambda: ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3), n=50, warm=5)
+        out[name] = {"poses": P, "beams": beams, "score_call_e2e_us": round(e2e, 1), "score_device_us": round(dev_us, 1),
+                     "evals_per_s_e2e": P * beams / (e2e * 1e-6), "append_scan_e2e_us": round(upd, 1), "cells_per_scan": int(cells),
+                     "cell_updates_per_s": cells / (upd * 1e-6)}
+        gm.close(); scan.close()
+    ctx.close()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
