@@ -275,6 +275,10 @@ int slamgpu_pyramid_rescale(slamgpu_pyramid *p, double target_scale); /* level i
 int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const double pose[3], double scan_quality,
                                 int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
                                 const double *point_quality, int64_t *cells_updated);
+/* the same for explicit beams (see slamgpu_append_beams): what a drop-in scan adder flushes */
+int slamgpu_pyramid_append_beams(slamgpu_pyramid *p, int32_t n, const double *beams /* 4*n */, const uint8_t *is_occ,
+                                 const double *quality, const slamgpu_estimator *est, double blur, double max_range,
+                                 int64_t *cells_updated);
 /* batched Match bounds: M windows, each over one of the pre-rotated scans.  windows =
  * {bot, top, left, right} per match (metres, relative to pose); bound[m] = scan probability
  * of scans[scan_id[m]] at the window centre on the level rescale(max side) with the `max`

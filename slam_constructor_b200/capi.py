@@ -68,7 +68,7 @@ SYMBOLS = [
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
-    "slamgpu_pyramid_append_scan", "slamgpu_score_windows", "slamgpu_match_m3rsm", "slamgpu_particles_create", "slamgpu_particles_destroy",
+    "slamgpu_pyramid_append_scan", "slamgpu_pyramid_append_beams", "slamgpu_score_windows", "slamgpu_match_m3rsm", "slamgpu_particles_create", "slamgpu_particles_destroy",
     "slamgpu_particles_count", "slamgpu_particles_map", "slamgpu_particles_score", "slamgpu_particles_match_hc",
     "slamgpu_particles_append_scan", "slamgpu_particles_resample",
 ]
@@ -141,6 +141,7 @@ def lib():
     L.slamgpu_pyramid_level_download.argtypes = [vp, i32, c_dp, c_dp]
     L.slamgpu_pyramid_rescale.argtypes = [vp, dbl]
     L.slamgpu_pyramid_append_scan.argtypes = [vp, vp, c_dp, dbl, i32, ep, dbl, dbl, c_dp, c_lp]
+    L.slamgpu_pyramid_append_beams.argtypes = [vp, i32, c_dp, c_u8p, c_dp, ep, dbl, dbl, c_lp]
     L.slamgpu_score_windows.argtypes = [vp, pvp, i32, c_ip, c_dp, i64, c_dp, sp, c_dp]
     L.slamgpu_match_m3rsm.argtypes = [vp, i32, c_dp, c_dp, c_dp, c_dp, sp, dbl, dbl, dbl, dbl, dbl, dbl, c_dp, c_dp, c_lp]
     L.slamgpu_particles_create.argtypes = [vp, i32, i32, i32, dbl, i32, i32, c_dp, pvp]

@@ -637,15 +637,10 @@ extern "C" int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_s
                              cells_updated, nullptr);
 }
 
-extern "C" int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
-                                    const double *quality, const slamgpu_estimator *est, double blur, double max_range,
-                                    int64_t *cells_updated) {
-  if (!ctx || !map || n < 0 || (n > 0 && (!beams || !is_occ || !quality)) || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_beams: bad argument");
-  if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
-  if (map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_scan");
-  if (cells_updated) *cells_updated = 0;
-  if (n == 0) return SLAMGPU_OK;
-  BeamPlan plan;
+// beams given explicitly (the arguments of GridMapScanAdder::handle_scan_point) -> plan
+int sg_plan_from_beams(slamgpu_ctx *ctx, const slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
+                       const double *quality, double blur, double max_range, BeamPlan *out) {
+  BeamPlan &plan = *out;
   const double scale = map->scale;
   const double px = beams[0], py = beams[1];
   plan.px = px; plan.py = py;
@@ -678,6 +673,19 @@ extern "C" int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t 
   }
   plan.offsets[n] = total;
   plan.M = total;
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
+                                    const double *quality, const slamgpu_estimator *est, double blur, double max_range,
+                                    int64_t *cells_updated) {
+  if (!ctx || !map || n < 0 || (n > 0 && (!beams || !is_occ || !quality)) || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_beams: bad argument");
+  if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
+  if (map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_beams");
+  if (cells_updated) *cells_updated = 0;
+  if (n == 0) return SLAMGPU_OK;
+  BeamPlan plan;
+  SG_TRY(sg_plan_from_beams(ctx, map, n, beams, is_occ, quality, blur, max_range, &plan));
   return sg_append_plan(ctx, map, plan, est, cells_updated, nullptr);
 }
 

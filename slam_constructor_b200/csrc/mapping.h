@@ -47,6 +47,8 @@ struct AppendTrace {  // what a pyramid needs from a scan insertion (device poin
 int sg_map_regrow(slamgpu_map *m, const GrowState &g);
 int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double pose[3], double scan_quality, int scan_margin,
                      double blur, double max_range, const double *point_quality, bool gate, BeamPlan *plan);
+int sg_plan_from_beams(slamgpu_ctx *ctx, const slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
+                       const double *quality, double blur, double max_range, BeamPlan *out);
 int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, const slamgpu_estimator *est,
                    int64_t *cells_updated, AppendTrace *trace);
 int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,

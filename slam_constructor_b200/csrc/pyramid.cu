@@ -395,17 +395,10 @@ extern "C" int slamgpu_pyramid_build(slamgpu_pyramid *p) {
   return SLAMGPU_OK;
 }
 
-extern "C" int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const double pose[3], double scan_quality,
-                                           int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
-                                           const double *point_quality, int64_t *cells_updated) {
-  if (!p) return SLAMGPU_E_INVALID;
+// walk the coarser levels for one scan insertion into the fine map (trace = what K3 recorded)
+static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
   slamgpu_ctx *ctx = p->ctx;
   slamgpu_map *fine = p->lv[0];
-  SG_TRY(ensure_continuous(p));
-  AppendTrace tr;
-  tr.oie = p->oie;
-  SG_TRY(sg_append_scan_impl(ctx, fine, scan, pose, scan_quality, scan_margin, est, blur, max_range, point_quality,
-                             cells_updated, &tr));
   const long long M = tr.M;
   if (M == 0) return SLAMGPU_OK;
   // per-position arrays: ent_slot (i32) coords (int2) keys vals keys_tmp vals_tmp (u32) alive alive_next (u8) counters
@@ -467,6 +460,35 @@ extern "C" int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *sca
   }
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const double pose[3], double scan_quality,
+                                           int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
+                                           const double *point_quality, int64_t *cells_updated) {
+  if (!p) return SLAMGPU_E_INVALID;
+  SG_TRY(ensure_continuous(p));
+  AppendTrace tr;
+  tr.oie = p->oie;
+  SG_TRY(sg_append_scan_impl(p->ctx, p->lv[0], scan, pose, scan_quality, scan_margin, est, blur, max_range, point_quality,
+                             cells_updated, &tr));
+  return pyramid_propagate(p, tr);
+}
+
+extern "C" int slamgpu_pyramid_append_beams(slamgpu_pyramid *p, int32_t n, const double *beams, const uint8_t *is_occ,
+                                            const double *quality, const slamgpu_estimator *est, double blur, double max_range,
+                                            int64_t *cells_updated) {
+  if (!p) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  if (n < 0 || (n > 0 && (!beams || !is_occ || !quality)) || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "pyramid_append_beams: bad argument");
+  if (cells_updated) *cells_updated = 0;
+  if (n == 0) return SLAMGPU_OK;
+  SG_TRY(ensure_continuous(p));
+  BeamPlan plan;
+  SG_TRY(sg_plan_from_beams(ctx, p->lv[0], n, beams, is_occ, quality, blur, max_range, &plan));
+  AppendTrace tr;
+  tr.oie = p->oie;
+  SG_TRY(sg_append_plan(ctx, p->lv[0], plan, est, cells_updated, &tr));
+  return pyramid_propagate(p, tr);
 }
 
 extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *scans, int32_t n_scans, const int32_t *scan_id,

@@ -10,6 +10,8 @@
 //   slamgpu::CudaPoseEnumerationScanMatcher<PE> : GridScanMatcher   any copyable PoseEnumerator (Monte-Carlo, hill climbing,
 //                                                 polar brute force) by speculative batches on K1 (list kernel)
 //   slamgpu::CudaMonteCarloScanMatcher, slamgpu::CudaHillClimbingScanMatcher   the two stock instances
+//   slamgpu::CudaPyramidGridMap     : CudaGridMap        fine map + max-pyramid (M3RSMRescalableGridMap)
+//   slamgpu::CudaBfMultiResScanMatcher : GridScanMatcher BruteForceMultiResolutionScanMatcher on K5
 //
 // They drop into SingleStateHypothesisLSGWProperties{grid_map, gsm, gmsa}
 // (src/core/states/single_state_hypothesis_laser_scan_grid_world.h:13-21) and hence into the
@@ -33,6 +35,7 @@
 #include "src/core/maps/grid_map_scan_adders.h"
 #include "src/core/maps/naive_grid_cells.h"
 #include "src/core/maps/tbm_grid_cells.h"
+#include "src/core/scan_matchers/bf_multi_res_scan_matcher.h"
 #include "src/core/scan_matchers/brute_force_scan_matcher.h"
 #include "src/core/scan_matchers/grid_scan_matcher.h"
 #include "src/core/scan_matchers/hill_climbing_scan_matcher.h"
@@ -221,13 +224,19 @@ public:
     std::vector<uint8_t> occ;
     std::vector<double> quality;
     beams.swap(_q_beams); occ.swap(_q_occ); quality.swap(_q_quality);  // re-entrancy: the queue is empty from here on
-    int64_t n = 0;
-    _ctx->check(slamgpu_append_beams(_ctx->handle(), _map, (int32_t)occ.size(), beams.data(), occ.data(), quality.data(),
-                                     &_q_params.est, _q_params.blur, _q_params.max_range, &n));
-    _cells_updated += n;
+    _cells_updated += append_beams_on_device((int32_t)occ.size(), beams.data(), occ.data(), quality.data(), _q_params);
     const_cast<CudaGridMap *>(this)->touched();
   }
   int64_t cells_updated() const { return _cells_updated; }
+
+protected:
+  virtual int64_t append_beams_on_device(int32_t n, const double *beams, const uint8_t *occ, const double *quality,
+                                         const AdderParams &p) const {
+    int64_t cells = 0;
+    _ctx->check(slamgpu_append_beams(_ctx->handle(), _map, n, beams, occ, quality, &p.est, p.blur, p.max_range, &cells));
+    return cells;
+  }
+  slamgpu_map *raw_device_map() const { return _map; }
 
 private:
   void touched() { _mirror_valid = false; refresh_info(); }
@@ -675,6 +684,81 @@ private:
   std::vector<double> _dx, _dy, _dt;
   bool _base_pose_is_set = false;
   RobotPose _base_pose;
+};
+
+//============================================================================//
+// CudaPyramidGridMap: M3RSMRescalableGridMap<UnboundedPlainGridMap> on the device
+// (src/core/scan_matchers/m3rsm_engine.h:17-131): the fine map plus its max-pyramid; scan insertion keeps
+// every level up to date with the reference's incremental rule.
+class CudaPyramidGridMap : public CudaGridMap {
+public:
+  CudaPyramidGridMap(std::shared_ptr<Context> ctx, std::shared_ptr<ObservationImpactEstimator> oie,
+                     std::shared_ptr<GridCell> prototype, const GridMapParams &params = MapValues::gmp,
+                     int grow = SLAMGPU_GROW_PLAIN)
+    : CudaGridMap{ctx, prototype, params, grow} {
+    int oie_id = SLAMGPU_OIE_DISCREPANCY;
+    if (dynamic_cast<const OccupancyOIE *>(oie.get())) oie_id = SLAMGPU_OIE_OCCUPANCY;
+    else if (!dynamic_cast<const DiscrepancyOIE *>(oie.get())) throw std::logic_error("CudaPyramidGridMap: unknown OIE class");
+    context()->check(slamgpu_pyramid_create(context()->handle(), raw_device_map(), oie_id, &_pyr));
+  }
+  ~CudaPyramidGridMap() override { slamgpu_pyramid_destroy(_pyr); }
+  slamgpu_pyramid *pyramid() const { flush(); return _pyr; }
+  int levels() const { flush(); return slamgpu_pyramid_levels(_pyr); }
+  void update(const Coord &, const AreaOccupancyObservation &) override {
+    throw std::logic_error("CudaPyramidGridMap: cells are updated through a scan adder (whole scans)");
+  }
+  void reset(const Coord &, const GridCell &) override {
+    throw std::logic_error("CudaPyramidGridMap: cells are updated through a scan adder (whole scans)");
+  }
+protected:
+  int64_t append_beams_on_device(int32_t n, const double *beams, const uint8_t *occ, const double *quality,
+                                 const AdderParams &p) const override {
+    int64_t cells = 0;
+    context()->check(slamgpu_pyramid_append_beams(_pyr, n, beams, occ, quality, &p.est, p.blur, p.max_range, &cells));
+    return cells;
+  }
+private:
+  slamgpu_pyramid *_pyr = nullptr;
+};
+
+// BruteForceMultiResolutionScanMatcher (src/core/scan_matchers/bf_multi_res_scan_matcher.h:9-71) on the device:
+// the branch-and-bound engine runs in the library, every batch of Match bounds is one K5 launch.
+class CudaBfMultiResScanMatcher : public GridScanMatcher {
+public:
+  CudaBfMultiResScanMatcher(std::shared_ptr<Context> ctx, SPE est, std::shared_ptr<ScanPointWeighting> spw, double x_limit = 1,
+                            double y_limit = 1, double rot_limit = deg2rad(5), double ang_step = deg2rad(0.1),
+                            double transl_step = 0.05)
+    : GridScanMatcher{est, x_limit, y_limit, rot_limit}, _ctx{ctx}, _spw{spw}, _ang_step{ang_step}, _transl_step{transl_step} {}
+
+  void set_target_accuracy(double angle_step, double translation_step) { _ang_step = angle_step; _transl_step = translation_step; }
+
+  double process_scan(const TransformedLaserScan &raw_scan, const RobotPose &pose, const GridMap &map,
+                      RobotPoseDelta &result_pose_delta) override {
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_start(pose, raw_scan, map); });
+    auto pm = dynamic_cast<const CudaPyramidGridMap *>(&map);
+    if (!pm) { throw std::logic_error("CudaBfMultiResScanMatcher needs a CudaPyramidGridMap"); }
+    auto setup = detect_score_setup(*scan_probability_estimator());
+    if (setup.oope != SLAMGPU_OOPE_MAX || setup.generic_oie) { throw std::logic_error("CudaBfMultiResScanMatcher: max OOPE expected"); }
+    auto fscan = filter_scan(raw_scan.scan, pose, map);
+    const auto &pts = fscan.points();
+    std::vector<double> r(pts.size()), a(pts.size()), w(pts.size());
+    for (std::size_t i = 0; i < pts.size(); ++i) { r[i] = pts[i].range(); a[i] = pts[i].angle(); w[i] = _spw->weight(pts, i); }
+    auto params = make_spe_params(setup, SLAMGPU_TRIG_HOST);
+    params.prerotated = 1;
+    const double p3[3] = {pose.x, pose.y, pose.theta};
+    double delta[3], prob = 0;
+    _ctx->check(slamgpu_match_m3rsm(pm->pyramid(), (int32_t)pts.size(), r.data(), a.data(), w.data(), p3, &params, max_x_error(),
+                                    max_y_error(), max_th_error(), _ang_step, _transl_step, 0.0, delta, &prob, _stats));
+    result_pose_delta = RobotPoseDelta{delta[0], delta[1], delta[2]};
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(result_pose_delta, fscan, prob); });
+    return prob;
+  }
+  const int64_t *stats() const { return _stats; }  // matches scored, K5 calls, branches, rotations
+private:
+  std::shared_ptr<Context> _ctx;
+  std::shared_ptr<ScanPointWeighting> _spw;
+  double _ang_step, _transl_step;
+  int64_t _stats[4] = {0, 0, 0, 0};
 };
 
 }  // namespace slamgpu

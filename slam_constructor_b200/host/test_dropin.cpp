@@ -7,6 +7,8 @@
 
 #include "slamgpu_backend.h"
 #include "src/core/maps/plain_grid_map.h"
+#include "src/core/maps/rescalable_caching_grid_map.h"
+#include "src/core/scan_matchers/m3rsm_engine.h"
 #include "src/core/states/single_state_hypothesis_laser_scan_grid_world.h"
 
 namespace {
@@ -193,6 +195,55 @@ void run_host_map(std::shared_ptr<slamgpu::Context> ctx) {
   }
 }
 
+// BF-M3RSM: the reference's M3RSMRescalableGridMap + BruteForceMultiResolutionScanMatcher world vs the CUDA pair
+void run_m3rsm(std::shared_ptr<slamgpu::Context> ctx) {
+  std::printf("== BF-M3RSM world: pyramid map + multi-resolution matcher\n");
+  GridMapParams gmp{160, 160, 0.05};
+  auto mk_spe = [](std::shared_ptr<ScanPointWeighting> spw) {
+    auto oope = std::make_shared<MaxOccupancyObservationPE>(std::make_shared<DiscrepancyOIE>());
+    return std::make_shared<WeightedMeanPointProbabilitySPE>(oope, spw);
+  };
+  auto spw1 = make_spw(0), spw2 = make_spw(0);
+  SingleStateHypothesisLSGWProperties pr, pg;
+  pr.localized_scan_quality = pg.localized_scan_quality = 0.9;
+  pr.raw_scan_quality = pg.raw_scan_quality = 0.6;
+  auto proto = std::make_shared<MeanProbabilityCell>();
+  pr.grid_map = std::make_shared<M3RSMRescalableGridMap<UnboundedPlainGridMap>>(std::make_shared<DiscrepancyOIE>(), proto, gmp);
+  pr.gsm = std::make_shared<BruteForceMultiResolutionScanMatcher>(mk_spe(spw1), 0.4, 0.4, deg2rad(3), deg2rad(0.5), 0.05);
+  auto est = std::make_shared<ConstOccupancyEstimator>(Occupancy{0.95, 1.0}, Occupancy{0.01, 1.0});
+  pr.gmsa = WallDistanceBlurringScanAdder::builder().set_blur_distance(0.3).set_occupancy_estimator(est)
+              .set_observation_quality_estimator(std::make_shared<IdleOMQE>()).build();
+  pg.grid_map = std::make_shared<slamgpu::CudaPyramidGridMap>(ctx, std::make_shared<DiscrepancyOIE>(), proto, gmp, SLAMGPU_GROW_PLAIN);
+  auto gsm = std::make_shared<slamgpu::CudaBfMultiResScanMatcher>(ctx, mk_spe(spw2), spw2, 0.4, 0.4, deg2rad(3), deg2rad(0.5), 0.05);
+  pg.gsm = gsm;
+  slamgpu::CudaScanAdder::Properties ap;
+  ap.blur_distance = 0.3;
+  pg.gmsa = std::make_shared<slamgpu::CudaScanAdder>(ap);
+  SingleStateHypothesisLaserScanGridWorld ref_world{pr}, gpu_world{pg};
+  std::mt19937 rng(21);
+  std::normal_distribution<double> odo(0.0, 0.03), odo_t(0.0, 0.01);
+  RobotPose truth{0.1, 0.2, -0.1};
+  for (int step = 0; step < 6; ++step) {
+    RobotPoseDelta motion = step == 0 ? RobotPoseDelta{truth.x, truth.y, truth.theta} : RobotPoseDelta{0.07, -0.04, 0.02};
+    if (step > 0) { truth += motion; }
+    RobotPoseDelta odom = step == 0 ? motion : RobotPoseDelta{motion.x + odo(rng), motion.y + odo(rng), motion.theta + odo_t(rng)};
+    auto scan = room_scan(truth, 181, 2 * M_PI, 3.0, 2.5, rng, 0.01);
+    TransformedLaserScan a{odom, scan, 1.0}, b{odom, scan, 1.0};
+    b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+    ref_world.handle_sensor_data(a);
+    gpu_world.handle_sensor_data(b);
+    const RobotPose &p1 = ref_world.pose(), &p2 = gpu_world.pose();
+    CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "m3rsm step %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)", step, p1.x,
+          p1.y, p1.theta, p2.x, p2.y, p2.theta);
+    if (g_failed > 5) return;
+  }
+  ref_world.map().rescale(0);
+  same_cells(ref_world.map(), gpu_world.map(), "m3rsm fine level");
+  std::printf("   6 scans; last scan: %ld matches scored in %ld K5 calls, %ld branches, %ld rotations; final pose %.6f %.6f %.6f\n",
+              (long)gsm->stats()[0], (long)gsm->stats()[1], (long)gsm->stats()[2], (long)gsm->stats()[3], gpu_world.pose().x,
+              gpu_world.pose().y, gpu_world.pose().theta);
+}
+
 }  // namespace
 
 int main() {
@@ -217,6 +268,7 @@ int main() {
     run_world_pair(hc, ctx);
     run_world_pair(bf, ctx);
     run_host_map(ctx);
+    run_m3rsm(ctx);
   } catch (const std::exception &e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 1;
