@@ -88,6 +88,10 @@ enum { SLAMGPU_EST_CONST = 0, SLAMGPU_EST_AREA = 1 };
  *            point that lands within a guard band of a cell border is recomputed with
  *            HOST trig before the result is returned, so cell indices stay bit-exact */
 enum { SLAMGPU_TRIG_DEVICE = 0, SLAMGPU_TRIG_HOST = 1 };
+/* ScanPointWeighting: src/core/scan_matchers/weighted_mean_point_probability_spe.h:21-60 */
+enum { SLAMGPU_SPW_EVEN = 0, SLAMGPU_SPW_VINY = 1, SLAMGPU_SPW_AHR = 2 };
+/* ObservationMappingQualityEstimator: src/core/maps/grid_map_scan_adders.h:22-46 */
+enum { SLAMGPU_OMQE_IDLE = 0, SLAMGPU_OMQE_AHR = 1 };
 
 typedef struct slamgpu_ctx slamgpu_ctx;
 typedef struct slamgpu_map slamgpu_map;
@@ -183,6 +187,17 @@ void slamgpu_scan_destroy(slamgpu_scan *s);
 int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian, const double *a /* range | x */,
                         const double *b /* angle | y */, const uint8_t *occ /* NULL: all occupied */,
                         const double *factor /* NULL: 1.0 */, const double *weight /* NULL: 1/n */);
+
+/* per-scan host preparation for callers that do not link the reference's C++ classes (O(n), libm, no GPU):
+ * WeightedMeanPointProbabilitySPE::filter_scan + should_skip_point (weighted_mean_point_probability_spe.h:75-95,
+ * 136-141) -> indices of the points kept, returns their count; the point weights of EvenSPW / VinySlamSPW /
+ * AngleHistogramReciprocalSPW (:21-60) for the FILTERED points; the per-point mapping quality of IdleOMQE /
+ * AngleHistogramResiprocalOMQE (grid_map_scan_adders.h:22-46) for the RAW points. */
+int slamgpu_scan_filter(const slamgpu_map *m, int32_t n, const double *range, const double *angle, const uint8_t *occ,
+                        const double pose[3], uint32_t skip_rate, double max_range, int32_t *keep_idx /* n */);
+int slamgpu_point_weights(int32_t kind /* SLAMGPU_SPW_* */, int32_t n, const double *range, const double *angle, double *out_w);
+int slamgpu_mapping_quality(int32_t kind /* SLAMGPU_OMQE_* */, int32_t n, const double *range, const double *angle,
+                            double *out_q);
 
 /* ------------------------------------------------------------------ K1: batched scan likelihood
  * replaces the candidate loop of PoseEnumerationScanMatcher::process_scan

@@ -17,6 +17,8 @@ OOPE_OBSTACLE, OOPE_MAX, OOPE_MEAN, OOPE_OVERLAP, OOPE_GMAPPING = range(5)
 GROW_NONE, GROW_PLAIN, GROW_TILED = range(3)
 EST_CONST, EST_AREA = 0, 1
 TRIG_DEVICE, TRIG_HOST = 0, 1
+SPW_EVEN, SPW_VINY, SPW_AHR = range(3)
+OMQE_IDLE, OMQE_AHR = 0, 1
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -51,6 +53,26 @@ class SlamGpuError(RuntimeError):
         self.code = code
 
 
+def point_weights(kind, r, a):
+    """ScanPointWeighting of the filtered points (host, libm)"""
+    r, a = _f64(r), _f64(a)
+    w = np.empty(len(r))
+    rc = lib().slamgpu_point_weights(kind, len(r), _dp(r), _dp(a), _dp(w))
+    if rc != 0:
+        raise SlamGpuError(rc, "slamgpu_point_weights")
+    return w
+
+
+def mapping_quality(kind, r, a):
+    """ObservationMappingQualityEstimator of the raw points (host, libm)"""
+    r, a = _f64(r), _f64(a)
+    q = np.empty(len(r))
+    rc = lib().slamgpu_mapping_quality(kind, len(r), _dp(r), _dp(a), _dp(q))
+    if rc != 0:
+        raise SlamGpuError(rc, "slamgpu_mapping_quality")
+    return q
+
+
 def library_path():
     return os.path.join(HERE, "lib", "libslamgpu.so")
 
@@ -64,7 +86,7 @@ SYMBOLS = [
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
-    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_stage_poses",
+    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_stage_poses",
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
@@ -118,6 +140,9 @@ def lib():
     L.slamgpu_scan_destroy.argtypes = [vp]
     L.slamgpu_scan_destroy.restype = None
     L.slamgpu_scan_upload.argtypes = [vp, i32, i32, c_dp, c_dp, c_u8p, c_dp, c_dp]
+    L.slamgpu_scan_filter.argtypes = [vp, i32, c_dp, c_dp, c_u8p, c_dp, C.c_uint32, dbl, c_ip]
+    L.slamgpu_point_weights.argtypes = [i32, i32, c_dp, c_dp, c_dp]
+    L.slamgpu_mapping_quality.argtypes = [i32, i32, c_dp, c_dp, c_dp]
     sp = C.POINTER(SpeParams)
     L.slamgpu_score_poses.argtypes = [vp, vp, vp, sp, c_dp, i64, dbl, c_dp, c_lp, c_dp]
     L.slamgpu_score_grid.argtypes = [vp, vp, vp, sp, c_dp, i32, c_dp, i32, c_dp, i32, dbl, c_dp, c_lp, c_dp]
@@ -360,6 +385,17 @@ class GridMap:
         ox = w // 2 if ox is None else ox
         oy = h // 2 if oy is None else oy
         self.ctx.check(self.ctx.L.slamgpu_map_upload_lut(self.h, oie, _dp(lut), unknown_value, w, h, ox, oy))
+
+    def filter_scan(self, r, a, pose, occ=None, skip_rate=0, max_range=-1.0):
+        """indices of the points WeightedMeanPointProbabilitySPE::filter_scan keeps"""
+        r, a, pose = _f64(r), _f64(a), _f64(pose)
+        o = np.ascontiguousarray(occ, dtype=np.uint8) if occ is not None else None
+        keep = np.zeros(len(r), dtype=np.int32)
+        k = self.ctx.L.slamgpu_scan_filter(self.h, len(r), _dp(r), _dp(a), o.ctypes.data_as(c_u8p) if o is not None else None,
+                                           _dp(pose), skip_rate, max_range, keep.ctypes.data_as(c_ip))
+        if k < 0:
+            self.ctx.check(k)
+        return keep[:k]
 
     def read_cell(self, x, y):
         rec = np.zeros(8)

@@ -488,3 +488,90 @@ extern "C" int slamgpu_map_upload_lut(slamgpu_map *m, int32_t oie, const double 
   m->lut_valid[1 - oie] = false;
   return SLAMGPU_OK;
 }
+
+// ------------------------------------------------------------------ per-scan host preparation
+// (once per scan, O(n), libm; the reference does the same work on the host before its hot loops)
+namespace {
+bool h_less(double a, double b) { return a < b + 2.220446049250313e-16; }
+
+// AngleHistogram (src/core/features/angle_histogram.h:9-102, 20 bins): occupancy of the bin each
+// point's direction-to-previous-point falls into; the first point reports n
+void angle_histogram_values(int n, const double *range, const double *angle, std::vector<uint32_t> &values) {
+  const int NB = 20;
+  unsigned hist[NB] = {0};
+  const double step = (180 * M_PI / 180) / NB;
+  std::vector<int> bin(std::max(n, 1), 0);
+  for (int i = 1; i < n; ++i) {
+    const double bx = range[i - 1] * std::cos(angle[i - 1]), by = range[i - 1] * std::sin(angle[i - 1]);
+    const double x = range[i] * std::cos(angle[i]), y = range[i] * std::sin(angle[i]);
+    const double d_x = x - bx, d_y = y - by;
+    double a = 0;
+    if (d_y != 0) {
+      const double d_d = std::sqrt(d_x * d_x + d_y * d_y);
+      a = std::acos(d_x / d_d);
+      if (d_y < 0 && d_x != 0) a = M_PI - a;
+    }
+    bin[i] = (int)(size_t)std::floor(a / step);
+    hist[bin[i]]++;
+  }
+  values.resize(n);
+  for (int i = 0; i < n; ++i) values[i] = i == 0 ? (uint32_t)n : hist[bin[i]];
+}
+}  // namespace
+
+extern "C" int slamgpu_scan_filter(const slamgpu_map *m, int32_t n, const double *range, const double *angle, const uint8_t *occ,
+                                   const double pose[3], uint32_t skip_rate, double max_range, int32_t *keep_idx) {
+  if (!m || n < 0 || (n > 0 && (!range || !angle || !keep_idx)) || !pose) return SLAMGPU_E_INVALID;
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    if (skip_rate && (unsigned)i % skip_rate) continue;
+    const double wx = pose[0] + range[i] * std::cos(pose[2] + angle[i]);
+    const double wy = pose[1] + range[i] * std::sin(pose[2] + angle[i]);
+    const int cx = (int)std::floor(wx / m->scale), cy = (int)std::floor(wy / m->scale);
+    bool has_cell = true;  // unbounded maps own every cell (plain_grid_map.h:77)
+    if (m->grow == SLAMGPU_GROW_NONE) {
+      const int ix = cx + m->ox, iy = cy + m->oy;
+      has_cell = ix >= 0 && ix < m->w && iy >= 0 && iy < m->h;
+    }
+    const bool skip = (occ && !occ[i]) || !has_cell || (h_less(0.0, max_range) && h_less(max_range, range[i]));
+    if (!skip) keep_idx[k++] = i;
+  }
+  return k;
+}
+
+extern "C" int slamgpu_point_weights(int32_t kind, int32_t n, const double *range, const double *angle, double *out_w) {
+  if (n < 0 || (n > 0 && (!range || !angle || !out_w))) return SLAMGPU_E_INVALID;
+  if (kind == SLAMGPU_SPW_EVEN) {
+    const double c = 1.0 / n;
+    for (int i = 0; i < n; ++i) out_w[i] = c;
+  } else if (kind == SLAMGPU_SPW_VINY) {
+    for (int i = 0; i < n; ++i) {
+      const double a = angle[i];
+      double w = std::fabs(std::sin(a)) + std::fabs(std::cos(a));
+      if (0.9 < std::fabs(std::cos(a))) w = 3;
+      else if (0.8 < std::fabs(std::cos(a))) w = 2;
+      out_w[i] = w * std::sqrt(range[i]);
+    }
+  } else if (kind == SLAMGPU_SPW_AHR) {
+    std::vector<uint32_t> v;
+    angle_histogram_values(n, range, angle, v);
+    for (int i = 0; i < n; ++i) out_w[i] = 1.0 / v[i];
+  } else {
+    return SLAMGPU_E_INVALID;
+  }
+  return SLAMGPU_OK;
+}
+
+extern "C" int slamgpu_mapping_quality(int32_t kind, int32_t n, const double *range, const double *angle, double *out_q) {
+  if (n < 0 || (n > 0 && (!range || !angle || !out_q))) return SLAMGPU_E_INVALID;
+  if (kind == SLAMGPU_OMQE_IDLE) {
+    for (int i = 0; i < n; ++i) out_q[i] = 1.0;
+  } else if (kind == SLAMGPU_OMQE_AHR) {
+    std::vector<uint32_t> v;
+    angle_histogram_values(n, range, angle, v);
+    for (int i = 0; i < n; ++i) out_q[i] = 1.0 / v[i];
+  } else {
+    return SLAMGPU_E_INVALID;
+  }
+  return SLAMGPU_OK;
+}

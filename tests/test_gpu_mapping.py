@@ -195,3 +195,18 @@ def test_viny_shape_full_size_update(sg, gpu):
     assert gm.info() == om.info()
     assert np.array_equal(gm.download(), om.cells(), equal_nan=True)
     gm.close()
+
+
+def test_filter_scan_matches_oracle(sg, gpu):
+    rng = np.random.default_rng(2500)
+    for grow in (ob.GROW_NONE, ob.GROW_PLAIN):
+        om = ob.OracleMap(60, 60, 0.1, ob.CELL_LWW, grow)
+        gm = sg.GridMap(gpu, 60, 60, 0.1, sg.CELL_LWW, grow)
+        r = rng.uniform(0.2, 6, 200); a = np.linspace(-2, 2, 200)
+        occ = (rng.random(200) < 0.8).astype(np.uint8)
+        for skip, mr in ((0, -1.0), (3, -1.0), (0, 3.0), (2, 2.5)):
+            k1 = np.zeros(200, np.int32)
+            n1 = ob.orc.orc_filter_scan(om.h_, 200, ob.dptr(r), ob.dptr(a), ob.u8ptr(occ), 0.3, 0.2, 0.5, skip, mr, ob.iptr(k1))
+            got = gm.filter_scan(r, a, (0.3, 0.2, 0.5), occ=occ, skip_rate=skip, max_range=mr)
+            assert np.array_equal(got, k1[:n1])
+        gm.close()
