@@ -104,51 +104,75 @@ def make_workload(seed=42, theta_blocks=1):
 
 # ---------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+    """polls SM clock and throttle reasons of one GPU through NVML from a thread (about 1 kHz), so even a
+    timed region of a few tens of milliseconds gets samples; falls back to `nvidia-smi -lms` if NVML is missing"""
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, gpu_index):
-        self.rows, self.p = [], None
+        self.rows, self.stop_flag, self.nv, self.p = [], False, None, None
+        self.max_mhz = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                      stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except OSError:
-            self.p = None
+        except Exception:
+            self.nv = None
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.t = threading.Thread(target=self._read_smi, daemon=True)
+                self.t.start()
+            except OSError:
+                self.p = None
 
-    def _read(self):
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), float(clk), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def _read_smi(self):
         for line in self.p.stdout:
-            self.rows.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.max_mhz = float(f[1])
+                self.rows.append((time.time(), float(f[0]), int(f[2], 16) if f[2].startswith("0x") else 0))
+            except (ValueError, IndexError):
+                pass
 
     def stop(self, t0, t1):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        mhz, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                clk = float(f[0]); mx = float(f[1])
-            except ValueError:
-                continue
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                mhz.append(clk)
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        if not mhz:  # the timed region was shorter than one sample: use every sample
-            for ts, line in self.rows:
-                try:
-                    mhz.append(float(line.split(",")[0]))
-                except ValueError:
-                    pass
-        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz)}
+        self.stop_flag = True
+        if self.p is not None:
+            time.sleep(0.05)
+            self.p.terminate()
+        if self.nv is None and self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        where = "timed region"
+        if not inside:
+            inside, where = self.rows, "whole run (timed region shorter than the sampling period)"
+        mask = 0
+        for r in inside:
+            mask |= r[2]
+        reasons = [n for n, bit in self.REASONS if mask & bit]
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside), "window": where}
 
 
 # ---------------------------------------------------------------- reference (CPU) arm
@@ -228,10 +252,11 @@ def run_reference_arm(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 100 more theta values (1 020 100 more candidates) per extra GPU; strong = the fixed "
                          "1 020 100 candidates split N ways")
@@ -377,6 +402,14 @@ def main():
                                     "sample": "%d consecutive candidates x %d beams of the same workload, best of 3; GPU "
                                               "scores on the sample bit-equal to the reference: %s"
                                               % (len(ref_poses), N_BEAMS, bool(np.array_equal(got, ref_scores)))}
+        if args.gpus == 1 and not args.no_secondary:
+            # the other rows of the path at the shapes of configs[0], [1] and [4] (per-call latency, scan
+            # insertion, pyramid build); a second or two in total
+            try:
+                from tools import latency_bench
+                line["secondary"] = latency_bench.measure(ctx)
+            except Exception as e:  # the headline line must survive a secondary failure
+                line["secondary"] = {"error": repr(e)}
         print(json.dumps(line))
     gmap.close(); scan.close(); ctx.close()
     if dist is not None:

@@ -23,8 +23,26 @@ def timeit(fn, n=200, warm=20):
     return (time.perf_counter() - t0) / n * 1e6
 
 
-def main():
-    ctx = sg.Context(0)
+def pyramid_numbers(ctx, size=4096, scale=0.025):
+    """BASELINE configs[4] shape: from-scratch max-pyramid over a size x size map (MeanProbabilityCell)"""
+    rng = np.random.default_rng(3)
+    cells = np.zeros((size, size, 2))
+    cells[..., 0] = rng.random((size, size)); cells[..., 1] = 1
+    gm = sg.GridMap(ctx, size, size, scale, sg.CELL_MEAN, sg.GROW_PLAIN)
+    gm.upload(cells)
+    pyr = sg.Pyramid(ctx, gm, sg.OIE_DISCREPANCY)
+    pyr.build()
+    ts = []
+    for _ in range(5):
+        ctx.sync(); ctx.timer_begin(); pyr.build(); ts.append(ctx.timer_end())
+    ms = float(np.median(ts))
+    levels = pyr.levels()
+    by = 4.0 / 3.0 * size * size * 2 * 8 * 2  # read + write of every level's records
+    pyr.close(); gm.close()
+    return {"grid": [size, size], "levels": levels, "build_ms": round(ms, 3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
+
+
+def measure(ctx):
     rng = np.random.default_rng(1)
     out = {}
     for name, size, scale, beams, fov, P, model, est_kind in (
@@ -50,10 +68,19 @@ def main():
             dev()
         dev_us = float(np.median([dev() for _ in range(200)])) * 1e3
         upd = timeit(lambda: ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3), n=50, warm=5)
+        rec_bytes = {sg.CELL_MEAN: 2 * 16 + 8, sg.CELL_TBM_CONSISTENT: 2 * 48 + 8}[model]  # 2 x record + LUT entry
         out[name] = {"poses": P, "beams": beams, "score_call_e2e_us": round(e2e, 1), "score_device_us": round(dev_us, 1),
                      "evals_per_s_e2e": P * beams / (e2e * 1e-6), "append_scan_e2e_us": round(upd, 1), "cells_per_scan": int(cells),
-                     "cell_updates_per_s": cells / (upd * 1e-6)}
+                     "cell_updates_per_s": cells / (upd * 1e-6),
+                     "update_algorithmic_GBps": cells * rec_bytes / (upd * 1e-6) / 1e9}
         gm.close(); scan.close()
+    out["pyramid_build"] = pyramid_numbers(ctx)
+    return out
+
+
+def main():
+    ctx = sg.Context(0)
+    out = measure(ctx)
     ctx.close()
     print(json.dumps(out))
 
