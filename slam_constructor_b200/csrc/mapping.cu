@@ -237,12 +237,37 @@ __global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigne
 }
 
 // ---------------------------------------------------------------- K3b
-struct ApplyArgs {
+// per sorted position: everything one cell update needs, gathered so that the (sequential) apply walk
+// streams through contiguous memory instead of chasing slot -> beam -> AOO pointers
+struct SortedAoo {
+  double p, q, quality, wx, wy;
+  unsigned slot, pad;
+};
+
+struct GatherArgs {
   const unsigned *keys, *vals;  // sorted
   long long M;
   const double *aoo_p, *aoo_q;
   const int *slot_beam;
   const BeamRec *beams;
+  SortedAoo *out;
+};
+
+__global__ void k_gather_sorted(GatherArgs a) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= a.M) return;
+  if (a.keys[t] == SG_INVALID_KEY) return;
+  const unsigned s = a.vals[t];
+  const BeamRec &b = a.beams[a.slot_beam[s]];
+  SortedAoo o;
+  o.p = a.aoo_p[s]; o.q = a.aoo_q[s]; o.quality = b.quality; o.wx = b.wx; o.wy = b.wy; o.slot = s; o.pad = 0;
+  a.out[t] = o;
+}
+
+struct ApplyArgs {
+  const unsigned *keys;  // sorted
+  const SortedAoo *aoo;  // sorted
+  long long M;
   double *cells;
   int stride, model;
   // optional trace for the pyramid: post-update impact of every applied slot (indexed by slot)
@@ -260,15 +285,20 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   double r[SLAMGPU_MAX_STRIDE];
   double *cell = a.cells + (size_t)key * a.stride;
   for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
-  for (long long t = j; t < a.M && a.keys[t] == key; ++t) {
-    const unsigned s = a.vals[t];
-    const BeamRec &b = a.beams[a.slot_beam[s]];
-    sg::cell_update(a.model, r, a.aoo_p[s], a.aoo_q[s], b.wx, b.wy, b.quality);
+  SortedAoo cur = a.aoo[j];
+  for (long long t = j;;) {
+    const bool more = t + 1 < a.M && a.keys[t + 1] == key;
+    SortedAoo nxt = cur;
+    if (more) nxt = a.aoo[t + 1];  // next update's operands are in flight while this one is computed
+    sg::cell_update(a.model, r, cur.p, cur.q, cur.wx, cur.wy, cur.quality);
     if (a.trace_impact) {
-      a.trace_impact[s] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
-      double *tr = a.trace_rec + (size_t)s * a.stride;
+      a.trace_impact[cur.slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+      double *tr = a.trace_rec + (size_t)cur.slot * a.stride;
       for (int k = 0; k < a.stride; ++k) tr[k] = r[k];
     }
+    if (!more) break;
+    cur = nxt;
+    ++t;
   }
   for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
 }
@@ -579,13 +609,14 @@ int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, con
   const long long M = plan.M;
   DevBuf &slotbuf = ctx->scratch[4];
   // layout: aoo_p[M] aoo_q[M] (double) | keys[M] vals[M] keys_tmp[M] vals_tmp[M] (u32) | slot_beam[M] (i32) | counters[2] (u64)
-  size_t bytes = (size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 64;
+  size_t bytes = (size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 64 + (size_t)M * sizeof(SortedAoo) + 64;
   if (slotbuf.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "slot buffers (%lld slots)", M);
   double *aoo_p = slotbuf.as<double>(), *aoo_q = aoo_p + M;
   unsigned *keys = (unsigned *)(aoo_q + M), *vals = keys + M, *keys_tmp = vals + M, *vals_tmp = keys_tmp + M;
   int *slot_beam = (int *)(vals_tmp + M);
   size_t coff = ((size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 15) & ~(size_t)15;
   unsigned long long *counters = (unsigned long long *)((char *)slotbuf.p + coff);
+  SortedAoo *sorted_aoo = (SortedAoo *)((char *)slotbuf.p + coff + 64);
   SG_CUDA(ctx, cudaMemsetAsync(counters, 0, 16, ctx->stream));
   EstimateArgs ea;
   ea.beams = ctx->scratch[0].as<BeamRec>(); ea.bout = ctx->scratch[3].as<BeamOut>(); ea.offsets = ctx->scratch[1].as<long long>();
@@ -600,9 +631,13 @@ int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, con
   // ---- sort by cell (stable), then apply each cell's run in order
   unsigned *ks, *vs;
   SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)map->w * map->h), &ks, &vs));
+  GatherArgs ga;
+  ga.keys = ks; ga.vals = vs; ga.M = M; ga.aoo_p = aoo_p; ga.aoo_q = aoo_q; ga.slot_beam = slot_beam;
+  ga.beams = ctx->scratch[0].as<BeamRec>(); ga.out = sorted_aoo;
+  k_gather_sorted<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ga);
+  SG_LAUNCHED(ctx);
   ApplyArgs aa;
-  aa.keys = ks; aa.vals = vs; aa.M = M; aa.aoo_p = aoo_p; aa.aoo_q = aoo_q; aa.slot_beam = slot_beam;
-  aa.beams = ctx->scratch[0].as<BeamRec>(); aa.cells = map->d_cells; aa.stride = map->stride; aa.model = map->model;
+  aa.keys = ks; aa.aoo = sorted_aoo; aa.M = M; aa.cells = map->d_cells; aa.stride = map->stride; aa.model = map->model;
   aa.trace_impact = nullptr; aa.trace_rec = nullptr; aa.trace_oie = 0;
   if (trace) {
     if (ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + map->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");

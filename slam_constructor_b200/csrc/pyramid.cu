@@ -161,12 +161,33 @@ __global__ void k_level_keys(KeyArgs a) {
   a.alive_next[pos] = next;
 }
 
-struct FoldArgs {
+struct FoldGatherArgs {
   const unsigned *keys, *vals;  // sorted by level cell; vals = positions in update order
   long long M;
   const int *ent_slot;
   const double *impact;  // per slot: impact of the fine cell right after its update
   const double *rec;     // per slot: fine cell record right after its update
+  int stride;
+  double *g_impact;      // per sorted position
+  double *g_rec;         // per sorted position, stride doubles
+};
+
+// operands of the fold in sorted order, so the sequential walk streams through contiguous memory
+__global__ void k_level_gather(FoldGatherArgs a) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= a.M) return;
+  if (a.keys[t] == SG_INVALID_KEY) return;
+  const int slot = a.ent_slot[a.vals[t]];
+  a.g_impact[t] = a.impact[slot];
+  const double *r = a.rec + (size_t)slot * a.stride;
+  double *o = a.g_rec + (size_t)t * a.stride;
+  for (int k = 0; k < a.stride; ++k) o[k] = r[k];
+}
+
+struct FoldArgs {
+  const unsigned *keys, *vals;  // sorted by level cell; vals = positions in update order
+  long long M;
+  const double *g_impact, *g_rec;  // sorted
   double *cells;         // this level
   int stride, model, oie;
   unsigned char *alive_next;
@@ -186,16 +207,14 @@ __global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
   double cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
   bool changed = false;
   for (long long t = j; t < a.M && a.keys[t] == key; ++t) {
-    const unsigned pos = a.vals[t];
-    const int slot = a.ent_slot[pos];
-    const double x = a.impact[slot];
-    if (!cur_unknown && sg::less_or_equal(x, cur_impact)) { a.alive_next[pos] = 0; continue; }
-    const double *r = a.rec + (size_t)slot * a.stride;
+    const double x = a.g_impact[t];
+    if (!cur_unknown && sg::less_or_equal(x, cur_impact)) { a.alive_next[a.vals[t]] = 0; continue; }
+    const double *r = a.g_rec + (size_t)t * a.stride;
     for (int k = 0; k < a.stride; ++k) cur[k] = r[k];
     cur_unknown = sg::rec_is_unknown(a.model, cur);
     cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
     changed = true;
-    a.alive_next[pos] = 1;
+    a.alive_next[a.vals[t]] = 1;
   }
   if (changed)
     for (int k = 0; k < a.stride; ++k) cell[k] = cur[k];
@@ -402,13 +421,14 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
   const long long M = tr.M;
   if (M == 0) return SLAMGPU_OK;
   // per-position arrays: ent_slot (i32) coords (int2) keys vals keys_tmp vals_tmp (u32) alive alive_next (u8) counters
-  const size_t bytes = (size_t)M * (4 + 8 + 16 + 2) + 256;
+  const size_t bytes = (size_t)M * (4 + 8 + 16 + 2) + 256 + (size_t)M * sizeof(double) * (1 + fine->stride) + 64;
   if (p->ent.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "pyramid update buffers (%lld updates)", M);
   int2 *coords = p->ent.as<int2>();
   int *ent_slot = (int *)(coords + M);
   unsigned *keys = (unsigned *)(ent_slot + M), *vals = keys + M, *keys_tmp = vals + M, *vals_tmp = keys_tmp + M;
   unsigned char *alive = (unsigned char *)(vals_tmp + M), *alive_next = alive + M;
   unsigned long long *counters = (unsigned long long *)(((uintptr_t)(alive_next + M) + 63) & ~(uintptr_t)63);
+  double *g_impact = (double *)(counters + 8), *g_rec = g_impact + M;
   const unsigned nblk = (unsigned)((M + 127) / 128);
   OrderArgs oa;
   oa.offsets = tr.d_offsets; oa.bout = tr.d_bout; oa.cells = tr.cells; oa.N = tr.N; oa.M = M;
@@ -448,8 +468,13 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
     SG_LAUNCHED(ctx);
     unsigned *ks, *vs;
     SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)lvl->w * lvl->h), &ks, &vs));
+    FoldGatherArgs fg;
+    fg.keys = ks; fg.vals = vs; fg.M = M; fg.ent_slot = ent_slot; fg.impact = tr.impact; fg.rec = tr.rec; fg.stride = lvl->stride;
+    fg.g_impact = g_impact; fg.g_rec = g_rec;
+    k_level_gather<<<nblk, 128, 0, ctx->stream>>>(fg);
+    SG_LAUNCHED(ctx);
     FoldArgs fa;
-    fa.keys = ks; fa.vals = vs; fa.M = M; fa.ent_slot = ent_slot; fa.impact = tr.impact; fa.rec = tr.rec;
+    fa.keys = ks; fa.vals = vs; fa.M = M; fa.g_impact = g_impact; fa.g_rec = g_rec;
     fa.cells = lvl->d_cells; fa.stride = lvl->stride; fa.model = lvl->model; fa.oie = p->oie; fa.alive_next = alive_next;
     k_level_fold<<<nblk, 128, 0, ctx->stream>>>(fa);
     SG_LAUNCHED(ctx);
