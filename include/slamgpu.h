@@ -136,6 +136,11 @@ int slamgpu_ctx_create_dist(int device, int rank, int nranks, const void *nccl_i
 void slamgpu_ctx_destroy(slamgpu_ctx *ctx);
 const char *slamgpu_last_error(const slamgpu_ctx *ctx); /* ctx may be NULL: last create error */
 int slamgpu_sync(slamgpu_ctx *ctx);
+/* tuning knobs (defaults are right for production):
+ *   "grid_variant"  highest brute-force grid kernel allowed: 2 = packed row words + L1-resident gathers
+ *                   (default, fastest measured), 3 = map patches staged in shared memory by TMA bulk
+ *                   copies (kept for comparison: 2.3x slower at configs[2]), 1 = explicit row table */
+int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_t value);
 /* device-side stop watch on the ctx stream (CUDA events) for bench.py */
 int slamgpu_timer_begin(slamgpu_ctx *ctx);
 int slamgpu_timer_end(slamgpu_ctx *ctx, float *ms);

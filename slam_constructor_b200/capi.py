@@ -82,7 +82,7 @@ _lib = None
 # every symbol include/slamgpu.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "slamgpu_abi_version", "slamgpu_device_count", "slamgpu_ctx_create", "slamgpu_nccl_unique_id", "slamgpu_ctx_create_dist",
-    "slamgpu_ctx_destroy", "slamgpu_last_error", "slamgpu_sync", "slamgpu_timer_begin", "slamgpu_timer_end",
+    "slamgpu_ctx_destroy", "slamgpu_last_error", "slamgpu_sync", "slamgpu_ctx_set_option", "slamgpu_timer_begin", "slamgpu_timer_end",
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
@@ -116,6 +116,7 @@ def lib():
     L.slamgpu_ctx_destroy.argtypes = [vp]
     L.slamgpu_ctx_destroy.restype = None
     L.slamgpu_sync.argtypes = [vp]
+    L.slamgpu_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
     L.slamgpu_timer_begin.argtypes = [vp]
     L.slamgpu_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
     L.slamgpu_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -226,6 +227,9 @@ class Context:
 
     def __del__(self):
         pass  # explicit close(); maps/scans hold the ctx alive by reference
+
+    def set_option(self, name, value):
+        self.check(self.L.slamgpu_ctx_set_option(self.h, name.encode(), int(value)))
 
     def sync(self):
         self.check(self.L.slamgpu_sync(self.h))

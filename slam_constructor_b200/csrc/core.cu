@@ -124,7 +124,7 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) sg_nccl_destroy(ctx->comm);
   Candidates &c = ctx->cand;
-  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.views, &c.view_id, &c.trc, &c.trs,
+  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,
                     &c.scores, &c.blk_best, &c.result, &ctx->flush, &ctx->gather};
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : ctx->scratch) b.release();
@@ -162,6 +162,15 @@ extern "C" int slamgpu_last_kernel_ms(slamgpu_ctx *ctx, float *ms) {
   SG_CUDA(ctx, cudaEventSynchronize(ctx->evk1));
   SG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->evk0, ctx->evk1));
   return SLAMGPU_OK;
+}
+extern "C" int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return SLAMGPU_E_INVALID;
+  if (strcmp(name, "grid_variant") == 0) {
+    if (value < 1 || value > 3) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_variant must be 1, 2 or 3");
+    ctx->cand.user_variant = (int)value;
+    return SLAMGPU_OK;
+  }
+  return sg_fail(ctx, SLAMGPU_E_INVALID, "unknown option '%s'", name);
 }
 extern "C" int64_t slamgpu_launch_count(const slamgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -341,7 +350,8 @@ int sg_map_ensure_lut(slamgpu_map *m, int oie) {
   if (need > m->lut_cap[oie]) {
     if (m->d_lut[oie]) cudaFree(m->d_lut[oie]);
     m->d_lut[oie] = nullptr; m->lut_cap[oie] = 0;
-    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], need * sizeof(double)));
+    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], (need + SG_LUT_SLACK) * sizeof(double)));
+    SG_CUDA(ctx, cudaMemsetAsync(m->d_lut[oie] + need, 0, SG_LUT_SLACK * sizeof(double), ctx->stream));
     m->lut_cap[oie] = need;
   }
   // the unknown cell's impact, computed by the same device code as every other cell
@@ -472,7 +482,8 @@ extern "C" int slamgpu_map_upload_lut(slamgpu_map *m, int32_t oie, const double 
   if (need > m->lut_cap[oie]) {
     if (m->d_lut[oie]) cudaFree(m->d_lut[oie]);
     m->d_lut[oie] = nullptr; m->lut_cap[oie] = 0;
-    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], need * sizeof(double)));
+    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], (need + SG_LUT_SLACK) * sizeof(double)));
+    SG_CUDA(ctx, cudaMemsetAsync(m->d_lut[oie] + need, 0, SG_LUT_SLACK * sizeof(double), ctx->stream));
     m->lut_cap[oie] = need;
   }
   size_t bytes = std::max<size_t>((size_t)w * h, 1) * sizeof(double);

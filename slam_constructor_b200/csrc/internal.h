@@ -8,6 +8,7 @@
 #include "../../include/slamgpu.h"
 
 #define SG_LUT_PAD 1  // ring of "unknown" cells around the padded score LUT
+#define SG_LUT_SLACK 512  // doubles allocated past the LUT: a staged patch row may run past the last row
 
 struct DevBuf {  // grow-only device scratch buffer
   void *p = nullptr;
@@ -42,6 +43,13 @@ struct Candidates {  // a staged candidate set (device resident)
   DevBuf cyw;        // v2: packed row words, one per (theta, beam, y-group)
   int32_t grid_R = 8, ngy = 0;  // rows per thread of the grid kernel, y-groups per (theta, beam)
   bool grid_v2 = true, force_v1 = false;
+  // 3: TMA-staged patches (experimental, slower: see DESIGN.md), 2: packed rows + L1 gathers (default), 1: explicit row table
+  int grid_variant = 2;   // variant of the staged set
+  int user_variant = 0;   // requested through slamgpu_ctx_set_option / SLAMGPU_GRID_VARIANT (0: default = 2)
+  int max_variant = 3;    // temporary cap while a launch falls back to a simpler variant
+  DevBuf blocks, blk_rows, porg;          // v3: block table, per (theta, block) y range, patch origins
+  int32_t nbt = 0, box_w = 0, box_h = 0, n_blocks3 = 0;
+  double h_extent_x = 0, h_extent_y = 0;  // metres spanned by the x sweep / by the y rows of one block
   bool uniform_w = false;
   // K6: every pose scored against its own particle's map
   bool multi = false;

@@ -329,10 +329,14 @@ struct GridIdxArgs {
   int *cyp;  // [(tl*N + i)*nyp + k]  padded LUT row * pitch            (v1 kernel)
   unsigned long long *cyw;  // [(tl*N + i)*ngy + gy] packed rows of one y-group (v2 kernel)
   int v2, R, ngy;
+  // v3 (TMA-staged patches): per (theta, beam, block-of-theta) patch origin {first padded column, first padded row}
+  int v3, nbt, box_w, box_h;
+  const int2 *blk_rows;  // [nbt] y range {k_lo, k_hi} (inclusive) each block of a theta touches
+  int2 *porg;            // [(tl*N + i)*nbt + b]
   Result *result;
 };
 
-// v2 row word: low 32 bits = padded LUT row offset of the group's first y, then one signed nibble per
+// v2/v3 row word: low 32 bits = padded LUT row of the group's first y, then one signed nibble per
 // further y = (cell row of y_m) - (cell row of y_{m-1}); 0 means "same cell row: reuse the gathered value"
 SG_DEV int nib_sext(unsigned long long w, int m) {  // m in 1..7
   int v = (int)((w >> (32 + 4 * (m - 1))) & 15ull);
@@ -371,6 +375,8 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
   // owns one axis value (an x or a y) and walks the beams, so the axis value is loaded once
   extern __shared__ int sh_rows[];  // [SG_IDX_PAIRS][ny] padded LUT rows (v2 packing)
   __shared__ double sh_rc[SG_IDX_PAIRS], sh_rs[SG_IDX_PAIRS];
+  __shared__ int sh_xmin[SG_IDX_PAIRS], sh_xmax[SG_IDX_PAIRS];
+  if (threadIdx.x < SG_IDX_PAIRS) { sh_xmin[threadIdx.x] = INT_MAX; sh_xmax[threadIdx.x] = INT_MIN; }
   const int tl = blockIdx.y;
   const int i0 = blockIdx.x * SG_IDX_PAIRS;
   const int np = min(SG_IDX_PAIRS, a.N - i0);
@@ -391,7 +397,9 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
       for (int pr = 0; pr < np; ++pr) {
         const double rc = sh_rc[pr];
         const int cx = grid_axis_cell(sg::add(x, rc), rc, a.scale, inv_scale, a.guard, &unsafe_any);
-        dst[(size_t)pr * a.nx] = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
+        const int col = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
+        dst[(size_t)pr * a.nx] = col;
+        if (a.v3) { atomicMin(&sh_xmin[pr], col); atomicMax(&sh_xmax[pr], col); }
       }
     } else {
       const int k = c - a.nx;
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
       const int pr = e / a.ngy, gy = e - pr * a.ngy;
       const int *rows = sh_rows + pr * a.ny;
       const int k0 = gy * a.R;
-      unsigned long long word = (unsigned)(rows[k0] * a.pitch);
+      unsigned long long word = (unsigned)rows[k0];
       int prev = rows[k0];
       for (int m = 1; m < a.R; ++m) {
         const int k = k0 + m;
@@ -425,6 +433,19 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
         prev = prow;
       }
       a.cyw[(ti0 + pr) * a.ngy + gy] = word;
+    }
+    if (a.v3) {
+      for (int e = threadIdx.x; e < np * a.nbt; e += blockDim.x) {
+        const int pr = e / a.nbt, b = e - pr * a.nbt;
+        const int *rows = sh_rows + pr * a.ny;
+        const int2 kr = a.blk_rows[(size_t)tl * a.nbt + b];
+        int ymin = INT_MAX, ymax = INT_MIN;
+        for (int k = kr.x; k <= kr.y && k < a.ny; ++k) { ymin = min(ymin, rows[k]); ymax = max(ymax, rows[k]); }
+        // the box must hold every cell this block can touch, else the call is redone with the v2 kernel
+        const int x0 = sh_xmin[pr] & ~1;  // 16-byte aligned source rows for the bulk copies
+        if (ymax - ymin + 1 > a.box_h || sh_xmax[pr] - x0 + 1 > a.box_w) atomicAdd((unsigned long long *)&a.result->pad, 1ull);
+        a.porg[(ti0 + pr) * a.nbt + b] = make_int2(x0, ymin);
+      }
     }
   }
   if (unsafe_any) atomicAdd((unsigned long long *)&a.result->guard, 1ull);
@@ -535,7 +556,7 @@ __global__ void __launch_bounds__(128) k_score_grid2(GridArgs2 a) {
       unsigned long long cw0 = a.N > 0 ? __ldg(pcw) : 0ull;
       if (a.N > 1) { cx1 = __ldg(pcx + a.nx); cw1 = __ldg(pcw + a.ngy); }
       if (a.N > 2) { cx2 = __ldg(pcx + 2 * (size_t)a.nx); cw2 = __ldg(pcw + 2 * (size_t)a.ngy); }
-      int off = (int)(unsigned)(cw0 & 0xffffffffull) + cx0;
+      int off = (int)(unsigned)(cw0 & 0xffffffffull) * a.pitch + cx0;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         if (m > 0) off += nib_sext(cw0, m) * a.pitch;
@@ -546,7 +567,7 @@ __global__ void __launch_bounds__(128) k_score_grid2(GridArgs2 a) {
       // gathers of beam i+1 (indices already in registers)
       double vn[R];
       {
-        int off = (int)(unsigned)(cw1 & 0xffffffffull) + cx1;
+        int off = (int)(unsigned)(cw1 & 0xffffffffull) * a.pitch + cx1;
 #pragma unroll
         for (int m = 0; m < R; ++m) {
           if (m > 0) off += nib_sext(cw1, m) * a.pitch;
@@ -575,6 +596,167 @@ __global__ void __launch_bounds__(128) k_score_grid2(GridArgs2 a) {
     }
   }
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+// ---------------------------------------------------------------- v3: map patches staged in shared memory by TMA
+// For one beam, every candidate of a block reads cells from one small patch of the LUT (the block's y rows
+// x the whole x sweep: about 10 x 44 cells).  Warp 0 asks the TMA unit for that patch S beams ahead, one
+// bulk copy per patch row (cp.async.bulk global -> shared, SASS UBLKCP); completion is counted on an
+// mbarrier per stage; the gathers then hit shared memory (fixed ~30-cycle latency) instead of chasing L1
+// misses into L2.  (The 2-D tensor form, cp.async.bulk.tensor / UTMALDG, faults with "illegal
+// instruction" on this pool's driver even in a minimal probe -- tools/scratch/tma_probe.cu -- so rows
+// are copied individually; patch columns start at an even column to keep the 16-byte source alignment.)
+SG_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+SG_DEV void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+SG_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SG_DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok = 0;
+  const unsigned addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+// one patch row: TMA bulk copy global -> shared, completion counted on the stage's mbarrier
+SG_DEV void bulk_load_row(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct GridArgs3 {
+  const double *lut;
+  int pitch, lut_rows;
+  const int *cxp;
+  const unsigned long long *cyw;
+  const int2 *porg;
+  const int4 *groups;  // {t, k0, m_lo, m_hi}
+  const int4 *blocks;  // per block {t, first group, end group, block index within its theta}
+  int nx, ny, ngy, N, t_lo, nbt, box_w, box_h;
+  const double *w, *f;
+  double w0, wsum;
+  long long p0;
+  double *scores;
+  Best *blk;
+};
+
+#define SG_TMA_STAGES 4
+
+// warp 0 fills one stage: lane 0 arms the barrier with the byte count, lanes copy one row each
+SG_DEV void fill_stage(const GridArgs3 &a, unsigned char *dst, unsigned long long *bar, int2 org, unsigned box_bytes) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) mbar_expect_tx(bar, box_bytes);
+  __syncwarp();
+  const unsigned row_bytes = (unsigned)a.box_w * 8u;
+  for (int r = lane; r < a.box_h; r += 32) {
+    const int row = min(org.y + r, a.lut_rows - 1);  // rows past the padded LUT are never indexed: any valid row will do
+    bulk_load_row(dst + (size_t)r * row_bytes, a.lut + (size_t)row * a.pitch + org.x, row_bytes, bar);
+  }
+}
+
+template <int R, bool FACTOR, bool UNIW>
+__global__ void __launch_bounds__(128) k_score_grid3(GridArgs3 a) {
+  extern __shared__ __align__(128) unsigned char sm_patches[];  // SG_TMA_STAGES boxes, 128-byte aligned each
+  __shared__ __align__(8) unsigned long long full_bar[SG_TMA_STAGES];
+  const int4 blkrec = __ldg(a.blocks + blockIdx.x);
+  const int tl = blkrec.x - a.t_lo;
+  const int q = blkrec.w * 128 + threadIdx.x;
+  const int gq = q / a.nx;
+  const int g = blkrec.y + gq;
+  const int j = q - gq * a.nx;
+  const bool active = g < blkrec.z;
+  const unsigned box_bytes = (unsigned)(a.box_w * a.box_h * 8);
+  const unsigned stage_bytes = (box_bytes + 127u) & ~127u;
+  const int2 *porg = a.porg + (size_t)tl * a.N * a.nbt + blkrec.w;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SG_TMA_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    for (int s = 0; s < SG_TMA_STAGES && s < a.N; ++s)
+      fill_stage(a, sm_patches + s * stage_bytes, &full_bar[s], __ldg(porg + (size_t)s * a.nbt), box_bytes);
+  }
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  int4 grp = make_int4(0, 0, 0, 0);
+  const int *pcx = a.cxp;
+  const unsigned long long *pcw = a.cyw;
+  if (active) {
+    grp = __ldg(a.groups + g);
+    pcx = a.cxp + (size_t)tl * a.N * a.nx + j;
+    pcw = a.cyw + (size_t)tl * a.N * a.ngy + grp.y / R;
+  }
+  double acc[R];
+#pragma unroll
+  for (int m = 0; m < R; ++m) acc[m] = 0.0;
+  // operands of beam i+1 and i+2 in registers (index tables are L2 streams)
+  int cx0 = 0, cx1 = 0;
+  unsigned long long cw0 = 0, cw1 = 0;
+  int2 og0 = make_int2(0, 0), og1 = make_int2(0, 0), ogp = make_int2(0, 0);
+  if (a.N > 0) { og0 = __ldg(porg); if (active) { cx0 = __ldg(pcx); cw0 = __ldg(pcw); } }
+  if (a.N > 1) { og1 = __ldg(porg + a.nbt); if (active) { cx1 = __ldg(pcx + a.nx); cw1 = __ldg(pcw + a.ngy); } }
+  if (threadIdx.x < 32 && SG_TMA_STAGES < a.N) ogp = __ldg(porg + (size_t)SG_TMA_STAGES * a.nbt);
+  for (int i = 0; i < a.N; ++i) {
+    const int stage = i % SG_TMA_STAGES;
+    const int cx = cx0;
+    const unsigned long long cw = cw0;
+    const int2 og = og0;
+    cx0 = cx1; cw0 = cw1; og0 = og1;
+    if (i + 2 < a.N) {
+      og1 = __ldg(porg + (size_t)(i + 2) * a.nbt);
+      if (active) { cx1 = __ldg(pcx + (size_t)(i + 2) * a.nx); cw1 = __ldg(pcw + (size_t)(i + 2) * a.ngy); }
+    }
+    const double wi = UNIW ? a.w0 : __ldg(a.w + i);
+    const double fi = FACTOR ? __ldg(a.f + i) : 1.0;
+    mbar_wait(&full_bar[stage], (unsigned)((i / SG_TMA_STAGES) & 1));
+    if (active) {
+      const double *patch = reinterpret_cast<const double *>(sm_patches + stage * stage_bytes);
+      int off = ((int)(unsigned)(cw & 0xffffffffull) - og.y) * a.box_w + (cx - og.x);
+      double v[R];
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        if (m > 0) off += nib_sext(cw, m) * a.box_w;
+        v[m] = patch[off];
+      }
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        double term = sg::mul(v[m], wi);
+        if (FACTOR) term = sg::mul(term, fi);
+        acc[m] = sg::add(acc[m], term);
+      }
+    }
+    __syncthreads();  // every thread is done with this stage: it can be refilled
+    if (threadIdx.x < 32 && i + SG_TMA_STAGES < a.N) {
+      fill_stage(a, sm_patches + stage * stage_bytes, &full_bar[stage], ogp, box_bytes);
+      if (i + SG_TMA_STAGES + 1 < a.N) ogp = __ldg(porg + (size_t)(i + SG_TMA_STAGES + 1) * a.nbt);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      if (m < grp.z || m >= grp.w) continue;
+      double score = a.wsum == 0 ? NAN : sg::div(acc[m], a.wsum);
+      long long idx = ((long long)grp.x * a.ny + (grp.y + m)) * a.nx + j;
+      a.scores[idx - a.p0] = score;
+      if (score == score && beats(score, idx, best_s, best_i)) { best_s = score; best_i = idx; }
+    }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+template <int R>
+void launch_grid3(slamgpu_ctx *ctx, const GridArgs3 &a, int nblk, size_t shm, bool factor, bool uniw) {
+  if (factor) {
+    if (uniw) k_score_grid3<R, true, true><<<nblk, 128, shm, ctx->stream>>>(a);
+    else k_score_grid3<R, true, false><<<nblk, 128, shm, ctx->stream>>>(a);
+  } else {
+    if (uniw) k_score_grid3<R, false, true><<<nblk, 128, shm, ctx->stream>>>(a);
+    else k_score_grid3<R, false, false><<<nblk, 128, shm, ctx->stream>>>(a);
+  }
 }
 
 template <int R>
@@ -718,7 +900,15 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   c.spe = *p; c.scan = scan;
   c.nx = nx; c.ny = ny; c.nt = nt; c.nyp = (ny + SG_GRID_R - 1) / SG_GRID_R * SG_GRID_R;
   c.P = (int64_t)nt * ny * nx;
-  c.grid_v2 = !c.force_v1 && (size_t)ny * SG_IDX_PAIRS * sizeof(int) <= 40 * 1024;  // index kernel stages the rows in smem
+  {
+    static const int env_variant = [] { const char *e = getenv("SLAMGPU_GRID_VARIANT"); return e ? atoi(e) : 0; }();
+    int v = c.user_variant ? c.user_variant : (env_variant >= 1 && env_variant <= 3 ? env_variant : 2);
+    v = std::min(v, c.max_variant);
+    if (c.force_v1) v = 1;
+    if ((size_t)ny * SG_IDX_PAIRS * sizeof(int) > 40 * 1024) v = 1;  // the index kernel stages the rows in smem
+    c.grid_variant = v;
+    c.grid_v2 = v >= 2;
+  }
   {
     // rows per thread: as many as keep the device full (one resident thread per pose column and y-group)
     int64_t r0_, r1_;
@@ -750,9 +940,52 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   }
   c.n_groups = (int32_t)(groups.size() / 4);
   c.rows_per_group = GR;
+  // v3: blocks never straddle a theta (one patch per block and beam); per (theta, block) the y rows it touches
+  std::vector<int32_t> blocks3, blk_rows3;
+  c.nbt = 0; c.n_blocks3 = 0;
+  if (c.grid_variant == 3) {
+    const int nt_seg = c.t_hi - c.t_lo + 1;
+    std::vector<std::pair<int, int>> seg(nt_seg, std::make_pair(-1, -1));  // [first group, end group) per theta
+    for (int g = 0; g < c.n_groups; ++g) {
+      const int tl = groups[4 * g] - c.t_lo;
+      if (seg[tl].first < 0) seg[tl].first = g;
+      seg[tl].second = g + 1;
+    }
+    for (int tl = 0; tl < nt_seg; ++tl)
+      if (seg[tl].first >= 0) c.nbt = std::max<int>(c.nbt, ((seg[tl].second - seg[tl].first) * nx + 127) / 128);
+    blk_rows3.assign((size_t)nt_seg * std::max(c.nbt, 1) * 2, 0);
+    double max_dy = 0;
+    for (int tl = 0; tl < nt_seg; ++tl) {
+      for (int b = 0; b < c.nbt; ++b) { blk_rows3[((size_t)tl * c.nbt + b) * 2] = 0; blk_rows3[((size_t)tl * c.nbt + b) * 2 + 1] = -1; }
+      if (seg[tl].first < 0) continue;
+      const int nthreads = (seg[tl].second - seg[tl].first) * nx;
+      for (int b = 0; b * 128 < nthreads; ++b) {
+        const int g_first = seg[tl].first + (b * 128) / nx, g_last = seg[tl].first + std::min(b * 128 + 127, nthreads - 1) / nx;
+        const int k_lo = groups[4 * g_first + 1], k_hi = std::min(groups[4 * g_last + 1] + GR - 1, ny - 1);
+        blk_rows3[((size_t)tl * c.nbt + b) * 2] = k_lo; blk_rows3[((size_t)tl * c.nbt + b) * 2 + 1] = k_hi;
+        double lo = ys[k_lo], hi = ys[k_lo];
+        for (int k = k_lo; k <= k_hi; ++k) { lo = std::min(lo, ys[k]); hi = std::max(hi, ys[k]); }
+        max_dy = std::max(max_dy, hi - lo);
+        blocks3.push_back(c.t_lo + tl); blocks3.push_back(seg[tl].first); blocks3.push_back(seg[tl].second); blocks3.push_back(b);
+      }
+    }
+    c.n_blocks3 = (int32_t)(blocks3.size() / 4);
+    double xlo = xs[0], xhi = xs[0];
+    for (int j = 0; j < nx; ++j) { xlo = std::min(xlo, xs[j]); xhi = std::max(xhi, xs[j]); }
+    const double sc = ctx->cand.scan ? 0 : 0;  // (map scale is only known at launch: boxes are sized there)
+    (void)sc;
+    c.box_w = 0; c.box_h = 0;
+    c.stats[6] = 0;
+    // remember the extents; launch_staged turns them into cells with the map's scale
+    c.h_extent_x = xhi - xlo; c.h_extent_y = max_dy;
+  }
   const int N = scan->n;
   const int nt_loc = c.t_hi - c.t_lo + 1;
   SG_TRY(upload(ctx, c.groups, groups.data(), groups.size() * sizeof(int32_t)));
+  if (c.grid_variant == 3) {
+    SG_TRY(upload(ctx, c.blocks, blocks3.data(), blocks3.size() * sizeof(int32_t)));
+    SG_TRY(upload(ctx, c.blk_rows, blk_rows3.data(), blk_rows3.size() * sizeof(int32_t)));
+  }
   SG_TRY(upload(ctx, c.d_xs, c.h_xs.data(), nx * sizeof(double)));
   SG_TRY(upload(ctx, c.d_ys, c.h_ys.data(), ny * sizeof(double)));
   SG_TRY(upload(ctx, c.d_thetas, c.h_ts.data(), nt * sizeof(double)));
@@ -763,7 +996,9 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   if (p->trig_mode == SLAMGPU_TRIG_HOST) SG_TRY(upload_host_trig(ctx, c, c.h_ts, N, 1));
   const int64_t Ploc = c.p1 - c.p0;
   long long threads = (long long)c.n_groups * nx;
-  int nblk = (int)((threads + 127) / 128);
+  int nblk = std::max((int)((threads + 127) / 128), (int)c.n_blocks3);
+  if (c.grid_variant == 3 && c.porg.reserve(std::max<size_t>((size_t)nt_loc * N * std::max(c.nbt, 1), 1) * sizeof(int2)) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "patch origin table");
   if (c.cxp.reserve(std::max<size_t>((size_t)nt_loc * N * nx, 1) * sizeof(int)) != SLAMGPU_OK ||
       c.cyp.reserve(std::max<size_t>(c.grid_v2 ? 1 : (size_t)nt_loc * N * c.nyp, 1) * sizeof(int)) != SLAMGPU_OK ||
       c.cyw.reserve(std::max<size_t>(c.grid_v2 ? (size_t)nt_loc * N * c.ngy : 1, 1) * sizeof(unsigned long long)) != SLAMGPU_OK ||
@@ -820,7 +1055,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   const bool device_trig = !c.trig_is_host && !c.spe.prerotated;
   int nblk = 0;
   memset(c.stats, 0, sizeof c.stats);
-  c.stats[1] = c.kind == 1 ? (c.grid_v2 ? 2 : 1) : 0; c.stats[2] = Ploc * N; c.stats[5] = c.grid_R; c.stats[3] = c.p0; c.stats[4] = Ploc;
+  c.stats[1] = c.kind == 1 ? c.grid_variant : 0; c.stats[2] = Ploc * N; c.stats[5] = c.grid_R; c.stats[3] = c.p0; c.stats[4] = Ploc;
   if (c.kind == 0) {
     const bool small = Ploc > 0 && Ploc <= SG_SMALL_MAX_POSES && Ploc * (long long)N <= SG_SMALL_MAX_TERMS && N > 0;
     if (!small && device_trig && c.T > 0 && N > 0) {
@@ -884,6 +1119,23 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       }
     }
   } else {
+    if (c.grid_variant == 3) {
+      // size the TMA box from the candidate extents and this map's cell size; too large -> v2
+      c.box_w = ((int)std::ceil(c.h_extent_x / map->scale) + 4 + 1) & ~1;  // +1: the patch starts at an even column
+      c.box_h = (int)std::ceil(c.h_extent_y / map->scale) + 3;
+      const size_t stage_bytes = ((size_t)c.box_w * c.box_h * 8 + 127) & ~(size_t)127;
+      if (c.box_w > 256 || c.box_h > 256 || stage_bytes * SG_TMA_STAGES > 26 * 1024 || c.n_blocks3 == 0) {
+        const int saved_max = c.max_variant;
+        c.max_variant = 2;
+        slamgpu_spe_params spe = c.spe;
+        std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
+        int r = slamgpu_stage_grid(ctx, c.scan, &spe, xs.data(), (int32_t)xs.size(), ys.data(), (int32_t)ys.size(), ts.data(),
+                                   (int32_t)ts.size());
+        c.max_variant = saved_max;
+        SG_TRY(r);
+        return launch_staged(ctx, map, init_score);
+      }
+    }
     const int nt_loc = c.t_hi - c.t_lo + 1;
     if (device_trig && N > 0) {
       long long tot = (long long)c.nt * N;
@@ -901,6 +1153,8 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       ia.guard = device_trig ? 1 : 0;
       ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
       ia.cyw = c.cyw.as<unsigned long long>(); ia.v2 = c.grid_v2 ? 1 : 0; ia.R = c.grid_R; ia.ngy = c.ngy;
+      ia.v3 = c.grid_variant == 3 ? 1 : 0; ia.nbt = c.nbt; ia.box_w = c.box_w; ia.box_h = c.box_h;
+      ia.blk_rows = c.blk_rows.as<int2>(); ia.porg = c.porg.as<int2>();
       {
         const size_t shm = c.grid_v2 ? sizeof(int) * SG_IDX_PAIRS * (size_t)c.ny : 0;
         dim3 grd((unsigned)((N + SG_IDX_PAIRS - 1) / SG_IDX_PAIRS), (unsigned)nt_loc);
@@ -908,7 +1162,24 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       }
       SG_LAUNCHED(ctx);
     }
-    if (nblk > 0 && c.grid_v2) {
+    if (nblk > 0 && c.grid_variant == 3) {
+      GridArgs3 a;
+      a.lut = map->d_lut[oie]; a.pitch = map->pitch; a.lut_rows = map->h + 2 * SG_LUT_PAD;
+      a.cxp = c.cxp.as<int>(); a.cyw = c.cyw.as<unsigned long long>(); a.porg = c.porg.as<int2>();
+      a.groups = c.groups.as<int4>(); a.blocks = c.blocks.as<int4>();
+      a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.N = N; a.t_lo = c.t_lo; a.nbt = c.nbt; a.box_w = c.box_w; a.box_h = c.box_h;
+      a.w = s->d_w; a.f = s->d_f; a.w0 = N > 0 ? s->weight[0] : 0.0; a.wsum = s->wsum; a.p0 = c.p0;
+      a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>();
+      nblk = c.n_blocks3;
+      const size_t shm = (((size_t)c.box_w * c.box_h * 8 + 127) & ~(size_t)127) * SG_TMA_STAGES;
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      if (c.grid_R == 8) launch_grid3<8>(ctx, a, nblk, shm, s->has_factor, c.uniform_w);
+      else if (c.grid_R == 4) launch_grid3<4>(ctx, a, nblk, shm, s->has_factor, c.uniform_w);
+      else launch_grid3<2>(ctx, a, nblk, shm, s->has_factor, c.uniform_w);
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->evk_valid = true;
+      SG_LAUNCHED(ctx);
+    } else if (nblk > 0 && c.grid_v2) {
       GridArgs2 a;
       a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<int>(); a.cyw = c.cyw.as<unsigned long long>(); a.groups = c.groups.as<int4>();
       a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.N = N; a.t_lo = c.t_lo; a.pitch = map->pitch;
@@ -976,16 +1247,17 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
   Result *h = (Result *)hp;
   SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (h->pad > 0 && c.kind == 1 && c.grid_v2 && map) {
-    // some pair of neighbouring y values is more than 7 cell rows apart: the packed row word cannot
-    // hold it; redo with the explicit row table (v1 kernel)
-    c.force_v1 = true;
+  while (h->pad > 0 && c.kind == 1 && c.grid_variant > 1 && map) {
+    // v3: some block's cells did not fit its TMA box -> v2; v2: two neighbouring y values are more than
+    // 7 cell rows apart, the packed row word cannot hold it -> the explicit row table (v1 kernel)
+    const int saved_max = c.max_variant;
+    c.max_variant = c.grid_variant - 1;
     slamgpu_spe_params spe = c.spe;
     std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
     double init = c.init_score;
     int r = slamgpu_stage_grid(ctx, c.scan, &spe, xs.data(), (int32_t)xs.size(), ys.data(), (int32_t)ys.size(), ts.data(),
                                (int32_t)ts.size());
-    c.force_v1 = false;
+    c.max_variant = saved_max;
     SG_TRY(r);
     SG_TRY(launch_staged(ctx, map, init));
     SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));

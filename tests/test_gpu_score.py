@@ -225,25 +225,31 @@ def test_full_size_bruteforce_properties(sg, gpu):
     gm.close(); gsc.close()
 
 
-@pytest.mark.parametrize("nx,ny,nt,ystep,expect_variant,expect_R", [
-    (33, 19, 5, 0.02, 2, 2),        # few candidates: 2 rows per thread
-    (400, 160, 8, 0.02, 2, 4),      # medium: 4 rows per thread
-    (300, 400, 12, 0.013, 2, 8),    # many: 8 rows per thread
-    (21, 10, 3, 0.6, 1, 8),         # neighbouring y more than 7 cell rows apart: explicit row table (v1 kernel)
-    (40, 17, 4, -0.03, 2, 2),       # decreasing y: negative row deltas
+@pytest.mark.parametrize("max_variant", [3, 2])
+@pytest.mark.parametrize("nx,ny,nt,ystep,expect_R,fits_box,fits_nibbles", [
+    (33, 19, 5, 0.02, 2, True, True),         # few candidates: 2 rows per thread
+    (400, 160, 8, 0.02, 4, True, True),       # medium: 4 rows per thread
+    (300, 400, 12, 0.013, 8, True, True),     # many: 8 rows per thread
+    (21, 10, 3, 0.6, 8, False, False),        # y values far apart: no TMA box, no nibble deltas -> explicit row table (v1)
+    (40, 17, 4, -0.03, 2, True, True),        # decreasing y: negative row deltas
 ])
-def test_grid_kernel_variants(sg, gpu, nx, ny, nt, ystep, expect_variant, expect_R):
+def test_grid_kernel_variants(sg, gpu, max_variant, nx, ny, nt, ystep, expect_R, fits_box, fits_nibbles):
     rng = np.random.default_rng(1700 + nx)
     om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_MEAN, 73, spw=ob.SPW_AHR, factor=(nx == 33))
     xs = p0[0] + 0.011 * (np.arange(nx) - nx // 2)
     ys = p0[1] + ystep * (np.arange(ny) - ny // 2)
     ts = p0[2] + 0.017 * (np.arange(nt) - nt // 2)
     P = np.stack(np.meshgrid(ts, ys, xs, indexing="ij"), -1).reshape(-1, 3)[:, ::-1]
-    got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+    gpu.set_option("grid_variant", max_variant)
+    try:
+        got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+    finally:
+        gpu.set_option("grid_variant", 2)
     st = gpu.score_stats()
     pick = rng.choice(len(P), min(len(P), 4000), replace=False)
     want = om.score(osc, ob.spe_params(), P[pick])
     assert np.array_equal(got[pick], want)
     assert idx == int(np.argmax(got)) and best == got[idx]
+    expect_variant = 1 if not fits_nibbles else (3 if (max_variant == 3 and fits_box) else 2)
     assert st["variant"] == expect_variant and st["rows_per_thread"] == expect_R, st
     gm.close(); gsc.close()
