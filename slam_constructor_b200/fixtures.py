@@ -93,3 +93,15 @@ def write_map(path, cells, model, scale, ox, oy):
     with open(path, "wb") as f:
         f.write(_HEADER.pack(h, w, scale, ox, oy))
         f.write(raw.tobytes())
+
+
+def write_pgm(path, cells):
+    """GridMapToPgmDumber::dump_map (src/utils/map_dumpers.h:65-89): binary PGM of the occupancy, top row
+    first, intensity = uint8(255 * (1 - occupancy)), occupancy -1 (a never-observed GMapping cell) as 0.5"""
+    occ = np.asarray(cells, dtype=np.float64)[..., 0]
+    h, w = occ.shape
+    occ = np.where(occ == -1, 0.5, np.clip(occ, 0.0, 1.0))
+    img = (255 * (1.0 - occ)).astype(np.uint8)[::-1]
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d\n%d\n255\n" % (w, h))
+        f.write(img.tobytes())

@@ -17,6 +17,7 @@
 #include "src/core/scan_matchers/observation_impact_estimators.h"
 #include "src/core/scan_matchers/occupancy_observation_probability.h"
 #include "src/core/scan_matchers/weighted_mean_point_probability_spe.h"
+#include "src/utils/map_dumpers.h"
 
 static LaserScan2D room_scan(const RobotPose &pose, int n, double fov, double hw, double hh, std::mt19937 &rng) {
   LaserScan2D scan;
@@ -49,6 +50,7 @@ static void one(const std::string &dir, const std::string &name, std::ofstream &
   { std::ofstream f(dir + "/" + name + ".pose2D"); f.precision(17); f << init.x << " " << init.y << " " << init.theta << "\n"; }
   { std::ofstream f(dir + "/" + name + ".scan2D"); f.precision(17); f << scan; }
   { auto buf = map->save_state(); std::ofstream f(dir + "/" + name + ".map", std::ios::binary); f.write(buf.data(), buf.size()); }
+  { std::ofstream f(dir + "/" + name + ".pgm", std::ios::binary); GridMapToPgmDumber::dump_map(f, *map); }
   auto spw = std::make_shared<EvenSPW>();
   auto oope = std::make_shared<ObstacleBasedOccupancyObservationPE>(std::make_shared<DiscrepancyOIE>());
   auto spe = std::make_shared<WeightedMeanPointProbabilitySPE>(oope, spw);

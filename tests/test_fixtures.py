@@ -50,3 +50,12 @@ def test_replay_dumped_state_on_gpu(sg, gpu, name, model):
     assert probs[0] == exp["prob"]
     assert np.array_equal(poses[0] - pose, exp["delta"])
     scan.close(); parts.close()
+
+
+@pytest.mark.parametrize("name,model", CASES)
+def test_pgm_export_matches_reference_dumper(sg, name, model, tmp_path):
+    """row f4: the PGM the reference's GridMapToPgmDumber wrote for the same map, byte for byte"""
+    from slam_constructor_b200 import fixtures
+    m = fixtures.read_map(os.path.join(G, name + ".map"), model)
+    fixtures.write_pgm(tmp_path / "m.pgm", m["cells"])
+    assert filecmp.cmp(tmp_path / "m.pgm", os.path.join(G, name + ".pgm"), shallow=False)
