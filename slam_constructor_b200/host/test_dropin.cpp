@@ -5,7 +5,8 @@
 #include <cstdio>
 #include <random>
 
-#include "slamgpu_backend.h"
+#include "slamgpu_init.h"
+#include "src/utils/init_slam.h"
 #include "src/core/maps/plain_grid_map.h"
 #include "src/core/maps/rescalable_caching_grid_map.h"
 #include "src/core/scan_matchers/m3rsm_engine.h"
@@ -244,6 +245,66 @@ void run_m3rsm(std::shared_ptr<slamgpu::Context> ctx) {
               gpu_world.pose().y, gpu_world.pose().theta);
 }
 
+// the shipped presets (config/slams/tiny_slam_base.properties, viny_slam_base.properties with their includes),
+// keys spelled out here because the config files do not travel to the GPU box; both factories read them
+void run_presets(std::shared_ptr<slamgpu::Context> ctx) {
+  struct Preset { const char *name; std::vector<std::pair<const char *, const char *>> kv; int beams; double fov; };
+  std::vector<Preset> presets = {
+    {"tiny_slam_base.properties",
+     {{"slam/mapping/blur", "0.5"}, {"slam/occupancy_estimator/type", "const"}, {"slam/occupancy_estimator/base_occupied/prob", "0.95"},
+      {"slam/occupancy_estimator/base_empty/prob", "0.01"}, {"slam/mapping/grid/area/type", "mean_probability"},
+      {"slam/mapping/corrected_pose_quality", "0.9"}, {"slam/mapping/raw_pose_quality", "0.6"},
+      {"slam/mapping/grid/type", "unbounded_plain"}, {"slam/map/height_in_meters", "10"}, {"slam/map/width_in_meters", "10"},
+      {"slam/map/meters_per_cell", "0.1"}, {"slam/scmtch/type", "MC"}, {"slam/scmtch/MC/dispersion/translation", "0.2"},
+      {"slam/scmtch/MC/dispersion/rotation", "0.1"}, {"slam/scmtch/MC/dispersion/failed_attempts_limit", "20"},
+      {"slam/scmtch/MC/attempts_limit", "100"}, {"slam/scmtch/MC/seed", "42"}, {"slam/scmtch/spe/type", "wmpp"},
+      {"slam/scmtch/spe/wmpp/weighting/type", "even"}}, 360, 2 * M_PI},
+    {"viny_slam_base.properties",
+     {{"slam/mapping/blur", "0.3"}, {"slam/occupancy_estimator/type", "const"}, {"slam/occupancy_estimator/base_occupied/prob", "0.95"},
+      {"slam/occupancy_estimator/base_occupied/qual", "0.04"}, {"slam/occupancy_estimator/base_empty/prob", "0.01"},
+      {"slam/occupancy_estimator/base_empty/qual", "0.003"}, {"slam/mapping/grid/area/type", "tbm_consistent"},
+      {"slam/mapping/corrected_pose_quality", "0.9"}, {"slam/mapping/raw_pose_quality", "0.6"},
+      {"slam/mapping/grid/type", "unbounded_plain"}, {"slam/map/height_in_meters", "10"}, {"slam/map/width_in_meters", "10"},
+      {"slam/map/meters_per_cell", "0.1"}, {"slam/scmtch/type", "MC"}, {"slam/scmtch/MC/dispersion/translation", "0.2"},
+      {"slam/scmtch/MC/dispersion/rotation", "0.1"}, {"slam/scmtch/MC/dispersion/failed_attempts_limit", "20"},
+      {"slam/scmtch/MC/attempts_limit", "100"}, {"slam/scmtch/MC/seed", "7"}, {"slam/scmtch/spe/type", "wmpp"},
+      {"slam/scmtch/spe/wmpp/weighting/type", "viny"}}, 541, 1.5 * M_PI},
+    {"hill climbing + area estimator + AHR mapping quality (factory keys)",
+     {{"slam/mapping/blur", "0.2"}, {"slam/occupancy_estimator/type", "area"}, {"slam/mapping/grid/area/type", "tbm_unknown_even_occ"},
+      {"slam/occupancy_estimator/base_occupied/qual", "0.3"}, {"slam/occupancy_estimator/base_empty/qual", "0.1"},
+      {"slam/mapping/grid/type", "unbounded_plain"}, {"slam/map/height_in_meters", "8"}, {"slam/map/width_in_meters", "8"},
+      {"slam/map/meters_per_cell", "0.05"}, {"slam/scmtch/type", "HC"}, {"slam/scmtch/spe/type", "wmpp"},
+      {"slam/scmtch/spe/wmpp/weighting/type", "ahr"}, {"slam/mapping/observation_quality_estimator/typetype", "ahr"},
+      {"slam/mapping/max_range", "20"}}, 361, 1.5 * M_PI},
+  };
+  for (auto &ps : presets) {
+    std::printf("== factories on %s\n", ps.name);
+    MapPropertiesProvider props;
+    for (auto &kv : ps.kv) props.set_property(kv.first, kv.second);
+    auto ref_world = init_1h_slam(props);
+    auto gpu_world = slamgpu::init_cuda_1h_slam(props, ctx);
+    std::mt19937 rng(31);
+    std::normal_distribution<double> odo(0.0, 0.02), odo_t(0.0, 0.01);
+    RobotPose truth{0.2, -0.1, 0.15};
+    for (int step = 0; step < 12; ++step) {
+      RobotPoseDelta motion = step == 0 ? RobotPoseDelta{truth.x, truth.y, truth.theta} : RobotPoseDelta{0.06, 0.03 * std::cos(0.5 * step), 0.02};
+      if (step > 0) { truth += motion; }
+      RobotPoseDelta odom = step == 0 ? motion : RobotPoseDelta{motion.x + odo(rng), motion.y + odo(rng), motion.theta + odo_t(rng)};
+      auto scan = room_scan(truth, ps.beams, ps.fov, 3.5, 3.0, rng, 0.01);
+      TransformedLaserScan a{odom, scan, 1.0}, b{odom, scan, 1.0};
+      b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+      ref_world->handle_sensor_data(a);
+      gpu_world->handle_sensor_data(b);
+      const RobotPose &p1 = ref_world->pose(), &p2 = gpu_world->pose();
+      CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "%s step %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)", ps.name,
+            step, p1.x, p1.y, p1.theta, p2.x, p2.y, p2.theta);
+      if (g_failed > 5) return;
+    }
+    same_cells(ref_world->map(), gpu_world->map(), ps.name);
+    std::printf("   12 scans, final pose %.6f %.6f %.6f\n", gpu_world->pose().x, gpu_world->pose().y, gpu_world->pose().theta);
+  }
+}
+
 }  // namespace
 
 int main() {
@@ -269,6 +330,7 @@ int main() {
     run_world_pair(bf, ctx);
     run_host_map(ctx);
     run_m3rsm(ctx);
+    run_presets(ctx);
   } catch (const std::exception &e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 1;
