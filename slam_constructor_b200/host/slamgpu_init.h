@@ -9,6 +9,7 @@
 #include "src/core/states/single_state_hypothesis_laser_scan_grid_world.h"
 #include "src/utils/init_occupancy_mapping.h"
 #include "src/utils/init_scan_matching.h"
+#include "src/slams/gmapping/init_gmapping.h"
 #include "src/utils/properties_providers.h"
 
 namespace slamgpu {
@@ -121,6 +122,27 @@ inline std::shared_ptr<SingleStateHypothesisLaserScanGridWorld> init_cuda_1h_sla
   slam_props.gsm = init_cuda_scan_matcher(props, ctx);
   slam_props.gmsa = init_cuda_scan_adder(props);
   return std::make_shared<SingleStateHypothesisLaserScanGridWorld>(slam_props);
+}
+
+// init_gmapping (src/slams/gmapping/init_gmapping.h:49-65): GmappingParticleFilter on the CUDA back end.  As upstream,
+// every particle is built from the same properties (so they share one map object, quirk Q6); pose noise, weights and
+// resampling stay in the reference's own particle filter.
+inline std::shared_ptr<GmappingParticleFilter> init_cuda_gmapping(const PropertiesProvider &props, std::shared_ptr<Context> ctx) {
+  const std::string OOPE_Pfx = "slam/scmtch/oope/";
+  ScoreSetup setup;
+  setup.oope = SLAMGPU_OOPE_GMAPPING;
+  setup.gm_fullness_th = props.get_dbl(OOPE_Pfx + "custom/fullness_threshold", 0.1);
+  setup.gm_window = (int)props.get_uint(OOPE_Pfx + "cutrom/window_size", 1);  // key spelled as upstream
+  auto oope = std::make_shared<GmappingOccupancyObservationPE>(setup.gm_fullness_th, setup.gm_window);
+  const std::string WMPP_Prefix = Slam_SM_NS + "spe/wmpp";
+  auto spw = init_swp(props);
+  auto spe = std::make_shared<WeightedMeanPointProbabilitySPE>(oope, spw, props.get_uint(WMPP_Prefix + "/sp_skip_rate", 0),
+                                                                props.get_dbl(WMPP_Prefix + "/sp_max_usable_range", -1));
+  auto matcher = std::make_shared<CudaHillClimbingScanMatcher>(ctx, spe, spw, 6, 0.1, 0.1);
+  matcher->set_score_setup(setup);
+  auto map = std::make_shared<CudaGridMap>(ctx, std::make_shared<GmappingBaseCell>(), init_grid_map_params(props), SLAMGPU_GROW_TILED);
+  auto shw_params = SingleStateHypothesisLSGWProperties{1.0, 1.0, 0, map, matcher, init_cuda_scan_adder(props)};
+  return std::make_shared<GmappingParticleFilter>(shw_params, init_gmapping_params(props), init_particles_nm(props));
 }
 
 }  // namespace slamgpu

@@ -305,6 +305,45 @@ void run_presets(std::shared_ptr<slamgpu::Context> ctx) {
   }
 }
 
+// GmappingParticleFilter with the CUDA plug-ins.  Upstream seeds every particle from std::random_device
+// (gmapping_world.h:48), so two runs never agree bit for bit: both filters must simply track the truth.
+void run_gmapping(std::shared_ptr<slamgpu::Context> ctx) {
+  std::printf("== GMapping particle filter (reference classes, CUDA plug-ins), 8 particles\n");
+  MapPropertiesProvider props;
+  for (auto kv : std::vector<std::pair<const char *, const char *>>{
+         {"slam/particles/number", "8"}, {"slam/map/height_in_meters", "12"}, {"slam/map/width_in_meters", "12"},
+         {"slam/map/meters_per_cell", "0.05"}, {"slam/scmtch/spe/type", "wmpp"}, {"slam/scmtch/spe/wmpp/weighting/type", "even"},
+         {"slam/particles/sm_delta_lim/xy/min", "0.05"}, {"slam/particles/sm_delta_lim/xy/max", "0.06"},
+         {"slam/particles/sm_delta_lim/theta/min", "0.02"}, {"slam/particles/sm_delta_lim/theta/max", "0.03"},
+         {"slam/particles/sample/xy/sigma", "0.02"}, {"slam/particles/sample/theta/sigma", "0.01"}})
+    props.set_property(kv.first, kv.second);
+  auto ref = init_gmapping(props);
+  auto gpu = slamgpu::init_cuda_gmapping(props, ctx);
+  std::mt19937 rng(41);
+  RobotPose truth{0.0, 0.0, 0.0};
+  for (int step = 0; step < 10; ++step) {
+    RobotPoseDelta motion = step == 0 ? RobotPoseDelta{0, 0, 0} : RobotPoseDelta{0.10, 0.04, 0.03};
+    truth += motion;
+    auto scan = room_scan(truth, 360, 2 * M_PI, 3.0, 2.5, rng, 0.005);
+    TransformedLaserScan a{motion, scan, 1.0}, b{motion, scan, 1.0};
+    b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+    ref->handle_sensor_data(a);
+    gpu->handle_sensor_data(b);
+  }
+  const RobotPose &p1 = ref->pose(), &p2 = gpu->pose();
+  double e1 = std::hypot(p1.x - truth.x, p1.y - truth.y), e2 = std::hypot(p2.x - truth.x, p2.y - truth.y);
+  std::printf("   truth %.3f %.3f %.3f | reference %.3f %.3f %.3f (err %.3f) | cuda %.3f %.3f %.3f (err %.3f)\n", truth.x, truth.y,
+              truth.theta, p1.x, p1.y, p1.theta, e1, p2.x, p2.y, p2.theta, e2);
+  CHECK(std::isfinite(p2.x) && std::isfinite(p2.y) && std::isfinite(p2.theta), "gmapping: pose is not finite");
+  CHECK(e2 < 0.25 && std::fabs(p2.theta - truth.theta) < 0.15, "gmapping: the CUDA filter lost track (err %.3f)", e2);
+  long known = 0;
+  const GridMap &m = gpu->map();
+  auto org = m.origin();
+  for (int y = 0; y < m.height(); ++y)
+    for (int x = 0; x < m.width(); ++x) known += !m[GridMap::Coord{x - org.x, y - org.y}].is_unknown();
+  CHECK(known > 2000, "gmapping: only %ld known cells in the heaviest particle's map", known);
+}
+
 }  // namespace
 
 int main() {
@@ -331,6 +370,7 @@ int main() {
     run_host_map(ctx);
     run_m3rsm(ctx);
     run_presets(ctx);
+    run_gmapping(ctx);
   } catch (const std::exception &e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 1;
