@@ -233,7 +233,7 @@ int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_p
 int slamgpu_score_launch(slamgpu_ctx *ctx, slamgpu_map *map, double init_score);
 int slamgpu_score_fetch(slamgpu_ctx *ctx, double *out_scores /* NULL ok */, int64_t *best_idx, double *best_score);
 /* counters of the last scoring call: [0] guard hits (points re-done with host trig),
- * [1] kernel variant used (0 list, 1 grid v1, 2 grid v2, 3 two-phase small batch), [2] evaluations (poses*points) on this rank,
+ * [1] kernel variant used (0 list, 1 grid v1, 2 grid v2 / 3 grid v3, 3 two-phase small batch when staged, 4 fused one-launch small batch), [2] evaluations (poses*points) on this rank,
  * [3] first candidate index of this rank's slice, [4] slice length, [5] grid kernel rows per thread */
 int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]);
 

@@ -317,6 +317,132 @@ __global__ void __launch_bounds__(128) k_pose_sums(PointArgs pa) {
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
 }
 
+// ---- the one-shot form of the small-batch path: two launches between ONE H2D and ONE D2H.  Inputs travel in
+// one staging buffer {header | poses | views | view ids}, outputs come back as {header | scores}.
+struct SmallHdr {
+  Result best;             // out: final (score, index, guard)
+  unsigned int ticket;     // in: 0
+  unsigned int pad0;
+  unsigned long long guard;  // in: 0
+  double pad1[2];
+};
+
+struct SmallArgs {
+  MapView map;
+  const MapView *views;  // or NULL
+  const int *view_id;
+  const double *poses;   // 3*P
+  const double *range, *angle, *sx, *sy, *w, *f;
+  int N, P;
+  double wsum, win_v, win_h, gm_th, init_score;
+  int gm_win;
+  SmallHdr *hdr;
+  double *scores;        // P, directly after the header in the output buffer
+  double *terms;         // P*N
+};
+
+template <int MODE, bool PREROT, bool FACTOR>
+__global__ void __launch_bounds__(128) k_small_fused(SmallArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.y;
+  if (i < a.N) {
+    const double px = a.poses[3 * p], py = a.poses[3 * p + 1];
+    const MapView &mv = a.views ? a.views[a.view_id[p]] : a.map;
+    const double s = mv.scale, inv_s = 1.0 / mv.scale;
+    double X, Y, rc = 0, rs = 0;
+    bool unsafe_any = false;
+    if (PREROT) {
+      X = sg::add(__ldg(a.sx + i), px); Y = sg::add(__ldg(a.sy + i), py);
+    } else {
+      double sn, cs;
+      sincos(sg::add(a.poses[3 * p + 2], __ldg(a.angle + i)), &sn, &cs);
+      const double r = __ldg(a.range + i);
+      rc = sg::mul(r, cs); rs = sg::mul(r, sn);
+      X = sg::add(px, rc); Y = sg::add(py, rs);
+    }
+    double prob;
+    if (MODE == SLAMGPU_OOPE_OBSTACLE || MODE == SLAMGPU_OOPE_GMAPPING) {
+      const int cx = grid_cell(X, rc, s, inv_s, PREROT ? 0 : 1, &unsafe_any);
+      const int cy = grid_cell(Y, rs, s, inv_s, PREROT ? 0 : 1, &unsafe_any);
+      prob = MODE == SLAMGPU_OOPE_OBSTACLE ? lut_at(mv, cx, cy) : gmapping_probability(mv, cx, cy, X, Y, a.gm_th, a.gm_win);
+    } else {
+      if (!PREROT) {
+        double hv = sg::div(a.win_v, 2.0), hh = sg::div(a.win_h, 2.0);
+        bool u;
+        sg::world_to_cell_guard(sg::sub(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::add(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::sub(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+      }
+      prob = window_probability<MODE>(mv, X, Y, a.win_v, a.win_h);
+    }
+    double term = sg::mul(prob, __ldg(a.w + i));
+    if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+    a.terms[(size_t)p * a.N + i] = term;
+    if (unsafe_any) atomicAdd(&a.hdr->guard, 1ull);
+  }
+}
+
+// phase 2 of the one-shot path: each block stages the terms of its G poses in shared memory (coalesced), one
+// thread per pose adds them in point order, block arg-max; the last block to finish (ticket) merges the block
+// results and applies the accept rule
+__global__ void __launch_bounds__(256) k_small_final(SmallArgs a, int G, Best *blk) {
+  extern __shared__ double sh_terms[];  // [G][N]
+  const int q0 = blockIdx.x * G;
+  const int nq = min(G, a.P - q0);
+  const double *src = a.terms + (size_t)q0 * a.N;
+  for (int e = threadIdx.x; e < nq * a.N; e += blockDim.x) sh_terms[e] = __ldcg(src + e);
+  __syncthreads();
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  if (threadIdx.x < nq) {
+    const double *t = sh_terms + (size_t)threadIdx.x * a.N;
+    double total = 0;
+    for (int k = 0; k < a.N; ++k) total = sg::add(total, t[k]);
+    const double score = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
+    const int q = q0 + threadIdx.x;
+    a.scores[q] = score;
+    if (score == score) { best_s = score; best_i = q; }
+  }
+  block_argmax(best_s, best_i, blk + blockIdx.x);
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&a.hdr->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  best_s = -INFINITY; best_i = LLONG_MAX;
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) {
+    const double bs = __ldcg(&blk[k].score);
+    const long long bi = __ldcg(&blk[k].idx);
+    if (beats(bs, bi, best_s, best_i)) { best_s = bs; best_i = bi; }
+  }
+  __shared__ Best s_best;
+  __syncthreads();
+  block_argmax(best_s, best_i, &s_best);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sc = s_best.score;
+    long long id = s_best.idx;
+    if (!(a.init_score < sc) || id == LLONG_MAX) { sc = a.init_score; id = -1; }
+    a.hdr->best.score = sc; a.hdr->best.idx = id;
+    a.hdr->best.guard = (long long)a.hdr->guard;
+    a.hdr->best.pad = 0;
+  }
+}
+
+template <int MODE>
+void launch_small_m(slamgpu_ctx *ctx, const SmallArgs &a, dim3 grd, bool prerot, bool factor) {
+  if (prerot) {
+    if (factor) k_small_fused<MODE, true, true><<<grd, 128, 0, ctx->stream>>>(a);
+    else k_small_fused<MODE, true, false><<<grd, 128, 0, ctx->stream>>>(a);
+  } else {
+    if (factor) k_small_fused<MODE, false, true><<<grd, 128, 0, ctx->stream>>>(a);
+    else k_small_fused<MODE, false, false><<<grd, 128, 0, ctx->stream>>>(a);
+  }
+}
+
 // ------------------------------------------------------------------ grid (brute force) path
 struct GridIdxArgs {
   const double *trc, *trs;  // [t*N + i]
@@ -1296,10 +1422,114 @@ extern "C" int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]) {
   return SLAMGPU_OK;
 }
 
+
+#define SG_FUSED_MAX_POSES 1024
+
+// returns 1 if the call was served by the fused small-batch path, 0 if the caller must take the staged path
+static int score_small_oneshot(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
+                               const slamgpu_spe_params *p, const double *poses, int64_t P, double init_score, double *out_scores,
+                               int64_t *best_idx, double *best_score, int *served) {
+  *served = 0;
+  const int N = scan->n;
+  if (ctx->nranks != 1 || P <= 0 || P > SG_FUSED_MAX_POSES || N <= 0 || P * (int64_t)N > SG_SMALL_MAX_TERMS) return SLAMGPU_OK;
+  if (p->trig_mode != SLAMGPU_TRIG_DEVICE && !p->prerotated) return SLAMGPU_OK;
+  if (p->oope == SLAMGPU_OOPE_OVERLAP && !p->prerotated) return SLAMGPU_OK;  // always libm trig: staged path
+  if (p->oope == SLAMGPU_OOPE_GMAPPING && p->reserved) return SLAMGPU_OK;    // cache emulation: staged path
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<MapView> views((size_t)n_maps);
+  for (int k = 0; k < n_maps; ++k) {
+    if (!maps[k] || maps[k]->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map %d is NULL or belongs to another ctx", k);
+    if (p->oope != SLAMGPU_OOPE_GMAPPING) SG_TRY(sg_map_ensure_lut(maps[k], p->oie));
+    views[k] = make_view(maps[k], p->oie);
+  }
+  const bool multi = view_id != nullptr;
+  // staging layout (8-byte aligned pieces)
+  const size_t o_hdr = 0, o_poses = sizeof(SmallHdr), o_views = o_poses + sizeof(double) * 3 * P;
+  const size_t o_vid = o_views + (multi ? sizeof(MapView) * n_maps : 0);
+  const size_t in_bytes = ((o_vid + (multi ? sizeof(int32_t) * P : 0)) + 15) & ~(size_t)15;
+  const size_t out_bytes = sizeof(SmallHdr) + sizeof(double) * P;
+  const size_t terms_bytes = sizeof(double) * (size_t)P * N;
+  // device: [in | scores (directly after the header? no: separate out block) | terms]
+  DevBuf &db = ctx->scratch[6];
+  const size_t d_out = in_bytes, d_terms = (d_out + out_bytes + 15) & ~(size_t)15, d_blk = (d_terms + terms_bytes + 15) & ~(size_t)15;
+  if (db.reserve(d_blk + sizeof(Best) * (size_t)(P + 1)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "small-batch buffers");
+  void *hp;
+  SG_TRY(sg_pinned(ctx, std::max(in_bytes, out_bytes), &hp));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  char *h = (char *)hp;
+  memset(h + o_hdr, 0, sizeof(SmallHdr));
+  memcpy(h + o_poses, poses, sizeof(double) * 3 * P);
+  if (multi) {
+    memcpy(h + o_views, views.data(), sizeof(MapView) * n_maps);
+    memcpy(h + o_vid, view_id, sizeof(int32_t) * P);
+    for (int64_t k = 0; k < P; ++k)
+      if (view_id[k] < 0 || view_id[k] >= n_maps) return sg_fail(ctx, SLAMGPU_E_INVALID, "pose %lld: bad particle id", (long long)k);
+  }
+  char *d = (char *)db.p;
+  SG_CUDA(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  SmallArgs a;
+  a.map = views[0];
+  a.views = multi ? (const MapView *)(d + o_views) : nullptr;
+  a.view_id = multi ? (const int *)(d + o_vid) : nullptr;
+  a.poses = (const double *)(d + o_poses);
+  a.range = scan->d_range; a.angle = scan->d_angle; a.sx = scan->d_x; a.sy = scan->d_y; a.w = scan->d_w; a.f = scan->d_f;
+  a.N = N; a.P = (int)P; a.wsum = scan->wsum; a.win_v = p->win_v; a.win_h = p->win_h; a.gm_th = p->gm_fullness_th;
+  a.init_score = init_score; a.gm_win = p->gm_window;
+  // the header the kernel updates is the one at the start of the OUT block: copy the zeroed input header there first
+  a.hdr = (SmallHdr *)(d + d_out);
+  a.scores = (double *)(d + d_out + sizeof(SmallHdr));
+  a.terms = (double *)(d + d_terms);
+  SG_CUDA(ctx, cudaMemcpyAsync(d + d_out, d, sizeof(SmallHdr), cudaMemcpyDeviceToDevice, ctx->stream));
+  dim3 grd((N + 127) / 128, (unsigned)P);
+  const bool pre = p->prerotated != 0, fac = scan->has_factor;
+  cudaEventRecord(ctx->evk0, ctx->stream);
+  switch (p->oope) {
+    case SLAMGPU_OOPE_OBSTACLE: launch_small_m<SLAMGPU_OOPE_OBSTACLE>(ctx, a, grd, pre, fac); break;
+    case SLAMGPU_OOPE_MAX: launch_small_m<SLAMGPU_OOPE_MAX>(ctx, a, grd, pre, fac); break;
+    case SLAMGPU_OOPE_MEAN: launch_small_m<SLAMGPU_OOPE_MEAN>(ctx, a, grd, pre, fac); break;
+    case SLAMGPU_OOPE_OVERLAP: launch_small_m<SLAMGPU_OOPE_OVERLAP>(ctx, a, grd, pre, fac); break;
+    default: launch_small_m<SLAMGPU_OOPE_GMAPPING>(ctx, a, grd, pre, fac); break;
+  }
+  cudaEventRecord(ctx->evk1, ctx->stream);
+  ctx->evk_valid = true;
+  {
+    static bool attr_set = false;
+    const size_t max_shm = 96 * 1024;
+    if (!attr_set) {
+      SG_CUDA(ctx, cudaFuncSetAttribute(k_small_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_shm));
+      attr_set = true;
+    }
+    int G = (int)std::min<int64_t>(16, (int64_t)(max_shm / (sizeof(double) * N)));
+    if (G < 1) return SLAMGPU_OK;  // a scan too long for the staging block: staged path
+    const int nb = (int)((P + G - 1) / G);
+    k_small_final<<<nb, 256, sizeof(double) * (size_t)G * N, ctx->stream>>>(a, G, (Best *)(d + d_blk));
+  }
+  ctx->launches += 2;
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaMemcpyAsync(h, d + d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const SmallHdr *rh = (const SmallHdr *)h;
+  if (rh->best.guard > 0) return SLAMGPU_OK;  // a point sits on a cell border: the staged path redoes it with libm trig
+  if (best_idx) *best_idx = rh->best.idx;
+  if (best_score) *best_score = rh->best.score;
+  if (out_scores) memcpy(out_scores, h + sizeof(SmallHdr), sizeof(double) * P);
+  Candidates &c = ctx->cand;
+  c.kind = -1; c.launched = false;
+  memset(c.stats, 0, sizeof c.stats);
+  c.stats[1] = 4; c.stats[2] = P * N; c.stats[4] = P;
+  *served = 1;
+  return SLAMGPU_OK;
+}
+
 extern "C" int slamgpu_score_poses(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
                                    const double *poses, int64_t P, double init_score, double *out_scores, int64_t *best_idx,
                                    double *best_score) {
   if (!ctx) return SLAMGPU_E_INVALID;
+  if (map && scan && p && poses && check_spe(ctx, scan, p) == SLAMGPU_OK) {
+    int served = 0;
+    SG_TRY(score_small_oneshot(ctx, &map, 1, nullptr, scan, p, poses, P, init_score, out_scores, best_idx, best_score, &served));
+    if (served) return SLAMGPU_OK;
+  }
   SG_TRY(slamgpu_stage_poses(ctx, scan, p, poses, P));
   SG_TRY(launch_staged(ctx, map, init_score));
   return fetch_impl(ctx, map, out_scores, best_idx, best_score);
@@ -1318,6 +1548,11 @@ extern "C" int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_sc
 int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
                          const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores) {
   if (!ctx || !maps || n_maps <= 0 || (P > 0 && !view_id)) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_multi: bad argument");
+  if (scan && p && poses && check_spe(ctx, scan, p) == SLAMGPU_OK) {
+    int served = 0;
+    SG_TRY(score_small_oneshot(ctx, maps, n_maps, view_id, scan, p, poses, P, -INFINITY, out_scores, nullptr, nullptr, &served));
+    if (served) return SLAMGPU_OK;
+  }
   SG_TRY(slamgpu_stage_poses(ctx, scan, p, poses, P));
   Candidates &c = ctx->cand;
   std::vector<MapView> views(n_maps);
