@@ -2,6 +2,7 @@
 // by side with the unmodified CPU classes on the same synthetic scans; every pose and every map cell
 // must be identical.  Built here against the reference headers (host/Makefile), run on the GPU box by
 // tests/test_gpu_dropin.py.
+#include <chrono>
 #include <cstdio>
 #include <random>
 
@@ -137,6 +138,7 @@ void run_world_pair(const Config &cfg, std::shared_ptr<slamgpu::Context> ctx) {
   std::mt19937 rng(7);
   std::normal_distribution<double> odo(0.0, 0.02), odo_t(0.0, 0.01);
   RobotPose truth{0.3, -0.2, 0.1};
+  double ref_ms = 0, gpu_ms = 0;
   // both worlds start at the origin; the first scan is matched against an empty map
   RobotPose prev = truth;
   for (int step = 0; step < cfg.steps; ++step) {
@@ -147,8 +149,13 @@ void run_world_pair(const Config &cfg, std::shared_ptr<slamgpu::Context> ctx) {
     auto scan = room_scan(truth, cfg.beams, cfg.fov, 4.0, 3.0, rng, 0.01);
     TransformedLaserScan a{odom, scan, 1.0}, b{odom, scan, 1.0};
     b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();  // no shared mutable state between the two worlds
+    auto t0 = std::chrono::steady_clock::now();
     ref_world.handle_sensor_data(a);
+    auto t1 = std::chrono::steady_clock::now();
     gpu_world.handle_sensor_data(b);
+    static_cast<const slamgpu::CudaGridMap &>(gpu_world.map()).flush();  // the queued scan insertion belongs to this scan
+    auto t2 = std::chrono::steady_clock::now();
+    if (step > 0) { ref_ms += std::chrono::duration<double, std::milli>(t1 - t0).count(); gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count(); }
     const RobotPose &p1 = ref_world.pose(), &p2 = gpu_world.pose();
     CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "%s step %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)", cfg.name,
           step, p1.x, p1.y, p1.theta, p2.x, p2.y, p2.theta);
@@ -161,6 +168,8 @@ void run_world_pair(const Config &cfg, std::shared_ptr<slamgpu::Context> ctx) {
   }
   std::printf("   %d scans, %ld candidate poses scored on the device, final pose %.6f %.6f %.6f\n", cfg.steps, obs_gpu->tests,
               gpu_world.pose().x, gpu_world.pose().y, gpu_world.pose().theta);
+  std::printf("   TIMING per scan (handle_sensor_data: match + insert, wall clock, scans 1..%d): reference CPU %.3f ms, CUDA plug-ins %.3f ms\n",
+              cfg.steps - 1, ref_ms / (cfg.steps - 1), gpu_ms / (cfg.steps - 1));
 }
 
 // a CUDA matcher handed a plain host map of the reference (score-LUT snapshot path)
