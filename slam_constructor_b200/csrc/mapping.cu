@@ -36,11 +36,12 @@ struct RaycastArgs {
   const BeamRec *beams;
   const long long *offsets;  // slot offset of each beam (exclusive prefix of the upper bounds)
   int N;
-  double px, py, scale;
+  const MapSlot *maps;
+  double scale;
   slamgpu_estimator est;
-  double shift_amount;
   int2 *cells;      // per slot
   BeamOut *out;     // per beam
+  unsigned long long *counters;  // per map: [2*id] cells visited (one add per beam)
 };
 
 __global__ void k_raycast(RaycastArgs a) {
@@ -52,14 +53,16 @@ __global__ void k_raycast(RaycastArgs a) {
   if (b.active) {
     int2 *dst = a.cells + a.offsets[i];
     int lx = 0, ly = 0;
-    o.count = sg::raycast(a.px, a.py, b.wx, b.wy, a.scale, [&](int k, int x, int y) {
+    const double px = a.maps[b.map_id].px, py = a.maps[b.map_id].py;
+    o.count = sg::raycast(px, py, b.wx, b.wy, a.scale, [&](int k, int x, int y) {
       dst[k] = make_int2(x, y);
       lx = x; ly = y;
     });
     o.lx = lx; o.ly = ly;
+    atomicAdd(a.counters + 2 * b.map_id, (unsigned long long)o.count);
     // the obstacle cell is estimated (and, in the reference, updated) first: grid_map_scan_adders.h:151-154
     const double s = a.scale;
-    sg::estimate_occupancy(a.est, a.shift_amount, a.px, a.py, b.wx, b.wy, sg::mul(s, (double)ly), sg::mul(s, (double)(ly + 1)),
+    sg::estimate_occupancy(a.est, a.maps[b.map_id].shift, px, py, b.wx, b.wy, sg::mul(s, (double)ly), sg::mul(s, (double)(ly + 1)),
                            sg::mul(s, (double)lx), sg::mul(s, (double)(lx + 1)), b.is_occ != 0, &o.base_p, &o.base_q);
   }
   a.out[i] = o;
@@ -72,23 +75,35 @@ struct EstimateArgs {
   const long long *offsets;  // N + 1
   int N;
   long long M;  // total slots
-  double px, py, scale;
+  const MapSlot *maps;
+  double scale;
   slamgpu_estimator est;
-  double shift_amount;
   const int2 *cells;
-  int w, h, ox, oy;
   double *aoo_p, *aoo_q;  // per slot
   unsigned *keys;         // per slot: internal cell index or SG_INVALID_KEY
   unsigned *vals;         // per slot: slot id
   int *slot_beam;         // per slot
-  unsigned long long *counters;  // [0] valid cells, [1] updates dropped outside a bounded map
+  unsigned long long *counters;  // per map: [2*id+1] updates dropped outside a bounded map ([2*id]: see k_raycast)
 };
 
 __global__ void k_estimate(EstimateArgs a) {
-  long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long s0 = blockIdx.x * (long long)blockDim.x;
+  long long s = s0 + threadIdx.x;
+  // beam of a slot: last i with offsets[i] <= s.  Two threads bracket the block's slots with a full binary search,
+  // the others search inside that bracket (a block rarely spans more than a couple of beams)
+  __shared__ int s_range[2];
+  if (threadIdx.x < 2) {
+    long long t = threadIdx.x == 0 ? s0 : min(s0 + (long long)blockDim.x - 1, a.M - 1);
+    int lo = 0, hi = a.N;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (a.offsets[mid] <= t) lo = mid; else hi = mid;
+    }
+    s_range[threadIdx.x] = lo;
+  }
+  __syncthreads();
   if (s >= a.M) return;
-  // beam of this slot: last i with offsets[i] <= s
-  int lo = 0, hi = a.N;
+  int lo = s_range[0], hi = s_range[1] + 1;
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
     if (a.offsets[mid] <= s) lo = mid; else hi = mid;
@@ -100,13 +115,14 @@ __global__ void k_estimate(EstimateArgs a) {
   a.slot_beam[s] = i;
   if (k >= bo.count) { a.keys[s] = SG_INVALID_KEY; return; }
   const BeamRec b = a.beams[i];
+  const MapSlot ms = a.maps[b.map_id];
   const int2 c = a.cells[s];
   double p, q;
   if (k == bo.count - 1) {
     p = bo.base_p; q = bo.base_q;
   } else {
     const double sc = a.scale;
-    sg::estimate_occupancy(a.est, a.shift_amount, a.px, a.py, b.wx, b.wy, sg::mul(sc, (double)c.y), sg::mul(sc, (double)(c.y + 1)),
+    sg::estimate_occupancy(a.est, ms.shift, ms.px, ms.py, b.wx, b.wy, sg::mul(sc, (double)c.y), sg::mul(sc, (double)(c.y + 1)),
                            sg::mul(sc, (double)c.x), sg::mul(sc, (double)(c.x + 1)), false, &p, &q);
     // wall blur ("hole"), grid_map_scan_adders.h:160-169; distances in cells, squared (exact in double)
     double ddx = (double)(c.x - b.obx), ddy = (double)(c.y - b.oby);
@@ -117,14 +133,13 @@ __global__ void k_estimate(EstimateArgs a) {
     }
   }
   a.aoo_p[s] = p; a.aoo_q[s] = q;
-  int ix = c.x + a.ox, iy = c.y + a.oy;
-  if (ix < 0 || ix >= a.w || iy < 0 || iy >= a.h) {
+  int ix = c.x + ms.ox, iy = c.y + ms.oy;
+  if (ix < 0 || ix >= ms.w || iy < 0 || iy >= ms.h) {
     a.keys[s] = SG_INVALID_KEY;
-    atomicAdd(a.counters + 1, 1ull);
+    atomicAdd(a.counters + 2 * b.map_id + 1, 1ull);
   } else {
-    a.keys[s] = (unsigned)iy * (unsigned)a.w + (unsigned)ix;
+    a.keys[s] = ms.key_base + (unsigned)iy * (unsigned)ms.w + (unsigned)ix;
   }
-  atomicAdd(a.counters, 1ull);
 }
 
 // ---------------------------------------------------------------- stable LSD radix sort (8-bit digits)
@@ -178,6 +193,52 @@ __global__ void __launch_bounds__(1024) k_radix_scan(unsigned *data, int n) {  /
     if (threadIdx.x == 1023) carry = excl + v;
     __syncthreads();
   }
+}
+
+// large histograms: per-chunk exclusive scan (4096 counters a block) + chunk totals, one-block scan of the
+// totals (k_radix_scan), then the chunk offsets are added back
+#define SG_SCAN_CHUNK 4096
+__global__ void __launch_bounds__(1024) k_scan_chunks(unsigned *data, int n, unsigned *totals) {
+  __shared__ unsigned warp_sums[32];
+  const int base = blockIdx.x * SG_SCAN_CHUNK + threadIdx.x * 4;
+  unsigned v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = base + k < n ? data[base + k] : 0u;
+  const unsigned mine = v[0] + v[1] + v[2] + v[3];
+  unsigned x = mine;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned ws = warp_sums[lane], sx = ws;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned y = __shfl_up_sync(0xffffffffu, sx, off);
+      if (lane >= off) sx += y;
+    }
+    warp_sums[lane] = sx - ws;
+    if (lane == 31) totals[blockIdx.x] = sx;
+  }
+  __syncthreads();
+  unsigned run = x - mine + warp_sums[wid];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(unsigned *data, int n, const unsigned *__restrict__ totals) {
+  const unsigned add = totals[blockIdx.x];
+  const int base = blockIdx.x * SG_SCAN_CHUNK + threadIdx.x * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n) data[base + k] += add;
 }
 
 __global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigned *__restrict__ keys_in,
@@ -241,7 +302,8 @@ __global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigne
 // streams through contiguous memory instead of chasing slot -> beam -> AOO pointers
 struct SortedAoo {
   double p, q, quality, wx, wy;
-  unsigned slot, pad;
+  unsigned slot;
+  int map_id;
 };
 
 struct GatherArgs {
@@ -260,7 +322,7 @@ __global__ void k_gather_sorted(GatherArgs a) {
   const unsigned s = a.vals[t];
   const BeamRec &b = a.beams[a.slot_beam[s]];
   SortedAoo o;
-  o.p = a.aoo_p[s]; o.q = a.aoo_q[s]; o.quality = b.quality; o.wx = b.wx; o.wy = b.wy; o.slot = s; o.pad = 0;
+  o.p = a.aoo_p[s]; o.q = a.aoo_q[s]; o.quality = b.quality; o.wx = b.wx; o.wy = b.wy; o.slot = s; o.map_id = b.map_id;
   a.out[t] = o;
 }
 
@@ -268,7 +330,7 @@ struct ApplyArgs {
   const unsigned *keys;  // sorted
   const SortedAoo *aoo;  // sorted
   long long M;
-  double *cells;
+  const MapSlot *maps;
   int stride, model;
   // optional trace for the pyramid: post-update impact of every applied slot (indexed by slot)
   double *trace_impact;
@@ -283,9 +345,10 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   if (key == SG_INVALID_KEY) return;
   if (j > 0 && a.keys[j - 1] == key) return;  // not the head of this cell's run
   double r[SLAMGPU_MAX_STRIDE];
-  double *cell = a.cells + (size_t)key * a.stride;
-  for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
   SortedAoo cur = a.aoo[j];
+  const MapSlot &ms = a.maps[cur.map_id];
+  double *cell = ms.cells + (size_t)(key - ms.key_base) * a.stride;
+  for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
   for (long long t = j;;) {
     const bool more = t + 1 < a.M && a.keys[t + 1] == key;
     SortedAoo nxt = cur;
@@ -493,6 +556,8 @@ int upload_async(slamgpu_ctx *ctx, DevBuf &dst, const void *src, size_t bytes) {
   return SLAMGPU_OK;
 }
 
+size_t map_counters_offset(size_t n) { return (n * sizeof(MapSlot) + 63) & ~(size_t)63; }
+
 double est_shift(const slamgpu_estimator &e, double scale, const BeamPlan &plan) {
   // Shift_Amount is a function-static of the reference, fixed by the first cell it ever estimates
   // (quirk Q10): the obstacle cell of the first inserted beam
@@ -503,20 +568,27 @@ double est_shift(const slamgpu_estimator &e, double scale, const BeamPlan &plan)
   return e.low_qual * (scale * (ly + 1) - scale * ly);
 }
 
-// K2 for a prepared plan: fills scratch[0] (beams), [1] (offsets), [2] (cells), [3] (BeamOut)
-int run_raycast(slamgpu_ctx *ctx, const slamgpu_map *m, const BeamPlan &plan, const slamgpu_estimator &est) {
-  const int N = (int)plan.beams.size();
-  SG_TRY(upload_async(ctx, ctx->scratch[0], plan.beams.data(), sizeof(BeamRec) * N));
-  SG_TRY(upload_async(ctx, ctx->scratch[1], plan.offsets.data(), sizeof(long long) * (N + 1)));
-  if (ctx->scratch[2].reserve(std::max<size_t>(plan.M, 1) * sizeof(int2)) != SLAMGPU_OK ||
+// K2 for prepared beams (one or several maps): fills scratch[0] (beams), [1] (offsets), [2] (cells), [3] (BeamOut),
+// scratch[7] (MapSlot array, px/py valid; dims are refreshed after the growth check)
+int run_raycast_multi(slamgpu_ctx *ctx, double scale, const std::vector<BeamRec> &beams, const std::vector<long long> &offsets,
+                      long long M, const std::vector<MapSlot> &slots, const slamgpu_estimator &est) {
+  const int N = (int)beams.size();
+  SG_TRY(upload_async(ctx, ctx->scratch[0], beams.data(), sizeof(BeamRec) * N));
+  SG_TRY(upload_async(ctx, ctx->scratch[1], offsets.data(), sizeof(long long) * (N + 1)));
+  // scratch[7]: MapSlot[n] | counters[2n]
+  const size_t coff = map_counters_offset(slots.size());
+  if (ctx->scratch[7].reserve(coff + 16 * slots.size()) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "map slots");
+  SG_TRY(upload_async(ctx, ctx->scratch[7], slots.data(), sizeof(MapSlot) * slots.size()));
+  SG_CUDA(ctx, cudaMemsetAsync((char *)ctx->scratch[7].p + coff, 0, 16 * slots.size(), ctx->stream));
+  if (ctx->scratch[2].reserve(std::max<size_t>(M, 1) * sizeof(int2)) != SLAMGPU_OK ||
       ctx->scratch[3].reserve(std::max<size_t>(N, 1) * sizeof(BeamOut)) != SLAMGPU_OK)
-    return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast buffers (%lld slots)", plan.M);
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast buffers (%lld slots)", M);
   if (N == 0) return SLAMGPU_OK;
   RaycastArgs a;
   a.beams = ctx->scratch[0].as<BeamRec>(); a.offsets = ctx->scratch[1].as<long long>(); a.N = N;
-  a.px = plan.px; a.py = plan.py; a.scale = m->scale; a.est = est;
-  a.shift_amount = est_shift(est, m->scale, plan);
+  a.maps = ctx->scratch[7].as<MapSlot>(); a.scale = scale; a.est = est;
   a.cells = ctx->scratch[2].as<int2>(); a.out = ctx->scratch[3].as<BeamOut>();
+  a.counters = (unsigned long long *)((char *)ctx->scratch[7].p + coff);
   cudaEventRecord(ctx->evk0, ctx->stream);
   k_raycast<<<(N + 31) / 32, 32, 0, ctx->stream>>>(a);
   cudaEventRecord(ctx->evk1, ctx->stream);
@@ -524,6 +596,17 @@ int run_raycast(slamgpu_ctx *ctx, const slamgpu_map *m, const BeamPlan &plan, co
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
   return SLAMGPU_OK;
+}
+
+MapSlot slot_of(const slamgpu_map *m, double px, double py, double shift, unsigned key_base) {
+  MapSlot s;
+  s.cells = m->d_cells; s.px = px; s.py = py; s.shift = shift; s.w = m->w; s.h = m->h; s.ox = m->ox; s.oy = m->oy; s.key_base = key_base; s.pad = 0;
+  return s;
+}
+
+int run_raycast(slamgpu_ctx *ctx, const slamgpu_map *m, const BeamPlan &plan, const slamgpu_estimator &est) {
+  std::vector<MapSlot> slots{slot_of(m, plan.px, plan.py, est_shift(est, m->scale, plan), 0)};
+  return run_raycast_multi(ctx, m->scale, plan.beams, plan.offsets, plan.M, slots, est);
 }
 
 }  // namespace
@@ -534,12 +617,22 @@ int sg_radix_sort(slamgpu_ctx *ctx, unsigned *keys, unsigned *vals, unsigned *ke
   while (bits < 32 && (max_key >> bits) != 0) ++bits;
   const int passes = (bits + 7) / 8;
   const int nb = (int)((n + SG_SORT_TILE - 1) / SG_SORT_TILE);
-  if (ctx->scratch[6].reserve((size_t)256 * std::max(nb, 1) * sizeof(unsigned)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "sort histogram");
+  const int nh = 256 * std::max(nb, 1);
+  const int nchunks = (nh + SG_SCAN_CHUNK - 1) / SG_SCAN_CHUNK;
+  if (ctx->scratch[6].reserve(((size_t)nh + nchunks) * sizeof(unsigned)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "sort histogram");
   unsigned *ghist = ctx->scratch[6].as<unsigned>();
+  unsigned *totals = ghist + nh;
   unsigned *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
   for (int p = 0; p < passes && nb > 0; ++p) {
     k_radix_hist<<<nb, SG_SORT_THREADS, 0, ctx->stream>>>(ki, n, 8 * p, ghist, nb);
-    k_radix_scan<<<1, 1024, 0, ctx->stream>>>(ghist, 256 * nb);
+    if (nchunks <= 4) {
+      k_radix_scan<<<1, 1024, 0, ctx->stream>>>(ghist, 256 * nb);
+    } else {
+      k_scan_chunks<<<nchunks, 1024, 0, ctx->stream>>>(ghist, 256 * nb, totals);
+      k_radix_scan<<<1, 1024, 0, ctx->stream>>>(totals, nchunks);
+      k_scan_add<<<nchunks, 1024, 0, ctx->stream>>>(ghist, 256 * nb, totals);
+      ctx->launches += 2;
+    }
     k_radix_scatter<<<nb, SG_SORT_THREADS, 0, ctx->stream>>>(ki, vi, ko, vo, n, 8 * p, ghist, nb);
     ctx->launches += 3;
     std::swap(ki, ko); std::swap(vi, vo);
@@ -569,78 +662,122 @@ int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, 
 // K2 + K3 for prepared beams (all sharing the begin point plan.px, plan.py)
 int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, const slamgpu_estimator *est,
                    int64_t *cells_updated, AppendTrace *trace) {
-  if (!ctx || !map || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append: NULL argument");
-  if (est->type != SLAMGPU_EST_CONST && est->type != SLAMGPU_EST_AREA) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad estimator type");
-  SG_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (cells_updated) *cells_updated = 0;
-  if (trace) { trace->M = 0; trace->applied = 0; }
-  const int N = (int)plan.beams.size();
-  if (plan.M == 0) return SLAMGPU_OK;
-  if (plan.M >= (1ll << 31)) return sg_fail(ctx, SLAMGPU_E_NOMEM, "scan insertion needs %lld cell slots", plan.M);
-  SG_TRY(run_raycast(ctx, map, plan, *est));
+  return sg_append_plans(ctx, &map, &plan, 1, est, cells_updated, trace);
+}
 
-  // ---- map growth (Q9): only when some beam leaves the current bounds; replays the reference's
-  // ensure_inside sequence over the cells in update order
-  if (map->grow != SLAMGPU_GROW_NONE) {
+// K2 + K3 for n maps at once (GMapping particles: every particle inserts the scan into its own map from its own
+// pose): one ray-cast launch, one estimate launch, ONE sort over (map, cell) keys and one apply launch for all of
+// them.  Maps must share cell model, cell size and ctx.  `trace` is only available for n == 1.
+int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *plans, int n, const slamgpu_estimator *est,
+                    int64_t *cells_updated, AppendTrace *trace) {
+  if (!ctx || !maps || !plans || n <= 0 || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append: NULL argument");
+  if (est->type != SLAMGPU_EST_CONST && est->type != SLAMGPU_EST_AREA) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad estimator type");
+  if (trace && n != 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "append: a trace needs a single map");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (cells_updated) for (int k = 0; k < n; ++k) cells_updated[k] = 0;
+  if (trace) { trace->M = 0; trace->applied = 0; }
+  for (int k = 0; k < n; ++k) {
+    if (!maps[k] || maps[k]->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map %d is NULL or belongs to another ctx", k);
+    if (maps[k]->model != maps[0]->model || maps[k]->scale != maps[0]->scale) return sg_fail(ctx, SLAMGPU_E_INVALID, "batched maps must share cell model and scale");
+  }
+  // ---- concatenate the plans
+  std::vector<long long> beam0(n + 1, 0), slot0(n + 1, 0);
+  for (int k = 0; k < n; ++k) { beam0[k + 1] = beam0[k] + (long long)plans[k].beams.size(); slot0[k + 1] = slot0[k] + plans[k].M; }
+  const long long M = slot0[n];
+  const int N = (int)beam0[n];
+  if (M == 0) return SLAMGPU_OK;
+  if (M >= (1ll << 31) || beam0[n] >= (1ll << 31)) return sg_fail(ctx, SLAMGPU_E_NOMEM, "scan insertion needs %lld cell slots", M);
+  const std::vector<BeamRec> *beams_ptr = &plans[0].beams;
+  const std::vector<long long> *offs_ptr = &plans[0].offsets;
+  std::vector<BeamRec> all_beams;
+  std::vector<long long> all_offs;
+  if (n > 1) {
+    all_beams.reserve(N); all_offs.reserve(N + 1);
+    for (int k = 0; k < n; ++k)
+      for (size_t i = 0; i < plans[k].beams.size(); ++i) {
+        BeamRec b = plans[k].beams[i];
+        b.map_id = k;
+        all_beams.push_back(b);
+        all_offs.push_back(slot0[k] + plans[k].offsets[i]);
+      }
+    all_offs.push_back(M);
+    beams_ptr = &all_beams; offs_ptr = &all_offs;
+  }
+  std::vector<MapSlot> slots(n);
+  // Shift_Amount per map, exactly as one call per map would fix it
+  for (int k = 0; k < n; ++k) slots[k] = slot_of(maps[k], plans[k].px, plans[k].py, est_shift(*est, maps[0]->scale, plans[k]), 0);
+  SG_TRY(run_raycast_multi(ctx, maps[0]->scale, *beams_ptr, *offs_ptr, M, slots, *est));
+
+  // ---- map growth (Q9): only when some beam leaves a map's current bounds; replays the reference's
+  // ensure_inside sequence over that map's cells in update order
+  for (int k = 0; k < n; ++k) {
+    slamgpu_map *map = maps[k];
+    const BeamPlan &plan = plans[k];
+    if (map->grow == SLAMGPU_GROW_NONE || plan.M == 0) continue;
     auto outside = [&](int x, int y) { int ix = x + map->ox, iy = y + map->oy; return ix < 0 || ix >= map->w || iy < 0 || iy >= map->h; };
     bool need = false;
-    for (int i = 0; i < N && !need; ++i)
+    const int Nk = (int)plan.beams.size();
+    for (int i = 0; i < Nk && !need; ++i)
       if (plan.beams[i].active && (outside(plan.rx, plan.ry) || outside(plan.beams[i].obx, plan.beams[i].oby))) need = true;
-    if (need) {
-      std::vector<int2> cells((size_t)plan.M);
-      std::vector<BeamOut> bout(N);
-      SG_CUDA(ctx, cudaMemcpyAsync(cells.data(), ctx->scratch[2].p, sizeof(int2) * plan.M, cudaMemcpyDeviceToHost, ctx->stream));
-      SG_CUDA(ctx, cudaMemcpyAsync(bout.data(), ctx->scratch[3].p, sizeof(BeamOut) * N, cudaMemcpyDeviceToHost, ctx->stream));
-      SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      GrowState g{map->w, map->h, map->ox, map->oy, map->grow};
-      for (int i = 0; i < N; ++i) {
-        if (!plan.beams[i].active) continue;
-        const int2 *c = cells.data() + plan.offsets[i];
-        const int n = bout[i].count;
-        g.ensure_inside(c[n - 1].x, c[n - 1].y);  // the obstacle cell is updated first
-        for (int k = 0; k < n - 1; ++k) g.ensure_inside(c[k].x, c[k].y);
-      }
-      SG_TRY(sg_map_regrow(map, g));
+    if (!need) continue;
+    std::vector<int2> cells((size_t)plan.M);
+    std::vector<BeamOut> bout(Nk);
+    SG_CUDA(ctx, cudaMemcpyAsync(cells.data(), ctx->scratch[2].as<int2>() + slot0[k], sizeof(int2) * plan.M, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(bout.data(), ctx->scratch[3].as<BeamOut>() + beam0[k], sizeof(BeamOut) * Nk, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GrowState g{map->w, map->h, map->ox, map->oy, map->grow};
+    for (int i = 0; i < Nk; ++i) {
+      if (!plan.beams[i].active) continue;
+      const int2 *c = cells.data() + plan.offsets[i];
+      const int cnt = bout[i].count;
+      g.ensure_inside(c[cnt - 1].x, c[cnt - 1].y);  // the obstacle cell is updated first
+      for (int q = 0; q < cnt - 1; ++q) g.ensure_inside(c[q].x, c[q].y);
     }
+    SG_TRY(sg_map_regrow(map, g));
   }
-  if ((long long)map->w * map->h >= 0xFFFFFFFFll) return sg_fail(ctx, SLAMGPU_E_NOMEM, "map too large for 32-bit cell keys");
+  // ---- key space: the maps end to end
+  unsigned long long key_total = 0;
+  for (int k = 0; k < n; ++k) {
+    slots[k] = slot_of(maps[k], plans[k].px, plans[k].py, slots[k].shift, (unsigned)key_total);
+    key_total += (unsigned long long)maps[k]->w * maps[k]->h;
+  }
+  if (key_total >= 0xFFFFFFFFull) return sg_fail(ctx, SLAMGPU_E_NOMEM, "maps too large for 32-bit cell keys (%llu cells): insert in smaller batches", key_total);
+  SG_TRY(upload_async(ctx, ctx->scratch[7], slots.data(), sizeof(MapSlot) * n));
 
   // ---- K3a: per-slot AOO + sort keys
-  const long long M = plan.M;
   DevBuf &slotbuf = ctx->scratch[4];
-  // layout: aoo_p[M] aoo_q[M] (double) | keys[M] vals[M] keys_tmp[M] vals_tmp[M] (u32) | slot_beam[M] (i32) | counters[2] (u64)
+  // layout: aoo_p[M] aoo_q[M] (double) | keys[M] vals[M] keys_tmp[M] vals_tmp[M] (u32) | slot_beam[M] (i32) | sorted aoo
+  const size_t cbytes = 0;
   size_t bytes = (size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 64 + (size_t)M * sizeof(SortedAoo) + 64;
   if (slotbuf.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "slot buffers (%lld slots)", M);
   double *aoo_p = slotbuf.as<double>(), *aoo_q = aoo_p + M;
   unsigned *keys = (unsigned *)(aoo_q + M), *vals = keys + M, *keys_tmp = vals + M, *vals_tmp = keys_tmp + M;
   int *slot_beam = (int *)(vals_tmp + M);
   size_t coff = ((size_t)M * (2 * sizeof(double) + 5 * sizeof(unsigned)) + 15) & ~(size_t)15;
-  unsigned long long *counters = (unsigned long long *)((char *)slotbuf.p + coff);
-  SortedAoo *sorted_aoo = (SortedAoo *)((char *)slotbuf.p + coff + 64);
-  SG_CUDA(ctx, cudaMemsetAsync(counters, 0, 16, ctx->stream));
+  unsigned long long *counters = (unsigned long long *)((char *)ctx->scratch[7].p + map_counters_offset(n));  // zeroed + cells counted by K2
+  SortedAoo *sorted_aoo = (SortedAoo *)((char *)slotbuf.p + coff + cbytes);
   EstimateArgs ea;
   ea.beams = ctx->scratch[0].as<BeamRec>(); ea.bout = ctx->scratch[3].as<BeamOut>(); ea.offsets = ctx->scratch[1].as<long long>();
-  ea.N = N; ea.M = M; ea.px = plan.px; ea.py = plan.py; ea.scale = map->scale; ea.est = *est;
-  ea.shift_amount = est_shift(*est, map->scale, plan);
-  ea.cells = ctx->scratch[2].as<int2>(); ea.w = map->w; ea.h = map->h; ea.ox = map->ox; ea.oy = map->oy;
+  ea.N = N; ea.M = M; ea.maps = ctx->scratch[7].as<MapSlot>(); ea.scale = maps[0]->scale; ea.est = *est;
+  ea.cells = ctx->scratch[2].as<int2>();
   ea.aoo_p = aoo_p; ea.aoo_q = aoo_q; ea.keys = keys; ea.vals = vals; ea.slot_beam = slot_beam; ea.counters = counters;
   k_estimate<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
 
-  // ---- sort by cell (stable), then apply each cell's run in order
+  // ---- sort by (map, cell) (stable), then apply each cell's run in order
   unsigned *ks, *vs;
-  SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)((long long)map->w * map->h), &ks, &vs));
+  SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)key_total, &ks, &vs));
   GatherArgs ga;
   ga.keys = ks; ga.vals = vs; ga.M = M; ga.aoo_p = aoo_p; ga.aoo_q = aoo_q; ga.slot_beam = slot_beam;
   ga.beams = ctx->scratch[0].as<BeamRec>(); ga.out = sorted_aoo;
   k_gather_sorted<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ga);
   SG_LAUNCHED(ctx);
   ApplyArgs aa;
-  aa.keys = ks; aa.aoo = sorted_aoo; aa.M = M; aa.cells = map->d_cells; aa.stride = map->stride; aa.model = map->model;
+  aa.keys = ks; aa.aoo = sorted_aoo; aa.M = M; aa.maps = ctx->scratch[7].as<MapSlot>(); aa.stride = maps[0]->stride; aa.model = maps[0]->model;
   aa.trace_impact = nullptr; aa.trace_rec = nullptr; aa.trace_oie = 0;
   if (trace) {
-    if (ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + map->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
+    if (ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + maps[0]->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
     aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_rec = aa.trace_impact + M; aa.trace_oie = trace->oie;
   }
   cudaEventRecord(ctx->evk0, ctx->stream);
@@ -649,11 +786,12 @@ int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, con
   ctx->evk_valid = true;
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
-  sg_map_invalidate_lut(map);
-  unsigned long long h_counters[2];
-  SG_CUDA(ctx, cudaMemcpyAsync(h_counters, counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int k = 0; k < n; ++k)
+    if (plans[k].M > 0) sg_map_invalidate_lut(maps[k]);
+  std::vector<unsigned long long> h_counters((size_t)n * 2);
+  SG_CUDA(ctx, cudaMemcpyAsync(h_counters.data(), counters, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (cells_updated) *cells_updated = (int64_t)h_counters[0];
+  if (cells_updated) for (int k = 0; k < n; ++k) cells_updated[k] = (int64_t)h_counters[2 * k];
   if (trace) {
     trace->M = M; trace->applied = (int64_t)h_counters[0];
     trace->cells = ctx->scratch[2].as<int2>(); trace->keys_sorted = ks; trace->vals_sorted = vs;

@@ -11,6 +11,7 @@ struct BeamRec {  // host-prepared, one per scan point
   double obst_sq;     // squared cell distance robot -> obstacle cell
   int obx, oby;       // obstacle cell
   int is_occ, active; // active: inside the margin and the range gate
+  int map_id, pad;    // which map of a batched insertion (0 for a single map)
 };
 struct BeamOut {  // device-produced, one per scan point
   int count;          // ray-cast cells of this beam
@@ -24,6 +25,15 @@ struct BeamPlan {
   long long M = 0;
   double px = 0, py = 0;
   int rx = 0, ry = 0;  // robot cell
+};
+// one map of a (possibly batched) insertion as the kernels see it
+struct MapSlot {
+  double *cells;
+  double px, py;       // robot position the beams of this map start at
+  double shift;        // the area estimator's Shift_Amount for this map's beams
+  int w, h, ox, oy;
+  unsigned key_base;   // first sort key of this map (maps are laid end to end in key space)
+  unsigned pad;
 };
 struct GrowState {
   int w, h, ox, oy, grow;
@@ -49,6 +59,8 @@ int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double p
                      double blur, double max_range, const double *point_quality, bool gate, BeamPlan *plan);
 int sg_plan_from_beams(slamgpu_ctx *ctx, const slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
                        const double *quality, double blur, double max_range, BeamPlan *out);
+int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *plans, int n, const slamgpu_estimator *est,
+                    int64_t *cells_updated, AppendTrace *trace);
 int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, const slamgpu_estimator *est,
                    int64_t *cells_updated, AppendTrace *trace);
 int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,

@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "mapping.h"
@@ -194,13 +196,55 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
                                              const slamgpu_estimator *est, double blur, double max_range,
                                              const double *point_quality, int64_t *cells_updated) {
   if (!p || !scan || !poses || !est) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  if (scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan belongs to another ctx");
+  if (scan_margin < 0) return sg_fail(ctx, SLAMGPU_E_INVALID, "negative scan margin");
   const int n = (int)p->maps.size();
-  for (int i = 0; i < n; ++i) {
-    int64_t cells = 0;
-    if (!do_update || do_update[i])
-      SG_TRY(sg_append_scan_impl(p->ctx, p->maps[i], scan, poses + 3 * i, scan_quality, scan_margin, est, blur, max_range,
-                                 point_quality, &cells, nullptr));
-    if (cells_updated) cells_updated[i] = cells;
+  if (cells_updated) for (int i = 0; i < n; ++i) cells_updated[i] = 0;
+  if (scan->n == 0) return SLAMGPU_OK;
+  std::vector<int> who;
+  for (int i = 0; i < n; ++i)
+    if (!do_update || do_update[i]) who.push_back(i);
+  if (who.empty()) return SLAMGPU_OK;
+  // host beam preparation (libm trig per beam, as the reference computes the end points) on a few threads
+  const int m = (int)who.size();
+  std::vector<BeamPlan> plans(m);
+  std::vector<int> rc(m, SLAMGPU_OK);
+  auto prep = [&](int k) {
+    rc[k] = sg_prepare_beams(p->maps[who[k]], scan, poses + 3 * who[k], scan_quality, scan_margin, blur, max_range, point_quality, true, &plans[k]);
+  };
+  const int nthreads = (int)std::min<long long>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u),
+                                               ((long long)m * scan->n + 16383) / 16384);
+  if (nthreads <= 1) {
+    for (int k = 0; k < m; ++k) prep(k);
+  } else {
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&] { for (int k; (k = next.fetch_add(1)) < m;) prep(k); });
+    for (auto &t : pool) t.join();
+  }
+  for (int k = 0; k < m; ++k)
+    if (rc[k] != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_INVALID, "particle %d: a beam spans more than 2^26 cells", who[k]);
+  // batches bounded by the 32-bit (map, cell) key space and 2^30 cell slots
+  std::vector<slamgpu_map *> maps;
+  std::vector<int64_t> counts;
+  for (int k0 = 0; k0 < m;) {
+    unsigned long long keys = 0;
+    long long slots = 0;
+    int k1 = k0;
+    while (k1 < m) {
+      // growth may enlarge a map before the keys are laid out: leave 4x head room
+      unsigned long long cells = 4ull * (unsigned long long)p->maps[who[k1]]->w * p->maps[who[k1]]->h;
+      if (k1 > k0 && (keys + cells >= 0xF0000000ull || slots + plans[k1].M >= (1ll << 30))) break;
+      keys += cells; slots += plans[k1].M; ++k1;
+    }
+    maps.clear();
+    for (int k = k0; k < k1; ++k) maps.push_back(p->maps[who[k]]);
+    counts.assign(k1 - k0, 0);
+    SG_TRY(sg_append_plans(ctx, maps.data(), plans.data() + k0, k1 - k0, est, counts.data(), nullptr));
+    if (cells_updated) for (int k = k0; k < k1; ++k) cells_updated[who[k]] = counts[k - k0];
+    k0 = k1;
   }
   return SLAMGPU_OK;
 }

@@ -106,3 +106,29 @@ def test_resample_copies_maps_on_device(sg, gpu):
     after[1] = clone
     _check_maps(parts, after)
     gsc.close(); parts.close()
+
+
+@pytest.mark.parametrize("grow", ["tiled", "plain"])
+def test_batched_insertion_grows_each_map_like_the_oracle(sg, gpu, grow):
+    """every particle's map starts too small, so the batched insertion replays a different growth per map"""
+    rng = np.random.default_rng(4100)
+    n = 9
+    g_gpu = sg.GROW_TILED if grow == "tiled" else sg.GROW_PLAIN
+    g_or = ob.GROW_TILED if grow == "tiled" else ob.GROW_PLAIN
+    parts = sg.Particles(gpu, n, 40, 40, 0.1, ob.CELL_TBM_CONSISTENT, g_gpu)
+    omaps = [ob.OracleMap(40, 40, 0.1, ob.CELL_TBM_CONSISTENT, g_or) for _ in range(n)]
+    oest, gest = ob.estimator(ob.EST_AREA), sg.estimator(sg.EST_AREA)
+    truth = np.array([0.3, 0.1, -0.2])
+    for k in range(3):
+        r, a = room_scan(rng, 151, 2 * np.pi, half_w=4.0 + k, half_h=3.0 + k, pose=truth, noise=0.01)
+        poses = truth + rng.normal(0, [0.2, 0.2, 0.05], (n, 3))
+        gsc = sg.Scan(gpu, r, a)
+        cells = parts.append_scan(gsc, poses, est=gest, blur=0.3)
+        for i in range(n):
+            c, _ = omaps[i].append_scan(ob.OracleScan(r, a), poses[i], 1.0, 0, oest, blur=0.3)
+            assert c == cells[i]
+        gsc.close()
+        truth = truth + [0.4, -0.3, 0.1]
+    infos = {tuple(sorted(parts.map(i).info().items())) for i in range(n)}
+    assert len(infos) > 1 or grow == "tiled"  # the maps really diverged (tiled growth may coincide)
+    _check_maps(parts, omaps)

@@ -42,6 +42,25 @@ def pyramid_numbers(ctx, size=4096, scale=0.025):
     return {"grid": [size, size], "levels": levels, "build_ms": round(ms, 3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
 
 
+def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=360):
+    """GMapping-shaped step: n particles, each with its own map; one batched scan insertion, one lock-step hill climb"""
+    rng = np.random.default_rng(7)
+    parts = sg.Particles(ctx, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
+    est = sg.estimator(sg.EST_CONST)
+    pose = np.array([0.3, -0.2, 0.1])
+    r, a = bench.room_ranges(rng, beams, 2 * np.pi, size * scale * 0.35, size * scale * 0.3, pose, 0.01)
+    scan = sg.Scan(ctx, r, a)
+    poses = pose + rng.normal(0, [0.02, 0.02, 0.01], (n, 3))
+    cells = parts.append_scan(scan, poses, est=est)
+    upd = timeit(lambda: parts.append_scan(scan, poses, est=est), n=10, warm=2)
+    params = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1)
+    hc = timeit(lambda: parts.match_hc(scan, params, poses), n=10, warm=2)
+    parts.close(); scan.close()
+    tot = int(np.sum(cells))
+    return {"particles": n, "grid": [size, size], "beams": beams, "append_scan_us": round(upd, 1), "cells_per_step": tot,
+            "cell_updates_per_s": tot / (upd * 1e-6), "hill_climb_us": round(hc, 1)}
+
+
 def measure(ctx):
     rng = np.random.default_rng(1)
     out = {}
@@ -76,6 +95,7 @@ def measure(ctx):
                      "update_algorithmic_GBps": cells * rec_bytes / (upd * 1e-6) / 1e9}
         gm.close(); scan.close()
     out["pyramid_build"] = pyramid_numbers(ctx)
+    out["gmapping_step"] = particle_numbers(ctx)
     return out
 
 
