@@ -322,7 +322,12 @@ int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *range, cons
  * replaces the per-particle loop of GmappingParticleFilter::handle_observation
  * (src/slams/gmapping/gmapping_particle_filter.h:70-85): n particles, each with its OWN device map.
  * Pose noise, weights, N_eff and the resampling draw stay on the host (libstdc++ <random>,
- * src/slams/gmapping/gmapping_world.h:81-85, src/core/particle_filter.h:34-106). */
+ * src/slams/gmapping/gmapping_world.h:81-85, src/core/particle_filter.h:34-106).
+ * On a distributed ctx (slamgpu_ctx_create_dist) the particles are sharded: rank r owns the contiguous range
+ * [r*ceil(n/R), (r+1)*ceil(n/R)) with those maps on its GPU.  Every call below is collective: all ranks pass the
+ * same arrays over all n particles and all receive the complete result (one NCCL all-gather per call); resample
+ * ships maps whose source lives on another rank with ncclSend/ncclRecv.  slamgpu_particles_map returns NULL for a
+ * particle of another rank. */
 int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
                              const double *unknown_rec, slamgpu_particles **out);
 void slamgpu_particles_destroy(slamgpu_particles *p);
@@ -340,12 +345,14 @@ int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *scan, const s
                                const double *init_poses /* 3*n */, const uint8_t *active /* n or NULL */,
                                uint32_t max_failed_rounds, double translation_delta, double rotation_delta,
                                double *out_poses /* 3*n */, double *out_probs /* n */, int64_t *out_tested /* n or NULL */);
-/* GridMapScanAdder::append_scan into every particle's own map from its own pose (do_update NULL: all) */
+/* GridMapScanAdder::append_scan into every particle's own map from its own pose (do_update NULL: all); the beams of
+ * all particles go through one batched ray-cast, one sort keyed by (map, cell) and one ordered apply */
 int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses /* 3*n */,
                                   const uint8_t *do_update /* n or NULL */, double scan_quality, int32_t scan_margin,
                                   const slamgpu_estimator *est, double blur, double max_range, const double *point_quality,
                                   int64_t *cells_updated /* n or NULL */);
-/* the copy step of ParticleFilter::try_resample (src/core/particle_filter.h:92-98): particle i := particle src[i] */
+/* the copy step of ParticleFilter::try_resample (src/core/particle_filter.h:92-98): particle i := particle src[i];
+ * a source drawn once is moved, the others are copied device to device (or rank to rank) */
 int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src /* n */);
 
 #ifdef __cplusplus

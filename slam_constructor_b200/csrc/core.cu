@@ -194,6 +194,21 @@ int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv) {
   return SLAMGPU_OK;
 }
 
+int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes) {
+  if (ctx->nranks <= 1 || chunk_bytes == 0) return SLAMGPU_OK;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t total = chunk_bytes * ctx->nranks, mine = chunk_bytes * ctx->rank;
+  if (ctx->gather.reserve(total) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "all-gather staging");
+  char *d = ctx->gather.as<char>();
+  SG_CUDA(ctx, cudaMemcpyAsync(d + mine, (char *)host + mine, chunk_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  std::string err;
+  int r = sg_nccl_allgather(ctx->comm, d + mine, d, chunk_bytes, ctx->stream, &err);  // in place
+  if (r != SLAMGPU_OK) return sg_fail(ctx, r, "%s", err.c_str());
+  SG_CUDA(ctx, cudaMemcpyAsync(host, d, total, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SLAMGPU_OK;
+}
+
 // ------------------------------------------------------------------ map
 extern "C" int slamgpu_model_stride(int model) { return sg::model_stride(model); }
 

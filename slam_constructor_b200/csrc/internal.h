@@ -147,4 +147,14 @@ int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv);
 int sg_nccl_unique_id(void *id128, std::string *err);
 int sg_nccl_init(int nranks, int rank, const void *id128, void **comm, std::string *err);
 int sg_nccl_allgather(void *comm, const void *send, void *recv, size_t bytes, cudaStream_t s, std::string *err);
+// rank-local work on a distributed ctx (per-particle scoring: the particles, not the candidates, are sharded)
+struct SgLocalScope {
+  slamgpu_ctx *c; int rank, nranks;
+  explicit SgLocalScope(slamgpu_ctx *ctx) : c(ctx), rank(ctx->rank), nranks(ctx->nranks) { c->rank = 0; c->nranks = 1; }
+  ~SgLocalScope() { c->rank = rank; c->nranks = nranks; }
+};
+struct SgXfer { int peer; void *ptr; size_t bytes; };
+int sg_nccl_exchange(void *comm, const SgXfer *sends, int n_sends, const SgXfer *recvs, int n_recvs, cudaStream_t s, std::string *err);
 void sg_nccl_destroy(void *comm);
+// all-gather of host data: `host` holds nranks chunks of chunk_bytes, this rank's chunk filled in; on return all are
+int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);

@@ -23,9 +23,15 @@
 
 #include "mapping.h"
 
+// On a distributed ctx the PARTICLES are sharded: rank r owns the contiguous range [lo, hi) of the n particles
+// (chunks of ceil(n / nranks)), with their maps on its GPU; `maps` has n entries, NULL for the others.  Every call
+// takes and returns arrays over all n particles and must be made by every rank with the same arguments; results are
+// exchanged with one all-gather per call, cloned maps travel rank to rank in slamgpu_particles_resample.
 struct slamgpu_particles {
   slamgpu_ctx *ctx = nullptr;
   std::vector<slamgpu_map *> maps;
+  int lo = 0, hi = 0, chunk = 0;
+  int owner(int i) const { return i / chunk; }
 };
 
 extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, int32_t h, double scale, int32_t model,
@@ -34,11 +40,13 @@ extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, 
   *out = nullptr;
   slamgpu_particles *p = new slamgpu_particles();
   p->ctx = ctx;
-  for (int i = 0; i < n; ++i) {
-    slamgpu_map *m = nullptr;
-    int r = slamgpu_map_create(ctx, w, h, scale, model, grow, unknown_rec, &m);
+  p->chunk = (n + ctx->nranks - 1) / ctx->nranks;
+  p->lo = std::min(n, p->chunk * ctx->rank);
+  p->hi = std::min(n, p->lo + p->chunk);
+  p->maps.assign(n, nullptr);
+  for (int i = p->lo; i < p->hi; ++i) {
+    int r = slamgpu_map_create(ctx, w, h, scale, model, grow, unknown_rec, &p->maps[i]);
     if (r != SLAMGPU_OK) { slamgpu_particles_destroy(p); return r; }
-    p->maps.push_back(m);
   }
   *out = p;
   return SLAMGPU_OK;
@@ -46,7 +54,8 @@ extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, 
 
 extern "C" void slamgpu_particles_destroy(slamgpu_particles *p) {
   if (!p) return;
-  for (slamgpu_map *m : p->maps) slamgpu_map_destroy(m);
+  for (slamgpu_map *m : p->maps)
+    if (m) slamgpu_map_destroy(m);
   delete p;
 }
 
@@ -60,11 +69,20 @@ extern "C" slamgpu_map *slamgpu_particles_map(slamgpu_particles *p, int32_t i) {
 extern "C" int slamgpu_particles_score(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
                                        const double *poses, int32_t per_particle, double *out_scores) {
   if (!p || !spe || per_particle < 0 || (per_particle > 0 && (!poses || !out_scores))) return SLAMGPU_E_INVALID;
-  const int n = (int)p->maps.size();
-  const int64_t P = (int64_t)n * per_particle;
-  std::vector<int32_t> vid((size_t)P);
-  for (int64_t k = 0; k < P; ++k) vid[k] = (int32_t)(k / per_particle);
-  return sg_score_poses_multi(p->ctx, p->maps.data(), n, vid.data(), scan, spe, poses, P, out_scores);
+  slamgpu_ctx *ctx = p->ctx;
+  const int n = (int)p->maps.size(), nl = p->hi - p->lo;
+  const int64_t P = (int64_t)nl * per_particle;
+  if (per_particle == 0) return SLAMGPU_OK;
+  std::vector<double> all((size_t)p->chunk * ctx->nranks * per_particle, NAN);
+  double *mine = all.data() + (size_t)p->chunk * ctx->rank * per_particle;
+  if (P > 0) {
+    std::vector<int32_t> vid((size_t)P);
+    for (int64_t k = 0; k < P; ++k) vid[k] = (int32_t)(k / per_particle);
+    SG_TRY(sg_score_poses_multi(ctx, p->maps.data() + p->lo, nl, vid.data(), scan, spe, poses + 3 * (size_t)p->lo * per_particle, P, mine));
+  }
+  SG_TRY(sg_allgather_host(ctx, all.data(), sizeof(double) * p->chunk * per_particle));
+  memcpy(out_scores, all.data(), sizeof(double) * (size_t)n * per_particle);
+  return SLAMGPU_OK;
 }
 
 namespace {
@@ -133,26 +151,29 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
                                           int64_t *out_tested) {
   if (!p || !scan || !spe || !init_poses || !out_poses || !out_probs) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
-  const int n = (int)p->maps.size();
+  const int n = (int)p->maps.size(), lo = p->lo, nl = p->hi - p->lo;
+  slamgpu_map *const *lmaps = p->maps.data() + lo;  // view ids are local: particle i is view i - lo
+  std::vector<char> mine(n, 0);
+  for (int i = 0; i < n; ++i) mine[i] = i >= lo && i < p->hi && (!active || active[i]);
   std::vector<HillClimb> hc(n);
   std::vector<double> poses;
   std::vector<int32_t> vid;
   std::vector<double> scores;
   // probability of the initial poses (pose_enumeration_scan_matcher.h:40)
   for (int i = 0; i < n; ++i) {
-    if (active && !active[i]) continue;
+    if (!mine[i]) continue;
     poses.insert(poses.end(), init_poses + 3 * i, init_poses + 3 * i + 3);
-    vid.push_back(i);
+    vid.push_back(i - lo);
   }
   scores.resize(vid.size());
   if (!vid.empty())
-    SG_TRY(sg_score_poses_multi(ctx, p->maps.data(), n, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
+    SG_TRY(sg_score_poses_multi(ctx, lmaps, nl, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
   size_t q = 0;
   for (int i = 0; i < n; ++i) {
     HillClimb &h = hc[i];
     h.bx = init_poses[3 * i]; h.by = init_poses[3 * i + 1]; h.bt = init_poses[3 * i + 2];
     h.tr = translation_delta; h.rot = rotation_delta;
-    if (active && !active[i]) { h.done = true; h.best = NAN; h.tested = 0; continue; }
+    if (!mine[i]) { h.done = true; h.best = NAN; h.tested = 0; continue; }
     h.best = scores[q++];
     h.done = !(0 < max_failed_rounds);
   }
@@ -169,18 +190,30 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
       cands.insert(cands.end(), &c6[0][0], &c6[0][0] + 18);
       for (int j = 0; j < k; ++j) {
         poses.push_back(c6[j][0]); poses.push_back(c6[j][1]); poses.push_back(c6[j][2]);
-        vid.push_back(i);
+        vid.push_back(i - lo);
       }
     }
     if (who.empty()) break;
     scores.resize(vid.size());
-    SG_TRY(sg_score_poses_multi(ctx, p->maps.data(), n, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
+    SG_TRY(sg_score_poses_multi(ctx, lmaps, nl, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
     size_t off = 0;
     for (size_t e = 0; e < who.size(); ++e) {
       double c6[6][3];
       memcpy(c6, cands.data() + 18 * e, sizeof c6);
       hc[who[e]].apply(max_failed_rounds, c6, scores.data() + off, cnt[e]);
       off += cnt[e];
+    }
+  }
+  if (ctx->nranks > 1) {  // every rank learns every particle's result: 5 x f64 per particle
+    std::vector<double> all((size_t)p->chunk * ctx->nranks * 5, 0.0);
+    for (int i = lo; i < p->hi; ++i) {
+      double *r = all.data() + 5 * (size_t)i;
+      r[0] = hc[i].bx; r[1] = hc[i].by; r[2] = hc[i].bt; r[3] = hc[i].best; r[4] = (double)hc[i].tested;
+    }
+    SG_TRY(sg_allgather_host(ctx, all.data(), sizeof(double) * 5 * p->chunk));
+    for (int i = 0; i < n; ++i) {
+      const double *r = all.data() + 5 * (size_t)i;
+      hc[i].bx = r[0]; hc[i].by = r[1]; hc[i].bt = r[2]; hc[i].best = r[3]; hc[i].tested = (int64_t)r[4];
     }
   }
   for (int i = 0; i < n; ++i) {
@@ -201,11 +234,17 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
   if (scan_margin < 0) return sg_fail(ctx, SLAMGPU_E_INVALID, "negative scan margin");
   const int n = (int)p->maps.size();
   if (cells_updated) for (int i = 0; i < n; ++i) cells_updated[i] = 0;
-  if (scan->n == 0) return SLAMGPU_OK;
+  if (scan->n == 0) return SLAMGPU_OK;  // on every rank alike: no collective is skipped one-sidedly
   std::vector<int> who;
-  for (int i = 0; i < n; ++i)
+  for (int i = p->lo; i < p->hi; ++i)
     if (!do_update || do_update[i]) who.push_back(i);
-  if (who.empty()) return SLAMGPU_OK;
+  std::vector<int64_t> all_counts((size_t)p->chunk * ctx->nranks, 0);
+  auto publish = [&]() -> int {
+    if (ctx->nranks > 1) SG_TRY(sg_allgather_host(ctx, all_counts.data(), sizeof(int64_t) * p->chunk));
+    if (cells_updated) memcpy(cells_updated, all_counts.data(), sizeof(int64_t) * n);
+    return SLAMGPU_OK;
+  };
+  if (who.empty()) return publish();
   // host beam preparation (libm trig per beam, as the reference computes the end points) on a few threads
   const int m = (int)who.size();
   std::vector<BeamPlan> plans(m);
@@ -243,10 +282,10 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
     for (int k = k0; k < k1; ++k) maps.push_back(p->maps[who[k]]);
     counts.assign(k1 - k0, 0);
     SG_TRY(sg_append_plans(ctx, maps.data(), plans.data() + k0, k1 - k0, est, counts.data(), nullptr));
-    if (cells_updated) for (int k = k0; k < k1; ++k) cells_updated[who[k]] = counts[k - k0];
+    for (int k = k0; k < k1; ++k) all_counts[who[k]] = counts[k - k0];
     k0 = k1;
   }
-  return SLAMGPU_OK;
+  return publish();
 }
 
 // ParticleFilter::try_resample's copy step (src/core/particle_filter.h:92-98): particle i becomes a
@@ -255,37 +294,80 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
 extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src) {
   if (!p || !src) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
-  const int n = (int)p->maps.size();
+  const int n = (int)p->maps.size(), lo = p->lo, hi = p->hi;
   for (int i = 0; i < n; ++i)
     if (src[i] < 0 || src[i] >= n) return sg_fail(ctx, SLAMGPU_E_INVALID, "resample: bad source index %d", src[i]);
   SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  // ---- sources on other ranks: every rank learns every map's geometry, then the cells travel in one NCCL group
+  // (sender: the map as it is now; receiver: a staging buffer, so that no map is overwritten while a peer reads it)
+  struct Geo { int32_t w, h, ox, oy; };
+  std::vector<Geo> geo;
+  std::vector<DevBuf> staged(n);
+  auto release_staged = [&]() { for (DevBuf &b : staged) b.release(); };
+  if (ctx->nranks > 1) {
+    geo.assign((size_t)p->chunk * ctx->nranks, Geo{0, 0, 0, 0});
+    for (int i = lo; i < hi; ++i) geo[i] = Geo{p->maps[i]->w, p->maps[i]->h, p->maps[i]->ox, p->maps[i]->oy};
+    SG_TRY(sg_allgather_host(ctx, geo.data(), sizeof(Geo) * p->chunk));
+    const int stride = slamgpu_model_stride(p->lo < p->hi ? p->maps[lo]->model : 0);
+    std::vector<SgXfer> sends, recvs;
+    for (int i = 0; i < n; ++i) {  // the same order on every rank
+      const int q = p->owner(src[i]), r = p->owner(i);
+      if (q == r) continue;
+      if (ctx->rank == q) {
+        slamgpu_map *m = p->maps[src[i]];
+        sends.push_back(SgXfer{r, m->d_cells, (size_t)m->w * m->h * m->stride * sizeof(double)});
+      } else if (ctx->rank == r) {
+        const Geo &g = geo[src[i]];
+        const size_t bytes = (size_t)g.w * g.h * stride * sizeof(double);
+        if (staged[i].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) { release_staged(); return sg_fail(ctx, SLAMGPU_E_NOMEM, "resample: staging for particle %d", i); }
+        recvs.push_back(SgXfer{q, staged[i].p, bytes});
+      }
+    }
+    std::string err;
+    int rc = sg_nccl_exchange(ctx->comm, sends.data(), (int)sends.size(), recvs.data(), (int)recvs.size(), ctx->stream, &err);
+    if (rc != SLAMGPU_OK) { release_staged(); return sg_fail(ctx, rc, "%s", err.c_str()); }
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  // ---- this rank's particles
   std::vector<slamgpu_map *> next(n, nullptr);
   std::vector<char> taken(n, 0);
+  auto local = [&](int i) { return i >= lo && i < hi; };
   // keep a surviving particle in place when it can be (no copy at all for the common "i -> i")
-  for (int i = 0; i < n; ++i)
+  for (int i = lo; i < hi; ++i)
     if (src[i] == i) { next[i] = p->maps[i]; taken[i] = 1; }
-  // first other use of a source whose own slot is not reused takes the object itself
-  for (int i = 0; i < n; ++i) {
-    if (next[i]) continue;
+  // first other use of a (local) source whose own slot is not reused takes the object itself
+  for (int i = lo; i < hi; ++i) {
+    if (next[i] || !local(src[i])) continue;
     if (!taken[src[i]]) { next[i] = p->maps[src[i]]; taken[src[i]] = 1; }
   }
   // the rest are copies into the maps nobody kept
   std::vector<slamgpu_map *> spare;
-  for (int i = 0; i < n; ++i)
+  for (int i = lo; i < hi; ++i)
     if (!taken[i]) spare.push_back(p->maps[i]);
-  for (int i = 0; i < n; ++i) {
-    if (next[i]) continue;
-    slamgpu_map *from = p->maps[src[i]];
-    slamgpu_map *to = spare.back();
-    spare.pop_back();
-    SG_TRY(sg_map_realloc(to, from->w, from->h));
-    to->ox = from->ox; to->oy = from->oy;
-    SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, from->d_cells, (size_t)from->w * from->h * from->stride * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, ctx->stream));
-    sg_map_invalidate_lut(to);
-    next[i] = to;
-  }
+  // local sources first (they are all kept maps), then the staged remote ones
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = lo; i < hi; ++i) {
+      if (next[i] || local(src[i]) != (pass == 0)) continue;
+      slamgpu_map *to = spare.back();
+      spare.pop_back();
+      if (pass == 0) {
+        slamgpu_map *from = p->maps[src[i]];
+        SG_TRY(sg_map_realloc(to, from->w, from->h));
+        to->ox = from->ox; to->oy = from->oy;
+        SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, from->d_cells, (size_t)from->w * from->h * from->stride * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      } else {
+        const Geo &g = geo[src[i]];
+        SG_TRY(sg_map_realloc(to, g.w, g.h));
+        to->ox = g.ox; to->oy = g.oy;
+        SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, staged[i].p, (size_t)g.w * g.h * to->stride * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      sg_map_invalidate_lut(to);
+      next[i] = to;
+    }
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  release_staged();
   p->maps.swap(next);
   return SLAMGPU_OK;
 }

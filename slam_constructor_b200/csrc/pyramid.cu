@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <string>
 #include <vector>
 
 #include "dev_window.cuh"
@@ -35,6 +36,7 @@ struct slamgpu_pyramid {
   std::vector<slamgpu_map *> lv;  // lv[0] is the caller's fine map (not owned)
   DevBuf ent;                     // per-update working arrays of the incremental fold
   DevBuf views, matches, scans, terms, bounds;  // K5 staging
+  std::vector<slamgpu_scan *> rot_scans;        // pre-rotated copies of the scan being matched (slamgpu_match_m3rsm)
 };
 
 namespace {
@@ -348,6 +350,7 @@ extern "C" void slamgpu_pyramid_destroy(slamgpu_pyramid *p) {
   if (!p) return;
   if (!p->lv.empty() && p->lv[0]) p->lv[0]->pyr = nullptr;
   for (size_t i = 1; i < p->lv.size(); ++i) slamgpu_map_destroy(p->lv[i]);
+  for (slamgpu_scan *s : p->rot_scans) slamgpu_scan_destroy(s);
   DevBuf *bufs[] = {&p->ent, &p->views, &p->matches, &p->scans, &p->terms, &p->bounds};
   for (DevBuf *b : bufs) b->release();
   delete p;
@@ -554,23 +557,40 @@ extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *sc
     if (used[l]) SG_TRY(sg_map_ensure_lut(p->lv[l], spe->oie));
     views[l] = level_view(p->lv[l], spe->oie);
   }
+  // multi-GPU: a large batch (the root matches of all rotations) is split into contiguous chunks, one per rank, on the
+  // replicated pyramid; one all-gather of the bounds (8 B x M) puts the whole batch on every rank, so the host engine
+  // advances identically everywhere.  Small batches (children of a branch) are scored redundantly: no collective.
+  const bool shard = ctx->nranks > 1 && M >= 4 * (int64_t)ctx->nranks;
+  const int64_t chunk = shard ? (M + ctx->nranks - 1) / ctx->nranks : M;
+  const int64_t m0 = shard ? std::min<int64_t>(M, chunk * ctx->rank) : 0;
+  const int64_t m1 = shard ? std::min<int64_t>(M, m0 + chunk) : M;
+  const int64_t Ml = m1 - m0;
+  const int64_t Mpad = shard ? chunk * ctx->nranks : M;
   if (p->views.reserve(sizeof(MapView) * L) != SLAMGPU_OK || p->matches.reserve(sizeof(MatchRec) * M) != SLAMGPU_OK ||
-      p->scans.reserve(sizeof(ScanView) * n_scans) != SLAMGPU_OK || p->terms.reserve(sizeof(double) * M * n_max) != SLAMGPU_OK ||
-      p->bounds.reserve(sizeof(double) * M) != SLAMGPU_OK)
+      p->scans.reserve(sizeof(ScanView) * n_scans) != SLAMGPU_OK || p->terms.reserve(sizeof(double) * std::max<int64_t>(Ml, 1) * n_max) != SLAMGPU_OK ||
+      p->bounds.reserve(sizeof(double) * Mpad) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "score_windows buffers");
   SG_CUDA(ctx, cudaMemcpyAsync(p->views.p, views.data(), sizeof(MapView) * L, cudaMemcpyHostToDevice, ctx->stream));
   SG_CUDA(ctx, cudaMemcpyAsync(p->matches.p, mr.data(), sizeof(MatchRec) * M, cudaMemcpyHostToDevice, ctx->stream));
   SG_CUDA(ctx, cudaMemcpyAsync(p->scans.p, sv.data(), sizeof(ScanView) * n_scans, cudaMemcpyHostToDevice, ctx->stream));
-  dim3 grd((n_max + 127) / 128, (unsigned)M);
-  cudaEventRecord(ctx->evk0, ctx->stream);
-  k_window_terms<<<grd, 128, 0, ctx->stream>>>(p->matches.as<MatchRec>(), p->scans.as<ScanView>(), p->views.as<MapView>(), n_max,
-                                                p->terms.as<double>());
-  cudaEventRecord(ctx->evk1, ctx->stream);
-  ctx->evk_valid = true;
-  k_ordered_sums<<<(unsigned)((M + 63) / 64), 64, 0, ctx->stream>>>(p->matches.as<MatchRec>(), p->scans.as<ScanView>(), n_max,
-                                                                   p->terms.as<double>(), M, p->bounds.as<double>());
-  ctx->launches += 2;
-  SG_CUDA(ctx, cudaGetLastError());
+  if (Ml > 0) {
+    dim3 grd((n_max + 127) / 128, (unsigned)Ml);
+    cudaEventRecord(ctx->evk0, ctx->stream);
+    k_window_terms<<<grd, 128, 0, ctx->stream>>>(p->matches.as<MatchRec>() + m0, p->scans.as<ScanView>(), p->views.as<MapView>(), n_max,
+                                                  p->terms.as<double>());
+    cudaEventRecord(ctx->evk1, ctx->stream);
+    ctx->evk_valid = true;
+    k_ordered_sums<<<(unsigned)((Ml + 63) / 64), 64, 0, ctx->stream>>>(p->matches.as<MatchRec>() + m0, p->scans.as<ScanView>(), n_max,
+                                                                      p->terms.as<double>(), Ml, p->bounds.as<double>() + m0);
+    ctx->launches += 2;
+    SG_CUDA(ctx, cudaGetLastError());
+  }
+  if (shard) {
+    std::string err;
+    double *b = p->bounds.as<double>();
+    int r = sg_nccl_allgather(ctx->comm, b + chunk * ctx->rank, b, sizeof(double) * chunk, ctx->stream, &err);  // in place
+    if (r != SLAMGPU_OK) return sg_fail(ctx, r, "%s", err.c_str());
+  }
   SG_CUDA(ctx, cudaMemcpyAsync(out_bounds, p->bounds.p, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
@@ -637,14 +657,12 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
     for (double rot : std::set<double>{rd, -rd}) rots.push_back(Rot{rot, (int)rots.size()});
   // ---- pre-rotated Cartesian copies of the scan: LaserScan2D::to_cartesian(rot + pose.theta)
   // (src/core/states/sensor_data.h:156-167, RawTrigonometryProvider: cos(base + angle))
-  static thread_local std::vector<slamgpu_scan *> pool;
+  std::vector<slamgpu_scan *> &pool = p->rot_scans;
   while (pool.size() < rots.size()) {
     slamgpu_scan *s = nullptr;
     SG_TRY(slamgpu_scan_create(ctx, &s));
     pool.push_back(s);
   }
-  for (slamgpu_scan *s : pool)
-    if (s->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_STATE, "match_m3rsm: one ctx per thread");
   std::vector<double> xs(std::max(n, 1)), ys(std::max(n, 1));
   for (size_t k = 0; k < rots.size(); ++k) {
     const double base = rots[k].rot + pose[2];

@@ -1548,6 +1548,7 @@ extern "C" int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_sc
 int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
                          const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores) {
   if (!ctx || !maps || n_maps <= 0 || (P > 0 && !view_id)) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_multi: bad argument");
+  SgLocalScope local_only(ctx);  // every pose of this call is scored here; ranks split the PARTICLES (particles.cu)
   if (scan && p && poses && check_spe(ctx, scan, p) == SLAMGPU_OK) {
     int served = 0;
     SG_TRY(score_small_oneshot(ctx, maps, n_maps, view_id, scan, p, poses, P, -INFINITY, out_scores, nullptr, nullptr, &served));
