@@ -108,8 +108,16 @@ typedef struct slamgpu_spe_params {
   int32_t trig_mode;     /* SLAMGPU_TRIG_* */
   double gm_fullness_th; /* GMapping OOPE fullness threshold */
   int32_t gm_window;     /* GMapping OOPE half window, cells */
-  int32_t reserved;
+  int32_t gm_cache;      /* GMapping OOPE one-entry cache (gmapping_occupancy_observation_pe.h:21-24,37-38):
+                            0 none (a pure function of the point), 1 restarted at every pose,
+                            2 carried from pose to pose as upstream does (slamgpu_score_poses_chained, particles) */
 } slamgpu_spe_params;
+
+/* the state of that cache: the cell and the probability last computed; prob == -1: nothing cached yet */
+typedef struct slamgpu_gm_cache {
+  int32_t cx, cy;
+  double prob;
+} slamgpu_gm_cache;
 
 /* CellOccupancyEstimator parameters (both kinds), src/utils/init_occupancy_mapping.h:42-80 */
 typedef struct slamgpu_estimator {
@@ -224,6 +232,15 @@ int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, c
                        const double *xs, int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt,
                        double init_score, double *out_scores /* nt*ny*nx or NULL */, int64_t *best_idx,
                        double *best_score);
+
+/* GMapping OOPE with its cache carried along: the poses are scored as ONE sequence, in the order given, the way a
+ * reference matcher evaluates its candidates one after the other -- pose k starts from the cache pose k-1 left,
+ * pose 0 from *state_in ({0, 0, -1} for a new estimator object).  out_states[k] = the cache after pose k: pass the
+ * state after the last candidate the matcher really consumed into the next call.  No arg-max: the accept rule of a
+ * cached estimator is order-dependent and stays with the caller.  At most 8192 poses and 4 Mi pose-points a call. */
+int slamgpu_score_poses_chained(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                                const double *poses, int64_t P, const slamgpu_gm_cache *state_in, double *out_scores /* P */,
+                                slamgpu_gm_cache *out_states /* P or NULL */);
 /* split form used by bench.py to time the device part with inputs resident in HBM:
  * stage a candidate set once, launch any number of times, fetch the last result */
 int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *poses,

@@ -29,13 +29,18 @@ c_u8p = C.POINTER(C.c_uint8)
 class SpeParams(C.Structure):
     _fields_ = [("oope", C.c_int32), ("oie", C.c_int32), ("win_v", C.c_double), ("win_h", C.c_double),
                 ("prerotated", C.c_int32), ("trig_mode", C.c_int32), ("gm_fullness_th", C.c_double),
-                ("gm_window", C.c_int32), ("reserved", C.c_int32)]
+                ("gm_window", C.c_int32), ("gm_cache", C.c_int32)]
 
 
 class Estimator(C.Structure):
     _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("occ_p", C.c_double), ("occ_q", C.c_double),
                 ("empty_p", C.c_double), ("empty_q", C.c_double), ("low_qual", C.c_double), ("unknown_qual", C.c_double),
                 ("shift_amount", C.c_double)]
+
+
+class GmCache(C.Structure):
+    """slamgpu_gm_cache: the GMapping OOPE's one-entry cache (cell, probability; prob == -1: empty)"""
+    _fields_ = [("cx", C.c_int32), ("cy", C.c_int32), ("prob", C.c_double)]
 
 
 def spe_params(oope=OOPE_OBSTACLE, oie=OIE_DISCREPANCY, win_v=0.0, win_h=0.0, prerotated=0, trig=TRIG_DEVICE, gm_th=0.1,
@@ -86,7 +91,7 @@ SYMBOLS = [
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
-    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_stage_poses",
+    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_stage_poses",
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
@@ -147,6 +152,7 @@ def lib():
     sp = C.POINTER(SpeParams)
     L.slamgpu_score_poses.argtypes = [vp, vp, vp, sp, c_dp, i64, dbl, c_dp, c_lp, c_dp]
     L.slamgpu_score_grid.argtypes = [vp, vp, vp, sp, c_dp, i32, c_dp, i32, c_dp, i32, dbl, c_dp, c_lp, c_dp]
+    L.slamgpu_score_poses_chained.argtypes = [vp, vp, vp, sp, c_dp, i64, C.POINTER(GmCache), c_dp, C.POINTER(GmCache)]
     L.slamgpu_stage_poses.argtypes = [vp, vp, sp, c_dp, i64]
     L.slamgpu_stage_grid.argtypes = [vp, vp, sp, c_dp, i32, c_dp, i32, c_dp, i32]
     L.slamgpu_score_launch.argtypes = [vp, vp, dbl]
@@ -271,6 +277,17 @@ class Context:
         self.check(self.L.slamgpu_score_grid(self.h, gmap.h, scan.h, C.byref(params), _dp(xs), len(xs), _dp(ys), len(ys),
                                              _dp(ts), len(ts), init_score, _dp(out), C.byref(idx), C.byref(best)))
         return out, idx.value, best.value
+
+    def score_poses_chained(self, gmap, scan, params, poses, state=None):
+        """GMapping OOPE with its cache carried from pose to pose; returns (scores, states after each pose)"""
+        poses = _f64(poses).reshape(-1, 3)
+        P = len(poses)
+        out = np.full(P, np.nan)
+        st_in = state if state is not None else GmCache(0, 0, -1.0)
+        states = (GmCache * max(P, 1))()
+        self.check(self.L.slamgpu_score_poses_chained(self.h, gmap.h, scan.h, C.byref(params), _dp(poses), P, C.byref(st_in), _dp(out),
+                                                      states))
+        return out, [GmCache(s.cx, s.cy, s.prob) for s in states[:P]]
 
     def stage_poses(self, scan, params, poses):
         poses = _f64(poses).reshape(-1, 3)

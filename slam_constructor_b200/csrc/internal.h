@@ -54,6 +54,9 @@ struct Candidates {  // a staged candidate set (device resident)
   // K6: every pose scored against its own particle's map
   bool multi = false;
   DevBuf views, view_id;
+  // GMapping OOPE cache chain (spe.gm_cache == 2): predecessor of each pose, entry states, state after each pose
+  bool gm_chain = false;
+  DevBuf gm_pred, gm_in, gm_out;
   // trig tables (device), layout given by strides
   DevBuf trc, trs;
   bool trig_is_host = false;
@@ -157,4 +160,10 @@ struct SgXfer { int peer; void *ptr; size_t bytes; };
 int sg_nccl_exchange(void *comm, const SgXfer *sends, int n_sends, const SgXfer *recvs, int n_recvs, cudaStream_t s, std::string *err);
 void sg_nccl_destroy(void *comm);
 // all-gather of host data: `host` holds nranks chunks of chunk_bytes, this rank's chunk filled in; on return all are
+// poses scored as the sequences the reference would evaluate them in, carrying GmappingOccupancyObservationPE's
+// one-entry cache from pose to pose: pred[k] >= 0 is the pose evaluated just before pose k, pred[k] < 0 means pose k
+// starts from states_in[-1 - pred[k]]; pred == NULL: one sequence, pose k after pose k-1, pose 0 from states_in[0]
+int sg_score_chained(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
+                     const slamgpu_spe_params *p, const double *poses, int64_t P, const int32_t *pred,
+                     const slamgpu_gm_cache *states_in, int n_states, double *out_scores, slamgpu_gm_cache *out_states);
 int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);

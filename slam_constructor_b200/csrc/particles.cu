@@ -32,6 +32,8 @@ struct slamgpu_particles {
   std::vector<slamgpu_map *> maps;
   int lo = 0, hi = 0, chunk = 0;
   int owner(int i) const { return i / chunk; }
+  // per particle: the GMapping OOPE cache its own estimator object would hold (spe.gm_cache == 2)
+  std::vector<slamgpu_gm_cache> gm_state;
 };
 
 extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, int32_t h, double scale, int32_t model,
@@ -44,6 +46,7 @@ extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, 
   p->lo = std::min(n, p->chunk * ctx->rank);
   p->hi = std::min(n, p->lo + p->chunk);
   p->maps.assign(n, nullptr);
+  p->gm_state.assign(n, slamgpu_gm_cache{0, 0, -1.0});
   for (int i = p->lo; i < p->hi; ++i) {
     int r = slamgpu_map_create(ctx, w, h, scale, model, grow, unknown_rec, &p->maps[i]);
     if (r != SLAMGPU_OK) { slamgpu_particles_destroy(p); return r; }
@@ -165,9 +168,24 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
     poses.insert(poses.end(), init_poses + 3 * i, init_poses + 3 * i + 3);
     vid.push_back(i - lo);
   }
-  scores.resize(vid.size());
-  if (!vid.empty())
-    SG_TRY(sg_score_poses_multi(ctx, lmaps, nl, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
+  // one batch = consecutive runs of poses per particle.  With the carried GMapping cache every run continues the
+  // sequence of its particle's own estimator: first pose from the particle's state, the others from the pose before
+  const bool chained = spe->oope == SLAMGPU_OOPE_GMAPPING && spe->gm_cache == 2;
+  std::vector<int32_t> pred;
+  std::vector<slamgpu_gm_cache> states;
+  auto score_batch = [&]() -> int {
+    scores.resize(vid.size());
+    if (vid.empty()) return SLAMGPU_OK;
+    if (!chained) return sg_score_poses_multi(ctx, lmaps, nl, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data());
+    pred.resize(vid.size()); states.resize(vid.size());
+    for (size_t k = 0; k < vid.size(); ++k) pred[k] = k > 0 && vid[k - 1] == vid[k] ? (int32_t)k - 1 : -1 - vid[k];
+    SG_TRY(sg_score_chained(ctx, lmaps, nl, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), pred.data(),
+                            p->gm_state.data() + lo, nl, scores.data(), states.data()));
+    for (size_t k = 0; k < vid.size(); ++k)
+      if (k + 1 == vid.size() || vid[k + 1] != vid[k]) p->gm_state[lo + vid[k]] = states[k];
+    return SLAMGPU_OK;
+  };
+  SG_TRY(score_batch());
   size_t q = 0;
   for (int i = 0; i < n; ++i) {
     HillClimb &h = hc[i];
@@ -194,8 +212,7 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
       }
     }
     if (who.empty()) break;
-    scores.resize(vid.size());
-    SG_TRY(sg_score_poses_multi(ctx, lmaps, nl, vid.data(), scan, spe, poses.data(), (int64_t)vid.size(), scores.data()));
+    SG_TRY(score_batch());
     size_t off = 0;
     for (size_t e = 0; e < who.size(); ++e) {
       double c6[6][3];
@@ -369,5 +386,18 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   release_staged();
   p->maps.swap(next);
+  // GMapping OOPE cache: the first particle (in index order) drawn from a source keeps the source's estimator object
+  // and with it the cache (particle_filter.h:92-101); every further copy starts with a new estimator, cache empty
+  std::vector<slamgpu_gm_cache> all = p->gm_state;
+  if (ctx->nranks > 1) {
+    all.resize((size_t)p->chunk * ctx->nranks, slamgpu_gm_cache{0, 0, -1.0});
+    SG_TRY(sg_allgather_host(ctx, all.data(), sizeof(slamgpu_gm_cache) * p->chunk));
+  }
+  std::vector<slamgpu_gm_cache> st(n, slamgpu_gm_cache{0, 0, -1.0});
+  std::vector<char> drawn(n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (!drawn[src[i]]) { st[i] = all[src[i]]; drawn[src[i]] = 1; }
+  }
+  p->gm_state.swap(st);
   return SLAMGPU_OK;
 }

@@ -317,6 +317,74 @@ __global__ void __launch_bounds__(128) k_pose_sums(PointArgs pa) {
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
 }
 
+// ---- GmappingOccupancyObservationPE's cache carried from pose to pose (gm_cache == 2).  The cache holds the cell
+// of the point evaluated last and the probability computed at the last MISS, so a point reuses the value computed
+// at the start of the run of consecutive same-cell points it belongs to -- a run that may begin in the pose
+// evaluated before (or, when a whole pose lies in one cell, further back).  Every pose finds its entry state by
+// walking its predecessors' cell ids backwards; no pose waits for another.
+struct ChainArgs {
+  const int *pred;                   // per pose: previous pose of its sequence, or -1 - (entry state index)
+  const slamgpu_gm_cache *states_in;
+  slamgpu_gm_cache *states_out;      // per pose: the cache after it
+};
+
+template <bool FACTOR>
+__global__ void __launch_bounds__(128) k_pose_sums_chained(PointArgs pa, ChainArgs ch) {
+  const ListArgs &a = pa.l;
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  if (p < a.Ploc) {
+    const int N = a.N;
+    // ---- entry state: the nearest predecessor whose final run starts inside it fixes the cache; the poses walked
+    // over on the way (each a single run from its first to its last point) are then re-applied forwards
+    int cache_x = 0, cache_y = 0;
+    double cache_p = -1;
+    int depth = 0;
+    long long q = ch.pred[p];
+    bool found = false;
+    while (q >= 0) {
+      if (N > 0) {
+        const int2 *c = pa.cellids + (size_t)q * N;
+        int j = N - 1;
+        while (j > 0 && c[j - 1].x == c[j].x && c[j - 1].y == c[j].y) --j;
+        if (j > 0) { cache_x = c[j].x; cache_y = c[j].y; cache_p = pa.terms[(size_t)q * N + j]; found = true; break; }
+        ++depth;
+      }
+      q = ch.pred[q];
+    }
+    if (!found && q < 0) {
+      const slamgpu_gm_cache st = ch.states_in[-1 - q];
+      cache_x = st.cx; cache_y = st.cy; cache_p = st.prob;
+    }
+    for (int d = depth; d > 0 && N > 0; --d) {  // single-run poses between the state found and pose p, oldest first
+      long long r = ch.pred[p];
+      for (int k = 1; k < d; ++k) r = ch.pred[r];
+      const int2 c0 = pa.cellids[(size_t)r * N];
+      if (!(c0.x == cache_x && c0.y == cache_y && cache_p != -1)) { cache_x = c0.x; cache_y = c0.y; cache_p = pa.terms[(size_t)r * N]; }
+    }
+    // ---- this pose, in point order
+    const double *t = pa.terms + (size_t)p * N;
+    const int2 *c = pa.cellids + (size_t)p * N;
+    double total = 0;
+    for (int i = 0; i < N; ++i) {
+      double prob = t[i];
+      if (c[i].x == cache_x && c[i].y == cache_y && cache_p != -1) prob = cache_p;
+      else { cache_x = c[i].x; cache_y = c[i].y; cache_p = prob; }
+      double term = sg::mul(prob, __ldg(a.w + i));
+      if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+      total = sg::add(total, term);
+    }
+    double score = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
+    a.scores[p] = score;
+    slamgpu_gm_cache out;
+    out.cx = cache_x; out.cy = cache_y; out.prob = cache_p;
+    ch.states_out[p] = out;
+    if (score == score) { best_s = score; best_i = a.p0 + p; }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
 // ---- the one-shot form of the small-batch path: two launches between ONE H2D and ONE D2H.  Inputs travel in
 // one staging buffer {header | poses | views | view ids}, outputs come back as {header | scores}.
 struct SmallHdr {
@@ -1200,12 +1268,12 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       a.trc = c.trc.as<double>(); a.trs = c.trs.as<double>(); a.T = c.T;
       a.sx = s->d_x; a.sy = s->d_y; a.w = s->d_w; a.f = s->d_f; a.N = N;
       a.Ploc = Ploc; a.p0 = c.p0; a.wsum = s->wsum; a.win_v = c.spe.win_v; a.win_h = c.spe.win_h;
-      a.gm_th = c.spe.gm_fullness_th; a.gm_win = c.spe.gm_window; a.gm_cache = c.spe.reserved;
+      a.gm_th = c.spe.gm_fullness_th; a.gm_win = c.spe.gm_window; a.gm_cache = c.spe.gm_cache;
       a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>(); a.result = res;
       const bool pre = c.spe.prerotated != 0, fac = s->has_factor;
       if (small) {
         c.stats[1] = 3;
-        const bool gmc = c.spe.oope == SLAMGPU_OOPE_GMAPPING && c.spe.reserved != 0;
+        const bool gmc = c.spe.oope == SLAMGPU_OOPE_GMAPPING && c.spe.gm_cache != 0;
         size_t tb = (size_t)Ploc * N * sizeof(double), cb = gmc ? (size_t)Ploc * N * sizeof(int2) : 0;
         if (ctx->scratch[7].reserve(tb + cb + 64) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "term buffer");
         PointArgs pa;
@@ -1223,7 +1291,13 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
         }
         cudaEventRecord(ctx->evk1, ctx->stream);
         ctx->evk_valid = true;
-        if (gmc) {
+        if (gmc && c.spe.gm_cache == 2) {
+          if (!c.gm_chain) return sg_fail(ctx, SLAMGPU_E_INVALID, "gm_cache == 2 needs the chained entry points (slamgpu_score_poses_chained)");
+          ChainArgs ch;
+          ch.pred = c.gm_pred.as<int>(); ch.states_in = c.gm_in.as<slamgpu_gm_cache>(); ch.states_out = c.gm_out.as<slamgpu_gm_cache>();
+          if (fac) k_pose_sums_chained<true><<<nblk, 128, 0, ctx->stream>>>(pa, ch);
+          else k_pose_sums_chained<false><<<nblk, 128, 0, ctx->stream>>>(pa, ch);
+        } else if (gmc) {
           if (fac) k_pose_sums<true, true><<<nblk, 128, 0, ctx->stream>>>(pa);
           else k_pose_sums<true, false><<<nblk, 128, 0, ctx->stream>>>(pa);
         } else {
@@ -1231,6 +1305,8 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
         }
         ctx->launches += 2;
       } else {
+        if (c.spe.oope == SLAMGPU_OOPE_GMAPPING && c.spe.gm_cache == 2)
+          return sg_fail(ctx, SLAMGPU_E_INVALID, "chained GMapping scoring takes at most %d poses and %lld pose-points a call", SG_SMALL_MAX_POSES, (long long)SG_SMALL_MAX_TERMS);
         cudaEventRecord(ctx->evk0, ctx->stream);
         switch (c.spe.oope) {
           case SLAMGPU_OOPE_OBSTACLE: launch_list_m<SLAMGPU_OOPE_OBSTACLE>(ctx, a, nblk, pre, device_trig, fac); break;
@@ -1434,7 +1510,7 @@ static int score_small_oneshot(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n
   if (ctx->nranks != 1 || P <= 0 || P > SG_FUSED_MAX_POSES || N <= 0 || P * (int64_t)N > SG_SMALL_MAX_TERMS) return SLAMGPU_OK;
   if (p->trig_mode != SLAMGPU_TRIG_DEVICE && !p->prerotated) return SLAMGPU_OK;
   if (p->oope == SLAMGPU_OOPE_OVERLAP && !p->prerotated) return SLAMGPU_OK;  // always libm trig: staged path
-  if (p->oope == SLAMGPU_OOPE_GMAPPING && p->reserved) return SLAMGPU_OK;    // cache emulation: staged path
+  if (p->oope == SLAMGPU_OOPE_GMAPPING && p->gm_cache) return SLAMGPU_OK;    // cache emulation: staged path
   SG_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<MapView> views((size_t)n_maps);
   for (int k = 0; k < n_maps; ++k) {
@@ -1545,16 +1621,7 @@ extern "C" int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_sc
 }
 
 // K6: one launch scores every particle's candidates against that particle's own map
-int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
-                         const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores) {
-  if (!ctx || !maps || n_maps <= 0 || (P > 0 && !view_id)) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_multi: bad argument");
-  SgLocalScope local_only(ctx);  // every pose of this call is scored here; ranks split the PARTICLES (particles.cu)
-  if (scan && p && poses && check_spe(ctx, scan, p) == SLAMGPU_OK) {
-    int served = 0;
-    SG_TRY(score_small_oneshot(ctx, maps, n_maps, view_id, scan, p, poses, P, -INFINITY, out_scores, nullptr, nullptr, &served));
-    if (served) return SLAMGPU_OK;
-  }
-  SG_TRY(slamgpu_stage_poses(ctx, scan, p, poses, P));
+static int stage_views(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, const slamgpu_spe_params *p, int64_t P) {
   Candidates &c = ctx->cand;
   std::vector<MapView> views(n_maps);
   for (int k = 0; k < n_maps; ++k) {
@@ -1566,10 +1633,67 @@ int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps,
     if (view_id[k] < 0 || view_id[k] >= n_maps) return sg_fail(ctx, SLAMGPU_E_INVALID, "pose %lld: bad particle id", (long long)k);
   SG_TRY(upload(ctx, c.views, views.data(), sizeof(MapView) * n_maps));
   SG_TRY(upload(ctx, c.view_id, view_id + c.p0, sizeof(int32_t) * (size_t)(c.p1 - c.p0)));
+  return SLAMGPU_OK;
+}
+
+int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
+                         const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores) {
+  if (!ctx || !maps || n_maps <= 0 || (P > 0 && !view_id)) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_multi: bad argument");
+  SgLocalScope local_only(ctx);  // every pose of this call is scored here; ranks split the PARTICLES (particles.cu)
+  if (scan && p && poses && check_spe(ctx, scan, p) == SLAMGPU_OK) {
+    int served = 0;
+    SG_TRY(score_small_oneshot(ctx, maps, n_maps, view_id, scan, p, poses, P, -INFINITY, out_scores, nullptr, nullptr, &served));
+    if (served) return SLAMGPU_OK;
+  }
+  SG_TRY(slamgpu_stage_poses(ctx, scan, p, poses, P));
+  Candidates &c = ctx->cand;
+  SG_TRY(stage_views(ctx, maps, n_maps, view_id, p, P));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   c.multi = true;
   int r = launch_staged(ctx, maps[0], -INFINITY);
   if (r == SLAMGPU_OK) r = fetch_impl(ctx, maps[0], out_scores, nullptr, nullptr);
   c.multi = false;
   return r;
+}
+
+int sg_score_chained(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
+                     const slamgpu_spe_params *p, const double *poses, int64_t P, const int32_t *pred,
+                     const slamgpu_gm_cache *states_in, int n_states, double *out_scores, slamgpu_gm_cache *out_states) {
+  if (!ctx || !maps || n_maps <= 0 || !p || !states_in || n_states <= 0 || P < 0) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_chained: bad argument");
+  if (p->oope != SLAMGPU_OOPE_GMAPPING) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_chained: only the GMapping OOPE keeps a cache");
+  if (P == 0) return SLAMGPU_OK;
+  SgLocalScope local_only(ctx);  // a sequence cannot be split over ranks
+  slamgpu_spe_params spe = *p;
+  spe.gm_cache = 2;
+  std::vector<int32_t> chain((size_t)P);
+  for (int64_t k = 0; k < P; ++k) {
+    chain[k] = pred ? pred[k] : (int32_t)k - 1;
+    if (chain[k] >= k || chain[k] < -n_states) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_chained: pose %lld has predecessor %d", (long long)k, chain[k]);
+  }
+  SG_TRY(slamgpu_stage_poses(ctx, scan, &spe, poses, P));
+  Candidates &c = ctx->cand;
+  const bool multi = view_id != nullptr;
+  if (multi) SG_TRY(stage_views(ctx, maps, n_maps, view_id, &spe, P));
+  SG_TRY(upload(ctx, c.gm_pred, chain.data(), sizeof(int32_t) * (size_t)P));
+  SG_TRY(upload(ctx, c.gm_in, states_in, sizeof(slamgpu_gm_cache) * (size_t)n_states));
+  if (c.gm_out.reserve(sizeof(slamgpu_gm_cache) * (size_t)P) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "cache states");
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  c.multi = multi; c.gm_chain = true;
+  int r = launch_staged(ctx, maps[0], -INFINITY);
+  if (r == SLAMGPU_OK) r = fetch_impl(ctx, maps[0], out_scores, nullptr, nullptr);
+  c.multi = false; c.gm_chain = false;
+  if (r == SLAMGPU_OK && out_states) {
+    SG_CUDA(ctx, cudaMemcpyAsync(out_states, c.gm_out.p, sizeof(slamgpu_gm_cache) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return r;
+}
+
+// One matcher's candidates, scored as the sequence the reference evaluates them in (GMapping OOPE only)
+extern "C" int slamgpu_score_poses_chained(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                                           const double *poses, int64_t P, const slamgpu_gm_cache *state_in, double *out_scores,
+                                           slamgpu_gm_cache *out_states) {
+  if (!ctx || !map || !state_in) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_poses_chained: NULL argument");
+  if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
+  return sg_score_chained(ctx, &map, 1, nullptr, scan, p, poses, P, nullptr, state_in, 1, out_scores, out_states);
 }

@@ -165,7 +165,23 @@ public:
     _unknown_cell = MirrorCell(_model, _unknown_rec);
     refresh_info();
   }
-  ~CudaGridMap() override { slamgpu_map_destroy(_map); }
+  // a view of a device map owned by somebody else (a particle's map, slamgpu_particles_map): same interface,
+  // never destroyed here; rebind() points the view at another map of the same model
+  CudaGridMap(std::shared_ptr<Context> ctx, std::shared_ptr<GridCell> prototype, const GridMapParams &params, int grow,
+              slamgpu_map *borrowed)
+    : GridMap{prototype, params}, _ctx{ctx}, _map{borrowed}, _owned{false}, _model{cell_model_of(*prototype)}, _grow{grow} {
+    _stride = slamgpu_model_stride(_model);
+    slamgpu_default_unknown(_model, _unknown_rec);
+    _unknown_cell = MirrorCell(_model, _unknown_rec);
+    refresh_info();
+  }
+  void rebind(slamgpu_map *m) {
+    if (_owned) { throw std::logic_error("CudaGridMap::rebind: this map owns its device map"); }
+    flush();
+    _map = m;
+    touched();
+  }
+  ~CudaGridMap() override { if (_owned) slamgpu_map_destroy(_map); }
   CudaGridMap(const CudaGridMap &) = delete;
   CudaGridMap &operator=(const CudaGridMap &) = delete;
 
@@ -239,7 +255,10 @@ protected:
   slamgpu_map *raw_device_map() const { return _map; }
 
 private:
+public:
+  // the device map changed behind this object's back (e.g. a batched particle insertion)
   void touched() { _mirror_valid = false; refresh_info(); }
+private:
   void refresh_info() const {
     int32_t st;
     double sc;
@@ -278,6 +297,7 @@ private:
   static constexpr std::size_t kRing = 4096;
   std::shared_ptr<Context> _ctx;
   slamgpu_map *_map = nullptr;
+  bool _owned = true;
   int _model, _grow, _stride = 0;
   double _unknown_rec[SLAMGPU_MAX_STRIDE];
   MirrorCell _unknown_cell;
@@ -352,6 +372,7 @@ struct ScoreSetup {
   int oope = SLAMGPU_OOPE_OBSTACLE, oie = SLAMGPU_OIE_DISCREPANCY;
   double gm_fullness_th = 0.1;
   int gm_window = 1;
+  int gm_cache = 0;  // 2: carry the GMapping OOPE's one-entry cache from candidate to candidate, as the estimator object does
   bool generic_oie = false;  // an OIE class this header does not know: score through a host-built LUT
 };
 
@@ -364,7 +385,7 @@ inline ScoreSetup detect_score_setup(const ScanProbabilityEstimator &spe) {
   else if (dynamic_cast<const MaxOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_MAX;
   else if (dynamic_cast<const MeanOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_MEAN;
   else if (dynamic_cast<const OverlapWeightedOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_OVERLAP;
-  else if (dynamic_cast<const GmappingOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_GMAPPING;
+  else if (dynamic_cast<const GmappingOccupancyObservationPE *>(oope.get())) { s.oope = SLAMGPU_OOPE_GMAPPING; s.gm_cache = 2; }
   else throw std::logic_error("slamgpu: unknown OccupancyObservationProbabilityEstimator class");
   auto oie = oope->impact_estimator();
   if (dynamic_cast<const DiscrepancyOIE *>(oie.get())) s.oie = SLAMGPU_OIE_DISCREPANCY;
@@ -437,6 +458,7 @@ inline slamgpu_spe_params make_spe_params(const ScoreSetup &s, int trig_mode) {
   p.oope = s.oope; p.oie = s.generic_oie ? 0 : s.oie;
   p.trig_mode = trig_mode;
   p.gm_fullness_th = s.gm_fullness_th; p.gm_window = s.gm_window;
+  p.gm_cache = s.oope == SLAMGPU_OOPE_GMAPPING ? s.gm_cache : 0;
   return p;
 }
 
@@ -471,10 +493,23 @@ protected:
     std::vector<double> flat(poses.size() * 3), out(poses.size());
     for (std::size_t i = 0; i < poses.size(); ++i) { flat[3 * i] = poses[i].x; flat[3 * i + 1] = poses[i].y; flat[3 * i + 2] = poses[i].theta; }
     int64_t idx; double best;
-    _ctx->check(slamgpu_score_poses(_ctx->handle(), p.map, p.dscan, &p.params, flat.data(), (int64_t)poses.size(),
-                                    -std::numeric_limits<double>::infinity(), out.data(), &idx, &best));
+    _gm_states.clear();
+    if (p.params.oope == SLAMGPU_OOPE_GMAPPING && p.params.gm_cache == 2) {
+      // one estimator object, one cache: the list is scored as the sequence it would be evaluated in, starting from
+      // the cache left by the last candidate really evaluated (see consumed())
+      _gm_states.resize(poses.size());
+      _ctx->check(slamgpu_score_poses_chained(_ctx->handle(), p.map, p.dscan, &p.params, flat.data(), (int64_t)poses.size(), &_gm_state,
+                                              out.data(), _gm_states.data()));
+    } else {
+      _ctx->check(slamgpu_score_poses(_ctx->handle(), p.map, p.dscan, &p.params, flat.data(), (int64_t)poses.size(),
+                                      -std::numeric_limits<double>::infinity(), out.data(), &idx, &best));
+    }
     _poses_tested += poses.size();
     return out;
+  }
+  // the reference evaluated the candidates of the last score() call up to and including index k
+  void consumed(std::size_t k) {
+    if (k < _gm_states.size()) { _gm_state = _gm_states[k]; }
   }
   bool has_observers() {
     bool any = false;
@@ -489,6 +524,8 @@ protected:
   MapBinding _map_binding;
   ScanBinding _scan_binding;
   std::size_t _poses_tested = 0;
+  slamgpu_gm_cache _gm_state{0, 0, -1.0};
+  std::vector<slamgpu_gm_cache> _gm_states;
 };
 
 //============================================================================//
@@ -518,6 +555,7 @@ public:
     const LaserScan2D &scan = prep.scan;
     auto best_pose = init_pose;
     double best_pose_prob = score(prep, {best_pose})[0];
+    consumed(0);
     do_for_each_observer([&](ObsPtr obs) {
       obs->on_scan_test(best_pose, scan, best_pose_prob);
       obs->on_pose_update(best_pose, scan, best_pose_prob);
@@ -553,6 +591,7 @@ public:
         auto pose_is_acceptable = best_pose_prob < sampled_scan_prob;
         _pe.feedback(pose_is_acceptable);
         history.push_back(Call{arg, pose_is_acceptable});
+        consumed(k);
         if (!pose_is_acceptable) { continue; }
         best_pose_prob = sampled_scan_prob;
         best_pose = sampled_pose;

@@ -6,6 +6,7 @@
 #pragma once
 
 #include "slamgpu_backend.h"
+#include "slamgpu_gmapping.h"
 #include "src/core/states/single_state_hypothesis_laser_scan_grid_world.h"
 #include "src/utils/init_occupancy_mapping.h"
 #include "src/utils/init_scan_matching.h"
@@ -95,7 +96,7 @@ inline std::shared_ptr<GridMap> init_cuda_grid_map(const PropertiesProvider &pro
 }
 
 // init_scan_adder (init_occupancy_mapping.h:82-93)
-inline std::shared_ptr<GridMapScanAdder> init_cuda_scan_adder(const PropertiesProvider &props) {
+inline CudaScanAdder::Properties init_cuda_scan_adder_properties(const PropertiesProvider &props) {
   static const auto COE_NS = std::string{"slam/occupancy_estimator/"};
   CudaScanAdder::Properties p;
   p.base_occupied = Occupancy{props.get_dbl(COE_NS + "base_occupied/prob", 0.95), props.get_dbl(COE_NS + "base_occupied/qual", 1.0)};
@@ -107,7 +108,10 @@ inline std::shared_ptr<GridMapScanAdder> init_cuda_scan_adder(const PropertiesPr
   p.observation_quality_estimator = init_omqe(props);
   p.blur_distance = props.get_dbl("slam/mapping/blur", 0.0);
   p.max_usable_range = props.get_dbl("slam/mapping/max_range", std::numeric_limits<double>::infinity());
-  return std::make_shared<CudaScanAdder>(p);
+  return p;
+}
+inline std::shared_ptr<GridMapScanAdder> init_cuda_scan_adder(const PropertiesProvider &props) {
+  return std::make_shared<CudaScanAdder>(init_cuda_scan_adder_properties(props));
 }
 
 // init_1h_slam (init_slam.h:12-24): the tinySLAM / vinySLAM world on the CUDA back end
@@ -130,7 +134,7 @@ inline std::shared_ptr<SingleStateHypothesisLaserScanGridWorld> init_cuda_1h_sla
 inline std::shared_ptr<GmappingParticleFilter> init_cuda_gmapping(const PropertiesProvider &props, std::shared_ptr<Context> ctx) {
   const std::string OOPE_Pfx = "slam/scmtch/oope/";
   ScoreSetup setup;
-  setup.oope = SLAMGPU_OOPE_GMAPPING;
+  setup.oope = SLAMGPU_OOPE_GMAPPING; setup.gm_cache = 2;
   setup.gm_fullness_th = props.get_dbl(OOPE_Pfx + "custom/fullness_threshold", 0.1);
   setup.gm_window = (int)props.get_uint(OOPE_Pfx + "cutrom/window_size", 1);  // key spelled as upstream
   auto oope = std::make_shared<GmappingOccupancyObservationPE>(setup.gm_fullness_th, setup.gm_window);
@@ -143,6 +147,26 @@ inline std::shared_ptr<GmappingParticleFilter> init_cuda_gmapping(const Properti
   auto map = std::make_shared<CudaGridMap>(ctx, std::make_shared<GmappingBaseCell>(), init_grid_map_params(props), SLAMGPU_GROW_TILED);
   auto shw_params = SingleStateHypothesisLSGWProperties{1.0, 1.0, 0, map, matcher, init_cuda_scan_adder(props)};
   return std::make_shared<GmappingParticleFilter>(shw_params, init_gmapping_params(props), init_particles_nm(props));
+}
+
+// The same properties on the batched filter: every particle owns its own device map, all particles hill-climb in
+// lock step and insert the scan in one batched pass (slamgpu_gmapping.h).
+inline std::shared_ptr<CudaGmappingParticleFilter> init_cuda_gmapping_batched(const PropertiesProvider &props, std::shared_ptr<Context> ctx) {
+  const std::string OOPE_Pfx = "slam/scmtch/oope/";
+  CudaGmappingParticleFilter::Properties p;
+  p.first_scan_keeps_weight = props.get_bool("slam/particles/first_scan_keeps_weight", true);  // key of this back end only
+  p.setup.oope = SLAMGPU_OOPE_GMAPPING; p.setup.gm_cache = 2;
+  p.setup.gm_fullness_th = props.get_dbl(OOPE_Pfx + "custom/fullness_threshold", 0.1);
+  p.setup.gm_window = (int)props.get_uint(OOPE_Pfx + "cutrom/window_size", 1);
+  auto oope = std::make_shared<GmappingOccupancyObservationPE>(p.setup.gm_fullness_th, p.setup.gm_window);
+  const std::string WMPP_Prefix = Slam_SM_NS + "spe/wmpp";
+  p.spw = init_swp(props);
+  p.spe = std::make_shared<WeightedMeanPointProbabilitySPE>(oope, p.spw, props.get_uint(WMPP_Prefix + "/sp_skip_rate", 0),
+                                                             props.get_dbl(WMPP_Prefix + "/sp_max_usable_range", -1));
+  p.map_params = init_grid_map_params(props);
+  p.adder = init_cuda_scan_adder_properties(props);
+  p.particles = init_particles_nm(props);
+  return std::make_shared<CudaGmappingParticleFilter>(ctx, p, init_gmapping_params(props));
 }
 
 }  // namespace slamgpu

@@ -4,7 +4,9 @@
 // tests/test_gpu_dropin.py.
 #include <chrono>
 #include <cstdio>
+#include <functional>
 #include <random>
+#include <unordered_set>
 
 #include "slamgpu_init.h"
 #include "src/utils/init_slam.h"
@@ -353,6 +355,236 @@ void run_gmapping(std::shared_ptr<slamgpu::Context> ctx) {
   CHECK(known > 2000, "gmapping: only %ld known cells in the heaviest particle's map", known);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The batched filter (slamgpu_gmapping.h): per-particle maps, lock-step hill climbing, batched insertion.
+MapPropertiesProvider gmapping_props(const char *particles, bool noiseless, const char *sigma_xy = "0.03", const char *sigma_th = "0.015") {
+  MapPropertiesProvider props;
+  for (auto kv : std::vector<std::pair<const char *, const char *>>{
+         {"slam/particles/number", particles}, {"slam/map/height_in_meters", "12"}, {"slam/map/width_in_meters", "12"},
+         {"slam/map/meters_per_cell", "0.05"}, {"slam/scmtch/spe/type", "wmpp"}, {"slam/scmtch/spe/wmpp/weighting/type", "even"},
+         {"slam/particles/sm_delta_lim/xy/min", "0.15"}, {"slam/particles/sm_delta_lim/xy/max", noiseless ? "0.15" : "0.25"},
+         {"slam/particles/sm_delta_lim/theta/min", "0.05"}, {"slam/particles/sm_delta_lim/theta/max", noiseless ? "0.05" : "0.08"},
+         {"slam/particles/sample/xy/sigma", noiseless ? "0" : sigma_xy}, {"slam/particles/sample/theta/sigma", noiseless ? "0" : sigma_th}})
+    props.set_property(kv.first, kv.second);
+  return props;
+}
+
+// a GmappingWorld-shaped particle built ONLY from reference components (matcher, adder, lazy tiled map), with its own
+// map and an injectable seed: the sequential statement of what the batched filter must compute
+// (gmapping_world.h:59-119; the real class seeds itself from std::random_device, :48)
+struct SeqParticle {
+  using Engine = std::mt19937;
+  SeqParticle(const PropertiesProvider &props, const GMappingParams &g, std::uint32_t seed)
+    : map{std::make_shared<UnboundedLazyTiledGridMap>(std::make_shared<GmappingBaseCell>(), init_grid_map_params(props))}
+    , matcher{std::make_shared<HillClimbingScanMatcher>(init_gmapping_prob_estimator(props), 6, 0.1, 0.1)}
+    , adder{init_scan_adder(props)}, engine(seed), guess_rv{g.pose_guess_rv}, next_rv{g.next_sm_delta_rv} {
+    const PropertiesProvider *pp = &props;
+    fresh_matcher = [pp] { return std::make_shared<HillClimbingScanMatcher>(init_gmapping_prob_estimator(*pp), 6, 0.1, 0.1); };
+    rearm();
+  }
+  // `*new_particle = *sampled`: the lazy tiled map forks copy-on-write.  The copy gets its own matcher (upstream's copies
+  // go on sharing the source's matcher object, and through it the OOPE's cell cache, with the particle they came from)
+  SeqParticle(const SeqParticle &o)
+    : map{std::make_shared<UnboundedLazyTiledGridMap>(*o.map)}, matcher{o.fresh_matcher()}, adder{o.adder}, pose{o.pose}, odom{o.odom}
+    , weight{o.weight}, master{o.master}, first{o.first}, engine{o.engine}, guess_rv{o.guess_rv}, next_rv{o.next_rv}
+    , since{o.since}, next{o.next} { fresh_matcher = o.fresh_matcher; }
+  std::function<std::shared_ptr<GridScanMatcher>()> fresh_matcher;
+  void rearm() { since.reset(); next = next_rv.sample(engine); }
+  void move(const RobotPoseDelta &d) {
+    double dth = (pose - odom).theta, sn = std::sin(dth), cs = std::cos(dth);
+    RobotPoseDelta corrected{cs * d.x - sn * d.y, sn * d.x + cs * d.y, d.theta};
+    odom += d; since += corrected.abs(); pose += corrected;
+  }
+  void observe(TransformedLaserScan &scan) {
+    if (since.sq_dist() < next.sq_dist() && std::fabs(since.theta) < next.theta) return;
+    if (!first) pose += guess_rv.sample(engine);
+    RobotPoseDelta delta;
+    double prob = matcher->process_scan(scan, pose, *map, delta);
+    pose += delta;
+    const bool was_first = first;
+    if (0.0 < prob || first) { adder->append_scan(*map, pose, scan.scan, scan.quality, 0); first = false; }
+    if (!was_first) weight = prob * weight;  // Properties::first_scan_keeps_weight (see slamgpu_gmapping.h)
+    rearm();
+  }
+  void make_master() {
+    using G = GaussianRV1D<Engine>;
+    master = true;
+    guess_rv = RobotPoseDeltaRV<Engine>{G{0, 0}, G{0, 0}, G{0, 0}};
+    next_rv = RobotPoseDeltaRV<Engine>{G{0, 0}, G{0, 0}, G{0, 0}};
+  }
+  std::shared_ptr<UnboundedLazyTiledGridMap> map;
+  std::shared_ptr<GridScanMatcher> matcher;
+  std::shared_ptr<GridMapScanAdder> adder;
+  RobotPose pose{0, 0, 0}, odom{0, 0, 0};
+  double weight = 1.0;
+  bool master = false, first = true;
+  Engine engine;
+  RobotPoseDeltaRV<Engine> guess_rv, next_rv;
+  RobotPoseDelta since, next;
+};
+
+// GmappingParticleFilter + ParticleFilter + UniformResamling over SeqParticles, draws from `seeds`
+struct SeqFilter {
+  SeqFilter(const PropertiesProvider &props, unsigned n, std::function<std::uint32_t()> seeds) : seeds{seeds} {
+    auto g = init_gmapping_params(props);
+    for (unsigned i = 0; i < n; ++i) { ps.push_back(std::make_shared<SeqParticle>(props, g, seeds())); ps.back()->weight = 1.0 / n; }
+    ps[heaviest()]->make_master();
+  }
+  std::size_t heaviest() const {
+    std::size_t b = 0;
+    for (std::size_t i = 1; i < ps.size(); ++i) if (!(ps[i]->weight < ps[b]->weight)) b = i;
+    return b;
+  }
+  void normalize() { double t = 0; for (auto &p : ps) t += p->weight; for (auto &p : ps) p->weight = p->weight / t; }
+  void step(TransformedLaserScan &scan) {
+    for (auto &p : ps) p->move(scan.pose_delta);
+    traversed += scan.pose_delta.abs();
+    for (auto &p : ps) p->observe(scan);
+    normalize();
+    if (traversed.sq_dist() <= 0.5 && std::fabs(traversed.theta <= 0.2)) return;
+    double sq = 0; for (auto &p : ps) sq += p->weight * p->weight;
+    if (!((1.0 / sq) * 2 < ps.size())) return;
+    std::vector<unsigned> inds(ps.size());
+    std::mt19937 engine(seeds());
+    std::uniform_real_distribution<> u(0, 1);
+    for (std::size_t i = 0; i < ps.size(); ++i) {
+      double sample = u(engine), tw = 0;
+      for (std::size_t j = 0; j < ps.size(); ++j) { tw += ps[j]->weight; if (sample < tw) { inds[i] = (unsigned)j; break; } }
+    }
+    std::vector<std::shared_ptr<SeqParticle>> nxt;
+    std::unordered_set<unsigned> seen;
+    for (unsigned i : inds) {
+      auto sp = ps[i];
+      if (seen.count(i)) { sp = std::make_shared<SeqParticle>(*sp); sp->master = false; } else { seen.insert(i); }
+      nxt.push_back(sp);
+    }
+    ps = std::move(nxt);
+    normalize();
+    ++resamplings;
+    traversed.reset();
+    bool has_master = false; for (auto &p : ps) has_master |= p->master;
+    if (!has_master) ps[heaviest()]->make_master();
+  }
+  std::function<std::uint32_t()> seeds;
+  std::vector<std::shared_ptr<SeqParticle>> ps;
+  RobotPoseDelta traversed;
+  std::size_t resamplings = 0;
+};
+
+bool same_as_device_map(const GridMap &ref, std::shared_ptr<slamgpu::Context> ctx, slamgpu_map *dev, const GridMapParams &gmp, const char *what) {
+  slamgpu::CudaGridMap view(ctx, std::make_shared<GmappingBaseCell>(), gmp, SLAMGPU_GROW_TILED, dev);
+  return same_cells(ref, view, what);
+}
+
+void run_gmapping_batched(std::shared_ptr<slamgpu::Context> ctx) {
+  // ---- A: against REAL GmappingWorld objects (fresh map each).  Their engines are seeded from std::random_device, so the
+  // random variables are made degenerate (sigma 0, min == max): every draw is then a constant, whatever the engine state.
+  {
+    std::printf("== batched GMapping filter vs GmappingWorld particles with their own maps (degenerate noise), 3 particles\n");
+    auto props = gmapping_props("3", true);
+    props.set_property("slam/particles/first_scan_keeps_weight", "false");  // upstream's literal weight product
+    auto gp = init_gmapping_params(props);
+    std::vector<std::shared_ptr<GmappingWorld>> ref;
+    for (int i = 0; i < 3; ++i) {
+      auto map = std::make_shared<UnboundedLazyTiledGridMap>(std::make_shared<GmappingBaseCell>(), init_grid_map_params(props));
+      auto shw = SingleStateHypothesisLSGWProperties{
+        1.0, 1.0, 0, map, std::make_shared<HillClimbingScanMatcher>(init_gmapping_prob_estimator(props), 6, 0.1, 0.1), init_scan_adder(props)};
+      ref.push_back(std::make_shared<GmappingWorld>(shw, gp));
+      ref.back()->set_weight(1.0 / 3);
+    }
+    ref[2]->mark_master();  // the heaviest of equal weights is the last one (particle_filter.h:114-121)
+    auto gpu = slamgpu::init_cuda_gmapping_batched(props, ctx);
+    CHECK(gpu->particle_is_master(2) && !gpu->particle_is_master(0), "batched filter: wrong initial master");
+    std::mt19937 rng(43);
+    RobotPose truth{0, 0, 0};
+    long matched_total = 0;
+    for (int step = 0; step < 9; ++step) {
+      RobotPoseDelta motion = step == 0 ? RobotPoseDelta{0, 0, 0} : RobotPoseDelta{0.06, 0.03, 0.02};
+      truth += motion;
+      auto scan = room_scan(truth, 360, 2 * M_PI, 3.0, 2.5, rng, 0.005);
+      TransformedLaserScan a{motion, scan, 1.0}, b{motion, scan, 1.0};
+      b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+      for (auto &w : ref) { w->update_robot_pose(motion); w->handle_observation(a); }
+      double tot = 0;
+      for (auto &w : ref) tot += w->weight();
+      for (auto &w : ref) w->set_weight(w->weight() / tot);
+      gpu->handle_sensor_data(b);
+      matched_total += (long)gpu->last_step().matched;
+      for (int i = 0; i < 3; ++i) {
+        const RobotPose &p1 = ref[i]->pose(), &p2 = gpu->particle_pose(i);
+        CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "step %d particle %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)",
+              step, i, p1.x, p1.y, p1.theta, p2.x, p2.y, p2.theta);
+        // (every particle's first match scores 0 on its empty map: upstream's weights end as 0/0, and so must ours)
+        const double w1 = ref[i]->weight(), w2 = gpu->particle_weight(i);
+        CHECK((std::isnan(w1) && std::isnan(w2)) || std::fabs(w1 - w2) <= 1e-5 * w1, "step %d particle %d: weight %.17g vs %.17g", step, i, w1, w2);
+      }
+      if (g_failed > 5) return;
+    }
+    // the master matches every scan, the others only past the (constant) gate: both paths were exercised
+    CHECK(matched_total > 9 && matched_total < 27, "gate: %ld particle-steps matched out of 27", matched_total);
+    for (int i = 0; i < 3; ++i) same_as_device_map(ref[i]->map(), ctx, gpu->particle_map(i), init_grid_map_params(props), "batched GMapping particle map");
+    std::printf("   9 scans, %ld particle-steps matched, heaviest pose %.6f %.6f %.6f\n", matched_total, gpu->pose().x, gpu->pose().y, gpu->pose().theta);
+  }
+  // ---- B: real noise, resampling, diverging particles: against the sequential statement above, same seeds
+  {
+    std::printf("== batched GMapping filter vs sequential reference components, seeded, 6 particles\n");
+    // pose noise far beyond what six halving rounds of hill climbing recover: some particles match badly, the weights
+    // spread and the filter resamples
+    auto props = gmapping_props("6", false, "1.5", "0.6");
+    std::uint32_t c1 = 1000, c2 = 1000;
+    SeqFilter ref(props, 6, [&c1] { return c1 += 7; });
+    const std::string OOPE_Pfx = "slam/scmtch/oope/";
+    slamgpu::CudaGmappingParticleFilter::Properties p;
+    p.setup.oope = SLAMGPU_OOPE_GMAPPING; p.setup.gm_cache = 2;
+    p.spw = init_swp(props);
+    p.spe = std::make_shared<WeightedMeanPointProbabilitySPE>(std::make_shared<GmappingOccupancyObservationPE>(0.1, 1), p.spw);
+    p.map_params = init_grid_map_params(props);
+    p.adder = slamgpu::init_cuda_scan_adder_properties(props);
+    p.particles = 6;
+    p.seed_source = [&c2] { return c2 += 7; };
+    slamgpu::CudaGmappingParticleFilter gpu(ctx, p, init_gmapping_params(props));
+    std::mt19937 rng(47);
+    RobotPose truth{0, 0, 0};
+    double t_ref = 0, t_gpu = 0;
+    for (int step = 0; step < 16; ++step) {
+      RobotPoseDelta motion = step == 0 ? RobotPoseDelta{0, 0, 0} : RobotPoseDelta{0.12, 0.05, 0.04};
+      truth += motion;
+      auto scan = room_scan(truth, 360, 2 * M_PI, 3.0, 2.5, rng, 0.005);
+      TransformedLaserScan a{motion, scan, 1.0}, b{motion, scan, 1.0};
+      b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+      auto t0 = std::chrono::steady_clock::now();
+      ref.step(a);
+      auto t1 = std::chrono::steady_clock::now();
+      gpu.handle_sensor_data(b);
+      auto t2 = std::chrono::steady_clock::now();
+      if (step > 0) { t_ref += std::chrono::duration<double, std::milli>(t1 - t0).count(); t_gpu += std::chrono::duration<double, std::milli>(t2 - t1).count(); }
+      CHECK(ref.resamplings == gpu.resamplings(), "step %d: %zu resamplings vs %zu", step, ref.resamplings, gpu.resamplings());
+      if (std::getenv("SLAMGPU_TEST_VERBOSE")) {
+        std::printf("   step %2d matched %zu weights", step, gpu.last_step().matched);
+        for (int i = 0; i < 6; ++i) std::printf(" %.4f", gpu.particle_weight(i));
+        std::printf("\n");
+      }
+      for (int i = 0; i < 6; ++i) {
+        const RobotPose &p1 = ref.ps[i]->pose, &p2 = gpu.particle_pose(i);
+        CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "step %d particle %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)",
+              step, i, p1.x, p1.y, p1.theta, p2.x, p2.y, p2.theta);
+        CHECK(std::fabs(ref.ps[i]->weight - gpu.particle_weight(i)) <= 1e-5 * ref.ps[i]->weight, "step %d particle %d: weight %.17g vs %.17g",
+              step, i, ref.ps[i]->weight, gpu.particle_weight(i));
+        CHECK(ref.ps[i]->master == gpu.particle_is_master(i), "step %d particle %d: master flag", step, i);
+      }
+      if (g_failed > 5) return;
+    }
+    CHECK(gpu.resamplings() > 0, "the sequence never resampled: the test does not cover it");
+    CHECK(ref.heaviest() == gpu.heaviest_particle(), "heaviest particle %zu vs %zu", ref.heaviest(), gpu.heaviest_particle());
+    for (int i = 0; i < 6; ++i) same_as_device_map(*ref.ps[i]->map, ctx, gpu.particle_map(i), p.map_params, "seeded GMapping particle map");
+    same_cells(*ref.ps[ref.heaviest()]->map, gpu.map(), "published map");
+    double err = std::hypot(gpu.pose().x - truth.x, gpu.pose().y - truth.y);
+    CHECK(err < 0.6, "batched filter lost track: err %.3f", err);
+    std::printf("   16 scans, %zu resamplings, err %.3f m; per scan: reference components %.2f ms, batched CUDA filter %.2f ms\n",
+                gpu.resamplings(), err, t_ref / 15, t_gpu / 15);
+  }
+}
+
 }  // namespace
 
 int main() {
@@ -380,6 +612,7 @@ int main() {
     run_m3rsm(ctx);
     run_presets(ctx);
     run_gmapping(ctx);
+    run_gmapping_batched(ctx);
   } catch (const std::exception &e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 1;

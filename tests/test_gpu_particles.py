@@ -132,3 +132,33 @@ def test_batched_insertion_grows_each_map_like_the_oracle(sg, gpu, grow):
     infos = {tuple(sorted(parts.map(i).info().items())) for i in range(n)}
     assert len(infos) > 1 or grow == "tiled"  # the maps really diverged (tiled growth may coincide)
     _check_maps(parts, omaps)
+
+
+def test_hill_climbing_with_the_estimators_lifetime_cache(sg, gpu):
+    """GmappingOccupancyObservationPE caches (cell -> probability) for its whole life: with gm_cache=2 every particle
+    carries its own estimator's cache through the rounds of one match and on into the next scan, like the oracle run
+    particle by particle with one cache object per particle"""
+    rng = np.random.default_rng(4200)
+    n = 8
+    parts, omaps, truth = _build(sg, gpu, rng, n, ob.CELL_GMAPPING)
+    gparams = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2)
+    oparams = ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1)
+    caches = [ob.GmCache(0, 0, -1.0) for _ in range(n)]
+    for k in range(3):  # the cache survives from scan to scan
+        r, a = room_scan(rng, 360, 2 * np.pi, half_w=3.0, half_h=2.5, pose=truth, noise=0.005)
+        gsc, osc = sg.Scan(gpu, r, a), ob.OracleScan(r, a)
+        init = truth + rng.normal(0, [0.04, 0.04, 0.02], (n, 3))
+        active = np.ones(n, np.uint8); active[k] = 0
+        poses, probs, tested = parts.match_hc(gsc, gparams, init, 6, 0.1, 0.1, active=active)
+        for i in range(n):
+            if not active[i]:
+                continue
+            m = ob.MatchResult()
+            ob.orc.orc_match_hill_climbing(omaps[i].h_, C.byref(osc.s), C.byref(oparams), *init[i], 6, 0.1, 0.1, C.byref(m),
+                                           C.byref(caches[i]))
+            assert tested[i] == m.poses_tested, (k, i)
+            assert np.array_equal(poses[i] - init[i], [m.dx, m.dy, m.dth]), (k, i)
+            assert abs(probs[i] - m.best_prob) <= 1e-12 * abs(m.best_prob)
+        gsc.close()
+        truth = truth + [0.02, 0.01, 0.01]
+    parts.close()

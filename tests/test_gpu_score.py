@@ -114,6 +114,53 @@ def test_list_gmapping_oope(sg, gpu):
                                 cache=ob.GmCache(0, 0, -1.0))[0] for p in poses[:60]])
     got_c, _, _ = gpu.score_poses(gm, gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=1), poses[:60])
     np.testing.assert_allclose(got_c, want_c, rtol=RTOL, atol=0)
+    # the cache as the estimator object really keeps it: alive across poses (and calls)
+    params_o = ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1)
+    params_g = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2)
+    cache = ob.GmCache(0, 0, -1.0)
+    # a scan that ends where it starts + tiny pose steps: a candidate's first point mostly falls into the cell of the
+    # previous candidate's last point and takes its (stale) probability
+    gsc.close()
+    r, a = np.append(r, r[0]), np.append(a, a[0])
+    osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+    seq = np.array([0.1, 0.1, 0.0]) + np.cumsum(rng.normal(0, [0.004, 0.004, 0.001], (120, 3)), axis=0)
+    want_1 = om.score(osc, params_o, seq[:70], cache=cache)
+    mid = ob.GmCache(cache.cx, cache.cy, cache.prob)
+    want_2 = om.score(osc, params_o, seq[70:], cache=cache)
+    fresh = np.array([om.score(osc, params_o, q[None], cache=ob.GmCache(0, 0, -1.0))[0] for q in seq])
+    assert (np.concatenate([want_1, want_2]) != fresh).sum() > 10  # the carried cache really changes scores
+    got_1, st_1 = gpu.score_poses_chained(gm, gsc, params_g, seq[:70])
+    np.testing.assert_allclose(got_1, want_1, rtol=1e-12, atol=0)
+    assert (st_1[-1].cx, st_1[-1].cy) == (mid.cx, mid.cy) and abs(st_1[-1].prob - mid.prob) <= 1e-12 * abs(mid.prob)
+    got_2, st_2 = gpu.score_poses_chained(gm, gsc, params_g, seq[70:], state=st_1[-1])
+    np.testing.assert_allclose(got_2, want_2, rtol=1e-12, atol=0)
+    assert (st_2[-1].cx, st_2[-1].cy) == (cache.cx, cache.cy)
+    # a consumer that stops early continues from the state after the pose it stopped at
+    got_3, _ = gpu.score_poses_chained(gm, gsc, params_g, seq[30:70], state=st_1[29])
+    np.testing.assert_allclose(got_3, want_1[30:], rtol=1e-12, atol=0)
+    with pytest.raises(sg.SlamGpuError):
+        gpu.score_poses(gm, gsc, params_g, seq[:5])  # the plain entry point has no cache to carry
+    gm.close(); gsc.close()
+
+
+def test_chained_cache_through_single_cell_poses(sg, gpu):
+    """degenerate chains: scans that fall into ONE cell keep the cache of an earlier pose alive across whole poses"""
+    rng = np.random.default_rng(1301)
+    cells = room_map_cells(rng, 120, 120, 0.05, ob.CELL_GMAPPING, passes=3)
+    om = ob.OracleMap(120, 120, 0.05, ob.CELL_GMAPPING); om.set_cells(cells)
+    gm = sg.GridMap(gpu, 120, 120, 0.05, sg.CELL_GMAPPING); gm.upload(cells)
+    # 5 beams inside half a degree at ~1 m: all end in the same cell for most poses
+    r = np.full(5, 1.0) + rng.normal(0, 1e-4, 5)
+    a = np.linspace(-0.004, 0.004, 5)
+    osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+    seq = np.array([0.2, 0.1, 0.3]) + np.cumsum(rng.normal(0, [0.003, 0.003, 0.0005], (200, 3)), axis=0)
+    po = ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.0, gm_window=1)
+    pg = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.0, gm_window=1, gm_cache=2)
+    cache = ob.GmCache(0, 0, -1.0)
+    want = om.score(osc, po, seq, cache=cache)
+    got, st = gpu.score_poses_chained(gm, gsc, pg, seq)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+    assert (st[-1].cx, st[-1].cy) == (cache.cx, cache.cy)
     gm.close(); gsc.close()
 
 
