@@ -336,7 +336,15 @@ struct ApplyArgs {
   double *trace_impact;
   double *trace_rec;  // per slot: the cell record right after this update (stride doubles)
   int trace_oie;
+  struct LongRun *long_runs;  // runs handed to k_apply_long
+  unsigned *n_long;
 };
+
+// One thread per cell run (the updates of one cell, in beam order).  Short runs are walked here; a run of
+// SG_LONG_RUN updates or more -- the robot's own cell takes one update from EVERY beam, the cells around it dozens --
+// is handed to k_apply_long, where a whole warp streams its operands.
+#define SG_LONG_RUN 24
+struct LongRun { long long head; int len; int pad; };
 
 __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -344,6 +352,17 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   const unsigned key = a.keys[j];
   if (key == SG_INVALID_KEY) return;
   if (j > 0 && a.keys[j - 1] == key) return;  // not the head of this cell's run
+  if (j + SG_LONG_RUN - 1 < a.M && a.keys[j + SG_LONG_RUN - 1] == key) {
+    // long run: find its end (the keys are sorted) and queue it
+    long long lo = j + SG_LONG_RUN - 1, hi = a.M;  // keys[lo] == key, keys[hi] > key (or hi == M)
+    while (hi - lo > 1) {
+      long long mid = (lo + hi) >> 1;
+      if (a.keys[mid] == key) lo = mid; else hi = mid;
+    }
+    unsigned slot = atomicAdd(a.n_long, 1u);
+    a.long_runs[slot] = LongRun{j, (int)(hi - j), 0};
+    return;
+  }
   double r[SLAMGPU_MAX_STRIDE];
   SortedAoo cur = a.aoo[j];
   const MapSlot &ms = a.maps[cur.map_id];
@@ -364,6 +383,45 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
     ++t;
   }
   for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+}
+
+// A warp per long run: the lanes fetch 32 consecutive operand records at once (coalesced, the next 32 already in
+// flight), then the updates are applied in order with the operands handed round by shuffles.  The chain of dependent
+// cell updates stays sequential (it is the reference's arithmetic), but it no longer waits on a memory round trip per
+// update.  Every lane carries the record, so no lane idles on a broadcast; lane l writes the trace of update l.
+__global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned n = *a.n_long;
+  for (unsigned e = warp; e < n; e += nwarps) {
+    const LongRun run = a.long_runs[e];
+    const unsigned key = a.keys[run.head];
+    const SortedAoo *src = a.aoo + run.head;
+    SortedAoo mine = src[min(lane, run.len - 1)];
+    const MapSlot &ms = a.maps[mine.map_id];
+    double *cell = ms.cells + (size_t)(key - ms.key_base) * a.stride;
+    double r[SLAMGPU_MAX_STRIDE];
+    for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
+    for (int base = 0; base < run.len; base += 32) {
+      const int cnt = min(32, run.len - base);
+      SortedAoo nxt = mine;
+      if (base + 32 < run.len) nxt = src[min(base + 32 + lane, run.len - 1)];
+      for (int l = 0; l < cnt; ++l) {
+        const double p = __shfl_sync(0xffffffffu, mine.p, l), q = __shfl_sync(0xffffffffu, mine.q, l);
+        const double wx = __shfl_sync(0xffffffffu, mine.wx, l), wy = __shfl_sync(0xffffffffu, mine.wy, l);
+        const double quality = __shfl_sync(0xffffffffu, mine.quality, l);
+        sg::cell_update(a.model, r, p, q, wx, wy, quality);
+        if (a.trace_impact && lane == l) {
+          a.trace_impact[mine.slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+          double *tr = a.trace_rec + (size_t)mine.slot * a.stride;
+          for (int k = 0; k < a.stride; ++k) tr[k] = r[k];
+        }
+      }
+      mine = nxt;
+    }
+    if (lane == 0)
+      for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+  }
 }
 
 // ---------------------------------------------------------------- map growth (device side)
@@ -780,8 +838,16 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     if (ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + maps[0]->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
     aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_rec = aa.trace_impact + M; aa.trace_oie = trace->oie;
   }
+  // long-run queue: at most M / SG_LONG_RUN entries, the counter in front
+  const size_t lr_bytes = 64 + ((size_t)(M / SG_LONG_RUN) + 1) * sizeof(LongRun);
+  if (ctx->scratch[6].reserve(lr_bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "long-run queue");
+  aa.n_long = ctx->scratch[6].as<unsigned>();
+  aa.long_runs = (LongRun *)((char *)ctx->scratch[6].p + 64);
+  SG_CUDA(ctx, cudaMemsetAsync(aa.n_long, 0, 64, ctx->stream));
   cudaEventRecord(ctx->evk0, ctx->stream);
   k_apply<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(aa);
+  k_apply_long<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(aa);
+  SG_LAUNCHED(ctx);
   cudaEventRecord(ctx->evk1, ctx->stream);
   ctx->evk_valid = true;
   SG_LAUNCHED(ctx);
