@@ -362,6 +362,15 @@ int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *scan, const s
                                const double *init_poses /* 3*n */, const uint8_t *active /* n or NULL */,
                                uint32_t max_failed_rounds, double translation_delta, double rotation_delta,
                                double *out_poses /* 3*n */, double *out_probs /* n */, int64_t *out_tested /* n or NULL */);
+/* The same for one matcher and one map -- HillClimbingScanMatcher::process_scan as a single call (and, for the
+ * obstacle / max / mean OOPEs with device trig, a single launch: the rounds run inside one thread block).  log, when
+ * log_cap > 0, receives {x, y, theta, probability} of every pose scored, in evaluation order (initial pose first), so
+ * that observers can be replayed; *log_count = entries produced (may exceed log_cap: the log was cut), or -1 when
+ * the call took the round-by-round path, which keeps no log. */
+int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *spe,
+                     const double init_pose[3], uint32_t max_failed_rounds, double translation_delta, double rotation_delta,
+                     double out_pose[3], double *out_prob, int64_t *out_tested, double *log /* 4*log_cap or NULL */,
+                     int32_t log_cap, int32_t *log_count /* or NULL */);
 /* GridMapScanAdder::append_scan into every particle's own map from its own pose (do_update NULL: all); the beams of
  * all particles go through one batched ray-cast, one sort keyed by (map, cell) and one ordered apply */
 int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses /* 3*n */,

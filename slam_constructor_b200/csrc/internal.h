@@ -166,4 +166,8 @@ void sg_nccl_destroy(void *comm);
 int sg_score_chained(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
                      const slamgpu_spe_params *p, const double *poses, int64_t P, const int32_t *pred,
                      const slamgpu_gm_cache *states_in, int n_states, double *out_scores, slamgpu_gm_cache *out_states);
+// a whole hill-climbing match per instance in one launch; out8 = 8 doubles per instance {x, y, theta, prob, tested, ...}
+int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                         const double *init, const uint8_t *active, uint32_t max_failed_rounds, double tr, double rot,
+                         double *out8, double *log, int log_cap, int *served);
 int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);

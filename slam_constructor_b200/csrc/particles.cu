@@ -21,6 +21,7 @@
 #include <thread>
 #include <vector>
 
+#include "hill_climb.h"
 #include "mapping.h"
 
 // On a distributed ctx the PARTICLES are sharded: rank r owns the contiguous range [lo, hi) of the n particles
@@ -88,65 +89,6 @@ extern "C" int slamgpu_particles_score(slamgpu_particles *p, slamgpu_scan *scan,
   return SLAMGPU_OK;
 }
 
-namespace {
-
-// FailedRoundsLimitedPoseEnumerator<Distorsion1DPoseEnumerator> + the accept loop of
-// PoseEnumerationScanMatcher, one instance per particle (hill_climbing_scan_matcher.h:10-126,
-// pose_enumeration_scan_matcher.h:48-65); frame rotation is always 0 upstream (quirk Q5)
-struct HillClimb {
-  double bx, by, bt, best;     // best pose so far and its probability
-  double rbx, rby, rbt;        // base of the current round
-  double tr, rot;
-  unsigned failed_rounds = 0, action = 0;
-  bool base_set = false, round_failed = true, done = false;
-  int64_t tested = 1;
-
-  // candidates the reference would test next, up to the end of the current round
-  int next_round(unsigned max_failed_rounds, double out[6][3]) {
-    int k = 0;
-    unsigned fr = failed_rounds, act = action;
-    bool bs = base_set, rf = round_failed;
-    double t_tr = tr, t_rot = rot, x0 = rbx, y0 = rby, t0 = rbt;
-    while (fr < max_failed_rounds && k < 6) {
-      if (!(act < 6)) {
-        if (k > 0) break;  // the next round depends on this round's accepts: stop here
-        if (rf) { t_tr *= 0.5; t_rot *= 0.5; ++fr; }
-        act = 0; bs = false; rf = true;
-      }
-      if (!bs) { x0 = bx; y0 = by; t0 = bt; bs = true; }
-      double x = x0, y = y0, t = t0;
-      const double dir = act % 2 ? -1 : 1;
-      switch (act % 3) {
-        case 0: x += 1.0 * dir * t_tr; y += 0.0 * dir * t_tr; break;
-        case 1: x += -0.0 * dir * t_tr; y += 1.0 * dir * t_tr; break;
-        case 2: t += dir * t_rot; break;
-      }
-      ++act;
-      out[k][0] = x; out[k][1] = y; out[k][2] = t;
-      ++k;
-    }
-    return k;
-  }
-  // replay the same steps with the scores known
-  void apply(unsigned max_failed_rounds, const double cand[6][3], const double *scores, int k) {
-    for (int j = 0; j < k; ++j) {
-      if (!(action < 6)) {
-        if (round_failed) { tr *= 0.5; rot *= 0.5; ++failed_rounds; }
-        action = 0; base_set = false; round_failed = true;
-      }
-      if (!base_set) { rbx = bx; rby = by; rbt = bt; base_set = true; }
-      ++action;
-      ++tested;
-      const bool ok = best < scores[j];
-      round_failed &= !ok;
-      if (ok) { best = scores[j]; bx = cand[j][0]; by = cand[j][1]; bt = cand[j][2]; }
-    }
-    done = !(failed_rounds < max_failed_rounds);
-    (void)max_failed_rounds;
-  }
-};
-
-}  // namespace
 
 extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
                                           const double *init_poses, const uint8_t *active, uint32_t max_failed_rounds,
@@ -162,6 +104,26 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
   std::vector<double> poses;
   std::vector<int32_t> vid;
   std::vector<double> scores;
+  // ---- fast path: every particle's whole match in one launch, one block per particle (score.cu: k_hill_climb)
+  int served = 0;
+  if (nl > 0) {
+    std::vector<double> out8((size_t)8 * nl);
+    SG_TRY(sg_hill_climb_device(ctx, lmaps, nl, scan, spe, init_poses + 3 * (size_t)lo, active ? active + lo : nullptr,
+                                max_failed_rounds, translation_delta, rotation_delta, out8.data(), nullptr, 0, &served));
+    if (served) {
+      for (int i = 0; i < n; ++i) {
+        HillClimb &h = hc[i];
+        h.bx = init_poses[3 * i]; h.by = init_poses[3 * i + 1]; h.bt = init_poses[3 * i + 2];
+        h.best = NAN; h.tested = 0; h.done = true;
+        if (!mine[i]) continue;
+        const double *o = out8.data() + 8 * (size_t)(i - lo);
+        h.bx = o[0]; h.by = o[1]; h.bt = o[2]; h.best = o[3]; h.tested = (int64_t)o[4];
+      }
+    }
+  }
+  // ---- general path (the carried GMapping cache, host trig, overlap OOPE, guard hits): all particles advance in lock
+  // step, one launch per hill-climbing round
+  if (!served) {
   // probability of the initial poses (pose_enumeration_scan_matcher.h:40)
   for (int i = 0; i < n; ++i) {
     if (!mine[i]) continue;
@@ -221,6 +183,7 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
       off += cnt[e];
     }
   }
+  }  // !served
   if (ctx->nranks > 1) {  // every rank learns every particle's result: 5 x f64 per particle
     std::vector<double> all((size_t)p->chunk * ctx->nranks * 5, 0.0);
     for (int i = lo; i < p->hi; ++i) {
@@ -239,6 +202,34 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
     if (out_tested) out_tested[i] = hc[i].tested;
   }
   return SLAMGPU_OK;
+}
+
+// HillClimbingScanMatcher::process_scan for ONE matcher and map: the whole match in one launch when the device kernel
+// covers the request, round by round otherwise.  log (optional) receives the candidates in evaluation order.
+extern "C" int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *spe,
+                                const double init_pose[3], uint32_t max_failed_rounds, double translation_delta,
+                                double rotation_delta, double out_pose[3], double *out_prob, int64_t *out_tested,
+                                double *log, int32_t log_cap, int32_t *log_count) {
+  if (!ctx || !map || !scan || !spe || !init_pose || !out_pose || !out_prob) return sg_fail(ctx, SLAMGPU_E_INVALID, "match_hc: NULL argument");
+  if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
+  if (log_count) *log_count = -1;  // -1: no log was produced (round-by-round path)
+  int served = 0;
+  double out8[8];
+  SG_TRY(sg_hill_climb_device(ctx, &map, 1, scan, spe, init_pose, nullptr, max_failed_rounds, translation_delta, rotation_delta,
+                              out8, log_cap > 0 ? log : nullptr, log_cap > 0 ? log_cap : 0, &served));
+  if (served) {
+    out_pose[0] = out8[0]; out_pose[1] = out8[1]; out_pose[2] = out8[2];
+    *out_prob = out8[3];
+    if (out_tested) *out_tested = (int64_t)out8[4];
+    if (log_count) *log_count = (int32_t)out8[6];
+    return SLAMGPU_OK;
+  }
+  slamgpu_particles one;
+  one.ctx = ctx; one.maps.assign(1, map); one.lo = 0; one.hi = 1; one.chunk = 1;
+  one.gm_state.assign(1, slamgpu_gm_cache{0, 0, -1.0});
+  SgLocalScope local_only(ctx);
+  return slamgpu_particles_match_hc(&one, scan, spe, init_pose, nullptr, max_failed_rounds, translation_delta, rotation_delta, out_pose,
+                                    out_prob, out_tested);
 }
 
 extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses,

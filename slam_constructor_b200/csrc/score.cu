@@ -23,6 +23,7 @@
 #include <unordered_map>
 
 #include "dev_window.cuh"
+#include "hill_climb.h"
 #include "internal.h"
 
 namespace {
@@ -315,6 +316,130 @@ __global__ void __launch_bounds__(128) k_pose_sums(PointArgs pa) {
     if (score == score) { best_s = score; best_i = a.p0 + p; }
   }
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+// ---- a whole hill-climbing match in ONE launch: one block per matcher instance (a world's matcher, or one GMapping
+// particle against its own map).  The block scores the candidates of a round (at most 6 poses x N points, terms in
+// shared memory, each pose's terms added in point order by one thread), thread 0 replays the reference's accept loop
+// and enumerator (hill_climb.h) and emits the next round, until the failed-rounds budget is spent.  No host round
+// trip per round: the ~15 rounds of a match cost ~15 block-level iterations instead of ~15 launch + copy cycles.
+struct HcArgs {
+  MapView map;
+  const MapView *views;  // per instance (NULL: every instance against `map`)
+  int n_inst;
+  const double *init;           // 3 per instance
+  const unsigned char *active;  // per instance or NULL
+  unsigned max_failed;
+  double tr, rot;
+  const double *range, *angle, *w, *f;
+  int N;
+  double wsum, win_v, win_h, gm_th;
+  int gm_win;
+  double *out;   // 8 per instance: best x, y, theta, probability, poses tested, guard hits, log entries, 0
+  double *log;   // per instance: log_cap x {x, y, theta, score}, in evaluation order
+  int log_cap;
+};
+
+template <int MODE, bool FACTOR>
+__global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
+  extern __shared__ double sh_terms[];  // [6][N]
+  __shared__ __align__(8) unsigned char hc_raw[sizeof(HillClimb)];  // (a __shared__ object cannot have initialisers)
+  HillClimb &hc = *reinterpret_cast<HillClimb *>(hc_raw);
+  __shared__ double cand[6][3], scores[6];
+  __shared__ int s_k, s_logged;
+  __shared__ unsigned int s_guard;
+  const int inst = blockIdx.x, tid = threadIdx.x, N = a.N;
+  double *out = a.out + 8 * (size_t)inst;
+  const double *init = a.init + 3 * (size_t)inst;
+  if (a.active && !a.active[inst]) {
+    if (tid == 0) { out[0] = init[0]; out[1] = init[1]; out[2] = init[2]; out[3] = NAN; out[4] = 0; out[5] = 0; out[6] = 0; out[7] = 0; }
+    return;
+  }
+  const MapView &mv = a.views ? a.views[inst] : a.map;
+  const double s = mv.scale, inv_s = 1.0 / mv.scale;
+  if (tid == 0) {
+    cand[0][0] = init[0]; cand[0][1] = init[1]; cand[0][2] = init[2];
+    s_k = 1; s_guard = 0; s_logged = 0;
+  }
+  __syncthreads();
+  bool first = true;
+  for (;;) {
+    const int k = s_k;
+    bool unsafe_any = false;
+    for (int e = tid; e < k * N; e += blockDim.x) {
+      const int j = e / N, i = e - j * N;
+      const double px = cand[j][0], py = cand[j][1];
+      double sn, cs;
+      sincos(sg::add(cand[j][2], __ldg(a.angle + i)), &sn, &cs);
+      const double r = __ldg(a.range + i);
+      const double rc = sg::mul(r, cs), rs = sg::mul(r, sn);
+      const double X = sg::add(px, rc), Y = sg::add(py, rs);
+      double prob;
+      if (MODE == SLAMGPU_OOPE_OBSTACLE || MODE == SLAMGPU_OOPE_GMAPPING) {
+        const int cx = grid_cell(X, rc, s, inv_s, 1, &unsafe_any);
+        const int cy = grid_cell(Y, rs, s, inv_s, 1, &unsafe_any);
+        prob = MODE == SLAMGPU_OOPE_OBSTACLE ? lut_at(mv, cx, cy) : gmapping_probability(mv, cx, cy, X, Y, a.gm_th, a.gm_win);
+      } else {
+        double hv = sg::div(a.win_v, 2.0), hh = sg::div(a.win_h, 2.0);
+        bool u;
+        sg::world_to_cell_guard(sg::sub(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::add(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::sub(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+        prob = window_probability<MODE>(mv, X, Y, a.win_v, a.win_h);
+      }
+      double term = sg::mul(prob, __ldg(a.w + i));
+      if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+      sh_terms[e] = term;
+    }
+    if (unsafe_any) atomicAdd(&s_guard, 1u);
+    __syncthreads();
+    if ((tid & 31) == 0 && (tid >> 5) < k) {  // one warp per pose: the sums run side by side
+      const int j = tid >> 5;
+      const double *t = sh_terms + (size_t)j * N;
+      double total = 0;
+      int i = 0;
+      for (; i + 8 <= N; i += 8) {  // loads first, then the chain of adds: the chain never waits on shared memory
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = t[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) total = sg::add(total, v[u]);
+      }
+      for (; i < N; ++i) total = sg::add(total, t[i]);
+      scores[j] = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int j = 0; j < k; ++j, ++s_logged)
+        if (a.log && s_logged < a.log_cap) {
+          double *l = a.log + ((size_t)inst * a.log_cap + s_logged) * 4;
+          l[0] = cand[j][0]; l[1] = cand[j][1]; l[2] = cand[j][2]; l[3] = scores[j];
+        }
+      if (first) {  // probability of the initial pose (pose_enumeration_scan_matcher.h:40), then reset()
+        hc = HillClimb();
+        hc.bx = init[0]; hc.by = init[1]; hc.bt = init[2];
+        hc.tr = a.tr; hc.rot = a.rot;
+        hc.best = scores[0];
+        hc.done = !(0 < a.max_failed);
+      } else {
+        hc.apply(a.max_failed, cand, scores, k);
+      }
+      int nk = 0;
+      if (!hc.done) {
+        nk = hc.next_round(a.max_failed, cand);
+        if (nk == 0) hc.done = true;
+      }
+      s_k = nk;
+    }
+    first = false;
+    __syncthreads();
+    if (s_k == 0) break;
+  }
+  if (tid == 0) {
+    out[0] = hc.bx; out[1] = hc.by; out[2] = hc.bt; out[3] = hc.best; out[4] = (double)hc.tested;
+    out[5] = (double)s_guard; out[6] = (double)s_logged; out[7] = 0;
+  }
 }
 
 // ---- GmappingOccupancyObservationPE's cache carried from pose to pose (gm_cache == 2).  The cache holds the cell
@@ -1696,4 +1821,82 @@ extern "C" int slamgpu_score_poses_chained(slamgpu_ctx *ctx, slamgpu_map *map, s
   if (!ctx || !map || !state_in) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_poses_chained: NULL argument");
   if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
   return sg_score_chained(ctx, &map, 1, nullptr, scan, p, poses, P, nullptr, state_in, 1, out_scores, out_states);
+}
+
+// The whole hill-climbing match of n instances on the device (k_hill_climb).  *served = 0 when the request is outside
+// what the kernel covers (the caller then runs the round-by-round path) or when a device-trig border guard fired.
+namespace {
+template <int MODE>
+void launch_hc(slamgpu_ctx *ctx, const HcArgs &a, size_t smem, bool fac) {
+  // one matcher: the widest block (latency); many particles: two resident blocks per SM, one wave for <= 2 x SMs
+  const int threads = a.n_inst > ctx->sm_count / 2 ? 512 : 1024;
+  if (fac) {
+    cudaFuncSetAttribute(k_hill_climb<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_hill_climb<MODE, true><<<a.n_inst, threads, smem, ctx->stream>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_hill_climb<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_hill_climb<MODE, false><<<a.n_inst, threads, smem, ctx->stream>>>(a);
+  }
+}
+}  // namespace
+
+int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                         const double *init, const uint8_t *active, uint32_t max_failed_rounds, double tr, double rot,
+                         double *out8, double *log, int log_cap, int *served) {
+  *served = 0;
+  if (!ctx || !maps || n <= 0 || !scan || !p || !init || !out8) return sg_fail(ctx, SLAMGPU_E_INVALID, "hill_climb: bad argument");
+  SG_TRY(check_spe(ctx, scan, p));
+  const int N = scan->n;
+  const size_t smem = (size_t)6 * std::max(N, 1) * sizeof(double);
+  if (p->prerotated || p->trig_mode != SLAMGPU_TRIG_DEVICE || p->oope == SLAMGPU_OOPE_OVERLAP || N <= 0 || smem > 200 * 1024 ||
+      (p->oope == SLAMGPU_OOPE_GMAPPING && p->gm_cache != 0))
+    return SLAMGPU_OK;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<MapView> views(n);
+  for (int k = 0; k < n; ++k) {
+    if (!maps[k] || maps[k]->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "hill_climb: map %d is NULL or belongs to another ctx", k);
+    if (active && !active[k]) { views[k] = make_view(maps[k], p->oie); continue; }
+    if (p->oope != SLAMGPU_OOPE_GMAPPING) SG_TRY(sg_map_ensure_lut(maps[k], p->oie));
+    views[k] = make_view(maps[k], p->oie);
+  }
+  Candidates &c = ctx->cand;
+  // staging: {views | init | active} in one upload, {out | log} in one download
+  const size_t vb = sizeof(MapView) * n, ib = sizeof(double) * 3 * n, ab = ((size_t)n + 7) & ~(size_t)7;
+  std::vector<char> stage(vb + ib + ab, 0);
+  memcpy(stage.data(), views.data(), vb);
+  memcpy(stage.data() + vb, init, ib);
+  if (active) memcpy(stage.data() + vb + ib, active, n);
+  SG_TRY(upload(ctx, c.views, stage.data(), stage.size()));
+  const size_t ob = sizeof(double) * 8 * n, lb = log ? sizeof(double) * 4 * (size_t)log_cap * n : 0;
+  if (c.scores.reserve(ob + lb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "hill_climb output");
+  HcArgs a;
+  a.map = views[0]; a.views = c.views.as<MapView>(); a.n_inst = n;
+  a.init = (const double *)((const char *)c.views.p + vb);
+  a.active = active ? (const unsigned char *)c.views.p + vb + ib : nullptr;
+  a.max_failed = max_failed_rounds; a.tr = tr; a.rot = rot;
+  a.range = scan->d_range; a.angle = scan->d_angle; a.w = scan->d_w; a.f = scan->d_f; a.N = N; a.wsum = scan->wsum;
+  a.win_v = p->win_v; a.win_h = p->win_h; a.gm_th = p->gm_fullness_th; a.gm_win = p->gm_window;
+  a.out = c.scores.as<double>(); a.log = log ? a.out + 8 * (size_t)n : nullptr; a.log_cap = log_cap;
+  cudaEventRecord(ctx->evk0, ctx->stream);
+  switch (p->oope) {
+    case SLAMGPU_OOPE_OBSTACLE: launch_hc<SLAMGPU_OOPE_OBSTACLE>(ctx, a, smem, scan->has_factor); break;
+    case SLAMGPU_OOPE_MAX: launch_hc<SLAMGPU_OOPE_MAX>(ctx, a, smem, scan->has_factor); break;
+    case SLAMGPU_OOPE_MEAN: launch_hc<SLAMGPU_OOPE_MEAN>(ctx, a, smem, scan->has_factor); break;
+    default: launch_hc<SLAMGPU_OOPE_GMAPPING>(ctx, a, smem, scan->has_factor); break;
+  }
+  cudaEventRecord(ctx->evk1, ctx->stream);
+  ctx->evk_valid = true;
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  std::vector<double> host((ob + lb) / sizeof(double));
+  SG_CUDA(ctx, cudaMemcpyAsync(host.data(), c.scores.p, ob + lb, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < n; ++k)
+    if (host[8 * (size_t)k + 5] != 0) return SLAMGPU_OK;  // a point within the device-trig slack of a cell border: host-trig path
+  memcpy(out8, host.data(), ob);
+  if (log) memcpy(log, host.data() + 8 * (size_t)n, lb);
+  c.stats[0] = 0; c.stats[1] = 5; c.stats[2] = 0;
+  for (int k = 0; k < n; ++k) c.stats[2] += (int64_t)host[8 * (size_t)k + 4] * N;
+  *served = 1;
+  return SLAMGPU_OK;
 }

@@ -621,14 +621,59 @@ public:
                                                             failed_attempts_per_dispersion, total_attempts}} {}
 };
 
-// HillClimbingScanMatcher (hill_climbing_scan_matcher.h:128-170) on the device
+// HillClimbingScanMatcher (hill_climbing_scan_matcher.h:128-170) on the device.  The enumerator is deterministic, so
+// the whole match -- every round, the accept loop included -- runs in one call (slamgpu_match_hc: one launch for the
+// obstacle / max / mean OOPEs); observers are replayed afterwards from the log of scored poses, in the reference's
+// order.  The GMapping OOPE with its carried cache keeps the speculative batches of the base class.
 class CudaHillClimbingScanMatcher : public CudaPoseEnumerationScanMatcher<HillClimbingPoseEnumerator> {
+  using Base = CudaPoseEnumerationScanMatcher<HillClimbingPoseEnumerator>;
 public:
   CudaHillClimbingScanMatcher(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
                               std::shared_ptr<ScanPointWeighting> spw, unsigned max_lookup_failed_attempts,
                               double translation_delta, double rotation_delta)
-    : CudaPoseEnumerationScanMatcher{ctx, spe, spw,
-                                     HillClimbingPoseEnumerator{max_lookup_failed_attempts, translation_delta, rotation_delta}} {}
+    : Base{ctx, spe, spw, HillClimbingPoseEnumerator{max_lookup_failed_attempts, translation_delta, rotation_delta}}
+    , _max_failed{max_lookup_failed_attempts}, _tr{translation_delta}, _rot{rotation_delta} {}
+
+  double process_scan(const TransformedLaserScan &raw_scan, const RobotPose &init_pose, const GridMap &map,
+                      RobotPoseDelta &pose_delta) override {
+    if (_setup.oope == SLAMGPU_OOPE_GMAPPING && _setup.gm_cache == 2) { return Base::process_scan(raw_scan, init_pose, map, pose_delta); }
+    auto prep = prepare(raw_scan, init_pose, map);
+    const bool observed = has_observers();
+    const int32_t cap = observed ? 8192 : 0;
+    _log.resize((std::size_t)4 * cap);
+    const double init[3] = {init_pose.x, init_pose.y, init_pose.theta};
+    double out[3], prob = 0;
+    int64_t tested = 0;
+    int32_t count = 0;
+    _ctx->check(slamgpu_match_hc(_ctx->handle(), prep.map, prep.dscan, &prep.params, init, _max_failed, _tr, _rot, out, &prob, &tested,
+                                 cap ? _log.data() : nullptr, cap, &count));
+    if (observed && (count < 0 || count > cap)) {
+      // no (complete) log to replay: the speculative path calls the observers itself
+      return Base::process_scan(raw_scan, init_pose, map, pose_delta);
+    }
+    _poses_tested = (std::size_t)tested;
+    const LaserScan2D &scan = prep.scan;
+    if (observed) {
+      do_for_each_observer([&](ObsPtr obs) { obs->on_matching_start(init_pose, raw_scan, map); });
+      double best = 0;
+      for (int32_t k = 0; k < count; ++k) {
+        const double *l = _log.data() + 4 * (std::size_t)k;
+        const RobotPose pose{l[0], l[1], l[2]};
+        const double p = l[3];
+        do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(pose, scan, p); });
+        if (k > 0 && !(best < p)) { continue; }
+        best = p;
+        do_for_each_observer([&](ObsPtr obs) { obs->on_pose_update(pose, scan, p); });
+      }
+    }
+    pose_delta = RobotPose{out[0], out[1], out[2]} - init_pose;
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(pose_delta, scan, prob); });
+    return prob;
+  }
+private:
+  unsigned _max_failed;
+  double _tr, _rot;
+  std::vector<double> _log;
 };
 
 //============================================================================//

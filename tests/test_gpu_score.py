@@ -300,3 +300,48 @@ def test_grid_kernel_variants(sg, gpu, max_variant, nx, ny, nt, ystep, expect_R,
     expect_variant = 1 if not fits_nibbles else (3 if (max_variant == 3 and fits_box) else 2)
     assert st["variant"] == expect_variant and st["rows_per_thread"] == expect_R, st
     gm.close(); gsc.close()
+
+
+@pytest.mark.parametrize("mode", ["obstacle", "max", "mean", "gmapping"])
+def test_whole_hill_climbing_match_in_one_launch(sg, gpu, mode):
+    """slamgpu_match_hc: every round of HillClimbingScanMatcher::process_scan inside one thread block; pose delta, number of
+    poses tested and probability against the oracle's sequential matcher, the log against the oracle's scores"""
+    rng = np.random.default_rng(1500)
+    model = ob.CELL_GMAPPING if mode == "gmapping" else ob.CELL_TBM_CONSISTENT
+    cells = room_map_cells(rng, 240, 240, 0.05, model, passes=4)
+    om = ob.OracleMap(240, 240, 0.05, model); om.set_cells(cells)
+    gm = sg.GridMap(gpu, 240, 240, 0.05, model); gm.upload(cells)
+    kw = dict(obstacle=(ob.OOPE_OBSTACLE, {}), max=(ob.OOPE_MAX, dict(win_v=0.1, win_h=0.1)), mean=(ob.OOPE_MEAN, dict(win_v=0.15, win_h=0.1)),
+              gmapping=(ob.OOPE_GMAPPING, dict(gm_th=0.1, gm_window=1)))[mode]
+    po, pg = ob.spe_params(kw[0], **kw[1]), sg.spe_params(kw[0], **kw[1])
+    for trial in range(4):
+        truth = np.array([0.1, -0.2, 0.2]) + rng.normal(0, 0.3, 3) * [1, 1, 0.3]
+        r, a = room_scan(rng, 541, 1.5 * np.pi, pose=truth, noise=0.005)
+        osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+        init = truth + rng.normal(0, [0.08, 0.08, 0.04])
+        limit = (6, 0.1, 0.1) if trial < 3 else (3, 0.07, 0.05)
+        m = ob.MatchResult()
+        ob.orc.orc_match_hill_climbing(om.h_, C.byref(osc.s), C.byref(po), *init, *limit, C.byref(m), None)
+        pose, prob, tested, log = gpu.match_hc(gm, gsc, pg, init, *limit, log_cap=2048)
+        st = gpu.score_stats()
+        assert st["variant"] == 5, "the match did not take the one-launch path"
+        assert tested == m.poses_tested and tested > 20
+        assert np.array_equal(pose - init, [m.dx, m.dy, m.dth])
+        if mode == "gmapping":
+            assert abs(prob - m.best_prob) <= RTOL * abs(m.best_prob)
+        else:
+            assert prob == m.best_prob
+        assert len(log) == tested and np.array_equal(log[0, :3], init)
+        want = om.score(osc, po, log[:, :3])
+        if mode == "gmapping":
+            np.testing.assert_allclose(log[:, 3], want, rtol=RTOL, atol=0)
+        else:
+            assert np.array_equal(log[:, 3], want)
+        # without a log, and with host trig (round-by-round path): same answer
+        pose2, prob2, tested2, _ = gpu.match_hc(gm, gsc, pg, init, *limit)
+        assert np.array_equal(pose2, pose) and prob2 == prob and tested2 == tested
+        ph = sg.spe_params(kw[0], trig=sg.TRIG_HOST, **kw[1])
+        pose3, prob3, tested3, log3 = gpu.match_hc(gm, gsc, ph, init, *limit, log_cap=16)
+        assert log3 is None and np.array_equal(pose3, pose) and tested3 == tested
+        gsc.close()
+    gm.close()

@@ -87,10 +87,15 @@ def measure(ctx):
         for _ in range(20):
             dev()
         dev_us = float(np.median([dev() for _ in range(200)])) * 1e3
+        hc_us = timeit(lambda: ctx.match_hc(gm, scan, params, pose + [0.06, -0.05, 0.03]), n=100, warm=10)
+        _, _, hc_tested, _ = ctx.match_hc(gm, scan, params, pose + [0.06, -0.05, 0.03])
+        hc_kernel_us = ctx.last_kernel_ms() * 1e3
         upd = timeit(lambda: ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3), n=50, warm=5)
         rec_bytes = {sg.CELL_MEAN: 2 * 16 + 8, sg.CELL_TBM_CONSISTENT: 2 * 48 + 8}[model]  # 2 x record + LUT entry
         out[name] = {"poses": P, "beams": beams, "score_call_e2e_us": round(e2e, 1), "score_device_us": round(dev_us, 1), "oneshot_terms_kernel_us": round(oneshot_kernel_us, 1),
-                     "evals_per_s_e2e": P * beams / (e2e * 1e-6), "append_scan_e2e_us": round(upd, 1), "cells_per_scan": int(cells),
+                     "evals_per_s_e2e": P * beams / (e2e * 1e-6),
+                     "hill_climb_match_e2e_us": round(hc_us, 1), "hill_climb_match_kernel_us": round(hc_kernel_us, 1), "hill_climb_poses_tested": int(hc_tested),
+                     "append_scan_e2e_us": round(upd, 1), "cells_per_scan": int(cells),
                      "cell_updates_per_s": cells / (upd * 1e-6),
                      "update_algorithmic_GBps": cells * rec_bytes / (upd * 1e-6) / 1e9}
         gm.close(); scan.close()
