@@ -381,6 +381,11 @@ int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, cons
  * a source drawn once is moved, the others are copied device to device (or rank to rank) */
 int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src /* n */);
 
+/* ------------------------------------------------------------------ test hook
+ * out[i] = a[i] / b[i] through the division the TBM cell update uses (with its exact shortcut for subnormal
+ * numerators): lets the parity tests hold it against the host's IEEE division. */
+int slamgpu_debug_div(slamgpu_ctx *ctx, int32_t n, const double *a, const double *b, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,7 +86,10 @@ static int ctx_create_common(int device, slamgpu_ctx **out) {
   ctx->sm_count = pr.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess) {
+      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     int r = sg_fail(nullptr, SLAMGPU_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return r;
@@ -133,6 +136,9 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evk0);
   cudaEventDestroy(ctx->evk1);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_join);
+  cudaStreamDestroy(ctx->side);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -191,6 +197,31 @@ int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv) {
   std::string err;
   int r = sg_nccl_allgather(ctx->comm, d_send16, d_recv, 16, ctx->stream, &err);
   if (r != SLAMGPU_OK) return sg_fail(ctx, r, "%s", err.c_str());
+  return SLAMGPU_OK;
+}
+
+// ------------------------------------------------------------------ test hook
+namespace {
+__global__ void k_debug_div(const double *a, const double *b, int n, double *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sg::div_chain(a[i], b[i]);
+}
+}  // namespace
+
+extern "C" int slamgpu_debug_div(slamgpu_ctx *ctx, int32_t n, const double *a, const double *b, double *out) {
+  if (!ctx || n < 0 || (n > 0 && (!a || !b || !out))) return sg_fail(ctx, SLAMGPU_E_INVALID, "debug_div: bad argument");
+  if (n == 0) return SLAMGPU_OK;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = sizeof(double) * (size_t)n;
+  if (ctx->scratch[0].reserve(bytes) != SLAMGPU_OK || ctx->scratch[1].reserve(bytes) != SLAMGPU_OK || ctx->scratch[2].reserve(bytes) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "debug_div buffers");
+  SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0].p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[1].p, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_debug_div<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch[0].as<double>(), ctx->scratch[1].as<double>(), n, ctx->scratch[2].as<double>());
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaMemcpyAsync(out, ctx->scratch[2].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
 }
 

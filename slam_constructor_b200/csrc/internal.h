@@ -73,6 +73,8 @@ struct Candidates {  // a staged candidate set (device resident)
 struct slamgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // the robot cell's update chain runs here, next to the sort (mapping.cu)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // around the dominant kernel of the last call
   bool evk_valid = false;

@@ -84,6 +84,7 @@ struct EstimateArgs {
   unsigned *vals;         // per slot: slot id
   int *slot_beam;         // per slot
   unsigned long long *counters;  // per map: [2*id+1] updates dropped outside a bounded map ([2*id]: see k_raycast)
+  int *robot_slot;        // per beam: the slot of its robot-cell update (taken out of the sort), or NULL
 };
 
 __global__ void k_estimate(EstimateArgs a) {
@@ -138,7 +139,12 @@ __global__ void k_estimate(EstimateArgs a) {
     a.keys[s] = SG_INVALID_KEY;
     atomicAdd(a.counters + 2 * b.map_id + 1, 1ull);
   } else {
-    a.keys[s] = ms.key_base + (unsigned)iy * (unsigned)ms.w + (unsigned)ix;
+    if (a.robot_slot && c.x == ms.rx && c.y == ms.ry) {
+      a.keys[s] = SG_INVALID_KEY;  // applied by k_apply_robot, in beam order
+      a.robot_slot[i] = (int)s;
+    } else {
+      a.keys[s] = ms.key_base + (unsigned)iy * (unsigned)ms.w + (unsigned)ix;
+    }
   }
 }
 
@@ -424,6 +430,54 @@ __global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
   }
 }
 
+// The robot's own cell is the first cell of EVERY ray, so its run is as long as the scan and its chain of dependent
+// updates is the critical path of an insertion (1081 TBM updates ~ 250 us).  It does not need the sort: its updates
+// are one per beam, in beam order.  One warp per map applies them straight from the per-slot estimates, on a side
+// stream, while the main stream sorts and applies every other cell.
+struct RobotArgs {
+  const MapSlot *maps;
+  int n_maps;
+  const BeamRec *beams;
+  const int *robot_slot;
+  const double *aoo_p, *aoo_q;
+  int stride, model;
+};
+
+__global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= a.n_maps) return;
+  const MapSlot ms = a.maps[m];
+  const int ix = ms.rx + ms.ox, iy = ms.ry + ms.oy;
+  if (ix < 0 || ix >= ms.w || iy < 0 || iy >= ms.h) return;
+  double *cell = ms.cells + ((size_t)iy * ms.w + ix) * a.stride;
+  double r[SLAMGPU_MAX_STRIDE];
+  for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
+  bool any = false;
+  for (int base = ms.beam_begin; base < ms.beam_end; base += 32) {
+    const int i = base + lane;
+    int rs = -1;
+    double p = 0, q = 0, quality = 0, wx = 0, wy = 0;
+    if (i < ms.beam_end) {
+      rs = a.robot_slot[i];
+      if (rs >= 0) {
+        const BeamRec &b = a.beams[i];
+        p = a.aoo_p[rs]; q = a.aoo_q[rs]; quality = b.quality; wx = b.wx; wy = b.wy;
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, rs >= 0);
+    any |= todo != 0;
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      sg::cell_update(a.model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
+                      __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l));
+    }
+  }
+  if (any && lane == 0)
+    for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+}
+
 // ---------------------------------------------------------------- map growth (device side)
 __global__ void k_copy_block(const double *__restrict__ src, int sw, int sh, double *__restrict__ dst, int dw, int offx,
                              int offy, int stride) {
@@ -659,6 +713,8 @@ int run_raycast_multi(slamgpu_ctx *ctx, double scale, const std::vector<BeamRec>
 MapSlot slot_of(const slamgpu_map *m, double px, double py, double shift, unsigned key_base) {
   MapSlot s;
   s.cells = m->d_cells; s.px = px; s.py = py; s.shift = shift; s.w = m->w; s.h = m->h; s.ox = m->ox; s.oy = m->oy; s.key_base = key_base; s.pad = 0;
+  s.rx = host_world_to_cell(px, m->scale); s.ry = host_world_to_cell(py, m->scale);
+  s.beam_begin = s.beam_end = 0;
   return s;
 }
 
@@ -797,6 +853,7 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   unsigned long long key_total = 0;
   for (int k = 0; k < n; ++k) {
     slots[k] = slot_of(maps[k], plans[k].px, plans[k].py, slots[k].shift, (unsigned)key_total);
+    slots[k].beam_begin = (int)beam0[k]; slots[k].beam_end = (int)beam0[k + 1];
     key_total += (unsigned long long)maps[k]->w * maps[k]->h;
   }
   if (key_total >= 0xFFFFFFFFull) return sg_fail(ctx, SLAMGPU_E_NOMEM, "maps too large for 32-bit cell keys (%llu cells): insert in smaller batches", key_total);
@@ -819,9 +876,27 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   ea.N = N; ea.M = M; ea.maps = ctx->scratch[7].as<MapSlot>(); ea.scale = maps[0]->scale; ea.est = *est;
   ea.cells = ctx->scratch[2].as<int2>();
   ea.aoo_p = aoo_p; ea.aoo_q = aoo_q; ea.keys = keys; ea.vals = vals; ea.slot_beam = slot_beam; ea.counters = counters;
+  // the robot cell's chain leaves the sort and runs on the side stream (not when a pyramid wants the per-slot trace)
+  const bool robot_split = trace == nullptr;
+  ea.robot_slot = nullptr;
+  if (robot_split) {
+    if (ctx->scratch[5].reserve(sizeof(int) * (size_t)std::max(N, 1)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "robot slots");
+    ea.robot_slot = ctx->scratch[5].as<int>();
+    SG_CUDA(ctx, cudaMemsetAsync(ea.robot_slot, 0xFF, sizeof(int) * (size_t)N, ctx->stream));
+  }
   k_estimate<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
+  if (robot_split) {
+    RobotArgs ra;
+    ra.maps = ctx->scratch[7].as<MapSlot>(); ra.n_maps = n; ra.beams = ctx->scratch[0].as<BeamRec>(); ra.robot_slot = ea.robot_slot;
+    ra.aoo_p = aoo_p; ra.aoo_q = aoo_q; ra.stride = maps[0]->stride; ra.model = maps[0]->model;
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    k_apply_robot<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+  }
 
   // ---- sort by (map, cell) (stable), then apply each cell's run in order
   unsigned *ks, *vs;
@@ -852,6 +927,7 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   ctx->evk_valid = true;
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
+  if (robot_split) SG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   for (int k = 0; k < n; ++k)
     if (plans[k].M > 0) sg_map_invalidate_lut(maps[k]);
   std::vector<unsigned long long> h_counters((size_t)n * 2);

@@ -210,3 +210,31 @@ def test_filter_scan_matches_oracle(sg, gpu):
             got = gm.filter_scan(r, a, (0.3, 0.2, 0.5), occ=occ, skip_rate=skip, max_range=mr)
             assert np.array_equal(got, k1[:n1])
         gm.close()
+
+
+def test_library_division_is_correctly_rounded(sg, gpu):
+    """the TBM update chain divides through a shortcut for subnormal numerators (sg::div_chain): against IEEE division on the
+    host, over random operands, the subnormal range, ties on the subnormal grid and denominators within rounding of one"""
+    rng = np.random.default_rng(77)
+    n = 400000
+    a = np.ldexp(rng.random(n) + 0.5, rng.integers(-1080, -880, n))          # tiny and subnormal numerators
+    b = np.ldexp(rng.random(n) + 0.5, rng.integers(-4, 4, n))
+    a[:1000] = 5e-324 * rng.integers(1, 40, 1000)                             # the bottom of the subnormal range
+    b[:500] = 1.0
+    b[500:1000] = 1.0 - 2.0 ** -53 * rng.integers(1, 8, 500)
+    a[1800:4000] = 5e-324 * rng.integers(1, 2 ** 20, 2200)                     # k units against b near one: around the shortcut's edge
+    b[1800:4000] = 1.0 + rng.normal(0, 1, 2200) * 2.0 ** -rng.integers(2, 30, 2200)
+    # exact ties: numerator = odd multiple of half the smallest subnormal, scaled by a power-of-two denominator
+    a[1000:1400] = 5e-324 * (2 * rng.integers(1, 1000, 400) + 1)
+    b[1000:1400] = 2.0
+    a[1400:1800] = np.ldexp(2 * rng.integers(1, 2 ** 40, 400) + 1.0, -1074 - 40 + 10)
+    b[1400:1800] = 2.0 ** 11
+    sign = rng.integers(0, 2, n) * 2 - 1
+    a2 = np.concatenate([a * sign, rng.normal(0, 1, 50000), np.ldexp(rng.random(50000), rng.integers(-1000, 1000, 50000))])
+    b2 = np.concatenate([b, rng.normal(0, 1, 50000), np.ldexp(rng.random(50000) + 0.5, rng.integers(-1000, 1000, 50000))])
+    with np.errstate(all="ignore"):
+        want = a2 / b2
+    got = gpu.debug_div(a2, b2)
+    bad = ~((got == want) | (np.isnan(got) & np.isnan(want)))
+    assert not bad.any(), (a2[bad][:5], b2[bad][:5], got[bad][:5], want[bad][:5])
+    assert (np.abs(want[:n]) < 2.3e-308).sum() > 100000  # the subnormal results really were exercised

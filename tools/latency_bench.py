@@ -47,7 +47,7 @@ def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=360):
     rng = np.random.default_rng(7)
     parts = sg.Particles(ctx, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
     est = sg.estimator(sg.EST_CONST)
-    pose = np.array([0.3, -0.2, 0.1])
+    pose = np.array([0.317, -0.223, 0.1])
     r, a = bench.room_ranges(rng, beams, 2 * np.pi, size * scale * 0.35, size * scale * 0.3, pose, 0.01)
     scan = sg.Scan(ctx, r, a)
     poses = pose + rng.normal(0, [0.02, 0.02, 0.01], (n, 3))
@@ -69,7 +69,7 @@ def measure(ctx):
             ("viny_hc_round", 800, 0.05, 1081, 1.5 * np.pi, 6, sg.CELL_TBM_CONSISTENT, sg.EST_AREA)):
         hw, hh = size * scale * 0.35, size * scale * 0.3
         gm = sg.GridMap(ctx, size, size, scale, model, sg.GROW_PLAIN)
-        pose = np.array([0.3, -0.2, 0.1])
+        pose = np.array([0.317, -0.223, 0.1])
         r, a = bench.room_ranges(rng, beams, fov, hw, hh, pose, 0.01)
         scan = sg.Scan(ctx, r, a)
         tbm = model == sg.CELL_TBM_CONSISTENT

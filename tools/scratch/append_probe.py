@@ -9,7 +9,7 @@ for name, size, scale, beams, fov, model, est_kind in (("tiny", 100, 0.1, 360, 2
                                                      ("viny", 800, 0.05, 1081, 1.5 * np.pi, sg.CELL_TBM_CONSISTENT, sg.EST_AREA)):
     hw, hh = size * scale * 0.35, size * scale * 0.3
     gm = sg.GridMap(ctx, size, size, scale, model, sg.GROW_PLAIN)
-    pose = np.array([0.3, -0.2, 0.1])
+    pose = np.array([0.317, -0.223, 0.1])
     r, a = bench.room_ranges(rng, beams, fov, hw, hh, pose, 0.01)
     scan = sg.Scan(ctx, r, a)
     tbm = model == sg.CELL_TBM_CONSISTENT

@@ -8,7 +8,7 @@ n, size, scale, beams = 256, 1000, 0.05, 360
 rng = np.random.default_rng(7)
 parts = sg.Particles(ctx, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
 est = sg.estimator(sg.EST_CONST)
-pose = np.array([0.3, -0.2, 0.1])
+pose = np.array([0.317, -0.223, 0.1])
 r, a = bench.room_ranges(rng, beams, 2 * np.pi, size * scale * 0.35, size * scale * 0.3, pose, 0.01)
 scan = sg.Scan(ctx, r, a)
 poses = pose + rng.normal(0, [0.02, 0.02, 0.01], (n, 3))
