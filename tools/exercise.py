@@ -31,11 +31,12 @@ def main():
     # K2/K3: configs[1] shape
     gm = sg.GridMap(ctx, 800, 800, 0.05, sg.CELL_TBM_CONSISTENT, sg.GROW_PLAIN)
     est = sg.estimator(sg.EST_AREA, occ=(0.95, 0.04), empty=(0.01, 0.003), shift=0.01 * 0.05)
-    pose = np.array([0.3, -0.2, 0.1])
+    pose = np.array([0.317, -0.223, 0.1])
     r, a = bench.room_ranges(rng, 1081, 1.5 * np.pi, 14.0, 12.0, pose, 0.01)
     scan = sg.Scan(ctx, r, a)
     for _ in range(3):
         ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3)
+    ctx.match_hc(gm, scan, sg.spe_params(), pose + [0.06, -0.05, 0.03])   # whole hill-climbing match, one launch
     gm.close()
     # K4/K5: pyramid, configs[4]-like at 2048
     gm = sg.GridMap(ctx, 2048, 2048, 0.025, sg.CELL_MEAN, sg.GROW_PLAIN)
@@ -53,7 +54,8 @@ def main():
     scan = sg.Scan(ctx, r, a)
     poses = pose + rng.normal(0, [0.03, 0.03, 0.01], (n, 3))
     parts.append_scan(scan, poses)
-    parts.match_hc(scan, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1), poses, 6, 0.1, 0.1)
+    parts.match_hc(scan, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1), poses, 6, 0.1, 0.1)            # one launch
+    parts.match_hc(scan, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2), poses, 6, 0.1, 0.1)  # carried cache: lock step
     parts.close(); scan.close(); ctx.close()
     print("exercise: done")
 
