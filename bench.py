@@ -267,8 +267,9 @@ def main():
                                   "candidate poses x 1081 beams, 2000x2000 grid @0.05 m, obstacle OOPE, even weights, "
                                   "MeanProbabilityCell map",
                       "candidates": 1020100, "beams": N_BEAMS, "grid": [MAP_SIZE, MAP_SIZE],
-                      "sharding": "candidate rows (theta, y) split contiguously over ranks, map replicated; one 32-byte "
-                                  "all-gather merges the per-rank arg-max",
+                      "sharding": "candidate rows (theta, y) split contiguously over ranks, map replicated; the per-rank arg-max "
+                                  "(32 bytes) is exchanged inside the finalize kernel through NVLink peer mailboxes "
+                                  "(ncclAllGather when peer mapping is unavailable)",
                       "scaling_mode": "weak: the theta sweep is extended by 100 values (1020100 candidates) per extra GPU"
                                       if args.scaling == "weak" else "strong: fixed 1020100 candidates split over ranks",
                       "l2": "flushed (256 MB write) before every timed step" if L2_FLUSH else "not flushed"}}
@@ -335,6 +336,8 @@ def main():
     _, idx1, best1 = ctx.score_fetch()
     assert (idx1, best1) == (idx0, best0), "result changed between launches"
     st = ctx.score_stats()
+    if world > 1:
+        cfg["config"]["result_exchange"] = "peer memory (fused in k_exchange_finalize)" if st.get("peer_exchange") else "ncclAllGather"
 
     # ---- end to end through the host-buffer C-ABI call (what a GridScanMatcher adapter calls)
     e2e_steps = args.steps

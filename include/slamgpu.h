@@ -251,7 +251,8 @@ int slamgpu_score_launch(slamgpu_ctx *ctx, slamgpu_map *map, double init_score);
 int slamgpu_score_fetch(slamgpu_ctx *ctx, double *out_scores /* NULL ok */, int64_t *best_idx, double *best_score);
 /* counters of the last scoring call: [0] guard hits (points re-done with host trig),
  * [1] kernel variant used (0 list, 1 grid v1, 2 grid v2 / 3 grid v3, 3 two-phase small batch when staged, 4 fused one-launch small batch), [2] evaluations (poses*points) on this rank,
- * [3] first candidate index of this rank's slice, [4] slice length, [5] grid kernel rows per thread */
+ * [3] first candidate index of this rank's slice, [4] slice length, [5] grid kernel rows per thread,
+ * [6] 1 when the per-rank results were exchanged through peer memory (NVLink mailboxes), 0 for ncclAllGather / one rank */
 int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]);
 
 /* ------------------------------------------------------------------ K2: ray casting

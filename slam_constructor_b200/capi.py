@@ -329,7 +329,7 @@ class Context:
     def score_stats(self):
         st = np.zeros(8, dtype=np.int64)
         self.check(self.L.slamgpu_score_stats(self.h, st.ctypes.data_as(c_lp)))
-        return dict(guard_hits=int(st[0]), variant=int(st[1]), evals=int(st[2]), slice_begin=int(st[3]), slice_len=int(st[4]), rows_per_thread=int(st[5]))
+        return dict(guard_hits=int(st[0]), variant=int(st[1]), evals=int(st[2]), slice_begin=int(st[3]), slice_len=int(st[4]), rows_per_thread=int(st[5]), peer_exchange=int(st[6]))
 
     # ---- K2 / K3 ----
     def raycast(self, gmap, scan, pose, want_cells=True):

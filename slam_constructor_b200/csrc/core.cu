@@ -2,9 +2,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "dev_math.cuh"
 #include "internal.h"
@@ -117,14 +119,67 @@ extern "C" int slamgpu_ctx_create_dist(int device, int rank, int nranks, const v
     std::string err;
     int r = sg_nccl_init(nranks, rank, nccl_id128, &ctx->comm, &err);
     if (r != SLAMGPU_OK) { slamgpu_ctx_destroy(ctx); *out = nullptr; return sg_fail(nullptr, r, "%s", err.c_str()); }
+    sg_p2p_setup(ctx);  // optional: without it the per-rank results travel by ncclAllGather
   }
   return SLAMGPU_OK;
+}
+
+// Mailboxes for the fused result exchange: each rank allocates one, the CUDA IPC handles are all-gathered over NCCL,
+// every rank maps every peer's mailbox (NVLink peer access).  All ranks must agree, so the outcome is all-gathered too;
+// any failure (no peer access, IPC not permitted in this container, SLAMGPU_NO_P2P=1) leaves the NCCL path in place.
+void sg_p2p_setup(slamgpu_ctx *ctx) {
+  const int n = ctx->nranks;
+  if (n < 2 || n > 64) return;
+  const char *off = getenv("SLAMGPU_NO_P2P");
+  int ok = !(off && off[0] == '1');
+  const size_t box_bytes = (size_t)2 * n * 64;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok && (cudaMalloc(&ctx->mailbox, box_bytes) != cudaSuccess || cudaMemset(ctx->mailbox, 0, box_bytes) != cudaSuccess ||
+             cudaIpcGetMemHandle(&mine, ctx->mailbox) != cudaSuccess))
+    ok = 0;
+  (void)cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  std::vector<cudaIpcMemHandle_t> all(n);
+  all[ctx->rank] = mine;
+  if (sg_allgather_host(ctx, all.data(), sizeof(cudaIpcMemHandle_t)) != SLAMGPU_OK) ok = 0;
+  std::vector<int> oks(n, 0);
+  oks[ctx->rank] = ok;
+  if (sg_allgather_host(ctx, oks.data(), sizeof(int)) != SLAMGPU_OK) return;
+  for (int r = 0; r < n; ++r) ok &= oks[r];
+  std::vector<void *> peers(n, nullptr);
+  if (ok) {
+    for (int r = 0; r < n && ok; ++r) {
+      if (r == ctx->rank) { peers[r] = ctx->mailbox; continue; }
+      if (cudaIpcOpenMemHandle(&ctx->peer_mapped[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; (void)cudaGetLastError(); }
+      peers[r] = ctx->peer_mapped[r];
+    }
+  }
+  if (ok && (cudaMalloc(&ctx->d_peer_mailbox, sizeof(void *) * n) != cudaSuccess ||
+             cudaMemcpy(ctx->d_peer_mailbox, peers.data(), sizeof(void *) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+             cudaMalloc(&ctx->d_p2p_status, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_p2p_status, 0, sizeof(int)) != cudaSuccess))
+    ok = 0;
+  oks.assign(n, 0);
+  oks[ctx->rank] = ok;
+  if (sg_allgather_host(ctx, oks.data(), sizeof(int)) != SLAMGPU_OK) ok = 0;
+  for (int r = 0; r < n; ++r) ok &= oks[r];
+  if (!ok) sg_p2p_teardown(ctx);
+}
+
+void sg_p2p_teardown(slamgpu_ctx *ctx) {
+  for (int r = 0; r < 64; ++r)
+    if (ctx->peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->peer_mapped[r]); ctx->peer_mapped[r] = nullptr; }
+  if (ctx->d_peer_mailbox) { cudaFree(ctx->d_peer_mailbox); ctx->d_peer_mailbox = nullptr; }
+  if (ctx->d_p2p_status) { cudaFree(ctx->d_p2p_status); ctx->d_p2p_status = nullptr; }
+  if (ctx->mailbox) { cudaFree(ctx->mailbox); ctx->mailbox = nullptr; }
+  (void)cudaGetLastError();
 }
 
 extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  sg_p2p_teardown(ctx);
   if (ctx->comm) sg_nccl_destroy(ctx->comm);
   Candidates &c = ctx->cand;
   DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,

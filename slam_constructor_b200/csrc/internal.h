@@ -73,6 +73,13 @@ struct Candidates {  // a staged candidate set (device resident)
 struct slamgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // peer-memory exchange of the per-rank results (score.cu: k_exchange_finalize): every rank owns a mailbox that its
+  // peers write through NVLink (CUDA IPC mappings); NULL when unavailable -> the NCCL all-gather is used instead
+  void *mailbox = nullptr;         // this rank's mailbox: 2 parities x nranks x 64 B
+  void **d_peer_mailbox = nullptr; // device array [nranks]: every rank's mailbox as seen from this GPU
+  void *peer_mapped[64] = {nullptr};
+  unsigned long long p2p_seq = 0;
+  int *d_p2p_status = nullptr;     // set by the kernel when a peer did not answer in time
   cudaStream_t side = nullptr;  // the robot cell's update chain runs here, next to the sort (mapping.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -173,3 +180,5 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
                          const double *init, const uint8_t *active, uint32_t max_failed_rounds, double tr, double rot,
                          double *out8, double *log, int log_cap, int *served);
 int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);
+void sg_p2p_setup(slamgpu_ctx *ctx);
+void sg_p2p_teardown(slamgpu_ctx *ctx);

@@ -89,6 +89,51 @@ __global__ void k_finalize(const Result *__restrict__ per_rank, int nranks, doub
   out->score = s; out->idx = i; out->guard = guard; out->pad = enc;
 }
 
+// The same merge fused with the exchange: instead of ncclAllGather + k_finalize, lane r of one warp stores this
+// rank's result straight into rank r's mailbox (a peer mapping over NVLink; slot = this rank, double-buffered by the
+// parity of the call number), publishes it with a system-scope fence + sequence number, then waits for rank r's result
+// to land in this rank's own mailbox.  Lane 0 merges in rank order exactly as k_finalize does.  A peer cannot run two
+// calls ahead (its next exchange needs this rank's next message), so two buffers suffice.
+struct Mail { Result res; unsigned long long seq; unsigned long long pad[3]; };  // 64 B
+__global__ void k_exchange_finalize(const Result *mine, void *const *peer_mailbox, int rank, int nranks, unsigned long long seq,
+                                    double init_score, Result *out, int *status) {
+  const int r = threadIdx.x;
+  const int parity = (int)(seq & 1ull);
+  __shared__ Result got[64];
+  __shared__ int timed_out;
+  if (r == 0) timed_out = 0;
+  __syncthreads();
+  if (r < nranks) {
+    volatile Mail *dst = reinterpret_cast<volatile Mail *>(peer_mailbox[r]) + (size_t)parity * nranks + rank;
+    const Result m = *mine;
+    dst->res.score = m.score; dst->res.idx = m.idx; dst->res.guard = m.guard; dst->res.pad = m.pad;
+    __threadfence_system();
+    dst->seq = seq;
+    volatile Mail *src = reinterpret_cast<volatile Mail *>(peer_mailbox[rank]) + (size_t)parity * nranks + r;
+    const long long t0 = clock64();
+    bool ok = true;
+    while (src->seq != seq) {
+      if (clock64() - t0 > 4000000000ll) { ok = false; break; }  // ~2 s: a peer is gone
+    }
+    __threadfence_system();
+    if (!ok) { atomicExch(status, 1); timed_out = 1; }
+    got[r].score = src->res.score; got[r].idx = src->res.idx; got[r].guard = src->res.guard; got[r].pad = src->res.pad;
+  }
+  __syncthreads();
+  if (r == 0) {
+    double s = -INFINITY;
+    long long i = LLONG_MAX, guard = 0, enc = 0;
+    for (int k = 0; k < nranks; ++k) {
+      guard += got[k].guard;
+      enc += got[k].pad;
+      if (beats(got[k].score, got[k].idx, s, i)) { s = got[k].score; i = got[k].idx; }
+    }
+    if (!(init_score < s) || i == LLONG_MAX) { s = init_score; i = -1; }
+    if (timed_out) { i = LLONG_MIN; guard = 0; enc = 0; }  // reported by the fetch
+    out->score = s; out->idx = i; out->guard = guard; out->pad = enc;
+  }
+}
+
 // ------------------------------------------------------------------ trig table
 // ScanPoint2D::move_origin + RawTrigonometryProvider: src/core/states/sensor_data.h:83-87,
 // src/core/trigonometry_utils.h:21-27 -- r*cos(theta + a), r*sin(theta + a)
@@ -1543,6 +1588,18 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
     Result empty{-INFINITY, LLONG_MAX, 0, 0};
     SG_CUDA(ctx, cudaMemcpyAsync(res, &empty, sizeof(Result), cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (ctx->nranks > 1 && ctx->d_peer_mailbox) {
+    k_exchange_finalize<<<1, 64, 0, ctx->stream>>>(res, ctx->d_peer_mailbox, ctx->rank, ctx->nranks, ++ctx->p2p_seq, init_score, local,
+                                                    ctx->d_p2p_status);
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaGetLastError());
+    c.stats[6] = 1;
+    c.launched = true;
+    c.init_score = init_score;
+    c.last_map = map;
+    return SLAMGPU_OK;
+  }
+  c.stats[6] = 0;
   const Result *per_rank = res;
   if (ctx->nranks > 1) {
     std::string err;
@@ -1574,6 +1631,7 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
   Result *h = (Result *)hp;
   SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h->idx == LLONG_MIN) return sg_fail(ctx, SLAMGPU_E_NCCL, "a peer rank did not deliver its result within 2 s (peer-memory exchange)");
   while (h->pad > 0 && c.kind == 1 && c.grid_variant > 1 && map) {
     // v3: some block's cells did not fit its TMA box -> v2; v2: two neighbouring y values are more than
     // 7 cell rows apart, the packed row word cannot hold it -> the explicit row table (v1 kernel)
