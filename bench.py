@@ -382,6 +382,9 @@ def main():
                 traffic = json.load(open(tf)).get("k_score_grid_dram_bytes_per_launch")
             except ValueError:
                 traffic = None
+        # context for frac > 1: the rate of random 8-byte loads that share nothing, over a table the size of the LUT
+        gather_peak = ctx.probe_gather(MAP_SIZE * MAP_SIZE * 8, 1024)
+        kernel_gathers = k_evals / (kern_ms / args.steps * 1e-3)
         line = {"metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
@@ -391,6 +394,10 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "k_score_grid", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "kernel_ms": kern_ms / args.steps,
+                             "l2_random_gather": {"loads_per_s": gather_peak, "table_MB": MAP_SIZE * MAP_SIZE * 8 / 1e6,
+                                                  "kernel_gathers_per_s": kernel_gathers, "ratio": kernel_gathers / gather_peak,
+                                                  "what": "uniformly random 8-byte loads over an L2-resident table of the LUT's "
+                                                          "size (slamgpu_probe_gather): gathers that share no sector"},
                              "note": "algorithmic bytes = 32 B (one sector) per pose-beam evaluation; the map is L2/L1 "
                                      "resident so frac > 1 means sector reuse, not an error"},
                 "result": {"best_idx": idx0, "best_score": best0, "guard_hits": st["guard_hits"]}}

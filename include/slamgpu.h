@@ -382,6 +382,11 @@ int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, cons
  * a source drawn once is moved, the others are copied device to device (or rank to rank) */
 int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src /* n */);
 
+/* ------------------------------------------------------------------ measurement aid
+ * rate (loads/s) of uniformly random 8-byte loads over an L2-resident table of table_bytes: the gather roofline of
+ * K1 when no two gathers share a sector (bench.py reports K1 against it next to the HBM figure) */
+int slamgpu_probe_gather(slamgpu_ctx *ctx, int64_t table_bytes, int32_t loads_per_thread, double *gathers_per_s);
+
 /* ------------------------------------------------------------------ test hook
  * out[i] = a[i] / b[i] through the division the TBM cell update uses (with its exact shortcut for subnormal
  * numerators): lets the parity tests hold it against the host's IEEE division. */

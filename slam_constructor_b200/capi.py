@@ -91,7 +91,7 @@ SYMBOLS = [
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
-    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_match_hc", "slamgpu_debug_div", "slamgpu_stage_poses",
+    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_match_hc", "slamgpu_debug_div", "slamgpu_probe_gather", "slamgpu_stage_poses",
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
@@ -153,6 +153,7 @@ def lib():
     L.slamgpu_score_poses.argtypes = [vp, vp, vp, sp, c_dp, i64, dbl, c_dp, c_lp, c_dp]
     L.slamgpu_score_grid.argtypes = [vp, vp, vp, sp, c_dp, i32, c_dp, i32, c_dp, i32, dbl, c_dp, c_lp, c_dp]
     L.slamgpu_score_poses_chained.argtypes = [vp, vp, vp, sp, c_dp, i64, C.POINTER(GmCache), c_dp, C.POINTER(GmCache)]
+    L.slamgpu_probe_gather.argtypes = [vp, i64, i32, c_dp]
     L.slamgpu_debug_div.argtypes = [vp, i32, c_dp, c_dp, c_dp]
     L.slamgpu_match_hc.argtypes = [vp, vp, vp, sp, c_dp, C.c_uint32, dbl, dbl, c_dp, c_dp, c_lp, c_dp, i32, c_ip]
     L.slamgpu_stage_poses.argtypes = [vp, vp, sp, c_dp, i64]
@@ -290,6 +291,11 @@ class Context:
         self.check(self.L.slamgpu_score_poses_chained(self.h, gmap.h, scan.h, C.byref(params), _dp(poses), P, C.byref(st_in), _dp(out),
                                                       states))
         return out, [GmCache(s.cx, s.cy, s.prob) for s in states[:P]]
+
+    def probe_gather(self, table_bytes=32 << 20, loads_per_thread=512):
+        out = C.c_double()
+        self.check(self.L.slamgpu_probe_gather(self.h, table_bytes, loads_per_thread, C.byref(out)))
+        return out.value
 
     def debug_div(self, a, b):
         a, b = _f64(a), _f64(b)

@@ -248,6 +248,50 @@ extern "C" int slamgpu_flush_l2(slamgpu_ctx *ctx) {
   return SLAMGPU_OK;
 }
 
+// ------------------------------------------------------------------ gather micro-benchmark (roofline context)
+// Uniformly random 8-byte loads over a table the size of a score LUT: the rate at which the memory system serves
+// gathers that share NOTHING (one 32-byte sector each).  K1's gathers share sectors between neighbouring candidates,
+// so it may exceed this rate; bench.py reports both.
+namespace {
+__global__ void __launch_bounds__(256) k_gather_probe(const double *__restrict__ table, unsigned long long mask, int loads, double *sink) {
+  unsigned long long x = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < loads; k += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+      acc[u] += __ldg(table + (x & mask));
+    }
+  }
+  double t = 0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) t += acc[u];
+  if (t == 123.456) sink[0] = t;  // keeps the loads alive
+}
+}  // namespace
+
+extern "C" int slamgpu_probe_gather(slamgpu_ctx *ctx, int64_t table_bytes, int32_t loads_per_thread, double *gathers_per_s) {
+  if (!ctx || !gathers_per_s || table_bytes < 4096 || loads_per_thread < 8) return sg_fail(ctx, SLAMGPU_E_INVALID, "probe_gather: bad argument");
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long n = 1;
+  while (n * 2 * sizeof(double) <= (unsigned long long)table_bytes) n *= 2;  // power of two entries
+  if (ctx->scratch[4].reserve(n * sizeof(double) + 64) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "probe table");
+  SG_CUDA(ctx, cudaMemsetAsync(ctx->scratch[4].p, 0, n * sizeof(double) + 64, ctx->stream));
+  const int blocks = ctx->sm_count * 8, loads = (loads_per_thread + 7) & ~7;
+  double *table = ctx->scratch[4].as<double>();
+  k_gather_probe<<<blocks, 256, 0, ctx->stream>>>(table, n - 1, loads, table + n);  // warm-up: the table becomes L2 resident
+  SG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  k_gather_probe<<<blocks, 256, 0, ctx->stream>>>(table, n - 1, loads, table + n);
+  SG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->launches += 2;
+  SG_CUDA(ctx, cudaGetLastError());
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  SG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *gathers_per_s = (double)blocks * 256.0 * loads / (ms * 1e-3);
+  return SLAMGPU_OK;
+}
+
 int sg_allgather16(slamgpu_ctx *ctx, const void *d_send16, void *d_recv) {
   std::string err;
   int r = sg_nccl_allgather(ctx->comm, d_send16, d_recv, 16, ctx->stream, &err);
