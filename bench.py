@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--grid-rows", type=int, default=0, help="experiment: rows per thread of the grid kernel (0 = automatic)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = 100 more theta values (1 020 100 more candidates) per extra GPU; strong = the fixed "
                          "1 020 100 candidates split N ways")
@@ -296,6 +297,8 @@ def main():
         dist.broadcast_object_list(box, src=0)
         nccl_id = box[0]
     ctx = sg.Context(local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
+    if args.grid_rows:
+        ctx.set_option("grid_rows", args.grid_rows)
 
     wl = make_workload(theta_blocks=world if args.scaling == "weak" else 1)
     P = len(wl["xs"]) * len(wl["ys"]) * len(wl["ts"])

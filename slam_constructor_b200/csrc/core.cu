@@ -231,6 +231,11 @@ extern "C" int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_
     ctx->cand.user_variant = (int)value;
     return SLAMGPU_OK;
   }
+  if (strcmp(name, "grid_rows") == 0) {  // rows per thread of the v2 grid kernel: 0 = automatic, or 2 / 4 / 8
+    if (value != 0 && value != 2 && value != 4 && value != 8) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_rows must be 0, 2, 4 or 8");
+    ctx->cand.user_rows = (int)value;
+    return SLAMGPU_OK;
+  }
   return sg_fail(ctx, SLAMGPU_E_INVALID, "unknown option '%s'", name);
 }
 extern "C" int64_t slamgpu_launch_count(const slamgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -55,6 +55,7 @@ struct Candidates {  // a staged candidate set (device resident)
   bool multi = false;
   DevBuf views, view_id;
   // GMapping OOPE cache chain (spe.gm_cache == 2): predecessor of each pose, entry states, state after each pose
+  int user_rows = 0;  // slamgpu_ctx_set_option("grid_rows")
   bool gm_chain = false;
   DevBuf gm_pred, gm_in, gm_out;
   // trig tables (device), layout given by strides

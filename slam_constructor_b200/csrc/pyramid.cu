@@ -638,6 +638,7 @@ HMatch make_match(double rot, double bot, double top, double left, double right,
 
 #include <queue>
 #include <set>
+#include <unordered_map>
 
 extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *range, const double *angle,
                                    const double *weight, const double pose[3], const slamgpu_spe_params *spe, double x_limit,
@@ -675,27 +676,89 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
   int64_t n_scored = 0, n_calls = 0, n_branches = 0;
   std::vector<int32_t> sid;
   std::vector<double> win, bounds;
+  // what the engine does with a match it pops: split a window that is still wider than the target accuracy
+  // (branch :337-357), or test the corners and the centre of a leaf as point windows; nothing for a point
+  auto expansions = [&](const HMatch &m, std::vector<HMatch> &out) {
+    const bool horz = h_less(transl_step, m.hside()), vert = h_less(transl_step, m.vside());
+    const double cx = m.left + m.hside() / 2, cy = m.bot + m.vside() / 2;  // center()
+    auto child = [&](double b, double t, double l, double r) { out.push_back(make_match(m.rotation, b, t, l, r, m.scan_id)); };
+    if (horz && vert) {  // split4_evenly: left-bot, left-top, right-bot, right-top
+      child(m.bot, cy, m.left, cx); child(cy, m.top, m.left, cx);
+      child(m.bot, cy, cx, m.right); child(cy, m.top, cx, m.right);
+    } else if (horz) {   // split_horz
+      child(m.bot, m.top, m.left, cx); child(m.bot, m.top, cx, m.right);
+    } else if (vert) {   // split_vert
+      child(m.bot, cy, m.left, m.right); child(cy, m.top, m.left, m.right);
+    } else if (!m.is_finest()) {  // exact translation hypotheses: the four corners and the centre
+      const double px[5] = {m.left, m.left, m.right, m.right, cx};
+      const double py[5] = {m.bot, m.top, m.bot, m.top, cy};
+      for (int k = 0; k < 5; ++k) child(py[k], py[k], px[k], px[k]);
+    }
+  };
+  // A bound is a pure function of (rotation, window), so it may be computed before the engine asks for it.  Every K5
+  // call therefore also scores what the engine is likely to ask next -- the expansions of the matches being added and
+  // of the best matches already queued -- and keeps the bounds; the engine itself (queue order, pruning, branching)
+  // is untouched and asks for exactly the matches upstream scores, most of which are then already known.
+  struct Key {
+    int scan_id; double b, t, l, r;
+    bool operator==(const Key &o) const { return scan_id == o.scan_id && b == o.b && t == o.t && l == o.l && r == o.r; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key &k) const {
+      uint64_t h = (uint64_t)k.scan_id * 0x9E3779B97F4A7C15ull;
+      for (double d : {k.b, k.t, k.l, k.r}) { uint64_t u; memcpy(&u, &d, 8); h = (h ^ u) * 0x100000001B3ull; h ^= h >> 29; }
+      return (size_t)h;
+    }
+  };
+  std::unordered_map<Key, double, KeyHash> known;
+  auto key_of = [](const HMatch &m) { return Key{m.scan_id, m.bot, m.top, m.left, m.right}; };
+  std::vector<HMatch> heap;  // std::priority_queue's own algorithm (push_heap / pop_heap), kept open for peeking
+  std::vector<HMatch> ask, spec, tmp;
+  const size_t kSpeculate = 192, kPeek = 12;
   auto score = [&](std::vector<HMatch> &ms) -> int {
     if (ms.empty()) return SLAMGPU_OK;
-    sid.clear(); win.clear();
-    for (const HMatch &m : ms) {
-      sid.push_back(m.scan_id);
-      win.push_back(m.bot); win.push_back(m.top); win.push_back(m.left); win.push_back(m.right);
+    ask.clear();
+    auto want = [&](const HMatch &m) {
+      const Key k = key_of(m);
+      if (known.count(k)) return;
+      known.emplace(k, NAN);
+      ask.push_back(m);
+    };
+    for (const HMatch &m : ms) want(m);
+    if (!ask.empty()) {  // a call is being made anyway: fill it up with likely next requests
+      spec.clear();
+      for (const HMatch &m : ms) expansions(m, spec);
+      tmp = heap;
+      for (size_t k = 0; k < kPeek && !tmp.empty(); ++k) {
+        std::pop_heap(tmp.begin(), tmp.end());
+        expansions(tmp.back(), spec);
+        tmp.pop_back();
+      }
+      for (const HMatch &m : spec) {
+        if (ask.size() >= ms.size() + kSpeculate) break;
+        want(m);
+      }
+      sid.clear(); win.clear();
+      for (const HMatch &m : ask) {
+        sid.push_back(m.scan_id);
+        win.push_back(m.bot); win.push_back(m.top); win.push_back(m.left); win.push_back(m.right);
+      }
+      bounds.resize(ask.size());
+      SG_TRY(slamgpu_score_windows(p, pool.data(), (int32_t)rots.size(), sid.data(), win.data(), (int64_t)ask.size(), pose, &sp,
+                                   bounds.data()));
+      for (size_t k = 0; k < ask.size(); ++k) known[key_of(ask[k])] = bounds[k];
+      n_scored += (int64_t)ask.size(); ++n_calls;
     }
-    bounds.resize(ms.size());
-    SG_TRY(slamgpu_score_windows(p, pool.data(), (int32_t)rots.size(), sid.data(), win.data(), (int64_t)ms.size(), pose, &sp,
-                                 bounds.data()));
-    for (size_t k = 0; k < ms.size(); ++k) ms[k].bound = bounds[k];
-    n_scored += (int64_t)ms.size(); ++n_calls;
+    for (HMatch &m : ms) m.bound = known[key_of(m)];
     return SLAMGPU_OK;
   };
   // ---- engine state (M3RSMEngine :252-289)
-  std::priority_queue<HMatch> queue;
   double best_finest = 0.0;
   auto add_match = [&](const HMatch &m) {
     if (m.bound < best_finest) return;
     if (m.is_finest()) best_finest = std::max(best_finest, m.bound - max_finest_prob_diff);
-    queue.push(m);
+    heap.push_back(m);
+    std::push_heap(heap.begin(), heap.end());
   };
   std::vector<HMatch> batch;
   for (const Rot &r : rots) {
@@ -708,23 +771,15 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
   for (;;) {
     HMatch best;
     bool found = false;
-    while (!queue.empty()) {
-      best = queue.top();
-      queue.pop();
+    while (!heap.empty()) {
+      std::pop_heap(heap.begin(), heap.end());
+      best = heap.back();
+      heap.pop_back();
       const bool horz = h_less(transl_step, best.hside()), vert = h_less(transl_step, best.vside());
       if (!horz && !vert) { found = true; break; }
       ++n_branches;
-      const double cx = best.left + best.hside() / 2, cy = best.bot + best.vside() / 2;  // center()
       batch.clear();
-      auto child = [&](double b, double t, double l, double r) { batch.push_back(make_match(best.rotation, b, t, l, r, best.scan_id)); };
-      if (horz && vert) {  // split4_evenly: left-bot, left-top, right-bot, right-top
-        child(best.bot, cy, best.left, cx); child(cy, best.top, best.left, cx);
-        child(best.bot, cy, cx, best.right); child(cy, best.top, cx, best.right);
-      } else if (horz) {   // split_horz
-        child(best.bot, best.top, best.left, cx); child(best.bot, best.top, cx, best.right);
-      } else {             // split_vert
-        child(best.bot, cy, best.left, best.right); child(cy, best.top, best.left, best.right);
-      }
+      expansions(best, batch);
       SG_TRY(score(batch));
       for (const HMatch &m : batch) add_match(m);
     }
@@ -736,12 +791,8 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
       *out_prob = best.bound;
       break;
     }
-    // exact translation hypotheses: the four corners and the centre as point windows
-    const double cx = best.left + best.hside() / 2, cy = best.bot + best.vside() / 2;
-    const double px[5] = {best.left, best.left, best.right, best.right, cx};
-    const double py[5] = {best.bot, best.top, best.bot, best.top, cy};
     batch.clear();
-    for (int k = 0; k < 5; ++k) batch.push_back(make_match(best.rotation, py[k], py[k], px[k], px[k], best.scan_id));
+    expansions(best, batch);
     SG_TRY(score(batch));
     for (const HMatch &m : batch) add_match(m);
   }

@@ -1280,6 +1280,7 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     const int64_t want_threads = (int64_t)ctx->sm_count * 768;
     int R = 8;
     while (c.grid_v2 && R > 2 && ((r1_ - r0_ + R - 1) / R) * nx < want_threads) R /= 2;
+    if (c.user_rows) R = c.user_rows;
     c.grid_R = c.grid_v2 ? R : SG_GRID_R;
     c.ngy = (ny + c.grid_R - 1) / c.grid_R;
   }

@@ -235,6 +235,7 @@ void run_m3rsm(std::shared_ptr<slamgpu::Context> ctx) {
   std::mt19937 rng(21);
   std::normal_distribution<double> odo(0.0, 0.03), odo_t(0.0, 0.01);
   RobotPose truth{0.1, 0.2, -0.1};
+  double m3_ref = 0, m3_gpu = 0;
   for (int step = 0; step < 6; ++step) {
     RobotPoseDelta motion = step == 0 ? RobotPoseDelta{truth.x, truth.y, truth.theta} : RobotPoseDelta{0.07, -0.04, 0.02};
     if (step > 0) { truth += motion; }
@@ -242,8 +243,12 @@ void run_m3rsm(std::shared_ptr<slamgpu::Context> ctx) {
     auto scan = room_scan(truth, 181, 2 * M_PI, 3.0, 2.5, rng, 0.01);
     TransformedLaserScan a{odom, scan, 1.0}, b{odom, scan, 1.0};
     b.scan.trig_provider = std::make_shared<RawTrigonometryProvider>();
+    auto t0 = std::chrono::steady_clock::now();
     ref_world.handle_sensor_data(a);
+    auto t1 = std::chrono::steady_clock::now();
     gpu_world.handle_sensor_data(b);
+    auto t2 = std::chrono::steady_clock::now();
+    if (step > 0) { m3_ref += std::chrono::duration<double, std::milli>(t1 - t0).count(); m3_gpu += std::chrono::duration<double, std::milli>(t2 - t1).count(); }
     const RobotPose &p1 = ref_world.pose(), &p2 = gpu_world.pose();
     CHECK(p1.x == p2.x && p1.y == p2.y && p1.theta == p2.theta, "m3rsm step %d: pose (%.17g %.17g %.17g) vs (%.17g %.17g %.17g)", step, p1.x,
           p1.y, p1.theta, p2.x, p2.y, p2.theta);
@@ -254,6 +259,7 @@ void run_m3rsm(std::shared_ptr<slamgpu::Context> ctx) {
   std::printf("   6 scans; last scan: %ld matches scored in %ld K5 calls, %ld branches, %ld rotations; final pose %.6f %.6f %.6f\n",
               (long)gsm->stats()[0], (long)gsm->stats()[1], (long)gsm->stats()[2], (long)gsm->stats()[3], gpu_world.pose().x,
               gpu_world.pose().y, gpu_world.pose().theta);
+  std::printf("   TIMING per scan (handle_sensor_data, wall clock, scans 1..5): reference CPU %.3f ms, CUDA plug-ins %.3f ms\n", m3_ref / 5, m3_gpu / 5);
 }
 
 // the shipped presets (config/slams/tiny_slam_base.properties, viny_slam_base.properties with their includes),
