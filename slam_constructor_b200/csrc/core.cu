@@ -603,6 +603,45 @@ extern "C" int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian
   return SLAMGPU_OK;
 }
 
+// Many Cartesian copies of one scan at once (the pre-rotated scans of the multi-resolution matcher): only what the
+// window kernels read is filled in -- x, y, weight, factor 1, occupied -- so no atan2/sqrt per point, one staging
+// buffer, one synchronisation.  xs / ys hold `count` rows of n values.
+int sg_scans_upload_xy(slamgpu_ctx *ctx, slamgpu_scan *const *scans, int count, int32_t n, const double *xs, const double *ys,
+                       const double *weight) {
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t nn = std::max(n, 1);
+  const size_t bytes = nn * 6 * sizeof(double) + ((nn + 7) & ~(size_t)7);
+  void *hp;
+  SG_TRY(sg_pinned(ctx, bytes * count, &hp));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging may still be in flight
+  std::vector<double> w(nn, 0.0);
+  for (int i = 0; i < n; ++i) w[i] = weight ? weight[i] : 1.0 / n;
+  double ws = 0;
+  for (int i = 0; i < n; ++i) ws += w[i];  // weighted_mean_point_probability_spe.h:125
+  for (int k = 0; k < count; ++k) {
+    slamgpu_scan *s = scans[k];
+    if (!s || s->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan %d is NULL or belongs to another ctx", k);
+    s->n = n; s->cartesian = 1; s->has_factor = false; s->wsum = ws;
+    s->x.assign(xs + (size_t)k * n, xs + (size_t)(k + 1) * n); s->y.assign(ys + (size_t)k * n, ys + (size_t)(k + 1) * n);
+    s->range.assign(n, NAN); s->angle.assign(n, NAN);  // not derived: these copies are only ever read as points
+    s->weight.assign(w.begin(), w.begin() + n); s->factor.assign(n, 1.0); s->occ.assign(n, 1);
+    if (s->d.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "scan buffer");
+    double *h = (double *)((char *)hp + bytes * k);
+    for (size_t i = 0; i < 2 * nn; ++i) h[i] = NAN;
+    memcpy(h + 2 * nn, s->x.data(), n * sizeof(double));
+    memcpy(h + 3 * nn, s->y.data(), n * sizeof(double));
+    memcpy(h + 4 * nn, w.data(), n * sizeof(double));
+    for (size_t i = 0; i < nn; ++i) h[5 * nn + i] = 1.0;
+    memset(h + 6 * nn, 1, nn);
+    double *d = s->d.as<double>();
+    s->d_range = d; s->d_angle = d + nn; s->d_x = d + 2 * nn; s->d_y = d + 3 * nn; s->d_w = d + 4 * nn; s->d_f = d + 5 * nn;
+    s->d_occ = (uint8_t *)(d + 6 * nn);
+    SG_CUDA(ctx, cudaMemcpyAsync(d, h, nn * 6 * sizeof(double) + nn, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->cand.scan == s) ctx->cand.kind = -1;
+  }
+  return SLAMGPU_OK;
+}
+
 // a score-only snapshot of a host-side map: the caller evaluated its own ObservationImpactEstimator per
 // cell (any cell class works), the kernels only ever gather this LUT
 __global__ void k_pad_lut(const double *__restrict__ src, int w, int h, double *__restrict__ lut, int pitch, double unknown_value) {

@@ -181,5 +181,7 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
                          const double *init, const uint8_t *active, uint32_t max_failed_rounds, double tr, double rot,
                          double *out8, double *log, int log_cap, int *served);
 int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);
+int sg_scans_upload_xy(slamgpu_ctx *ctx, slamgpu_scan *const *scans, int count, int32_t n, const double *xs, const double *ys,
+                       const double *weight);
 void sg_p2p_setup(slamgpu_ctx *ctx);
 void sg_p2p_teardown(slamgpu_ctx *ctx);

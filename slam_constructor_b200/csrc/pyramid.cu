@@ -308,6 +308,34 @@ __global__ void k_ordered_sums(const MatchRec *__restrict__ matches, const ScanV
   out[m] = sv.wsum == 0 ? NAN : sg::div(total, sv.wsum);
 }
 
+// the same with the rows staged in shared memory: G matches per block, coalesced loads, then one lane per match (each
+// in its own warp) runs the chain of adds from shared memory with the loads issued eight ahead
+__global__ void __launch_bounds__(256) k_ordered_sums_staged(const MatchRec *__restrict__ matches, const ScanView *__restrict__ scans,
+                                                             int n_max, const double *__restrict__ terms, long long M, int G,
+                                                             double *__restrict__ out) {
+  extern __shared__ double sh_rows[];  // [G][n_max]
+  const long long m0 = (long long)blockIdx.x * G;
+  const int nm = (int)min((long long)G, M - m0);
+  const double *src = terms + (size_t)m0 * n_max;
+  for (int e = threadIdx.x; e < nm * n_max; e += blockDim.x) sh_rows[e] = src[e];
+  __syncthreads();
+  const int g = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) != 0 || g >= nm) return;
+  const ScanView sv = scans[matches[m0 + g].scan_id];
+  const double *t = sh_rows + (size_t)g * n_max;
+  double total = 0;
+  int i = 0;
+  for (; i + 8 <= sv.n; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = t[i + u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) total = sg::add(total, v[u]);
+  }
+  for (; i < sv.n; ++i) total = sg::add(total, t[i]);
+  out[m0 + g] = sv.wsum == 0 ? NAN : sg::div(total, sv.wsum);
+}
+
 MapView level_view(const slamgpu_map *m, int oie) {
   MapView v;
   v.lut = m->d_lut[oie]; v.cells = m->d_cells;
@@ -566,22 +594,42 @@ extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *sc
   const int64_t m1 = shard ? std::min<int64_t>(M, m0 + chunk) : M;
   const int64_t Ml = m1 - m0;
   const int64_t Mpad = shard ? chunk * ctx->nranks : M;
-  if (p->views.reserve(sizeof(MapView) * L) != SLAMGPU_OK || p->matches.reserve(sizeof(MatchRec) * M) != SLAMGPU_OK ||
-      p->scans.reserve(sizeof(ScanView) * n_scans) != SLAMGPU_OK || p->terms.reserve(sizeof(double) * std::max<int64_t>(Ml, 1) * n_max) != SLAMGPU_OK ||
+  // one staging block {views | scans | matches} through pinned memory: one copy per call
+  auto up8 = [](size_t b) { return (b + 63) & ~(size_t)63; };
+  const size_t off_s = up8(sizeof(MapView) * L), off_m = off_s + up8(sizeof(ScanView) * n_scans);
+  const size_t stage_bytes = off_m + sizeof(MatchRec) * M;
+  if (p->views.reserve(stage_bytes) != SLAMGPU_OK || p->terms.reserve(sizeof(double) * std::max<int64_t>(Ml, 1) * n_max) != SLAMGPU_OK ||
       p->bounds.reserve(sizeof(double) * Mpad) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "score_windows buffers");
-  SG_CUDA(ctx, cudaMemcpyAsync(p->views.p, views.data(), sizeof(MapView) * L, cudaMemcpyHostToDevice, ctx->stream));
-  SG_CUDA(ctx, cudaMemcpyAsync(p->matches.p, mr.data(), sizeof(MatchRec) * M, cudaMemcpyHostToDevice, ctx->stream));
-  SG_CUDA(ctx, cudaMemcpyAsync(p->scans.p, sv.data(), sizeof(ScanView) * n_scans, cudaMemcpyHostToDevice, ctx->stream));
+  void *hp;
+  SG_TRY(sg_pinned(ctx, stage_bytes + sizeof(double) * M, &hp));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging may still be in flight
+  memcpy(hp, views.data(), sizeof(MapView) * L);
+  memcpy((char *)hp + off_s, sv.data(), sizeof(ScanView) * n_scans);
+  memcpy((char *)hp + off_m, mr.data(), sizeof(MatchRec) * M);
+  SG_CUDA(ctx, cudaMemcpyAsync(p->views.p, hp, stage_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const MapView *d_views = p->views.as<MapView>();
+  const ScanView *d_scans = (const ScanView *)((const char *)p->views.p + off_s);
+  const MatchRec *d_matches = (const MatchRec *)((const char *)p->views.p + off_m);
+  double *h_bounds = (double *)((char *)hp + stage_bytes);
   if (Ml > 0) {
     dim3 grd((n_max + 127) / 128, (unsigned)Ml);
     cudaEventRecord(ctx->evk0, ctx->stream);
-    k_window_terms<<<grd, 128, 0, ctx->stream>>>(p->matches.as<MatchRec>() + m0, p->scans.as<ScanView>(), p->views.as<MapView>(), n_max,
-                                                  p->terms.as<double>());
+    k_window_terms<<<grd, 128, 0, ctx->stream>>>(d_matches + m0, d_scans, d_views, n_max, p->terms.as<double>());
     cudaEventRecord(ctx->evk1, ctx->stream);
     ctx->evk_valid = true;
-    k_ordered_sums<<<(unsigned)((Ml + 63) / 64), 64, 0, ctx->stream>>>(p->matches.as<MatchRec>() + m0, p->scans.as<ScanView>(), n_max,
-                                                                      p->terms.as<double>(), Ml, p->bounds.as<double>() + m0);
+    // rows staged in shared memory when up to 8 of them fit (they do below ~5600 points); else straight from global
+    const int G = (int)std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)n_max * sizeof(double)));
+    if (G >= 1) {
+      const size_t smem = (size_t)G * n_max * sizeof(double);
+      static bool attr_set = false;
+      if (!attr_set) { cudaFuncSetAttribute(k_ordered_sums_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+      k_ordered_sums_staged<<<(unsigned)((Ml + G - 1) / G), 256, smem, ctx->stream>>>(d_matches + m0, d_scans, n_max, p->terms.as<double>(), Ml, G,
+                                                                                   p->bounds.as<double>() + m0);
+    } else {
+      k_ordered_sums<<<(unsigned)((Ml + 63) / 64), 64, 0, ctx->stream>>>(d_matches + m0, d_scans, n_max, p->terms.as<double>(), Ml,
+                                                                        p->bounds.as<double>() + m0);
+    }
     ctx->launches += 2;
     SG_CUDA(ctx, cudaGetLastError());
   }
@@ -591,8 +639,9 @@ extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *sc
     int r = sg_nccl_allgather(ctx->comm, b + chunk * ctx->rank, b, sizeof(double) * chunk, ctx->stream, &err);  // in place
     if (r != SLAMGPU_OK) return sg_fail(ctx, r, "%s", err.c_str());
   }
-  SG_CUDA(ctx, cudaMemcpyAsync(out_bounds, p->bounds.p, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaMemcpyAsync(h_bounds, p->bounds.p, sizeof(double) * M, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out_bounds, h_bounds, sizeof(double) * M);
   return SLAMGPU_OK;
 }
 
@@ -664,15 +713,16 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
     SG_TRY(slamgpu_scan_create(ctx, &s));
     pool.push_back(s);
   }
-  std::vector<double> xs(std::max(n, 1)), ys(std::max(n, 1));
+  std::vector<double> xs(std::max<size_t>((size_t)n * rots.size(), 1)), ys(xs.size());
   for (size_t k = 0; k < rots.size(); ++k) {
     const double base = rots[k].rot + pose[2];
+    double *x = xs.data() + k * (size_t)n, *y = ys.data() + k * (size_t)n;
     for (int i = 0; i < n; ++i) {
-      xs[i] = 0 + range[i] * std::cos(base + angle[i]);
-      ys[i] = 0 + range[i] * std::sin(base + angle[i]);
+      x[i] = 0 + range[i] * std::cos(base + angle[i]);
+      y[i] = 0 + range[i] * std::sin(base + angle[i]);
     }
-    SG_TRY(slamgpu_scan_upload(pool[k], n, 1, xs.data(), ys.data(), nullptr, nullptr, weight));
   }
+  SG_TRY(sg_scans_upload_xy(ctx, pool.data(), (int)rots.size(), n, xs.data(), ys.data(), weight));
   int64_t n_scored = 0, n_calls = 0, n_branches = 0;
   std::vector<int32_t> sid;
   std::vector<double> win, bounds;

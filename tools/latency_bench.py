@@ -39,7 +39,28 @@ def pyramid_numbers(ctx, size=4096, scale=0.025):
     levels = pyr.levels()
     by = 4.0 / 3.0 * size * size * 2 * 8 * 2  # read + write of every level's records
     pyr.close(); gm.close()
-    return {"grid": [size, size], "levels": levels, "build_ms": round(ms, 3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
+    # incremental maintenance on a map built from scans: one scan inserted into the fine map and folded up through
+    # every level (K2/K3 + K4)
+    gm = sg.GridMap(ctx, size, size, scale, sg.CELL_MEAN, sg.GROW_PLAIN)
+    pyr = sg.Pyramid(ctx, gm, sg.OIE_DISCREPANCY)
+    pose = np.array([0.317, -0.223, 0.1])
+    r, a = bench.room_ranges(rng, 1081, 1.5 * np.pi, size * scale * 0.35, size * scale * 0.3, pose, 0.01)
+    scan = sg.Scan(ctx, r, a)
+    est = sg.estimator(sg.EST_CONST)
+    for k in range(6):
+        cells = pyr.append_scan(scan, pose + [0.01 * k, -0.01 * k, 0.002 * k], 0.9, 0, est, blur=0.3)
+    l0 = ctx.launch_count()
+    upd = timeit(lambda: pyr.append_scan(scan, pose, 0.9, 0, est, blur=0.3), n=20, warm=3)
+    launches = (ctx.launch_count() - l0) / 23
+    # BF-M3RSM match on it (13 levels, +-0.5 m, +-5 deg @0.5 deg = 21 rotations)
+    params = sg.spe_params(sg.OOPE_MAX, sg.OIE_DISCREPANCY, prerotated=1)
+    init = pose + [0.12, -0.08, 0.03]
+    _, _, st = pyr.match_m3rsm(r, a, init, params, 0.5, 0.5, np.deg2rad(5), np.deg2rad(0.5), 0.05)
+    m3 = timeit(lambda: pyr.match_m3rsm(r, a, init, params, 0.5, 0.5, np.deg2rad(5), np.deg2rad(0.5), 0.05), n=10, warm=2)
+    pyr.close(); gm.close(); scan.close()
+    return {"grid": [size, size], "levels": levels, "build_ms": round(ms, 3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9,
+            "append_scan_us": round(upd, 1), "append_scan_cells": int(cells), "append_scan_launches": round(launches, 1),
+            "m3rsm_match_us": round(m3, 1), "m3rsm_stats": st}
 
 
 def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=360):
