@@ -571,13 +571,13 @@ extern "C" int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian
       s->angle[i] = std::atan2(b[i], a[i]);
     } else {
       s->range[i] = a[i]; s->angle[i] = b[i];
-      s->x[i] = a[i] * std::cos(b[i]);
-      s->y[i] = a[i] * std::sin(b[i]);
+      s->x[i] = NAN; s->y[i] = NAN;  // derived on demand (sg_scan_ensure_xy): 2 libm calls per point nobody may need
     }
     s->weight[i] = weight ? weight[i] : 1.0 / n;
     s->factor[i] = factor ? factor[i] : 1.0;
     s->occ[i] = occ ? occ[i] : 1;
   }
+  s->xy_valid = cartesian != 0;
   double ws = 0;
   for (int i = 0; i < n; ++i) ws += s->weight[i];  // weighted_mean_point_probability_spe.h:125
   s->wsum = ws;
@@ -600,6 +600,24 @@ extern "C" int slamgpu_scan_upload(slamgpu_scan *s, int32_t n, int32_t cartesian
   s->d_occ = (uint8_t *)(d + 6 * nn);
   SG_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (ctx->cand.scan == s) ctx->cand.kind = -1;  // staged candidates depend on the scan
+  return SLAMGPU_OK;
+}
+
+// x = r*cos(a), y = r*sin(a) of a polar scan (ScanPoint2D::x / y, sensor_data.h:47-70), for the paths that read points
+int sg_scan_ensure_xy(slamgpu_scan *s) {
+  if (!s || s->xy_valid) return SLAMGPU_OK;
+  slamgpu_ctx *ctx = s->ctx;
+  const int n = s->n;
+  for (int i = 0; i < n; ++i) {
+    s->x[i] = s->range[i] * std::cos(s->angle[i]);
+    s->y[i] = s->range[i] * std::sin(s->angle[i]);
+  }
+  s->xy_valid = true;
+  if (n > 0) {
+    SG_CUDA(ctx, cudaSetDevice(ctx->device));
+    SG_CUDA(ctx, cudaMemcpyAsync(s->d_x, s->x.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(s->d_y, s->y.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
   return SLAMGPU_OK;
 }
 

@@ -55,6 +55,9 @@ struct Candidates {  // a staged candidate set (device resident)
   bool multi = false;
   DevBuf views, view_id;
   // GMapping OOPE cache chain (spe.gm_cache == 2): predecessor of each pose, entry states, state after each pose
+  std::vector<int32_t> h_groups;          // grid staging kept alive past the asynchronous uploads
+  std::vector<double> h_axes;             // {xs | ys | thetas}
+  const double *p_xs = nullptr, *p_ys = nullptr, *p_ts = nullptr;  // views into d_xs
   int user_rows = 0;  // slamgpu_ctx_set_option("grid_rows")
   bool gm_chain = false;
   DevBuf gm_pred, gm_in, gm_out;
@@ -125,6 +128,7 @@ struct slamgpu_scan {
   std::vector<double> range, angle, x, y, weight, factor;
   std::vector<uint8_t> occ;
   double wsum = 0;  // sequential sum of weights (pose independent)
+  bool xy_valid = true;  // polar uploads derive x, y (libm, host) only when a pre-rotated / window path asks: sg_scan_ensure_xy
   // device: one block of 6*n doubles + n bytes
   DevBuf d;
   double *d_range = nullptr, *d_angle = nullptr, *d_x = nullptr, *d_y = nullptr, *d_w = nullptr, *d_f = nullptr;
@@ -183,5 +187,6 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
 int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);
 int sg_scans_upload_xy(slamgpu_ctx *ctx, slamgpu_scan *const *scans, int count, int32_t n, const double *xs, const double *ys,
                        const double *weight);
+int sg_scan_ensure_xy(slamgpu_scan *s);
 void sg_p2p_setup(slamgpu_ctx *ctx);
 void sg_p2p_teardown(slamgpu_ctx *ctx);

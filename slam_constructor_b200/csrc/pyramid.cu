@@ -565,6 +565,7 @@ extern "C" int slamgpu_score_windows(slamgpu_pyramid *p, slamgpu_scan *const *sc
   for (int k = 0; k < n_scans; ++k) {
     const slamgpu_scan *s = scans[k];
     if (!s || s->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan %d is NULL or belongs to another ctx", k);
+    SG_TRY(sg_scan_ensure_xy(scans[k]));
     sv[k] = ScanView{s->d_x, s->d_y, s->d_w, s->d_f, s->n, s->has_factor ? 1 : 0, s->wsum};
     n_max = std::max(n_max, s->n);
   }

@@ -1151,6 +1151,7 @@ MapView make_view(const slamgpu_map *m, int oie) {
 
 int check_spe(slamgpu_ctx *ctx, const slamgpu_scan *scan, const slamgpu_spe_params *p) {
   if (!scan || !p) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan/params is NULL");
+  if (p->prerotated) SG_TRY(sg_scan_ensure_xy(const_cast<slamgpu_scan *>(scan)));  // pre-rotated scoring reads the points as (x, y)
   if (scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan belongs to another ctx");
   if (p->oope < 0 || p->oope > SLAMGPU_OOPE_GMAPPING) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oope %d", p->oope);
   if (p->oie < 0 || p->oie > 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oie %d", p->oie);
@@ -1293,7 +1294,8 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   int64_t r0, r1;
   slice_of(ctx, rows, &r0, &r1);
   c.p0 = r0 * nx; c.p1 = r1 * nx;
-  std::vector<int32_t> groups;
+  std::vector<int32_t> &groups = c.h_groups;
+  groups.clear();
   c.t_lo = (int32_t)(r0 / ny);
   c.t_hi = r1 > r0 ? (int32_t)((r1 - 1) / ny) : c.t_lo;
   for (int32_t t = c.t_lo; t <= c.t_hi && r1 > r0; ++t) {
@@ -1351,10 +1353,14 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     SG_TRY(upload(ctx, c.blocks, blocks3.data(), blocks3.size() * sizeof(int32_t)));
     SG_TRY(upload(ctx, c.blk_rows, blk_rows3.data(), blk_rows3.size() * sizeof(int32_t)));
   }
-  SG_TRY(upload(ctx, c.d_xs, c.h_xs.data(), nx * sizeof(double)));
-  SG_TRY(upload(ctx, c.d_ys, c.h_ys.data(), ny * sizeof(double)));
-  SG_TRY(upload(ctx, c.d_thetas, c.h_ts.data(), nt * sizeof(double)));
-  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // the three axes travel as one block {xs | ys | thetas}; every source is a member vector, so nothing waits here
+  c.h_axes.resize((size_t)nx + ny + nt);
+  std::copy(xs, xs + nx, c.h_axes.begin());
+  std::copy(ys, ys + ny, c.h_axes.begin() + nx);
+  std::copy(thetas, thetas + nt, c.h_axes.begin() + nx + ny);
+  SG_TRY(upload(ctx, c.d_xs, c.h_axes.data(), c.h_axes.size() * sizeof(double)));
+  c.p_xs = c.d_xs.as<double>(); c.p_ys = c.p_xs + nx; c.p_ts = c.p_ys + ny;
+  if (c.grid_variant == 3) SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // blocks3 / blk_rows3 are locals
   size_t tb = std::max<size_t>((size_t)nt * N, 1) * sizeof(double);
   if (c.trc.reserve(tb) != SLAMGPU_OK || c.trs.reserve(tb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trig table");
   c.trig_is_host = false;
@@ -1512,7 +1518,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
     const int nt_loc = c.t_hi - c.t_lo + 1;
     if (device_trig && N > 0) {
       long long tot = (long long)c.nt * N;
-      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.d_thetas.as<double>(), c.nt, s->d_range, s->d_angle,
+      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.p_ts, c.nt, s->d_range, s->d_angle,
                                                                             N, N, 1, c.trc.as<double>(), c.trs.as<double>());
       SG_LAUNCHED(ctx);
     }
@@ -1520,7 +1526,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
     nblk = (int)((threads + 127) / 128);
     if (nblk > 0 && N > 0) {
       GridIdxArgs ia;
-      ia.trc = c.trc.as<double>(); ia.trs = c.trs.as<double>(); ia.xs = c.d_xs.as<double>(); ia.ys = c.d_ys.as<double>();
+      ia.trc = c.trc.as<double>(); ia.trs = c.trs.as<double>(); ia.xs = c.p_xs; ia.ys = c.p_ys;
       ia.nx = c.nx; ia.ny = c.ny; ia.nyp = c.nyp; ia.N = N; ia.t_lo = c.t_lo; ia.nt_loc = nt_loc;
       ia.w = map->w; ia.h = map->h; ia.ox = map->ox; ia.oy = map->oy; ia.pitch = map->pitch; ia.scale = map->scale;
       ia.guard = device_trig ? 1 : 0;
