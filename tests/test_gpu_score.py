@@ -345,3 +345,24 @@ def test_whole_hill_climbing_match_in_one_launch(sg, gpu, mode):
         assert log3 is None and np.array_equal(pose3, pose) and tested3 == tested
         gsc.close()
     gm.close()
+
+
+def test_measurement_aids(sg, gpu):
+    """slamgpu_probe_gather returns a plausible rate; the grid_rows experiment option forces the rows per thread without
+    changing a single score"""
+    assert gpu.probe_gather(8 << 20, 64) > 1e9
+    rng = np.random.default_rng(1800)
+    om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_MEAN, 91)
+    xs = p0[0] + 0.02 * (np.arange(60) - 30); ys = p0[1] + 0.02 * (np.arange(50) - 25); ts = p0[2] + 0.01 * (np.arange(6) - 3)
+    base, idx0, best0 = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+    for rows in (2, 4, 8):
+        gpu.set_option("grid_rows", rows)
+        try:
+            got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+        finally:
+            gpu.set_option("grid_rows", 0)
+        assert gpu.score_stats()["rows_per_thread"] == rows
+        assert np.array_equal(got, base) and (idx, best) == (idx0, best0)
+    with pytest.raises(sg.SlamGpuError):
+        gpu.set_option("grid_rows", 3)
+    gm.close(); gsc.close()
