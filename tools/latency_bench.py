@@ -63,8 +63,9 @@ def pyramid_numbers(ctx, size=4096, scale=0.025):
             "m3rsm_match_us": round(m3, 1), "m3rsm_stats": st}
 
 
-def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=360):
-    """GMapping-shaped step: n particles, each with its own map; one batched scan insertion, one lock-step hill climb"""
+def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=720):
+    """BASELINE configs[3]: 256 particles x 720 beams, each particle with its own map; one batched scan insertion, the hill
+    climbing of all particles (one launch without the OOPE cache; lock step with the cache carried as upstream does)"""
     rng = np.random.default_rng(7)
     parts = sg.Particles(ctx, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
     est = sg.estimator(sg.EST_CONST)
@@ -76,10 +77,14 @@ def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=360):
     upd = timeit(lambda: parts.append_scan(scan, poses, est=est), n=10, warm=2)
     params = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1)
     hc = timeit(lambda: parts.match_hc(scan, params, poses), n=10, warm=2)
+    params_c = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2)
+    hc_c = timeit(lambda: parts.match_hc(scan, params_c, poses), n=5, warm=1)
+    _, _, tested = parts.match_hc(scan, params_c, poses)
     parts.close(); scan.close()
     tot = int(np.sum(cells))
     return {"particles": n, "grid": [size, size], "beams": beams, "append_scan_us": round(upd, 1), "cells_per_step": tot,
-            "cell_updates_per_s": tot / (upd * 1e-6), "hill_climb_us": round(hc, 1)}
+            "cell_updates_per_s": tot / (upd * 1e-6), "hill_climb_us": round(hc, 1), "hill_climb_carried_cache_us": round(hc_c, 1),
+            "hill_climb_poses_tested": int(np.sum(tested))}
 
 
 def measure(ctx):
