@@ -254,14 +254,17 @@ __global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigne
                                                                    const unsigned *__restrict__ ghist, int nb) {
   constexpr int NW = SG_SORT_THREADS / 32;
   __shared__ unsigned wcount[NW][256];
-  __shared__ unsigned gbase[256];
+  __shared__ unsigned gbase[256];     // global position of this tile's first element of each digit
+  __shared__ unsigned dstart[257];    // position of each digit's run inside the tile, once sorted
+  __shared__ unsigned skey[SG_SORT_TILE], sval[SG_SORT_TILE];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int k = threadIdx.x; k < NW * 256; k += SG_SORT_THREADS) (&wcount[0][0])[k] = 0;
   gbase[threadIdx.x] = ghist[(size_t)threadIdx.x * nb + blockIdx.x];
   __syncthreads();
   // each warp owns a contiguous 256-element span of the tile and walks it in order, 32 at a time,
   // so ranks within a digit follow the input order (stability)
-  const long long wbase = (long long)blockIdx.x * SG_SORT_TILE + (long long)w * (32 * SG_SORT_ITEMS);
+  const long long tbase = (long long)blockIdx.x * SG_SORT_TILE;
+  const long long wbase = tbase + (long long)w * (32 * SG_SORT_ITEMS);
   unsigned key[SG_SORT_ITEMS], val[SG_SORT_ITEMS], rank[SG_SORT_ITEMS];
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigne
     rank[c] = pre + r;
   }
   __syncthreads();
-  {  // exclusive prefix over the warps of this block, per digit
+  {  // exclusive prefix over the warps of this block, per digit; its total is the digit's count in the tile
     unsigned run = 0;
     const int d = threadIdx.x;
 #pragma unroll
@@ -289,17 +292,45 @@ __global__ void __launch_bounds__(SG_SORT_THREADS) k_radix_scatter(const unsigne
       wcount[ww][d] = run;
       run += t;
     }
+    dstart[d + 1] = run;
+  }
+  if (threadIdx.x == 0) dstart[0] = 0;
+  __syncthreads();
+  if (threadIdx.x < 32) {  // inclusive scan of the 256 digit counts by one warp, 8 per lane
+    unsigned v[8], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { v[u] = dstart[1 + lane * 8 + u]; sum += v[u]; }
+    unsigned x = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += y;
+    }
+    unsigned run = x - sum;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { run += v[u]; dstart[1 + lane * 8 + u] = run; }
   }
   __syncthreads();
+  // the tile, sorted by this digit, in shared memory ...
 #pragma unroll
   for (int c = 0; c < SG_SORT_ITEMS; ++c) {
     long long idx = wbase + c * 32 + lane;
     if (idx < n) {
       unsigned digit = (key[c] >> shift) & 255u;
-      unsigned dst = gbase[digit] + wcount[w][digit] + rank[c];
-      keys_out[dst] = key[c];
-      vals_out[dst] = val[c];
+      unsigned pos = dstart[digit] + wcount[w][digit] + rank[c];
+      skey[pos] = key[c];
+      sval[pos] = val[c];
     }
+  }
+  __syncthreads();
+  // ... then out: neighbouring threads write neighbouring elements of a digit's run (whole sectors, not 4-byte scatters)
+  const int cnt = (int)min((long long)SG_SORT_TILE, n - tbase);
+  for (int e = threadIdx.x; e < cnt; e += SG_SORT_THREADS) {
+    const unsigned k = skey[e];
+    const unsigned digit = (k >> shift) & 255u;
+    const unsigned dst = gbase[digit] + ((unsigned)e - dstart[digit]);
+    keys_out[dst] = k;
+    vals_out[dst] = sval[e];
   }
 }
 
