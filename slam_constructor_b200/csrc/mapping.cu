@@ -87,7 +87,9 @@ struct EstimateArgs {
   int *robot_slot;        // per beam: the slot of its robot-cell update (taken out of the sort), or NULL
 };
 
-__global__ void k_estimate(EstimateArgs a) {
+// AREA = false: the const estimator only (a select); the kernel then does not carry the area estimator's registers
+template <bool AREA>
+__global__ void __launch_bounds__(128) k_estimate(EstimateArgs a) {
   const long long s0 = blockIdx.x * (long long)blockDim.x;
   long long s = s0 + threadIdx.x;
   // beam of a slot: last i with offsets[i] <= s.  Two threads bracket the block's slots with a full binary search,
@@ -122,9 +124,13 @@ __global__ void k_estimate(EstimateArgs a) {
   if (k == bo.count - 1) {
     p = bo.base_p; q = bo.base_q;
   } else {
-    const double sc = a.scale;
-    sg::estimate_occupancy(a.est, ms.shift, ms.px, ms.py, b.wx, b.wy, sg::mul(sc, (double)c.y), sg::mul(sc, (double)(c.y + 1)),
-                           sg::mul(sc, (double)c.x), sg::mul(sc, (double)(c.x + 1)), false, &p, &q);
+    if (AREA) {
+      const double sc = a.scale;
+      sg::estimate_occupancy(a.est, ms.shift, ms.px, ms.py, b.wx, b.wy, sg::mul(sc, (double)c.y), sg::mul(sc, (double)(c.y + 1)),
+                             sg::mul(sc, (double)c.x), sg::mul(sc, (double)(c.x + 1)), false, &p, &q);
+    } else {
+      p = a.est.empty_p; q = a.est.empty_q;  // ConstOccupancyEstimator: a free cell of the ray
+    }
     // wall blur ("hole"), grid_map_scan_adders.h:160-169; distances in cells, squared (exact in double)
     double ddx = (double)(c.x - b.obx), ddy = (double)(c.y - b.oby);
     double d_sq = sg::add(sg::mul(ddx, ddx), sg::mul(ddy, ddy));
@@ -915,7 +921,8 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     ea.robot_slot = ctx->scratch[5].as<int>();
     SG_CUDA(ctx, cudaMemsetAsync(ea.robot_slot, 0xFF, sizeof(int) * (size_t)N, ctx->stream));
   }
-  k_estimate<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
+  if (est->type == SLAMGPU_EST_AREA) k_estimate<true><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
+  else k_estimate<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
   if (robot_split) {

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import bench
 import slam_constructor_b200 as sg
 ctx = sg.Context(0)
-n, size, scale, beams = 256, 1000, 0.05, 360
+n, size, scale, beams = 256, 1000, 0.05, 720
 rng = np.random.default_rng(7)
 parts = sg.Particles(ctx, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
 est = sg.estimator(sg.EST_CONST)
