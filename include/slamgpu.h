@@ -371,7 +371,8 @@ int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *scan, const s
 int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *spe,
                      const double init_pose[3], uint32_t max_failed_rounds, double translation_delta, double rotation_delta,
                      double out_pose[3], double *out_prob, int64_t *out_tested, double *log /* 4*log_cap or NULL */,
-                     int32_t log_cap, int32_t *log_count /* or NULL */);
+                     int32_t log_cap, int32_t *log_count /* or NULL */,
+                     slamgpu_gm_cache *gm_state /* in/out: the estimator's cache when spe->gm_cache == 2; NULL = a new estimator */);
 /* GridMapScanAdder::append_scan into every particle's own map from its own pose (do_update NULL: all); the beams of
  * all particles go through one batched ray-cast, one sort keyed by (map, cell) and one ordered apply */
 int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses /* 3*n */,

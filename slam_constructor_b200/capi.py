@@ -155,7 +155,7 @@ def lib():
     L.slamgpu_score_poses_chained.argtypes = [vp, vp, vp, sp, c_dp, i64, C.POINTER(GmCache), c_dp, C.POINTER(GmCache)]
     L.slamgpu_probe_gather.argtypes = [vp, i64, i32, c_dp]
     L.slamgpu_debug_div.argtypes = [vp, i32, c_dp, c_dp, c_dp]
-    L.slamgpu_match_hc.argtypes = [vp, vp, vp, sp, c_dp, C.c_uint32, dbl, dbl, c_dp, c_dp, c_lp, c_dp, i32, c_ip]
+    L.slamgpu_match_hc.argtypes = [vp, vp, vp, sp, c_dp, C.c_uint32, dbl, dbl, c_dp, c_dp, c_lp, c_dp, i32, c_ip, C.POINTER(GmCache)]
     L.slamgpu_stage_poses.argtypes = [vp, vp, sp, c_dp, i64]
     L.slamgpu_stage_grid.argtypes = [vp, vp, sp, c_dp, i32, c_dp, i32, c_dp, i32]
     L.slamgpu_score_launch.argtypes = [vp, vp, dbl]
@@ -303,13 +303,14 @@ class Context:
         self.check(self.L.slamgpu_debug_div(self.h, len(a), _dp(a), _dp(b), _dp(out)))
         return out
 
-    def match_hc(self, gmap, scan, params, init_pose, max_failed_rounds=6, tr=0.1, rot=0.1, log_cap=0):
+    def match_hc(self, gmap, scan, params, init_pose, max_failed_rounds=6, tr=0.1, rot=0.1, log_cap=0, gm_state=None):
         """HillClimbingScanMatcher::process_scan as one call; returns (pose, prob, tested, log or None)"""
         init, out = _f64(init_pose), np.zeros(3)
         prob, tested, count = C.c_double(), C.c_int64(), C.c_int32()
         log = np.zeros((max(log_cap, 1), 4))
         self.check(self.L.slamgpu_match_hc(self.h, gmap.h, scan.h, C.byref(params), _dp(init), max_failed_rounds, tr, rot, _dp(out),
-                                           C.byref(prob), C.byref(tested), _dp(log) if log_cap else None, log_cap, C.byref(count)))
+                                           C.byref(prob), C.byref(tested), _dp(log) if log_cap else None, log_cap, C.byref(count),
+                                           C.byref(gm_state) if gm_state is not None else None))
         return out, prob.value, tested.value, (log[:min(count.value, log_cap)] if log_cap and count.value >= 0 else None)
 
     def stage_poses(self, scan, params, poses):

@@ -183,7 +183,8 @@ int sg_score_chained(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, con
 // a whole hill-climbing match per instance in one launch; out8 = 8 doubles per instance {x, y, theta, prob, tested, ...}
 int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slamgpu_scan *scan, const slamgpu_spe_params *p,
                          const double *init, const uint8_t *active, uint32_t max_failed_rounds, double tr, double rot,
-                         double *out8, double *log, int log_cap, int *served);
+                         double *out8, double *log, int log_cap, slamgpu_gm_cache *gm_states /* n, in/out: gm_cache == 2 */,
+                         int *served);
 int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);
 int sg_scans_upload_xy(slamgpu_ctx *ctx, slamgpu_scan *const *scans, int count, int32_t n, const double *xs, const double *ys,
                        const double *weight);

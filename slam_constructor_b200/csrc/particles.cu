@@ -109,7 +109,8 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
   if (nl > 0) {
     std::vector<double> out8((size_t)8 * nl);
     SG_TRY(sg_hill_climb_device(ctx, lmaps, nl, scan, spe, init_poses + 3 * (size_t)lo, active ? active + lo : nullptr,
-                                max_failed_rounds, translation_delta, rotation_delta, out8.data(), nullptr, 0, &served));
+                                max_failed_rounds, translation_delta, rotation_delta, out8.data(), nullptr, 0,
+                                p->gm_state.data() + lo, &served));
     if (served) {
       for (int i = 0; i < n; ++i) {
         HillClimb &h = hc[i];
@@ -209,14 +210,16 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
 extern "C" int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *spe,
                                 const double init_pose[3], uint32_t max_failed_rounds, double translation_delta,
                                 double rotation_delta, double out_pose[3], double *out_prob, int64_t *out_tested,
-                                double *log, int32_t log_cap, int32_t *log_count) {
+                                double *log, int32_t log_cap, int32_t *log_count, slamgpu_gm_cache *gm_state) {
   if (!ctx || !map || !scan || !spe || !init_pose || !out_pose || !out_prob) return sg_fail(ctx, SLAMGPU_E_INVALID, "match_hc: NULL argument");
   if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
   if (log_count) *log_count = -1;  // -1: no log was produced (round-by-round path)
   int served = 0;
   double out8[8];
+  slamgpu_gm_cache fresh{0, 0, -1.0};
+  slamgpu_gm_cache *state = gm_state ? gm_state : &fresh;
   SG_TRY(sg_hill_climb_device(ctx, &map, 1, scan, spe, init_pose, nullptr, max_failed_rounds, translation_delta, rotation_delta,
-                              out8, log_cap > 0 ? log : nullptr, log_cap > 0 ? log_cap : 0, &served));
+                              out8, log_cap > 0 ? log : nullptr, log_cap > 0 ? log_cap : 0, state, &served));
   if (served) {
     out_pose[0] = out8[0]; out_pose[1] = out8[1]; out_pose[2] = out8[2];
     *out_prob = out8[3];
@@ -226,10 +229,12 @@ extern "C" int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan
   }
   slamgpu_particles one;
   one.ctx = ctx; one.maps.assign(1, map); one.lo = 0; one.hi = 1; one.chunk = 1;
-  one.gm_state.assign(1, slamgpu_gm_cache{0, 0, -1.0});
+  one.gm_state.assign(1, *state);
   SgLocalScope local_only(ctx);
-  return slamgpu_particles_match_hc(&one, scan, spe, init_pose, nullptr, max_failed_rounds, translation_delta, rotation_delta, out_pose,
-                                    out_prob, out_tested);
+  int r = slamgpu_particles_match_hc(&one, scan, spe, init_pose, nullptr, max_failed_rounds, translation_delta, rotation_delta, out_pose,
+                                     out_prob, out_tested);
+  *state = one.gm_state[0];
+  return r;
 }
 
 extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses,

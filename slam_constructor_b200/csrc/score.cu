@@ -380,24 +380,34 @@ struct HcArgs {
   int N;
   double wsum, win_v, win_h, gm_th;
   int gm_win;
-  double *out;   // 8 per instance: best x, y, theta, probability, poses tested, guard hits, log entries, 0
+  double *out;   // SG_HC_OUT per instance: best x, y, theta, probability, poses tested, guard hits, log entries, 0,
+                 // then the GMapping OOPE cache after the match: cell x, cell y, probability
   double *log;   // per instance: log_cap x {x, y, theta, score}, in evaluation order
   int log_cap;
+  const slamgpu_gm_cache *gm_in;  // per instance, or NULL: the GMapping OOPE's cache is carried through the match
 };
+#define SG_HC_OUT 12
 
 template <int MODE, bool FACTOR>
 __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
-  extern __shared__ double sh_terms[];  // [6][N]
+  extern __shared__ double sh_terms[];  // [6][N] terms (raw probabilities when the cache is carried), then [6][N] cell ids
   __shared__ __align__(8) unsigned char hc_raw[sizeof(HillClimb)];  // (a __shared__ object cannot have initialisers)
+  __shared__ int s_cx, s_cy, s_ecx[6], s_ecy[6];   // carried cache: at the round's entry, and after each of its poses
+  __shared__ double s_cp, s_ecp[6];
+  const bool chain = MODE == SLAMGPU_OOPE_GMAPPING && a.gm_in != nullptr;
+  int2 *sh_cell = reinterpret_cast<int2 *>(sh_terms + (size_t)6 * a.N);
   HillClimb &hc = *reinterpret_cast<HillClimb *>(hc_raw);
   __shared__ double cand[6][3], scores[6];
   __shared__ int s_k, s_logged;
   __shared__ unsigned int s_guard;
   const int inst = blockIdx.x, tid = threadIdx.x, N = a.N;
-  double *out = a.out + 8 * (size_t)inst;
+  double *out = a.out + SG_HC_OUT * (size_t)inst;
   const double *init = a.init + 3 * (size_t)inst;
   if (a.active && !a.active[inst]) {
-    if (tid == 0) { out[0] = init[0]; out[1] = init[1]; out[2] = init[2]; out[3] = NAN; out[4] = 0; out[5] = 0; out[6] = 0; out[7] = 0; }
+    if (tid == 0) {
+      out[0] = init[0]; out[1] = init[1]; out[2] = init[2]; out[3] = NAN; out[4] = 0; out[5] = 0; out[6] = 0; out[7] = 0;
+      if (chain) { out[8] = a.gm_in[inst].cx; out[9] = a.gm_in[inst].cy; out[10] = a.gm_in[inst].prob; }
+    }
     return;
   }
   const MapView &mv = a.views ? a.views[inst] : a.map;
@@ -405,6 +415,7 @@ __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
   if (tid == 0) {
     cand[0][0] = init[0]; cand[0][1] = init[1]; cand[0][2] = init[2];
     s_k = 1; s_guard = 0; s_logged = 0;
+    if (chain) { s_cx = a.gm_in[inst].cx; s_cy = a.gm_in[inst].cy; s_cp = a.gm_in[inst].prob; }
   }
   __syncthreads();
   bool first = true;
@@ -424,6 +435,7 @@ __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
         const int cx = grid_cell(X, rc, s, inv_s, 1, &unsafe_any);
         const int cy = grid_cell(Y, rs, s, inv_s, 1, &unsafe_any);
         prob = MODE == SLAMGPU_OOPE_OBSTACLE ? lut_at(mv, cx, cy) : gmapping_probability(mv, cx, cy, X, Y, a.gm_th, a.gm_win);
+        if (chain) sh_cell[e] = make_int2(cx, cy);
       } else {
         double hv = sg::div(a.win_v, 2.0), hh = sg::div(a.win_h, 2.0);
         bool u;
@@ -433,13 +445,48 @@ __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
         sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
         prob = window_probability<MODE>(mv, X, Y, a.win_v, a.win_h);
       }
-      double term = sg::mul(prob, __ldg(a.w + i));
-      if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+      double term = prob;  // the carried cache replaces raw probabilities: weights are applied while summing
+      if (!chain) {
+        term = sg::mul(prob, __ldg(a.w + i));
+        if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+      }
       sh_terms[e] = term;
     }
     if (unsafe_any) atomicAdd(&s_guard, 1u);
     __syncthreads();
-    if ((tid & 31) == 0 && (tid >> 5) < k) {  // one warp per pose: the sums run side by side
+    if (chain && (tid & 31) == 0 && (tid >> 5) < k) {
+      // GmappingOccupancyObservationPE's cache through the round (see k_pose_sums_chained): pose j enters with the cache
+      // its predecessor left -- found by walking the predecessors' cell ids backwards, the round's entry state at the end
+      const int j = tid >> 5;
+      int cache_x = s_cx, cache_y = s_cy;
+      double cache_p = s_cp;
+      int depth = 0;
+      for (int q = j - 1; q >= 0; --q) {
+        const int2 *c = sh_cell + (size_t)q * N;
+        int jj = N - 1;
+        while (jj > 0 && c[jj - 1].x == c[jj].x && c[jj - 1].y == c[jj].y) --jj;
+        if (jj > 0) { cache_x = c[jj].x; cache_y = c[jj].y; cache_p = sh_terms[(size_t)q * N + jj]; break; }
+        ++depth;
+      }
+      for (int d = depth; d > 0; --d) {  // poses lying in one cell between that state and pose j, oldest first
+        const int r = j - d;
+        const int2 c0 = sh_cell[(size_t)r * N];
+        if (!(c0.x == cache_x && c0.y == cache_y && cache_p != -1)) { cache_x = c0.x; cache_y = c0.y; cache_p = sh_terms[(size_t)r * N]; }
+      }
+      const double *t = sh_terms + (size_t)j * N;
+      const int2 *c = sh_cell + (size_t)j * N;
+      double total = 0;
+      for (int i = 0; i < N; ++i) {
+        double prob = t[i];
+        if (c[i].x == cache_x && c[i].y == cache_y && cache_p != -1) prob = cache_p;
+        else { cache_x = c[i].x; cache_y = c[i].y; cache_p = prob; }
+        double term = sg::mul(prob, __ldg(a.w + i));
+        if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+        total = sg::add(total, term);
+      }
+      scores[j] = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
+      s_ecx[j] = cache_x; s_ecy[j] = cache_y; s_ecp[j] = cache_p;
+    } else if ((tid & 31) == 0 && (tid >> 5) < k) {  // one warp per pose: the sums run side by side
       const int j = tid >> 5;
       const double *t = sh_terms + (size_t)j * N;
       double total = 0;
@@ -456,6 +503,7 @@ __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
     }
     __syncthreads();
     if (tid == 0) {
+      if (chain) { s_cx = s_ecx[k - 1]; s_cy = s_ecy[k - 1]; s_cp = s_ecp[k - 1]; }  // every pose of a round is evaluated
       for (int j = 0; j < k; ++j, ++s_logged)
         if (a.log && s_logged < a.log_cap) {
           double *l = a.log + ((size_t)inst * a.log_cap + s_logged) * 4;
@@ -484,6 +532,7 @@ __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
   if (tid == 0) {
     out[0] = hc.bx; out[1] = hc.by; out[2] = hc.bt; out[3] = hc.best; out[4] = (double)hc.tested;
     out[5] = (double)s_guard; out[6] = (double)s_logged; out[7] = 0;
+    if (chain) { out[8] = s_cx; out[9] = s_cy; out[10] = s_cp; }
   }
 }
 
@@ -1907,14 +1956,16 @@ void launch_hc(slamgpu_ctx *ctx, const HcArgs &a, size_t smem, bool fac) {
 
 int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slamgpu_scan *scan, const slamgpu_spe_params *p,
                          const double *init, const uint8_t *active, uint32_t max_failed_rounds, double tr, double rot,
-                         double *out8, double *log, int log_cap, int *served) {
+                         double *out8, double *log, int log_cap, slamgpu_gm_cache *gm_states, int *served) {
   *served = 0;
   if (!ctx || !maps || n <= 0 || !scan || !p || !init || !out8) return sg_fail(ctx, SLAMGPU_E_INVALID, "hill_climb: bad argument");
   SG_TRY(check_spe(ctx, scan, p));
   const int N = scan->n;
-  const size_t smem = (size_t)6 * std::max(N, 1) * sizeof(double);
+  const bool chain = p->oope == SLAMGPU_OOPE_GMAPPING && p->gm_cache == 2;
+  if (chain && !gm_states) return sg_fail(ctx, SLAMGPU_E_INVALID, "hill_climb: gm_cache == 2 needs the cache states");
+  const size_t smem = (size_t)6 * std::max(N, 1) * (sizeof(double) + (chain ? sizeof(int2) : 0));
   if (p->prerotated || p->trig_mode != SLAMGPU_TRIG_DEVICE || p->oope == SLAMGPU_OOPE_OVERLAP || N <= 0 || smem > 200 * 1024 ||
-      (p->oope == SLAMGPU_OOPE_GMAPPING && p->gm_cache != 0))
+      (p->oope == SLAMGPU_OOPE_GMAPPING && p->gm_cache == 1))
     return SLAMGPU_OK;
   SG_CUDA(ctx, cudaSetDevice(ctx->device));
   std::vector<MapView> views(n);
@@ -1927,12 +1978,14 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
   Candidates &c = ctx->cand;
   // staging: {views | init | active} in one upload, {out | log} in one download
   const size_t vb = sizeof(MapView) * n, ib = sizeof(double) * 3 * n, ab = ((size_t)n + 7) & ~(size_t)7;
-  std::vector<char> stage(vb + ib + ab, 0);
+  const size_t gb = chain ? sizeof(slamgpu_gm_cache) * n : 0;
+  std::vector<char> stage(vb + ib + ab + gb, 0);
   memcpy(stage.data(), views.data(), vb);
   memcpy(stage.data() + vb, init, ib);
   if (active) memcpy(stage.data() + vb + ib, active, n);
+  if (chain) memcpy(stage.data() + vb + ib + ab, gm_states, gb);
   SG_TRY(upload(ctx, c.views, stage.data(), stage.size()));
-  const size_t ob = sizeof(double) * 8 * n, lb = log ? sizeof(double) * 4 * (size_t)log_cap * n : 0;
+  const size_t ob = sizeof(double) * SG_HC_OUT * n, lb = log ? sizeof(double) * 4 * (size_t)log_cap * n : 0;
   if (c.scores.reserve(ob + lb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "hill_climb output");
   HcArgs a;
   a.map = views[0]; a.views = c.views.as<MapView>(); a.n_inst = n;
@@ -1941,7 +1994,8 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
   a.max_failed = max_failed_rounds; a.tr = tr; a.rot = rot;
   a.range = scan->d_range; a.angle = scan->d_angle; a.w = scan->d_w; a.f = scan->d_f; a.N = N; a.wsum = scan->wsum;
   a.win_v = p->win_v; a.win_h = p->win_h; a.gm_th = p->gm_fullness_th; a.gm_win = p->gm_window;
-  a.out = c.scores.as<double>(); a.log = log ? a.out + 8 * (size_t)n : nullptr; a.log_cap = log_cap;
+  a.out = c.scores.as<double>(); a.log = log ? a.out + SG_HC_OUT * (size_t)n : nullptr; a.log_cap = log_cap;
+  a.gm_in = chain ? (const slamgpu_gm_cache *)((const char *)c.views.p + vb + ib + ab) : nullptr;
   cudaEventRecord(ctx->evk0, ctx->stream);
   switch (p->oope) {
     case SLAMGPU_OOPE_OBSTACLE: launch_hc<SLAMGPU_OOPE_OBSTACLE>(ctx, a, smem, scan->has_factor); break;
@@ -1957,11 +2011,16 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
   SG_CUDA(ctx, cudaMemcpyAsync(host.data(), c.scores.p, ob + lb, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < n; ++k)
-    if (host[8 * (size_t)k + 5] != 0) return SLAMGPU_OK;  // a point within the device-trig slack of a cell border: host-trig path
-  memcpy(out8, host.data(), ob);
-  if (log) memcpy(log, host.data() + 8 * (size_t)n, lb);
+    if (host[SG_HC_OUT * (size_t)k + 5] != 0) return SLAMGPU_OK;  // a point within the device-trig slack of a cell border: host-trig path
+  for (int k = 0; k < n; ++k) memcpy(out8 + 8 * (size_t)k, host.data() + SG_HC_OUT * (size_t)k, 8 * sizeof(double));
+  if (chain)
+    for (int k = 0; k < n; ++k) {
+      const double *o = host.data() + SG_HC_OUT * (size_t)k;
+      gm_states[k].cx = (int32_t)o[8]; gm_states[k].cy = (int32_t)o[9]; gm_states[k].prob = o[10];
+    }
+  if (log) memcpy(log, host.data() + SG_HC_OUT * (size_t)n, lb);
   c.stats[0] = 0; c.stats[1] = 5; c.stats[2] = 0;
-  for (int k = 0; k < n; ++k) c.stats[2] += (int64_t)host[8 * (size_t)k + 4] * N;
+  for (int k = 0; k < n; ++k) c.stats[2] += (int64_t)host[SG_HC_OUT * (size_t)k + 4] * N;
   *served = 1;
   return SLAMGPU_OK;
 }

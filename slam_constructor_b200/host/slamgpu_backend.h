@@ -624,7 +624,7 @@ public:
 // HillClimbingScanMatcher (hill_climbing_scan_matcher.h:128-170) on the device.  The enumerator is deterministic, so
 // the whole match -- every round, the accept loop included -- runs in one call (slamgpu_match_hc: one launch for the
 // obstacle / max / mean OOPEs); observers are replayed afterwards from the log of scored poses, in the reference's
-// order.  The GMapping OOPE with its carried cache keeps the speculative batches of the base class.
+// order.  The GMapping OOPE's carried cache rides along in the same launch.
 class CudaHillClimbingScanMatcher : public CudaPoseEnumerationScanMatcher<HillClimbingPoseEnumerator> {
   using Base = CudaPoseEnumerationScanMatcher<HillClimbingPoseEnumerator>;
 public:
@@ -636,7 +636,6 @@ public:
 
   double process_scan(const TransformedLaserScan &raw_scan, const RobotPose &init_pose, const GridMap &map,
                       RobotPoseDelta &pose_delta) override {
-    if (_setup.oope == SLAMGPU_OOPE_GMAPPING && _setup.gm_cache == 2) { return Base::process_scan(raw_scan, init_pose, map, pose_delta); }
     auto prep = prepare(raw_scan, init_pose, map);
     const bool observed = has_observers();
     const int32_t cap = observed ? 8192 : 0;
@@ -645,10 +644,12 @@ public:
     double out[3], prob = 0;
     int64_t tested = 0;
     int32_t count = 0;
+    const slamgpu_gm_cache gm_before = _gm_state;
     _ctx->check(slamgpu_match_hc(_ctx->handle(), prep.map, prep.dscan, &prep.params, init, _max_failed, _tr, _rot, out, &prob, &tested,
-                                 cap ? _log.data() : nullptr, cap, &count));
+                                 cap ? _log.data() : nullptr, cap, &count, &_gm_state));  // (the GMapping OOPE's cache rides along)
     if (observed && (count < 0 || count > cap)) {
-      // no (complete) log to replay: the speculative path calls the observers itself
+      // no (complete) log to replay: the speculative path calls the observers itself (from the cache state before the match)
+      _gm_state = gm_before;
       return Base::process_scan(raw_scan, init_pose, map, pose_delta);
     }
     _poses_tested = (std::size_t)tested;

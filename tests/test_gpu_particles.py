@@ -150,6 +150,7 @@ def test_hill_climbing_with_the_estimators_lifetime_cache(sg, gpu):
         init = truth + rng.normal(0, [0.04, 0.04, 0.02], (n, 3))
         active = np.ones(n, np.uint8); active[k] = 0
         poses, probs, tested = parts.match_hc(gsc, gparams, init, 6, 0.1, 0.1, active=active)
+        assert gpu.score_stats()["variant"] == 5  # the whole match of every particle in one launch, cache included
         for i in range(n):
             if not active[i]:
                 continue
@@ -162,3 +163,24 @@ def test_hill_climbing_with_the_estimators_lifetime_cache(sg, gpu):
         gsc.close()
         truth = truth + [0.02, 0.01, 0.01]
     parts.close()
+
+
+def test_carried_cache_round_by_round_path_agrees(sg, gpu):
+    """host trig forces the lock-step path (one launch per round): same poses, same counts, same cache afterwards"""
+    rng = np.random.default_rng(4300)
+    n = 5
+    parts_a, omaps, truth = _build(sg, gpu, rng, n, ob.CELL_GMAPPING, scans=2)
+    rng = np.random.default_rng(4300)
+    parts_b, _, _ = _build(sg, gpu, rng, n, ob.CELL_GMAPPING, scans=2)
+    for k in range(2):
+        r, a = room_scan(rng, 360, 2 * np.pi, half_w=3.0, half_h=2.5, pose=truth, noise=0.005)
+        gsc = sg.Scan(gpu, r, a)
+        init = truth + rng.normal(0, [0.04, 0.04, 0.02], (n, 3))
+        fast = parts_a.match_hc(gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2), init, 6, 0.1, 0.1)
+        v_fast = gpu.score_stats()["variant"]
+        slow = parts_b.match_hc(gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2, trig=sg.TRIG_HOST), init, 6, 0.1, 0.1)
+        assert v_fast == 5 and gpu.score_stats()["variant"] != 5
+        assert np.array_equal(fast[0], slow[0]) and np.array_equal(fast[2], slow[2])
+        np.testing.assert_allclose(fast[1], slow[1], rtol=1e-12, atol=0)
+        gsc.close()
+    parts_a.close(); parts_b.close()
