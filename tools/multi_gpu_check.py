@@ -122,6 +122,14 @@ def check_k6(dctx, lctx, out, n=10):
     hd = pd.match_hc(sd, params, init, 6, 0.1, 0.1, active=active)
     hl = pl.match_hc(sl, params, init, 6, 0.1, 0.1, active=active)
     h_ok = all(np.array_equal(x, y, equal_nan=True) for x, y in zip(hd, hl))
+    # the estimator's carried cache (gm_cache = 2): per-particle state on the owning rank, two matches in a row
+    params_c = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2)
+    c_ok = True
+    for _ in range(2):
+        cd_, cl_ = pd.match_hc(sd, params_c, init, 6, 0.1, 0.1), pl.match_hc(sl, params_c, init, 6, 0.1, 0.1)
+        c_ok &= all(np.array_equal(x, y, equal_nan=True) for x, y in zip(cd_, cl_))
+    out["k6_hill_climb_carried_cache"] = {"identical": bool(c_ok)}
+    h_ok &= c_ok
     out["k6_score"] = {"identical": s_ok}
     out["k6_hill_climb"] = {"identical": bool(h_ok), "tested_min": int(np.min(hd[2][active > 0]))}
     # resampling with sources on the other rank, kept-in-place particles, duplicates and dropped ones
