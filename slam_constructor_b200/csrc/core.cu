@@ -96,6 +96,9 @@ static int ctx_create_common(int device, slamgpu_ctx **out) {
     delete ctx;
     return r;
   }
+  // pinned staging sized up front: growing it later (cudaFreeHost + cudaMallocHost) can stall a scan for ~100 ms
+  void *hp;
+  if (sg_pinned(ctx, (size_t)4 << 20, &hp) != SLAMGPU_OK) (void)cudaGetLastError();
   *out = ctx;
   return SLAMGPU_OK;
 }

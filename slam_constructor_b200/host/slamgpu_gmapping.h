@@ -19,6 +19,7 @@
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <random>
 #include <unordered_set>
@@ -111,7 +112,11 @@ public:
   std::size_t heaviest_particle() const { return heaviest(); }
   std::size_t resamplings() const { return _resamplings; }
   // device work of the last handle_observation: particles matched, hill-climbing candidates scored, cells updated
-  struct StepStats { std::size_t matched = 0; int64_t poses_tested = 0, cells_updated = 0; };
+  struct StepStats {
+    std::size_t matched = 0;
+    int64_t poses_tested = 0, cells_updated = 0;
+    double match_ms = 0, insert_ms = 0, resample_ms = 0;  // wall clock of the three device phases
+  };
   const StepStats &last_step() const { return _last; }
 
 protected:
@@ -137,8 +142,10 @@ protected:
       std::vector<double> init(3 * n), best(3 * n), probs(n);
       std::vector<int64_t> tested(n);
       for (std::size_t i = 0; i < n; ++i) { init[3 * i] = _particles[i]->pose.x; init[3 * i + 1] = _particles[i]->pose.y; init[3 * i + 2] = _particles[i]->pose.theta; }
+      const auto t_match = std::chrono::steady_clock::now();
       _ctx->check(slamgpu_particles_match_hc(_parts, dscan, &params, init.data(), active.data(), _props.max_failed_rounds,
                                              _props.translation_delta, _props.rotation_delta, best.data(), probs.data(), tested.data()));
+      _last.match_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_match).count();
       // ---- second half: pose correction, map update decision, weight
       std::vector<uint8_t> do_update(n, 0);
       std::vector<double> poses(3 * n);
@@ -165,8 +172,10 @@ protected:
         _props.adder.observation_quality_estimator->reset(obs.scan);
         for (std::size_t k = 0; k < pts.size(); ++k) { pq[k] = _props.adder.observation_quality_estimator->quality(pts, k); }
         std::vector<int64_t> cells(n);
+        const auto t_ins = std::chrono::steady_clock::now();
         _ctx->check(slamgpu_particles_append_scan(_parts, raw, poses.data(), do_update.data(), obs.quality, 0, &_est,
                                                   _props.adder.blur_distance, _props.adder.max_usable_range, pq.data(), cells.data()));
+        _last.insert_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ins).count();
         for (int64_t c : cells) { _last.cells_updated += c; }
         _view->touched();
       }
@@ -257,7 +266,9 @@ private:
       }
       next.push_back(sampled);
     }
+    const auto t_res = std::chrono::steady_clock::now();
     _ctx->check(slamgpu_particles_resample(_parts, src.data()));
+    _last.resample_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_res).count();
     _particles = std::move(next);
     normalize_weights();
     ++_resamplings;
