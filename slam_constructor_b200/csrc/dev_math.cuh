@@ -26,11 +26,25 @@ SG_DEV double div(double a, double b) { return __ddiv_rn(a, b); }
 // absorbing state has an exact shortcut: a subnormal a is k units of 2^-1074 (k integer), and a / b rounds back to
 // k units whenever |k/b - k| < 1/2, which k*|1 - b| < 1/4 with b >= 1/2 guarantees.  There b is a sum of masses
 // within rounding of 1 and k is 1 or 2, so the shortcut always fires; everything else takes the real division.
-SG_DEV bool is_subnormal(double a) { return a != 0.0 && (((unsigned)__double2hiint(a) >> 20) & 0x7ffu) == 0u; }
+SG_DEV unsigned biased_exponent(double a) { return ((unsigned)__double2hiint(a) >> 20) & 0x7ffu; }
+SG_DEV bool is_tiny(double a) { return a != 0.0 && biased_exponent(a) < 123u; }  // 0 < |a| < 2^-900, subnormals included
 SG_DEV double div_chain(double a, double b) {
-  if ((((unsigned)__double2hiint(a) >> 20) & 0x7ffu) == 0u && b >= 0.5) {  // a is zero or subnormal
-    const double k = (fabs(a) * 0x1p537) * 0x1p537;                       // exact
-    if (fabs(b - 1.0) * k < 0.25) return a;
+  const unsigned ea = biased_exponent(a);
+  if (ea < 123u) {
+    if (ea == 0u && b >= 0.5) {                          // a is zero or subnormal: k units of 2^-1074
+      const double k = (fabs(a) * 0x1p537) * 0x1p537;    // exact
+      if (fabs(b - 1.0) * k < 0.25) return a;
+    }
+    // a tiny but normal quotient: scale the numerator up (exact), divide on the fast path, scale back (exact, because
+    // the result is a normal number)
+    const double aa = fabs(a), ab = fabs(b);
+    if (ab >= 0x1p-60 && ab <= 0x1p60) {
+      const double a600 = aa * 0x1p600;
+      if (a600 >= ab * 0x1p-422) {
+        const double q = __ddiv_rn(a600, ab) * 0x1p-600;
+        return ((a < 0) != (b < 0)) ? -q : q;
+      }
+    }
   }
   return __ddiv_rn(a, b);
 }
@@ -99,10 +113,18 @@ SG_DEV bool rec_is_unknown(int model, const double *r) {
 
 // TBM belief {unknown, empty, occupied, conflict}: src/core/maps/transferable_belief_model.h:63-143
 struct Tbm { double u, e, o, c; };
-// CAREFUL selects div_chain (the exact shortcut for zero / subnormal numerators) for the divisions; the cell update
-// decides once per update whether any mass is in that range, so ordinary cells pay nothing for it
+// CAREFUL selects the divisions with the exact shortcuts for zero / subnormal numerators; the cell update decides once
+// per update whether any mass is in that range, so ordinary cells pay nothing for it.  With a divisor within 2^-5 of
+// one (a sum of masses), a numerator of at most 8 units of 2^-1074 divides to itself: |k/b - k| = k|1 - b|/b < 1/2.
+// That is one predicate per divisor and an integer compare per numerator; anything else goes to div_chain.
+SG_DEV bool near_one(double b) { return fabs(b - 1.0) < 0x1p-5; }
+SG_DEV bool few_units(double a) { return (unsigned long long)__double_as_longlong(a) <= 8ull; }  // +0 .. 8 * 2^-1074
 template <bool CAREFUL>
-SG_DEV double tbm_div(double a, double b) { return CAREFUL ? div_chain(a, b) : __ddiv_rn(a, b); }
+SG_DEV double tbm_div(double a, double b, bool b_near_one) {
+  if (!CAREFUL) return __ddiv_rn(a, b);
+  if (b_near_one && few_units(a)) return a;
+  return div_chain(a, b);
+}
 template <bool CAREFUL = false>
 SG_DEV Tbm tbm_conj(const Tbm &l, const Tbm &r) {
   // t[i|j] += l[i]*r[j] over i, j in {0:u, 1:e, 2:o, 3:c}, accumulated in (i, j) order
@@ -115,14 +137,17 @@ SG_DEV Tbm tbm_conj(const Tbm &l, const Tbm &r) {
   double tot = add(add(add(t[0], t[1]), t[2]), t[3]);
   Tbm out;
   if (tot == 0.0) { out.u = 1.0; out.e = out.o = out.c = 0.0; return out; }
-  out.u = tbm_div<CAREFUL>(t[0], tot); out.e = tbm_div<CAREFUL>(t[1], tot); out.o = tbm_div<CAREFUL>(t[2], tot); out.c = tbm_div<CAREFUL>(t[3], tot);
+  const bool n1 = CAREFUL && near_one(tot);
+  out.u = tbm_div<CAREFUL>(t[0], tot, n1); out.e = tbm_div<CAREFUL>(t[1], tot, n1);
+  out.o = tbm_div<CAREFUL>(t[2], tot, n1); out.c = tbm_div<CAREFUL>(t[3], tot, n1);
   return out;
 }
 template <bool CAREFUL = false>
 SG_DEV void tbm_norm_conflict(Tbm &t) {
   double w = add(add(t.u, t.e), t.o);
   if (w == 0.0) { t.u = 1.0; t.e = t.o = t.c = 0.0; return; }
-  t.u = tbm_div<CAREFUL>(t.u, w); t.e = tbm_div<CAREFUL>(t.e, w); t.o = tbm_div<CAREFUL>(t.o, w); t.c = 0.0;
+  const bool n1 = CAREFUL && near_one(w);
+  t.u = tbm_div<CAREFUL>(t.u, w, n1); t.e = tbm_div<CAREFUL>(t.e, w, n1); t.o = tbm_div<CAREFUL>(t.o, w, n1); t.c = 0.0;
 }
 // aoo2tbm, src/core/maps/tbm_grid_cells.h:57-66
 SG_DEV Tbm aoo2tbm(double p, double q, double quality) {
@@ -156,14 +181,14 @@ SG_DEV void cell_update(int model, double *r, double p, double q, double obx, do
     case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: {
       if (!valid) return;
       Tbm b = {r[2], r[3], r[4], 0.0}, m = aoo2tbm(p, q, quality);
-      // a subnormal mass anywhere: take the divisions with the exact shortcut (see div_chain)
-      const bool careful = is_subnormal(b.u) || is_subnormal(b.e) || is_subnormal(b.o);
+      // a tiny or subnormal mass anywhere: take the divisions with the exact shortcuts (see div_chain)
+      const bool careful = is_tiny(b.u) || is_tiny(b.e) || is_tiny(b.o);
       if (careful) { b = tbm_conj<true>(b, m); tbm_norm_conflict<true>(b); }
       else { b = tbm_conj<false>(b, m); tbm_norm_conflict<false>(b); }
       r[2] = b.u; r[3] = b.e; r[4] = b.o;
       if (model == SLAMGPU_CELL_TBM_CONSISTENT) {
         double qual = add(b.o, b.e);
-        r[0] = careful ? div_chain(b.o, qual) : div(b.o, qual); r[1] = qual;
+        r[0] = careful ? tbm_div<true>(b.o, qual, near_one(qual)) : div(b.o, qual); r[1] = qual;
       } else {
         r[0] = add(b.o, mul(0.5, b.u)); r[1] = 1.0;
       }

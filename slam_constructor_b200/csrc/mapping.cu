@@ -29,6 +29,15 @@
 
 namespace {
 
+// record copy with compile-time indices (a loop bounded by the runtime stride would push the record into local memory)
+#ifndef SG_COPY_REC
+#define SG_COPY_REC(dst, src, stride)                                   \
+  do {                                                                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < SLAMGPU_MAX_STRIDE; ++k_)   \
+      if (k_ < (stride)) (dst)[k_] = (src)[k_];                         \
+  } while (0)
+#endif
+
 #define SG_INVALID_KEY 0xFFFFFFFFu
 
 // ---------------------------------------------------------------- K2
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   SortedAoo cur = a.aoo[j];
   const MapSlot &ms = a.maps[cur.map_id];
   double *cell = ms.cells + (size_t)(key - ms.key_base) * a.stride;
-  for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
+  SG_COPY_REC(r, cell, a.stride);
   for (long long t = j;;) {
     const bool more = t + 1 < a.M && a.keys[t + 1] == key;
     SortedAoo nxt = cur;
@@ -419,13 +428,13 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
     if (a.trace_impact) {
       a.trace_impact[cur.slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
       double *tr = a.trace_rec + (size_t)cur.slot * a.stride;
-      for (int k = 0; k < a.stride; ++k) tr[k] = r[k];
+      SG_COPY_REC(tr, r, a.stride);
     }
     if (!more) break;
     cur = nxt;
     ++t;
   }
-  for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+  SG_COPY_REC(cell, r, a.stride);
 }
 
 // A chain of updates often repeats one observation (const estimator: every beam leaves the same "empty" estimate in
@@ -437,22 +446,72 @@ struct FixedPoint {
   double p, q, quality;
   bool have;
 };
-SG_DEV void chain_update(int model, int stride, double *r, double p, double q, double wx, double wy, double quality, FixedPoint &fx) {
-  (void)stride;
-  const bool tbm = model == SLAMGPU_CELL_TBM_CONSISTENT || model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
-  const bool repeated = tbm && __double_as_longlong(p) == __double_as_longlong(fx.p) && __double_as_longlong(q) == __double_as_longlong(fx.q) &&
-                        __double_as_longlong(quality) == __double_as_longlong(fx.quality);
-  if (!repeated) {  // the common case pays three compares
-    sg::cell_update(model, r, p, q, wx, wy, quality);
-    fx.have = false;
-    fx.p = p; fx.q = q; fx.quality = quality;
-    return;
+// The TBM update (tbm_grid_cells.h:12-19 over transferable_belief_model.h:63-143) for a WARP that carries one cell:
+// every lane holds the belief and does the cheap part (16 products, the ordered sums), but the divisions -- four
+// masses by their total in the conjunction, three by the non-conflict weight in the normalisation, each a ~20
+// instruction dependent sequence behind a slow-path branch -- are spread over lanes 0..3 and handed back by shuffles:
+// one division sequence where the scalar code runs four, then three.  Same operations, same operands, same order of
+// every sum: bit-identical results.  The published fields (probability, quality) are functions of the masses and are
+// derived when somebody needs them (tbm_publish), not once per update.
+SG_DEV void tbm_update_warp(double *r, double p, double q, double quality, int lane) {
+  using namespace sg;
+  if (isnan(p) || isnan(q)) return;  // an invalid occupancy is skipped (uniform over the warp)
+  const Tbm bel = {r[2], r[3], r[4], 0.0}, m = aoo2tbm(p, q, quality);
+  const bool careful = is_tiny(bel.u) || is_tiny(bel.e) || is_tiny(bel.o);
+  const double lb[4] = {bel.u, bel.e, bel.o, bel.c}, rb[4] = {m.u, m.e, m.o, m.c};
+  double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[i | j] = add(t[i | j], mul(lb[i], rb[j]));
+  const double tot = add(add(add(t[0], t[1]), t[2]), t[3]);
+  const int k = lane & 3;
+  Tbm out;
+  if (tot == 0.0) {
+    out.u = 1.0; out.e = out.o = out.c = 0.0;
+  } else {
+    const double num = k == 0 ? t[0] : (k == 1 ? t[1] : (k == 2 ? t[2] : t[3]));
+    const double qv = careful ? tbm_div<true>(num, tot, near_one(tot)) : __ddiv_rn(num, tot);
+    out.u = __shfl_sync(0xffffffffu, qv, 0); out.e = __shfl_sync(0xffffffffu, qv, 1);
+    out.o = __shfl_sync(0xffffffffu, qv, 2); out.c = __shfl_sync(0xffffffffu, qv, 3);
   }
-  if (fx.have) return;  // same observation on a saturated belief: the identity
+  const double w = add(add(out.u, out.e), out.o);  // normalize_conflict
+  if (w == 0.0) {
+    out.u = 1.0; out.e = out.o = 0.0;
+  } else {
+    const double num = k == 0 ? out.u : (k == 1 ? out.e : out.o);
+    const double qv = careful ? tbm_div<true>(num, w, near_one(w)) : __ddiv_rn(num, w);
+    out.u = __shfl_sync(0xffffffffu, qv, 0); out.e = __shfl_sync(0xffffffffu, qv, 1); out.o = __shfl_sync(0xffffffffu, qv, 2);
+  }
+  r[2] = out.u; r[3] = out.e; r[4] = out.o;
+}
+// probability / quality / "known" flag of a TBM record from its masses, as the scalar update leaves them
+SG_DEV void tbm_publish(int model, double *r) {
+  using namespace sg;
+  if (model == SLAMGPU_CELL_TBM_CONSISTENT) {
+    const double qual = add(r[4], r[3]);
+    r[0] = (is_tiny(r[4]) || r[4] == 0.0) ? tbm_div<true>(r[4], qual, near_one(qual)) : div(r[4], qual);
+    r[1] = qual;
+  } else {
+    r[0] = add(r[4], mul(0.5, r[2])); r[1] = 1.0;
+  }
+  r[5] = 1;
+}
+
+// One update of a warp-carried chain.  *dirty: a TBM record whose published fields are behind its masses.
+SG_DEV void chain_update(int model, double *r, double p, double q, double wx, double wy, double quality, FixedPoint &fx, int lane,
+                         bool *dirty) {
+  const bool tbm = model == SLAMGPU_CELL_TBM_CONSISTENT || model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
+  if (!tbm) { sg::cell_update(model, r, p, q, wx, wy, quality); return; }
+  const bool repeated = __double_as_longlong(p) == __double_as_longlong(fx.p) && __double_as_longlong(q) == __double_as_longlong(fx.q) &&
+                        __double_as_longlong(quality) == __double_as_longlong(fx.quality);
+  if (repeated && fx.have) return;  // same observation on a saturated belief: the identity
   // the belief masses (record fields 2..4) are the whole state of a TBM cell: the other fields are functions of them
   const long long u0 = __double_as_longlong(r[2]), e0 = __double_as_longlong(r[3]), o0 = __double_as_longlong(r[4]);
-  sg::cell_update(model, r, p, q, wx, wy, quality);
-  fx.have = u0 == __double_as_longlong(r[2]) && e0 == __double_as_longlong(r[3]) && o0 == __double_as_longlong(r[4]);
+  tbm_update_warp(r, p, q, quality, lane);
+  *dirty |= !(isnan(p) || isnan(q));
+  fx.have = repeated && u0 == __double_as_longlong(r[2]) && e0 == __double_as_longlong(r[3]) && o0 == __double_as_longlong(r[4]);
+  fx.p = p; fx.q = q; fx.quality = quality;
 }
 
 // A warp per long run: the lanes fetch 32 consecutive operand records at once (coalesced, the next 32 already in
@@ -471,8 +530,9 @@ __global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
     const MapSlot &ms = a.maps[mine.map_id];
     double *cell = ms.cells + (size_t)(key - ms.key_base) * a.stride;
     double r[SLAMGPU_MAX_STRIDE];
-    for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
+    SG_COPY_REC(r, cell, a.stride);
     FixedPoint fx{NAN, NAN, NAN, false};
+    bool dirty = false;
     for (int base = 0; base < run.len; base += 32) {
       const int cnt = min(32, run.len - base);
       SortedAoo nxt = mine;
@@ -481,17 +541,19 @@ __global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
         const double p = __shfl_sync(0xffffffffu, mine.p, l), q = __shfl_sync(0xffffffffu, mine.q, l);
         const double wx = __shfl_sync(0xffffffffu, mine.wx, l), wy = __shfl_sync(0xffffffffu, mine.wy, l);
         const double quality = __shfl_sync(0xffffffffu, mine.quality, l);
-        chain_update(a.model, a.stride, r, p, q, wx, wy, quality, fx);
+        chain_update(a.model, r, p, q, wx, wy, quality, fx, lane, &dirty);
+        if (a.trace_impact && dirty) { tbm_publish(a.model, r); dirty = false; }  // a pyramid reads every intermediate record
         if (a.trace_impact && lane == l) {
           a.trace_impact[mine.slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
           double *tr = a.trace_rec + (size_t)mine.slot * a.stride;
-          for (int k = 0; k < a.stride; ++k) tr[k] = r[k];
+          SG_COPY_REC(tr, r, a.stride);
         }
       }
       mine = nxt;
     }
+    if (dirty) tbm_publish(a.model, r);
     if (lane == 0)
-      for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+      SG_COPY_REC(cell, r, a.stride);
   }
 }
 
@@ -517,8 +579,8 @@ __global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
   if (ix < 0 || ix >= ms.w || iy < 0 || iy >= ms.h) return;
   double *cell = ms.cells + ((size_t)iy * ms.w + ix) * a.stride;
   double r[SLAMGPU_MAX_STRIDE];
-  for (int k = 0; k < a.stride; ++k) r[k] = cell[k];
-  bool any = false;
+  SG_COPY_REC(r, cell, a.stride);
+  bool any = false, dirty = false;
   FixedPoint fx{NAN, NAN, NAN, false};
   for (int base = ms.beam_begin; base < ms.beam_end; base += 32) {
     const int i = base + lane;
@@ -536,12 +598,13 @@ __global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
     while (todo) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
-      chain_update(a.model, a.stride, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
-                   __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l), fx);
+      chain_update(a.model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
+                   __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l), fx, lane, &dirty);
     }
   }
+  if (dirty) tbm_publish(a.model, r);
   if (any && lane == 0)
-    for (int k = 0; k < a.stride; ++k) cell[k] = r[k];
+    SG_COPY_REC(cell, r, a.stride);
 }
 
 // ---------------------------------------------------------------- map growth (device side)

@@ -41,6 +41,15 @@ struct slamgpu_pyramid {
 
 namespace {
 
+// record copy with compile-time indices (a loop bounded by the runtime stride would push the record into local memory)
+#ifndef SG_COPY_REC
+#define SG_COPY_REC(dst, src, stride)                                   \
+  do {                                                                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < SLAMGPU_MAX_STRIDE; ++k_)   \
+      if (k_ < (stride)) (dst)[k_] = (src)[k_];                         \
+  } while (0)
+#endif
+
 #define SG_INVALID_KEY 0xFFFFFFFFu
 
 int ge_pow2(int i) {
@@ -183,7 +192,7 @@ __global__ void k_level_gather(FoldGatherArgs a) {
   a.g_impact[t] = a.impact[slot];
   const double *r = a.rec + (size_t)slot * a.stride;
   double *o = a.g_rec + (size_t)t * a.stride;
-  for (int k = 0; k < a.stride; ++k) o[k] = r[k];
+  SG_COPY_REC(o, r, a.stride);
 }
 
 struct FoldArgs {
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
   if (j > 0 && a.keys[j - 1] == key) return;
   double cur[SLAMGPU_MAX_STRIDE];
   double *cell = a.cells + (size_t)key * a.stride;
-  for (int k = 0; k < a.stride; ++k) cur[k] = cell[k];
+  SG_COPY_REC(cur, cell, a.stride);
   bool cur_unknown = sg::rec_is_unknown(a.model, cur);
   double cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
   bool changed = false;
@@ -212,14 +221,14 @@ __global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
     const double x = a.g_impact[t];
     if (!cur_unknown && sg::less_or_equal(x, cur_impact)) { a.alive_next[a.vals[t]] = 0; continue; }
     const double *r = a.g_rec + (size_t)t * a.stride;
-    for (int k = 0; k < a.stride; ++k) cur[k] = r[k];
+    SG_COPY_REC(cur, r, a.stride);
     cur_unknown = sg::rec_is_unknown(a.model, cur);
     cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
     changed = true;
     a.alive_next[a.vals[t]] = 1;
   }
   if (changed)
-    for (int k = 0; k < a.stride; ++k) cell[k] = cur[k];
+    SG_COPY_REC(cell, cur, a.stride);
 }
 
 // ---------------------------------------------------------------- from-scratch build
@@ -234,11 +243,11 @@ struct BuildArgs {
 
 SG_DEV void build_take(const BuildArgs &a, const double *r, double *cur, bool *cur_unknown, double *cur_impact) {
   double rec[SLAMGPU_MAX_STRIDE];
-  for (int k = 0; k < a.stride; ++k) rec[k] = r[k];
+  SG_COPY_REC(rec, r, a.stride);
   if (sg::rec_is_unknown(a.model, rec)) return;  // a cell nobody wrote never propagated
   double x = sg::cell_impact(a.model, a.oie, rec, 0.0, 0.0);
   if (!*cur_unknown && sg::less_or_equal(x, *cur_impact)) return;
-  for (int k = 0; k < a.stride; ++k) cur[k] = rec[k];
+  SG_COPY_REC(cur, rec, a.stride);
   *cur_unknown = false;
   *cur_impact = x;
 }
@@ -248,7 +257,7 @@ __global__ void k_build_level(BuildArgs a) {
   if (ix >= a.dw || iy >= a.dh) return;
   double *cell = a.dst + ((size_t)iy * a.dw + ix) * a.stride;
   double cur[SLAMGPU_MAX_STRIDE];
-  for (int k = 0; k < a.stride; ++k) cur[k] = cell[k];
+  SG_COPY_REC(cur, cell, a.stride);
   bool cur_unknown = true;
   double cur_impact = 0;
   if (a.last) {
@@ -264,7 +273,7 @@ __global__ void k_build_level(BuildArgs a) {
       }
   }
   if (!cur_unknown)
-    for (int k = 0; k < a.stride; ++k) cell[k] = cur[k];
+    SG_COPY_REC(cell, cur, a.stride);
 }
 
 struct RecParam { double v[SLAMGPU_MAX_STRIDE]; };

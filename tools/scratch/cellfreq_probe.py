@@ -19,5 +19,5 @@ for k in o: print(u[k], c[k])
 est = sg.estimator(sg.EST_AREA, occ=(0.95, 0.04), empty=(0.01, 0.003), shift=0.01 * scale)
 for _ in range(3):
     ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3)
-    rec = gm.read_cell(int(np.floor(pose[0] / scale)), int(np.floor(pose[1] / scale)))
-    print("robot cell record", rec)
+    for k in o[:5]:
+        print("  cell", u[k], c[k], "record", gm.read_cell(int(u[k][0]), int(u[k][1])))
