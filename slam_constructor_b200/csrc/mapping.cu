@@ -455,35 +455,31 @@ struct FixedPoint {
 // derived when somebody needs them (tbm_publish), not once per update.
 SG_DEV void tbm_update_warp(double *r, double p, double q, double quality, int lane) {
   using namespace sg;
-  if (isnan(p) || isnan(q)) return;  // an invalid occupancy is skipped (uniform over the warp)
-  const Tbm bel = {r[2], r[3], r[4], 0.0}, m = aoo2tbm(p, q, quality);
-  const bool careful = is_tiny(bel.u) || is_tiny(bel.e) || is_tiny(bel.o);
-  const double lb[4] = {bel.u, bel.e, bel.o, bel.c}, rb[4] = {m.u, m.e, m.o, m.c};
-  double t[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) t[i | j] = add(t[i | j], mul(lb[i], rb[j]));
-  const double tot = add(add(add(t[0], t[1]), t[2]), t[3]);
+  // aoo2tbm (the caller has already skipped invalid occupancies)
+  const double est = mul(q, quality);
+  const double mo = mul(p, est), me = mul(sub(1.0, p), est);
+  const double mu = sub(sub(1.0, mo), me);
+  const double bu = r[2], be = r[3], bo = r[4];
+  const bool careful = is_tiny(bu) || is_tiny(be) || is_tiny(bo);
+  // conjunction: t[i|j] += l[i]*r[j] over i, j in {u, e, o, c} in (i, j) order, with c = 0 on both sides.  The products
+  // with a zero conflict mass are +0 (the masses are finite and non-negative) and adding +0 changes nothing, except
+  // that it turns a -0 sum into +0 -- which a sum of non-negative products never is.  So they are left out.
+  const double tu = add(0.0, mul(bu, mu));
+  const double te = add(add(add(0.0, mul(bu, me)), mul(be, mu)), mul(be, me));
+  const double to = add(add(add(0.0, mul(bu, mo)), mul(bo, mu)), mul(bo, mo));
+  const double tc = add(add(0.0, mul(be, mo)), mul(bo, me));
+  const double tot = add(add(add(tu, te), to), tc);
   const int k = lane & 3;
-  Tbm out;
-  if (tot == 0.0) {
-    out.u = 1.0; out.e = out.o = out.c = 0.0;
-  } else {
-    const double num = k == 0 ? t[0] : (k == 1 ? t[1] : (k == 2 ? t[2] : t[3]));
-    const double qv = careful ? tbm_div<true>(num, tot, near_one(tot)) : __ddiv_rn(num, tot);
-    out.u = __shfl_sync(0xffffffffu, qv, 0); out.e = __shfl_sync(0xffffffffu, qv, 1);
-    out.o = __shfl_sync(0xffffffffu, qv, 2); out.c = __shfl_sync(0xffffffffu, qv, 3);
-  }
-  const double w = add(add(out.u, out.e), out.o);  // normalize_conflict
-  if (w == 0.0) {
-    out.u = 1.0; out.e = out.o = 0.0;
-  } else {
-    const double num = k == 0 ? out.u : (k == 1 ? out.e : out.o);
-    const double qv = careful ? tbm_div<true>(num, w, near_one(w)) : __ddiv_rn(num, w);
-    out.u = __shfl_sync(0xffffffffu, qv, 0); out.e = __shfl_sync(0xffffffffu, qv, 1); out.o = __shfl_sync(0xffffffffu, qv, 2);
-  }
-  r[2] = out.u; r[3] = out.e; r[4] = out.o;
+  double num = k == 0 ? tu : (k == 1 ? te : (k == 2 ? to : tc));
+  double qv = careful ? tbm_div<true>(num, tot, near_one(tot)) : __ddiv_rn(num, tot);
+  double ou = __shfl_sync(0xffffffffu, qv, 0), oe = __shfl_sync(0xffffffffu, qv, 1), oo = __shfl_sync(0xffffffffu, qv, 2);
+  if (tot == 0.0) { ou = 1.0; oe = 0.0; oo = 0.0; }
+  const double w = add(add(ou, oe), oo);  // normalize_conflict
+  num = k == 0 ? ou : (k == 1 ? oe : oo);
+  qv = careful ? tbm_div<true>(num, w, near_one(w)) : __ddiv_rn(num, w);
+  double nu = __shfl_sync(0xffffffffu, qv, 0), ne = __shfl_sync(0xffffffffu, qv, 1), no = __shfl_sync(0xffffffffu, qv, 2);
+  if (w == 0.0) { nu = 1.0; ne = 0.0; no = 0.0; }
+  r[2] = nu; r[3] = ne; r[4] = no;
 }
 // probability / quality / "known" flag of a TBM record from its masses, as the scalar update leaves them
 SG_DEV void tbm_publish(int model, double *r) {
@@ -498,18 +494,17 @@ SG_DEV void tbm_publish(int model, double *r) {
   r[5] = 1;
 }
 
-// One update of a warp-carried chain.  *dirty: a TBM record whose published fields are behind its masses.
-SG_DEV void chain_update(int model, double *r, double p, double q, double wx, double wy, double quality, FixedPoint &fx, int lane,
-                         bool *dirty) {
-  const bool tbm = model == SLAMGPU_CELL_TBM_CONSISTENT || model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
-  if (!tbm) { sg::cell_update(model, r, p, q, wx, wy, quality); return; }
+// One TBM update of a warp-carried chain.  *dirty: the record's published fields are behind its masses.
+SG_DEV void chain_update_tbm(double *r, double p, double q, double quality, FixedPoint &fx, int lane, bool *dirty) {
   const bool repeated = __double_as_longlong(p) == __double_as_longlong(fx.p) && __double_as_longlong(q) == __double_as_longlong(fx.q) &&
                         __double_as_longlong(quality) == __double_as_longlong(fx.quality);
   if (repeated && fx.have) return;  // same observation on a saturated belief: the identity
   // the belief masses (record fields 2..4) are the whole state of a TBM cell: the other fields are functions of them
   const long long u0 = __double_as_longlong(r[2]), e0 = __double_as_longlong(r[3]), o0 = __double_as_longlong(r[4]);
-  tbm_update_warp(r, p, q, quality, lane);
-  *dirty |= !(isnan(p) || isnan(q));
+  if (!(isnan(p) || isnan(q))) {  // an invalid occupancy is skipped (uniform over the warp)
+    tbm_update_warp(r, p, q, quality, lane);
+    *dirty = true;
+  }
   fx.have = repeated && u0 == __double_as_longlong(r[2]) && e0 == __double_as_longlong(r[3]) && o0 == __double_as_longlong(r[4]);
   fx.p = p; fx.q = q; fx.quality = quality;
 }
@@ -518,6 +513,7 @@ SG_DEV void chain_update(int model, double *r, double p, double q, double wx, do
 // flight), then the updates are applied in order with the operands handed round by shuffles.  The chain of dependent
 // cell updates stays sequential (it is the reference's arithmetic), but it no longer waits on a memory round trip per
 // update.  Every lane carries the record, so no lane idles on a broadcast; lane l writes the trace of update l.
+template <bool TBM, bool TRACE>
 __global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -539,11 +535,15 @@ __global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
       if (base + 32 < run.len) nxt = src[min(base + 32 + lane, run.len - 1)];
       for (int l = 0; l < cnt; ++l) {
         const double p = __shfl_sync(0xffffffffu, mine.p, l), q = __shfl_sync(0xffffffffu, mine.q, l);
-        const double wx = __shfl_sync(0xffffffffu, mine.wx, l), wy = __shfl_sync(0xffffffffu, mine.wy, l);
         const double quality = __shfl_sync(0xffffffffu, mine.quality, l);
-        chain_update(a.model, r, p, q, wx, wy, quality, fx, lane, &dirty);
-        if (a.trace_impact && dirty) { tbm_publish(a.model, r); dirty = false; }  // a pyramid reads every intermediate record
-        if (a.trace_impact && lane == l) {
+        if (TBM) {  // (the obstacle position is not part of a TBM update)
+          chain_update_tbm(r, p, q, quality, fx, lane, &dirty);
+        } else {
+          const double wx = __shfl_sync(0xffffffffu, mine.wx, l), wy = __shfl_sync(0xffffffffu, mine.wy, l);
+          sg::cell_update(a.model, r, p, q, wx, wy, quality);
+        }
+        if (TRACE && dirty) { tbm_publish(a.model, r); dirty = false; }  // a pyramid reads every intermediate record
+        if (TRACE && lane == l) {
           a.trace_impact[mine.slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
           double *tr = a.trace_rec + (size_t)mine.slot * a.stride;
           SG_COPY_REC(tr, r, a.stride);
@@ -570,6 +570,7 @@ struct RobotArgs {
   int stride, model;
 };
 
+template <bool TBM>
 __global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
   const int lane = threadIdx.x & 31;
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -598,8 +599,11 @@ __global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
     while (todo) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
-      chain_update(a.model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
-                   __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l), fx, lane, &dirty);
+      if (TBM)
+        chain_update_tbm(r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, quality, l), fx, lane, &dirty);
+      else
+        sg::cell_update(a.model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
+                        __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l));
     }
   }
   if (dirty) tbm_publish(a.model, r);
@@ -1026,7 +1030,9 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     ra.aoo_p = aoo_p; ra.aoo_q = aoo_q; ra.stride = maps[0]->stride; ra.model = maps[0]->model;
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    k_apply_robot<<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
+    const bool tbm_cells = ra.model == SLAMGPU_CELL_TBM_CONSISTENT || ra.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
+    if (tbm_cells) k_apply_robot<true><<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
+    else k_apply_robot<false><<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
     SG_LAUNCHED(ctx);
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
   }
@@ -1054,7 +1060,14 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   SG_CUDA(ctx, cudaMemsetAsync(aa.n_long, 0, 64, ctx->stream));
   cudaEventRecord(ctx->evk0, ctx->stream);
   k_apply<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(aa);
-  k_apply_long<<<ctx->sm_count * 2, 128, 0, ctx->stream>>>(aa);
+  {
+    const bool tbm_cells = aa.model == SLAMGPU_CELL_TBM_CONSISTENT || aa.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
+    const int blocks = ctx->sm_count * 2;
+    if (tbm_cells && trace) k_apply_long<true, true><<<blocks, 128, 0, ctx->stream>>>(aa);
+    else if (tbm_cells) k_apply_long<true, false><<<blocks, 128, 0, ctx->stream>>>(aa);
+    else if (trace) k_apply_long<false, true><<<blocks, 128, 0, ctx->stream>>>(aa);
+    else k_apply_long<false, false><<<blocks, 128, 0, ctx->stream>>>(aa);
+  }
   SG_LAUNCHED(ctx);
   cudaEventRecord(ctx->evk1, ctx->stream);
   ctx->evk_valid = true;
