@@ -41,7 +41,9 @@ struct RayWalker {
     if (cells_nm < n) return false;  // fail-over on fp rounding errors
     double e_x = add(e, e_x_inc), e_y = add(e, e_y_inc);
     double diff = sub(fabs(e_y), fabs(e_x));
-    if (are_equal(diff, 0.0)) {
+    // are_equal(diff, 0.0) (math_utils.h:10-16) is |diff - 0| <= 1e-7 * max(1, |diff|, 0): for |diff| <= 1 the scale is
+    // 1, above 1 the test fails either way -- so it is exactly |diff| <= 1e-7, without the chain of max / multiply
+    if (fabs(diff) <= 1e-7) {
       if (px == endx) py += inc_y;
       else if (py == endy) px += inc_x;
       else { px += inc_x; py += inc_y; }
