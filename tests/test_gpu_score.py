@@ -366,3 +366,24 @@ def test_measurement_aids(sg, gpu):
     with pytest.raises(sg.SlamGpuError):
         gpu.set_option("grid_rows", 3)
     gm.close(); gsc.close()
+
+
+def test_new_entry_points_on_degenerate_inputs(sg, gpu):
+    """an empty scan scores NaN everywhere: hill climbing accepts nothing and still walks its full failed-rounds budget, as
+    the oracle's matcher does; an empty chained pose list is a no-op"""
+    rng = np.random.default_rng(1900)
+    om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_MEAN, 31)
+    empty_g, empty_o = sg.Scan(gpu, np.zeros(0), np.zeros(0)), ob.OracleScan(np.zeros(0), np.zeros(0))
+    m = ob.MatchResult()
+    op = ob.spe_params()
+    ob.orc.orc_match_hill_climbing(om.h_, C.byref(empty_o.s), C.byref(op), *p0, 6, 0.1, 0.1, C.byref(m), None)
+    pose, prob, tested, log = gpu.match_hc(gm, empty_g, sg.spe_params(), p0, 6, 0.1, 0.1, log_cap=64)
+    assert np.array_equal(pose, p0) and np.isnan(prob) and np.isnan(m.best_prob) and tested == m.poses_tested
+    # a budget of zero failed rounds: only the initial pose is scored
+    m0 = ob.MatchResult()
+    ob.orc.orc_match_hill_climbing(om.h_, C.byref(osc.s), C.byref(op), *p0, 0, 0.1, 0.1, C.byref(m0), None)
+    pose, prob, tested, log = gpu.match_hc(gm, gsc, sg.spe_params(), p0, 0, 0.1, 0.1, log_cap=8)
+    assert tested == m0.poses_tested == 1 and prob == m0.best_prob and np.array_equal(pose, p0) and len(log) == 1
+    scores, states = gpu.score_poses_chained(gm, gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_cache=2), np.zeros((0, 3)))
+    assert len(scores) == 0 and len(states) == 0
+    gm.close(); gsc.close(); empty_g.close()
