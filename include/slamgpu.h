@@ -392,6 +392,13 @@ int slamgpu_probe_gather(slamgpu_ctx *ctx, int64_t table_bytes, int32_t loads_pe
  * out[i] = a[i] / b[i] through the division the TBM cell update uses (with its exact shortcut for subnormal
  * numerators): lets the parity tests hold it against the host's IEEE division. */
 int slamgpu_debug_div(slamgpu_ctx *ctx, int32_t n, const double *a, const double *b, double *out);
+/* the hill-climbing enumerator + accept loop (HillClimbingScanMatcher, hill_climbing_scan_matcher.h:10-170) that the
+ * device kernel and the round-by-round path share, run on the host over a caller-supplied scoring function: no GPU
+ * and no ctx needed, so CPU-only tests can hold it against the oracle's sequential matcher */
+typedef double (*slamgpu_score_fn)(const double pose[3], void *user);
+int slamgpu_debug_hill_climb(const double init_pose[3], uint32_t max_failed_rounds, double translation_delta,
+                             double rotation_delta, slamgpu_score_fn score, void *user, double out_pose[3],
+                             double *out_prob, int64_t *out_tested);
 
 #ifdef __cplusplus
 }

@@ -205,6 +205,31 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
   return SLAMGPU_OK;
 }
 
+// Test hook (no GPU, no ctx): the hill-climbing state machine of hill_climb.h -- the one the device kernel and the
+// round-by-round path share -- driven by a caller-supplied scoring function, so that CPU-only tests can hold its
+// enumeration and accept logic against a sequential reference matcher.
+extern "C" int slamgpu_debug_hill_climb(const double init_pose[3], uint32_t max_failed_rounds, double translation_delta,
+                                        double rotation_delta, slamgpu_score_fn score, void *user, double out_pose[3],
+                                        double *out_prob, int64_t *out_tested) {
+  if (!init_pose || !score || !out_pose || !out_prob) return SLAMGPU_E_INVALID;
+  HillClimb h;
+  h.bx = init_pose[0]; h.by = init_pose[1]; h.bt = init_pose[2];
+  h.tr = translation_delta; h.rot = rotation_delta;
+  h.best = score(init_pose, user);
+  h.done = !(0 < max_failed_rounds);
+  while (!h.done) {
+    double c6[6][3], s6[6];
+    const int k = h.next_round(max_failed_rounds, c6);
+    if (k == 0) break;
+    for (int j = 0; j < k; ++j) s6[j] = score(c6[j], user);
+    h.apply(max_failed_rounds, c6, s6, k);
+  }
+  out_pose[0] = h.bx; out_pose[1] = h.by; out_pose[2] = h.bt;
+  *out_prob = h.best;
+  if (out_tested) *out_tested = h.tested;
+  return SLAMGPU_OK;
+}
+
 // HillClimbingScanMatcher::process_scan for ONE matcher and map: the whole match in one launch when the device kernel
 // covers the request, round by round otherwise.  log (optional) receives the candidates in evaluation order.
 extern "C" int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *spe,
