@@ -400,6 +400,13 @@ int slamgpu_debug_hill_climb(const double init_pose[3], uint32_t max_failed_roun
                              double rotation_delta, slamgpu_score_fn score, void *user, double out_pose[3],
                              double *out_prob, int64_t *out_tested);
 
+/* M3RSMEngine's best-first search (m3rsm_engine.h:252-365) as slamgpu_match_m3rsm runs it, over a caller-supplied
+ * bound function: bounds[k] = Match bound of (rotations[k], windows[4k..4k+3] = bot, top, left, right) */
+typedef void (*slamgpu_bounds_fn)(int32_t count, const double *rotations, const double *windows, double *out_bounds, void *user);
+int slamgpu_debug_m3rsm(double x_limit, double y_limit, double rot_limit, double ang_step, double transl_step,
+                        double max_finest_prob_diff, slamgpu_bounds_fn fn, void *user, double out_delta[3], double *out_prob,
+                        int64_t stats[4]);
+
 #ifdef __cplusplus
 }
 #endif

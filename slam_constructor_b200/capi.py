@@ -91,7 +91,7 @@ SYMBOLS = [
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
-    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_match_hc", "slamgpu_debug_div", "slamgpu_debug_hill_climb", "slamgpu_probe_gather", "slamgpu_stage_poses",
+    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_match_hc", "slamgpu_debug_div", "slamgpu_debug_hill_climb", "slamgpu_debug_m3rsm", "slamgpu_probe_gather", "slamgpu_stage_poses",
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",

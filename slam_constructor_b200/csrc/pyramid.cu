@@ -695,44 +695,19 @@ HMatch make_match(double rot, double bot, double top, double left, double right,
 
 }  // namespace
 
+#include <functional>
 #include <queue>
 #include <set>
 #include <unordered_map>
 
-extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *range, const double *angle,
-                                   const double *weight, const double pose[3], const slamgpu_spe_params *spe, double x_limit,
-                                   double y_limit, double rot_limit, double ang_step, double transl_step,
-                                   double max_finest_prob_diff, double out_delta[3], double *out_prob, int64_t stats[4]) {
-  if (!p) return SLAMGPU_E_INVALID;
-  slamgpu_ctx *ctx = p->ctx;
-  if (n < 0 || (n > 0 && (!range || !angle)) || !pose || !spe || !out_delta || !out_prob || !(ang_step > 0))
-    return sg_fail(ctx, SLAMGPU_E_INVALID, "match_m3rsm: bad argument");
-  slamgpu_spe_params sp = *spe;
-  sp.oope = SLAMGPU_OOPE_MAX; sp.prerotated = 1;
-  // ---- rotations in the engine's order (add_scan_matching_request :291-316)
-  struct Rot { double rot; int scan_id; };
-  std::vector<Rot> rots;
-  const double sector = 2 * rot_limit;
-  for (double rd = 0; h_less_or_equal(2 * rd, sector); rd += ang_step)
-    for (double rot : std::set<double>{rd, -rd}) rots.push_back(Rot{rot, (int)rots.size()});
-  // ---- pre-rotated Cartesian copies of the scan: LaserScan2D::to_cartesian(rot + pose.theta)
-  // (src/core/states/sensor_data.h:156-167, RawTrigonometryProvider: cos(base + angle))
-  std::vector<slamgpu_scan *> &pool = p->rot_scans;
-  while (pool.size() < rots.size()) {
-    slamgpu_scan *s = nullptr;
-    SG_TRY(slamgpu_scan_create(ctx, &s));
-    pool.push_back(s);
-  }
-  std::vector<double> xs(std::max<size_t>((size_t)n * rots.size(), 1)), ys(xs.size());
-  for (size_t k = 0; k < rots.size(); ++k) {
-    const double base = rots[k].rot + pose[2];
-    double *x = xs.data() + k * (size_t)n, *y = ys.data() + k * (size_t)n;
-    for (int i = 0; i < n; ++i) {
-      x[i] = 0 + range[i] * std::cos(base + angle[i]);
-      y[i] = 0 + range[i] * std::sin(base + angle[i]);
-    }
-  }
-  SG_TRY(sg_scans_upload_xy(ctx, pool.data(), (int)rots.size(), n, xs.data(), ys.data(), weight));
+namespace {
+struct M3Rot { double rot; int scan_id; };
+// scores M matches: scan (= rotation) id and window {bot, top, left, right} per match -> bounds
+using M3RawScore = std::function<int(const int32_t *scan_id, const double *windows, int64_t M, double *bounds)>;
+
+// M3RSMEngine's best-first search over a scoring function (the K5 kernels, or a host callback in the CPU-only test hook)
+int m3rsm_search(const std::vector<M3Rot> &rots, double x_limit, double y_limit, double transl_step, double max_finest_prob_diff,
+                 const M3RawScore &raw_score, double out_delta[3], double *out_prob, int64_t stats[4]) {
   int64_t n_scored = 0, n_calls = 0, n_branches = 0;
   std::vector<int32_t> sid;
   std::vector<double> win, bounds;
@@ -776,7 +751,7 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
   std::vector<HMatch> ask, spec, tmp;
   const size_t kSpeculate = 192, kPeek = 12;
   auto score = [&](std::vector<HMatch> &ms) -> int {
-    if (ms.empty()) return SLAMGPU_OK;
+    if (ms.empty()) return (int)SLAMGPU_OK;
     ask.clear();
     auto want = [&](const HMatch &m) {
       const Key k = key_of(m);
@@ -804,13 +779,12 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
         win.push_back(m.bot); win.push_back(m.top); win.push_back(m.left); win.push_back(m.right);
       }
       bounds.resize(ask.size());
-      SG_TRY(slamgpu_score_windows(p, pool.data(), (int32_t)rots.size(), sid.data(), win.data(), (int64_t)ask.size(), pose, &sp,
-                                   bounds.data()));
+      { int rc_ = raw_score(sid.data(), win.data(), (int64_t)ask.size(), bounds.data()); if (rc_ != SLAMGPU_OK) return rc_; }
       for (size_t k = 0; k < ask.size(); ++k) known[key_of(ask[k])] = bounds[k];
       n_scored += (int64_t)ask.size(); ++n_calls;
     }
     for (HMatch &m : ms) m.bound = known[key_of(m)];
-    return SLAMGPU_OK;
+    return (int)SLAMGPU_OK;
   };
   // ---- engine state (M3RSMEngine :252-289)
   double best_finest = 0.0;
@@ -821,11 +795,11 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
     std::push_heap(heap.begin(), heap.end());
   };
   std::vector<HMatch> batch;
-  for (const Rot &r : rots) {
+  for (const M3Rot &r : rots) {
     batch.push_back(make_match(r.rot, 0, 0, 0, 0, r.scan_id));
     batch.push_back(make_match(r.rot, -y_limit, y_limit, -x_limit, x_limit, r.scan_id));
   }
-  SG_TRY(score(batch));
+  { int rc_ = score(batch); if (rc_ != SLAMGPU_OK) return rc_; }
   for (const HMatch &m : batch) add_match(m);
   // ---- best-first search (bf_multi_res_scan_matcher.h:44-65, next_best_match :318-333, branch :337-357)
   for (;;) {
@@ -840,10 +814,10 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
       ++n_branches;
       batch.clear();
       expansions(best, batch);
-      SG_TRY(score(batch));
+      { int rc_ = score(batch); if (rc_ != SLAMGPU_OK) return rc_; }
       for (const HMatch &m : batch) add_match(m);
     }
-    if (!found) return sg_fail(ctx, SLAMGPU_E_STATE, "match_m3rsm: the match queue ran empty");
+    if (!found) return SLAMGPU_E_STATE;  // the match queue ran empty
     if (best.is_finest()) {
       out_delta[0] = best.left + best.hside() / 2;
       out_delta[1] = best.bot + best.vside() / 2;
@@ -853,9 +827,72 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
     }
     batch.clear();
     expansions(best, batch);
-    SG_TRY(score(batch));
+    { int rc_ = score(batch); if (rc_ != SLAMGPU_OK) return rc_; }
     for (const HMatch &m : batch) add_match(m);
   }
   if (stats) { stats[0] = n_scored; stats[1] = n_calls; stats[2] = n_branches; stats[3] = (int64_t)rots.size(); }
   return SLAMGPU_OK;
+}
+}  // namespace
+
+extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *range, const double *angle,
+                                   const double *weight, const double pose[3], const slamgpu_spe_params *spe, double x_limit,
+                                   double y_limit, double rot_limit, double ang_step, double transl_step,
+                                   double max_finest_prob_diff, double out_delta[3], double *out_prob, int64_t stats[4]) {
+  if (!p) return SLAMGPU_E_INVALID;
+  slamgpu_ctx *ctx = p->ctx;
+  if (n < 0 || (n > 0 && (!range || !angle)) || !pose || !spe || !out_delta || !out_prob || !(ang_step > 0))
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "match_m3rsm: bad argument");
+  slamgpu_spe_params sp = *spe;
+  sp.oope = SLAMGPU_OOPE_MAX; sp.prerotated = 1;
+  // ---- rotations in the engine's order (add_scan_matching_request :291-316)
+  std::vector<M3Rot> rots;
+  const double sector = 2 * rot_limit;
+  for (double rd = 0; h_less_or_equal(2 * rd, sector); rd += ang_step)
+    for (double rot : std::set<double>{rd, -rd}) rots.push_back(M3Rot{rot, (int)rots.size()});
+  // ---- pre-rotated Cartesian copies of the scan: LaserScan2D::to_cartesian(rot + pose.theta)
+  // (src/core/states/sensor_data.h:156-167, RawTrigonometryProvider: cos(base + angle))
+  std::vector<slamgpu_scan *> &pool = p->rot_scans;
+  while (pool.size() < rots.size()) {
+    slamgpu_scan *s = nullptr;
+    SG_TRY(slamgpu_scan_create(ctx, &s));
+    pool.push_back(s);
+  }
+  std::vector<double> xs(std::max<size_t>((size_t)n * rots.size(), 1)), ys(xs.size());
+  for (size_t k = 0; k < rots.size(); ++k) {
+    const double base = rots[k].rot + pose[2];
+    double *x = xs.data() + k * (size_t)n, *y = ys.data() + k * (size_t)n;
+    for (int i = 0; i < n; ++i) {
+      x[i] = 0 + range[i] * std::cos(base + angle[i]);
+      y[i] = 0 + range[i] * std::sin(base + angle[i]);
+    }
+  }
+  SG_TRY(sg_scans_upload_xy(ctx, pool.data(), (int)rots.size(), n, xs.data(), ys.data(), weight));
+  M3RawScore raw = [&](const int32_t *sid, const double *win, int64_t M, double *bounds) -> int {
+    return slamgpu_score_windows(p, pool.data(), (int32_t)rots.size(), sid, win, M, pose, &sp, bounds);
+  };
+  int rc = m3rsm_search(rots, x_limit, y_limit, transl_step, max_finest_prob_diff, raw, out_delta, out_prob, stats);
+  if (rc == SLAMGPU_E_STATE) return sg_fail(ctx, SLAMGPU_E_STATE, "match_m3rsm: the match queue ran empty");
+  return rc;
+}
+
+// Test hook (no GPU, no ctx): the same search over a caller-supplied bound function, so that CPU-only tests can hold
+// the engine -- queue order, pruning, branching, the speculative filling of every scoring call -- against the
+// reference's BruteForceMultiResolutionScanMatcher.
+extern "C" int slamgpu_debug_m3rsm(double x_limit, double y_limit, double rot_limit, double ang_step, double transl_step,
+                                   double max_finest_prob_diff, slamgpu_bounds_fn fn, void *user, double out_delta[3],
+                                   double *out_prob, int64_t stats[4]) {
+  if (!fn || !out_delta || !out_prob || !(ang_step > 0)) return SLAMGPU_E_INVALID;
+  std::vector<M3Rot> rots;
+  const double sector = 2 * rot_limit;
+  for (double rd = 0; h_less_or_equal(2 * rd, sector); rd += ang_step)
+    for (double rot : std::set<double>{rd, -rd}) rots.push_back(M3Rot{rot, (int)rots.size()});
+  std::vector<double> rv;
+  M3RawScore raw = [&](const int32_t *sid, const double *win, int64_t M, double *bounds) -> int {
+    rv.resize((size_t)M);
+    for (int64_t k = 0; k < M; ++k) rv[k] = rots[sid[k]].rot;
+    fn((int32_t)M, rv.data(), win, bounds, user);
+    return SLAMGPU_OK;
+  };
+  return m3rsm_search(rots, x_limit, y_limit, transl_step, max_finest_prob_diff, raw, out_delta, out_prob, stats);
 }

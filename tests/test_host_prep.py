@@ -65,3 +65,52 @@ def test_hill_climbing_state_machine_against_the_oracle_matcher(sg, budget):
         assert rc == 0
         assert tested.value == m.poses_tested == len(calls)
         assert np.array_equal(out - init, [m.dx, m.dy, m.dth]) and prob.value == m.best_prob
+
+
+@pytest.mark.parametrize("seed,lims", [(80, (0.4, 0.4, 3.0, 0.5, 0.05)), (81, (0.6, 0.3, 2.0, 1.0, 0.1))])
+def test_m3rsm_engine_against_the_reference_matcher(sg, refso, seed, lims):
+    """the host branch-and-bound engine of slamgpu_match_m3rsm (queue order, pruning, branching, the speculative filling of
+    every scoring call), run on the CPU over Match bounds computed by the unmodified reference: it must return what the
+    reference's BruteForceMultiResolutionScanMatcher returns on the same map and scan"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import room_scan
+    rng = np.random.default_rng(seed)
+    rm = ob.RefMap(256, 256, 0.05, ob.CELL_MEAN, ob.GROW_PLAIN, pyramid_oie=ob.OIE_DISCREPANCY)
+    est = ob.estimator(ob.EST_CONST)
+    truth = np.array([0.3, -0.2, 0.1])
+    for k in range(3):
+        pose = truth + rng.normal(0, [0.1, 0.1, 0.05])
+        r, a = room_scan(rng, 200, 2 * np.pi, pose=pose)
+        refso.ref_append_scan(rm.h_, 200, ob.dptr(ob.f64(r)), ob.dptr(ob.f64(a)), ob.u8ptr(np.ones(200, np.uint8)), pose[0], pose[1], pose[2],
+                              1.0, 0, C.byref(est), 0.3, np.inf, 0)
+    xlim, ylim, rot_deg, ang_deg, tstep = lims
+    r, a = room_scan(rng, 90, np.deg2rad(270), pose=truth, noise=0.003)
+    r, a = ob.f64(r), ob.f64(a)
+    init = truth + np.array([0.11, -0.07, np.deg2rad(0.8)])
+    m = ob.MatchResult()
+    oparams = ob.spe_params(ob.OOPE_MAX, ob.OIE_DISCREPANCY)
+    refso.ref_match_bf_m3rsm(rm.h_, len(r), ob.dptr(r), ob.dptr(a), ob.u8ptr(np.ones(len(r), np.uint8)), ob.SPW_EVEN, C.byref(oparams), *init,
+                             xlim, ylim, np.deg2rad(rot_deg), np.deg2rad(ang_deg), tstep, C.byref(m))
+    bparams = ob.spe_params(ob.OOPE_MAX, ob.OIE_DISCREPANCY, prerotated=1)
+    asked = [0]
+
+    def bounds(count, rots, wins, out, _user):
+        asked[0] += count
+        for k in range(count):
+            rot = rots[k]
+            # LaserScan2D::to_cartesian(rot + pose.theta), as slamgpu_match_m3rsm pre-rotates the scan
+            x, y = ob.f64(0 + r * np.cos(rot + init[2] + a)), ob.f64(0 + r * np.sin(rot + init[2] + a))
+            out[k] = refso.ref_match_bound(rm.h_, len(r), ob.dptr(x), ob.dptr(y), 1, ob.SPW_EVEN, C.byref(bparams), init[0], init[1], init[2],
+                                           rot, wins[4 * k], wins[4 * k + 1], wins[4 * k + 2], wins[4 * k + 3])
+
+    cb_t = C.CFUNCTYPE(None, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
+    L = sg.lib()
+    L.slamgpu_debug_m3rsm.argtypes = [C.c_double] * 6 + [cb_t, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    delta, prob, st = np.zeros(3), C.c_double(), np.zeros(4, np.int64)
+    rc = L.slamgpu_debug_m3rsm(xlim, ylim, np.deg2rad(rot_deg), np.deg2rad(ang_deg), tstep, 0.0, cb_t(bounds), None,
+                               delta.ctypes.data_as(C.POINTER(C.c_double)), C.byref(prob), st.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert rc == 0
+    assert np.array_equal(delta, [m.dx, m.dy, m.dth]), (delta, (m.dx, m.dy, m.dth))
+    assert prob.value == m.best_prob
+    assert st[0] == asked[0] and st[1] < st[2] + 2  # far fewer scoring calls than branches: the calls were filled up
