@@ -186,7 +186,7 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   if (ctx->comm) sg_nccl_destroy(ctx->comm);
   Candidates &c = ctx->cand;
   DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,
-                    &c.scores, &c.blk_best, &c.result, &ctx->flush, &ctx->gather};
+                    &c.scores, &c.blk_best, &c.result, &c.gm_pred, &c.gm_in, &c.gm_out, &ctx->flush, &ctx->gather};
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : ctx->scratch) b.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
