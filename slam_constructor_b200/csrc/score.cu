@@ -682,12 +682,23 @@ __global__ void __launch_bounds__(256) k_small_final(SmallArgs a, int G, Best *b
   __syncthreads();
   double best_s = -INFINITY;
   long long best_i = LLONG_MAX;
-  if (threadIdx.x < nq) {
-    const double *t = sh_terms + (size_t)threadIdx.x * a.N;
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < nq) {
+    // one pose per WARP (lane 0): neighbouring lanes walking rows N doubles apart would collide on the shared-memory
+    // banks (8-way for N = 360); loads are issued eight ahead of the chain of adds
+    const int j = threadIdx.x >> 5;
+    const double *t = sh_terms + (size_t)j * a.N;
     double total = 0;
-    for (int k = 0; k < a.N; ++k) total = sg::add(total, t[k]);
+    int k = 0;
+    for (; k + 8 <= a.N; k += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = t[k + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) total = sg::add(total, v[u]);
+    }
+    for (; k < a.N; ++k) total = sg::add(total, t[k]);
     const double score = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
-    const int q = q0 + threadIdx.x;
+    const int q = q0 + j;
     a.scores[q] = score;
     if (score == score) { best_s = score; best_i = q; }
   }
@@ -1814,7 +1825,7 @@ static int score_small_oneshot(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n
       SG_CUDA(ctx, cudaFuncSetAttribute(k_small_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_shm));
       attr_set = true;
     }
-    int G = (int)std::min<int64_t>(16, (int64_t)(max_shm / (sizeof(double) * N)));
+    int G = (int)std::min<int64_t>(8, (int64_t)(max_shm / (sizeof(double) * N)));  // one warp of the block per pose
     if (G < 1) return SLAMGPU_OK;  // a scan too long for the staging block: staged path
     const int nb = (int)((P + G - 1) / G);
     k_small_final<<<nb, 256, sizeof(double) * (size_t)G * N, ctx->stream>>>(a, G, (Best *)(d + d_blk));
