@@ -373,6 +373,20 @@ int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, con
                      double out_pose[3], double *out_prob, int64_t *out_tested, double *log /* 4*log_cap or NULL */,
                      int32_t log_cap, int32_t *log_count /* or NULL */,
                      slamgpu_gm_cache *gm_state /* in/out: the estimator's cache when spe->gm_cache == 2; NULL = a new estimator */);
+/* A segment of MonteCarloScanMatcher::process_scan (GaussianPoseEnumerator, monte_carlo_scan_matcher.h:10-100) in one
+ * launch.  The enumerator's noise is libstdc++'s and stays with the caller: noise[3k..3k+2] is the pose shift candidate k
+ * would get (it does not depend on the scores), candidate k = best pose so far + noise[k].  The device runs the accept
+ * loop with the enumerator's counters (failed attempts, poses tested) from the state given, until the budget is spent,
+ * the K shifts are used up or an accept resets the dispersion (the noise that follows is then different: the caller
+ * samples it and calls again).  have_best = 0: best_pose is the initial pose and is scored first.
+ * out[10] = best x, y, theta, probability, shifts consumed, failed attempts, poses tested, 1 if the dispersion was
+ * reset, guard hits, log entries; log = {x, y, theta, probability} of every pose scored, in order.
+ * *served = 0: not covered by the device kernel (host trig, overlap OOPE, carried GMapping cache, very long scans) or a
+ * device-trig border guard fired: nothing was consumed, use slamgpu_score_poses batches instead. */
+int slamgpu_match_mc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                     const double best_pose[3], double best_prob, int32_t have_best, const double *noise /* 3*K */, int32_t K,
+                     uint32_t failed, uint32_t poses_nm, uint32_t max_failed, uint32_t max_poses, double out[10],
+                     double *log /* 4*log_cap or NULL */, int32_t log_cap, int32_t *served);
 /* GridMapScanAdder::append_scan into every particle's own map from its own pose (do_update NULL: all); the beams of
  * all particles go through one batched ray-cast, one sort keyed by (map, cell) and one ordered apply */
 int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses /* 3*n */,

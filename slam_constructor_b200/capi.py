@@ -91,7 +91,7 @@ SYMBOLS = [
     "slamgpu_last_kernel_ms", "slamgpu_launch_count", "slamgpu_flush_l2", "slamgpu_model_stride", "slamgpu_default_unknown", "slamgpu_map_create",
     "slamgpu_map_destroy", "slamgpu_map_info", "slamgpu_map_upload", "slamgpu_map_download", "slamgpu_map_read_cell",
     "slamgpu_map_reset_cell", "slamgpu_map_update_cell", "slamgpu_map_lut_download", "slamgpu_map_upload_lut", "slamgpu_scan_create",
-    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_match_hc", "slamgpu_debug_div", "slamgpu_debug_hill_climb", "slamgpu_debug_m3rsm", "slamgpu_probe_gather", "slamgpu_stage_poses",
+    "slamgpu_scan_destroy", "slamgpu_scan_upload", "slamgpu_scan_filter", "slamgpu_point_weights", "slamgpu_mapping_quality", "slamgpu_score_poses", "slamgpu_score_grid", "slamgpu_score_poses_chained", "slamgpu_match_hc", "slamgpu_match_mc", "slamgpu_debug_div", "slamgpu_debug_hill_climb", "slamgpu_debug_m3rsm", "slamgpu_probe_gather", "slamgpu_stage_poses",
     "slamgpu_stage_grid", "slamgpu_score_launch", "slamgpu_score_fetch", "slamgpu_score_stats", "slamgpu_raycast", "slamgpu_raycast_segments", "slamgpu_estimate_occupancy",
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
@@ -154,6 +154,7 @@ def lib():
     L.slamgpu_score_grid.argtypes = [vp, vp, vp, sp, c_dp, i32, c_dp, i32, c_dp, i32, dbl, c_dp, c_lp, c_dp]
     L.slamgpu_score_poses_chained.argtypes = [vp, vp, vp, sp, c_dp, i64, C.POINTER(GmCache), c_dp, C.POINTER(GmCache)]
     L.slamgpu_probe_gather.argtypes = [vp, i64, i32, c_dp]
+    L.slamgpu_match_mc.argtypes = [vp, vp, vp, sp, c_dp, dbl, i32, c_dp, i32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_dp, c_dp, i32, c_ip]
     L.slamgpu_debug_div.argtypes = [vp, i32, c_dp, c_dp, c_dp]
     L.slamgpu_match_hc.argtypes = [vp, vp, vp, sp, c_dp, C.c_uint32, dbl, dbl, c_dp, c_dp, c_lp, c_dp, i32, c_ip, C.POINTER(GmCache)]
     L.slamgpu_stage_poses.argtypes = [vp, vp, sp, c_dp, i64]
@@ -296,6 +297,20 @@ class Context:
         out = C.c_double()
         self.check(self.L.slamgpu_probe_gather(self.h, table_bytes, loads_per_thread, C.byref(out)))
         return out.value
+
+    def match_mc(self, gmap, scan, params, best_pose, noise, max_failed, max_poses, best_prob=None, failed=0, poses_nm=0, log_cap=0):
+        """a segment of MonteCarloScanMatcher::process_scan over the given pose shifts; returns (out dict, log) or None when the
+        device kernel declines the request"""
+        best, noise = _f64(best_pose), _f64(noise).reshape(-1, 3)
+        out, served = np.zeros(10), C.c_int32()
+        log = np.zeros((max(log_cap, 1), 4))
+        self.check(self.L.slamgpu_match_mc(self.h, gmap.h, scan.h, C.byref(params), _dp(best), best_prob if best_prob is not None else np.nan,
+                                           0 if best_prob is None else 1, _dp(noise), len(noise), failed, poses_nm, max_failed, max_poses,
+                                           _dp(out), _dp(log) if log_cap else None, log_cap, C.byref(served)))
+        if not served.value:
+            return None
+        keys = ("x", "y", "theta", "prob", "consumed", "failed", "poses_nm", "reset", "guard", "logged")
+        return dict(zip(keys, out.tolist())), log[:min(int(out[9]), log_cap)]
 
     def debug_div(self, a, b):
         a, b = _f64(a), _f64(b)

@@ -536,6 +536,147 @@ __global__ void __launch_bounds__(1024) k_hill_climb(HcArgs a) {
   }
 }
 
+// ---- a Monte-Carlo match (GaussianPoseEnumerator, monte_carlo_scan_matcher.h:10-82, under the accept loop of
+// PoseEnumerationScanMatcher) in one launch.  The enumerator's noise comes from libstdc++'s normal_distribution and
+// cannot be produced here, but it does not depend on the scores: candidate k is (best pose so far) + noise[k], and the
+// noise sequence only changes when an accept shrinks the dispersion (reset_shift).  The host passes the noise list,
+// the block speculates a batch of candidates from the current best pose, scores them (terms in shared memory, one
+// warp per pose adds them in point order), thread 0 walks the batch in order with the enumerator's counters, re-bases
+// at the first accept, and stops at a dispersion reset (the host then supplies the next noise list) or when the
+// enumerator's budget is spent.
+struct McArgs {
+  MapView map;
+  const double *noise;  // 3 per candidate: the pose shifts the enumerator would sample, in order
+  int K;                // candidates available
+  double bx, by, bt, best;  // best pose so far and its probability (NaN with have_best = 0: score it first)
+  int have_best;
+  unsigned failed, poses_nm, max_failed, max_poses;  // the enumerator's counters and limits
+  int batch;            // candidates per speculation round (shared memory holds batch x N terms)
+  const double *range, *angle, *w, *f;
+  int N;
+  double wsum, win_v, win_h, gm_th;
+  int gm_win;
+  double *out;   // bx, by, bt, best, consumed, failed, poses_nm, reset (1: dispersion was reset), guard hits, log entries
+  double *log;   // {x, y, theta, probability} of every pose scored and consumed, in order
+  int log_cap;
+};
+#define SG_MC_OUT 10
+
+template <int MODE, bool FACTOR>
+__global__ void __launch_bounds__(1024) k_monte_carlo(McArgs a) {
+  extern __shared__ double sh_terms[];  // [batch][N]
+  __shared__ double cand[32][3], scores[32];
+  __shared__ double s_bx, s_by, s_bt, s_best;
+  __shared__ int s_b, s_k, s_logged, s_stop, s_reset;
+  __shared__ unsigned s_failed, s_poses, s_guard;
+  const int tid = threadIdx.x, N = a.N;
+  const MapView &mv = a.map;
+  const double s = mv.scale, inv_s = 1.0 / mv.scale;
+  if (tid == 0) {
+    s_bx = a.bx; s_by = a.by; s_bt = a.bt; s_best = a.best;
+    s_failed = a.failed; s_poses = a.poses_nm; s_guard = 0; s_logged = 0; s_k = 0; s_stop = 0; s_reset = 0;
+    if (!a.have_best) { cand[0][0] = a.bx; cand[0][1] = a.by; cand[0][2] = a.bt; s_b = 1; }
+  }
+  __syncthreads();
+  bool init_round = !a.have_best;
+  for (;;) {
+    if (tid == 0 && !init_round) {
+      // has_next(): failed < max_failed && poses_nm < max_poses; the batch = what would be tested if everything failed
+      int b = 0;
+      if (s_failed < a.max_failed && s_poses < a.max_poses && s_k < a.K) {
+        b = min(min(a.batch, a.K - s_k), (int)min(a.max_failed - s_failed, a.max_poses - s_poses));
+        for (int j = 0; j < b; ++j) {  // RobotPose + RobotPoseDelta: component-wise sums
+          const double *nz = a.noise + 3 * (size_t)(s_k + j);
+          cand[j][0] = sg::add(s_bx, nz[0]); cand[j][1] = sg::add(s_by, nz[1]); cand[j][2] = sg::add(s_bt, nz[2]);
+        }
+      }
+      s_b = b;
+    }
+    __syncthreads();
+    const int b = s_b;
+    if (b == 0) break;
+    bool unsafe_any = false;
+    for (int e = tid; e < b * N; e += blockDim.x) {
+      const int j = e / N, i = e - j * N;
+      const double px = cand[j][0], py = cand[j][1];
+      double sn, cs;
+      sincos(sg::add(cand[j][2], __ldg(a.angle + i)), &sn, &cs);
+      const double r = __ldg(a.range + i);
+      const double rc = sg::mul(r, cs), rs = sg::mul(r, sn);
+      const double X = sg::add(px, rc), Y = sg::add(py, rs);
+      double prob;
+      if (MODE == SLAMGPU_OOPE_OBSTACLE || MODE == SLAMGPU_OOPE_GMAPPING) {
+        const int cx = grid_cell(X, rc, s, inv_s, 1, &unsafe_any);
+        const int cy = grid_cell(Y, rs, s, inv_s, 1, &unsafe_any);
+        prob = MODE == SLAMGPU_OOPE_OBSTACLE ? lut_at(mv, cx, cy) : gmapping_probability(mv, cx, cy, X, Y, a.gm_th, a.gm_win);
+      } else {
+        double hv = sg::div(a.win_v, 2.0), hh = sg::div(a.win_h, 2.0);
+        bool u;
+        sg::world_to_cell_guard(sg::sub(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::add(X, hh), s, trig_slack(rc, X), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::sub(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+        sg::world_to_cell_guard(sg::add(Y, hv), s, trig_slack(rs, Y), &u); unsafe_any |= u;
+        prob = window_probability<MODE>(mv, X, Y, a.win_v, a.win_h);
+      }
+      double term = sg::mul(prob, __ldg(a.w + i));
+      if (FACTOR) term = sg::mul(term, __ldg(a.f + i));
+      sh_terms[e] = term;
+    }
+    if (unsafe_any) atomicAdd(&s_guard, 1u);
+    __syncthreads();
+    if ((tid & 31) == 0 && (tid >> 5) < b) {  // one warp per pose
+      const int j = tid >> 5;
+      const double *t = sh_terms + (size_t)j * N;
+      double total = 0;
+      int i = 0;
+      for (; i + 8 <= N; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = t[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) total = sg::add(total, v[u]);
+      }
+      for (; i < N; ++i) total = sg::add(total, t[i]);
+      scores[j] = a.wsum == 0 ? NAN : sg::div(total, a.wsum);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      auto log_it = [&](int j) {
+        if (a.log && s_logged < a.log_cap) {
+          double *l = a.log + (size_t)s_logged * 4;
+          l[0] = cand[j][0]; l[1] = cand[j][1]; l[2] = cand[j][2]; l[3] = scores[j];
+        }
+        ++s_logged;
+      };
+      if (init_round) {
+        s_best = scores[0];
+        log_it(0);
+      } else {
+        int used = b;
+        for (int j = 0; j < b; ++j) {
+          log_it(j);
+          const bool ok = s_best < scores[j];
+          ++s_poses;  // feedback(): ++_poses_nm
+          if (!ok) { ++s_failed; continue; }
+          s_best = scores[j]; s_bx = cand[j][0]; s_by = cand[j][1]; s_bt = cand[j][2];
+          used = j + 1;  // the candidates after an accept were speculated from the old best pose
+          if (!(s_failed <= a.max_failed / 3)) { s_failed = 0; s_reset = 1; s_stop = 1; }  // reset_shift(0.5): counter cleared, new dispersion, new noise
+          break;
+        }
+        s_k += used;
+      }
+    }
+    init_round = false;
+    __syncthreads();
+    if (s_stop) break;
+  }
+  if (tid == 0) {
+    double *o = a.out;
+    o[0] = s_bx; o[1] = s_by; o[2] = s_bt; o[3] = s_best; o[4] = (double)s_k; o[5] = (double)s_failed; o[6] = (double)s_poses;
+    o[7] = (double)s_reset; o[8] = (double)s_guard; o[9] = (double)s_logged;
+  }
+}
+
 // ---- GmappingOccupancyObservationPE's cache carried from pose to pose (gm_cache == 2).  The cache holds the cell
 // of the point evaluated last and the probability computed at the last MISS, so a point reuses the value computed
 // at the start of the run of consecutive same-cell points it belongs to -- a run that may begin in the pose
@@ -2032,6 +2173,76 @@ int sg_hill_climb_device(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n, slam
   if (log) memcpy(log, host.data() + SG_HC_OUT * (size_t)n, lb);
   c.stats[0] = 0; c.stats[1] = 5; c.stats[2] = 0;
   for (int k = 0; k < n; ++k) c.stats[2] += (int64_t)host[SG_HC_OUT * (size_t)k + 4] * N;
+  *served = 1;
+  return SLAMGPU_OK;
+}
+
+// A Monte-Carlo match segment on the device (k_monte_carlo): from the enumerator state given, over the noise list given,
+// until the budget is spent, the list runs out or an accept resets the dispersion.
+namespace {
+template <int MODE>
+void launch_mc(slamgpu_ctx *ctx, const McArgs &a, size_t smem, bool fac) {
+  if (fac) {
+    cudaFuncSetAttribute(k_monte_carlo<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_monte_carlo<MODE, true><<<1, 1024, smem, ctx->stream>>>(a);
+  } else {
+    cudaFuncSetAttribute(k_monte_carlo<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_monte_carlo<MODE, false><<<1, 1024, smem, ctx->stream>>>(a);
+  }
+}
+}  // namespace
+
+extern "C" int slamgpu_match_mc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
+                                const double best_pose[3], double best_prob, int32_t have_best, const double *noise, int32_t K,
+                                uint32_t failed, uint32_t poses_nm, uint32_t max_failed, uint32_t max_poses, double out[10],
+                                double *log, int32_t log_cap, int32_t *served) {
+  if (!ctx || !map || !scan || !p || !best_pose || K < 0 || (K > 0 && !noise) || !out || !served)
+    return sg_fail(ctx, SLAMGPU_E_INVALID, "match_mc: bad argument");
+  *served = 0;
+  if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
+  SG_TRY(check_spe(ctx, scan, p));
+  const int N = scan->n;
+  if (p->prerotated || p->trig_mode != SLAMGPU_TRIG_DEVICE || p->oope == SLAMGPU_OOPE_OVERLAP || N <= 0 ||
+      (p->oope == SLAMGPU_OOPE_GMAPPING && p->gm_cache != 0))
+    return SLAMGPU_OK;
+  const int batch = (int)std::min<size_t>(32, (size_t)(190 * 1024) / ((size_t)N * sizeof(double)));
+  if (batch < 4) return SLAMGPU_OK;
+  SG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (p->oope != SLAMGPU_OOPE_GMAPPING) SG_TRY(sg_map_ensure_lut(map, p->oie));
+  Candidates &c = ctx->cand;
+  const size_t nb = sizeof(double) * 3 * (size_t)std::max(K, 1);
+  SG_TRY(upload(ctx, c.poses, noise, sizeof(double) * 3 * (size_t)K));
+  if (c.poses.reserve(nb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "match_mc noise");
+  const size_t ob = sizeof(double) * SG_MC_OUT, lb = log && log_cap > 0 ? sizeof(double) * 4 * (size_t)log_cap : 0;
+  if (c.scores.reserve(ob + lb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "match_mc output");
+  McArgs a;
+  a.map = make_view(map, p->oie);
+  a.noise = c.poses.as<double>(); a.K = K;
+  a.bx = best_pose[0]; a.by = best_pose[1]; a.bt = best_pose[2]; a.best = best_prob; a.have_best = have_best ? 1 : 0;
+  a.failed = failed; a.poses_nm = poses_nm; a.max_failed = max_failed; a.max_poses = max_poses; a.batch = batch;
+  a.range = scan->d_range; a.angle = scan->d_angle; a.w = scan->d_w; a.f = scan->d_f; a.N = N; a.wsum = scan->wsum;
+  a.win_v = p->win_v; a.win_h = p->win_h; a.gm_th = p->gm_fullness_th; a.gm_win = p->gm_window;
+  a.out = c.scores.as<double>(); a.log = lb ? a.out + SG_MC_OUT : nullptr; a.log_cap = lb ? log_cap : 0;
+  const size_t smem = (size_t)batch * N * sizeof(double);
+  cudaEventRecord(ctx->evk0, ctx->stream);
+  switch (p->oope) {
+    case SLAMGPU_OOPE_OBSTACLE: launch_mc<SLAMGPU_OOPE_OBSTACLE>(ctx, a, smem, scan->has_factor); break;
+    case SLAMGPU_OOPE_MAX: launch_mc<SLAMGPU_OOPE_MAX>(ctx, a, smem, scan->has_factor); break;
+    case SLAMGPU_OOPE_MEAN: launch_mc<SLAMGPU_OOPE_MEAN>(ctx, a, smem, scan->has_factor); break;
+    default: launch_mc<SLAMGPU_OOPE_GMAPPING>(ctx, a, smem, scan->has_factor); break;
+  }
+  cudaEventRecord(ctx->evk1, ctx->stream);
+  ctx->evk_valid = true;
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  std::vector<double> host((ob + lb) / sizeof(double));
+  SG_CUDA(ctx, cudaMemcpyAsync(host.data(), c.scores.p, ob + lb, cudaMemcpyDeviceToHost, ctx->stream));
+  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (host[8] != 0) return SLAMGPU_OK;  // a point within the device-trig slack of a cell border: the caller's host-trig path
+  memcpy(out, host.data(), ob);
+  if (lb) memcpy(log, host.data() + SG_MC_OUT, lb);
+  c.kind = -1;  // the pose staging buffer was reused
+  c.stats[0] = 0; c.stats[1] = 6; c.stats[2] = (int64_t)host[9] * N;
   *served = 1;
   return SLAMGPU_OK;
 }

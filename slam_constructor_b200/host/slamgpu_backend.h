@@ -603,22 +603,102 @@ public:
     do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(pose_delta, scan, best_pose_prob); });
     return best_pose_prob;
   }
-private:
+protected:
   PE _pe;
+private:
   std::size_t _max_batch;
 };
 
 using HillClimbingPoseEnumerator = FailedRoundsLimitedPoseEnumerator<Distorsion1DPoseEnumerator>;
 
-// MonteCarloScanMatcher (monte_carlo_scan_matcher.h:84-100) on the device
+// MonteCarloScanMatcher (monte_carlo_scan_matcher.h:84-100) on the device.  The Gaussian enumerator's pose shifts come
+// from libstdc++'s normal_distribution and do not depend on the scores, only on how many were drawn and on the
+// dispersion resets; so a copy of the enumerator samples the shifts ahead, slamgpu_match_mc runs the accept loop over
+// them in one launch (re-basing at every accept), and only a dispersion reset -- an accept after more than a third of
+// the failed-attempts budget -- brings the loop back to the host for the next list.  The real enumerator is advanced
+// afterwards by replaying the recorded decisions (next / feedback / observers in the reference's order), so a match
+// the device declines (host trig, border guard, ...) falls back to the speculative batches with nothing consumed.
 class CudaMonteCarloScanMatcher : public CudaPoseEnumerationScanMatcher<GaussianPoseEnumerator> {
+  using Base = CudaPoseEnumerationScanMatcher<GaussianPoseEnumerator>;
 public:
   CudaMonteCarloScanMatcher(std::shared_ptr<Context> ctx, std::shared_ptr<ScanProbabilityEstimator> spe,
                             std::shared_ptr<ScanPointWeighting> spw, unsigned seed, double translation_dispersion,
                             double rotation_dispersion, unsigned failed_attempts_per_dispersion, unsigned total_attempts)
-    : CudaPoseEnumerationScanMatcher{ctx, spe, spw,
-                                     GaussianPoseEnumerator{seed, translation_dispersion, rotation_dispersion,
-                                                            failed_attempts_per_dispersion, total_attempts}} {}
+    : Base{ctx, spe, spw,
+           GaussianPoseEnumerator{seed, translation_dispersion, rotation_dispersion, failed_attempts_per_dispersion, total_attempts}}
+    , _max_failed{failed_attempts_per_dispersion}, _max_poses{total_attempts} {}
+
+  double process_scan(const TransformedLaserScan &raw_scan, const RobotPose &init_pose, const GridMap &map,
+                      RobotPoseDelta &pose_delta) override {
+    if (_setup.oope == SLAMGPU_OOPE_GMAPPING && _setup.gm_cache == 2) { return Base::process_scan(raw_scan, init_pose, map, pose_delta); }
+    auto prep = prepare(raw_scan, init_pose, map);
+    const LaserScan2D &scan = prep.scan;
+    GaussianPoseEnumerator clean = _pe;
+    clean.reset();  // what process_scan's own reset() leaves: counters cleared, base dispersion, the engine where it is
+    struct Step { RobotPose arg, pose; double prob; bool accepted; };
+    std::vector<Step> steps;  // every candidate the reference loop would have tested, in order
+    RobotPose best = init_pose;
+    double best_prob = std::numeric_limits<double>::quiet_NaN(), init_prob = best_prob;
+    bool have_best = false;
+    unsigned failed = 0, poses = 0;
+    std::vector<double> noise, log;
+    for (;;) {
+      if (have_best && !(failed < _max_failed && poses < _max_poses)) { break; }  // has_next()
+      GaussianPoseEnumerator ahead = clean;  // a copy is state-identical only right after reset(): replay the history on it
+      for (const Step &st : steps) { ahead.next(st.arg); ahead.feedback(st.accepted); }
+      const int32_t K = (int32_t)(_max_poses - poses);
+      noise.resize((std::size_t)3 * K);
+      for (int32_t j = 0; j < K; ++j) {  // 0 + shift = the shift itself
+        const RobotPose nz = ahead.next(RobotPose{0, 0, 0});
+        noise[3 * j] = nz.x; noise[3 * j + 1] = nz.y; noise[3 * j + 2] = nz.theta;
+      }
+      log.resize((std::size_t)4 * (K + 1));
+      const double b3[3] = {best.x, best.y, best.theta};
+      double out[10];
+      int32_t served = 0;
+      _ctx->check(slamgpu_match_mc(_ctx->handle(), prep.map, prep.dscan, &prep.params, b3, best_prob, have_best ? 1 : 0, noise.data(), K,
+                                   failed, poses, _max_failed, _max_poses, out, log.data(), K + 1, &served));
+      if (!served) { return Base::process_scan(raw_scan, init_pose, map, pose_delta); }  // nothing was consumed from _pe
+      const int32_t entries = (int32_t)out[9];
+      int32_t e = 0;
+      if (!have_best) { init_prob = best_prob = log[3]; have_best = true; e = 1; }
+      for (; e < entries; ++e) {  // the same accept rule, to label the steps
+        const double *l = log.data() + 4 * (std::size_t)e;
+        const bool ok = best_prob < l[3];
+        steps.push_back(Step{best, RobotPose{l[0], l[1], l[2]}, l[3], ok});
+        if (ok) { best = RobotPose{l[0], l[1], l[2]}; best_prob = l[3]; }
+      }
+      if (best.x != out[0] || best.y != out[1] || best.theta != out[2] || !(best_prob == out[3] || (best_prob != best_prob && out[3] != out[3]))) {
+        throw std::logic_error("slamgpu: the Monte-Carlo log does not reproduce the device's result");
+      }
+      failed = (unsigned)out[5]; poses = (unsigned)out[6];
+      if ((int32_t)out[4] == 0 && out[7] == 0) { break; }  // nothing consumed and no reset: the budget is spent
+    }
+    // ---- the reference's calls, in its order, on the real enumerator
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_start(init_pose, raw_scan, map); });
+    _poses_tested = 1 + steps.size();
+    do_for_each_observer([&](ObsPtr obs) {
+      obs->on_scan_test(init_pose, scan, init_prob);
+      obs->on_pose_update(init_pose, scan, init_prob);
+    });
+    _pe.reset();
+    for (const Step &st : steps) {
+      if (!_pe.has_next()) { throw std::logic_error("slamgpu: the Monte-Carlo replay ran past the enumerator's budget"); }
+      const RobotPose sampled = _pe.next(st.arg);
+      if (sampled.x != st.pose.x || sampled.y != st.pose.y || sampled.theta != st.pose.theta) {
+        throw std::logic_error("slamgpu: the pose enumerator is not reproducible from a copy taken after reset()");
+      }
+      do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(sampled, scan, st.prob); });
+      _pe.feedback(st.accepted);
+      if (st.accepted) { do_for_each_observer([&](ObsPtr obs) { obs->on_pose_update(sampled, scan, st.prob); }); }
+    }
+    if (_pe.has_next()) { throw std::logic_error("slamgpu: the Monte-Carlo replay stopped before the enumerator's budget was spent"); }
+    pose_delta = best - init_pose;
+    do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(pose_delta, scan, best_prob); });
+    return best_prob;
+  }
+private:
+  unsigned _max_failed, _max_poses;
 };
 
 // HillClimbingScanMatcher (hill_climbing_scan_matcher.h:128-170) on the device.  The enumerator is deterministic, so

@@ -387,3 +387,57 @@ def test_new_entry_points_on_degenerate_inputs(sg, gpu):
     scores, states = gpu.score_poses_chained(gm, gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_cache=2), np.zeros((0, 3)))
     assert len(scores) == 0 and len(states) == 0
     gm.close(); gsc.close(); empty_g.close()
+
+
+@pytest.mark.parametrize("mode", ["obstacle", "mean"])
+def test_monte_carlo_segment_in_one_launch(sg, gpu, mode):
+    """slamgpu_match_mc: the accept loop of MonteCarloScanMatcher over a given list of pose shifts -- re-basing at every
+    accept, the enumerator's counters, the stop at a dispersion reset -- against the same loop run on the host with the
+    oracle's scores"""
+    rng = np.random.default_rng(1950)
+    cells = room_map_cells(rng, 200, 200, 0.05, ob.CELL_MEAN, passes=4)
+    om = ob.OracleMap(200, 200, 0.05, ob.CELL_MEAN); om.set_cells(cells)
+    gm = sg.GridMap(gpu, 200, 200, 0.05, ob.CELL_MEAN); gm.upload(cells)
+    kw = dict(obstacle=(ob.OOPE_OBSTACLE, {}), mean=(ob.OOPE_MEAN, dict(win_v=0.15, win_h=0.1)))[mode]
+    po, pg = ob.spe_params(kw[0], **kw[1]), sg.spe_params(kw[0], **kw[1])
+    resets = 0
+    for trial in range(6):
+        truth = np.array([0.1, -0.2, 0.2]) + rng.normal(0, 0.3, 3) * [1, 1, 0.3]
+        r, a = room_scan(rng, 360, 2 * np.pi, pose=truth, noise=0.005)
+        osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+        init = truth + rng.normal(0, [0.15, 0.15, 0.08])
+        max_failed, max_poses = (20, 100) if trial % 2 == 0 else (7, 40)
+        noise = rng.normal(0, [0.2, 0.2, 0.1], (max_poses, 3))
+        # the reference loop (pose_enumeration_scan_matcher.h:48-65 over GaussianPoseEnumerator::feedback :46-57)
+        best, bp = init.copy(), om.score(osc, po, init[None])[0]
+        failed = poses = k = 0
+        reset = False
+        want_log = [np.append(init, bp)]
+        while failed < max_failed and poses < max_poses and k < len(noise) and not reset:
+            cand = best + noise[k]
+            p = om.score(osc, po, cand[None])[0]
+            want_log.append(np.append(cand, p))
+            k += 1; poses += 1
+            if not bp < p:
+                failed += 1
+                continue
+            best, bp = cand, p
+            if failed > max_failed // 3:
+                failed, reset = 0, True
+        res = gpu.match_mc(gm, gsc, pg, init, noise, max_failed, max_poses, log_cap=max_poses + 1)
+        assert res is not None and gpu.score_stats()["variant"] == 6
+        out, log = res
+        assert (out["consumed"], out["failed"], out["poses_nm"], bool(out["reset"])) == (k, failed, poses, reset)
+        assert np.array_equal([out["x"], out["y"], out["theta"]], best) and out["prob"] == bp
+        assert np.array_equal(log, np.array(want_log))
+        resets += reset
+        # a second segment continues from the state the first one left
+        if reset:
+            noise2 = rng.normal(0, [0.1, 0.1, 0.05], (max_poses - poses, 3))
+            res2 = gpu.match_mc(gm, gsc, pg, best, noise2, max_failed, max_poses, best_prob=bp, failed=failed, poses_nm=poses, log_cap=max_poses)
+            out2, log2 = res2
+            assert out2["poses_nm"] >= poses and out2["prob"] >= bp and len(log2) == out2["consumed"]
+        gsc.close()
+    assert resets > 0, "no trial reached a dispersion reset"
+    assert gpu.match_mc(gm, sg.Scan(gpu, r, a), sg.spe_params(kw[0], trig=sg.TRIG_HOST, **kw[1]), init, noise, 20, 100) is None
+    gm.close()
