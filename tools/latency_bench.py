@@ -113,6 +113,10 @@ def measure(ctx):
         for _ in range(20):
             dev()
         dev_us = float(np.median([dev() for _ in range(200)])) * 1e3
+        shifts = rng.normal(0, [0.2, 0.2, 0.1], (100, 3))  # MC(0.2 / 0.1, 20 failed attempts, 100 poses): one dispersion segment
+        mc_us = timeit(lambda: ctx.match_mc(gm, scan, params, pose + [0.06, -0.05, 0.03], shifts, 20, 100), n=100, warm=10)
+        mc_out, _ = ctx.match_mc(gm, scan, params, pose + [0.06, -0.05, 0.03], shifts, 20, 100)
+        mc_kernel_us = ctx.last_kernel_ms() * 1e3
         hc_us = timeit(lambda: ctx.match_hc(gm, scan, params, pose + [0.06, -0.05, 0.03]), n=100, warm=10)
         _, _, hc_tested, _ = ctx.match_hc(gm, scan, params, pose + [0.06, -0.05, 0.03])
         hc_kernel_us = ctx.last_kernel_ms() * 1e3
@@ -120,6 +124,8 @@ def measure(ctx):
         rec_bytes = {sg.CELL_MEAN: 2 * 16 + 8, sg.CELL_TBM_CONSISTENT: 2 * 48 + 8}[model]  # 2 x record + LUT entry
         out[name] = {"poses": P, "beams": beams, "score_call_e2e_us": round(e2e, 1), "score_device_us": round(dev_us, 1), "oneshot_terms_kernel_us": round(oneshot_kernel_us, 1),
                      "evals_per_s_e2e": P * beams / (e2e * 1e-6),
+                     "monte_carlo_segment_e2e_us": round(mc_us, 1), "monte_carlo_segment_kernel_us": round(mc_kernel_us, 1),
+                     "monte_carlo_poses_tested": int(mc_out["poses_nm"]),
                      "hill_climb_match_e2e_us": round(hc_us, 1), "hill_climb_match_kernel_us": round(hc_kernel_us, 1), "hill_climb_poses_tested": int(hc_tested),
                      "append_scan_e2e_us": round(upd, 1), "cells_per_scan": int(cells),
                      "cell_updates_per_s": cells / (upd * 1e-6),
