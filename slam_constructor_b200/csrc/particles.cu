@@ -4,10 +4,13 @@
 // (src/slams/gmapping/gmapping_particle_filter.h:70-85) around GmappingWorld::handle_observation
 // (src/slams/gmapping/gmapping_world.h:73-101): every particle hill-climbs from its own pose against
 // its OWN map (HillClimbingScanMatcher(6, 0.1, 0.1) upstream, src/slams/gmapping/init_gmapping.h:58-60),
-// then inserts the scan into its own map.  Here all particles advance in lock step: one K1 launch
-// scores the current hill-climbing round of every particle (6 candidates each, each against its
-// particle's map), the accept logic of the round runs on the host, repeat until every particle has
-// exhausted its failed-rounds budget.  Resampling copies maps on the device.
+// then inserts the scan into its own map.  Here the whole match of every particle runs in ONE launch
+// (score.cu: k_hill_climb, one block per particle, the estimator's cell cache carried along); requests
+// that kernel does not cover (host trig, overlap OOPE, a border guard hit) advance all particles in
+// lock step instead: one K1 launch scores the current round of every particle (6 candidates each,
+// each against its particle's map), the accept logic runs on the host.  The scan then goes into all
+// maps by one batched insertion (mapping.cu: sg_append_plans).  Resampling moves or copies maps on
+// the device; on a distributed ctx the particles are sharded over the ranks.
 //
 // Each particle owns a dense device map (the reference shares copy-on-write 128x128 tiles between
 // particles, src/core/maps/lazy_tiled_grid_map.h:18-118; tile sharing on the device is future work --
