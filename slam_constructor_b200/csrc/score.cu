@@ -176,6 +176,10 @@ SG_DEV double gmapping_probability(const MapView &m, int cx, int cy, double X, d
 
 // exact cell of a world coordinate (+ the device-trig border guard; the tolerance itself need not be exact)
 SG_DEV int grid_cell(double v, double rc, double scale, double inv_scale, int guard, bool *unsafe) {
+  {  // the common case: the quotient is nowhere near a cell border (see grid_axis_cell for the bound)
+    const double qa = v * inv_scale, fa = floor(qa), da = qa - fa;
+    if (da > 1e-6 && da < 1.0 - 1e-6 && fabs(qa) < 1e9) return cell_of(fa);
+  }
   const double f = sg::floor_div(v, scale, inv_scale);
   if (guard) {
     const double q = v * inv_scale;
@@ -918,8 +922,14 @@ SG_DEV int nib_sext(unsigned long long w, int m) {  // m in 1..7
 // within `margin` of a border (a few ulps, or the device-trig slack when the guard is on) takes the
 // real division, and with the guard on such a value also flags the call for a libm-trig redo.
 SG_DEV int grid_axis_cell(double v, double rc, double scale, double inv_scale, int guard, bool *unsafe) {
-  int c = __double2int_rd(v * inv_scale);  // saturating
+  const double qa = v * inv_scale;
+  int c = __double2int_rd(qa);  // saturating
   const double f = (double)c;
+  // qa is within |qa| * 2.3e-16 of the exact quotient (two roundings), i.e. within 2.3e-7 cells below 1e9 cells; the
+  // device-trig slack is ~1e-13 cells.  A fractional part farther than 1e-6 from both ends therefore fixes the cell
+  // for the reference's floor(v / scale) and for the guard at once: no residuals needed (the common case by far)
+  const double da = qa - f;
+  if (da > 1e-6 && da < 1.0 - 1e-6 && fabs(qa) < 1e9) return c;
   const double lo = fma(-f, scale, v);        // v - f*scale
   const double hi = fma(f + 1.0, scale, -v);  // (f+1)*scale - v
   double margin = fabs(v) * 8.9e-16 + 1e-300;
