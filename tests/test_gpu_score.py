@@ -441,3 +441,36 @@ def test_monte_carlo_segment_in_one_launch(sg, gpu, mode):
     assert resets > 0, "no trial reached a dispersion reset"
     assert gpu.match_mc(gm, sg.Scan(gpu, r, a), sg.spe_params(kw[0], trig=sg.TRIG_HOST, **kw[1]), init, noise, 20, 100) is None
     gm.close()
+
+
+def test_whole_match_kernels_at_their_size_limits(sg, gpu):
+    """long scans: the one-launch kernels hold 6 (hill climbing) or >= 4 (Monte-Carlo) poses x N terms in shared memory;
+    beyond that the hill climbing takes the round-by-round path and the Monte-Carlo entry declines -- same answers"""
+    rng = np.random.default_rng(1960)
+    cells = room_map_cells(rng, 200, 200, 0.05, ob.CELL_MEAN, passes=3)
+    om = ob.OracleMap(200, 200, 0.05, ob.CELL_MEAN); om.set_cells(cells)
+    gm = sg.GridMap(gpu, 200, 200, 0.05, ob.CELL_MEAN); gm.upload(cells)
+    truth = np.array([0.1, -0.2, 0.2])
+    init = truth + [0.06, -0.05, 0.03]
+    po, pg = ob.spe_params(), sg.spe_params()
+    for n_beams, one_launch in ((4000, True), (4400, False)):
+        r, a = room_scan(rng, n_beams, 2 * np.pi, pose=truth, noise=0.005)
+        osc, gsc = ob.OracleScan(r, a), sg.Scan(gpu, r, a)
+        m = ob.MatchResult()
+        ob.orc.orc_match_hill_climbing(om.h_, C.byref(osc.s), C.byref(po), *init, 6, 0.1, 0.1, C.byref(m), None)
+        pose, prob, tested, _ = gpu.match_hc(gm, gsc, pg, init, 6, 0.1, 0.1)
+        assert (gpu.score_stats()["variant"] == 5) == one_launch
+        assert tested == m.poses_tested and prob == m.best_prob and np.array_equal(pose - init, [m.dx, m.dy, m.dth])
+        gsc.close()
+    noise = rng.normal(0, [0.2, 0.2, 0.1], (30, 3))
+    for n_beams, served in ((5000, True), (7000, False)):
+        r, a = room_scan(rng, n_beams, 2 * np.pi, pose=truth, noise=0.005)
+        gsc, osc = sg.Scan(gpu, r, a), ob.OracleScan(r, a)
+        res = gpu.match_mc(gm, gsc, pg, init, noise, 20, 30, log_cap=31)
+        assert (res is not None) == served
+        if served:
+            out, log = res
+            assert np.array_equal(log[:, 3], om.score(osc, po, log[:, :3]))
+            assert out["prob"] == log[:, 3].max() or out["reset"]
+        gsc.close()
+    gm.close()
