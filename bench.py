@@ -410,8 +410,12 @@ def main():
             ref_poses = ref.sample(30000 * cores)
             best_dt, ref_scores, thr = min((ref.score(ref_poses, cores) for _ in range(3)), key=lambda r: r[0])
             got, _, _ = ctx.score_poses(gmap, scan, sg.spe_params(trig=sg.TRIG_DEVICE), ref_poses)
+            # the reference as shipped has no threads: the same code on ONE core, on a smaller sample
+            one_dt, _, _ = min((ref.score(ref_poses[:40000], 1) for _ in range(2)), key=lambda r: r[0])
             line["cpu_baseline"] = {"value": len(ref_poses) * N_BEAMS / best_dt, "unit": cfg["unit"], "cores": thr,
                                     "kind": ref.kind,
+                                    "single_thread": {"value": 40000 * N_BEAMS / one_dt, "unit": cfg["unit"], "cores": 1,
+                                                      "sample": "40000 consecutive candidates, best of 2"},
                                     "sample": "%d consecutive candidates x %d beams of the same workload, best of 3; GPU "
                                               "scores on the sample bit-equal to the reference: %s"
                                               % (len(ref_poses), N_BEAMS, bool(np.array_equal(got, ref_scores)))}
