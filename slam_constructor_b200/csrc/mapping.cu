@@ -93,7 +93,7 @@ struct EstimateArgs {
   unsigned *vals;         // per slot: slot id
   int *slot_beam;         // per slot
   unsigned long long *counters;  // per map: [2*id+1] updates dropped outside a bounded map ([2*id]: see k_raycast)
-  int *robot_slot;        // per beam: the slot of its robot-cell update (taken out of the sort), or NULL
+  int ring;               // >= 0: cells within this many cells of the robot are taken out of the sort (k_apply_ring)
 };
 
 // AREA = false: the const estimator only (a select); the kernel then does not carry the area estimator's registers
@@ -154,9 +154,8 @@ __global__ void __launch_bounds__(128) k_estimate(EstimateArgs a) {
     a.keys[s] = SG_INVALID_KEY;
     atomicAdd(a.counters + 2 * b.map_id + 1, 1ull);
   } else {
-    if (a.robot_slot && c.x == ms.rx && c.y == ms.ry) {
-      a.keys[s] = SG_INVALID_KEY;  // applied by k_apply_robot, in beam order
-      a.robot_slot[i] = (int)s;
+    if (a.ring >= 0 && abs(c.x - ms.rx) <= a.ring && abs(c.y - ms.ry) <= a.ring) {
+      a.keys[s] = SG_INVALID_KEY;  // applied by k_apply_ring, in beam order
     } else {
       a.keys[s] = ms.key_base + (unsigned)iy * (unsigned)ms.w + (unsigned)ix;
     }
@@ -565,18 +564,30 @@ struct RobotArgs {
   const MapSlot *maps;
   int n_maps;
   const BeamRec *beams;
-  const int *robot_slot;
-  const double *aoo_p, *aoo_q;
+  const BeamOut *bout;         // per beam: cells of its ray
+  const long long *offsets;    // per beam: first slot
+  const int2 *cells;           // per slot: external cell
+  const double *aoo_p, *aoo_q; // per slot: the occupancy estimate
   int stride, model;
+  int ring;                    // half size W of the window of cells around the robot handled here (0: the robot cell only)
 };
 
+// One warp per cell of the (2W+1)^2 window around the robot of each map.  A ray is monotone in x and y, so it can only
+// be inside the window during its first 2W+1 cells, and it visits a cell at most once: the updates of a window cell
+// are one per beam at most, in beam order -- no sort needed.  The lanes test 32 beams at a time for "does this ray
+// pass through my cell", then the hits are applied in beam order (the chain of dependent updates), W = 0 being the
+// robot's own cell, which every ray starts in.
 template <bool TBM>
-__global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
+__global__ void __launch_bounds__(128) k_apply_ring(RobotArgs a) {
   const int lane = threadIdx.x & 31;
-  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int side = 2 * a.ring + 1, per_map = side * side;
+  const int m = wid / per_map;
   if (m >= a.n_maps) return;
+  const int t = wid - m * per_map;
   const MapSlot ms = a.maps[m];
-  const int ix = ms.rx + ms.ox, iy = ms.ry + ms.oy;
+  const int tx = ms.rx + (t % side) - a.ring, ty = ms.ry + (t / side) - a.ring;  // the cell of this warp
+  const int ix = tx + ms.ox, iy = ty + ms.oy;
   if (ix < 0 || ix >= ms.w || iy < 0 || iy >= ms.h) return;
   double *cell = ms.cells + ((size_t)iy * ms.w + ix) * a.stride;
   double r[SLAMGPU_MAX_STRIDE];
@@ -585,10 +596,23 @@ __global__ void __launch_bounds__(128) k_apply_robot(RobotArgs a) {
   FixedPoint fx{NAN, NAN, NAN, false};
   for (int base = ms.beam_begin; base < ms.beam_end; base += 32) {
     const int i = base + lane;
-    int rs = -1;
+    long long rs = -1;
     double p = 0, q = 0, quality = 0, wx = 0, wy = 0;
     if (i < ms.beam_end) {
-      rs = a.robot_slot[i];
+      const int cnt = min(a.bout[i].count, side);  // cells of this ray that can lie in the window
+      const long long off = a.offsets[i];
+      if (tx == ms.rx && ty == ms.ry) {  // the robot's own cell (the longest chain): every ray starts there
+        if (cnt > 0) { const int2 c = a.cells[off]; if (c.x == tx && c.y == ty) rs = off; }
+      } else {
+        // a ray visits a cell at most once: all candidate slots are loaded at once (independent loads), no early exit
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+          if (k < cnt) {
+            const int2 c = a.cells[off + k];
+            if (c.x == tx && c.y == ty) rs = off + k;
+          }
+        }
+      }
       if (rs >= 0) {
         const BeamRec &b = a.beams[i];
         p = a.aoo_p[rs]; q = a.aoo_q[rs]; quality = b.quality; wx = b.wx; wy = b.wy;
@@ -1012,27 +1036,27 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   ea.N = N; ea.M = M; ea.maps = ctx->scratch[7].as<MapSlot>(); ea.scale = maps[0]->scale; ea.est = *est;
   ea.cells = ctx->scratch[2].as<int2>();
   ea.aoo_p = aoo_p; ea.aoo_q = aoo_q; ea.keys = keys; ea.vals = vals; ea.slot_beam = slot_beam; ea.counters = counters;
-  // the robot cell's chain leaves the sort and runs on the side stream (not when a pyramid wants the per-slot trace)
+  // the cells around the robot leave the sort and run on the side stream (not when a pyramid wants the per-slot trace):
+  // the robot's own cell always (every ray starts in it: the longest chain of an insertion); for a few maps also the
+  // ring of cells around it, whose runs of dozens to hundreds of updates would otherwise follow the sort
   const bool robot_split = trace == nullptr;
-  ea.robot_slot = nullptr;
-  if (robot_split) {
-    if (ctx->scratch[5].reserve(sizeof(int) * (size_t)std::max(N, 1)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "robot slots");
-    ea.robot_slot = ctx->scratch[5].as<int>();
-    SG_CUDA(ctx, cudaMemsetAsync(ea.robot_slot, 0xFF, sizeof(int) * (size_t)N, ctx->stream));
-  }
+  const int ring = !robot_split ? -1 : (n <= 8 ? 6 : 0);  // (k_apply_ring unrolls 2 * 6 + 1 = 13 candidate slots per ray)
+  ea.ring = ring;
   if (est->type == SLAMGPU_EST_AREA) k_estimate<true><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   else k_estimate<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
   if (robot_split) {
     RobotArgs ra;
-    ra.maps = ctx->scratch[7].as<MapSlot>(); ra.n_maps = n; ra.beams = ctx->scratch[0].as<BeamRec>(); ra.robot_slot = ea.robot_slot;
-    ra.aoo_p = aoo_p; ra.aoo_q = aoo_q; ra.stride = maps[0]->stride; ra.model = maps[0]->model;
+    ra.maps = ctx->scratch[7].as<MapSlot>(); ra.n_maps = n; ra.beams = ctx->scratch[0].as<BeamRec>();
+    ra.bout = ctx->scratch[3].as<BeamOut>(); ra.offsets = ctx->scratch[1].as<long long>(); ra.cells = ctx->scratch[2].as<int2>();
+    ra.aoo_p = aoo_p; ra.aoo_q = aoo_q; ra.stride = maps[0]->stride; ra.model = maps[0]->model; ra.ring = ring;
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     const bool tbm_cells = ra.model == SLAMGPU_CELL_TBM_CONSISTENT || ra.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
-    if (tbm_cells) k_apply_robot<true><<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
-    else k_apply_robot<false><<<(unsigned)((n * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
+    const long long warps = (long long)n * (2 * ring + 1) * (2 * ring + 1);
+    if (tbm_cells) k_apply_ring<true><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
+    else k_apply_ring<false><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
     SG_LAUNCHED(ctx);
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
   }
