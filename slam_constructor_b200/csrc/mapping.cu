@@ -18,6 +18,7 @@
 // The reference updates cells beam by beam (obstacle cell first, then along the beam); a cell
 // appears at most once per beam, so per-cell order == beam order, which the stable sort keeps.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1040,7 +1041,8 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   // the robot's own cell always (every ray starts in it: the longest chain of an insertion); for a few maps also the
   // ring of cells around it, whose runs of dozens to hundreds of updates would otherwise follow the sort
   const bool robot_split = trace == nullptr;
-  const int ring = !robot_split ? -1 : (n <= 8 ? 6 : 0);  // (k_apply_ring unrolls 2 * 6 + 1 = 13 candidate slots per ray)
+  static const int ring_env = getenv("SLAMGPU_RING") ? atoi(getenv("SLAMGPU_RING")) : -1;  // experiment: 0..6
+  const int ring = !robot_split ? -1 : (ring_env >= 0 && ring_env <= 6 ? ring_env : (n <= 8 ? 6 : 0));  // (k_apply_ring unrolls 2 * 6 + 1 = 13 candidate slots per ray)
   ea.ring = ring;
   if (est->type == SLAMGPU_EST_AREA) k_estimate<true><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   else k_estimate<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
