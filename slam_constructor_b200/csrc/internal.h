@@ -189,5 +189,7 @@ int sg_allgather_host(slamgpu_ctx *ctx, void *host, size_t chunk_bytes);
 int sg_scans_upload_xy(slamgpu_ctx *ctx, slamgpu_scan *const *scans, int count, int32_t n, const double *xs, const double *ys,
                        const double *weight);
 int sg_scan_ensure_xy(slamgpu_scan *s);
+void sg_preload_score();
+void sg_preload_mapping();
 void sg_p2p_setup(slamgpu_ctx *ctx);
 void sg_p2p_teardown(slamgpu_ctx *ctx);

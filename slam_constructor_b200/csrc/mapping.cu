@@ -1298,3 +1298,12 @@ extern "C" int slamgpu_estimate_occupancy(slamgpu_ctx *ctx, const slamgpu_estima
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
 }
+
+#define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
+void sg_preload_mapping() {  // see sg_preload_score
+  SG_TOUCH(k_raycast); SG_TOUCH(k_estimate<true>); SG_TOUCH(k_estimate<false>); SG_TOUCH(k_radix_hist); SG_TOUCH(k_radix_scan);
+  SG_TOUCH(k_scan_chunks); SG_TOUCH(k_scan_add); SG_TOUCH(k_radix_scatter); SG_TOUCH(k_gather_sorted); SG_TOUCH(k_apply);
+  SG_TOUCH((k_apply_long<true, false>)); SG_TOUCH((k_apply_long<false, false>)); SG_TOUCH((k_apply_long<false, true>));
+  SG_TOUCH(k_apply_ring<true>); SG_TOUCH(k_apply_ring<false>); SG_TOUCH(k_copy_block); SG_TOUCH(k_fill);
+  (void)cudaGetLastError();
+}

@@ -2256,3 +2256,18 @@ extern "C" int slamgpu_match_mc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan
   *served = 1;
   return SLAMGPU_OK;
 }
+
+// CUDA loads a kernel's code at its first launch (lazy module loading): tens of milliseconds in the middle of somebody's
+// scan.  Touching the kernels once at ctx creation moves that cost to start-up.
+#define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
+void sg_preload_score() {
+  SG_TOUCH((k_score_grid2<8, false, true>)); SG_TOUCH((k_score_grid2<8, false, false>)); SG_TOUCH((k_score_grid2<4, false, true>));
+  SG_TOUCH((k_score_grid2<2, false, true>)); SG_TOUCH(k_grid_indices); SG_TOUCH(k_trig_table); SG_TOUCH(k_reduce_blocks); SG_TOUCH(k_finalize);
+  SG_TOUCH((k_score_list<SLAMGPU_OOPE_OBSTACLE, false, true, false>)); SG_TOUCH((k_point_terms<SLAMGPU_OOPE_OBSTACLE, false, true, false>));
+  SG_TOUCH((k_pose_sums<false, false>)); SG_TOUCH((k_pose_sums_chained<false>));
+  SG_TOUCH((k_small_fused<SLAMGPU_OOPE_OBSTACLE, false, false>)); SG_TOUCH((k_small_fused<SLAMGPU_OOPE_GMAPPING, false, false>));
+  SG_TOUCH(k_small_final);
+  SG_TOUCH((k_hill_climb<SLAMGPU_OOPE_OBSTACLE, false>)); SG_TOUCH((k_hill_climb<SLAMGPU_OOPE_GMAPPING, false>));
+  SG_TOUCH((k_monte_carlo<SLAMGPU_OOPE_OBSTACLE, false>));
+  (void)cudaGetLastError();
+}
