@@ -99,7 +99,7 @@ static int ctx_create_common(int device, slamgpu_ctx **out) {
   // kernels loaded now rather than at their first launch in the middle of a scan (SLAMGPU_LAZY_KERNELS=1 skips)
   {
     const char *lazy = getenv("SLAMGPU_LAZY_KERNELS");
-    if (!(lazy && lazy[0] == '1')) { sg_preload_score(); sg_preload_mapping(); }
+    if (!(lazy && lazy[0] == '1')) { sg_preload_score(); sg_preload_mapping(); sg_preload_pyramid(); }
   }
   // pinned staging sized up front: growing it later (cudaFreeHost + cudaMallocHost) can stall a scan for ~100 ms
   void *hp;

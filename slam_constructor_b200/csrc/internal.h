@@ -191,5 +191,6 @@ int sg_scans_upload_xy(slamgpu_ctx *ctx, slamgpu_scan *const *scans, int count, 
 int sg_scan_ensure_xy(slamgpu_scan *s);
 void sg_preload_score();
 void sg_preload_mapping();
+void sg_preload_pyramid();
 void sg_p2p_setup(slamgpu_ctx *ctx);
 void sg_p2p_teardown(slamgpu_ctx *ctx);

@@ -896,3 +896,10 @@ extern "C" int slamgpu_debug_m3rsm(double x_limit, double y_limit, double rot_li
   };
   return m3rsm_search(rots, x_limit, y_limit, transl_step, max_finest_prob_diff, raw, out_delta, out_prob, stats);
 }
+
+#define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
+void sg_preload_pyramid() {  // see sg_preload_score
+  SG_TOUCH(k_order_entries); SG_TOUCH(k_level_coords); SG_TOUCH(k_level_keys); SG_TOUCH(k_level_gather); SG_TOUCH(k_level_fold);
+  SG_TOUCH(k_build_level); SG_TOUCH(k_fill_level); SG_TOUCH(k_window_terms); SG_TOUCH(k_ordered_sums); SG_TOUCH(k_ordered_sums_staged);
+  (void)cudaGetLastError();
+}
