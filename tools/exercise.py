@@ -37,6 +37,8 @@ def main():
     for _ in range(3):
         ctx.append_scan(gm, scan, pose, 0.9, 0, est, blur=0.3)
     ctx.match_hc(gm, scan, sg.spe_params(), pose + [0.06, -0.05, 0.03])   # whole hill-climbing match, one launch
+    shifts = rng.normal(0, [0.2, 0.2, 0.1], (120, 3))
+    ctx.match_mc(gm, scan, sg.spe_params(), pose + [0.06, -0.05, 0.03], shifts, 20, 100)  # Monte-Carlo segment, one launch
     gm.close()
     # K4/K5: pyramid, configs[4]-like at 2048
     gm = sg.GridMap(ctx, 2048, 2048, 0.025, sg.CELL_MEAN, sg.GROW_PLAIN)
