@@ -34,7 +34,7 @@ struct MapSlot {
   int w, h, ox, oy;
   unsigned key_base;   // first sort key of this map (maps are laid end to end in key space)
   unsigned pad;
-  int rx, ry;          // the robot's own cell: every beam updates it once; its chain runs apart (k_apply_robot)
+  int rx, ry;          // the robot's own cell: every beam updates it once; the window around it is updated apart (k_apply_ring)
   int beam_begin, beam_end;  // this map's beams in the batch
 };
 struct GrowState {
