@@ -1,5 +1,5 @@
 """The reference arm of bench.py (`--impl reference`): runs on host cores only, so its JSON contract is checked here on
-the CPU.  The product arm needs a GPU; its line is checked by the driver and by tests/test_gpu_dropin.py's neighbours."""
+the CPU.  The product arm needs a GPU; its line is checked by the gpu-marked test at the end of this file."""
 import json
 import os
 import subprocess
@@ -44,3 +44,27 @@ def test_reference_arm_only_rank_zero_works_under_torchrun():
     assert _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, "--gpus", "2") == []
     lines = _run({"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2"}, "--gpus", "2")
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_product_arm_line_on_the_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--no-secondary"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert (BASE_KEYS - {"impl"}) | {"roofline", "clocks", "gpu_launches"} <= set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["dtype"] == "f64" and d["unit"] == "evals/s"
+    assert d["gpu_launches"] >= 5 and d["value"] > 1e10
+    e = d["e2e"]
+    assert 0 < e["value"] <= d["value"] * 1.05 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and r["peak"] > 0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 * max(1.0, r["frac"])
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
