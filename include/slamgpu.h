@@ -145,9 +145,12 @@ void slamgpu_ctx_destroy(slamgpu_ctx *ctx);
 const char *slamgpu_last_error(const slamgpu_ctx *ctx); /* ctx may be NULL: last create error */
 int slamgpu_sync(slamgpu_ctx *ctx);
 /* tuning knobs (defaults are right for production):
- *   "grid_variant"  highest brute-force grid kernel allowed: 2 = packed row words + L1-resident gathers
- *                   (default, fastest measured), 3 = map patches staged in shared memory by TMA bulk
- *                   copies (kept for comparison: 2.3x slower at configs[2]), 1 = explicit row table */
+ *   "grid_variant"  highest brute-force grid kernel allowed: 0 = automatic (= 4), 4 = every distinct map row gathered
+ *                   once per thread + indexed-branch accumulate (default; needs ascending y, unit point factors and at
+ *                   most 8 cell rows under 8 consecutive y, else 2), 2 = packed row words + L1-resident gathers,
+ *                   3 = map patches staged in shared memory by TMA bulk copies (kept for comparison: 2.3x slower
+ *                   than 2 at configs[2]), 1 = explicit row table
+ *   "grid_rows"     rows per thread of variant 2: 0 = automatic, 2 / 4 / 8 */
 int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_t value);
 /* device-side stop watch on the ctx stream (CUDA events) for bench.py */
 int slamgpu_timer_begin(slamgpu_ctx *ctx);
@@ -250,7 +253,7 @@ int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_p
 int slamgpu_score_launch(slamgpu_ctx *ctx, slamgpu_map *map, double init_score);
 int slamgpu_score_fetch(slamgpu_ctx *ctx, double *out_scores /* NULL ok */, int64_t *best_idx, double *best_score);
 /* counters of the last scoring call: [0] guard hits (points re-done with host trig),
- * [1] kernel variant used (0 list, 1 grid v1, 2 grid v2 / 3 grid v3, 3 two-phase small batch when staged, 4 fused one-launch small batch), [2] evaluations (poses*points) on this rank,
+ * [1] kernel variant used (after slamgpu_stage_grid: 1..4 = grid kernel variant; after slamgpu_stage_poses: 0 list, 3 two-phase small batch, 4 fused one-launch small batch; 5 / 6 whole hill-climbing / Monte-Carlo match), [2] evaluations (poses*points) on this rank,
  * [3] first candidate index of this rank's slice, [4] slice length, [5] grid kernel rows per thread,
  * [6] 1 when the per-rank results were exchanged through peer memory (NVLink mailboxes), 0 for ncclAllGather / one rank */
 int slamgpu_score_stats(const slamgpu_ctx *ctx, int64_t stats[8]);

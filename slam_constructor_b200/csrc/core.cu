@@ -190,7 +190,7 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   sg_p2p_teardown(ctx);
   if (ctx->comm) sg_nccl_destroy(ctx->comm);
   Candidates &c = ctx->cand;
-  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,
+  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.sm_cnt, &c.wtask, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,
                     &c.scores, &c.blk_best, &c.result, &c.gm_pred, &c.gm_in, &c.gm_out, &ctx->flush, &ctx->gather};
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : ctx->scratch) b.release();
@@ -235,13 +235,17 @@ extern "C" int slamgpu_last_kernel_ms(slamgpu_ctx *ctx, float *ms) {
 extern "C" int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_t value) {
   if (!ctx || !name) return SLAMGPU_E_INVALID;
   if (strcmp(name, "grid_variant") == 0) {
-    if (value < 1 || value > 3) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_variant must be 1, 2 or 3");
+    if (value < 0 || value > 4) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_variant must be 0 (automatic), 1, 2, 3 or 4");
     ctx->cand.user_variant = (int)value;
     return SLAMGPU_OK;
   }
   if (strcmp(name, "grid_rows") == 0) {  // rows per thread of the v2 grid kernel: 0 = automatic, or 2 / 4 / 8
     if (value != 0 && value != 2 && value != 4 && value != 8) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_rows must be 0, 2, 4 or 8");
     ctx->cand.user_rows = (int)value;
+    return SLAMGPU_OK;
+  }
+  if (strcmp(name, "warm_l2") == 0) {  // experiment: 0 = no L2 warm-up of the score LUT before big grid launches
+    ctx->cand.warm_l2 = value != 0;
     return SLAMGPU_OK;
   }
   return sg_fail(ctx, SLAMGPU_E_INVALID, "unknown option '%s'", name);
@@ -504,12 +508,15 @@ int sg_map_ensure_lut(slamgpu_map *m, int oie) {
   slamgpu_ctx *ctx = m->ctx;
   if (oie < 0 || oie > 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad oie %d", oie);
   if (m->lut_valid[oie]) return SLAMGPU_OK;
-  size_t need = (size_t)m->pitch * (m->h + 2 * SG_LUT_PAD);
+  // SG_LUT_SLACK_ROWS rows + SG_LUT_SLACK doubles past the padded LUT: k_score_grid4 loads up to 7 rows below the
+  // one it needs, a staged patch row (v3) may run past the last row; the values are never used
+  const size_t rows_used = (size_t)m->pitch * (m->h + 2 * SG_LUT_PAD);
+  size_t need = rows_used + (size_t)m->pitch * SG_LUT_SLACK_ROWS + SG_LUT_SLACK;
   if (need > m->lut_cap[oie]) {
     if (m->d_lut[oie]) cudaFree(m->d_lut[oie]);
     m->d_lut[oie] = nullptr; m->lut_cap[oie] = 0;
-    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], (need + SG_LUT_SLACK) * sizeof(double)));
-    SG_CUDA(ctx, cudaMemsetAsync(m->d_lut[oie] + need, 0, SG_LUT_SLACK * sizeof(double), ctx->stream));
+    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], need * sizeof(double)));
+    SG_CUDA(ctx, cudaMemsetAsync(m->d_lut[oie] + rows_used, 0, (need - rows_used) * sizeof(double), ctx->stream));
     m->lut_cap[oie] = need;
   }
   // the unknown cell's impact, computed by the same device code as every other cell
@@ -693,12 +700,15 @@ extern "C" int slamgpu_map_upload_lut(slamgpu_map *m, int32_t oie, const double 
     }
   }
   m->ox = ox; m->oy = oy;
-  size_t need = (size_t)m->pitch * (m->h + 2 * SG_LUT_PAD);
+  // SG_LUT_SLACK_ROWS rows + SG_LUT_SLACK doubles past the padded LUT: k_score_grid4 loads up to 7 rows below the
+  // one it needs, a staged patch row (v3) may run past the last row; the values are never used
+  const size_t rows_used = (size_t)m->pitch * (m->h + 2 * SG_LUT_PAD);
+  size_t need = rows_used + (size_t)m->pitch * SG_LUT_SLACK_ROWS + SG_LUT_SLACK;
   if (need > m->lut_cap[oie]) {
     if (m->d_lut[oie]) cudaFree(m->d_lut[oie]);
     m->d_lut[oie] = nullptr; m->lut_cap[oie] = 0;
-    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], (need + SG_LUT_SLACK) * sizeof(double)));
-    SG_CUDA(ctx, cudaMemsetAsync(m->d_lut[oie] + need, 0, SG_LUT_SLACK * sizeof(double), ctx->stream));
+    SG_CUDA(ctx, cudaMalloc(&m->d_lut[oie], need * sizeof(double)));
+    SG_CUDA(ctx, cudaMemsetAsync(m->d_lut[oie] + rows_used, 0, (need - rows_used) * sizeof(double), ctx->stream));
     m->lut_cap[oie] = need;
   }
   size_t bytes = std::max<size_t>((size_t)w * h, 1) * sizeof(double);

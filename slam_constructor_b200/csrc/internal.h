@@ -9,6 +9,7 @@
 
 #define SG_LUT_PAD 1  // ring of "unknown" cells around the padded score LUT
 #define SG_LUT_SLACK 512  // doubles allocated past the LUT: a staged patch row may run past the last row
+#define SG_LUT_SLACK_ROWS 7  // whole rows allocated past the LUT (k_score_grid4 loads rows it does not use)
 
 struct DevBuf {  // grow-only device scratch buffer
   void *p = nullptr;
@@ -41,16 +42,22 @@ struct Candidates {  // a staged candidate set (device resident)
   int32_t t_lo = 0, t_hi = 0;  // theta planes touched by this rank
   DevBuf cxp, cyp;   // int32 index tables
   DevBuf cyw;        // v2: packed row words, one per (theta, beam, y-group)
+  DevBuf sm_cnt;     // v4: per-SM task counters
+  DevBuf wtask;      // v4: warp table {first y-group, band | -groups}
+  std::vector<int32_t> h_wtask;
+  int32_t n_warps4 = 0;
   int32_t grid_R = 8, ngy = 0;  // rows per thread of the grid kernel, y-groups per (theta, beam)
   bool grid_v2 = true, force_v1 = false;
-  // 3: TMA-staged patches (experimental, slower: see DESIGN.md), 2: packed rows + L1 gathers (default), 1: explicit row table
-  int grid_variant = 2;   // variant of the staged set
-  int user_variant = 0;   // requested through slamgpu_ctx_set_option / SLAMGPU_GRID_VARIANT (0: default = 2)
-  int max_variant = 3;    // temporary cap while a launch falls back to a simpler variant
+  // 4: each distinct row gathered once per thread + indexed-branch accumulate (default), 3: TMA-staged patches (experimental,
+  // slower: see DESIGN.md), 2: packed rows + L1 gathers (fallback of 4), 1: explicit row table
+  int grid_variant = 4;   // variant of the staged set
+  int user_variant = 0;   // requested through slamgpu_ctx_set_option / SLAMGPU_GRID_VARIANT (0: default = 4)
+  int max_variant = 4;    // temporary cap while a launch falls back to a simpler variant
   DevBuf blocks, blk_rows, porg;          // v3: block table, per (theta, block) y range, patch origins
   int32_t nbt = 0, box_w = 0, box_h = 0, n_blocks3 = 0;
   double h_extent_x = 0, h_extent_y = 0;  // metres spanned by the x sweep / by the y rows of one block
   bool uniform_w = false;
+  bool warm_l2 = true;    // stream the score LUT through L2 before a big grid launch (slamgpu_ctx_set_option "warm_l2")
   // K6: every pose scored against its own particle's map
   bool multi = false;
   DevBuf views, view_id;

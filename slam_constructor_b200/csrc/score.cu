@@ -134,6 +134,23 @@ __global__ void k_exchange_finalize(const Result *mine, void *const *peer_mailbo
   }
 }
 
+// Streams a table through L2 (ld.global.cg: L2 only).  The brute-force kernels make a few data-dependent gathers per beam
+// and can hide an L2 hit, not a DRAM miss (ncu on a cold L2: ~0.8 DRAM sector fetches per warp and beam, ~1000 cycles each,
+// 41 % of all stall samples on the first use of a gathered value).  Reading the 32 MB score LUT once costs ~5 us of HBM
+// time and runs on the side stream beside the index kernels.
+__global__ void k_warm_l2(const double2 *__restrict__ p, size_t n16, double *sink) {
+  double acc = 0.0;
+  const size_t st = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += 4 * st) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * st < n16) ? __ldcg(p + i + u * st) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += v[u].x + v[u].y;
+  }
+  if (acc == -1.2345678e-300) *sink = acc;  // never true for LUT values (they are in [0, 1]); keeps the loads alive
+}
+
 // ------------------------------------------------------------------ trig table
 // ScanPoint2D::move_origin + RawTrigonometryProvider: src/core/states/sensor_data.h:83-87,
 // src/core/trigonometry_utils.h:21-27 -- r*cos(theta + a), r*sin(theta + a)
@@ -898,6 +915,7 @@ struct GridIdxArgs {
   int *cyp;  // [(tl*N + i)*nyp + k]  padded LUT row * pitch            (v1 kernel)
   unsigned long long *cyw;  // [(tl*N + i)*ngy + gy] packed rows of one y-group (v2 kernel)
   int v2, R, ngy;
+  int v4, dmax;  // v4 row word: low 32 bits = element offset of the first y's padded LUT row, bits 32..38 = "new row" mask
   // v3 (TMA-staged patches): per (theta, beam, block-of-theta) patch origin {first padded column, first padded row}
   int v3, nbt, box_w, box_h;
   const int2 *blk_rows;  // [nbt] y range {k_lo, k_hi} (inclusive) each block of a theta touches
@@ -997,6 +1015,23 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
       const int pr = e / a.ngy, gy = e - pr * a.ngy;
       const int *rows = sh_rows + pr * a.ny;
       const int k0 = gy * a.R;
+      if (a.v4) {
+        // k_score_grid4: rows of the group must be base, base + 1, ... (steps of 0 or 1, fewer than dmax distinct ones)
+        unsigned mask = 0;
+        int prev4 = rows[k0], distinct = 1;
+        bool ok = true;
+        for (int m = 1; m < 8; ++m) {
+          const int k = k0 + m;
+          const int prow = k < a.ny ? rows[k] : prev4;
+          const int d = prow - prev4;
+          if (d == 1) { mask |= 1u << (m - 1); ++distinct; }
+          else if (d != 0) ok = false;
+          prev4 = prow;
+        }
+        if (!ok || distinct > a.dmax) atomicAdd((unsigned long long *)&a.result->pad, 1ull);
+        a.cyw[(ti0 + pr) * a.ngy + gy] = ((unsigned long long)mask << 32) | (unsigned)(rows[k0] * a.pitch);
+        continue;
+      }
       unsigned long long word = (unsigned)rows[k0];
       int prev = rows[k0];
       for (int m = 1; m < a.R; ++m) {
@@ -1173,6 +1208,206 @@ __global__ void __launch_bounds__(128) k_score_grid2(GridArgs2 a) {
   block_argmax(best_s, best_i, a.blk + blockIdx.x);
 }
 
+
+// v4 of the grid kernel: each distinct map row is gathered once per thread.
+// The 8 consecutive y of a thread (0.02 m apart on 0.05 m cells in configs[2]) fall into 3-4 consecutive cell rows, so
+// v2 gathers, multiplies and address-computes the same LUT entry two or three times.  Here the thread loads the DMAX
+// consecutive rows base..base+DMAX-1 of its column once (one IMAD.WIDE + LDG each, row base pointers in uniform
+// registers), multiplies each by the point weight once, and a 7-bit "new row" mask from the index kernel says which
+// product every accumulator takes.  The mask is the same for a whole warp (lanes = 32 consecutive x of one y-group), so
+// it selects one of 128 straight-line bodies of 8 DADDs through an indexed branch (brx.idx; grid4_dispatch.inc,
+// generated by tools/gen_grid4_dispatch.py -- NVVM lowers a C++ switch to a 12-instruction compare tree instead).
+// The adds are the same FP64 adds in the same (beam) order as in every other variant: scores are bit-identical.
+// Columns are split into bands of 32 so that full bands give warp-uniform masks; the nx % 32 leftover columns are
+// packed several y-groups to a warp (the branch diverges there, which is correct, only slower).
+struct GridArgs4 {
+  const double *lut;
+  const unsigned *cxp;
+  const uint2 *cyw;
+  const int4 *groups;  // {t, k0, m_lo, m_hi}
+  int n_groups, nx, ny, ngy, N, t_lo, pitch;
+  int nb_full, wr;         // full 32-column bands per y-group, width of the leftover band
+  const int2 *wtask;       // warp table (see grid4_task)
+  int n_warps;
+  const double *w;
+  double w0, wsum;
+  long long p0;
+  double *scores;
+  Best *blk;
+  int *sm_cnt;  // per-chunk task counters, zeroed before the launch (NULL: task = blockIdx.x)
+  int n_chunks, chunk;  // chunks (= SMs), tasks per chunk
+  unsigned zero;        // 0 (a run-time value: see the beam loop)
+};
+
+#define SG_G4_DEPTH 4  // stages of the index ring (power of two); the index tables carry that many beam rows of slack
+SG_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+SG_DEV void cp_async4(unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+SG_DEV void cp_async8(unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+SG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+SG_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+SG_DEV uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+template <class T>
+SG_DEV T *opaque_ptr(T *p, unsigned zero) {
+  unsigned long long v = (unsigned long long)p;
+  asm volatile("{ .reg .u64 z; cvt.u64.u32 z, %1; add.u64 %0, %0, z; }" : "+l"(v) : "r"(zero));
+  return (T *)v;
+}
+
+template <int DMAX>
+SG_DEV void add_pattern(unsigned mask, double (&acc)[8], const double (&t)[DMAX]) {
+  // ranks past DMAX-1 never occur (k_grid_indices counts such groups and the call falls back to v2): any register will do
+#define SG_G4T(d) t[(d) < DMAX ? (d) : DMAX - 1]
+  asm(
+#include "grid4_dispatch.inc"
+      : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+d"(acc[4]), "+d"(acc[5]), "+d"(acc[6]), "+d"(acc[7])
+      : "d"(SG_G4T(0)), "d"(SG_G4T(1)), "d"(SG_G4T(2)), "d"(SG_G4T(3)), "d"(SG_G4T(4)), "d"(SG_G4T(5)), "d"(SG_G4T(6)),
+        "d"(SG_G4T(7)), "r"(mask));
+#undef SG_G4T
+}
+
+// thread -> (y-group, column) through the warp table: warp w of the launch (4 per task) takes wtask[w] = {first y-group, band}
+// -- a full band of 32 columns of one y-group -- or {first y-group, -count}: the nx % 32 leftover columns of `count`
+// consecutive y-groups packed into one warp.  false: no work, (0, 0) returned: a thread without work walks group 0 / column 0
+// and drops the result, so that the beam loop sits in uniform control flow.
+SG_DEV bool grid4_task(const GridArgs4 &a, int task, int &g, int &j) {
+  const int w = task * 4 + (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  bool valid = false;
+  g = 0; j = 0;
+  if (task >= 0 && w < a.n_warps) {
+    const int2 e = __ldg(a.wtask + w);
+    if (e.y >= 0) {
+      g = e.x; j = e.y * 32 + lane; valid = true;
+    } else if (lane < -e.y * a.wr) {
+      const int k = lane / a.wr;
+      g = e.x + k; j = a.nb_full * 32 + (lane - k * a.wr); valid = true;
+    }
+  }
+  return valid;
+}
+
+template <int DMAX, bool UNIW>
+__global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_score_grid4(GridArgs4 a) {
+  // 7 blocks of 4 warps per SM (72 registers) hold configs[2]'s 1026 blocks in ONE wave: every task (a warp walking all the
+  // beams) takes the same time, so a second, nearly empty wave would double the kernel time
+  // Which 128 candidates-columns this block takes.  Blocks are handed out per SM: the work is cut into one contiguous chunk
+  // per SM (neighbouring y-groups of the same theta read the same LUT lines for a given beam), so that the warps resident on
+  // an SM share their gathers in L1.  With blocks dealt round-robin (task = blockIdx.x) every SM holds ~7 different thetas,
+  // every LUT line of a beam's patch is requested by most SMs at about the same time (all warps walk the beams in step) and
+  // the L2 slices serve those bursts one sector at a time: ncu showed ~1000 cycles from gather to first use.  A block that
+  // finds its SM's chunk empty takes a leftover task of another chunk (every task is taken exactly once).
+  __shared__ int s_task;
+  if (threadIdx.x == 0) {
+    int task = -1;
+    if (a.sm_cnt) {
+      unsigned smid;
+      asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      const int nsm = a.n_chunks, per = a.chunk;
+      int s0 = (int)(smid % (unsigned)nsm);
+      for (int k = 0; k < nsm && task < 0; ++k) {
+        const int s2 = s0 + k < nsm ? s0 + k : s0 + k - nsm;
+        if (*(volatile int *)(a.sm_cnt + s2) >= per) continue;
+        const int c2 = atomicAdd(a.sm_cnt + s2, 1);
+        if (c2 < per && s2 * per + c2 < (int)gridDim.x) task = s2 * per + c2;
+      }
+    } else {
+      task = blockIdx.x;
+    }
+    s_task = task;
+  }
+  __syncthreads();
+  int g, j;
+  bool valid = grid4_task(a, *(volatile int *)&s_task, g, j);
+  // element offsets into the index tables (the host checks that they fit 32 bits): one register each instead of a pointer pair
+  unsigned ox, ow;
+  {
+    const int4 grp = __ldg(a.groups + g);
+    const int tl = grp.x - a.t_lo;
+    ox = (unsigned)tl * (unsigned)a.N * (unsigned)a.nx + (unsigned)j;
+    ow = (unsigned)tl * (unsigned)a.N * (unsigned)a.ngy + (unsigned)(grp.y >> 3);
+  }
+  // Loop invariants are made opaque to ptxas with a real instruction (an add of a run-time zero): otherwise it re-derives
+  // them from the constant bank every beam (LDC + IMAD.WIDE), and those LDCs occupy the scoreboards the loads need.
+  const unsigned zero = a.zero;  // 0, but not to the compiler
+  const double *rowp[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) rowp[d] = opaque_ptr(a.lut + (size_t)d * (size_t)a.pitch, zero);
+  const unsigned *const cxp = opaque_ptr(a.cxp, zero);
+  const uint2 *const cyw = opaque_ptr(a.cyw, zero);
+  const unsigned sx = a.nx, sw = a.ngy;
+  const int N = a.N;
+  const double w0 = a.w0;
+  double acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+  // Software pipeline without register rotation: the beam loop is unrolled by two; index set A serves the odd beams, B the
+  // even ones (each reloaded two beams ahead of its use, right after it was consumed), value sets v0 / v1 alternate.
+  // The index tables carry four zeroed beam rows of slack, so the prefetches past the last beam need no guard.
+  double v0[DMAX], v1[DMAX];
+  unsigned m0, m1 = 0;
+  {
+    const unsigned cx0 = __ldcg(cxp + ox);
+    const uint2 cw0 = __ldcg(cyw + ow);
+    m0 = cw0.y;
+    const unsigned b = cw0.x + cx0;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) v0[d] = __ldg(rowp[d] + b);
+  }
+  // the index tables are streamed (L2 only: they would only push LUT lines out of L1); two register sets, A for the odd beams
+  // and B for the even ones, each reloaded in place right after it was consumed (two beams ahead of its next use)
+  unsigned cxA = __ldcg(cxp + (ox + sx)), cxB = __ldcg(cxp + (ox + 2 * sx));
+  uint2 cwA = __ldcg(cyw + (ow + sw)), cwB = __ldcg(cyw + (ow + 2 * sw));
+  ox += 3 * sx; ow += 3 * sw;
+  // One half of the loop body (beam I, values in VCUR): FIRST the products -- the place where the warp waits for its loads --,
+  // THEN the gathers of beam I+1, whose address is made to depend on a product so that the scheduler cannot hoist them above
+  // that wait, then the reload of the index set, then the adds.
+#define SG_G4_HALF(VCUR, VNXT, MCUR, MNXT, CX, CW, I)                                      \
+  {                                                                                       \
+    const double wi = UNIW ? w0 : __ldg(a.w + (I));                                       \
+    double t[DMAX];                                                                       \
+    _Pragma("unroll") for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(VCUR[d], wi);         \
+    const unsigned b = CW.x + CX + ((unsigned)__double2hiint(t[0]) & zero);               \
+    MNXT = CW.y;                                                                          \
+    _Pragma("unroll") for (int d = 0; d < DMAX; ++d) VNXT[d] = __ldg(rowp[d] + b);        \
+    CX = __ldcg(cxp + ox); CW = __ldcg(cyw + ow);                                         \
+    ox += sx; ow += sw;                                                                   \
+    add_pattern<DMAX>(MCUR, acc, t);                                                      \
+  }
+#pragma unroll 1
+  for (int i = 0; i < N; i += 2) {
+    SG_G4_HALF(v0, v1, m0, m1, cxA, cwA, i)
+    if (i + 1 < N) SG_G4_HALF(v1, v0, m1, m0, cxB, cwB, i + 1)
+  }
+#undef SG_G4_HALF
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  // (group, column) are derived again from the task number rather than kept in registers across the beam loop
+  valid = grid4_task(a, *(volatile int *)&s_task, g, j);
+  if (valid) {
+    const int4 grp = __ldg(a.groups + g);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      if (m < grp.z || m >= grp.w) continue;
+      double score = a.wsum == 0 ? NAN : sg::div(acc[m], a.wsum);
+      long long idx = ((long long)grp.x * a.ny + (grp.y + m)) * a.nx + j;
+      a.scores[idx - a.p0] = score;
+      if (score == score && beats(score, idx, best_s, best_i)) { best_s = score; best_i = idx; }
+    }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+template <int DMAX>
+void launch_grid4(slamgpu_ctx *ctx, const GridArgs4 &a, int nblk, bool uniw) {
+  if (uniw) k_score_grid4<DMAX, true><<<nblk, 128, 0, ctx->stream>>>(a);
+  else k_score_grid4<DMAX, false><<<nblk, 128, 0, ctx->stream>>>(a);
+}
+
 // ---------------------------------------------------------------- v3: map patches staged in shared memory by TMA
 // For one beam, every candidate of a block reads cells from one small patch of the LUT (the block's y rows
 // x the whole x sweep: about 10 x 44 cells).  Warp 0 asks the TMA unit for that patch S beams ahead, one
@@ -1181,7 +1416,6 @@ __global__ void __launch_bounds__(128) k_score_grid2(GridArgs2 a) {
 // misses into L2.  (The 2-D tensor form, cp.async.bulk.tensor / UTMALDG, faults with "illegal
 // instruction" on this pool's driver even in a minimal probe -- tools/scratch/tma_probe.cu -- so rows
 // are copied individually; patch columns start at an even column to keep the 16-byte source alignment.)
-SG_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 SG_DEV void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -1404,6 +1638,7 @@ int upload_host_trig(slamgpu_ctx *ctx, Candidates &c, const std::vector<double> 
 }
 
 #define SG_LIST_MAX_TABLE_BYTES (1ull << 30)
+#define SG_IDX_SLACK 8  // zeroed beam rows behind the grid index tables (k_score_grid4 prefetches past the last beam)
 
 }  // namespace
 
@@ -1478,8 +1713,14 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   c.P = (int64_t)nt * ny * nx;
   {
     static const int env_variant = [] { const char *e = getenv("SLAMGPU_GRID_VARIANT"); return e ? atoi(e) : 0; }();
-    int v = c.user_variant ? c.user_variant : (env_variant >= 1 && env_variant <= 3 ? env_variant : 2);
-    v = std::min(v, c.max_variant);
+    int v = c.user_variant ? c.user_variant : (env_variant >= 1 && env_variant <= 4 ? env_variant : 4);
+    if (v == 4) {
+      // k_score_grid4 needs ascending y (cell rows of a thread's 8 y then step by 0 or 1) and unit factors
+      bool asc = !scan->has_factor;
+      for (int k = 1; k < ny && asc; ++k) asc = ys[k] > ys[k - 1];
+      if (!asc || c.user_rows == 2 || c.user_rows == 4) v = 2;
+    }
+    if (v > c.max_variant) v = std::min(c.max_variant, 2);  // 4 and 3 fall back to 2, then 1
     if (c.force_v1) v = 1;
     if ((size_t)ny * SG_IDX_PAIRS * sizeof(int) > 40 * 1024) v = 1;  // the index kernel stages the rows in smem
     c.grid_variant = v;
@@ -1491,8 +1732,8 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     slice_of(ctx, (int64_t)nt * ny, &r0_, &r1_);
     const int64_t want_threads = (int64_t)ctx->sm_count * 768;
     int R = 8;
-    while (c.grid_v2 && R > 2 && ((r1_ - r0_ + R - 1) / R) * nx < want_threads) R /= 2;
-    if (c.user_rows) R = c.user_rows;
+    while (c.grid_v2 && c.grid_variant != 4 && R > 2 && ((r1_ - r0_ + R - 1) / R) * nx < want_threads) R /= 2;
+    if (c.user_rows && c.grid_variant != 4) R = c.user_rows;
     c.grid_R = c.grid_v2 ? R : SG_GRID_R;
     c.ngy = (ny + c.grid_R - 1) / c.grid_R;
   }
@@ -1578,17 +1819,38 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   if (p->trig_mode == SLAMGPU_TRIG_HOST) SG_TRY(upload_host_trig(ctx, c, c.h_ts, N, 1));
   const int64_t Ploc = c.p1 - c.p0;
   long long threads = (long long)c.n_groups * nx;
-  int nblk = std::max((int)((threads + 127) / 128), (int)c.n_blocks3);
+  // (v4 packs the leftover columns of several y-groups into one warp: at most one extra warp per y-group)
+  int nblk = std::max((int)((threads + 127) / 128), (int)c.n_blocks3) + (c.n_groups + 3) / 4 + 1;
   if (c.grid_variant == 3 && c.porg.reserve(std::max<size_t>((size_t)nt_loc * N * std::max(c.nbt, 1), 1) * sizeof(int2)) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "patch origin table");
-  if (c.cxp.reserve(std::max<size_t>((size_t)nt_loc * N * nx, 1) * sizeof(int)) != SLAMGPU_OK ||
+  // beam rows of slack behind the index tables: k_score_grid4 prefetches past the last beam without a guard
+  const size_t idx_rows = (size_t)nt_loc * N + SG_IDX_SLACK;
+  if (c.cxp.reserve(idx_rows * nx * sizeof(int)) != SLAMGPU_OK ||
       c.cyp.reserve(std::max<size_t>(c.grid_v2 ? 1 : (size_t)nt_loc * N * c.nyp, 1) * sizeof(int)) != SLAMGPU_OK ||
-      c.cyw.reserve(std::max<size_t>(c.grid_v2 ? (size_t)nt_loc * N * c.ngy : 1, 1) * sizeof(unsigned long long)) != SLAMGPU_OK ||
+      c.cyw.reserve(std::max<size_t>(c.grid_v2 ? idx_rows * c.ngy : 1, 1) * sizeof(unsigned long long)) != SLAMGPU_OK ||
       c.scores.reserve(std::max<size_t>(Ploc, 1) * sizeof(double)) != SLAMGPU_OK ||
       c.blk_best.reserve(std::max(nblk, 1) * sizeof(Best)) != SLAMGPU_OK ||
-      c.result.reserve(sizeof(Result) * 2) != SLAMGPU_OK ||
+      c.result.reserve(sizeof(Result) * 2 + 64) != SLAMGPU_OK ||
       ctx->gather.reserve(sizeof(Result) * std::max(ctx->nranks, 1)) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "grid score buffers");
+  if (c.grid_variant == 4) {
+    // warp table: the full bands of G = 32 / (nx % 32) consecutive y-groups, then ONE warp with the leftover columns of those
+    // groups -- slow warps (their indexed branch diverges) so spread evenly over the launch
+    std::vector<int32_t> &wt = c.h_wtask;
+    wt.clear();
+    const int nbf = nx / 32, wr = nx % 32, G = wr ? 32 / wr : c.n_groups + 1;
+    for (int g0 = 0; g0 < c.n_groups; g0 += G) {
+      const int g1 = std::min(g0 + G, (int)c.n_groups);
+      for (int g = g0; g < g1; ++g)
+        for (int b = 0; b < nbf; ++b) { wt.push_back(g); wt.push_back(b); }
+      if (wr) { wt.push_back(g0); wt.push_back(-(g1 - g0)); }
+    }
+    c.n_warps4 = (int32_t)(wt.size() / 2);
+    SG_TRY(upload(ctx, c.wtask, wt.data(), wt.size() * sizeof(int32_t)));
+    SG_CUDA(ctx, cudaMemsetAsync(c.cxp.as<int>() + (idx_rows - SG_IDX_SLACK) * nx, 0, SG_IDX_SLACK * (size_t)nx * sizeof(int), ctx->stream));
+    SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngy, 0, SG_IDX_SLACK * (size_t)c.ngy * sizeof(unsigned long long),
+                                 ctx->stream));
+  }
   c.kind = 1;
   return SLAMGPU_OK;
 }
@@ -1726,7 +1988,43 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
         return launch_staged(ctx, map, init_score);
       }
     }
+    int dmax = 0;
+    if (c.grid_variant == 4) {
+      // distinct cell rows the 8 y of one thread can touch: floor(span / cell) + 2, at most 8 (else v2)
+      double span = 0;
+      for (int k0 = 0; k0 < c.ny; k0 += 8) span = std::max(span, c.h_ys[std::min(k0 + 7, c.ny - 1)] - c.h_ys[k0]);
+      const double cells = std::floor(span / map->scale) + 2.0;
+      const size_t lut_elems = (size_t)map->pitch * (map->h + 2 * SG_LUT_PAD + SG_LUT_SLACK_ROWS);
+      const size_t idx_elems = ((size_t)(c.t_hi - c.t_lo + 1) * N + SG_IDX_SLACK) * (size_t)std::max(c.nx, c.ngy);
+      if (!(cells <= 8.0) || lut_elems >= (1ull << 31) || idx_elems >= (1ull << 32) || N <= 0) {
+        const int saved_max = c.max_variant;
+        c.max_variant = 2;
+        slamgpu_spe_params spe = c.spe;
+        std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
+        int r = slamgpu_stage_grid(ctx, c.scan, &spe, xs.data(), (int32_t)xs.size(), ys.data(), (int32_t)ys.size(), ts.data(),
+                                   (int32_t)ts.size());
+        c.max_variant = saved_max;
+        SG_TRY(r);
+        return launch_staged(ctx, map, init_score);
+      }
+      dmax = std::max(2, (int)cells);
+      if (dmax == 7) dmax = 8;
+    }
     const int nt_loc = c.t_hi - c.t_lo + 1;
+    // big sets: make the score LUT L2-resident while the trig / index kernels run (side stream)
+    static const bool env_warm = [] { const char *e = getenv("SLAMGPU_WARM_L2"); return !e || atoi(e) != 0; }();
+    const bool warm = (long long)Ploc * N >= (1ll << 26) && c.warm_l2 && env_warm;
+    if (warm) {
+      const size_t lut_bytes = (size_t)map->pitch * (map->h + 2 * SG_LUT_PAD) * sizeof(double);
+      if (lut_bytes <= (96ull << 20)) {
+        SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        SG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        k_warm_l2<<<ctx->sm_count * 4, 256, 0, ctx->side>>>(reinterpret_cast<const double2 *>(map->d_lut[oie]), lut_bytes / 16,
+                                                            c.result.as<double>() + 8);
+        SG_LAUNCHED(ctx);
+        SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+      }
+    }
     if (device_trig && N > 0) {
       long long tot = (long long)c.nt * N;
       k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.p_ts, c.nt, s->d_range, s->d_angle,
@@ -1743,6 +2041,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       ia.guard = device_trig ? 1 : 0;
       ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
       ia.cyw = c.cyw.as<unsigned long long>(); ia.v2 = c.grid_v2 ? 1 : 0; ia.R = c.grid_R; ia.ngy = c.ngy;
+      ia.v4 = c.grid_variant == 4 ? 1 : 0; ia.dmax = dmax;
       ia.v3 = c.grid_variant == 3 ? 1 : 0; ia.nbt = c.nbt; ia.box_w = c.box_w; ia.box_h = c.box_h;
       ia.blk_rows = c.blk_rows.as<int2>(); ia.porg = c.porg.as<int2>();
       {
@@ -1752,6 +2051,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       }
       SG_LAUNCHED(ctx);
     }
+    if (warm) SG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // no-op if the event was not recorded in this call
     if (nblk > 0 && c.grid_variant == 3) {
       GridArgs3 a;
       a.lut = map->d_lut[oie]; a.pitch = map->pitch; a.lut_rows = map->h + 2 * SG_LUT_PAD;
@@ -1766,6 +2066,37 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       if (c.grid_R == 8) launch_grid3<8>(ctx, a, nblk, shm, s->has_factor, c.uniform_w);
       else if (c.grid_R == 4) launch_grid3<4>(ctx, a, nblk, shm, s->has_factor, c.uniform_w);
       else launch_grid3<2>(ctx, a, nblk, shm, s->has_factor, c.uniform_w);
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->evk_valid = true;
+      SG_LAUNCHED(ctx);
+    } else if (nblk > 0 && c.grid_variant == 4) {
+      GridArgs4 a;
+      a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<unsigned>(); a.cyw = c.cyw.as<uint2>(); a.groups = c.groups.as<int4>();
+      a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.N = N; a.t_lo = c.t_lo; a.pitch = map->pitch;
+      a.nb_full = c.nx / 32; a.wr = c.nx % 32;
+      a.w = s->d_w; a.w0 = s->weight[0]; a.wsum = s->wsum; a.p0 = c.p0;
+      a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>();
+      a.wtask = c.wtask.as<int2>(); a.n_warps = c.n_warps4;
+      nblk = (c.n_warps4 + 3) / 4;
+      {
+        static const bool env_affine = [] { const char *e = getenv("SLAMGPU_SM_AFFINE"); return !e || atoi(e) != 0; }();
+        a.zero = 0u;
+        a.sm_cnt = nullptr; a.n_chunks = ctx->sm_count; a.chunk = (nblk + ctx->sm_count - 1) / ctx->sm_count;
+        if (env_affine && nblk > ctx->sm_count) {
+          if (c.sm_cnt.reserve(sizeof(int) * (size_t)ctx->sm_count) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "task counters");
+          SG_CUDA(ctx, cudaMemsetAsync(c.sm_cnt.p, 0, sizeof(int) * (size_t)ctx->sm_count, ctx->stream));
+          a.sm_cnt = c.sm_cnt.as<int>();
+        }
+      }
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      switch (dmax) {
+        case 2: launch_grid4<2>(ctx, a, nblk, c.uniform_w); break;
+        case 3: launch_grid4<3>(ctx, a, nblk, c.uniform_w); break;
+        case 4: launch_grid4<4>(ctx, a, nblk, c.uniform_w); break;
+        case 5: launch_grid4<5>(ctx, a, nblk, c.uniform_w); break;
+        case 6: launch_grid4<6>(ctx, a, nblk, c.uniform_w); break;
+        default: launch_grid4<8>(ctx, a, nblk, c.uniform_w); break;
+      }
       cudaEventRecord(ctx->evk1, ctx->stream);
       ctx->evk_valid = true;
       SG_LAUNCHED(ctx);
@@ -1851,10 +2182,11 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (h->idx == LLONG_MIN) return sg_fail(ctx, SLAMGPU_E_NCCL, "a peer rank did not deliver its result within 2 s (peer-memory exchange)");
   while (h->pad > 0 && c.kind == 1 && c.grid_variant > 1 && map) {
-    // v3: some block's cells did not fit its TMA box -> v2; v2: two neighbouring y values are more than
-    // 7 cell rows apart, the packed row word cannot hold it -> the explicit row table (v1 kernel)
+    // v4: some thread's 8 y do not fall into consecutive cell rows -> v2; v3: some block's cells did not fit its TMA box
+    // -> v2; v2: two neighbouring y values are more than 7 cell rows apart, the packed row word cannot hold it -> the
+    // explicit row table (v1 kernel)
     const int saved_max = c.max_variant;
-    c.max_variant = c.grid_variant - 1;
+    c.max_variant = c.grid_variant >= 3 ? 2 : 1;
     slamgpu_spe_params spe = c.spe;
     std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
     double init = c.init_score;

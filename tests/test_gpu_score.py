@@ -272,15 +272,19 @@ def test_full_size_bruteforce_properties(sg, gpu):
     gm.close(); gsc.close()
 
 
-@pytest.mark.parametrize("max_variant", [3, 2])
+@pytest.mark.parametrize("max_variant", [4, 3, 2])
 @pytest.mark.parametrize("nx,ny,nt,ystep,expect_R,fits_box,fits_nibbles", [
-    (33, 19, 5, 0.02, 2, True, True),         # few candidates: 2 rows per thread
-    (400, 160, 8, 0.02, 4, True, True),       # medium: 4 rows per thread
+    (33, 19, 5, 0.02, 2, True, True),         # few candidates: 2 rows per thread (v4: point factors -> v2)
+    (400, 160, 8, 0.02, 4, True, True),       # medium: 4 rows per thread (v4: always 8)
     (300, 400, 12, 0.013, 8, True, True),     # many: 8 rows per thread
+    (101, 53, 7, 0.049, 2, True, True),       # y step just under a cell: 8 distinct rows per thread (v4 with DMAX = 8)
+    (37, 21, 3, 0.031, 2, True, True),        # leftover columns only from the second band on; DMAX = 6
     (21, 10, 3, 0.6, 8, False, False),        # y values far apart: no TMA box, no nibble deltas -> explicit row table (v1)
-    (40, 17, 4, -0.03, 2, True, True),        # decreasing y: negative row deltas
+    (40, 17, 4, -0.03, 2, True, True),        # decreasing y: negative row deltas (v4 -> v2)
 ])
 def test_grid_kernel_variants(sg, gpu, max_variant, nx, ny, nt, ystep, expect_R, fits_box, fits_nibbles):
+    if max_variant == 3 and nx in (101, 37):
+        pytest.skip("the two v4-specific shapes are not run through the experimental TMA variant")
     rng = np.random.default_rng(1700 + nx)
     om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_MEAN, 73, spw=ob.SPW_AHR, factor=(nx == 33))
     xs = p0[0] + 0.011 * (np.arange(nx) - nx // 2)
@@ -291,15 +295,42 @@ def test_grid_kernel_variants(sg, gpu, max_variant, nx, ny, nt, ystep, expect_R,
     try:
         got, idx, best = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
     finally:
-        gpu.set_option("grid_variant", 2)
+        gpu.set_option("grid_variant", 0)
     st = gpu.score_stats()
     pick = rng.choice(len(P), min(len(P), 4000), replace=False)
     want = om.score(osc, ob.spe_params(), P[pick])
     assert np.array_equal(got[pick], want)
     assert idx == int(np.argmax(got)) and best == got[idx]
-    expect_variant = 1 if not fits_nibbles else (3 if (max_variant == 3 and fits_box) else 2)
-    assert st["variant"] == expect_variant and st["rows_per_thread"] == expect_R, st
+    v4 = max_variant == 4 and ystep > 0 and fits_nibbles and nx != 33
+    expect_variant = 4 if v4 else (1 if not fits_nibbles else (3 if (max_variant == 3 and fits_box) else 2))
+    assert st["variant"] == expect_variant and st["rows_per_thread"] == (8 if v4 else expect_R), st
     gm.close(); gsc.close()
+
+
+def test_grid_row_dedupe_kernel_against_the_general_one(sg, gpu):
+    """k_score_grid4 (default) against k_score_grid2 on the same candidate grids, every score: all DMAX instantiations
+    (y steps from a fifth of a cell to a full cell), column counts around the 32-wide bands, uneven point weights"""
+    rng = np.random.default_rng(1750)
+    for nx, ny, nt, ystep, spw in [(32, 8, 2, 0.004, ob.SPW_EVEN), (65, 23, 3, 0.012, ob.SPW_VINY), (31, 40, 2, 0.02, ob.SPW_EVEN),
+                                   (101, 101, 2, 0.02, ob.SPW_EVEN), (96, 9, 4, 0.027, ob.SPW_AHR), (70, 33, 2, 0.035, ob.SPW_EVEN),
+                                   (45, 17, 3, 0.0499, ob.SPW_VINY), (5, 64, 3, 0.02, ob.SPW_EVEN)]:
+        om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_TBM_CONSISTENT, 97, spw=spw)
+        xs = p0[0] + 0.013 * (np.arange(nx) - nx // 2)
+        ys = p0[1] + ystep * (np.arange(ny) - ny // 2)
+        ts = p0[2] + 0.02 * (np.arange(nt) - nt // 2)
+        got4, idx4, best4 = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+        assert gpu.score_stats()["variant"] == 4
+        gpu.set_option("grid_variant", 2)
+        try:
+            got2, idx2, best2 = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+        finally:
+            gpu.set_option("grid_variant", 0)
+        assert gpu.score_stats()["variant"] == 2
+        assert np.array_equal(got4, got2) and (idx4, best4) == (idx2, best2)
+        P = np.stack(np.meshgrid(ts, ys, xs, indexing="ij"), -1).reshape(-1, 3)[:, ::-1]
+        pick = rng.choice(len(P), min(len(P), 1500), replace=False)
+        assert np.array_equal(got4[pick], om.score(osc, ob.spe_params(), P[pick]))
+        gm.close(); gsc.close()
 
 
 @pytest.mark.parametrize("mode", ["obstacle", "max", "mean", "gmapping"])

@@ -1,0 +1,23 @@
+"""K1 at the configs[2] shape, a few launches: the command ncu wraps (tools/..., not a bench: no number printed here counts)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+import slam_constructor_b200 as sg
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+ctx = sg.Context(0)
+wl = bench.make_workload()
+gm = sg.GridMap(ctx, bench.MAP_SIZE, bench.MAP_SIZE, bench.MAP_SCALE, sg.CELL_MEAN)
+gm.upload(wl["cells"])
+scan = sg.Scan(ctx, wl["r"], wl["a"])
+params = sg.spe_params(sg.OOPE_OBSTACLE, sg.OIE_DISCREPANCY, trig=sg.TRIG_DEVICE)
+ctx.stage_grid(scan, params, wl["xs"], wl["ys"], wl["ts"])
+tot = 0.0
+for _ in range(n):
+    if not os.environ.get("NOFLUSH"):
+        ctx.flush_l2()
+    ctx.score_launch(gm)
+    ctx.sync()
+    tot += ctx.last_kernel_ms()
+_, idx, best = ctx.score_fetch()
+print("variant", ctx.score_stats()["variant"], "kernel ms (not a bench value)", tot / n, idx, best)
