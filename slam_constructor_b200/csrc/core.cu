@@ -190,7 +190,7 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   sg_p2p_teardown(ctx);
   if (ctx->comm) sg_nccl_destroy(ctx->comm);
   Candidates &c = ctx->cand;
-  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.sm_cnt, &c.wtask, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,
+  DevBuf *bufs[] = {&c.poses, &c.theta_id, &c.d_thetas, &c.d_xs, &c.d_ys, &c.groups, &c.cxp, &c.cyp, &c.cyw, &c.sm_cnt, &c.wtask, &c.colrec, &c.w2, &c.views, &c.view_id, &c.blocks, &c.blk_rows, &c.porg, &c.trc, &c.trs,
                     &c.scores, &c.blk_best, &c.result, &c.gm_pred, &c.gm_in, &c.gm_out, &ctx->flush, &ctx->gather};
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : ctx->scratch) b.release();
@@ -235,7 +235,7 @@ extern "C" int slamgpu_last_kernel_ms(slamgpu_ctx *ctx, float *ms) {
 extern "C" int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_t value) {
   if (!ctx || !name) return SLAMGPU_E_INVALID;
   if (strcmp(name, "grid_variant") == 0) {
-    if (value < 0 || value > 4) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_variant must be 0 (automatic), 1, 2, 3 or 4");
+    if (value < 0 || value > 5) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_variant must be 0 (automatic) or 1..5");
     ctx->cand.user_variant = (int)value;
     return SLAMGPU_OK;
   }

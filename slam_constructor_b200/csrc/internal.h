@@ -43,16 +43,20 @@ struct Candidates {  // a staged candidate set (device resident)
   DevBuf cxp, cyp;   // int32 index tables
   DevBuf cyw;        // v2: packed row words, one per (theta, beam, y-group)
   DevBuf sm_cnt;     // v4: per-SM task counters
+  DevBuf colrec, w2;  // v5: column records per (theta, beam, band); weight pairs
+  std::vector<double> h_w2;
+  int32_t nb5 = 0, bw5 = 0;  // v5: bands per y-group, columns per band
   DevBuf wtask;      // v4: warp table {first y-group, band | -groups}
   std::vector<int32_t> h_wtask;
   int32_t n_warps4 = 0;
+  int32_t ngys = 0;  // row stride of cyw (v4 / v5: ngy rounded up to even)
   int32_t grid_R = 8, ngy = 0;  // rows per thread of the grid kernel, y-groups per (theta, beam)
   bool grid_v2 = true, force_v1 = false;
-  // 4: each distinct row gathered once per thread + indexed-branch accumulate (default), 3: TMA-staged patches (experimental,
+  // 5: v4's arithmetic behind a cp.async pipeline (default), 4: each distinct row gathered once per thread + indexed-branch accumulate, 3: TMA-staged patches (experimental,
   // slower: see DESIGN.md), 2: packed rows + L1 gathers (fallback of 4), 1: explicit row table
-  int grid_variant = 4;   // variant of the staged set
-  int user_variant = 0;   // requested through slamgpu_ctx_set_option / SLAMGPU_GRID_VARIANT (0: default = 4)
-  int max_variant = 4;    // temporary cap while a launch falls back to a simpler variant
+  int grid_variant = 5;   // variant of the staged set
+  int user_variant = 0;   // requested through slamgpu_ctx_set_option / SLAMGPU_GRID_VARIANT (0: default = 5)
+  int max_variant = 5;    // temporary cap while a launch falls back to a simpler variant
   DevBuf blocks, blk_rows, porg;          // v3: block table, per (theta, block) y range, patch origins
   int32_t nbt = 0, box_w = 0, box_h = 0, n_blocks3 = 0;
   double h_extent_x = 0, h_extent_y = 0;  // metres spanned by the x sweep / by the y rows of one block

@@ -915,7 +915,10 @@ struct GridIdxArgs {
   int *cyp;  // [(tl*N + i)*nyp + k]  padded LUT row * pitch            (v1 kernel)
   unsigned long long *cyw;  // [(tl*N + i)*ngy + gy] packed rows of one y-group (v2 kernel)
   int v2, R, ngy;
+  int ngys;      // v4 / v5: row stride of cyw (ngy rounded up to even: 16-byte copies of a pair of row words stay aligned)
   int v4, dmax;  // v4 row word: low 32 bits = element offset of the first y's padded LUT row, bits 32..38 = "new row" mask
+  int v5, nb, bw;   // v5: column records per (theta, beam, band of bw columns) instead of the cxp table
+  uint4 *colrec;    // [(tl*N + i)*nb + band][2]: {first column (even), 0, 0, 0} {32 nibbles: column of lane - first column}
   // v3 (TMA-staged patches): per (theta, beam, block-of-theta) patch origin {first padded column, first padded row}
   int v3, nbt, box_w, box_h;
   const int2 *blk_rows;  // [nbt] y range {k_lo, k_hi} (inclusive) each block of a theta touches
@@ -991,7 +994,8 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
         const double rc = sh_rc[pr];
         const int cx = grid_axis_cell(sg::add(x, rc), rc, a.scale, inv_scale, a.guard, &unsafe_any);
         const int col = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
-        dst[(size_t)pr * a.nx] = col;
+        if (a.v5) sh_rows[SG_IDX_PAIRS * a.ny + pr * a.nx + c] = col;
+        else dst[(size_t)pr * a.nx] = col;
         if (a.v3) { atomicMin(&sh_xmin[pr], col); atomicMax(&sh_xmax[pr], col); }
       }
     } else {
@@ -1029,7 +1033,7 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
           prev4 = prow;
         }
         if (!ok || distinct > a.dmax) atomicAdd((unsigned long long *)&a.result->pad, 1ull);
-        a.cyw[(ti0 + pr) * a.ngy + gy] = ((unsigned long long)mask << 32) | (unsigned)(rows[k0] * a.pitch);
+        a.cyw[(ti0 + pr) * a.ngys + gy] = ((unsigned long long)mask << 32) | (unsigned)(rows[k0] * a.pitch);
         continue;
       }
       unsigned long long word = (unsigned)rows[k0];
@@ -1043,6 +1047,28 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
         prev = prow;
       }
       a.cyw[(ti0 + pr) * a.ngy + gy] = word;
+    }
+    if (a.v5) {
+      // k_score_grid5: one record per band of <= 30 consecutive x; a band's 14-column window must hold all its columns
+      const int *cols_all = sh_rows + SG_IDX_PAIRS * a.ny;
+      for (int e = threadIdx.x; e < np * a.nb; e += blockDim.x) {
+        const int pr = e / a.nb, b = e - pr * a.nb;
+        const int *cols = cols_all + pr * a.nx;
+        const int j0 = b * a.bw, j1 = min(j0 + a.bw, a.nx);
+        const int col0 = cols[j0] & ~1;
+        unsigned nib[4] = {0u, 0u, 0u, 0u};
+        bool ok = true;
+        for (int jj = j0; jj < j1; ++jj) {
+          const int d = cols[jj] - col0;
+          if (d < 0 || d > 13) { ok = false; continue; }
+          const int l = jj - j0;
+          nib[l >> 3] |= (unsigned)d << ((l & 7) * 4);
+        }
+        if (!ok) atomicAdd((unsigned long long *)&a.result->pad, 1ull);
+        uint4 *dst = a.colrec + ((ti0 + pr) * a.nb + b) * 2;
+        dst[0] = make_uint4((unsigned)col0, 0u, 0u, 0u);
+        dst[1] = make_uint4(nib[0], nib[1], nib[2], nib[3]);
+      }
     }
     if (a.v3) {
       for (int e = threadIdx.x; e < np * a.nbt; e += blockDim.x) {
@@ -1225,7 +1251,7 @@ struct GridArgs4 {
   const unsigned *cxp;
   const uint2 *cyw;
   const int4 *groups;  // {t, k0, m_lo, m_hi}
-  int n_groups, nx, ny, ngy, N, t_lo, pitch;
+  int n_groups, nx, ny, ngy, ngys, N, t_lo, pitch;
   int nb_full, wr;         // full 32-column bands per y-group, width of the leftover band
   const int2 *wtask;       // warp table (see grid4_task)
   int n_warps;
@@ -1239,18 +1265,10 @@ struct GridArgs4 {
   unsigned zero;        // 0 (a run-time value: see the beam loop)
 };
 
-#define SG_G4_DEPTH 4  // stages of the index ring (power of two); the index tables carry that many beam rows of slack
 SG_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-SG_DEV void cp_async4(unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
-SG_DEV void cp_async8(unsigned dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
 SG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_PENDING>
 SG_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
-SG_DEV uint4 lds128(unsigned addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
 
 template <class T>
 SG_DEV T *opaque_ptr(T *p, unsigned zero) {
@@ -1329,7 +1347,7 @@ __global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_sc
     const int4 grp = __ldg(a.groups + g);
     const int tl = grp.x - a.t_lo;
     ox = (unsigned)tl * (unsigned)a.N * (unsigned)a.nx + (unsigned)j;
-    ow = (unsigned)tl * (unsigned)a.N * (unsigned)a.ngy + (unsigned)(grp.y >> 3);
+    ow = (unsigned)tl * (unsigned)a.N * (unsigned)a.ngys + (unsigned)(grp.y >> 3);
   }
   // Loop invariants are made opaque to ptxas with a real instruction (an add of a run-time zero): otherwise it re-derives
   // them from the constant bank every beam (LDC + IMAD.WIDE), and those LDCs occupy the scoreboards the loads need.
@@ -1339,7 +1357,7 @@ __global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_sc
   for (int d = 0; d < DMAX; ++d) rowp[d] = opaque_ptr(a.lut + (size_t)d * (size_t)a.pitch, zero);
   const unsigned *const cxp = opaque_ptr(a.cxp, zero);
   const uint2 *const cyw = opaque_ptr(a.cyw, zero);
-  const unsigned sx = a.nx, sw = a.ngy;
+  const unsigned sx = a.nx, sw = a.ngys;
   const int N = a.N;
   const double w0 = a.w0;
   double acc[8];
@@ -1348,6 +1366,14 @@ __global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_sc
   // Software pipeline without register rotation: the beam loop is unrolled by two; index set A serves the odd beams, B the
   // even ones (each reloaded two beams ahead of its use, right after it was consumed), value sets v0 / v1 alternate.
   // The index tables carry four zeroed beam rows of slack, so the prefetches past the last beam need no guard.
+  // One beam per loop half; values of beam i in v0 (even) / v1 (odd).  ptxas puts EVERY global load of the loop on one
+  // scoreboard (SB5 in all our kernels), so the first use of any loaded register waits for all loads in flight: the loads
+  // cannot run more than one beam ahead of their use whatever the source says.  Each half therefore does FIRST the products
+  // of its beam (the one place where the warp waits), THEN issues the gathers of the next beam -- their address is made to
+  // depend on a product so that the scheduler cannot hoist them above the wait --, reloads its index set in place (A serves
+  // the odd beams, B the even ones), and only then runs the adds, which overlap the loads' flight.
+  // (Measured alternatives: gathers issued before the wait 0.67 ms; index pairs through a cp.async ring 0.91 ms -- LDGSTS
+  // costs ~1 cycle per lane here; two beams per wait 0.59 ms; this order 0.50 ms at configs[2].)
   double v0[DMAX], v1[DMAX];
   unsigned m0, m1 = 0;
   {
@@ -1358,14 +1384,10 @@ __global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_sc
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) v0[d] = __ldg(rowp[d] + b);
   }
-  // the index tables are streamed (L2 only: they would only push LUT lines out of L1); two register sets, A for the odd beams
-  // and B for the even ones, each reloaded in place right after it was consumed (two beams ahead of its next use)
+  // the index tables are streamed (L2 only: they would only push LUT lines out of L1)
   unsigned cxA = __ldcg(cxp + (ox + sx)), cxB = __ldcg(cxp + (ox + 2 * sx));
   uint2 cwA = __ldcg(cyw + (ow + sw)), cwB = __ldcg(cyw + (ow + 2 * sw));
   ox += 3 * sx; ow += 3 * sw;
-  // One half of the loop body (beam I, values in VCUR): FIRST the products -- the place where the warp waits for its loads --,
-  // THEN the gathers of beam I+1, whose address is made to depend on a product so that the scheduler cannot hoist them above
-  // that wait, then the reload of the index set, then the adds.
 #define SG_G4_HALF(VCUR, VNXT, MCUR, MNXT, CX, CW, I)                                      \
   {                                                                                       \
     const double wi = UNIW ? w0 : __ldg(a.w + (I));                                       \
@@ -1406,6 +1428,177 @@ template <int DMAX>
 void launch_grid4(slamgpu_ctx *ctx, const GridArgs4 &a, int nblk, bool uniw) {
   if (uniw) k_score_grid4<DMAX, true><<<nblk, 128, 0, ctx->stream>>>(a);
   else k_score_grid4<DMAX, false><<<nblk, 128, 0, ctx->stream>>>(a);
+}
+
+
+// v5 of the grid kernel: v4's arithmetic (each distinct map row once, indexed-branch accumulate) behind an asynchronous
+// copy pipeline.  ptxas puts EVERY global load of a loop on one scoreboard (SB5 in all our kernels), so the first use of any
+// loaded register waits for all loads in flight: register prefetching cannot run more than one beam ahead, and a warp pays a
+// full L2 round trip per beam (ncu, lone warp: ~700 cycles per beam).  cp.async (LDGSTS) completes per commit group
+// instead, so here each warp issues ONE 16-byte-per-lane copy per beam, two beams ahead of its use:
+//   lanes 0 .. 7*DMAX-1   the LUT patch of beam i+2: DMAX consecutive rows x 14 columns (7 aligned pairs) holding every
+//                         cell the warp's <= 30 consecutive x can touch in its 8 y;
+//   lanes 28, 29          the column record of beam i+4 {first column, 32 nibbles};
+//   lane 30               the row word pair of beam i+4 {row offset, new-row mask};
+//   lane 31               the point weight pair of beam i+2 (uneven weights only);
+// into a ring of four 512-byte stages private to the warp (no block barrier anywhere).  Every value the loop consumes comes
+// from shared memory (LDS, ~30 cycles); cp.async.wait_group 1 leaves the youngest copy in flight.
+struct GridArgs5 {
+  const double *lut;
+  const uint4 *colrec;
+  const uint2 *cyw;
+  const double2 *w2;   // {w[i], w[i+1]} per beam (uneven weights)
+  const int4 *groups;  // {t, k0, m_lo, m_hi}
+  int n_groups, nx, ny, ngy, ngys, N, t_lo, pitch, nb, bw;
+  double w0, wsum;
+  long long p0;
+  double *scores;
+  Best *blk;
+  unsigned zero;
+};
+
+SG_DEV void cp_async16(unsigned dst, const void *src, bool on) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 16; }" ::"r"(dst), "l"(src), "r"((unsigned)on) : "memory");
+}
+SG_DEV unsigned lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+SG_DEV uint2 lds64(unsigned addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+SG_DEV double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+#define SG_G5_STAGE 512u  // bytes per stage: 32 lanes x 16
+#define SG_G5_ROW 112u    // bytes per patch row in a stage: 7 pairs
+#define SG_G5_STAGES 8    // ring depth (power of two, > SG_G5_P + SG_G5_Q)
+#define SG_G5_P 4         // the patch (and weight) of a beam is copied this many beams ahead of its use
+#define SG_G5_Q 3         // ... and its index records this many beams ahead of the patch copy that needs them
+
+template <int DMAX, bool UNIW>
+__global__ void __launch_bounds__(64, 18) k_score_grid5(GridArgs5 a) {
+  __shared__ __align__(16) unsigned char ring[2][SG_G5_STAGES * SG_G5_STAGE];
+  const int lane = (int)(threadIdx.x & 31), wib = (int)(threadIdx.x >> 5);
+  int w = (int)blockIdx.x * 2 + wib;
+  const bool wvalid = w < a.n_groups * a.nb;
+  if (!wvalid) w = 0;  // walks task 0 and drops the result: the beam loop stays in uniform control flow
+  const int g = w / a.nb, band = w - g * a.nb;
+  int tl, gy;
+  {
+    const int4 grp = __ldg(a.groups + g);
+    tl = grp.x - a.t_lo; gy = grp.y >> 3;
+  }
+  // what this lane copies every beam: src = base + 8 * u, u = (row offset + first column) for the patch lanes, a running
+  // table offset for the others
+  const bool is_patch = lane < 7 * DMAX;
+  const bool is_idx = lane >= 28 && lane <= 30, is_w = lane == 31 && !UNIW;
+  const char *base;
+  unsigned uidx = 0, inc = 0;
+  {
+    const int r = lane / 7, cp = lane - r * 7;
+    if (is_patch) base = reinterpret_cast<const char *>(a.lut + (size_t)r * (size_t)a.pitch + 2 * cp);
+    else if (lane == 28 || lane == 29) {
+      base = reinterpret_cast<const char *>(a.colrec) + (lane - 28) * 16;
+      uidx = ((unsigned)tl * (unsigned)a.N * (unsigned)a.nb + (unsigned)band) * 4u; inc = (unsigned)a.nb * 4u;
+    } else if (lane == 30) {
+      base = reinterpret_cast<const char *>(a.cyw);
+      uidx = (unsigned)tl * (unsigned)a.N * (unsigned)a.ngys + (unsigned)(gy & ~1); inc = (unsigned)a.ngys;
+    } else if (is_w) {
+      base = reinterpret_cast<const char *>(a.w2); inc = 2u;
+    } else base = reinterpret_cast<const char *>(a.lut);  // idle lane: copies the first LUT pair
+  }
+  base = opaque_ptr(base, a.zero);
+  const unsigned ring_w = smem_u32(&ring[wib][0]);
+  const unsigned my_chunk = ring_w + (unsigned)lane * 16u;
+  const unsigned nib_addr = ring_w + 29u * 16u + (unsigned)(lane >> 3) * 4u, nib_shift = (unsigned)(lane & 7) * 4u;
+  const unsigned rw_addr = ring_w + 30u * 16u + (unsigned)(gy & 1) * 8u;
+  const unsigned ring_mask = SG_G5_STAGES * SG_G5_STAGE - 1u;
+  const int N = a.N;
+  const double w0 = a.w0;
+  double acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+
+  // The copy of iteration m goes to slot m & 7 and carries {patch(m+P), weight(m+P), index records of beam m+P+Q}; negative
+  // m are the prologue.  Iteration i reads: the records of beam i+P (slot (i-Q) & 7) to address the patch it requests, the
+  // patch and weight of beam i (slot (i-P) & 7), and the column nibble / new-row mask of beam i (slot (i-P-Q) & 7, still
+  // alive because the ring is deeper than P+Q).
+  // ---- prologue 1: the records of beams 0 .. P+Q-1 (iterations -P-Q .. -1), nothing else
+#pragma unroll
+  for (int m = -(SG_G5_P + SG_G5_Q); m < 0; ++m) {
+    cp_async16(my_chunk + ((unsigned)(m & (SG_G5_STAGES - 1))) * SG_G5_STAGE, base + (size_t)uidx * 8u, is_idx);
+    if (is_idx) uidx += inc;
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  // ---- prologue 2: patches and weights of beams 0 .. P-1 (iterations -P .. -1) from the records just fetched
+#pragma unroll
+  for (int m = -SG_G5_P; m < 0; ++m) {
+    const unsigned rs = ((unsigned)((m - SG_G5_Q) & (SG_G5_STAGES - 1))) * SG_G5_STAGE;  // records of beam m+P
+    const unsigned col0 = lds32(ring_w + 28u * 16u + rs);
+    const uint2 rw = lds64(rw_addr + rs);
+    const unsigned u = is_patch ? rw.x + col0 : uidx;
+    cp_async16(my_chunk + ((unsigned)(m & (SG_G5_STAGES - 1))) * SG_G5_STAGE, base + (size_t)u * 8u, is_patch || is_w);
+    if (is_w) uidx += inc;
+    cp_async_commit();
+  }
+
+  // ---- beam loop
+  unsigned sw_ = 0;  // stage offset of slot i & 7
+#pragma unroll 1
+  for (int i = 0; i < N; ++i) {
+    cp_async_wait<SG_G5_Q - 1>();  // all copies but the last Q-1 have landed: iterations <= i-Q
+    __syncwarp();
+    const unsigned s_adr = (sw_ - SG_G5_Q * SG_G5_STAGE) & ring_mask;                  // records of beam i+P
+    const unsigned s_val = (sw_ - SG_G5_P * SG_G5_STAGE) & ring_mask;                  // patch, weight of beam i
+    const unsigned s_cur = (sw_ - (SG_G5_P + SG_G5_Q) * SG_G5_STAGE) & ring_mask;      // records of beam i
+    const unsigned col0 = lds32(ring_w + 28u * 16u + s_adr);
+    const uint2 rw = lds64(rw_addr + s_adr);
+    const unsigned nibw = lds32(nib_addr + s_cur);
+    const unsigned msk = lds32(rw_addr + 4u + s_cur);
+    const unsigned u = is_patch ? rw.x + col0 : uidx;
+    uidx += inc;
+    cp_async16(my_chunk + sw_, base + (size_t)u * 8u, true);
+    cp_async_commit();
+    const unsigned va = ring_w + s_val + ((nibw >> nib_shift) & 15u) * 8u;
+    const double wi = UNIW ? w0 : lds_f64(ring_w + 31u * 16u + s_val);
+    double t[DMAX];
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(lds_f64(va + d * SG_G5_ROW), wi);
+    add_pattern<DMAX>(msk, acc, t);
+    sw_ = (sw_ + SG_G5_STAGE) & ring_mask;
+  }
+  cp_async_wait<0>();
+
+  double best_s = -INFINITY;
+  long long best_i = LLONG_MAX;
+  const int j = band * a.bw + lane;
+  if (wvalid && lane < a.bw && j < a.nx) {
+    const int4 grp = __ldg(a.groups + g);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      if (m < grp.z || m >= grp.w) continue;
+      double score = a.wsum == 0 ? NAN : sg::div(acc[m], a.wsum);
+      long long idx = ((long long)grp.x * a.ny + (grp.y + m)) * a.nx + j;
+      a.scores[idx - a.p0] = score;
+      if (score == score && beats(score, idx, best_s, best_i)) { best_s = score; best_i = idx; }
+    }
+  }
+  block_argmax(best_s, best_i, a.blk + blockIdx.x);
+}
+
+template <int DMAX>
+void launch_grid5(slamgpu_ctx *ctx, const GridArgs5 &a, int nblk, bool uniw) {
+  if (uniw) k_score_grid5<DMAX, true><<<nblk, 64, 0, ctx->stream>>>(a);
+  else k_score_grid5<DMAX, false><<<nblk, 64, 0, ctx->stream>>>(a);
 }
 
 // ---------------------------------------------------------------- v3: map patches staged in shared memory by TMA
@@ -1713,14 +1906,19 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   c.P = (int64_t)nt * ny * nx;
   {
     static const int env_variant = [] { const char *e = getenv("SLAMGPU_GRID_VARIANT"); return e ? atoi(e) : 0; }();
-    int v = c.user_variant ? c.user_variant : (env_variant >= 1 && env_variant <= 4 ? env_variant : 4);
-    if (v == 4) {
-      // k_score_grid4 needs ascending y (cell rows of a thread's 8 y then step by 0 or 1) and unit factors
+    int v = c.user_variant ? c.user_variant : (env_variant >= 1 && env_variant <= 5 ? env_variant : 5);
+    if (v >= 4) {
+      // k_score_grid4 / 5 need ascending y (cell rows of a thread's 8 y then step by 0 or 1) and unit factors
       bool asc = !scan->has_factor;
       for (int k = 1; k < ny && asc; ++k) asc = ys[k] > ys[k - 1];
       if (!asc || c.user_rows == 2 || c.user_rows == 4) v = 2;
     }
-    if (v > c.max_variant) v = std::min(c.max_variant, 2);  // 4 and 3 fall back to 2, then 1
+    if (v == 5) {  // ... and ascending x (a band's columns then start at its first x)
+      bool asc = true;
+      for (int j = 1; j < nx && asc; ++j) asc = xs[j] > xs[j - 1];
+      if (!asc) v = 4;
+    }
+    if (v > c.max_variant) v = (v == 5 && c.max_variant == 4) ? 4 : std::min(c.max_variant, 2);  // 5 -> 4 -> 2 -> 1, 3 -> 2
     if (c.force_v1) v = 1;
     if ((size_t)ny * SG_IDX_PAIRS * sizeof(int) > 40 * 1024) v = 1;  // the index kernel stages the rows in smem
     c.grid_variant = v;
@@ -1732,10 +1930,24 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     slice_of(ctx, (int64_t)nt * ny, &r0_, &r1_);
     const int64_t want_threads = (int64_t)ctx->sm_count * 768;
     int R = 8;
-    while (c.grid_v2 && c.grid_variant != 4 && R > 2 && ((r1_ - r0_ + R - 1) / R) * nx < want_threads) R /= 2;
-    if (c.user_rows && c.grid_variant != 4) R = c.user_rows;
+    while (c.grid_v2 && c.grid_variant < 4 && R > 2 && ((r1_ - r0_ + R - 1) / R) * nx < want_threads) R /= 2;
+    if (c.user_rows && c.grid_variant < 4) R = c.user_rows;
     c.grid_R = c.grid_v2 ? R : SG_GRID_R;
     c.ngy = (ny + c.grid_R - 1) / c.grid_R;
+    c.ngys = c.grid_variant >= 4 ? (c.ngy + 1) & ~1 : c.ngy;
+  }
+  if (c.grid_variant == 5 && !c.user_variant) {
+    // The cp.async pipeline of v5 hides the memory latency with a handful of warps per SM but is bound by the copy rate
+    // (~30 cycles per 512-byte LDGSTS and SM) when the device is full; v4 needs ~28 resident warps per SM to hide its one L2
+    // round trip per beam and is then 12 % faster (configs[2] on one GPU: 0.50 vs 0.58 ms; half of it: 0.44 vs 0.30 ms).
+    static const int env_variant5 = [] { const char *e = getenv("SLAMGPU_GRID_VARIANT"); return e ? atoi(e) : 0; }();
+    int64_t r0_, r1_;
+    slice_of(ctx, (int64_t)nt * ny, &r0_, &r1_);
+    const int64_t warps5 = ((r1_ - r0_ + 7) / 8) * ((nx + 29) / 30);
+    if (env_variant5 != 5 && warps5 > (int64_t)ctx->sm_count * 29) {
+      c.grid_variant = 4;
+      c.ngys = (c.ngy + 1) & ~1;
+    }
   }
   const int GR = c.grid_R;
   c.uniform_w = scan->n > 0;
@@ -1821,18 +2033,32 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   long long threads = (long long)c.n_groups * nx;
   // (v4 packs the leftover columns of several y-groups into one warp: at most one extra warp per y-group)
   int nblk = std::max((int)((threads + 127) / 128), (int)c.n_blocks3) + (c.n_groups + 3) / 4 + 1;
+  if (c.grid_variant == 5) nblk = std::max(nblk, (int)((c.n_groups * ((nx + 29) / 30) + 1) / 2));
   if (c.grid_variant == 3 && c.porg.reserve(std::max<size_t>((size_t)nt_loc * N * std::max(c.nbt, 1), 1) * sizeof(int2)) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "patch origin table");
   // beam rows of slack behind the index tables: k_score_grid4 prefetches past the last beam without a guard
   const size_t idx_rows = (size_t)nt_loc * N + SG_IDX_SLACK;
-  if (c.cxp.reserve(idx_rows * nx * sizeof(int)) != SLAMGPU_OK ||
+  if (c.cxp.reserve((c.grid_variant == 5 ? 16 : idx_rows * nx) * sizeof(int)) != SLAMGPU_OK ||
       c.cyp.reserve(std::max<size_t>(c.grid_v2 ? 1 : (size_t)nt_loc * N * c.nyp, 1) * sizeof(int)) != SLAMGPU_OK ||
-      c.cyw.reserve(std::max<size_t>(c.grid_v2 ? idx_rows * c.ngy : 1, 1) * sizeof(unsigned long long)) != SLAMGPU_OK ||
+      c.cyw.reserve(std::max<size_t>(c.grid_v2 ? idx_rows * c.ngys : 1, 1) * sizeof(unsigned long long)) != SLAMGPU_OK ||
       c.scores.reserve(std::max<size_t>(Ploc, 1) * sizeof(double)) != SLAMGPU_OK ||
       c.blk_best.reserve(std::max(nblk, 1) * sizeof(Best)) != SLAMGPU_OK ||
       c.result.reserve(sizeof(Result) * 2 + 64) != SLAMGPU_OK ||
       ctx->gather.reserve(sizeof(Result) * std::max(ctx->nranks, 1)) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "grid score buffers");
+  if (c.grid_variant == 5) {
+    // bands of at most 30 consecutive x, balanced: their columns fit the 14-column window of a warp's patch
+    c.nb5 = (nx + 29) / 30; c.bw5 = (nx + c.nb5 - 1) / c.nb5;
+    if (c.colrec.reserve(idx_rows * c.nb5 * 32) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "column records");
+    SG_CUDA(ctx, cudaMemsetAsync((char *)c.colrec.p + (idx_rows - SG_IDX_SLACK) * c.nb5 * 32, 0, (size_t)SG_IDX_SLACK * c.nb5 * 32, ctx->stream));
+    SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngys, 0, SG_IDX_SLACK * (size_t)c.ngys * sizeof(unsigned long long),
+                                 ctx->stream));
+    if (!c.uniform_w) {  // weight pairs {w[i], w[i+1]}: the copy lanes move 16 bytes
+      c.h_w2.assign(2 * ((size_t)N + SG_IDX_SLACK), 0.0);
+      for (int i = 0; i < N; ++i) { c.h_w2[2 * (size_t)i] = scan->weight[i]; c.h_w2[2 * (size_t)i + 1] = i + 1 < N ? scan->weight[i + 1] : 0.0; }
+      SG_TRY(upload(ctx, c.w2, c.h_w2.data(), c.h_w2.size() * sizeof(double)));
+    }
+  }
   if (c.grid_variant == 4) {
     // warp table: the full bands of G = 32 / (nx % 32) consecutive y-groups, then ONE warp with the leftover columns of those
     // groups -- slow warps (their indexed branch diverges) so spread evenly over the launch
@@ -1848,7 +2074,7 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     c.n_warps4 = (int32_t)(wt.size() / 2);
     SG_TRY(upload(ctx, c.wtask, wt.data(), wt.size() * sizeof(int32_t)));
     SG_CUDA(ctx, cudaMemsetAsync(c.cxp.as<int>() + (idx_rows - SG_IDX_SLACK) * nx, 0, SG_IDX_SLACK * (size_t)nx * sizeof(int), ctx->stream));
-    SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngy, 0, SG_IDX_SLACK * (size_t)c.ngy * sizeof(unsigned long long),
+    SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngys, 0, SG_IDX_SLACK * (size_t)c.ngys * sizeof(unsigned long long),
                                  ctx->stream));
   }
   c.kind = 1;
@@ -1989,13 +2215,13 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       }
     }
     int dmax = 0;
-    if (c.grid_variant == 4) {
+    if (c.grid_variant >= 4) {
       // distinct cell rows the 8 y of one thread can touch: floor(span / cell) + 2, at most 8 (else v2)
       double span = 0;
       for (int k0 = 0; k0 < c.ny; k0 += 8) span = std::max(span, c.h_ys[std::min(k0 + 7, c.ny - 1)] - c.h_ys[k0]);
       const double cells = std::floor(span / map->scale) + 2.0;
       const size_t lut_elems = (size_t)map->pitch * (map->h + 2 * SG_LUT_PAD + SG_LUT_SLACK_ROWS);
-      const size_t idx_elems = ((size_t)(c.t_hi - c.t_lo + 1) * N + SG_IDX_SLACK) * (size_t)std::max(c.nx, c.ngy);
+      const size_t idx_elems = ((size_t)(c.t_hi - c.t_lo + 1) * N + SG_IDX_SLACK) * (size_t)std::max(c.nx, std::max(c.ngys, 4 * c.nb5));
       if (!(cells <= 8.0) || lut_elems >= (1ull << 31) || idx_elems >= (1ull << 32) || N <= 0) {
         const int saved_max = c.max_variant;
         c.max_variant = 2;
@@ -2009,6 +2235,17 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       }
       dmax = std::max(2, (int)cells);
       if (dmax == 7) dmax = 8;
+      if (c.grid_variant == 5 && dmax > 4) {  // the patch of k_score_grid5 holds 4 rows: more -> v4
+        const int saved_max = c.max_variant;
+        c.max_variant = 4;
+        slamgpu_spe_params spe = c.spe;
+        std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
+        int r = slamgpu_stage_grid(ctx, c.scan, &spe, xs.data(), (int32_t)xs.size(), ys.data(), (int32_t)ys.size(), ts.data(),
+                                   (int32_t)ts.size());
+        c.max_variant = saved_max;
+        SG_TRY(r);
+        return launch_staged(ctx, map, init_score);
+      }
     }
     const int nt_loc = c.t_hi - c.t_lo + 1;
     // big sets: make the score LUT L2-resident while the trig / index kernels run (side stream)
@@ -2041,11 +2278,12 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       ia.guard = device_trig ? 1 : 0;
       ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
       ia.cyw = c.cyw.as<unsigned long long>(); ia.v2 = c.grid_v2 ? 1 : 0; ia.R = c.grid_R; ia.ngy = c.ngy;
-      ia.v4 = c.grid_variant == 4 ? 1 : 0; ia.dmax = dmax;
+      ia.v4 = c.grid_variant >= 4 ? 1 : 0; ia.dmax = dmax; ia.ngys = c.ngys;
+      ia.v5 = c.grid_variant == 5 ? 1 : 0; ia.nb = c.nb5; ia.bw = c.bw5; ia.colrec = c.colrec.as<uint4>();
       ia.v3 = c.grid_variant == 3 ? 1 : 0; ia.nbt = c.nbt; ia.box_w = c.box_w; ia.box_h = c.box_h;
       ia.blk_rows = c.blk_rows.as<int2>(); ia.porg = c.porg.as<int2>();
       {
-        const size_t shm = c.grid_v2 ? sizeof(int) * SG_IDX_PAIRS * (size_t)c.ny : 0;
+        const size_t shm = c.grid_v2 ? sizeof(int) * SG_IDX_PAIRS * ((size_t)c.ny + (c.grid_variant == 5 ? c.nx : 0)) : 0;
         dim3 grd((unsigned)((N + SG_IDX_PAIRS - 1) / SG_IDX_PAIRS), (unsigned)nt_loc);
         k_grid_indices<<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia);
       }
@@ -2069,10 +2307,27 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       cudaEventRecord(ctx->evk1, ctx->stream);
       ctx->evk_valid = true;
       SG_LAUNCHED(ctx);
+    } else if (nblk > 0 && c.grid_variant == 5) {
+      GridArgs5 a;
+      a.lut = map->d_lut[oie]; a.colrec = c.colrec.as<uint4>(); a.cyw = c.cyw.as<uint2>(); a.w2 = c.w2.as<double2>();
+      a.groups = c.groups.as<int4>();
+      a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.ngys = c.ngys; a.N = N; a.t_lo = c.t_lo; a.pitch = map->pitch;
+      a.nb = c.nb5; a.bw = c.bw5; a.w0 = s->weight[0]; a.wsum = s->wsum; a.p0 = c.p0;
+      a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>(); a.zero = 0u;
+      nblk = (c.n_groups * c.nb5 + 1) / 2;
+      cudaEventRecord(ctx->evk0, ctx->stream);
+      switch (dmax) {
+        case 2: launch_grid5<2>(ctx, a, nblk, c.uniform_w); break;
+        case 3: launch_grid5<3>(ctx, a, nblk, c.uniform_w); break;
+        default: launch_grid5<4>(ctx, a, nblk, c.uniform_w); break;
+      }
+      cudaEventRecord(ctx->evk1, ctx->stream);
+      ctx->evk_valid = true;
+      SG_LAUNCHED(ctx);
     } else if (nblk > 0 && c.grid_variant == 4) {
       GridArgs4 a;
       a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<unsigned>(); a.cyw = c.cyw.as<uint2>(); a.groups = c.groups.as<int4>();
-      a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.N = N; a.t_lo = c.t_lo; a.pitch = map->pitch;
+      a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.ngy = c.ngy; a.ngys = c.ngys; a.N = N; a.t_lo = c.t_lo; a.pitch = map->pitch;
       a.nb_full = c.nx / 32; a.wr = c.nx % 32;
       a.w = s->d_w; a.w0 = s->weight[0]; a.wsum = s->wsum; a.p0 = c.p0;
       a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>();
@@ -2186,7 +2441,7 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
     // -> v2; v2: two neighbouring y values are more than 7 cell rows apart, the packed row word cannot hold it -> the
     // explicit row table (v1 kernel)
     const int saved_max = c.max_variant;
-    c.max_variant = c.grid_variant >= 3 ? 2 : 1;
+    c.max_variant = c.grid_variant == 5 ? 4 : (c.grid_variant >= 3 ? 2 : 1);
     slamgpu_spe_params spe = c.spe;
     std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
     double init = c.init_score;

@@ -272,7 +272,7 @@ def test_full_size_bruteforce_properties(sg, gpu):
     gm.close(); gsc.close()
 
 
-@pytest.mark.parametrize("max_variant", [4, 3, 2])
+@pytest.mark.parametrize("max_variant", [5, 4, 3, 2])
 @pytest.mark.parametrize("nx,ny,nt,ystep,expect_R,fits_box,fits_nibbles", [
     (33, 19, 5, 0.02, 2, True, True),         # few candidates: 2 rows per thread (v4: point factors -> v2)
     (400, 160, 8, 0.02, 4, True, True),       # medium: 4 rows per thread (v4: always 8)
@@ -301,35 +301,43 @@ def test_grid_kernel_variants(sg, gpu, max_variant, nx, ny, nt, ystep, expect_R,
     want = om.score(osc, ob.spe_params(), P[pick])
     assert np.array_equal(got[pick], want)
     assert idx == int(np.argmax(got)) and best == got[idx]
-    v4 = max_variant == 4 and ystep > 0 and fits_nibbles and nx != 33
-    expect_variant = 4 if v4 else (1 if not fits_nibbles else (3 if (max_variant == 3 and fits_box) else 2))
+    v4 = max_variant >= 4 and ystep > 0 and fits_nibbles and nx != 33
+    v5 = v4 and max_variant == 5 and int(np.floor(7 * ystep / 0.05)) + 2 <= 4  # the 4-row patch of the cp.async pipeline
+    expect_variant = 5 if v5 else 4 if v4 else (1 if not fits_nibbles else (3 if (max_variant == 3 and fits_box) else 2))
     assert st["variant"] == expect_variant and st["rows_per_thread"] == (8 if v4 else expect_R), st
     gm.close(); gsc.close()
 
 
-def test_grid_row_dedupe_kernel_against_the_general_one(sg, gpu):
-    """k_score_grid4 (default) against k_score_grid2 on the same candidate grids, every score: all DMAX instantiations
-    (y steps from a fifth of a cell to a full cell), column counts around the 32-wide bands, uneven point weights"""
+def test_grid_row_dedupe_kernels_against_the_general_one(sg, gpu):
+    """k_score_grid5 (default: cp.async pipeline) and k_score_grid4 against k_score_grid2 on the same candidate grids, every
+    score: all DMAX instantiations (y steps from a tenth of a cell to a full cell), column counts around the band widths,
+    uneven point weights (the weight pairs ride in the copy), odd and tiny beam counts"""
     rng = np.random.default_rng(1750)
-    for nx, ny, nt, ystep, spw in [(32, 8, 2, 0.004, ob.SPW_EVEN), (65, 23, 3, 0.012, ob.SPW_VINY), (31, 40, 2, 0.02, ob.SPW_EVEN),
-                                   (101, 101, 2, 0.02, ob.SPW_EVEN), (96, 9, 4, 0.027, ob.SPW_AHR), (70, 33, 2, 0.035, ob.SPW_EVEN),
-                                   (45, 17, 3, 0.0499, ob.SPW_VINY), (5, 64, 3, 0.02, ob.SPW_EVEN)]:
-        om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_TBM_CONSISTENT, 97, spw=spw)
+    for nx, ny, nt, ystep, spw, n_pts in [(32, 8, 2, 0.004, ob.SPW_EVEN, 97), (65, 23, 3, 0.012, ob.SPW_VINY, 96),
+                                          (31, 40, 2, 0.02, ob.SPW_EVEN, 1), (101, 101, 2, 0.02, ob.SPW_EVEN, 97),
+                                          (96, 9, 4, 0.027, ob.SPW_AHR, 2), (70, 33, 2, 0.035, ob.SPW_EVEN, 3),
+                                          (45, 17, 3, 0.0499, ob.SPW_VINY, 97), (5, 64, 3, 0.02, ob.SPW_EVEN, 4),
+                                          (61, 30, 2, 0.02, ob.SPW_VINY, 5)]:
+        om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, ob.CELL_TBM_CONSISTENT, n_pts, spw=spw)
         xs = p0[0] + 0.013 * (np.arange(nx) - nx // 2)
         ys = p0[1] + ystep * (np.arange(ny) - ny // 2)
         ts = p0[2] + 0.02 * (np.arange(nt) - nt // 2)
-        got4, idx4, best4 = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
-        assert gpu.score_stats()["variant"] == 4
-        gpu.set_option("grid_variant", 2)
-        try:
-            got2, idx2, best2 = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
-        finally:
-            gpu.set_option("grid_variant", 0)
-        assert gpu.score_stats()["variant"] == 2
-        assert np.array_equal(got4, got2) and (idx4, best4) == (idx2, best2)
+        dmax = int(np.floor(7 * ystep / 0.05)) + 2
+        got5, idx5, best5 = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+        assert gpu.score_stats()["variant"] == (5 if dmax <= 4 else 4)
+        res = {}
+        for v in (4, 2):
+            gpu.set_option("grid_variant", v)
+            try:
+                res[v] = gpu.score_grid(gm, gsc, sg.spe_params(), xs, ys, ts)
+            finally:
+                gpu.set_option("grid_variant", 0)
+            assert gpu.score_stats()["variant"] == v
+        for v in (4, 2):
+            assert np.array_equal(got5, res[v][0]) and (idx5, best5) == res[v][1:]
         P = np.stack(np.meshgrid(ts, ys, xs, indexing="ij"), -1).reshape(-1, 3)[:, ::-1]
         pick = rng.choice(len(P), min(len(P), 1500), replace=False)
-        assert np.array_equal(got4[pick], om.score(osc, ob.spe_params(), P[pick]))
+        assert np.array_equal(got5[pick], om.score(osc, ob.spe_params(), P[pick]))
         gm.close(); gsc.close()
 
 

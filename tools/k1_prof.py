@@ -11,7 +11,8 @@ gm = sg.GridMap(ctx, bench.MAP_SIZE, bench.MAP_SIZE, bench.MAP_SCALE, sg.CELL_ME
 gm.upload(wl["cells"])
 scan = sg.Scan(ctx, wl["r"], wl["a"])
 params = sg.spe_params(sg.OOPE_OBSTACLE, sg.OIE_DISCREPANCY, trig=sg.TRIG_DEVICE)
-ctx.stage_grid(scan, params, wl["xs"], wl["ys"], wl["ts"])
+nt = int(os.environ.get("NT", "0")) or len(wl["ts"])
+ctx.stage_grid(scan, params, wl["xs"], wl["ys"], wl["ts"][:nt])
 tot = 0.0
 for _ in range(n):
     if not os.environ.get("NOFLUSH"):
@@ -20,4 +21,4 @@ for _ in range(n):
     ctx.sync()
     tot += ctx.last_kernel_ms()
 _, idx, best = ctx.score_fetch()
-print("variant", ctx.score_stats()["variant"], "kernel ms (not a bench value)", tot / n, idx, best)
+print("nt", nt, "variant", ctx.score_stats()["variant"], "kernel ms (not a bench value)", tot / n, idx, best)
