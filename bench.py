@@ -258,9 +258,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--grid-rows", type=int, default=0, help="experiment: rows per thread of the grid kernel (0 = automatic)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = 100 more theta values (1 020 100 more candidates) per extra GPU; strong = the fixed "
-                         "1 020 100 candidates split N ways")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = the fixed 1 020 100 candidates of configs[2] split N ways; weak = 100 more "
+                         "theta values (1 020 100 more candidates) per extra GPU (also reported as a secondary key at N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = {"metric": "pose-beam likelihood evaluations/sec (brute-force scan matcher)", "unit": "evals/s",
@@ -272,7 +272,7 @@ def main():
                                   "(32 bytes) is exchanged inside the finalize kernel through NVLink peer mailboxes "
                                   "(ncclAllGather when peer mapping is unavailable)",
                       "scaling_mode": "weak: the theta sweep is extended by 100 values (1020100 candidates) per extra GPU"
-                                      if args.scaling == "weak" else "strong: fixed 1020100 candidates split over ranks",
+                                      if args.scaling == "weak" else "strong: the fixed 1020100 candidates of configs[2] split over ranks",
                       "l2": "flushed (256 MB write) before every timed step" if L2_FLUSH else "not flushed"}}
     if args.impl == "reference":
         return run_reference_arm(args, cfg)
@@ -301,6 +301,8 @@ def main():
         ctx.set_option("grid_rows", args.grid_rows)
 
     wl = make_workload(theta_blocks=world if args.scaling == "weak" else 1)
+    cfg["config"]["kernel_selection"] = ("k_score_grid4 (row de-duplication, register loads) when the GPU is full, k_score_grid5 (the same "
+                                         "arithmetic behind a cp.async pipeline) when a rank's share leaves it partly empty")
     P = len(wl["xs"]) * len(wl["ys"]) * len(wl["ts"])
     cfg["config"]["candidates"] = P
     gmap = sg.GridMap(ctx, MAP_SIZE, MAP_SIZE, MAP_SCALE, sg.CELL_MEAN)
@@ -316,31 +318,55 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-timed steps, inputs resident in HBM
-    ctx.stage_grid(scan, params, wl["xs"], wl["ys"], wl["ts"])
-    for _ in range(args.warmup):
-        ctx.score_launch(gmap)
-    _, idx0, best0 = ctx.score_fetch()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    launches0 = ctx.launch_count()
-    t_wall0 = time.time()
-    total_ms, kern_ms = 0.0, 0.0
-    for _ in range(args.steps):
-        if L2_FLUSH:
-            ctx.flush_l2()
-        ctx.timer_begin()
-        ctx.score_launch(gmap)
-        total_ms += ctx.timer_end()
-        kern_ms += ctx.last_kernel_ms()
-    barrier()
-    t_wall1 = time.time()
-    launches = ctx.launch_count() - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    _, idx1, best1 = ctx.score_fetch()
-    assert (idx1, best1) == (idx0, best0), "result changed between launches"
-    st = ctx.score_stats()
+    def timed_steps(workload, steps, sample_clocks):
+        ctx.stage_grid(scan, params, workload["xs"], workload["ys"], workload["ts"])
+        for _ in range(args.warmup):
+            ctx.score_launch(gmap)
+        _, i0, b0 = ctx.score_fetch()
+        smp = sampler if sample_clocks else None
+        barrier()
+        l0 = ctx.launch_count()
+        tw0 = time.time()
+        tot, kern = 0.0, 0.0
+        for _ in range(steps):
+            if L2_FLUSH:
+                ctx.flush_l2()
+            ctx.timer_begin()
+            ctx.score_launch(gmap)
+            tot += ctx.timer_end()
+            kern += ctx.last_kernel_ms()
+        barrier()
+        tw1 = time.time()
+        n_launch = ctx.launch_count() - l0
+        clk = smp.stop(tw0, tw1) if smp else None
+        _, i1, b1 = ctx.score_fetch()
+        assert (i1, b1) == (i0, b0), "result changed between launches"
+        return dict(total_ms=tot, kern_ms=kern, launches=n_launch, clocks=clk, idx=i0, best=b0, stats=ctx.score_stats())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # polls from here on; the timed region is cut out afterwards
+    run = timed_steps(wl, args.steps, True)
+    total_ms, kern_ms, launches, clocks, idx0, best0, st = (run[k] for k in ("total_ms", "kern_ms", "launches", "clocks", "idx", "best", "stats"))
     if world > 1:
         cfg["config"]["result_exchange"] = "peer memory (fused in k_exchange_finalize)" if st.get("peer_exchange") else "ncclAllGather"
+
+    # ---- N > 1: the merged result against a single-rank recompute of the whole set on this GPU (outside the timed region)
+    parity_vs_n1 = None
+    if world > 1:
+        solo = sg.Context(local_rank)
+        smap = sg.GridMap(solo, MAP_SIZE, MAP_SIZE, MAP_SCALE, sg.CELL_MEAN)
+        smap.upload(wl["cells"])
+        sscan = sg.Scan(solo, wl["r"], wl["a"])
+        _, sidx, sbest = solo.score_grid(smap, sscan, params, wl["xs"], wl["ys"], wl["ts"], want_scores=False)
+        parity_vs_n1 = (sidx, sbest) == (idx0, best0)
+        smap.close(); sscan.close(); solo.close()
+
+    # ---- N > 1, secondary: weak scaling (the theta sweep grows with N)
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_secondary:
+        wlw = make_workload(theta_blocks=world)
+        rw = timed_steps(wlw, max(3, args.steps // 2), False)
+        weak = dict(candidates=len(wlw["xs"]) * len(wlw["ys"]) * len(wlw["ts"]), steps=max(3, args.steps // 2), total_ms=rw["total_ms"])
+        ctx.stage_grid(scan, params, wl["xs"], wl["ys"], wl["ts"])
 
     # ---- end to end through the host-buffer C-ABI call (what a GridScanMatcher adapter calls)
     e2e_steps = args.steps
@@ -355,14 +381,20 @@ def main():
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     assert (idx2, best2) == (idx0, best0)
-    h2d = N_BEAMS * (6 * 8 + 1) + 8 * (len(wl["xs"]) + len(wl["ys"]) + len(wl["ts"])) + 16 * ((len(wl["ys"]) + 7) // 8) * len(wl["ts"])
+    # per call: the scan (6 doubles + 1 byte per beam) and the three axes (the y-group / warp tables are re-used while the shape of
+    # the candidate set stays the same)
+    h2d = N_BEAMS * (6 * 8 + 1) + 8 * (len(wl["xs"]) + len(wl["ys"]) + len(wl["ts"]))
     d2h = 32
 
     if dist is not None:
         import torch
-        t = torch.tensor([total_ms, kern_ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([total_ms, kern_ms, e2e_s, weak["total_ms"] if weak else 0.0, 0.0 if parity_vs_n1 else 1.0], device="cuda",
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms, e2e_s = (float(v) for v in t.tolist())
+        total_ms, kern_ms, e2e_s, weak_ms, parity_bad = (float(v) for v in t.tolist())
+        parity_vs_n1 = parity_bad == 0.0
+        if weak:
+            weak["total_ms"] = weak_ms
         ln = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(ln, op=dist.ReduceOp.SUM)
         launches = int(ln.item())
@@ -404,6 +436,23 @@ def main():
                              "note": "algorithmic bytes = 32 B (one sector) per pose-beam evaluation; the map is L2/L1 "
                                      "resident so frac > 1 means sector reuse, not an error"},
                 "result": {"best_idx": idx0, "best_score": best0, "guard_hits": st["guard_hits"]}}
+        line["roofline"]["kernel"] = {4: "k_score_grid4", 5: "k_score_grid5", 2: "k_score_grid2"}.get(st["variant"], "k_score_grid")
+        bounds_file = os.path.join(ROOT, "profiles", "r02_k1_bounds.json")
+        if os.path.exists(bounds_file):
+            # what actually binds the kernel (ncu of this round, profiles/): issue slots, L1 wavefronts, measured DRAM traffic
+            try:
+                bd = json.load(open(bounds_file)).get(line["roofline"]["kernel"])
+                if bd:
+                    line["roofline"]["traffic"] = bd.get("dram_bytes_per_launch", traffic)
+                    line["roofline"]["binding"] = bd
+            except ValueError:
+                pass
+        if world > 1:
+            line["parity_vs_n1"] = parity_vs_n1
+            if weak:
+                line["weak_scaling"] = {"value": weak["candidates"] * N_BEAMS * weak["steps"] / (weak["total_ms"] * 1e-3), "unit": cfg["unit"],
+                                        "candidates": weak["candidates"], "ms_per_step": weak["total_ms"] / weak["steps"],
+                                        "what": "the theta sweep extended by 100 values per extra GPU (round 1's headline mode)"}
         if args.gpus == 1 and not args.no_cpu_baseline:
             cores = host_cores()
             ref = ReferenceScorer(wl)

@@ -86,6 +86,10 @@ static int ctx_create_common(int device, slamgpu_ctx **out) {
   slamgpu_ctx *ctx = new slamgpu_ctx();
   ctx->device = device;
   ctx->sm_count = pr.multiProcessorCount;
+  {
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) == cudaSuccess && khz > 0) ctx->clock_hz = 1e3 * khz;
+  }
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess ||
@@ -242,6 +246,11 @@ extern "C" int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_
   if (strcmp(name, "grid_rows") == 0) {  // rows per thread of the v2 grid kernel: 0 = automatic, or 2 / 4 / 8
     if (value != 0 && value != 2 && value != 4 && value != 8) return sg_fail(ctx, SLAMGPU_E_INVALID, "grid_rows must be 0, 2, 4 or 8");
     ctx->cand.user_rows = (int)value;
+    return SLAMGPU_OK;
+  }
+  if (strcmp(name, "p2p_timeout_ms") == 0) {  // how long a rank waits for its peers' results in the fused exchange
+    if (value < 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "p2p_timeout_ms must be positive");
+    ctx->p2p_timeout_ms = (double)value;
     return SLAMGPU_OK;
   }
   if (strcmp(name, "warm_l2") == 0) {  // experiment: 0 = no L2 warm-up of the score LUT before big grid launches

@@ -61,6 +61,8 @@ struct Candidates {  // a staged candidate set (device resident)
   int32_t nbt = 0, box_w = 0, box_h = 0, n_blocks3 = 0;
   double h_extent_x = 0, h_extent_y = 0;  // metres spanned by the x sweep / by the y rows of one block
   bool uniform_w = false;
+  int64_t shape_key[8] = {0};  // shape of the last grid staging (see slamgpu_stage_grid)
+  bool shape_valid = false;
   bool warm_l2 = true;    // stream the score LUT through L2 before a big grid launch (slamgpu_ctx_set_option "warm_l2")
   // K6: every pose scored against its own particle's map
   bool multi = false;
@@ -95,6 +97,9 @@ struct slamgpu_ctx {
   void *peer_mapped[64] = {nullptr};
   unsigned long long p2p_seq = 0;
   int *d_p2p_status = nullptr;     // set by the kernel when a peer did not answer in time
+  bool p2p_broken = false;         // after a timeout: results go through ncclAllGather
+  double p2p_timeout_ms = 20000.0; // slamgpu_ctx_set_option("p2p_timeout_ms")
+  double clock_hz = 1.965e9;       // SM clock (cudaDevAttrClockRate) for clock64 deadlines
   cudaStream_t side = nullptr;  // the robot cell's update chain runs here, next to the sort (mapping.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

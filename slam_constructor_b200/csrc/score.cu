@@ -95,25 +95,37 @@ __global__ void k_finalize(const Result *__restrict__ per_rank, int nranks, doub
 // to land in this rank's own mailbox.  Lane 0 merges in rank order exactly as k_finalize does.  A peer cannot run two
 // calls ahead (its next exchange needs this rank's next message), so two buffers suffice.
 struct Mail { Result res; unsigned long long seq; unsigned long long pad[3]; };  // 64 B
-__global__ void k_exchange_finalize(const Result *mine, void *const *peer_mailbox, int rank, int nranks, unsigned long long seq,
-                                    double init_score, Result *out, int *status) {
+// The block results are reduced here as well (blk != NULL: what k_reduce_blocks does, by the same 1024 threads), so a
+// multi-rank step has one launch less.  A peer that has not delivered within `deadline` clock cycles (ctx option
+// "p2p_timeout_ms", default 20 s: rank skew from module loads, map regrowth or a stalled host thread is not an error) makes the
+// fetch fail and the ctx fall back to ncclAllGather for the following calls, so a late message can never be taken for a new one.
+__global__ void __launch_bounds__(1024) k_exchange_finalize(const Best *__restrict__ blk, int n_blk, Result *mine, void *const *peer_mailbox, int rank,
+                                                            int nranks, unsigned long long seq, long long deadline, double init_score, Result *out,
+                                                            int *status) {
   const int r = threadIdx.x;
   const int parity = (int)(seq & 1ull);
   __shared__ Result got[64];
   __shared__ int timed_out;
   if (r == 0) timed_out = 0;
+  if (blk) {
+    double s = -INFINITY;
+    long long i = LLONG_MAX;
+    for (int k = r; k < n_blk; k += blockDim.x)
+      if (beats(blk[k].score, blk[k].idx, s, i)) { s = blk[k].score; i = blk[k].idx; }
+    block_argmax(s, i, reinterpret_cast<Best *>(mine));  // {score, idx} of this rank; guard / pad were accumulated by the kernels
+  }
   __syncthreads();
   if (r < nranks) {
     volatile Mail *dst = reinterpret_cast<volatile Mail *>(peer_mailbox[r]) + (size_t)parity * nranks + rank;
-    const Result m = *mine;
-    dst->res.score = m.score; dst->res.idx = m.idx; dst->res.guard = m.guard; dst->res.pad = m.pad;
+    volatile Result *vm = mine;
+    dst->res.score = vm->score; dst->res.idx = vm->idx; dst->res.guard = vm->guard; dst->res.pad = vm->pad;
     __threadfence_system();
     dst->seq = seq;
     volatile Mail *src = reinterpret_cast<volatile Mail *>(peer_mailbox[rank]) + (size_t)parity * nranks + r;
     const long long t0 = clock64();
     bool ok = true;
     while (src->seq != seq) {
-      if (clock64() - t0 > 4000000000ll) { ok = false; break; }  // ~2 s: a peer is gone
+      if (clock64() - t0 > deadline) { ok = false; break; }
     }
     __threadfence_system();
     if (!ok) { atomicExch(status, 1); timed_out = 1; }
@@ -134,10 +146,9 @@ __global__ void k_exchange_finalize(const Result *mine, void *const *peer_mailbo
   }
 }
 
-// Streams a table through L2 (ld.global.cg: L2 only).  The brute-force kernels make a few data-dependent gathers per beam
-// and can hide an L2 hit, not a DRAM miss (ncu on a cold L2: ~0.8 DRAM sector fetches per warp and beam, ~1000 cycles each,
-// 41 % of all stall samples on the first use of a gathered value).  Reading the 32 MB score LUT once costs ~5 us of HBM
-// time and runs on the side stream beside the index kernels.
+// Streams a table through L2 (ld.global.cg: L2 only).  A scoring kernel that follows an L2-cold LUT (the map was just
+// rebuilt, or another working set went through the cache) would take its first touches from DRAM inside the latency-bound
+// beam loop; reading the 32 MB score LUT once costs ~5 us of HBM time and runs on the side stream beside the index kernels.
 __global__ void k_warm_l2(const double2 *__restrict__ p, size_t n16, double *sink) {
   double acc = 0.0;
   const size_t st = (size_t)gridDim.x * blockDim.x;
@@ -1949,6 +1960,11 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
       c.ngys = (c.ngy + 1) & ~1;
     }
   }
+  // group / warp tables and the zeroed slack rows depend on the shape of the candidate set only, not on the axis values: a
+  // matcher that scores the same window around a new pose every scan re-uses them (saves two uploads and the memsets)
+  const int64_t shape_key[8] = {nx, ny, nt, c.grid_variant, c.grid_R, scan->n, ctx->rank, ctx->nranks};
+  const bool same_shape = c.shape_valid && memcmp(shape_key, c.shape_key, sizeof shape_key) == 0;
+  c.shape_valid = false;
   const int GR = c.grid_R;
   c.uniform_w = scan->n > 0;
   for (int i = 1; i < scan->n && c.uniform_w; ++i) c.uniform_w = scan->weight[i] == scan->weight[0];
@@ -1959,10 +1975,10 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   slice_of(ctx, rows, &r0, &r1);
   c.p0 = r0 * nx; c.p1 = r1 * nx;
   std::vector<int32_t> &groups = c.h_groups;
-  groups.clear();
+  if (!same_shape) groups.clear();
   c.t_lo = (int32_t)(r0 / ny);
   c.t_hi = r1 > r0 ? (int32_t)((r1 - 1) / ny) : c.t_lo;
-  for (int32_t t = c.t_lo; t <= c.t_hi && r1 > r0; ++t) {
+  for (int32_t t = c.t_lo; t <= c.t_hi && r1 > r0 && !same_shape; ++t) {
     int64_t ka = std::max<int64_t>(r0 - (int64_t)t * ny, 0), kb = std::min<int64_t>(r1 - (int64_t)t * ny, ny);
     for (int32_t k0 = (int32_t)(ka / GR * GR); k0 < kb; k0 += GR) {
       int32_t lo = (int32_t)std::max<int64_t>(ka - k0, 0), hi = (int32_t)std::min<int64_t>(kb - k0, GR);
@@ -2012,7 +2028,7 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   }
   const int N = scan->n;
   const int nt_loc = c.t_hi - c.t_lo + 1;
-  SG_TRY(upload(ctx, c.groups, groups.data(), groups.size() * sizeof(int32_t)));
+  if (!same_shape) SG_TRY(upload(ctx, c.groups, groups.data(), groups.size() * sizeof(int32_t)));
   if (c.grid_variant == 3) {
     SG_TRY(upload(ctx, c.blocks, blocks3.data(), blocks3.size() * sizeof(int32_t)));
     SG_TRY(upload(ctx, c.blk_rows, blk_rows3.data(), blk_rows3.size() * sizeof(int32_t)));
@@ -2050,16 +2066,18 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     // bands of at most 30 consecutive x, balanced: their columns fit the 14-column window of a warp's patch
     c.nb5 = (nx + 29) / 30; c.bw5 = (nx + c.nb5 - 1) / c.nb5;
     if (c.colrec.reserve(idx_rows * c.nb5 * 32) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "column records");
-    SG_CUDA(ctx, cudaMemsetAsync((char *)c.colrec.p + (idx_rows - SG_IDX_SLACK) * c.nb5 * 32, 0, (size_t)SG_IDX_SLACK * c.nb5 * 32, ctx->stream));
-    SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngys, 0, SG_IDX_SLACK * (size_t)c.ngys * sizeof(unsigned long long),
-                                 ctx->stream));
+    if (!same_shape) {
+      SG_CUDA(ctx, cudaMemsetAsync((char *)c.colrec.p + (idx_rows - SG_IDX_SLACK) * c.nb5 * 32, 0, (size_t)SG_IDX_SLACK * c.nb5 * 32, ctx->stream));
+      SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngys, 0,
+                                   SG_IDX_SLACK * (size_t)c.ngys * sizeof(unsigned long long), ctx->stream));
+    }
     if (!c.uniform_w) {  // weight pairs {w[i], w[i+1]}: the copy lanes move 16 bytes
       c.h_w2.assign(2 * ((size_t)N + SG_IDX_SLACK), 0.0);
       for (int i = 0; i < N; ++i) { c.h_w2[2 * (size_t)i] = scan->weight[i]; c.h_w2[2 * (size_t)i + 1] = i + 1 < N ? scan->weight[i + 1] : 0.0; }
       SG_TRY(upload(ctx, c.w2, c.h_w2.data(), c.h_w2.size() * sizeof(double)));
     }
   }
-  if (c.grid_variant == 4) {
+  if (c.grid_variant == 4 && !same_shape) {
     // warp table: the full bands of G = 32 / (nx % 32) consecutive y-groups, then ONE warp with the leftover columns of those
     // groups -- slow warps (their indexed branch diverges) so spread evenly over the launch
     std::vector<int32_t> &wt = c.h_wtask;
@@ -2076,6 +2094,10 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
     SG_CUDA(ctx, cudaMemsetAsync(c.cxp.as<int>() + (idx_rows - SG_IDX_SLACK) * nx, 0, SG_IDX_SLACK * (size_t)nx * sizeof(int), ctx->stream));
     SG_CUDA(ctx, cudaMemsetAsync(c.cyw.as<unsigned long long>() + (idx_rows - SG_IDX_SLACK) * c.ngys, 0, SG_IDX_SLACK * (size_t)c.ngys * sizeof(unsigned long long),
                                  ctx->stream));
+  }
+  if (c.grid_variant != 3) {  // (v3's block tables depend on the axis values)
+    memcpy(c.shape_key, shape_key, sizeof shape_key);
+    c.shape_valid = true;
   }
   c.kind = 1;
   return SLAMGPU_OK;
@@ -2263,9 +2285,11 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       }
     }
     if (device_trig && N > 0) {
-      long long tot = (long long)c.nt * N;
-      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.p_ts, c.nt, s->d_range, s->d_angle,
-                                                                            N, N, 1, c.trc.as<double>(), c.trs.as<double>());
+      // only the theta planes of this rank's slice (the table is indexed by the global theta number)
+      long long tot = (long long)nt_loc * N;
+      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.p_ts + c.t_lo, nt_loc, s->d_range, s->d_angle, N, N, 1,
+                                                                            c.trc.as<double>() + (size_t)c.t_lo * N,
+                                                                            c.trs.as<double>() + (size_t)c.t_lo * N);
       SG_LAUNCHED(ctx);
     }
     long long threads = (long long)c.n_groups * c.nx;
@@ -2385,16 +2409,18 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   SG_CUDA(ctx, cudaGetLastError());
   // per-rank best -> res[1] (keeps the guard counter accumulated in res[0].guard)
   Result *local = res + 1;
-  if (nblk > 0) {
+  const bool p2p = ctx->nranks > 1 && ctx->d_peer_mailbox && !ctx->p2p_broken;
+  if (nblk > 0 && !p2p) {
     k_reduce_blocks<<<1, 1024, 0, ctx->stream>>>(c.blk_best.as<Best>(), nblk, res);
     SG_LAUNCHED(ctx);
-  } else {
+  } else if (nblk <= 0) {
     Result empty{-INFINITY, LLONG_MAX, 0, 0};
     SG_CUDA(ctx, cudaMemcpyAsync(res, &empty, sizeof(Result), cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (ctx->nranks > 1 && ctx->d_peer_mailbox) {
-    k_exchange_finalize<<<1, 64, 0, ctx->stream>>>(res, ctx->d_peer_mailbox, ctx->rank, ctx->nranks, ++ctx->p2p_seq, init_score, local,
-                                                    ctx->d_p2p_status);
+  if (p2p) {
+    const long long deadline = (long long)(ctx->p2p_timeout_ms * 1.0e-3 * ctx->clock_hz);
+    k_exchange_finalize<<<1, 1024, 0, ctx->stream>>>(nblk > 0 ? c.blk_best.as<Best>() : nullptr, nblk, res, ctx->d_peer_mailbox, ctx->rank,
+                                                      ctx->nranks, ++ctx->p2p_seq, deadline, init_score, local, ctx->d_p2p_status);
     SG_LAUNCHED(ctx);
     SG_CUDA(ctx, cudaGetLastError());
     c.stats[6] = 1;
@@ -2435,7 +2461,11 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
   Result *h = (Result *)hp;
   SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (h->idx == LLONG_MIN) return sg_fail(ctx, SLAMGPU_E_NCCL, "a peer rank did not deliver its result within 2 s (peer-memory exchange)");
+  if (h->idx == LLONG_MIN) {
+    ctx->p2p_broken = true;  // a late message must never be taken for a new one: ncclAllGather from here on
+    return sg_fail(ctx, SLAMGPU_E_NCCL, "a peer rank did not deliver its result within %.0f ms (peer-memory exchange; ctx option p2p_timeout_ms)",
+                   ctx->p2p_timeout_ms);
+  }
   while (h->pad > 0 && c.kind == 1 && c.grid_variant > 1 && map) {
     // v4: some thread's 8 y do not fall into consecutive cell rows -> v2; v3: some block's cells did not fit its TMA box
     // -> v2; v2: two neighbouring y values are more than 7 cell rows apart, the packed row word cannot hold it -> the
