@@ -88,6 +88,14 @@ def estimator(type=EST_CONST, occ=(0.95, 1.0), empty=(0.01, 1.0), low_qual=0.01,
     return Estimator(type, occ[0], occ[1], empty[0], empty[1], low_qual, unknown_qual, shift)
 
 
+class Mt19937(C.Structure):
+    _fields_ = [("mt", C.c_uint32 * 624), ("idx", C.c_int)]
+
+
+class Normal(C.Structure):
+    _fields_ = [("mean", C.c_double), ("stddev", C.c_double), ("saved", C.c_double), ("saved_available", C.c_int)]
+
+
 def _load_orc():
     if not os.path.exists(ORC_SO):
         build(ref=False)
@@ -155,6 +163,9 @@ def _load_orc():
     L.orc_match_monte_carlo.argtypes = [C.c_void_p, C.POINTER(Scan), C.POINTER(SpeParams)] + [C.c_double] * 3 + [
         C.c_uint, C.c_double, C.c_double, C.c_uint, C.c_uint, C.POINTER(MatchResult)]
     L.orc_angle_histogram_values.argtypes = [C.c_int, c_dp, c_dp, C.POINTER(C.c_uint32)]
+    L.orc_mt_seed.argtypes = [C.POINTER(Mt19937), C.c_uint32]
+    L.orc_normal_sample.restype = C.c_double
+    L.orc_normal_sample.argtypes = [C.POINTER(Normal), C.POINTER(Mt19937)]
     return L
 
 
