@@ -276,6 +276,150 @@ __global__ void k_build_level(BuildArgs a) {
     SG_COPY_REC(cell, cur, a.stride);
 }
 
+// From-scratch build, five levels per pass.  k_build_level re-reads every level it has just written (and k_fill_level writes
+// each level once more before it): 4096^2 mean cells moved 625 MB for 357 MB of compulsory traffic, in 24 launches.  Here a
+// block owns one cell of level L0+5 = a 32 x 32 tile of the source level L0 (in external coordinates, so the 2 x 2 groups are
+// the reference's at every level whatever the origins).  Each of its 256 threads reads one 2 x 2 group of the source and
+// folds it in registers (level L0+1); the 16 x 16 results {record, impact, known} go to shared memory and are folded
+// 16x16 -> 8x8 -> 4x4 -> 2x2 -> 1, every level's cells written as they appear (the unknown prototype where no known child
+// exists).  The fold of one cell is build_take's: children in x-outer / y-inner order, a child replaces the current pick only
+// if its impact is greater by more than the reference's eps (rescalable_caching_grid_map.h:171-194, m3rsm_engine.h:101-126).
+// A cell that lies outside its level's array does not exist for the next level, exactly as when that level is read back
+// from memory.
+#define SG_FUSED_LEVELS 5
+struct FusedLevel { double *cells; int w, h, ox, oy; double unknown[SLAMGPU_MAX_STRIDE]; };
+struct FusedArgs {
+  const double *src;
+  int sw, sh, sox, soy;
+  FusedLevel lv[SG_FUSED_LEVELS];
+  int nlv, model, oie, tx0, ty0;
+};
+
+// one fold step of build_take on {have, impact}: true if the candidate replaces the current pick
+SG_DEV bool fused_takes(bool have, double best_imp, bool known, double xi) {
+  return known && !(have && sg::less_or_equal(xi, best_imp));
+}
+
+template <int STRIDE>
+SG_DEV void fused_store(const FusedLevel &L, int ix, int iy, bool have, double (&rec)[STRIDE], bool *inside) {
+  *inside = ix >= 0 && ix < L.w && iy >= 0 && iy < L.h;
+#pragma unroll
+  for (int k = 0; k < STRIDE; ++k) rec[k] = have ? rec[k] : L.unknown[k];
+  if (*inside) {
+    double *d = L.cells + ((size_t)iy * L.w + ix) * STRIDE;
+    if (STRIDE == 2) *reinterpret_cast<double2 *>(d) = make_double2(rec[0], rec[1]);
+    else {
+#pragma unroll
+      for (int k = 0; k < STRIDE; ++k) d[k] = rec[k];
+    }
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256, 6) k_build_fused(FusedArgs a) {
+  constexpr int STRIDE = MODEL == SLAMGPU_CELL_LWW ? 3 : (MODEL == SLAMGPU_CELL_AFFINE || MODEL == SLAMGPU_CELL_MEAN) ? 2 :
+                         MODEL == SLAMGPU_CELL_GMAPPING ? 5 : 6;
+  // levels L0+3 .. L0+5 are folded by warp 0 alone out of this buffer (8 x 8 cells of level L0+2, then 4 x 4, 2 x 2)
+  __shared__ double s_rec[STRIDE][64 + 16 + 4];
+  __shared__ double s_imp[64 + 16 + 4];
+  __shared__ unsigned char s_known[64 + 16 + 4];
+  const int t = threadIdx.x, lane = t & 31;
+  const int TX = a.tx0 + (int)blockIdx.x, TY = a.ty0 + (int)blockIdx.y;
+  // a warp holds 16 x 2 cells of level L0+1: lane = (qy & 1) * 16 + qx
+  const int qx = t & 15, qy = t >> 4;
+  // ---- level L0+1 from this thread's 2 x 2 group of the source, in registers
+  bool have = false;
+  double imp = 0.0, pick[STRIDE];
+#pragma unroll
+  for (int k = 0; k < STRIDE; ++k) pick[k] = 0.0;
+#pragma unroll
+  for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int sx = TX * 32 + 2 * qx + dx + a.sox, sy = TY * 32 + 2 * qy + dy + a.soy;
+      if (sx < 0 || sx >= a.sw || sy < 0 || sy >= a.sh) continue;
+      double rec[SLAMGPU_MAX_STRIDE];
+      const double *r = a.src + ((size_t)sy * a.sw + sx) * STRIDE;
+      if (STRIDE == 2) {  // one 16-byte load per cell
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(r));
+        rec[0] = v.x; rec[1] = v.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < STRIDE; ++k) rec[k] = __ldg(r + k);
+      }
+      const bool known = !sg::rec_is_unknown(MODEL, rec);
+      const double xi = sg::cell_impact(MODEL, a.oie, rec, 0.0, 0.0);
+      if (!fused_takes(have, imp, known, xi)) continue;
+      have = true; imp = xi;
+#pragma unroll
+      for (int k = 0; k < STRIDE; ++k) pick[k] = rec[k];
+    }
+  bool inside;
+  fused_store<STRIDE>(a.lv[0], TX * 16 + qx + a.lv[0].ox, TY * 16 + qy + a.lv[0].oy, have, pick, &inside);
+  have = have && inside;
+  if (a.nlv < 2) return;
+  // ---- level L0+2 by shuffles: the 2 x 2 group of a level-(L0+2) cell sits in one warp; its leader is the lane with even qx, qy
+  {
+    const int base = lane & 14;  // lane of child (dx, dy) = base + dx + 16 * dy
+    bool h2 = false;
+    double i2 = 0.0;
+    int src = base;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int l = base + dx + 16 * dy;
+        const bool known = __shfl_sync(0xffffffffu, (int)have, l) != 0;
+        const double xi = __shfl_sync(0xffffffffu, imp, l);
+        if (!fused_takes(h2, i2, known, xi)) continue;
+        h2 = true; i2 = xi; src = l;
+      }
+    double rec2[STRIDE];
+#pragma unroll
+    for (int k = 0; k < STRIDE; ++k) rec2[k] = __shfl_sync(0xffffffffu, pick[k], src);
+    if ((qx & 1) == 0 && (qy & 1) == 0) {
+      const int x = qx >> 1, y = qy >> 1;
+      bool in2;
+      fused_store<STRIDE>(a.lv[1], TX * 8 + x + a.lv[1].ox, TY * 8 + y + a.lv[1].oy, h2, rec2, &in2);
+      const int c = y * 8 + x;
+#pragma unroll
+      for (int k = 0; k < STRIDE; ++k) s_rec[k][c] = rec2[k];
+      s_imp[c] = i2; s_known[c] = (h2 && in2) ? 1 : 0;
+    }
+  }
+  if (a.nlv < 3) return;
+  __syncthreads();
+  if (t >= 32) return;
+  // ---- levels L0+3 .. L0+5: warp 0, out of shared memory
+  int side = 8, off = 0;
+#pragma unroll 1
+  for (int j = 2; j < a.nlv; ++j) {
+    const int n = side >> 1, noff = off + side * side;
+    if (t < n * n) {
+      const int x = t % n, y = t / n;
+      bool h = false;
+      double bi = 0.0;
+      int best = off;
+      for (int dx = 0; dx < 2; ++dx)
+        for (int dy = 0; dy < 2; ++dy) {
+          const int c = off + (2 * y + dy) * side + 2 * x + dx;
+          if (!fused_takes(h, bi, s_known[c] != 0, s_imp[c])) continue;
+          h = true; bi = s_imp[c]; best = c;
+        }
+      double rec[STRIDE];
+#pragma unroll
+      for (int k = 0; k < STRIDE; ++k) rec[k] = s_rec[k][best];
+      bool in;
+      fused_store<STRIDE>(a.lv[j], TX * n + x + a.lv[j].ox, TY * n + y + a.lv[j].oy, h, rec, &in);
+#pragma unroll
+      for (int k = 0; k < STRIDE; ++k) s_rec[k][noff + t] = rec[k];
+      s_imp[noff + t] = bi; s_known[noff + t] = (h && in) ? 1 : 0;
+    }
+    __syncwarp();
+    side = n; off = noff;
+  }
+}
+
 struct RecParam { double v[SLAMGPU_MAX_STRIDE]; };
 __global__ void k_fill_level(double *cells, size_t n_cells, int stride, RecParam rec) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
@@ -418,37 +562,77 @@ extern "C" int slamgpu_pyramid_level_download(slamgpu_pyramid *p, int32_t level,
   return SLAMGPU_OK;
 }
 
+static int floor_div_i(int v, int d) { return v >= 0 ? v / d : -((-v + d - 1) / d); }
+
 extern "C" int slamgpu_pyramid_build(slamgpu_pyramid *p) {
   if (!p) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   SG_CUDA(ctx, cudaSetDevice(ctx->device));
   SG_TRY(ensure_continuous(p));
-  for (size_t id = 1; id < p->lv.size(); ++id) {
+  // geometry first (it depends on the finer level's extent only): every level covers the finer one, as the reference's would
+  for (size_t id = 1; id + 1 < p->lv.size(); ++id) {
     slamgpu_map *src = p->lv[id - 1], *dst = p->lv[id];
-    const bool last = id + 1 == p->lv.size();
-    if (!last && dst->grow != SLAMGPU_GROW_NONE && src->w > 0 && src->h > 0) {
-      // make the level cover the finer one: the two extreme finer cells, halved toward -inf
+    if (dst->grow != SLAMGPU_GROW_NONE && src->w > 0 && src->h > 0) {
       GrowState g{dst->w, dst->h, dst->ox, dst->oy, dst->grow};
       auto half = [](int v) { return (int)std::floor(v / 2.0); };
       bool grew = g.ensure_inside(half(-src->ox), half(-src->oy));
       grew |= g.ensure_inside(half(src->w - 1 - src->ox), half(src->h - 1 - src->oy));
       if (grew) SG_TRY(sg_map_regrow(dst, g));
     }
+    SG_TRY(ensure_continuous(p));
+  }
+  const size_t nlev = p->lv.size();
+  // levels 1 .. nlev-2, five per pass (k_build_fused); the last level is the single infinite cell
+  bool first = true;
+  for (size_t l0 = 0; l0 + 2 < nlev; l0 += SG_FUSED_LEVELS) {
+    slamgpu_map *src = p->lv[l0];
+    FusedArgs a;
+    a.src = src->d_cells; a.sw = src->w; a.sh = src->h; a.sox = src->ox; a.soy = src->oy;
+    a.model = src->model; a.oie = p->oie;
+    a.nlv = (int)std::min<size_t>(SG_FUSED_LEVELS, nlev - 2 - l0);
+    int tx0 = floor_div_i(-src->ox, 32), tx1 = floor_div_i(src->w - 1 - src->ox, 32);
+    int ty0 = floor_div_i(-src->oy, 32), ty1 = floor_div_i(src->h - 1 - src->oy, 32);
+    for (int j = 0; j < a.nlv; ++j) {
+      slamgpu_map *m = p->lv[l0 + 1 + j];
+      FusedLevel &L = a.lv[j];
+      L.cells = m->d_cells; L.w = m->w; L.h = m->h; L.ox = m->ox; L.oy = m->oy;
+      memcpy(L.unknown, m->unknown, sizeof L.unknown);
+      const int per = 32 >> (j + 1);  // cells of this level per tile side
+      if (m->w > 0 && m->h > 0) {
+        tx0 = std::min(tx0, floor_div_i(-m->ox, per)); tx1 = std::max(tx1, floor_div_i(m->w - 1 - m->ox, per));
+        ty0 = std::min(ty0, floor_div_i(-m->oy, per)); ty1 = std::max(ty1, floor_div_i(m->h - 1 - m->oy, per));
+      }
+      sg_map_invalidate_lut(m);
+    }
+    a.tx0 = tx0; a.ty0 = ty0;
+    dim3 grd((unsigned)(tx1 - tx0 + 1), (unsigned)(ty1 - ty0 + 1));
+    if (first) cudaEventRecord(ctx->evk0, ctx->stream);
+    switch (src->model) {
+      case SLAMGPU_CELL_LWW: k_build_fused<SLAMGPU_CELL_LWW><<<grd, 256, 0, ctx->stream>>>(a); break;
+      case SLAMGPU_CELL_AFFINE: k_build_fused<SLAMGPU_CELL_AFFINE><<<grd, 256, 0, ctx->stream>>>(a); break;
+      case SLAMGPU_CELL_MEAN: k_build_fused<SLAMGPU_CELL_MEAN><<<grd, 256, 0, ctx->stream>>>(a); break;
+      case SLAMGPU_CELL_TBM_CONSISTENT: k_build_fused<SLAMGPU_CELL_TBM_CONSISTENT><<<grd, 256, 0, ctx->stream>>>(a); break;
+      case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: k_build_fused<SLAMGPU_CELL_TBM_UNKNOWN_EVEN><<<grd, 256, 0, ctx->stream>>>(a); break;
+      default: k_build_fused<SLAMGPU_CELL_GMAPPING><<<grd, 256, 0, ctx->stream>>>(a); break;
+    }
+    if (first) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->evk_valid = true; first = false; }
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaGetLastError());
+  }
+  if (nlev >= 2) {
+    slamgpu_map *src = p->lv[nlev - 2], *dst = p->lv[nlev - 1];
     RecParam rp;
     memcpy(rp.v, dst->unknown, sizeof rp.v);
-    k_fill_level<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dst->d_cells, (size_t)dst->w * dst->h, dst->stride, rp);
+    k_fill_level<<<1, 32, 0, ctx->stream>>>(dst->d_cells, (size_t)dst->w * dst->h, dst->stride, rp);
     BuildArgs a;
     a.src = src->d_cells; a.sw = src->w; a.sh = src->h; a.sox = src->ox; a.soy = src->oy;
     a.dst = dst->d_cells; a.dw = dst->w; a.dh = dst->h; a.dox = dst->ox; a.doy = dst->oy;
-    a.stride = dst->stride; a.model = dst->model; a.oie = p->oie; a.last = last ? 1 : 0;
+    a.stride = dst->stride; a.model = dst->model; a.oie = p->oie; a.last = 1;
     dim3 blk(32, 8), grd((dst->w + 31) / 32, (dst->h + 7) / 8);
-    if (id == 1) { cudaEventRecord(ctx->evk0, ctx->stream); }
     k_build_level<<<grd, blk, 0, ctx->stream>>>(a);
-    if (id == 1) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->evk_valid = true; }
     ctx->launches += 2;
     SG_CUDA(ctx, cudaGetLastError());
     sg_map_invalidate_lut(dst);
-    if (!last) SG_TRY(ensure_continuous(p));
   }
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
@@ -900,6 +1084,6 @@ extern "C" int slamgpu_debug_m3rsm(double x_limit, double y_limit, double rot_li
 #define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
 void sg_preload_pyramid() {  // see sg_preload_score
   SG_TOUCH(k_order_entries); SG_TOUCH(k_level_coords); SG_TOUCH(k_level_keys); SG_TOUCH(k_level_gather); SG_TOUCH(k_level_fold);
-  SG_TOUCH(k_build_level); SG_TOUCH(k_fill_level); SG_TOUCH(k_window_terms); SG_TOUCH(k_ordered_sums); SG_TOUCH(k_ordered_sums_staged);
+  SG_TOUCH(k_build_level); SG_TOUCH(k_build_fused<SLAMGPU_CELL_LWW>); SG_TOUCH(k_build_fused<SLAMGPU_CELL_MEAN>); SG_TOUCH(k_build_fused<SLAMGPU_CELL_TBM_CONSISTENT>); SG_TOUCH(k_build_fused<SLAMGPU_CELL_GMAPPING>); SG_TOUCH(k_fill_level); SG_TOUCH(k_window_terms); SG_TOUCH(k_ordered_sums); SG_TOUCH(k_ordered_sums_staged);
   (void)cudaGetLastError();
 }

@@ -191,3 +191,64 @@ def test_configs4_pyramid_4096_13_levels_and_m3rsm_match(sg, gpu, refso):
         assert st["scored"] > 2 * st["rotations"] and st["branches"] > 3
     finally:
         pyr.close(); gm.close()
+
+
+def _le(a, b):
+    """sg::less_or_equal / math_utils.h:10-51 on arrays"""
+    sc = np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    return (np.abs(a - b) <= 1e-7 * sc) | (a < b + 2.220446049250313e-16)
+
+
+def _fold_level(fine, fi, ci, unknown):
+    """one level of RescalableCachingGridMap from the finer one, in numpy: per coarse cell the children in x-outer / y-inner
+    order, a child replaces the pick only if its impact is greater by more than eps; MeanProbabilityCell records {p, n},
+    discrepancy impact 1 - |p - 1|, unknown = n == 0"""
+    H, W = ci["h"], ci["w"]
+    Y, X = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    out = np.empty((H, W, 2)); out[...] = unknown
+    have = np.zeros((H, W), bool)
+    best = np.zeros((H, W))
+    for dx in (0, 1):
+        for dy in (0, 1):
+            sx = 2 * (X - ci["ox"]) + dx + fi["ox"]
+            sy = 2 * (Y - ci["oy"]) + dy + fi["oy"]
+            ok = (sx >= 0) & (sx < fi["w"]) & (sy >= 0) & (sy < fi["h"])
+            rec = fine[np.clip(sy, 0, fi["h"] - 1), np.clip(sx, 0, fi["w"] - 1)]
+            known = ok & (rec[..., 1] != 0)
+            imp = 1.0 - np.abs(rec[..., 0] - 1.0)
+            take = known & (~have | ~_le(imp, best))
+            out[take] = rec[take]
+            best = np.where(take, imp, best)
+            have |= take
+    return out
+
+
+def test_configs4_from_scratch_build_4096(sg, gpu):
+    """k_build_fused at the configs[4] size: every level equals the fold of the level below it (bit-equal records), with
+    unknown holes and impacts closer than the comparison's eps in the input"""
+    rng = np.random.default_rng(5300)
+    size = 4096
+    cells = np.zeros((size, size, 2))
+    cells[..., 0] = np.round(rng.random((size, size)), 6) * 0.999 + rng.integers(0, 3, (size, size)) * 3e-8  # near-ties within eps
+    cells[..., 1] = rng.integers(0, 4, (size, size))   # a quarter of the cells unknown
+    cells[1000:1400, 2000:2600, 1] = 0                  # and a hole larger than several coarse cells
+    cells[..., 0] = np.where(cells[..., 1] == 0, 0.5, cells[..., 0])
+    gm = sg.GridMap(gpu, size, size, 0.025, sg.CELL_MEAN, sg.GROW_PLAIN)
+    gm.upload(cells)
+    pyr = sg.Pyramid(gpu, gm, sg.OIE_DISCREPANCY)
+    try:
+        pyr.build()
+        n = pyr.levels()
+        assert n == 13
+        fine, fi = cells, pyr.level_info(0)
+        unknown = np.array([0.5, 0.0])
+        for lv in range(1, n - 1):
+            ci = pyr.level_info(lv)
+            got = pyr.level(lv)
+            want = _fold_level(fine, fi, ci, unknown)
+            assert np.array_equal(got, want), lv
+            fine, fi = got, ci
+        top = pyr.level(n - 1)
+        assert top.shape[:2] == (1, 1) and top[0, 0, 1] != 0
+    finally:
+        pyr.close(); gm.close()

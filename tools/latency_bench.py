@@ -37,7 +37,7 @@ def pyramid_numbers(ctx, size=4096, scale=0.025):
         ctx.sync(); ctx.timer_begin(); pyr.build(); ts.append(ctx.timer_end())
     ms = float(np.median(ts))
     levels = pyr.levels()
-    by = 4.0 / 3.0 * size * size * 2 * 8 * 2  # read + write of every level's records
+    by = size * size * 2 * 8 * (1.0 + 1.0 / 3.0)  # compulsory traffic: the fine records read once, every coarser level written once
     pyr.close(); gm.close()
     # incremental maintenance on a map built from scans: one scan inserted into the fine map and folded up through
     # every level (K2/K3 + K4)
