@@ -61,7 +61,8 @@ enum {
   SLAMGPU_CELL_TBM_CONSISTENT = 3,
   SLAMGPU_CELL_TBM_UNKNOWN_EVEN = 4,
   SLAMGPU_CELL_GMAPPING = 5,
-  SLAMGPU_CELL_MODELS = 6
+  SLAMGPU_CELL_CREDIBILIST = 6, /* src/slams/credibilist/grid_cell.h:10-68: TBM belief, disjunctive score */
+  SLAMGPU_CELL_MODELS = 7
 };
 #define SLAMGPU_MAX_STRIDE 8
 

@@ -11,7 +11,7 @@
 #define MAXD(a, b) (((a) < (b)) ? (b) : (a))
 
 int orc_model_stride(int model) {
-  static const int s[ORC_CELL_MODELS] = {3, 2, 2, 6, 6, 5};
+  static const int s[ORC_CELL_MODELS] = {3, 2, 2, 6, 6, 5, 6};
   return (model >= 0 && model < ORC_CELL_MODELS) ? s[model] : 0;
 }
 
@@ -24,7 +24,8 @@ void orc_default_unknown(int model, double *r) {
   case ORC_CELL_AFFINE: r[0] = 0.5; r[1] = 0; break;
   case ORC_CELL_MEAN: r[0] = 0.5; r[1] = 0; break;
   case ORC_CELL_TBM_CONSISTENT:
-  case ORC_CELL_TBM_UNKNOWN_EVEN: r[0] = 0.5; r[1] = 1; r[2] = 1; r[3] = 0; r[4] = 0; r[5] = 0; break;
+  case ORC_CELL_TBM_UNKNOWN_EVEN:
+  case ORC_CELL_CREDIBILIST: r[0] = 0.5; r[1] = 1; r[2] = 1; r[3] = 0; r[4] = 0; r[5] = 0; break;
   case ORC_CELL_GMAPPING: r[0] = -1; break;
   }
 }
@@ -175,7 +176,8 @@ void orc_cell_update(int model, double *r, int aoo_is_occ, double p, double q, d
     break;
   }
   case ORC_CELL_TBM_CONSISTENT:
-  case ORC_CELL_TBM_UNKNOWN_EVEN: {
+  case ORC_CELL_TBM_UNKNOWN_EVEN:
+  case ORC_CELL_CREDIBILIST: { /* credibilist/grid_cell.h:23-29 + TBM_prob_conversion.h:8-21: the unknown-even arithmetic */
     if (!valid) return;
     tbm b = {{r[2], r[3], r[4], 0.0}}, m = aoo2tbm(p, q, quality);
     b = tbm_conj(&b, &m);
@@ -221,6 +223,14 @@ double orc_cell_discrepancy(int model, const double *r, double p, double q, doub
     double known = 1 - unknown;
     double known_disc = known * (comb.b[3] + d_occ) / 2.0;
     return unknown / 2 + known_disc;
+  }
+  case ORC_CELL_CREDIBILIST: { /* 1 - score: credibilist/grid_cell.h:31-40, disjunctive transferable_belief_model.h:145-162 */
+    tbm that = aoo2tbm(p, q, quality), b = {{r[2], r[3], r[4], 0.0}}, t = {{0.0, 0.0, 0.0, 0.0}};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) t.b[i & j] += that.b[i] * b.b[j];
+    double tot = t.b[0] + t.b[1] + t.b[2] + t.b[3];
+    double occ = tot == 0.0 ? 0.0 : t.b[2] / tot; /* TBM::normalize: all-zero -> default (occupied 0) */
+    return 1.0 - occ;
   }
   case ORC_CELL_GMAPPING: {
     double d = pow(r[1] - ox, 2) + pow(r[2] - oy, 2);

@@ -59,6 +59,7 @@
 #include "src/core/scan_matchers/bf_multi_res_scan_matcher.h"
 #include "src/slams/gmapping/gmapping_grid_cell.h"
 #include "src/slams/gmapping/gmapping_occupancy_observation_pe.h"
+#include "src/slams/credibilist/grid_cell.h"
 #undef private
 #undef protected
 
@@ -82,7 +83,7 @@ template <class F, class G> static void ref_guarded(F body, G on_assert) {
 namespace {
 
 int shim_stride(int model) {
-  static const int s[ORC_CELL_MODELS] = {3, 2, 2, 6, 6, 5};
+  static const int s[ORC_CELL_MODELS] = {3, 2, 2, 6, 6, 5, 6};
   return s[model];
 }
 void shim_default_unknown(int model, double *r) {
@@ -92,7 +93,8 @@ void shim_default_unknown(int model, double *r) {
   case ORC_CELL_AFFINE: r[0] = 0.5; break;
   case ORC_CELL_MEAN: r[0] = 0.5; break;
   case ORC_CELL_TBM_CONSISTENT:
-  case ORC_CELL_TBM_UNKNOWN_EVEN: r[0] = 0.5; r[1] = 1; r[2] = 1; break;
+  case ORC_CELL_TBM_UNKNOWN_EVEN:
+  case ORC_CELL_CREDIBILIST: r[0] = 0.5; r[1] = 1; r[2] = 1; break;
   case ORC_CELL_GMAPPING: r[0] = -1; break;
   }
 }
@@ -127,6 +129,13 @@ std::shared_ptr<GridCell> make_cell(int model, const double *r) {
     c->_is_unknown = r[5] == 0;
     return c;
   }
+  case ORC_CELL_CREDIBILIST: {
+    auto c = std::make_shared<CredibilistCell>();
+    c->_occupancy = Occupancy{r[0], r[1]};
+    c->_belief = TBM(r[2], r[3], r[4], 0.0);
+    c->_is_unknown = r[5] == 0;
+    return c;
+  }
   case ORC_CELL_GMAPPING: {
     auto c = std::make_shared<GmappingBaseCell>();
     c->_occupancy.prob_occ = r[0];
@@ -149,6 +158,13 @@ void export_cell(int model, const GridCell &c, double *r) {
   case ORC_CELL_TBM_CONSISTENT:
   case ORC_CELL_TBM_UNKNOWN_EVEN: {
     auto &t = static_cast<const TbmBaseCell &>(c);
+    r[0] = c.occupancy().prob_occ; r[1] = c.occupancy().estimation_quality;
+    r[2] = t._belief.unknown(); r[3] = t._belief.empty(); r[4] = t._belief.occupied();
+    r[5] = c.is_unknown() ? 0 : 1;
+    break;
+  }
+  case ORC_CELL_CREDIBILIST: {
+    auto &t = static_cast<const CredibilistCell &>(c);
     r[0] = c.occupancy().prob_occ; r[1] = c.occupancy().estimation_quality;
     r[2] = t._belief.unknown(); r[3] = t._belief.empty(); r[4] = t._belief.occupied();
     r[5] = c.is_unknown() ? 0 : 1;

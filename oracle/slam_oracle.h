@@ -44,7 +44,7 @@ extern "C" {
  */
 enum { ORC_CELL_LWW = 0, ORC_CELL_AFFINE = 1, ORC_CELL_MEAN = 2,
        ORC_CELL_TBM_CONSISTENT = 3, ORC_CELL_TBM_UNKNOWN_EVEN = 4,
-       ORC_CELL_GMAPPING = 5, ORC_CELL_MODELS = 6 };
+       ORC_CELL_GMAPPING = 5, ORC_CELL_CREDIBILIST = 6 /* src/slams/credibilist/grid_cell.h */, ORC_CELL_MODELS = 7 };
 #define ORC_MAX_STRIDE 8
 
 enum { ORC_OIE_DISCREPANCY = 0, ORC_OIE_OCCUPANCY = 1 };

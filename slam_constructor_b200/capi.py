@@ -10,8 +10,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-CELL_LWW, CELL_AFFINE, CELL_MEAN, CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN, CELL_GMAPPING = range(6)
-STRIDE = {0: 3, 1: 2, 2: 2, 3: 6, 4: 6, 5: 5}
+CELL_LWW, CELL_AFFINE, CELL_MEAN, CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN, CELL_GMAPPING, CELL_CREDIBILIST = range(7)
+STRIDE = {0: 3, 1: 2, 2: 2, 3: 6, 4: 6, 5: 5, 6: 6}
 OIE_DISCREPANCY, OIE_OCCUPANCY = 0, 1
 OOPE_OBSTACLE, OOPE_MAX, OOPE_MEAN, OOPE_OVERLAP, OOPE_GMAPPING = range(5)
 GROW_NONE, GROW_PLAIN, GROW_TILED = range(3)

@@ -377,7 +377,8 @@ extern "C" void slamgpu_default_unknown(int model, double *r) {
     case SLAMGPU_CELL_AFFINE:
     case SLAMGPU_CELL_MEAN: r[0] = 0.5; break;
     case SLAMGPU_CELL_TBM_CONSISTENT:
-    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: r[0] = 0.5; r[1] = 1; r[2] = 1; break;
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN:
+    case SLAMGPU_CELL_CREDIBILIST: r[0] = 0.5; r[1] = 1; r[2] = 1; break;
     case SLAMGPU_CELL_GMAPPING: r[0] = -1; break;
   }
 }

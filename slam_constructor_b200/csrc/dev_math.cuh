@@ -95,7 +95,8 @@ SG_HD int model_stride(int model) {
     case SLAMGPU_CELL_AFFINE: return 2;
     case SLAMGPU_CELL_MEAN: return 2;
     case SLAMGPU_CELL_TBM_CONSISTENT:
-    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: return 6;
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN:
+    case SLAMGPU_CELL_CREDIBILIST: return 6;
     case SLAMGPU_CELL_GMAPPING: return 5;
   }
   return 0;
@@ -178,7 +179,8 @@ SG_DEV void cell_update(int model, double *r, double p, double q, double obx, do
       break;
     }
     case SLAMGPU_CELL_TBM_CONSISTENT:
-    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: {
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN:
+    case SLAMGPU_CELL_CREDIBILIST: {  // CredibilistCell::operator+= is TbmUnknownEvenOccCell's arithmetic (grid_cell.h:23-29, TBM_prob_conversion.h:8-21)
       if (!valid) return;
       Tbm b = {r[2], r[3], r[4], 0.0}, m = aoo2tbm(p, q, quality);
       // a tiny or subnormal mass anywhere: take the divisions with the exact shortcuts (see div_chain)
@@ -227,6 +229,20 @@ SG_DEV double cell_discrepancy_obstacle(int model, const double *r, double obx, 
       double known = sub(1.0, unknown);
       double known_disc = div(mul(known, add(comb.c, d_occ)), 2.0);
       return add(div(unknown, 2.0), known_disc);
+    }
+    case SLAMGPU_CELL_CREDIBILIST: {
+      // 1 - score(aoo): disjunctive(AOO_to_TBM(aoo), belief).occupied(), src/slams/credibilist/grid_cell.h:31-40,
+      // transferable_belief_model.h:145-162 -- products accumulated in (this, that) order into t[this & that], then normalised
+      const Tbm that = aoo2tbm(1.0, 1.0, 1.0);
+      const double lb[4] = {that.u, that.e, that.o, that.c}, rb[4] = {r[2], r[3], r[4], 0.0};
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[i & j] = add(t[i & j], mul(lb[i], rb[j]));
+      const double tot = add(add(add(t[0], t[1]), t[2]), t[3]);
+      const double occ = tot == 0.0 ? 0.0 : div(t[2], tot);
+      return sub(1.0, occ);
     }
     case SLAMGPU_CELL_GMAPPING: {
       double dx = sub(r[1], obx), dy = sub(r[2], oby);

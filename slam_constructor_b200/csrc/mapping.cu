@@ -1055,7 +1055,7 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     ra.aoo_p = aoo_p; ra.aoo_q = aoo_q; ra.stride = maps[0]->stride; ra.model = maps[0]->model; ra.ring = ring;
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     SG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    const bool tbm_cells = ra.model == SLAMGPU_CELL_TBM_CONSISTENT || ra.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
+    const bool tbm_cells = ra.model == SLAMGPU_CELL_TBM_CONSISTENT || ra.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN || ra.model == SLAMGPU_CELL_CREDIBILIST;
     const long long warps = (long long)n * (2 * ring + 1) * (2 * ring + 1);
     if (tbm_cells) k_apply_ring<true><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
     else k_apply_ring<false><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
@@ -1087,7 +1087,7 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   cudaEventRecord(ctx->evk0, ctx->stream);
   k_apply<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(aa);
   {
-    const bool tbm_cells = aa.model == SLAMGPU_CELL_TBM_CONSISTENT || aa.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
+    const bool tbm_cells = aa.model == SLAMGPU_CELL_TBM_CONSISTENT || aa.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN || aa.model == SLAMGPU_CELL_CREDIBILIST;
     const int blocks = ctx->sm_count * 2;
     if (tbm_cells && trace) k_apply_long<true, true><<<blocks, 128, 0, ctx->stream>>>(aa);
     else if (tbm_cells) k_apply_long<true, false><<<blocks, 128, 0, ctx->stream>>>(aa);

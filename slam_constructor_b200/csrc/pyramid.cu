@@ -613,6 +613,7 @@ extern "C" int slamgpu_pyramid_build(slamgpu_pyramid *p) {
       case SLAMGPU_CELL_MEAN: k_build_fused<SLAMGPU_CELL_MEAN><<<grd, 256, 0, ctx->stream>>>(a); break;
       case SLAMGPU_CELL_TBM_CONSISTENT: k_build_fused<SLAMGPU_CELL_TBM_CONSISTENT><<<grd, 256, 0, ctx->stream>>>(a); break;
       case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: k_build_fused<SLAMGPU_CELL_TBM_UNKNOWN_EVEN><<<grd, 256, 0, ctx->stream>>>(a); break;
+      case SLAMGPU_CELL_CREDIBILIST: k_build_fused<SLAMGPU_CELL_CREDIBILIST><<<grd, 256, 0, ctx->stream>>>(a); break;
       default: k_build_fused<SLAMGPU_CELL_GMAPPING><<<grd, 256, 0, ctx->stream>>>(a); break;
     }
     if (first) { cudaEventRecord(ctx->evk1, ctx->stream); ctx->evk_valid = true; first = false; }

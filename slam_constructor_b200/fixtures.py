@@ -17,7 +17,7 @@ import struct
 
 import numpy as np
 
-from .capi import (CELL_AFFINE, CELL_GMAPPING, CELL_LWW, CELL_MEAN, CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN, STRIDE)
+from .capi import (CELL_AFFINE, CELL_CREDIBILIST, CELL_GMAPPING, CELL_LWW, CELL_MEAN, CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN, STRIDE)
 
 _HEADER = struct.Struct("<iidii")
 _BASE = np.dtype([("p", "<f8"), ("q", "<f8"), ("unknown", "u1")])
@@ -50,7 +50,7 @@ def write_scan2d(path, r, a, occ=None):
 
 
 def _cell_dtype(model):
-    return _TBM if model in (CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN) else _BASE
+    return _TBM if model in (CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN, CELL_CREDIBILIST) else _BASE
 
 
 def read_map(path, model):
@@ -70,7 +70,7 @@ def read_map(path, model):
         cells[..., 1] = known
     elif model == CELL_MEAN:
         cells[..., 1] = known  # _n is not serialised upstream
-    elif model in (CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN):
+    elif model in (CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN, CELL_CREDIBILIST):
         cells[..., 1] = raw["q"]; cells[..., 2] = raw["u"]; cells[..., 3] = raw["e"]; cells[..., 4] = raw["o"]
         cells[..., 5] = known
     elif model == CELL_GMAPPING:
@@ -85,7 +85,7 @@ def write_map(path, cells, model, scale, ox, oy):
     dt = _cell_dtype(model)
     raw = np.zeros((h, w), dtype=dt)
     raw["p"] = cells[..., 0]
-    known_col = {CELL_LWW: 2, CELL_AFFINE: 1, CELL_MEAN: 1, CELL_TBM_CONSISTENT: 5, CELL_TBM_UNKNOWN_EVEN: 5, CELL_GMAPPING: 4}[model]
+    known_col = {CELL_LWW: 2, CELL_AFFINE: 1, CELL_MEAN: 1, CELL_TBM_CONSISTENT: 5, CELL_TBM_UNKNOWN_EVEN: 5, CELL_CREDIBILIST: 5, CELL_GMAPPING: 4}[model]
     raw["unknown"] = (cells[..., known_col] == 0).astype(np.uint8)
     raw["q"] = cells[..., 1] if model in (CELL_LWW, CELL_TBM_CONSISTENT, CELL_TBM_UNKNOWN_EVEN) else 1.0
     if dt is _TBM:

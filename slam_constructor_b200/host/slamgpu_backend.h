@@ -81,6 +81,9 @@ inline int cell_model_of(const GridCell &proto) {
   if (dynamic_cast<const TbmOccConsistentCell *>(&proto)) return SLAMGPU_CELL_TBM_CONSISTENT;
   if (dynamic_cast<const TbmUnknownEvenOccCell *>(&proto)) return SLAMGPU_CELL_TBM_UNKNOWN_EVEN;
   if (dynamic_cast<const GmappingBaseCell *>(&proto)) return SLAMGPU_CELL_GMAPPING;
+#ifdef SLAM_CTOR_SLAM_CREDIBILIST_GRID_CELL_H  // src/slams/credibilist/grid_cell.h included before this header
+  if (dynamic_cast<const CredibilistCell *>(&proto)) return SLAMGPU_CELL_CREDIBILIST;
+#endif
   return SLAMGPU_CELL_LWW;  // GridCell itself (last write wins) and test doubles built on it
 }
 
@@ -121,7 +124,8 @@ public:
     switch (model) {
     case SLAMGPU_CELL_LWW: return Occupancy{r[0], r[1]};
     case SLAMGPU_CELL_TBM_CONSISTENT:
-    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN: return Occupancy{r[0], r[1]};
+    case SLAMGPU_CELL_TBM_UNKNOWN_EVEN:
+    case SLAMGPU_CELL_CREDIBILIST: return Occupancy{r[0], r[1]};
     default: return Occupancy{r[0], 1};
     }
   }

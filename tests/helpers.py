@@ -16,7 +16,7 @@ def random_cells(rng, h, w, model, known_frac=0.7):
         c[..., 0] = np.where(known, p, 0.5); c[..., 1] = known
     elif model == ob.CELL_MEAN:
         c[..., 0] = np.where(known, p, 0.5); c[..., 1] = np.where(known, rng.integers(1, 30, (h, w)), 0)
-    elif model in (ob.CELL_TBM_CONSISTENT, ob.CELL_TBM_UNKNOWN_EVEN):
+    elif model in (ob.CELL_TBM_CONSISTENT, ob.CELL_TBM_UNKNOWN_EVEN, ob.CELL_CREDIBILIST):
         b = rng.random((h, w, 3)) + 1e-3
         b /= b.sum(-1, keepdims=True)
         u, e, o = b[..., 0], b[..., 1], b[..., 2]

@@ -94,6 +94,7 @@ def test_area_estimator_against_oracle(sg, gpu):
     (ob.CELL_AFFINE, ob.EST_AREA, 0.2, ob.GROW_NONE),
     (ob.CELL_LWW, ob.EST_AREA, -0.01, ob.GROW_PLAIN),
     (ob.CELL_GMAPPING, ob.EST_CONST, 0.0, ob.GROW_TILED),
+    (ob.CELL_CREDIBILIST, ob.EST_AREA, 0.3, ob.GROW_PLAIN),
 ])
 def test_append_scan_matches_oracle(sg, gpu, model, est_type, blur, grow):
     rng = np.random.default_rng(2100 + model)
@@ -146,7 +147,7 @@ def test_append_scan_bounded_map_drops_outside_updates(sg, gpu):
 
 
 @pytest.mark.parametrize("model", [ob.CELL_LWW, ob.CELL_AFFINE, ob.CELL_MEAN, ob.CELL_TBM_CONSISTENT, ob.CELL_TBM_UNKNOWN_EVEN,
-                                   ob.CELL_GMAPPING])
+                                   ob.CELL_GMAPPING, ob.CELL_CREDIBILIST])
 def test_single_cell_update_reset_read(sg, gpu, model):
     rng = np.random.default_rng(2300 + model)
     for grow in (ob.GROW_PLAIN, ob.GROW_TILED):
@@ -240,7 +241,7 @@ def test_library_division_is_correctly_rounded(sg, gpu):
     assert (np.abs(want[:n]) < 2.3e-308).sum() > 100000  # the subnormal results really were exercised
 
 
-@pytest.mark.parametrize("model", [ob.CELL_TBM_CONSISTENT, ob.CELL_TBM_UNKNOWN_EVEN])
+@pytest.mark.parametrize("model", [ob.CELL_TBM_CONSISTENT, ob.CELL_TBM_UNKNOWN_EVEN, ob.CELL_CREDIBILIST])
 @pytest.mark.parametrize("est_type", [ob.EST_CONST, ob.EST_AREA])
 def test_tbm_cells_through_the_subnormal_regime(sg, gpu, model, est_type):
     """a robot that stands still: the cells around it take thousands of "empty" observations, their occupied / unknown

@@ -40,7 +40,7 @@ def _argbest(scores, init):
 
 
 @pytest.mark.parametrize("model,oie", [(ob.CELL_LWW, 0), (ob.CELL_MEAN, 0), (ob.CELL_TBM_CONSISTENT, 0),
-                                       (ob.CELL_TBM_UNKNOWN_EVEN, 1), (ob.CELL_AFFINE, 1)])
+                                       (ob.CELL_TBM_UNKNOWN_EVEN, 1), (ob.CELL_AFFINE, 1), (ob.CELL_CREDIBILIST, 0)])
 @pytest.mark.parametrize("trig", [0, 1])
 def test_list_obstacle_bit_exact(sg, gpu, model, oie, trig):
     rng = np.random.default_rng(1000 + model * 3 + trig)

@@ -12,7 +12,7 @@ from helpers import random_cells, room_map_cells, room_scan
 from oracle import binding as ob
 
 ALL_MODELS = [ob.CELL_LWW, ob.CELL_AFFINE, ob.CELL_MEAN, ob.CELL_TBM_CONSISTENT, ob.CELL_TBM_UNKNOWN_EVEN,
-              ob.CELL_GMAPPING]
+              ob.CELL_GMAPPING, ob.CELL_CREDIBILIST]
 
 
 def test_raycast_matches_reference(refso):
@@ -163,7 +163,7 @@ def _orc_scores(om, r, a, params, spw, f0, poses, occ=None, skip=0, max_range=-1
 
 
 @pytest.mark.parametrize("model,oie", [(ob.CELL_LWW, 0), (ob.CELL_MEAN, 0), (ob.CELL_TBM_CONSISTENT, 0),
-                                       (ob.CELL_TBM_UNKNOWN_EVEN, 1), (ob.CELL_AFFINE, 1)])
+                                       (ob.CELL_TBM_UNKNOWN_EVEN, 1), (ob.CELL_AFFINE, 1), (ob.CELL_CREDIBILIST, 0)])
 @pytest.mark.parametrize("spw", [ob.SPW_EVEN, ob.SPW_VINY, ob.SPW_AHR])
 def test_scores_obstacle_mode_match_reference(refso, model, oie, spw):
     rng = np.random.default_rng(100 + model * 7 + spw)
@@ -231,6 +231,7 @@ def test_gmapping_oope_with_cache_matches_reference(refso):
     (ob.CELL_AFFINE, ob.EST_AREA, 0.2, ob.GROW_NONE),
     (ob.CELL_LWW, ob.EST_AREA, -0.01, ob.GROW_PLAIN),
     (ob.CELL_GMAPPING, ob.EST_CONST, 0.0, ob.GROW_TILED),
+    (ob.CELL_CREDIBILIST, ob.EST_AREA, 0.3, ob.GROW_PLAIN),
 ])
 def test_append_scan_matches_reference(refso, model, est_type, blur, grow):
     rng = np.random.default_rng(300 + model)
@@ -378,12 +379,7 @@ def test_normal_distribution_restatement(refso):
         out2 = np.empty(501)
         refso.ref_normal_samples(seed, mean, sd, 501, ob.dptr(out2))
 
-        class MT(C.Structure):
-            _fields_ = [("mt", C.c_uint32 * 624), ("idx", C.c_int)]
-
-        class ND(C.Structure):
-            _fields_ = [("mean", C.c_double), ("stddev", C.c_double), ("saved", C.c_double), ("avail", C.c_int)]
-        g, d = MT(), ND(mean, sd, 0.0, 0)
+        g, d = ob.Mt19937(), ob.Normal(mean, sd, 0.0, 0)
         ob.orc.orc_mt_seed(C.byref(g), seed)
         ob.orc.orc_normal_sample.restype = C.c_double
         out1 = np.array([ob.orc.orc_normal_sample(C.byref(d), C.byref(g)) for _ in range(501)])
