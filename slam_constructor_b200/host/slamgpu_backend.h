@@ -56,19 +56,36 @@ public:
   int code;
 };
 
+// How the plug-ins report a failure.  The reference is exception-free by convention: a broken contract is an assert
+// (abort), a bad configuration prints to std::cerr and calls std::exit(-1) (init_scan_matching.h:212-215), "unknown" is a
+// NaN.  The default mode follows it, so nothing is ever thrown through the reference's world classes (or a ROS node built
+// on them); a host that prefers exceptions -- the test binaries do -- opts in with error_mode() = ErrorMode::Throw.
+enum class ErrorMode { Fatal, Throw };
+inline ErrorMode &error_mode() { static ErrorMode m = ErrorMode::Fatal; return m; }
+[[noreturn]] inline void fail(int code, const std::string &msg) {  // a C-ABI call returned an error (device lost, out of memory, ...)
+  if (error_mode() == ErrorMode::Throw) throw Error(code, msg);
+  std::cerr << "[slamgpu] error " << code << ": " << msg << std::endl;
+  std::exit(-1);
+}
+[[noreturn]] inline void contract_violation(const char *msg) {  // the plug-in is used against its contract (upstream: assert)
+  if (error_mode() == ErrorMode::Throw) throw std::logic_error(msg);
+  std::cerr << "[slamgpu] contract violation: " << msg << std::endl;
+  std::abort();
+}
+
 // one CUDA context (stream, scratch) per world; shared by the map, the adder and the matcher
 class Context {
 public:
   explicit Context(int device = 0) {
     int r = slamgpu_ctx_create(device, &_h);
-    if (r != SLAMGPU_OK) throw Error(r, slamgpu_last_error(nullptr));
+    if (r != SLAMGPU_OK) fail(r, slamgpu_last_error(nullptr));
   }
   ~Context() { slamgpu_ctx_destroy(_h); }
   Context(const Context &) = delete;
   Context &operator=(const Context &) = delete;
   slamgpu_ctx *handle() const { return _h; }
   void check(int r) const {
-    if (r != SLAMGPU_OK) throw Error(r, slamgpu_last_error(_h));
+    if (r != SLAMGPU_OK) fail(r, slamgpu_last_error(_h));
   }
 private:
   slamgpu_ctx *_h = nullptr;
@@ -98,7 +115,7 @@ public:
   }
   std::unique_ptr<GridCell> clone() const override { return std::make_unique<MirrorCell>(*this); }
   void operator+=(const AreaOccupancyObservation &) override {
-    throw std::logic_error("MirrorCell is read-only: update the CudaGridMap, not the cell");
+    contract_violation("MirrorCell is read-only: update the CudaGridMap, not the cell");
   }
   double discrepancy(const AreaOccupancyObservation &aoo) const override {
     switch (_model) {
@@ -180,7 +197,7 @@ public:
     refresh_info();
   }
   void rebind(slamgpu_map *m) {
-    if (_owned) { throw std::logic_error("CudaGridMap::rebind: this map owns its device map"); }
+    if (_owned) { contract_violation("CudaGridMap::rebind: this map owns its device map"); }
     flush();
     _map = m;
     touched();
@@ -294,7 +311,7 @@ private:
     }
     // MeanProbabilityCell / GmappingBaseCell keep their counters private: a written cell of those
     // classes cannot be moved onto the device through the public API
-    throw std::logic_error("CudaGridMap::reset: cannot take over a known cell of this class");
+    contract_violation("CudaGridMap::reset: cannot take over a known cell of this class");
   }
 
 private:
@@ -344,7 +361,7 @@ public:
 protected:
   void handle_scan_point(GridMap &map, bool is_occ, double scan_quality, const Segment2D &beam) const override {
     auto *cm = dynamic_cast<CudaGridMap *>(&map);
-    if (!cm) { throw std::logic_error("CudaScanAdder updates a CudaGridMap only (there is no CPU fallback)"); }
+    if (!cm) { contract_violation("CudaScanAdder updates a CudaGridMap only (there is no CPU fallback)"); }
     if (_params.est.type == SLAMGPU_EST_AREA && _params.est.shift_amount < 0) {
       // AreaOccupancyEstimator::ensure_segment_not_on_edge keeps a function-static shift computed from
       // the first cell it ever sees (area_occupancy_estimator.h:71): the obstacle cell of the first beam
@@ -390,7 +407,7 @@ inline ScoreSetup detect_score_setup(const ScanProbabilityEstimator &spe) {
   else if (dynamic_cast<const MeanOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_MEAN;
   else if (dynamic_cast<const OverlapWeightedOccupancyObservationPE *>(oope.get())) s.oope = SLAMGPU_OOPE_OVERLAP;
   else if (dynamic_cast<const GmappingOccupancyObservationPE *>(oope.get())) { s.oope = SLAMGPU_OOPE_GMAPPING; s.gm_cache = 2; }
-  else throw std::logic_error("slamgpu: unknown OccupancyObservationProbabilityEstimator class");
+  else contract_violation("slamgpu: unknown OccupancyObservationProbabilityEstimator class");
   auto oie = oope->impact_estimator();
   if (dynamic_cast<const DiscrepancyOIE *>(oie.get())) s.oie = SLAMGPU_OIE_DISCREPANCY;
   else if (dynamic_cast<const OccupancyOIE *>(oie.get())) s.oie = SLAMGPU_OIE_OCCUPANCY;
@@ -406,10 +423,10 @@ public:
   ~MapBinding() { if (_snapshot) slamgpu_map_destroy(_snapshot); }
   slamgpu_map *bind(const GridMap &map, const ScanProbabilityEstimator &spe, const ScoreSetup &setup) {
     if (auto cm = dynamic_cast<const CudaGridMap *>(&map)) {
-      if (setup.generic_oie) throw std::logic_error("slamgpu: a custom ObservationImpactEstimator needs a host map");
+      if (setup.generic_oie) contract_violation("slamgpu: a custom ObservationImpactEstimator needs a host map");
       return cm->device();
     }
-    if (setup.oope == SLAMGPU_OOPE_GMAPPING) throw std::logic_error("slamgpu: the GMapping OOPE gathers cell records: use a CudaGridMap");
+    if (setup.oope == SLAMGPU_OOPE_GMAPPING) contract_violation("slamgpu: the GMapping OOPE gathers cell records: use a CudaGridMap");
     const int w = map.width(), h = map.height();
     const auto org = map.origin();
     if (!_snapshot) {
@@ -588,7 +605,7 @@ public:
         const RobotPose arg = best_pose;
         auto sampled_pose = _pe.next(arg);
         if (sampled_pose.x != batch[k].x || sampled_pose.y != batch[k].y || sampled_pose.theta != batch[k].theta) {
-          throw std::logic_error("slamgpu: the pose enumerator is not reproducible from a copy taken after reset()");
+          contract_violation("slamgpu: the pose enumerator is not reproducible from a copy taken after reset()");
         }
         double sampled_scan_prob = probs[k];
         do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(sampled_pose, scan, sampled_scan_prob); });
@@ -673,7 +690,7 @@ public:
         if (ok) { best = RobotPose{l[0], l[1], l[2]}; best_prob = l[3]; }
       }
       if (best.x != out[0] || best.y != out[1] || best.theta != out[2] || !(best_prob == out[3] || (best_prob != best_prob && out[3] != out[3]))) {
-        throw std::logic_error("slamgpu: the Monte-Carlo log does not reproduce the device's result");
+        contract_violation("slamgpu: the Monte-Carlo log does not reproduce the device's result");
       }
       failed = (unsigned)out[5]; poses = (unsigned)out[6];
       if ((int32_t)out[4] == 0 && out[7] == 0) { break; }  // nothing consumed and no reset: the budget is spent
@@ -687,16 +704,16 @@ public:
     });
     _pe.reset();
     for (const Step &st : steps) {
-      if (!_pe.has_next()) { throw std::logic_error("slamgpu: the Monte-Carlo replay ran past the enumerator's budget"); }
+      if (!_pe.has_next()) { contract_violation("slamgpu: the Monte-Carlo replay ran past the enumerator's budget"); }
       const RobotPose sampled = _pe.next(st.arg);
       if (sampled.x != st.pose.x || sampled.y != st.pose.y || sampled.theta != st.pose.theta) {
-        throw std::logic_error("slamgpu: the pose enumerator is not reproducible from a copy taken after reset()");
+        contract_violation("slamgpu: the pose enumerator is not reproducible from a copy taken after reset()");
       }
       do_for_each_observer([&](ObsPtr obs) { obs->on_scan_test(sampled, scan, st.prob); });
       _pe.feedback(st.accepted);
       if (st.accepted) { do_for_each_observer([&](ObsPtr obs) { obs->on_pose_update(sampled, scan, st.prob); }); }
     }
-    if (_pe.has_next()) { throw std::logic_error("slamgpu: the Monte-Carlo replay stopped before the enumerator's budget was spent"); }
+    if (_pe.has_next()) { contract_violation("slamgpu: the Monte-Carlo replay stopped before the enumerator's budget was spent"); }
     pose_delta = best - init_pose;
     do_for_each_observer([&](ObsPtr obs) { obs->on_matching_end(pose_delta, scan, best_prob); });
     return best_prob;
@@ -867,17 +884,17 @@ public:
     : CudaGridMap{ctx, prototype, params, grow} {
     int oie_id = SLAMGPU_OIE_DISCREPANCY;
     if (dynamic_cast<const OccupancyOIE *>(oie.get())) oie_id = SLAMGPU_OIE_OCCUPANCY;
-    else if (!dynamic_cast<const DiscrepancyOIE *>(oie.get())) throw std::logic_error("CudaPyramidGridMap: unknown OIE class");
+    else if (!dynamic_cast<const DiscrepancyOIE *>(oie.get())) contract_violation("CudaPyramidGridMap: unknown OIE class");
     context()->check(slamgpu_pyramid_create(context()->handle(), raw_device_map(), oie_id, &_pyr));
   }
   ~CudaPyramidGridMap() override { slamgpu_pyramid_destroy(_pyr); }
   slamgpu_pyramid *pyramid() const { flush(); return _pyr; }
   int levels() const { flush(); return slamgpu_pyramid_levels(_pyr); }
   void update(const Coord &, const AreaOccupancyObservation &) override {
-    throw std::logic_error("CudaPyramidGridMap: cells are updated through a scan adder (whole scans)");
+    contract_violation("CudaPyramidGridMap: cells are updated through a scan adder (whole scans)");
   }
   void reset(const Coord &, const GridCell &) override {
-    throw std::logic_error("CudaPyramidGridMap: cells are updated through a scan adder (whole scans)");
+    contract_violation("CudaPyramidGridMap: cells are updated through a scan adder (whole scans)");
   }
 protected:
   int64_t append_beams_on_device(int32_t n, const double *beams, const uint8_t *occ, const double *quality,
@@ -905,9 +922,9 @@ public:
                       RobotPoseDelta &result_pose_delta) override {
     do_for_each_observer([&](ObsPtr obs) { obs->on_matching_start(pose, raw_scan, map); });
     auto pm = dynamic_cast<const CudaPyramidGridMap *>(&map);
-    if (!pm) { throw std::logic_error("CudaBfMultiResScanMatcher needs a CudaPyramidGridMap"); }
+    if (!pm) { contract_violation("CudaBfMultiResScanMatcher needs a CudaPyramidGridMap"); }
     auto setup = detect_score_setup(*scan_probability_estimator());
-    if (setup.oope != SLAMGPU_OOPE_MAX || setup.generic_oie) { throw std::logic_error("CudaBfMultiResScanMatcher: max OOPE expected"); }
+    if (setup.oope != SLAMGPU_OOPE_MAX || setup.generic_oie) { contract_violation("CudaBfMultiResScanMatcher: max OOPE expected"); }
     auto fscan = filter_scan(raw_scan.scan, pose, map);
     const auto &pts = fscan.points();
     std::vector<double> r(pts.size()), a(pts.size()), w(pts.size());

@@ -37,7 +37,9 @@ public:
     GridMapParams map_params = MapValues::gmp;
     std::shared_ptr<ScanProbabilityEstimator> spe;   // WeightedMeanPointProbabilitySPE over GmappingOccupancyObservationPE
     std::shared_ptr<ScanPointWeighting> spw;          // the SPE's own weighting object
-    ScoreSetup setup;                                 // oope = SLAMGPU_OOPE_GMAPPING + its two parameters
+    // the GMapping OOPE with its cache carried from candidate to candidate as the estimator object does (the setup
+    // detect_score_setup() gives that estimator); any other OOPE is refused by the constructor
+    ScoreSetup setup = [] { ScoreSetup s; s.oope = SLAMGPU_OOPE_GMAPPING; s.gm_cache = 2; return s; }();
     CudaScanAdder::Properties adder;
     unsigned max_failed_rounds = 6;                   // HillClimbingScanMatcher(spe, 6, 0.1, 0.1), init_gmapping.h:58-60
     double translation_delta = 0.1, rotation_delta = 0.1;
@@ -55,7 +57,8 @@ public:
 
   CudaGmappingParticleFilter(std::shared_ptr<Context> ctx, const Properties &props, const GMappingParams &gparams)
     : _ctx{ctx}, _props{props}, _scan_binding{ctx}, _raw_binding{ctx} {
-    if (!props.spe || !props.spw || props.particles == 0) { throw std::logic_error("CudaGmappingParticleFilter: incomplete properties"); }
+    if (!props.spe || !props.spw || props.particles == 0) { contract_violation("CudaGmappingParticleFilter: incomplete properties"); }
+    if (props.setup.oope != SLAMGPU_OOPE_GMAPPING) { contract_violation("CudaGmappingParticleFilter: the GMapping OOPE is the only one this filter scores with"); }
     const auto &mp = props.map_params;
     _ctx->check(slamgpu_particles_create(_ctx->handle(), (int32_t)props.particles, mp.width_cells, mp.height_cells, mp.meters_per_cell,
                                          SLAMGPU_CELL_GMAPPING, SLAMGPU_GROW_TILED, nullptr, &_parts));
@@ -167,6 +170,7 @@ protected:
         // scan_adder()->append_scan(map(), pose(), scan.scan, scan.quality, 0): the RAW scan, per-point mapping quality
         // from the adder's OMQE (grid_map_scan_adders.h:54-75)
         const auto &pts = obs.scan.points();
+        _even.reset(obs.scan);  // EvenSPW::_common_weight is set by reset() only (weighted_mean_point_probability_spe.h:21-32)
         slamgpu_scan *raw = _raw_binding.upload(obs.scan, _even);
         std::vector<double> pq(pts.size());
         _props.adder.observation_quality_estimator->reset(obs.scan);

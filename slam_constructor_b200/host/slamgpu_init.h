@@ -7,6 +7,7 @@
 
 #include "slamgpu_backend.h"
 #include "slamgpu_gmapping.h"
+#include "slamgpu_factory_hooks.h"
 #include "src/core/states/single_state_hypothesis_laser_scan_grid_world.h"
 #include "src/utils/init_occupancy_mapping.h"
 #include "src/utils/init_scan_matching.h"
@@ -80,8 +81,9 @@ inline std::shared_ptr<GridScanMatcher> init_cuda_scan_matcher(const PropertiesP
 }
 
 // init_grid_map (init_occupancy_mapping.h:126-146)
-inline std::shared_ptr<GridMap> init_cuda_grid_map(const PropertiesProvider &props, std::shared_ptr<Context> ctx) {
-  auto area_model = init_occupied_area_model(props);
+inline std::shared_ptr<GridMap> init_cuda_grid_map(const PropertiesProvider &props, std::shared_ptr<Context> ctx,
+                                                   std::shared_ptr<GridCell> area_model = nullptr) {
+  if (!area_model) area_model = init_occupied_area_model(props);
   auto map_params = init_grid_map_params(props);
   auto map_type = props.get_str("slam/mapping/grid/type", "<undefined>");
   int grow;
@@ -112,6 +114,17 @@ inline CudaScanAdder::Properties init_cuda_scan_adder_properties(const Propertie
 }
 inline std::shared_ptr<GridMapScanAdder> init_cuda_scan_adder(const PropertiesProvider &props) {
   return std::make_shared<CudaScanAdder>(init_cuda_scan_adder_properties(props));
+}
+
+// `slam/backend=cuda` inside the reference's OWN factories: with integration/slam_backend_key.patch applied to
+// src/utils/init_scan_matching.h / init_occupancy_mapping.h, init_scan_matcher / init_grid_map / init_scan_adder (and so
+// init_1h_slam, init_gmapping, ...) hand the preset to these hooks when it carries that key -- no code change in the
+// application beyond this one call.  (slamgpu_factory_hooks.h is what the patched headers include.)
+inline void install_backend(std::shared_ptr<Context> ctx) {
+  auto &h = slamgpu_hooks::hooks();
+  h.scan_matcher = [ctx](const PropertiesProvider &props) { return init_cuda_scan_matcher(props, ctx); };
+  h.grid_map = [ctx](const PropertiesProvider &props, std::shared_ptr<GridCell> area_model) { return init_cuda_grid_map(props, ctx, area_model); };
+  h.scan_adder = [](const PropertiesProvider &props) { return init_cuda_scan_adder(props); };
 }
 
 // init_1h_slam (init_slam.h:12-24): the tinySLAM / vinySLAM world on the CUDA back end

@@ -607,6 +607,7 @@ void run_gmapping_batched(std::shared_ptr<slamgpu::Context> ctx) {
 }  // namespace
 
 int main() {
+  slamgpu::error_mode() = slamgpu::ErrorMode::Throw;  // this binary reports failures itself
   std::shared_ptr<slamgpu::Context> ctx;
   try {
     ctx = std::make_shared<slamgpu::Context>(0);

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(sg):
 def test_abi_version_and_strides(sg):
     L = sg.lib()
     assert L.slamgpu_abi_version() == 1
-    assert [L.slamgpu_model_stride(m) for m in range(6)] == [3, 2, 2, 6, 6, 5]
+    assert [L.slamgpu_model_stride(m) for m in range(7)] == [3, 2, 2, 6, 6, 5, 6]
     assert L.slamgpu_model_stride(99) == 0
 
 
