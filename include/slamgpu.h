@@ -354,6 +354,14 @@ int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, int32_t h, 
                              const double *unknown_rec, slamgpu_particles **out);
 void slamgpu_particles_destroy(slamgpu_particles *p);
 int slamgpu_particles_count(const slamgpu_particles *p);
+/* Storage of the particle maps.  With SLAMGPU_GROW_TILED (UnboundedLazyTiledGridMap upstream) the maps share copy-on-write
+ * 128 x 128 tiles out of one pool (LazyTiledGridMap, src/core/maps/lazy_tiled_grid_map.h:18-118: shared_ptr tiles cloned on
+ * first write :57-71): a new map is a table of references to one all-unknown tile, scan insertion first makes the tiles
+ * under the scan private, resampling copies tables.  stats: [0] 1 if tiled, [1] tiles in use, [2] tiles cloned so far,
+ * [3] bytes per tile, [4] bytes of device memory held by the pool; of the last resampling: [5] bytes copied or received,
+ * [6] tile references handed to copies instead, [7] device time in microseconds.  (SLAMGPU_DENSE_PARTICLES=1 in the
+ * environment keeps round 1's dense per-particle arrays, for comparison.) */
+int slamgpu_particles_tile_stats(const slamgpu_particles *p, int64_t stats[8]);
 /* borrowed handle of particle i's map: valid for every slamgpu_map_* call until the next resample */
 slamgpu_map *slamgpu_particles_map(slamgpu_particles *p, int32_t i);
 /* scores[i*c + k] = scan probability of poses[i*c + k] on particle i's map; one launch for all particles */

@@ -96,7 +96,7 @@ SYMBOLS = [
     "slamgpu_append_scan", "slamgpu_append_beams", "slamgpu_pyramid_create", "slamgpu_pyramid_destroy", "slamgpu_pyramid_levels",
     "slamgpu_pyramid_level_info", "slamgpu_pyramid_build", "slamgpu_pyramid_level_download", "slamgpu_pyramid_rescale",
     "slamgpu_pyramid_append_scan", "slamgpu_pyramid_append_beams", "slamgpu_score_windows", "slamgpu_match_m3rsm", "slamgpu_particles_create", "slamgpu_particles_destroy",
-    "slamgpu_particles_count", "slamgpu_particles_map", "slamgpu_particles_score", "slamgpu_particles_match_hc",
+    "slamgpu_particles_count", "slamgpu_particles_tile_stats", "slamgpu_particles_map", "slamgpu_particles_score", "slamgpu_particles_match_hc",
     "slamgpu_particles_append_scan", "slamgpu_particles_resample",
 ]
 
@@ -184,6 +184,7 @@ def lib():
     L.slamgpu_particles_destroy.argtypes = [vp]
     L.slamgpu_particles_destroy.restype = None
     L.slamgpu_particles_count.argtypes = [vp]
+    L.slamgpu_particles_tile_stats.argtypes = [vp, c_lp]
     L.slamgpu_particles_map.argtypes = [vp, i32]
     L.slamgpu_particles_map.restype = vp
     L.slamgpu_particles_score.argtypes = [vp, vp, sp, c_dp, i32, c_dp]
@@ -598,6 +599,12 @@ class Particles:
 
     def map(self, i):
         return _BorrowedMap(self.ctx, self.ctx.L.slamgpu_particles_map(self.h, i), self.model)
+
+    def tile_stats(self):
+        st = np.zeros(8, dtype=np.int64)
+        self.ctx.check(self.ctx.L.slamgpu_particles_tile_stats(self.h, st.ctypes.data_as(c_lp)))
+        keys = ("tiled", "tiles_live", "tiles_cloned", "tile_bytes", "pool_bytes", "resample_bytes", "resample_tiles_shared", "resample_us")
+        return dict(zip(keys, (int(v) for v in st)))
 
     def score(self, scan, params, poses):
         poses = _f64(poses).reshape(self.n, -1, 3)

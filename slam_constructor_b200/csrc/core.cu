@@ -391,8 +391,10 @@ __global__ void k_fill_cells(double *cells, size_t n_cells, int stride, RecParam
   for (; i < n; i += st) cells[i] = rec.v[i % stride];
 }
 
+static int map_reset_tiles(slamgpu_map *m, int32_t w, int32_t h);
 int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h) {
   slamgpu_ctx *ctx = m->ctx;
+  if (m->pool) return map_reset_tiles(m, w, h);
   size_t need = (size_t)w * h * m->stride;
   if (need > m->cells_cap) {
     if (m->d_cells) cudaFree(m->d_cells);
@@ -407,6 +409,206 @@ int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h) {
 }
 
 void sg_map_invalidate_lut(slamgpu_map *m) { m->lut_valid[0] = m->lut_valid[1] = false; }
+
+
+// ------------------------------------------------------------------ copy-on-write tiles (see internal.h: SgTilePool)
+struct TileCopy { const double *src; double *dst; };
+__global__ void k_copy_tiles(const TileCopy *__restrict__ jobs, size_t tile_doubles) {
+  const TileCopy j = jobs[blockIdx.y];
+  const double2 *s = reinterpret_cast<const double2 *>(j.src);
+  double2 *d = reinterpret_cast<double2 *>(j.dst);
+  const size_t n2 = tile_doubles / 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+// dense [h][w][stride] <-> tiles
+__global__ void k_tiles_gather(double *const *__restrict__ tiles, int tw, int w, int h, int stride, double *__restrict__ dense) {
+  const size_t n = (size_t)w * h * stride;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t cell = i / stride;
+    const int k = (int)(i - cell * stride), y = (int)(cell / w), x = (int)(cell - (size_t)y * w);
+    const double *t = tiles[(y >> SG_TILE_BITS) * tw + (x >> SG_TILE_BITS)];
+    dense[i] = t[((size_t)(y & (SG_TILE - 1)) * SG_TILE + (x & (SG_TILE - 1))) * stride + k];
+  }
+}
+__global__ void k_tiles_scatter(double *const *__restrict__ tiles, int tw, int w, int h, int stride, const double *__restrict__ dense) {
+  const size_t n = (size_t)w * h * stride;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t cell = i / stride;
+    const int k = (int)(i - cell * stride), y = (int)(cell / w), x = (int)(cell - (size_t)y * w);
+    double *t = tiles[(y >> SG_TILE_BITS) * tw + (x >> SG_TILE_BITS)];
+    t[((size_t)(y & (SG_TILE - 1)) * SG_TILE + (x & (SG_TILE - 1))) * stride + k] = dense[i];
+  }
+}
+
+static int pool_alloc(SgTilePool *pool, int32_t *id) {
+  slamgpu_ctx *ctx = pool->ctx;
+  if (pool->free_ids.empty()) {
+    double *chunk = nullptr;
+    SG_CUDA(ctx, cudaMalloc(&chunk, pool->tile_doubles * sizeof(double) * pool->tiles_per_chunk));
+    const int32_t base = (int32_t)pool->chunks.size() * pool->tiles_per_chunk;
+    pool->chunks.push_back(chunk);
+    pool->refcnt.resize((size_t)base + pool->tiles_per_chunk, 0);
+    for (int k = pool->tiles_per_chunk - 1; k >= 0; --k) pool->free_ids.push_back(base + k);
+  }
+  *id = pool->free_ids.back();
+  pool->free_ids.pop_back();
+  pool->refcnt[*id] = 1;
+  ++pool->tiles_live;
+  return SLAMGPU_OK;
+}
+static void pool_decref(SgTilePool *pool, int32_t id) {
+  if (id == 0) return;  // the shared unknown tile lives as long as the pool
+  if (--pool->refcnt[id] == 0) { pool->free_ids.push_back(id); --pool->tiles_live; }
+}
+
+int sg_pool_create(slamgpu_ctx *ctx, int model, const double *unknown_rec, SgTilePool **out) {
+  SgTilePool *pool = new SgTilePool();
+  pool->ctx = ctx; pool->stride = sg::model_stride(model);
+  pool->tile_doubles = (size_t)SG_TILE * SG_TILE * pool->stride;
+  int32_t id0 = -1;
+  int r = pool_alloc(pool, &id0);  // tile 0: every cell unknown
+  if (r != SLAMGPU_OK) { sg_pool_destroy(pool); return r; }
+  RecParam rp;
+  memset(rp.v, 0, sizeof rp.v);
+  if (unknown_rec) memcpy(rp.v, unknown_rec, sizeof(double) * pool->stride);
+  else slamgpu_default_unknown(model, rp.v);
+  k_fill_cells<<<ctx->sm_count, 256, 0, ctx->stream>>>(pool->ptr(0), (size_t)SG_TILE * SG_TILE, pool->stride, rp);
+  SG_LAUNCHED(ctx);
+  pool->refcnt[0] = 1 << 30;
+  *out = pool;
+  return SLAMGPU_OK;
+}
+void sg_pool_destroy(SgTilePool *pool) {
+  if (!pool) return;
+  cudaStreamSynchronize(pool->ctx->stream);
+  for (double *c : pool->chunks) cudaFree(c);
+  pool->jobs.release();
+  delete pool;
+}
+
+static void map_set_tile(slamgpu_map *m, size_t slot, int32_t id) {
+  m->tile_ids[slot] = id;
+  m->h_tile_ptrs[slot] = m->pool->ptr(id);
+  m->tiles_dirty = true;
+}
+// new geometry, every tile unknown (the old tiles are released)
+static int map_reset_tiles(slamgpu_map *m, int32_t w, int32_t h) {
+  for (int32_t id : m->tile_ids) pool_decref(m->pool, id);
+  m->w = w; m->h = h;
+  m->tw = (w + SG_TILE - 1) >> SG_TILE_BITS; m->th = (h + SG_TILE - 1) >> SG_TILE_BITS;
+  m->tile_ids.assign((size_t)m->tw * m->th, 0);
+  m->h_tile_ptrs.assign((size_t)m->tw * m->th, m->pool->ptr(0));
+  m->tiles_dirty = true;
+  m->pitch = (w + 2 * SG_LUT_PAD + 1) & ~1;
+  sg_map_invalidate_lut(m);
+  return SLAMGPU_OK;
+}
+int sg_map_sync_tiles(slamgpu_map *m) {
+  if (!m->pool || !m->tiles_dirty) return SLAMGPU_OK;
+  slamgpu_ctx *ctx = m->ctx;
+  const size_t n = m->h_tile_ptrs.size();
+  if (n > m->d_tile_cap) {
+    if (m->d_tile_ptrs) { SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(m->d_tile_ptrs); }
+    m->d_tile_ptrs = nullptr; m->d_tile_cap = 0;
+    SG_CUDA(ctx, cudaMalloc(&m->d_tile_ptrs, std::max<size_t>(n, 1) * sizeof(double *)));
+    m->d_tile_cap = n;
+  }
+  if (n) SG_CUDA(ctx, cudaMemcpyAsync(m->d_tile_ptrs, m->h_tile_ptrs.data(), n * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+  m->tiles_dirty = false;
+  return SLAMGPU_OK;
+}
+int sg_map_make_writable(slamgpu_map *m, int x0, int y0, int x1, int y1, std::vector<int32_t> *copies) {
+  if (!m->pool || m->w <= 0 || m->h <= 0) return SLAMGPU_OK;
+  x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, m->w - 1); y1 = std::min(y1, m->h - 1);
+  for (int ty = y0 >> SG_TILE_BITS; ty <= (y1 >> SG_TILE_BITS); ++ty)
+    for (int tx = x0 >> SG_TILE_BITS; tx <= (x1 >> SG_TILE_BITS); ++tx) {
+      const size_t slot = (size_t)ty * m->tw + tx;
+      const int32_t id = m->tile_ids[slot];
+      if (id != 0 && m->pool->refcnt[id] == 1) continue;  // already private
+      int32_t nid;
+      SG_TRY(pool_alloc(m->pool, &nid));
+      copies->push_back(id); copies->push_back(nid);
+      pool_decref(m->pool, id);
+      map_set_tile(m, slot, nid);
+      ++m->pool->tiles_cloned;
+    }
+  return SLAMGPU_OK;
+}
+int sg_pool_run_copies(SgTilePool *pool, const std::vector<int32_t> &copies) {
+  if (copies.empty()) return SLAMGPU_OK;
+  slamgpu_ctx *ctx = pool->ctx;
+  const size_t n = copies.size() / 2;
+  std::vector<TileCopy> jobs(n);
+  for (size_t k = 0; k < n; ++k) jobs[k] = TileCopy{pool->ptr(copies[2 * k]), pool->ptr(copies[2 * k + 1])};
+  // (a source tile freed by the same batch keeps its content until something writes to the id again, which only happens
+  // after these copies on the stream)
+  DevBuf &buf = pool->jobs;
+  if (buf.reserve(n * sizeof(TileCopy)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "tile copy list");
+  SG_CUDA(ctx, cudaMemcpyAsync(buf.p, jobs.data(), n * sizeof(TileCopy), cudaMemcpyHostToDevice, ctx->stream));
+  for (size_t k0 = 0; k0 < n; k0 += 65535) {
+    const unsigned cnt = (unsigned)std::min<size_t>(65535, n - k0);
+    k_copy_tiles<<<dim3(8, cnt), 256, 0, ctx->stream>>>(buf.as<TileCopy>() + k0, pool->tile_doubles);
+    SG_LAUNCHED(ctx);
+  }
+  SG_CUDA(ctx, cudaGetLastError());
+  return SLAMGPU_OK;
+}
+int sg_map_share_tiles(slamgpu_map *to, const slamgpu_map *from) {
+  if (!to->pool || to->pool != from->pool) return sg_fail(to->ctx, SLAMGPU_E_STATE, "tile sharing needs two maps of one pool");
+  for (int32_t id : from->tile_ids)
+    if (id != 0) ++to->pool->refcnt[id];
+  for (int32_t id : to->tile_ids) pool_decref(to->pool, id);
+  to->w = from->w; to->h = from->h; to->ox = from->ox; to->oy = from->oy; to->tw = from->tw; to->th = from->th;
+  to->tile_ids = from->tile_ids; to->h_tile_ptrs = from->h_tile_ptrs; to->tiles_dirty = true;
+  to->pitch = from->pitch;
+  sg_map_invalidate_lut(to);
+  return SLAMGPU_OK;
+}
+int sg_map_gather_dense(slamgpu_map *m, double *d_dst) {
+  slamgpu_ctx *ctx = m->ctx;
+  SG_TRY(sg_map_sync_tiles(m));
+  if ((size_t)m->w * m->h == 0) return SLAMGPU_OK;
+  k_tiles_gather<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->d_tile_ptrs, m->tw, m->w, m->h, m->stride, d_dst);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  return SLAMGPU_OK;
+}
+int sg_map_scatter_dense(slamgpu_map *m, const double *d_src) {
+  slamgpu_ctx *ctx = m->ctx;
+  std::vector<int32_t> copies;
+  SG_TRY(sg_map_make_writable(m, 0, 0, m->w - 1, m->h - 1, &copies));  // (no need to run the copies: every cell is overwritten...
+  // ... except the cells of edge tiles past w / h, which nothing ever reads)
+  SG_TRY(sg_map_sync_tiles(m));
+  if ((size_t)m->w * m->h == 0) return SLAMGPU_OK;
+  k_tiles_scatter<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m->d_tile_ptrs, m->tw, m->w, m->h, m->stride, d_src);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  sg_map_invalidate_lut(m);
+  return SLAMGPU_OK;
+}
+int sg_map_create_tiled(slamgpu_ctx *ctx, SgTilePool *pool, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
+                        const double *unknown_rec, slamgpu_map **out) {
+  if (!ctx || !pool || !out || w < 0 || h < 0 || !(scale > 0)) return sg_fail(ctx, SLAMGPU_E_INVALID, "sg_map_create_tiled: bad arguments");
+  slamgpu_map *m = new slamgpu_map();
+  m->ctx = ctx; m->scale = scale; m->model = model; m->grow = grow; m->pool = pool;
+  m->stride = sg::model_stride(model);
+  m->ox = w / 2; m->oy = h / 2;
+  if (unknown_rec) memcpy(m->unknown, unknown_rec, sizeof(double) * m->stride);
+  else slamgpu_default_unknown(model, m->unknown);
+  map_reset_tiles(m, w, h);
+  *out = m;
+  return SLAMGPU_OK;
+}
+// dense staging of a tiled map for the slow paths (download, LUT build): scratch[5] holds [h][w][stride]
+static int map_dense_view(slamgpu_map *m, const double **cells) {
+  if (!m->pool) { *cells = m->d_cells; return SLAMGPU_OK; }
+  slamgpu_ctx *ctx = m->ctx;
+  const size_t bytes = std::max<size_t>((size_t)m->w * m->h * m->stride, 1) * sizeof(double);
+  if (ctx->scratch[5].reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "dense staging of a tiled map (%zu bytes)", bytes);
+  SG_TRY(sg_map_gather_dense(m, ctx->scratch[5].as<double>()));
+  *cells = ctx->scratch[5].as<double>();
+  return SLAMGPU_OK;
+}
 
 extern "C" int slamgpu_map_create(slamgpu_ctx *ctx, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
                                   const double *unknown_rec, slamgpu_map **out) {
@@ -441,6 +643,10 @@ extern "C" void slamgpu_map_destroy(slamgpu_map *m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   if (m->d_cells) cudaFree(m->d_cells);
+  if (m->pool) {
+    for (int32_t id : m->tile_ids) pool_decref(m->pool, id);
+    if (m->d_tile_ptrs) cudaFree(m->d_tile_ptrs);
+  }
   for (int i = 0; i < 2; ++i)
     if (m->d_lut[i]) cudaFree(m->d_lut[i]);
   delete m;
@@ -465,6 +671,13 @@ extern "C" int slamgpu_map_upload(slamgpu_map *m, const double *cells, int32_t w
   SG_TRY(sg_map_realloc(m, w, h));
   m->ox = ox; m->oy = oy;
   size_t bytes = (size_t)w * h * m->stride * sizeof(double);
+  if (m->pool) {
+    if (ctx->scratch[5].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "upload staging");
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[5].p, cells, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SG_TRY(sg_map_scatter_dense(m, ctx->scratch[5].as<double>()));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMGPU_OK;
+  }
   SG_CUDA(ctx, cudaMemcpyAsync(m->d_cells, cells, bytes, cudaMemcpyHostToDevice, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
@@ -474,7 +687,9 @@ extern "C" int slamgpu_map_download(slamgpu_map *m, double *cells) {
   if (!m || !cells) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = m->ctx;
   size_t bytes = (size_t)m->w * m->h * m->stride * sizeof(double);
-  SG_CUDA(ctx, cudaMemcpyAsync(cells, m->d_cells, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  const double *src = nullptr;
+  SG_TRY(map_dense_view(m, &src));
+  SG_CUDA(ctx, cudaMemcpyAsync(cells, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
 }
@@ -487,8 +702,10 @@ extern "C" int slamgpu_map_read_cell(slamgpu_map *m, int32_t x, int32_t y, doubl
     memcpy(rec, m->unknown, sizeof(double) * m->stride);
     return SLAMGPU_OK;
   }
-  SG_CUDA(ctx, cudaMemcpyAsync(rec, m->d_cells + ((size_t)iy * m->w + ix) * m->stride, sizeof(double) * m->stride,
-                               cudaMemcpyDeviceToHost, ctx->stream));
+  const double *cell = m->pool ? m->pool->ptr(m->tile_ids[(size_t)(iy >> SG_TILE_BITS) * m->tw + (ix >> SG_TILE_BITS)]) +
+                                   ((size_t)(iy & (SG_TILE - 1)) * SG_TILE + (ix & (SG_TILE - 1))) * m->stride
+                             : m->d_cells + ((size_t)iy * m->w + ix) * m->stride;
+  SG_CUDA(ctx, cudaMemcpyAsync(rec, cell, sizeof(double) * m->stride, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SLAMGPU_OK;
 }
@@ -540,7 +757,9 @@ int sg_map_ensure_lut(slamgpu_map *m, int oie) {
   SG_CUDA(ctx, cudaMemcpyAsync(&m->unknown_lut[oie], d_tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   dim3 blk(32, 8), grd((m->pitch + 31) / 32, (m->h + 2 * SG_LUT_PAD + 7) / 8);
-  k_build_lut<<<grd, blk, 0, ctx->stream>>>(m->d_cells, m->w, m->h, m->stride, m->model, oie, m->d_lut[oie], m->pitch,
+  const double *dense = nullptr;
+  SG_TRY(map_dense_view(m, &dense));
+  k_build_lut<<<grd, blk, 0, ctx->stream>>>(dense, m->w, m->h, m->stride, m->model, oie, m->d_lut[oie], m->pitch,
                                              m->unknown_lut[oie]);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());

@@ -10,7 +10,9 @@ namespace {
 
 struct MapView {
   const double *lut;    // padded score LUT (pitch doubles per row, ring of unknown)
-  const double *cells;  // dense records (GMapping OOPE gathers these)
+  const double *cells;  // dense records (GMapping OOPE gathers these); NULL for a tiled map
+  double *const *tiles; // copy-on-write particle maps: tile pointers [th][tw] (128 x 128 cells each)
+  int tw;
   int w, h, ox, oy, pitch, stride, model;
   double scale;
   double unknown_lut;
@@ -21,6 +23,14 @@ SG_DEV int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 SG_DEV int cell_of(double q_floor) {  // floor(q) -> int without overflow
   q_floor = q_floor < -1e9 ? -1e9 : (q_floor > 1e9 ? 1e9 : q_floor);
   return (int)q_floor;
+}
+
+SG_DEV const double *view_cell(const MapView &m, int ix, int iy) {  // record of an internal cell (inside the map)
+  if (m.tiles) {
+    const double *t = m.tiles[(iy >> 7) * m.tw + (ix >> 7)];
+    return t + ((size_t)(iy & 127) * 128 + (ix & 127)) * m.stride;
+  }
+  return m.cells + ((size_t)iy * m.w + ix) * m.stride;
 }
 
 SG_DEV double lut_at(const MapView &m, int cx, int cy) {  // external cell -> impact (unknown outside)

@@ -7,6 +7,14 @@
 
 #include "../../include/slamgpu.h"
 
+// NVTX ranges around the K1..K6 entry points (header-only nvtx3: a no-op until a tool such as nsys / ncu --nvtx attaches)
+#include <nvtx3/nvToolsExt.h>
+struct SgNvtxRange {
+  explicit SgNvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~SgNvtxRange() { nvtxRangePop(); }
+};
+#define SG_NVTX(name) SgNvtxRange sg_nvtx_range_(name)
+
 #define SG_LUT_PAD 1  // ring of "unknown" cells around the padded score LUT
 #define SG_LUT_SLACK 512  // doubles allocated past the LUT: a staged patch row may run past the last row
 #define SG_LUT_SLACK_ROWS 7  // whole rows allocated past the LUT (k_score_grid4 loads rows it does not use)
@@ -118,8 +126,36 @@ struct slamgpu_ctx {
   DevBuf scratch[8];  // generic scratch (append_scan etc.)
 };
 
+// Copy-on-write tiles for the per-particle maps of K6 (LazyTiledGridMap, src/core/maps/lazy_tiled_grid_map.h:18-118: 128 x 128
+// tiles behind shared_ptr, cloned on first write :57-71).  A pool hands out tiles of 128*128*stride doubles from device
+// chunks; maps of the pool hold a table of tile ids (host) and of tile pointers (device).  Tile 0 is the shared "all
+// unknown" tile every new map starts with; a tile referenced more than once (or tile 0) is cloned before a map writes to it,
+// so resampling a particle is a table copy.
+#define SG_TILE_BITS 7
+#define SG_TILE (1 << SG_TILE_BITS)
+struct SgTilePool {
+  slamgpu_ctx *ctx = nullptr;
+  int stride = 0;
+  size_t tile_doubles = 0;
+  int tiles_per_chunk = 64;
+  std::vector<double *> chunks;
+  std::vector<int32_t> refcnt;    // per tile id
+  std::vector<int32_t> free_ids;
+  int64_t tiles_cloned = 0, tiles_live = 0;  // statistics (slamgpu_particles_tile_stats)
+  DevBuf jobs;                    // device copy of a batch of clone jobs
+  double *ptr(int32_t id) const { return chunks[(size_t)id / tiles_per_chunk] + (size_t)(id % tiles_per_chunk) * tile_doubles; }
+};
+
 struct slamgpu_map {
   slamgpu_ctx *ctx = nullptr;
+  // tiled storage (pool != NULL): d_cells stays NULL, the cells live in pool tiles
+  SgTilePool *pool = nullptr;
+  int32_t tw = 0, th = 0;               // tiles per row / column = ceil(w / 128), ceil(h / 128)
+  std::vector<int32_t> tile_ids;        // [th][tw]
+  std::vector<double *> h_tile_ptrs;    // the same as device pointers (kept for the uploads)
+  double **d_tile_ptrs = nullptr;       // device copy of h_tile_ptrs
+  size_t d_tile_cap = 0;
+  bool tiles_dirty = false;             // h_tile_ptrs changed since the last upload
   int32_t w = 0, h = 0, ox = 0, oy = 0;
   double scale = 1;
   int32_t model = 0, stride = 0, grow = 0;
@@ -171,6 +207,19 @@ int sg_pinned(slamgpu_ctx *ctx, size_t bytes, void **out);
 int sg_map_ensure_lut(slamgpu_map *m, int oie);
 void sg_map_invalidate_lut(slamgpu_map *m);
 int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h);
+// tiled maps (core.cu)
+int sg_pool_create(slamgpu_ctx *ctx, int model, const double *unknown_rec, SgTilePool **out);
+void sg_pool_destroy(SgTilePool *pool);
+int sg_map_create_tiled(slamgpu_ctx *ctx, SgTilePool *pool, int32_t w, int32_t h, double scale, int32_t model, int32_t grow,
+                        const double *unknown_rec, slamgpu_map **out);
+int sg_map_sync_tiles(slamgpu_map *m);  // upload the tile pointer table if it changed
+// make the tiles covering internal cells [x0, x1] x [y0, y1] private to this map (clones are queued in `copies` as
+// {src id, dst id}; run them with sg_pool_run_copies before anything writes)
+int sg_map_make_writable(slamgpu_map *m, int x0, int y0, int x1, int y1, std::vector<int32_t> *copies);
+int sg_pool_run_copies(SgTilePool *pool, const std::vector<int32_t> &copies);
+int sg_map_share_tiles(slamgpu_map *to, const slamgpu_map *from);  // `to` becomes a copy-on-write copy of `from`
+int sg_map_gather_dense(slamgpu_map *m, double *d_dst);            // tiles -> dense [h][w][stride] on the device
+int sg_map_scatter_dense(slamgpu_map *m, const double *d_src);     // dense -> private tiles
 // K6 (score.cu): poses[k] is scored against maps[view_id[k]]; out_scores may be NULL
 int sg_score_poses_multi(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, const int32_t *view_id, slamgpu_scan *scan,
                          const slamgpu_spe_params *p, const double *poses, int64_t P, double *out_scores);

@@ -398,6 +398,23 @@ struct ApplyArgs {
 #define SG_LONG_RUN 24
 struct LongRun { long long head; int len; int pad; };
 
+// the record of internal cell (ix, iy) of one map of the batch: dense array or copy-on-write tile
+SG_DEV double *slot_cell_xy(const MapSlot &ms, int ix, int iy, int stride) {
+  if (ms.tiles) {
+    double *t = ms.tiles[(iy >> SG_TILE_BITS) * ms.tw + (ix >> SG_TILE_BITS)];
+    return t + ((size_t)(iy & (SG_TILE - 1)) * SG_TILE + (ix & (SG_TILE - 1))) * stride;
+  }
+  return ms.cells + ((size_t)iy * ms.w + ix) * stride;
+}
+SG_DEV double *slot_cell_key(const MapSlot &ms, unsigned key, int stride) {  // key = key_base + iy * w + ix
+  const unsigned local = key - ms.key_base;
+  if (ms.tiles) {
+    const int iy = (int)(local / (unsigned)ms.w), ix = (int)(local - (unsigned)iy * (unsigned)ms.w);
+    return slot_cell_xy(ms, ix, iy, stride);
+  }
+  return ms.cells + (size_t)local * stride;
+}
+
 __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (j >= a.M) return;
@@ -418,7 +435,7 @@ __global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
   double r[SLAMGPU_MAX_STRIDE];
   SortedAoo cur = a.aoo[j];
   const MapSlot &ms = a.maps[cur.map_id];
-  double *cell = ms.cells + (size_t)(key - ms.key_base) * a.stride;
+  double *cell = slot_cell_key(ms, key, a.stride);
   SG_COPY_REC(r, cell, a.stride);
   for (long long t = j;;) {
     const bool more = t + 1 < a.M && a.keys[t + 1] == key;
@@ -524,7 +541,7 @@ __global__ void __launch_bounds__(128) k_apply_long(ApplyArgs a) {
     const SortedAoo *src = a.aoo + run.head;
     SortedAoo mine = src[min(lane, run.len - 1)];
     const MapSlot &ms = a.maps[mine.map_id];
-    double *cell = ms.cells + (size_t)(key - ms.key_base) * a.stride;
+    double *cell = slot_cell_key(ms, key, a.stride);
     double r[SLAMGPU_MAX_STRIDE];
     SG_COPY_REC(r, cell, a.stride);
     FixedPoint fx{NAN, NAN, NAN, false};
@@ -590,7 +607,7 @@ __global__ void __launch_bounds__(128) k_apply_ring(RobotArgs a) {
   const int tx = ms.rx + (t % side) - a.ring, ty = ms.ry + (t / side) - a.ring;  // the cell of this warp
   const int ix = tx + ms.ox, iy = ty + ms.oy;
   if (ix < 0 || ix >= ms.w || iy < 0 || iy >= ms.h) return;
-  double *cell = ms.cells + ((size_t)iy * ms.w + ix) * a.stride;
+  double *cell = slot_cell_xy(ms, ix, iy, a.stride);
   double r[SLAMGPU_MAX_STRIDE];
   SG_COPY_REC(r, cell, a.stride);
   bool any = false, dirty = false;
@@ -714,6 +731,24 @@ int sg_map_regrow(slamgpu_map *m, const GrowState &g) {
   if (g.w == m->w && g.h == m->h && g.ox == m->ox && g.oy == m->oy) return SLAMGPU_OK;
   const int offx = g.ox - m->ox, offy = g.oy - m->oy;
   if (offx < 0 || offy < 0 || offx + m->w > g.w || offy + m->h > g.h) return sg_fail(ctx, SLAMGPU_E_STATE, "map growth would shrink the map");
+  if (m->pool) {
+    // UnboundedLazyTiledGridMap grows by whole tiles (lazy_tiled_grid_map.h:151-181): the tile table is re-laid, no cell moves
+    if ((offx | offy) & (SG_TILE - 1)) return sg_fail(ctx, SLAMGPU_E_STATE, "a tiled map grows by whole tiles");
+    const int ntw = (g.w + SG_TILE - 1) >> SG_TILE_BITS, nth = (g.h + SG_TILE - 1) >> SG_TILE_BITS;
+    std::vector<int32_t> ids((size_t)ntw * nth, 0);
+    std::vector<double *> ptrs((size_t)ntw * nth, m->pool->ptr(0));
+    const int tx0 = offx >> SG_TILE_BITS, ty0 = offy >> SG_TILE_BITS;
+    for (int ty = 0; ty < m->th; ++ty)
+      for (int tx = 0; tx < m->tw; ++tx) {
+        ids[(size_t)(ty + ty0) * ntw + tx + tx0] = m->tile_ids[(size_t)ty * m->tw + tx];
+        ptrs[(size_t)(ty + ty0) * ntw + tx + tx0] = m->h_tile_ptrs[(size_t)ty * m->tw + tx];
+      }
+    m->tile_ids.swap(ids); m->h_tile_ptrs.swap(ptrs); m->tw = ntw; m->th = nth; m->tiles_dirty = true;
+    m->w = g.w; m->h = g.h; m->ox = g.ox; m->oy = g.oy;
+    m->pitch = (m->w + 2 * SG_LUT_PAD + 1) & ~1;
+    sg_map_invalidate_lut(m);
+    return SLAMGPU_OK;
+  }
   size_t need = (size_t)g.w * g.h * m->stride;
   double *nc = nullptr;
   SG_CUDA(ctx, cudaMalloc(&nc, std::max<size_t>(need, 1) * sizeof(double)));
@@ -735,6 +770,17 @@ int sg_map_regrow(slamgpu_map *m, const GrowState &g) {
   return SLAMGPU_OK;
 }
 
+// device address of one internal cell for the single-cell entry points; a tiled map first makes the cell's tile private
+static int writable_cell_ptr(slamgpu_map *m, int ix, int iy, double **out) {
+  if (!m->pool) { *out = m->d_cells + ((size_t)iy * m->w + ix) * m->stride; return SLAMGPU_OK; }
+  std::vector<int32_t> copies;
+  SG_TRY(sg_map_make_writable(m, ix, iy, ix, iy, &copies));
+  SG_TRY(sg_pool_run_copies(m->pool, copies));
+  *out = m->pool->ptr(m->tile_ids[(size_t)(iy >> SG_TILE_BITS) * m->tw + (ix >> SG_TILE_BITS)]) +
+         ((size_t)(iy & (SG_TILE - 1)) * SG_TILE + (ix & (SG_TILE - 1))) * m->stride;
+  return SLAMGPU_OK;
+}
+
 // ---------------------------------------------------------------- single-cell plumbing
 extern "C" int slamgpu_map_reset_cell(slamgpu_map *m, int32_t x, int32_t y, const double *rec) {
   if (!m || !rec) return SLAMGPU_E_INVALID;
@@ -747,7 +793,9 @@ extern "C" int slamgpu_map_reset_cell(slamgpu_map *m, int32_t x, int32_t y, cons
   RecParam rp;
   memset(rp.v, 0, sizeof rp.v);
   memcpy(rp.v, rec, sizeof(double) * m->stride);
-  k_reset_cell<<<1, 1, 0, ctx->stream>>>(m->d_cells + ((size_t)iy * m->w + ix) * m->stride, m->stride, rp);
+  double *cell = nullptr;
+  SG_TRY(writable_cell_ptr(m, ix, iy, &cell));
+  k_reset_cell<<<1, 1, 0, ctx->stream>>>(cell, m->stride, rp);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
   sg_map_invalidate_lut(m);
@@ -764,7 +812,9 @@ extern "C" int slamgpu_map_update_cell(slamgpu_map *m, int32_t x, int32_t y, int
   if (g.ensure_inside(x, y)) SG_TRY(sg_map_regrow(m, g));
   int ix = x + m->ox, iy = y + m->oy;
   if (ix < 0 || ix >= m->w || iy < 0 || iy >= m->h) return sg_fail(ctx, SLAMGPU_E_INVALID, "cell (%d, %d) is outside the bounded map", x, y);
-  k_update_cell<<<1, 1, 0, ctx->stream>>>(m->d_cells + ((size_t)iy * m->w + ix) * m->stride, m->stride, m->model, aoo_p, aoo_q,
+  double *cell = nullptr;
+  SG_TRY(writable_cell_ptr(m, ix, iy, &cell));
+  k_update_cell<<<1, 1, 0, ctx->stream>>>(cell, m->stride, m->model, aoo_p, aoo_q,
                                          obst_x, obst_y, quality);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
@@ -869,7 +919,8 @@ int run_raycast_multi(slamgpu_ctx *ctx, double scale, const BeamRec *beams, int 
 
 MapSlot slot_of(const slamgpu_map *m, double px, double py, double shift, unsigned key_base) {
   MapSlot s;
-  s.cells = m->d_cells; s.px = px; s.py = py; s.shift = shift; s.w = m->w; s.h = m->h; s.ox = m->ox; s.oy = m->oy; s.key_base = key_base; s.pad = 0;
+  s.cells = m->d_cells; s.px = px; s.py = py; s.shift = shift; s.w = m->w; s.h = m->h; s.ox = m->ox; s.oy = m->oy; s.key_base = key_base;
+  s.tiles = m->pool ? m->d_tile_ptrs : nullptr; s.tw = m->tw;
   s.rx = host_world_to_cell(px, m->scale); s.ry = host_world_to_cell(py, m->scale);
   s.beam_begin = s.beam_end = 0;
   return s;
@@ -1010,6 +1061,28 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     }
     SG_TRY(sg_map_regrow(map, g));
   }
+  // ---- copy-on-write maps: the tiles under the bounding box of each map's beams (robot cell .. end cells, which holds every
+  // ray-cast cell and the ring around the robot) become private to the map before anything is written
+  {
+    std::vector<int32_t> copies;
+    SgTilePool *pool = nullptr;
+    for (int k = 0; k < n; ++k) {
+      slamgpu_map *map = maps[k];
+      if (!map->pool || plans[k].M == 0) continue;
+      pool = map->pool;
+      const BeamPlan &plan = plans[k];
+      int x0 = plan.rx - 7, x1 = plan.rx + 7, y0 = plan.ry - 7, y1 = plan.ry + 7;  // k_apply_ring's window
+      bool any = false;
+      for (const BeamRec &b : plan.beams) {
+        if (!b.active) continue;
+        any = true;
+        x0 = std::min(x0, b.obx - 1); x1 = std::max(x1, b.obx + 1); y0 = std::min(y0, b.oby - 1); y1 = std::max(y1, b.oby + 1);
+      }
+      if (any) SG_TRY(sg_map_make_writable(map, x0 + map->ox, y0 + map->oy, x1 + map->ox, y1 + map->oy, &copies));
+    }
+    if (pool) SG_TRY(sg_pool_run_copies(pool, copies));
+    for (int k = 0; k < n; ++k) SG_TRY(sg_map_sync_tiles(maps[k]));
+  }
   // ---- key space: the maps end to end
   unsigned long long key_total = 0;
   for (int k = 0; k < n; ++k) {
@@ -1118,6 +1191,7 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
 extern "C" int slamgpu_append_scan(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
                                    double scan_quality, int32_t scan_margin, const slamgpu_estimator *est, double blur,
                                    double max_range, const double *point_quality, int64_t *cells_updated) {
+  SG_NVTX("K2/K3 append_scan");
   if (!ctx) return SLAMGPU_E_INVALID;
   if (map && map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_scan");
   return sg_append_scan_impl(ctx, map, scan, pose, scan_quality, scan_margin, est, blur, max_range, point_quality,
@@ -1166,6 +1240,7 @@ int sg_plan_from_beams(slamgpu_ctx *ctx, const slamgpu_map *map, int32_t n, cons
 extern "C" int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
                                     const double *quality, const slamgpu_estimator *est, double blur, double max_range,
                                     int64_t *cells_updated) {
+  SG_NVTX("K2/K3 append_beams");
   if (!ctx || !map || n < 0 || (n > 0 && (!beams || !is_occ || !quality)) || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append_beams: bad argument");
   if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
   if (map->pyr) return sg_fail(ctx, SLAMGPU_E_STATE, "this map is level 0 of a pyramid: use slamgpu_pyramid_append_beams");
@@ -1178,6 +1253,7 @@ extern "C" int slamgpu_append_beams(slamgpu_ctx *ctx, slamgpu_map *map, int32_t 
 
 extern "C" int slamgpu_raycast(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3],
                                int64_t *out_offsets, int32_t *out_cells, int64_t cap, int64_t *total) {
+  SG_NVTX("K2 raycast");
   if (!ctx || !map || !scan || !pose || !out_offsets) return sg_fail(ctx, SLAMGPU_E_INVALID, "raycast: NULL argument");
   if (map->ctx != ctx || scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map/scan belongs to another ctx");
   SG_CUDA(ctx, cudaSetDevice(ctx->device));

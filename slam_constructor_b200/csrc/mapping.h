@@ -33,7 +33,8 @@ struct MapSlot {
   double shift;        // the area estimator's Shift_Amount for this map's beams
   int w, h, ox, oy;
   unsigned key_base;   // first sort key of this map (maps are laid end to end in key space)
-  unsigned pad;
+  int tw;              // tiled map: tiles per row
+  double *const *tiles;  // tiled map (copy-on-write particle maps): tile pointers [th][tw], cells == NULL
   int rx, ry;          // the robot's own cell: every beam updates it once; the window around it is updated apart (k_apply_ring)
   int beam_begin, beam_end;  // this map's beams in the batch
 };

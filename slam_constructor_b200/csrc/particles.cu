@@ -34,6 +34,10 @@
 struct slamgpu_particles {
   slamgpu_ctx *ctx = nullptr;
   std::vector<slamgpu_map *> maps;
+  // GROW_TILED particle maps (UnboundedLazyTiledGridMap upstream) share copy-on-write tiles out of this pool; NULL: dense maps
+  SgTilePool *pool = nullptr;
+  int64_t resample_bytes = 0, resample_tiles_shared = 0;  // of the last resampling
+  double resample_ms = 0;
   int lo = 0, hi = 0, chunk = 0;
   int owner(int i) const { return i / chunk; }
   // per particle: the GMapping OOPE cache its own estimator object would hold (spe.gm_cache == 2)
@@ -51,8 +55,15 @@ extern "C" int slamgpu_particles_create(slamgpu_ctx *ctx, int32_t n, int32_t w, 
   p->hi = std::min(n, p->lo + p->chunk);
   p->maps.assign(n, nullptr);
   p->gm_state.assign(n, slamgpu_gm_cache{0, 0, -1.0});
+  static const bool env_dense = [] { const char *e = getenv("SLAMGPU_DENSE_PARTICLES"); return e && atoi(e) != 0; }();
+  if (grow == SLAMGPU_GROW_TILED && !env_dense) {
+    SG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int r = sg_pool_create(ctx, model, unknown_rec, &p->pool);
+    if (r != SLAMGPU_OK) { slamgpu_particles_destroy(p); return r; }
+  }
   for (int i = p->lo; i < p->hi; ++i) {
-    int r = slamgpu_map_create(ctx, w, h, scale, model, grow, unknown_rec, &p->maps[i]);
+    int r = p->pool ? sg_map_create_tiled(ctx, p->pool, w, h, scale, model, grow, unknown_rec, &p->maps[i])
+                    : slamgpu_map_create(ctx, w, h, scale, model, grow, unknown_rec, &p->maps[i]);
     if (r != SLAMGPU_OK) { slamgpu_particles_destroy(p); return r; }
   }
   *out = p;
@@ -63,7 +74,21 @@ extern "C" void slamgpu_particles_destroy(slamgpu_particles *p) {
   if (!p) return;
   for (slamgpu_map *m : p->maps)
     if (m) slamgpu_map_destroy(m);
+  sg_pool_destroy(p->pool);
   delete p;
+}
+
+extern "C" int slamgpu_particles_tile_stats(const slamgpu_particles *p, int64_t stats[8]) {
+  if (!p || !stats) return SLAMGPU_E_INVALID;
+  memset(stats, 0, sizeof(int64_t) * 8);
+  stats[0] = p->pool ? 1 : 0;
+  if (p->pool) {
+    stats[1] = p->pool->tiles_live; stats[2] = p->pool->tiles_cloned;
+    stats[3] = (int64_t)(p->pool->tile_doubles * sizeof(double));
+    stats[4] = (int64_t)p->pool->chunks.size() * p->pool->tiles_per_chunk * stats[3];
+  }
+  stats[5] = p->resample_bytes; stats[6] = p->resample_tiles_shared; stats[7] = (int64_t)(p->resample_ms * 1e3);
+  return SLAMGPU_OK;
 }
 
 extern "C" int slamgpu_particles_count(const slamgpu_particles *p) { return p ? (int)p->maps.size() : SLAMGPU_E_INVALID; }
@@ -75,6 +100,7 @@ extern "C" slamgpu_map *slamgpu_particles_map(slamgpu_particles *p, int32_t i) {
 
 extern "C" int slamgpu_particles_score(slamgpu_particles *p, slamgpu_scan *scan, const slamgpu_spe_params *spe,
                                        const double *poses, int32_t per_particle, double *out_scores) {
+  SG_NVTX("K6 particles_score");
   if (!p || !spe || per_particle < 0 || (per_particle > 0 && (!poses || !out_scores))) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   const int n = (int)p->maps.size(), nl = p->hi - p->lo;
@@ -97,6 +123,7 @@ extern "C" int slamgpu_particles_match_hc(slamgpu_particles *p, slamgpu_scan *sc
                                           const double *init_poses, const uint8_t *active, uint32_t max_failed_rounds,
                                           double translation_delta, double rotation_delta, double *out_poses, double *out_probs,
                                           int64_t *out_tested) {
+  SG_NVTX("K6 particles_match_hc");
   if (!p || !scan || !spe || !init_poses || !out_poses || !out_probs) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   const int n = (int)p->maps.size(), lo = p->lo, nl = p->hi - p->lo;
@@ -239,6 +266,7 @@ extern "C" int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan
                                 const double init_pose[3], uint32_t max_failed_rounds, double translation_delta,
                                 double rotation_delta, double out_pose[3], double *out_prob, int64_t *out_tested,
                                 double *log, int32_t log_cap, int32_t *log_count, slamgpu_gm_cache *gm_state) {
+  SG_NVTX("K1 match_hc");
   if (!ctx || !map || !scan || !spe || !init_pose || !out_pose || !out_prob) return sg_fail(ctx, SLAMGPU_E_INVALID, "match_hc: NULL argument");
   if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
   if (log_count) *log_count = -1;  // -1: no log was produced (round-by-round path)
@@ -269,6 +297,7 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
                                              const uint8_t *do_update, double scan_quality, int32_t scan_margin,
                                              const slamgpu_estimator *est, double blur, double max_range,
                                              const double *point_quality, int64_t *cells_updated) {
+  SG_NVTX("K6 particles_append_scan");
   if (!p || !scan || !poses || !est) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   if (scan->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "scan belongs to another ctx");
@@ -333,6 +362,7 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
 // copy of particle src[i].  A source that survives exactly once is moved, the others are copied on
 // the device.
 extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *src) {
+  SG_NVTX("K6 particles_resample");
   if (!p || !src) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   const int n = (int)p->maps.size(), lo = p->lo, hi = p->hi;
@@ -343,8 +373,12 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
   // (sender: the map as it is now; receiver: a staging buffer, so that no map is overwritten while a peer reads it)
   struct Geo { int32_t w, h, ox, oy; };
   std::vector<Geo> geo;
-  std::vector<DevBuf> staged(n);
-  auto release_staged = [&]() { for (DevBuf &b : staged) b.release(); };
+  std::vector<DevBuf> staged(n), send_staged(n);
+  auto release_staged = [&]() { for (DevBuf &b : staged) b.release(); for (DevBuf &b : send_staged) b.release(); };
+  cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
+  cudaEventCreate(&ev_r0); cudaEventCreate(&ev_r1);
+  cudaEventRecord(ev_r0, ctx->stream);
+  p->resample_bytes = 0; p->resample_tiles_shared = 0;
   if (ctx->nranks > 1) {
     geo.assign((size_t)p->chunk * ctx->nranks, Geo{0, 0, 0, 0});
     for (int i = lo; i < hi; ++i) geo[i] = Geo{p->maps[i]->w, p->maps[i]->h, p->maps[i]->ox, p->maps[i]->oy};
@@ -356,7 +390,15 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
       if (q == r) continue;
       if (ctx->rank == q) {
         slamgpu_map *m = p->maps[src[i]];
-        sends.push_back(SgXfer{r, m->d_cells, (size_t)m->w * m->h * m->stride * sizeof(double)});
+        const size_t bytes = (size_t)m->w * m->h * m->stride * sizeof(double);
+        void *cells = m->d_cells;
+        if (m->pool) {  // a tiled map travels as the dense array it stands for
+          if (send_staged[i].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) { release_staged(); return sg_fail(ctx, SLAMGPU_E_NOMEM, "resample: send staging for particle %d", i); }
+          int rc2 = sg_map_gather_dense(m, send_staged[i].as<double>());
+          if (rc2 != SLAMGPU_OK) { release_staged(); return rc2; }
+          cells = send_staged[i].p;
+        }
+        sends.push_back(SgXfer{r, cells, bytes});
       } else if (ctx->rank == r) {
         const Geo &g = geo[src[i]];
         const size_t bytes = (size_t)g.w * g.h * stride * sizeof(double);
@@ -393,21 +435,37 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
       spare.pop_back();
       if (pass == 0) {
         slamgpu_map *from = p->maps[src[i]];
-        SG_TRY(sg_map_realloc(to, from->w, from->h));
-        to->ox = from->ox; to->oy = from->oy;
-        SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, from->d_cells, (size_t)from->w * from->h * from->stride * sizeof(double),
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        if (to->pool) {
+          // copy-on-write: the copy shares every tile of its source (lazy_tiled_grid_map.h:57-71); nothing moves
+          SG_TRY(sg_map_share_tiles(to, from));
+          for (int32_t id : from->tile_ids) p->resample_tiles_shared += id != 0;
+        } else {
+          SG_TRY(sg_map_realloc(to, from->w, from->h));
+          to->ox = from->ox; to->oy = from->oy;
+          const size_t bytes = (size_t)from->w * from->h * from->stride * sizeof(double);
+          SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, from->d_cells, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+          p->resample_bytes += (int64_t)bytes;
+        }
       } else {
         const Geo &g = geo[src[i]];
         SG_TRY(sg_map_realloc(to, g.w, g.h));
         to->ox = g.ox; to->oy = g.oy;
-        SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, staged[i].p, (size_t)g.w * g.h * to->stride * sizeof(double),
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        const size_t bytes = (size_t)g.w * g.h * to->stride * sizeof(double);
+        if (to->pool) SG_TRY(sg_map_scatter_dense(to, staged[i].as<double>()));
+        else SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, staged[i].p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        p->resample_bytes += (int64_t)bytes;
       }
       sg_map_invalidate_lut(to);
       next[i] = to;
     }
+  cudaEventRecord(ev_r1, ctx->stream);
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    float ms = 0;
+    if (ev_r0 && ev_r1 && cudaEventElapsedTime(&ms, ev_r0, ev_r1) == cudaSuccess) p->resample_ms = ms;
+    if (ev_r0) cudaEventDestroy(ev_r0);
+    if (ev_r1) cudaEventDestroy(ev_r1);
+  }
   release_staged();
   p->maps.swap(next);
   // GMapping OOPE cache: the first particle (in index order) drawn from a source keeps the source's estimator object

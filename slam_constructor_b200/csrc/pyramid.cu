@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256) k_ordered_sums_staged(const MatchRec *__r
 
 MapView level_view(const slamgpu_map *m, int oie) {
   MapView v;
-  v.lut = m->d_lut[oie]; v.cells = m->d_cells;
+  v.lut = m->d_lut[oie]; v.cells = m->d_cells; v.tiles = nullptr; v.tw = 0;
   v.w = m->w; v.h = m->h; v.ox = m->ox; v.oy = m->oy; v.pitch = m->pitch; v.stride = m->stride; v.model = m->model;
   v.scale = m->scale; v.unknown_lut = m->unknown_lut[oie];
   memcpy(v.unknown_rec, m->unknown, sizeof v.unknown_rec);
@@ -565,6 +565,7 @@ extern "C" int slamgpu_pyramid_level_download(slamgpu_pyramid *p, int32_t level,
 static int floor_div_i(int v, int d) { return v >= 0 ? v / d : -((-v + d - 1) / d); }
 
 extern "C" int slamgpu_pyramid_build(slamgpu_pyramid *p) {
+  SG_NVTX("K4 pyramid_build");
   if (!p) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   SG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -715,6 +716,7 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
 extern "C" int slamgpu_pyramid_append_scan(slamgpu_pyramid *p, slamgpu_scan *scan, const double pose[3], double scan_quality,
                                            int32_t scan_margin, const slamgpu_estimator *est, double blur, double max_range,
                                            const double *point_quality, int64_t *cells_updated) {
+  SG_NVTX("K4 pyramid_append_scan");
   if (!p) return SLAMGPU_E_INVALID;
   SG_TRY(ensure_continuous(p));
   AppendTrace tr;
@@ -1024,6 +1026,7 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
                                    const double *weight, const double pose[3], const slamgpu_spe_params *spe, double x_limit,
                                    double y_limit, double rot_limit, double ang_step, double transl_step,
                                    double max_finest_prob_diff, double out_delta[3], double *out_prob, int64_t stats[4]) {
+  SG_NVTX("K5 match_m3rsm");
   if (!p) return SLAMGPU_E_INVALID;
   slamgpu_ctx *ctx = p->ctx;
   if (n < 0 || (n > 0 && (!range || !angle)) || !pose || !spe || !out_delta || !out_prob || !(ang_step > 0))

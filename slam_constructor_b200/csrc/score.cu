@@ -192,7 +192,7 @@ SG_DEV double gmapping_probability(const MapView &m, int cx, int cy, double X, d
 #pragma unroll
         for (int k = 0; k < SLAMGPU_MAX_STRIDE; ++k) r[k] = m.unknown_rec[k];
       } else {
-        const double *src = m.cells + ((size_t)iy * m.w + ix) * m.stride;
+        const double *src = view_cell(m, ix, iy);
         for (int k = 0; k < m.stride; ++k) r[k] = __ldg(src + k);
       }
       if (r[0] < th) continue;
@@ -1791,7 +1791,8 @@ void slice_of(const slamgpu_ctx *ctx, int64_t P, int64_t *p0, int64_t *p1) {
 
 MapView make_view(const slamgpu_map *m, int oie) {
   MapView v;
-  v.lut = m->d_lut[oie]; v.cells = m->d_cells;
+  if (m->pool) (void)sg_map_sync_tiles(const_cast<slamgpu_map *>(m));  // the tile table the kernels read is the current one
+  v.lut = m->d_lut[oie]; v.cells = m->d_cells; v.tiles = m->pool ? m->d_tile_ptrs : nullptr; v.tw = m->tw;
   v.w = m->w; v.h = m->h; v.ox = m->ox; v.oy = m->oy; v.pitch = m->pitch; v.stride = m->stride; v.model = m->model;
   v.scale = m->scale; v.unknown_lut = m->unknown_lut[oie];
   memcpy(v.unknown_rec, m->unknown, sizeof v.unknown_rec);
@@ -1848,6 +1849,7 @@ int upload_host_trig(slamgpu_ctx *ctx, Candidates &c, const std::vector<double> 
 
 extern "C" int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *poses,
                                    int64_t P) {
+  SG_NVTX("K1 stage_poses");
   if (!ctx) return SLAMGPU_E_INVALID;
   SG_TRY(check_spe(ctx, scan, p));
   if (P < 0 || (P > 0 && !poses)) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad pose list");
@@ -1903,6 +1905,7 @@ extern "C" int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const s
 
 extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *xs,
                                   int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt) {
+  SG_NVTX("K1 stage_grid");
   if (!ctx) return SLAMGPU_E_INVALID;
   SG_TRY(check_spe(ctx, scan, p));
   if (nx <= 0 || ny <= 0 || nt <= 0 || !xs || !ys || !thetas) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad grid axes");
@@ -2449,6 +2452,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
 }  // namespace
 
 extern "C" int slamgpu_score_launch(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
+  SG_NVTX("K1 score_launch");
   if (!ctx) return SLAMGPU_E_INVALID;
   return launch_staged(ctx, map, init_score);
 }
@@ -2506,6 +2510,7 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
 }
 
 extern "C" int slamgpu_score_fetch(slamgpu_ctx *ctx, double *out_scores, int64_t *best_idx, double *best_score) {
+  SG_NVTX("K1 score_fetch");
   if (!ctx) return SLAMGPU_E_INVALID;
   return fetch_impl(ctx, ctx->cand.last_map, out_scores, best_idx, best_score);
 }
@@ -2618,6 +2623,7 @@ static int score_small_oneshot(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n
 extern "C" int slamgpu_score_poses(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
                                    const double *poses, int64_t P, double init_score, double *out_scores, int64_t *best_idx,
                                    double *best_score) {
+  SG_NVTX("K1 score_poses");
   if (!ctx) return SLAMGPU_E_INVALID;
   if (map && scan && p && poses && check_spe(ctx, scan, p) == SLAMGPU_OK) {
     int served = 0;
@@ -2632,6 +2638,7 @@ extern "C" int slamgpu_score_poses(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_s
 extern "C" int slamgpu_score_grid(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
                                   const double *xs, int32_t nx, const double *ys, int32_t ny, const double *thetas, int32_t nt,
                                   double init_score, double *out_scores, int64_t *best_idx, double *best_score) {
+  SG_NVTX("K1 score_grid");
   if (!ctx) return SLAMGPU_E_INVALID;
   SG_TRY(slamgpu_stage_grid(ctx, scan, p, xs, nx, ys, ny, thetas, nt));
   SG_TRY(launch_staged(ctx, map, init_score));
@@ -2711,6 +2718,7 @@ int sg_score_chained(slamgpu_ctx *ctx, slamgpu_map *const *maps, int n_maps, con
 extern "C" int slamgpu_score_poses_chained(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const slamgpu_spe_params *p,
                                            const double *poses, int64_t P, const slamgpu_gm_cache *state_in, double *out_scores,
                                            slamgpu_gm_cache *out_states) {
+  SG_NVTX("K1 score_poses_chained");
   if (!ctx || !map || !state_in) return sg_fail(ctx, SLAMGPU_E_INVALID, "score_poses_chained: NULL argument");
   if (map->ctx != ctx) return sg_fail(ctx, SLAMGPU_E_INVALID, "map belongs to another ctx");
   return sg_score_chained(ctx, &map, 1, nullptr, scan, p, poses, P, nullptr, state_in, 1, out_scores, out_states);
@@ -2823,6 +2831,7 @@ extern "C" int slamgpu_match_mc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan
                                 const double best_pose[3], double best_prob, int32_t have_best, const double *noise, int32_t K,
                                 uint32_t failed, uint32_t poses_nm, uint32_t max_failed, uint32_t max_poses, double out[10],
                                 double *log, int32_t log_cap, int32_t *served) {
+  SG_NVTX("K1 match_mc");
   if (!ctx || !map || !scan || !p || !best_pose || K < 0 || (K > 0 && !noise) || !out || !served)
     return sg_fail(ctx, SLAMGPU_E_INVALID, "match_mc: bad argument");
   *served = 0;

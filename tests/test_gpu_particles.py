@@ -184,3 +184,66 @@ def test_carried_cache_round_by_round_path_agrees(sg, gpu):
         np.testing.assert_allclose(fast[1], slow[1], rtol=1e-12, atol=0)
         gsc.close()
     parts_a.close(); parts_b.close()
+
+
+def test_copy_on_write_tiles_of_the_particle_maps(sg, gpu):
+    """LazyTiledGridMap (lazy_tiled_grid_map.h:18-118): a new particle map references one shared all-unknown tile, a scan
+    makes only the tiles under it private, resampling hands out tile references instead of copying cells, and the first
+    insertion after it clones exactly the tiles it writes.  Every map stays bit-equal to the oracle's throughout."""
+    rng = np.random.default_rng(4400)
+    n, size, scale = 16, 1024, 0.05                       # 8 x 8 tiles of 128 x 128 cells per map
+    parts = sg.Particles(gpu, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
+    omaps = [ob.OracleMap(size, size, scale, ob.CELL_GMAPPING, ob.GROW_TILED) for _ in range(n)]
+    oest, gest = ob.estimator(ob.EST_CONST), sg.estimator(sg.EST_CONST)
+    st = parts.tile_stats()
+    assert st["tiled"] == 1 and st["tiles_live"] == 1     # only the shared unknown tile exists
+    truth = np.array([0.3, -0.2, 0.1])
+
+    def insert(upd=None):
+        r, a = room_scan(rng, 240, 2 * np.pi, half_w=6.0, half_h=5.0, pose=truth, noise=0.01)   # 12 x 10 m room: 2 x 2 .. 3 x 3 tiles
+        poses = truth + rng.normal(0, [0.03, 0.03, 0.01], (n, 3))
+        gsc = sg.Scan(gpu, r, a)
+        cells = parts.append_scan(gsc, poses, do_update=upd, est=gest)
+        for i in range(n):
+            if upd is None or upd[i]:
+                c, _ = omaps[i].append_scan(ob.OracleScan(r, a), poses[i], 1.0, 0, oest)
+                assert c == cells[i]
+        gsc.close()
+
+    insert()
+    st1 = parts.tile_stats()
+    per_map = (st1["tiles_live"] - 1) / n
+    assert 4 <= per_map <= 16 and st1["tiles_live"] - 1 == st1["tiles_cloned"]   # a few of the 64 tiles per map, all cloned from tile 0
+    assert st1["pool_bytes"] < 0.3 * n * size * size * 5 * 8                  # far below 16 dense maps
+    _check_maps(parts, omaps)
+    insert()                                                                   # same room: nothing new to clone
+    assert parts.tile_stats()["tiles_cloned"] == st1["tiles_cloned"]
+    # resample: particle i becomes a copy of src[i]; 0 and 5 survive, the others are copies of them
+    src = np.array([0, 0, 0, 5, 5, 5, 5, 0, 0, 5, 5, 0, 0, 5, 0, 5], np.int32)
+    parts.resample(src)
+    st2 = parts.tile_stats()
+    assert st2["resample_bytes"] == 0 and st2["resample_tiles_shared"] > 0    # table copies only
+    assert st2["tiles_live"] < st1["tiles_live"]                               # the dropped particles' tiles went back to the pool
+    after = []
+    for i in range(n):
+        after.append(omaps[src[i]] if src[i] == i else
+                     ob.OracleMap(model=ob.CELL_GMAPPING, handle=ob.orc.orc_map_clone(omaps[src[i]].h_), owner=True))
+    omaps = after
+    _check_maps(parts, omaps)
+    # an insertion into SOME of the copies clones only their tiles; the untouched copies keep sharing
+    upd = np.zeros(n, np.uint8); upd[[1, 2, 3]] = 1
+    live_before = parts.tile_stats()["tiles_live"]
+    insert(upd)
+    grown = parts.tile_stats()["tiles_live"] - live_before
+    assert 3 * 4 <= grown <= 3 * 16
+    _check_maps(parts, omaps)
+    insert()
+    _check_maps(parts, omaps)
+    # scoring reads through the tile tables
+    r, a = room_scan(rng, 181, 2 * np.pi, half_w=6.0, half_h=5.0, pose=truth, noise=0.005)
+    gsc, osc = sg.Scan(gpu, r, a), ob.OracleScan(r, a)
+    cand = truth + rng.normal(0, [0.05, 0.05, 0.02], (n, 5, 3))
+    got = parts.score(gsc, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1), cand)
+    want = np.stack([omaps[i].score(osc, ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1), cand[i]) for i in range(n)])
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    gsc.close(); parts.close()
