@@ -408,7 +408,7 @@ int sg_map_realloc(slamgpu_map *m, int32_t w, int32_t h) {
   return SLAMGPU_OK;
 }
 
-void sg_map_invalidate_lut(slamgpu_map *m) { m->lut_valid[0] = m->lut_valid[1] = false; }
+void sg_map_invalidate_lut(slamgpu_map *m) { m->lut_valid[0] = m->lut_valid[1] = false; m->wlut_valid = false; }
 
 
 // ------------------------------------------------------------------ copy-on-write tiles (see internal.h: SgTilePool)
@@ -649,6 +649,7 @@ extern "C" void slamgpu_map_destroy(slamgpu_map *m) {
   }
   for (int i = 0; i < 2; ++i)
     if (m->d_lut[i]) cudaFree(m->d_lut[i]);
+  if (m->d_wlut) cudaFree(m->d_wlut);
   delete m;
 }
 

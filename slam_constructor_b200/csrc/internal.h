@@ -59,9 +59,10 @@ struct Candidates {  // a staged candidate set (device resident)
   int32_t n_warps4 = 0;
   int32_t ngys = 0;  // row stride of cyw (v4 / v5: ngy rounded up to even)
   int32_t grid_R = 8, ngy = 0;  // rows per thread of the grid kernel, y-groups per (theta, beam)
-  bool grid_v2 = true, force_v1 = false;
+  bool grid_v2 = true, force_v1 = false, force_list = false;
   // 5: v4's arithmetic behind a cp.async pipeline (default), 4: each distinct row gathered once per thread + indexed-branch accumulate, 3: TMA-staged patches (experimental,
   // slower: see DESIGN.md), 2: packed rows + L1 gathers (fallback of 4), 1: explicit row table
+  int win_mode = 0;       // SLAMGPU_OOPE_MAX / _MEAN: the grid is scored out of the map's window LUTs (v1 kernel)
   int grid_variant = 5;   // variant of the staged set
   int user_variant = 0;   // requested through slamgpu_ctx_set_option / SLAMGPU_GRID_VARIANT (0: default = 5)
   int max_variant = 5;    // temporary cap while a launch falls back to a simpler variant
@@ -168,6 +169,14 @@ struct slamgpu_map {
   bool lut_valid[2] = {false, false};
   int32_t pitch = 0;
   double unknown_lut[2] = {0, 0};
+  // window LUTs of the brute-force grid path (score.cu: sg_map_ensure_wlut): for the max / mean OOPEs the probability of a
+  // window depends only on its first cell and on how many cells it spans per axis (two possibilities each) -> 4 tables
+  double *d_wlut = nullptr;
+  size_t wlut_cap = 0;
+  bool wlut_valid = false;
+  int wl_oie = 0, wl_mode = 0, wl_nxmin = 0, wl_nymin = 0, wl_pitch = 0, wl_rows = 0;
+  double wl_v = 0, wl_h = 0;
+  size_t wl_T = 0;  // doubles per table
   struct slamgpu_pyramid *pyr = nullptr;  // owning pyramid if this is its level 0
 };
 

@@ -928,6 +928,11 @@ struct GridIdxArgs {
   int v2, R, ngy;
   int ngys;      // v4 / v5: row stride of cyw (ngy rounded up to even: 16-byte copies of a pair of row words stay aligned)
   int v4, dmax;  // v4 row word: low 32 bits = element offset of the first y's padded LUT row, bits 32..38 = "new row" mask
+  // window OOPEs (max / mean) out of the map's window LUTs: the x table holds (first column of the window) + vx * T, the y
+  // table (first row) * pitch + vy * 2T, vx / vy = cells spanned beyond the minimum; see sg_map_ensure_wlut
+  int win, wl_nxmin, wl_nymin, wl_pitch;
+  double win_hh, win_hv;   // half window sides
+  long long wl_T;
   int v5, nb, bw;   // v5: column records per (theta, beam, band of bw columns) instead of the cxp table
   uint4 *colrec;    // [(tl*N + i)*nb + band][2]: {first column (even), 0, 0, 0} {32 nibbles: column of lane - first column}
   // v3 (TMA-staged patches): per (theta, beam, block-of-theta) patch origin {first padded column, first padded row}
@@ -1003,6 +1008,17 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
       int *dst = a.cxp + ti0 * a.nx + c;
       for (int pr = 0; pr < np; ++pr) {
         const double rc = sh_rc[pr];
+        if (a.win) {
+          // window_probability (dev_window.cuh): lx = floor((X - hh) / s), rx = floor((X + hh) / s), x outer loop
+          const double X = sg::add(x, rc);
+          const int lx = grid_axis_cell(sg::sub(X, a.win_hh), rc, a.scale, inv_scale, a.guard, &unsafe_any);
+          const int rx = grid_axis_cell(sg::add(X, a.win_hh), rc, a.scale, inv_scale, a.guard, &unsafe_any);
+          int vx = rx - lx + 1 - a.wl_nxmin;
+          if (vx < 0 || vx > 1) { atomicAdd((unsigned long long *)&a.result->pad, 1ull); vx = 0; }
+          const int K = a.wl_nxmin + 1;
+          dst[(size_t)pr * a.nx] = clampi(lx + a.ox, -K, a.w) + K + vx * (int)a.wl_T;
+          continue;
+        }
         const int cx = grid_axis_cell(sg::add(x, rc), rc, a.scale, inv_scale, a.guard, &unsafe_any);
         const int col = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
         if (a.v5) sh_rows[SG_IDX_PAIRS * a.ny + pr * a.nx + c] = col;
@@ -1014,6 +1030,21 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
       const double y = k < a.ny ? a.ys[k] : 0.0;
       for (int pr = 0; pr < np; ++pr) {
         int prow = 0;  // v1 padding rows point at the ring row 0 (always valid memory)
+        if (a.win) {
+          int enc = 0;
+          if (k < a.ny) {
+            const double rs = sh_rs[pr];
+            const double Y = sg::add(y, rs);
+            const int ly = grid_axis_cell(sg::sub(Y, a.win_hv), rs, a.scale, inv_scale, a.guard, &unsafe_any);
+            const int ry = grid_axis_cell(sg::add(Y, a.win_hv), rs, a.scale, inv_scale, a.guard, &unsafe_any);
+            int vy = ry - ly + 1 - a.wl_nymin;
+            if (vy < 0 || vy > 1) { atomicAdd((unsigned long long *)&a.result->pad, 1ull); vy = 0; }
+            const int K = a.wl_nymin + 1;
+            enc = (clampi(ly + a.oy, -K, a.h) + K) * a.wl_pitch + vy * 2 * (int)a.wl_T;
+          }
+          a.cyp[(ti0 + pr) * a.nyp + k] = enc;
+          continue;
+        }
         if (k < a.ny) {
           const double rs = sh_rs[pr];
           const int cy = grid_axis_cell(sg::add(y, rs), rs, a.scale, inv_scale, a.guard, &unsafe_any);
@@ -1783,6 +1814,69 @@ void launch_grid2(slamgpu_ctx *ctx, const GridArgs2 &a, int nblk, bool factor, b
   }
 }
 
+// ------------------------------------------------------------------ window LUTs (max / mean OOPEs on the candidate grid)
+// MaxOccupancyObservationPE / MeanOccupancyObservationPE (occupancy_observation_probability.h:29-72) fold the impacts of the
+// cells a window covers, walking x outer / y inner (GridRasterizedRectangle, grid_rasterization.h:26-64).  The result depends
+// only on the window's first cell and on how many cells it spans per axis, and for a window of fixed size that number takes
+// two values (nmin or nmin + 1).  So the four possible folds are tabulated per first cell -- in the reference's operation
+// order, hence bit-equal -- and a brute-force evaluation becomes one gather, exactly as for the obstacle OOPE: the existing
+// grid kernel runs unchanged on offsets that select table and cell (k_grid_indices, a.win).
+struct WlutArgs {
+  const double *lut;   // padded impact LUT of the map
+  int w, h, pitch;
+  int mode, nxmin, nymin, pitch_w, rows_w;
+  long long T;
+  double *out;         // [vy][vx][rows_w][pitch_w]
+};
+__global__ void k_build_wlut(WlutArgs a) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+  if (px >= a.pitch_w || py >= a.rows_w) return;
+  const int Kx = a.nxmin + 1, Ky = a.nymin + 1;
+  const int ix0 = px - Kx, iy0 = py - Ky;  // internal cell the window starts at (may be outside the map)
+#pragma unroll
+  for (int vy = 0; vy < 2; ++vy)
+#pragma unroll
+    for (int vx = 0; vx < 2; ++vx) {
+      const int nxc = a.nxmin + vx, nyc = a.nymin + vy;
+      double acc = 0.0;
+      for (int x = 0; x < nxc; ++x)
+        for (int y = 0; y < nyc; ++y) {
+          const int ix = clampi(ix0 + x, -1, a.w) + SG_LUT_PAD, iy = clampi(iy0 + y, -1, a.h) + SG_LUT_PAD;
+          const double impact = __ldg(a.lut + (size_t)iy * a.pitch + ix);
+          acc = a.mode == SLAMGPU_OOPE_MAX ? sg::maxd(impact, acc) : sg::add(acc, impact);
+        }
+      const double v = a.mode == SLAMGPU_OOPE_MAX ? acc : sg::div(acc, (double)(nxc * nyc));
+      a.out[(size_t)(vy * 2 + vx) * a.T + (size_t)py * a.pitch_w + px] = v;
+    }
+}
+
+int sg_map_ensure_wlut(slamgpu_map *m, int oie, int mode, double win_v, double win_h) {
+  slamgpu_ctx *ctx = m->ctx;
+  SG_TRY(sg_map_ensure_lut(m, oie));
+  if (m->wlut_valid && m->wl_oie == oie && m->wl_mode == mode && m->wl_v == win_v && m->wl_h == win_h) return SLAMGPU_OK;
+  const int nxmin = (int)std::floor(win_h / m->scale) + 1, nymin = (int)std::floor(win_v / m->scale) + 1;
+  const int pitch_w = (m->w + nxmin + 1 + 1 + 1) & ~1, rows_w = m->h + nymin + 1 + 1;
+  const size_t T = (size_t)pitch_w * rows_w;
+  const size_t need = 4 * T + SG_LUT_SLACK;
+  if (need > m->wlut_cap) {
+    if (m->d_wlut) cudaFree(m->d_wlut);
+    m->d_wlut = nullptr; m->wlut_cap = 0;
+    SG_CUDA(ctx, cudaMalloc(&m->d_wlut, need * sizeof(double)));
+    m->wlut_cap = need;
+  }
+  WlutArgs a;
+  a.lut = m->d_lut[oie]; a.w = m->w; a.h = m->h; a.pitch = m->pitch;
+  a.mode = mode; a.nxmin = nxmin; a.nymin = nymin; a.pitch_w = pitch_w; a.rows_w = rows_w; a.T = (long long)T; a.out = m->d_wlut;
+  dim3 blk(32, 8), grd((pitch_w + 31) / 32, (rows_w + 7) / 8);
+  k_build_wlut<<<grd, blk, 0, ctx->stream>>>(a);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
+  m->wl_oie = oie; m->wl_mode = mode; m->wl_v = win_v; m->wl_h = win_h; m->wl_nxmin = nxmin; m->wl_nymin = nymin;
+  m->wl_pitch = pitch_w; m->wl_rows = rows_w; m->wl_T = T;
+  m->wlut_valid = true;
+  return SLAMGPU_OK;
+}
+
 // ------------------------------------------------------------------ host side
 void slice_of(const slamgpu_ctx *ctx, int64_t P, int64_t *p0, int64_t *p1) {
   *p0 = (int64_t)((__int128)P * ctx->rank / ctx->nranks);
@@ -1847,6 +1941,51 @@ int upload_host_trig(slamgpu_ctx *ctx, Candidates &c, const std::vector<double> 
 
 }  // namespace
 
+static int finish_list_stage(slamgpu_ctx *ctx, const slamgpu_spe_params *p);
+
+// the candidate grid of slamgpu_stage_grid written out as a pose list on the device (OOPEs without a tiled kernel)
+__global__ void k_expand_grid(const double *__restrict__ xs, const double *__restrict__ ys, const double *__restrict__ ts, int nx, int ny,
+                              long long p0, long long Ploc, double *__restrict__ poses, int *__restrict__ theta_id) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= Ploc) return;
+  const long long p = p0 + k;
+  const int j = (int)(p % nx);
+  const long long row = p / nx;
+  const int y = (int)(row % ny), t = (int)(row / ny);
+  poses[3 * k] = xs[j]; poses[3 * k + 1] = ys[y]; poses[3 * k + 2] = ts[t];
+  theta_id[k] = t;
+}
+
+static int stage_grid_as_list(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *xs, int32_t nx,
+                              const double *ys, int32_t ny, const double *thetas, int32_t nt) {
+  Candidates &c = ctx->cand;
+  c.kind = -1; c.launched = false;
+  c.P = (int64_t)nt * ny * nx; c.spe = *p; c.scan = scan;
+  slice_of(ctx, c.P, &c.p0, &c.p1);
+  const int64_t Ploc = c.p1 - c.p0;
+  if ((unsigned long long)nt * std::max(scan->n, 1) * 16ull > SG_LIST_MAX_TABLE_BYTES)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "%d thetas x %d points exceed the trig table budget; split the call", nt, scan->n);
+  c.h_axes.resize((size_t)nx + ny + nt);
+  std::copy(xs, xs + nx, c.h_axes.begin());
+  std::copy(ys, ys + ny, c.h_axes.begin() + nx);
+  std::copy(thetas, thetas + nt, c.h_axes.begin() + nx + ny);
+  SG_TRY(upload(ctx, c.d_xs, c.h_axes.data(), c.h_axes.size() * sizeof(double)));
+  c.h_thetas.assign(thetas, thetas + nt);
+  c.T = nt;
+  SG_TRY(upload(ctx, c.d_thetas, c.h_thetas.data(), c.h_thetas.size() * sizeof(double)));
+  if (c.poses.reserve(std::max<size_t>((size_t)Ploc * 3, 1) * sizeof(double)) != SLAMGPU_OK ||
+      c.theta_id.reserve(std::max<size_t>((size_t)Ploc, 1) * sizeof(int)) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "pose list of the candidate grid");
+  if (Ploc > 0) {
+    const double *d = c.d_xs.as<double>();
+    k_expand_grid<<<(unsigned)((Ploc + 255) / 256), 256, 0, ctx->stream>>>(d, d + nx, d + nx + ny, nx, ny, c.p0, Ploc, c.poses.as<double>(),
+                                                                         c.theta_id.as<int>());
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaGetLastError());
+  }
+  return finish_list_stage(ctx, p);
+}
+
 extern "C" int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const slamgpu_spe_params *p, const double *poses,
                                    int64_t P) {
   SG_NVTX("K1 stage_poses");
@@ -1886,6 +2025,14 @@ extern "C" int slamgpu_stage_poses(slamgpu_ctx *ctx, slamgpu_scan *scan, const s
   SG_TRY(upload(ctx, c.theta_id, tid.data(), tid.size() * sizeof(int32_t)));
   SG_TRY(upload(ctx, c.d_thetas, c.h_thetas.data(), c.h_thetas.size() * sizeof(double)));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tid is a local
+  return finish_list_stage(ctx, p);
+}
+
+// the tail of a list staging: trig tables, score buffers (c.poses / c.theta_id / c.d_thetas / c.h_thetas are in place)
+static int finish_list_stage(slamgpu_ctx *ctx, const slamgpu_spe_params *p) {
+  Candidates &c = ctx->cand;
+  const int N = c.scan->n;
+  const int64_t Ploc = c.p1 - c.p0;
   size_t tb = std::max<size_t>((size_t)c.T * N, 1) * sizeof(double);
   if (c.trc.reserve(tb) != SLAMGPU_OK || c.trs.reserve(tb) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trig table");
   c.trig_is_host = false;
@@ -1909,11 +2056,20 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   if (!ctx) return SLAMGPU_E_INVALID;
   SG_TRY(check_spe(ctx, scan, p));
   if (nx <= 0 || ny <= 0 || nt <= 0 || !xs || !ys || !thetas) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad grid axes");
-  if (p->oope != SLAMGPU_OOPE_OBSTACLE || p->prerotated)
-    return sg_fail(ctx, SLAMGPU_E_INVALID, "slamgpu_stage_grid: only the obstacle OOPE on polar scans has a tiled kernel; "
-                                           "expand the grid and use slamgpu_stage_poses");
+  if (p->prerotated) return sg_fail(ctx, SLAMGPU_E_INVALID, "slamgpu_stage_grid takes polar scans (pre-rotated ones carry one theta)");
   SG_CUDA(ctx, cudaSetDevice(ctx->device));
   Candidates &c = ctx->cand;
+  c.win_mode = 0;
+  if (p->oope == SLAMGPU_OOPE_MAX || p->oope == SLAMGPU_OOPE_MEAN) {
+    // windows of a finite, non-zero size: scored out of the map's window LUTs by the grid kernel; anything else as a list
+    const bool regular = p->win_v > 0 && p->win_h > 0 && std::isfinite(p->win_v) && std::isfinite(p->win_h);
+    if (!regular || c.force_list) return stage_grid_as_list(ctx, scan, p, xs, nx, ys, ny, thetas, nt);
+    c.win_mode = p->oope;
+  } else if (p->oope != SLAMGPU_OOPE_OBSTACLE) {
+    // overlap weights and the GMapping OOPE depend on where inside its cell a point falls: no table; the grid is written out
+    // as a pose list on the device and scored by the list kernel
+    return stage_grid_as_list(ctx, scan, p, xs, nx, ys, ny, thetas, nt);
+  }
   c.kind = -1; c.launched = false;
   c.spe = *p; c.scan = scan;
   c.nx = nx; c.ny = ny; c.nt = nt; c.nyp = (ny + SG_GRID_R - 1) / SG_GRID_R * SG_GRID_R;
@@ -1933,7 +2089,7 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
       if (!asc) v = 4;
     }
     if (v > c.max_variant) v = (v == 5 && c.max_variant == 4) ? 4 : std::min(c.max_variant, 2);  // 5 -> 4 -> 2 -> 1, 3 -> 2
-    if (c.force_v1) v = 1;
+    if (c.force_v1 || c.win_mode) v = 1;  // (window tables are selected per y: the explicit row table carries that)
     if ((size_t)ny * SG_IDX_PAIRS * sizeof(int) > 40 * 1024) v = 1;  // the index kernel stages the rows in smem
     c.grid_variant = v;
     c.grid_v2 = v >= 2;
@@ -1965,7 +2121,7 @@ extern "C" int slamgpu_stage_grid(slamgpu_ctx *ctx, slamgpu_scan *scan, const sl
   }
   // group / warp tables and the zeroed slack rows depend on the shape of the candidate set only, not on the axis values: a
   // matcher that scores the same window around a new pose every scan re-uses them (saves two uploads and the memsets)
-  const int64_t shape_key[8] = {nx, ny, nt, c.grid_variant, c.grid_R, scan->n, ctx->rank, ctx->nranks};
+  const int64_t shape_key[8] = {nx, ny, nt, c.grid_variant + 16 * c.win_mode, c.grid_R, scan->n, ctx->rank, ctx->nranks};
   const bool same_shape = c.shape_valid && memcmp(shape_key, c.shape_key, sizeof shape_key) == 0;
   c.shape_valid = false;
   const int GR = c.grid_R;
@@ -2275,7 +2431,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
     const int nt_loc = c.t_hi - c.t_lo + 1;
     // big sets: make the score LUT L2-resident while the trig / index kernels run (side stream)
     static const bool env_warm = [] { const char *e = getenv("SLAMGPU_WARM_L2"); return !e || atoi(e) != 0; }();
-    const bool warm = (long long)Ploc * N >= (1ll << 26) && c.warm_l2 && env_warm;
+    const bool warm = (long long)Ploc * N >= (1ll << 26) && c.warm_l2 && env_warm && !c.win_mode;
     if (warm) {
       const size_t lut_bytes = (size_t)map->pitch * (map->h + 2 * SG_LUT_PAD) * sizeof(double);
       if (lut_bytes <= (96ull << 20)) {
@@ -2305,6 +2461,13 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       ia.guard = device_trig ? 1 : 0;
       ia.cxp = c.cxp.as<int>(); ia.cyp = c.cyp.as<int>(); ia.result = res;
       ia.cyw = c.cyw.as<unsigned long long>(); ia.v2 = c.grid_v2 ? 1 : 0; ia.R = c.grid_R; ia.ngy = c.ngy;
+      ia.win = 0;
+      if (c.win_mode) {
+        SG_TRY(sg_map_ensure_wlut(map, oie, c.win_mode, c.spe.win_v, c.spe.win_h));
+        if (4 * map->wl_T >= (1ull << 31)) return sg_fail(ctx, SLAMGPU_E_NOMEM, "window tables too large for 32-bit offsets");
+        ia.win = 1; ia.wl_nxmin = map->wl_nxmin; ia.wl_nymin = map->wl_nymin; ia.wl_pitch = map->wl_pitch; ia.wl_T = (long long)map->wl_T;
+        ia.win_hh = c.spe.win_h / 2.0; ia.win_hv = c.spe.win_v / 2.0;
+      }
       ia.v4 = c.grid_variant >= 4 ? 1 : 0; ia.dmax = dmax; ia.ngys = c.ngys;
       ia.v5 = c.grid_variant == 5 ? 1 : 0; ia.nb = c.nb5; ia.bw = c.bw5; ia.colrec = c.colrec.as<uint4>();
       ia.v3 = c.grid_variant == 3 ? 1 : 0; ia.nbt = c.nbt; ia.box_w = c.box_w; ia.box_h = c.box_h;
@@ -2397,7 +2560,7 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       SG_LAUNCHED(ctx);
     } else if (nblk > 0) {
       GridArgs a;
-      a.lut = map->d_lut[oie]; a.cxp = c.cxp.as<int>(); a.cyp = c.cyp.as<int>(); a.groups = c.groups.as<int4>();
+      a.lut = c.win_mode ? map->d_wlut : map->d_lut[oie]; a.cxp = c.cxp.as<int>(); a.cyp = c.cyp.as<int>(); a.groups = c.groups.as<int4>();
       a.n_groups = c.n_groups; a.nx = c.nx; a.ny = c.ny; a.nyp = c.nyp; a.N = N; a.t_lo = c.t_lo;
       a.w = s->d_w; a.f = s->d_f; a.wsum = s->wsum; a.p0 = c.p0;
       a.scores = c.scores.as<double>(); a.blk = c.blk_best.as<Best>();
@@ -2469,6 +2632,19 @@ static int fetch_impl(slamgpu_ctx *ctx, slamgpu_map *map, double *out_scores, in
     ctx->p2p_broken = true;  // a late message must never be taken for a new one: ncclAllGather from here on
     return sg_fail(ctx, SLAMGPU_E_NCCL, "a peer rank did not deliver its result within %.0f ms (peer-memory exchange; ctx option p2p_timeout_ms)",
                    ctx->p2p_timeout_ms);
+  }
+  if (h->pad > 0 && c.kind == 1 && c.win_mode && map) {
+    // some window spans a cell count outside the two tabulated ones (a corner within an ulp of a cell border): as a list
+    slamgpu_spe_params spe = c.spe;
+    std::vector<double> xs = c.h_xs, ys = c.h_ys, ts = c.h_ts;
+    double init = c.init_score;
+    c.force_list = true;
+    int r = slamgpu_stage_grid(ctx, c.scan, &spe, xs.data(), (int32_t)xs.size(), ys.data(), (int32_t)ys.size(), ts.data(), (int32_t)ts.size());
+    c.force_list = false;
+    SG_TRY(r);
+    SG_TRY(launch_staged(ctx, map, init));
+    SG_CUDA(ctx, cudaMemcpyAsync(h, c.result.as<Result>() + 1, sizeof(Result), cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   while (h->pad > 0 && c.kind == 1 && c.grid_variant > 1 && map) {
     // v4: some thread's 8 y do not fall into consecutive cell rows -> v2; v3: some block's cells did not fit its TMA box

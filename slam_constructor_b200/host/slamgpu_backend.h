@@ -816,17 +816,11 @@ public:
     std::vector<double> probs(observed ? P : 0);
     int64_t idx = -1;
     double best = best_pose_prob;
-    if (prep.params.oope == SLAMGPU_OOPE_OBSTACLE) {
-      _ctx->check(slamgpu_score_grid(_ctx->handle(), prep.map, prep.dscan, &prep.params, xs.data(), (int32_t)xs.size(), ys.data(),
-                                     (int32_t)ys.size(), ts.data(), (int32_t)ts.size(), best_pose_prob,
-                                     observed ? probs.data() : nullptr, &idx, &best));
-    } else {  // window / GMapping OOPEs: the list kernel over the expanded product
-      std::vector<double> flat(P * 3);
-      std::size_t k = 0;
-      for (double t : ts) for (double y : ys) for (double x : xs) { flat[k++] = x; flat[k++] = y; flat[k++] = t; }
-      _ctx->check(slamgpu_score_poses(_ctx->handle(), prep.map, prep.dscan, &prep.params, flat.data(), (int64_t)P, best_pose_prob,
-                                      observed ? probs.data() : nullptr, &idx, &best));
-    }
+    // every OOPE goes through the grid entry point: obstacle / max / mean are tabulated per cell (one gather per evaluation),
+    // overlap and GMapping are expanded to a pose list on the device
+    _ctx->check(slamgpu_score_grid(_ctx->handle(), prep.map, prep.dscan, &prep.params, xs.data(), (int32_t)xs.size(), ys.data(),
+                                   (int32_t)ys.size(), ts.data(), (int32_t)ts.size(), best_pose_prob,
+                                   observed ? probs.data() : nullptr, &idx, &best));
     _poses_tested += P;
     auto pose_at = [&](std::size_t i) {
       const std::size_t nx = xs.size(), ny = ys.size();

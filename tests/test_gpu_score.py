@@ -226,8 +226,8 @@ def test_empty_and_degenerate_inputs(sg, gpu):
     # all-unknown map: every point reads the prototype
     got, idx, _ = gpu.score_poses(gm, gsc, sg.spe_params(), np.array([[0.0, 0.0, 0.0], [100.0, 5.0, 1.0]]))
     assert got[0] == got[1] == 0.5 and idx == 0
-    with pytest.raises(sg.SlamGpuError):
-        gpu.score_grid(gm, gsc, sg.spe_params(sg.OOPE_MAX), [0.0], [0.0], [0.0])
+    with pytest.raises(sg.SlamGpuError):  # a pre-rotated scan carries its theta: no candidate grid over it
+        gpu.score_grid(gm, gsc, sg.spe_params(prerotated=1), [0.0], [0.0], [0.0])
     gm.close(); gsc.close(); empty.close()
 
 
@@ -339,6 +339,41 @@ def test_grid_row_dedupe_kernels_against_the_general_one(sg, gpu):
         pick = rng.choice(len(P), min(len(P), 1500), replace=False)
         assert np.array_equal(got5[pick], om.score(osc, ob.spe_params(), P[pick]))
         gm.close(); gsc.close()
+
+
+@pytest.mark.parametrize("trig", [0, 1])
+@pytest.mark.parametrize("mode,win", [("max", (0.1, 0.1)), ("max", (0.15, 0.1)), ("mean", (0.1, 0.1)), ("mean", (0.12, 0.07)),
+                                      ("mean", (0.26, 0.31)), ("max", (0.0, 0.1)), ("overlap", (0.1, 0.1)), ("gmapping", None)])
+def test_candidate_grid_with_every_oope(sg, gpu, mode, win, trig):
+    """slamgpu_stage_grid with the window OOPEs (occupancy_observation_probability.h:29-99) and the GMapping OOPE: max / mean
+    are scored by the grid kernel out of the map's window LUTs (one gather per evaluation), overlap / GMapping / degenerate
+    windows as a device-expanded pose list; every score against the oracle and against slamgpu_score_poses"""
+    rng = np.random.default_rng(1760 + trig)
+    model = ob.CELL_GMAPPING if mode == "gmapping" else ob.CELL_TBM_CONSISTENT
+    om, gm, osc, gsc, p0 = _setup(sg, gpu, rng, model, 83, spw=ob.SPW_VINY)
+    if mode == "gmapping":
+        po, pg = ob.spe_params(ob.OOPE_GMAPPING, gm_th=0.1, gm_window=1), sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, trig=trig)
+    else:
+        code = dict(max=ob.OOPE_MAX, mean=ob.OOPE_MEAN, overlap=ob.OOPE_OVERLAP)[mode]
+        po, pg = ob.spe_params(code, win_v=win[0], win_h=win[1]), sg.spe_params(code, win_v=win[0], win_h=win[1], trig=trig)
+    xs = p0[0] + 0.02 * (np.arange(41) - 20); ys = p0[1] + 0.02 * (np.arange(29) - 14); ts = p0[2] + 0.01 * (np.arange(5) - 2)
+    # a few candidates far outside the map: windows over unknown cells on every side
+    xs[0] -= 9.0; xs[-1] += 9.0; ys[0] -= 9.0; ys[-1] += 9.0
+    P = np.stack(np.meshgrid(ts, ys, xs, indexing="ij"), -1).reshape(-1, 3)[:, ::-1]
+    want = om.score(osc, po, P)
+    got, idx, best = gpu.score_grid(gm, gsc, pg, xs, ys, ts)
+    st = gpu.score_stats()
+    tabulated = mode in ("max", "mean") and win[0] > 0
+    assert (st["variant"] == 1) if tabulated else (st["variant"] in (0, 3, 4)), st   # grid kernel on the window tables / list kernels
+    if mode == "gmapping":
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    else:
+        assert np.array_equal(got, want)
+        assert idx == int(np.argmax(want)) and best == want[idx]
+    got2, idx2, best2 = gpu.score_poses(gm, gsc, pg, P)
+    assert np.array_equal(got2, got) and (idx2, best2) == (idx, best)
+    assert len(set(np.round(want, 12))) > 100
+    gm.close(); gsc.close()
 
 
 @pytest.mark.parametrize("mode", ["obstacle", "max", "mean", "gmapping"])

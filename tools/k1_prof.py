@@ -22,3 +22,14 @@ for _ in range(n):
     tot += ctx.last_kernel_ms()
 _, idx, best = ctx.score_fetch()
 print("nt", nt, "variant", ctx.score_stats()["variant"], "kernel ms (not a bench value)", tot / n, idx, best)
+if os.environ.get("WIN"):
+    # the same candidate set under the max / mean window OOPEs (0.1 x 0.1 m windows = 3 x 3 cells)
+    for code, name in ((sg.OOPE_MAX, "max"), (sg.OOPE_MEAN, "mean")):
+        pw = sg.spe_params(code, sg.OIE_DISCREPANCY, win_v=0.1, win_h=0.1, trig=sg.TRIG_DEVICE)
+        ctx.stage_grid(scan, pw, wl["xs"], wl["ys"], wl["ts"][:nt])
+        tot = 0.0
+        for _ in range(n):
+            ctx.flush_l2(); ctx.score_launch(gm); ctx.sync(); tot += ctx.last_kernel_ms()
+        _, idx, best = ctx.score_fetch()
+        print("window OOPE", name, "variant", ctx.score_stats()["variant"], "kernel ms (not a bench value)", tot / n, idx, best,
+              "window evals/s", len(wl["xs"]) * len(wl["ys"]) * nt * 1081 / (tot / n * 1e-3))

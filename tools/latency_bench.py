@@ -63,14 +63,15 @@ def pyramid_numbers(ctx, size=4096, scale=0.025):
             "m3rsm_match_us": round(m3, 1), "m3rsm_stats": st}
 
 
-def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=720):
-    """BASELINE configs[3]: 256 particles x 720 beams, each particle with its own map; one batched scan insertion, the hill
-    climbing of all particles (one launch without the OOPE cache; lock step with the cache carried as upstream does)"""
+def particle_numbers(ctx, n=256, size=2560, scale=0.05, beams=720):
+    """BASELINE configs[3]: 256 particles x 720 beams, each particle with its own 2560 x 2560 map (copy-on-write tiles) in a
+    35 x 30 m room; one batched scan insertion, the hill climbing of all particles (one launch without the OOPE cache; with the
+    cache carried as upstream does), one resampling"""
     rng = np.random.default_rng(7)
     parts = sg.Particles(ctx, n, size, size, scale, sg.CELL_GMAPPING, sg.GROW_TILED)
     est = sg.estimator(sg.EST_CONST)
     pose = np.array([0.317, -0.223, 0.1])
-    r, a = bench.room_ranges(rng, beams, 2 * np.pi, size * scale * 0.35, size * scale * 0.3, pose, 0.01)
+    r, a = bench.room_ranges(rng, beams, 2 * np.pi, 17.5, 15.0, pose, 0.01)
     scan = sg.Scan(ctx, r, a)
     poses = pose + rng.normal(0, [0.02, 0.02, 0.01], (n, 3))
     cells = parts.append_scan(scan, poses, est=est)
@@ -80,11 +81,23 @@ def particle_numbers(ctx, n=256, size=1000, scale=0.05, beams=720):
     params_c = sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2)
     hc_c = timeit(lambda: parts.match_hc(scan, params_c, poses), n=5, warm=1)
     _, _, tested = parts.match_hc(scan, params_c, poses)
+    st0 = parts.tile_stats()
+    # a resampling that keeps a third of the particles (two copies of each), then the insertion that un-shares their tiles
+    src = (np.arange(n) // 3 * 3).astype(np.int32)
+    t0 = time.perf_counter(); parts.resample(src); res_us = (time.perf_counter() - t0) * 1e6
+    st1 = parts.tile_stats()
+    t0 = time.perf_counter(); parts.append_scan(scan, poses, est=est); ctx.sync(); first_us = (time.perf_counter() - t0) * 1e6
+    st2 = parts.tile_stats()
     parts.close(); scan.close()
     tot = int(np.sum(cells))
     return {"particles": n, "grid": [size, size], "beams": beams, "append_scan_us": round(upd, 1), "cells_per_step": tot,
             "cell_updates_per_s": tot / (upd * 1e-6), "hill_climb_us": round(hc, 1), "hill_climb_carried_cache_us": round(hc_c, 1),
-            "hill_climb_poses_tested": int(np.sum(tested))}
+            "hill_climb_poses_tested": int(np.sum(tested)),
+            "map_storage": {"kind": "copy-on-write 128x128 tiles" if st0["tiled"] else "dense", "pool_MB": st0["pool_bytes"] / 1e6,
+                            "tiles_live": st0["tiles_live"], "dense_equivalent_MB": n * size * size * 5 * 8 / 1e6},
+            "resample": {"e2e_us": round(res_us, 1), "device_us": st1["resample_us"], "bytes_copied": st1["resample_bytes"],
+                         "tile_references_shared": st1["resample_tiles_shared"],
+                         "first_insertion_after_us": round(first_us, 1), "tiles_cloned_by_it": st2["tiles_cloned"] - st1["tiles_cloned"]}}
 
 
 def measure(ctx):
