@@ -27,6 +27,16 @@ def main():
     P = np.stack(np.meshgrid(wl["ts"][:4], wl["ys"], wl["xs"], indexing="ij"), -1).reshape(-1, 3)[:, ::-1]
     ctx.score_poses(gm, scan, sg.spe_params(), P)           # list kernel (40 804 poses)
     ctx.score_poses(gm, scan, sg.spe_params(), P[:100])     # two-phase small batch
+    # a quarter of the candidate set: the share of one rank of four -> k_score_grid5 (cp.async pipeline)
+    ctx.stage_grid(scan, sg.spe_params(), wl["xs"], wl["ys"], wl["ts"][:25])
+    for _ in range(2):
+        ctx.score_launch(gm)
+    ctx.score_fetch()
+    # the window OOPEs on the grid: window tables (k_build_wlut) + the v1 grid kernel
+    ctx.stage_grid(scan, sg.spe_params(sg.OOPE_MAX, win_v=0.1, win_h=0.1), wl["xs"], wl["ys"], wl["ts"])
+    for _ in range(2):
+        ctx.score_launch(gm)
+    ctx.score_fetch()
     gm.close(); scan.close()
     # K2/K3: configs[1] shape
     gm = sg.GridMap(ctx, 800, 800, 0.05, sg.CELL_TBM_CONSISTENT, sg.GROW_PLAIN)
@@ -58,6 +68,8 @@ def main():
     parts.append_scan(scan, poses)
     parts.match_hc(scan, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1), poses, 6, 0.1, 0.1)            # one launch
     parts.match_hc(scan, sg.spe_params(sg.OOPE_GMAPPING, gm_th=0.1, gm_window=1, gm_cache=2), poses, 6, 0.1, 0.1)  # carried cache: lock step
+    parts.resample((np.arange(n) // 2 * 2).astype(np.int32))   # copy-on-write: table copies ...
+    parts.append_scan(scan, poses)                             # ... and the clones of the tiles this scan writes (k_copy_tiles)
     parts.close(); scan.close(); ctx.close()
     print("exercise: done")
 
