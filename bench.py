@@ -433,8 +433,10 @@ def main():
                                                   "kernel_gathers_per_s": kernel_gathers, "ratio": kernel_gathers / gather_peak,
                                                   "what": "uniformly random 8-byte loads over an L2-resident table of the LUT's "
                                                           "size (slamgpu_probe_gather): gathers that share no sector"},
-                             "note": "algorithmic bytes = 32 B (one sector) per pose-beam evaluation; the map is L2/L1 "
-                                     "resident so frac > 1 means sector reuse, not an error"},
+                             "note": "algorithmic bytes = 32 B (one sector) per pose-beam evaluation (SURVEY 8d); the map is L2/L1 "
+                                     "resident and neighbouring candidates share sectors, so frac > 1 is sector reuse, not an "
+                                     "efficiency: `binding` holds the counters that say what limits the kernel, `traffic` the "
+                                     "DRAM bytes ncu measured for one launch"},
                 "result": {"best_idx": idx0, "best_score": best0, "guard_hits": st["guard_hits"]}}
         line["roofline"]["kernel"] = {4: "k_score_grid4", 5: "k_score_grid5", 2: "k_score_grid2"}.get(st["variant"], "k_score_grid")
         bounds_file = os.path.join(ROOT, "profiles", "r02_k1_bounds.json")
@@ -444,7 +446,12 @@ def main():
                 bd = json.load(open(bounds_file)).get(line["roofline"]["kernel"])
                 if bd:
                     line["roofline"]["traffic"] = bd.get("dram_bytes_per_launch", traffic)
-                    line["roofline"]["binding"] = bd
+                    line["roofline"]["binding"] = dict(bd)
+                    if "floors_ms" in bd and world == 1:
+                        # this run's kernel time against the floors the ncu counters give for the same launch: the largest
+                        # fraction is how close the kernel is to ANY pipe's limit (the 32 B/evaluation figure above is not one)
+                        k_ms = kern_ms / args.steps
+                        line["roofline"]["binding"]["frac_of_floor_this_run"] = {k: v / k_ms for k, v in bd["floors_ms"].items()}
             except ValueError:
                 pass
         if world > 1:

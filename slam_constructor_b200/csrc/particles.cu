@@ -293,6 +293,21 @@ extern "C" int slamgpu_match_hc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan
   return r;
 }
 
+// Every rank of a distributed ctx must leave a collective entry point with the same verdict, or the ranks that went on
+// block forever in the next all-gather: the local status travels to every rank and the first failure wins.
+static int agree_on_status(slamgpu_ctx *ctx, int local_rc) {
+  if (ctx->nranks <= 1) return local_rc;
+  std::vector<int32_t> all((size_t)ctx->nranks, SLAMGPU_OK);
+  all[ctx->rank] = local_rc;
+  SG_TRY(sg_allgather_host(ctx, all.data(), sizeof(int32_t)));
+  for (int r = 0; r < ctx->nranks; ++r)
+    if (all[r] != SLAMGPU_OK) {
+      if (local_rc == SLAMGPU_OK) return sg_fail(ctx, all[r], "rank %d failed in this collective call (its own error string says why)", r);
+      return local_rc;
+    }
+  return SLAMGPU_OK;
+}
+
 extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan *scan, const double *poses,
                                              const uint8_t *do_update, double scan_quality, int32_t scan_margin,
                                              const slamgpu_estimator *est, double blur, double max_range,
@@ -308,13 +323,23 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
   std::vector<int> who;
   for (int i = p->lo; i < p->hi; ++i)
     if (!do_update || do_update[i]) who.push_back(i);
-  std::vector<int64_t> all_counts((size_t)p->chunk * ctx->nranks, 0);
-  auto publish = [&]() -> int {
-    if (ctx->nranks > 1) SG_TRY(sg_allgather_host(ctx, all_counts.data(), sizeof(int64_t) * p->chunk));
-    if (cells_updated) memcpy(cells_updated, all_counts.data(), sizeof(int64_t) * n);
+  // per rank: chunk counts + the rank's status, so one all-gather both publishes the counts and agrees on the verdict
+  const size_t slot = (size_t)p->chunk + 1;
+  std::vector<int64_t> all_counts(slot * ctx->nranks, 0);
+  auto count_of = [&](int i) -> int64_t & { return all_counts[(size_t)p->owner(i) * slot + (size_t)(i - p->owner(i) * p->chunk)]; };
+  auto publish = [&](int local_rc) -> int {
+    all_counts[(size_t)ctx->rank * slot + p->chunk] = local_rc;
+    if (ctx->nranks > 1) SG_TRY(sg_allgather_host(ctx, all_counts.data(), sizeof(int64_t) * slot));
+    for (int r = 0; r < ctx->nranks; ++r) {
+      const int rc_r = (int)all_counts[(size_t)r * slot + p->chunk];
+      if (rc_r == SLAMGPU_OK) continue;
+      if (local_rc != SLAMGPU_OK) return local_rc;
+      return sg_fail(ctx, rc_r, "particles_append_scan failed on rank %d (its own error string says why)", r);
+    }
+    if (cells_updated) for (int i = 0; i < n; ++i) cells_updated[i] = count_of(i);
     return SLAMGPU_OK;
   };
-  if (who.empty()) return publish();
+  if (who.empty()) return publish(SLAMGPU_OK);
   // host beam preparation (libm trig per beam, as the reference computes the end points) on a few threads
   const int m = (int)who.size();
   std::vector<BeamPlan> plans(m);
@@ -334,7 +359,7 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
     for (auto &t : pool) t.join();
   }
   for (int k = 0; k < m; ++k)
-    if (rc[k] != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_INVALID, "particle %d: a beam spans more than 2^26 cells", who[k]);
+    if (rc[k] != SLAMGPU_OK) return publish(sg_fail(ctx, SLAMGPU_E_INVALID, "particle %d: a beam spans more than 2^26 cells", who[k]));
   // batches bounded by the 32-bit (map, cell) key space and 2^30 cell slots
   std::vector<slamgpu_map *> maps;
   std::vector<int64_t> counts;
@@ -351,11 +376,12 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
     maps.clear();
     for (int k = k0; k < k1; ++k) maps.push_back(p->maps[who[k]]);
     counts.assign(k1 - k0, 0);
-    SG_TRY(sg_append_plans(ctx, maps.data(), plans.data() + k0, k1 - k0, est, counts.data(), nullptr));
-    for (int k = k0; k < k1; ++k) all_counts[who[k]] = counts[k - k0];
+    const int arc = sg_append_plans(ctx, maps.data(), plans.data() + k0, k1 - k0, est, counts.data(), nullptr);
+    if (arc != SLAMGPU_OK) return publish(arc);
+    for (int k = k0; k < k1; ++k) count_of(who[k]) = counts[k - k0];
     k0 = k1;
   }
-  return publish();
+  return publish(SLAMGPU_OK);
 }
 
 // ParticleFilter::try_resample's copy step (src/core/particle_filter.h:92-98): particle i becomes a
@@ -378,14 +404,16 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
   cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;
   cudaEventCreate(&ev_r0); cudaEventCreate(&ev_r1);
   cudaEventRecord(ev_r0, ctx->stream);
+  auto leave = [&](int rc) { release_staged(); if (ev_r0) cudaEventDestroy(ev_r0); if (ev_r1) cudaEventDestroy(ev_r1); return rc; };
   p->resample_bytes = 0; p->resample_tiles_shared = 0;
   if (ctx->nranks > 1) {
     geo.assign((size_t)p->chunk * ctx->nranks, Geo{0, 0, 0, 0});
     for (int i = lo; i < hi; ++i) geo[i] = Geo{p->maps[i]->w, p->maps[i]->h, p->maps[i]->ox, p->maps[i]->oy};
-    SG_TRY(sg_allgather_host(ctx, geo.data(), sizeof(Geo) * p->chunk));
+    { int grc = sg_allgather_host(ctx, geo.data(), sizeof(Geo) * p->chunk); if (grc != SLAMGPU_OK) return leave(grc); }
     const int stride = slamgpu_model_stride(p->lo < p->hi ? p->maps[lo]->model : 0);
     std::vector<SgXfer> sends, recvs;
-    for (int i = 0; i < n; ++i) {  // the same order on every rank
+    int stage_rc = SLAMGPU_OK;  // a rank that cannot stage still reaches the agreement below: no peer waits in the exchange
+    for (int i = 0; i < n && stage_rc == SLAMGPU_OK; ++i) {  // the same order on every rank
       const int q = p->owner(src[i]), r = p->owner(i);
       if (q == r) continue;
       if (ctx->rank == q) {
@@ -393,23 +421,25 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
         const size_t bytes = (size_t)m->w * m->h * m->stride * sizeof(double);
         void *cells = m->d_cells;
         if (m->pool) {  // a tiled map travels as the dense array it stands for
-          if (send_staged[i].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) { release_staged(); return sg_fail(ctx, SLAMGPU_E_NOMEM, "resample: send staging for particle %d", i); }
-          int rc2 = sg_map_gather_dense(m, send_staged[i].as<double>());
-          if (rc2 != SLAMGPU_OK) { release_staged(); return rc2; }
+          if (send_staged[i].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) { stage_rc = sg_fail(ctx, SLAMGPU_E_NOMEM, "resample: send staging for particle %d", i); break; }
+          stage_rc = sg_map_gather_dense(m, send_staged[i].as<double>());
+          if (stage_rc != SLAMGPU_OK) break;
           cells = send_staged[i].p;
         }
         sends.push_back(SgXfer{r, cells, bytes});
       } else if (ctx->rank == r) {
         const Geo &g = geo[src[i]];
         const size_t bytes = (size_t)g.w * g.h * stride * sizeof(double);
-        if (staged[i].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) { release_staged(); return sg_fail(ctx, SLAMGPU_E_NOMEM, "resample: staging for particle %d", i); }
+        if (staged[i].reserve(std::max<size_t>(bytes, 16)) != SLAMGPU_OK) { stage_rc = sg_fail(ctx, SLAMGPU_E_NOMEM, "resample: staging for particle %d", i); break; }
         recvs.push_back(SgXfer{q, staged[i].p, bytes});
       }
     }
+    stage_rc = agree_on_status(ctx, stage_rc);
+    if (stage_rc != SLAMGPU_OK) return leave(stage_rc);
     std::string err;
     int rc = sg_nccl_exchange(ctx->comm, sends.data(), (int)sends.size(), recvs.data(), (int)recvs.size(), ctx->stream, &err);
-    if (rc != SLAMGPU_OK) { release_staged(); return sg_fail(ctx, rc, "%s", err.c_str()); }
-    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (rc != SLAMGPU_OK) return leave(sg_fail(ctx, rc, "%s", err.c_str()));
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return leave(sg_fail(ctx, SLAMGPU_E_CUDA, "resample: exchange did not complete"));
   }
   // ---- this rank's particles
   std::vector<slamgpu_map *> next(n, nullptr);
@@ -428,8 +458,10 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
   for (int i = lo; i < hi; ++i)
     if (!taken[i]) spare.push_back(p->maps[i]);
   // local sources first (they are all kept maps), then the staged remote ones
-  for (int pass = 0; pass < 2; ++pass)
-    for (int i = lo; i < hi; ++i) {
+  int copy_rc = SLAMGPU_OK;
+  auto copy_ok = [&](int r) { if (r != SLAMGPU_OK && copy_rc == SLAMGPU_OK) copy_rc = r; return r == SLAMGPU_OK; };
+  for (int pass = 0; pass < 2 && copy_rc == SLAMGPU_OK; ++pass)
+    for (int i = lo; i < hi && copy_rc == SLAMGPU_OK; ++i) {
       if (next[i] || local(src[i]) != (pass == 0)) continue;
       slamgpu_map *to = spare.back();
       spare.pop_back();
@@ -437,34 +469,38 @@ extern "C" int slamgpu_particles_resample(slamgpu_particles *p, const int32_t *s
         slamgpu_map *from = p->maps[src[i]];
         if (to->pool) {
           // copy-on-write: the copy shares every tile of its source (lazy_tiled_grid_map.h:57-71); nothing moves
-          SG_TRY(sg_map_share_tiles(to, from));
+          if (!copy_ok(sg_map_share_tiles(to, from))) break;
           for (int32_t id : from->tile_ids) p->resample_tiles_shared += id != 0;
         } else {
-          SG_TRY(sg_map_realloc(to, from->w, from->h));
+          if (!copy_ok(sg_map_realloc(to, from->w, from->h))) break;
           to->ox = from->ox; to->oy = from->oy;
           const size_t bytes = (size_t)from->w * from->h * from->stride * sizeof(double);
-          SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, from->d_cells, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+          if (cudaMemcpyAsync(to->d_cells, from->d_cells, bytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { copy_ok(sg_fail(ctx, SLAMGPU_E_CUDA, "resample: copy of particle %d", src[i])); break; }
           p->resample_bytes += (int64_t)bytes;
         }
       } else {
         const Geo &g = geo[src[i]];
-        SG_TRY(sg_map_realloc(to, g.w, g.h));
+        if (!copy_ok(sg_map_realloc(to, g.w, g.h))) break;
         to->ox = g.ox; to->oy = g.oy;
         const size_t bytes = (size_t)g.w * g.h * to->stride * sizeof(double);
-        if (to->pool) SG_TRY(sg_map_scatter_dense(to, staged[i].as<double>()));
-        else SG_CUDA(ctx, cudaMemcpyAsync(to->d_cells, staged[i].p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (to->pool) { if (!copy_ok(sg_map_scatter_dense(to, staged[i].as<double>()))) break; }
+        else if (cudaMemcpyAsync(to->d_cells, staged[i].p, bytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { copy_ok(sg_fail(ctx, SLAMGPU_E_CUDA, "resample: copy into particle %d", i)); break; }
         p->resample_bytes += (int64_t)bytes;
       }
       sg_map_invalidate_lut(to);
       next[i] = to;
     }
   cudaEventRecord(ev_r1, ctx->stream);
-  SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) copy_ok(sg_fail(ctx, SLAMGPU_E_CUDA, "resample: copies did not complete"));
+  // every rank learns whether every rank's copies went through before the estimator states are exchanged
+  copy_rc = agree_on_status(ctx, copy_rc);
+  if (copy_rc != SLAMGPU_OK) return leave(copy_rc);
   {
     float ms = 0;
     if (ev_r0 && ev_r1 && cudaEventElapsedTime(&ms, ev_r0, ev_r1) == cudaSuccess) p->resample_ms = ms;
     if (ev_r0) cudaEventDestroy(ev_r0);
     if (ev_r1) cudaEventDestroy(ev_r1);
+    ev_r0 = ev_r1 = nullptr;
   }
   release_staged();
   p->maps.swap(next);
