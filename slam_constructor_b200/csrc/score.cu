@@ -1520,12 +1520,12 @@ SG_DEV double lds_f64(unsigned addr) {
 
 #define SG_G5_STAGE 512u  // bytes per stage: 32 lanes x 16
 #define SG_G5_ROW 112u    // bytes per patch row in a stage: 7 pairs
-#define SG_G5_STAGES 8    // ring depth (power of two, > SG_G5_P + SG_G5_Q)
-#define SG_G5_P 4         // the patch (and weight) of a beam is copied this many beams ahead of its use
-#define SG_G5_Q 3         // ... and its index records this many beams ahead of the patch copy that needs them
+#define SG_G5_STAGES 16   // ring depth (power of two, > SG_G5_P + SG_G5_Q)
+#define SG_G5_P 8         // the patch (and weight) of a beam is copied this many beams ahead of its use
+#define SG_G5_Q 7         // ... and its index records this many beams ahead of the patch copy that needs them
 
 template <int DMAX, bool UNIW>
-__global__ void __launch_bounds__(64, 18) k_score_grid5(GridArgs5 a) {
+__global__ void __launch_bounds__(64, 13) k_score_grid5(GridArgs5 a) {
   __shared__ __align__(16) unsigned char ring[2][SG_G5_STAGES * SG_G5_STAGE];
   const int lane = (int)(threadIdx.x & 31), wib = (int)(threadIdx.x >> 5);
   int w = (int)blockIdx.x * 2 + wib;
@@ -1568,9 +1568,9 @@ __global__ void __launch_bounds__(64, 18) k_score_grid5(GridArgs5 a) {
 #pragma unroll
   for (int m = 0; m < 8; ++m) acc[m] = 0.0;
 
-  // The copy of iteration m goes to slot m & 7 and carries {patch(m+P), weight(m+P), index records of beam m+P+Q}; negative
-  // m are the prologue.  Iteration i reads: the records of beam i+P (slot (i-Q) & 7) to address the patch it requests, the
-  // patch and weight of beam i (slot (i-P) & 7), and the column nibble / new-row mask of beam i (slot (i-P-Q) & 7, still
+  // The copy of iteration m goes to slot m % STAGES and carries {patch(m+P), weight(m+P), index records of beam m+P+Q}; negative
+  // m are the prologue.  Iteration i reads: the records of beam i+P (slot (i-Q) % STAGES) to address the patch it requests, the
+  // patch and weight of beam i (slot (i-P) % STAGES), and the column nibble / new-row mask of beam i (slot (i-P-Q) % STAGES, still
   // alive because the ring is deeper than P+Q).
   // ---- prologue 1: the records of beams 0 .. P+Q-1 (iterations -P-Q .. -1), nothing else
 #pragma unroll
@@ -1593,30 +1593,56 @@ __global__ void __launch_bounds__(64, 18) k_score_grid5(GridArgs5 a) {
     cp_async_commit();
   }
 
-  // ---- beam loop
-  unsigned sw_ = 0;  // stage offset of slot i & 7
+  // ---- beam loop, software-pipelined through registers: iteration i adds beam i out of values it loaded from the ring
+  // during iteration i-1 and meanwhile loads beam i+1's (the LDS -> FP64 -> indexed-branch chain of a lone warp was ~300
+  // cycles per beam; with the loads a beam ahead only the arithmetic is left on it)
+  cp_async_wait<SG_G5_P - 1>();  // the patch of beam 0 has landed
+  __syncwarp();
+  constexpr unsigned ST = SG_G5_STAGE;
+  unsigned sw_ = 0;  // stage offset of slot i % STAGES
+  // slots relative to sw_: patch / weight of beam i+k at sw_ + (k-P)*ST, records of beam i+k at sw_ + (k-P-Q)*ST
+  unsigned msk_cur = lds32(rw_addr + 4u + ((sw_ - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
+  unsigned nibw_next = lds32(nib_addr + ((sw_ + ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
+  double t_cur[DMAX], wi_cur = w0;
+  {
+    const unsigned nibw0 = lds32(nib_addr + ((sw_ - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
+    const unsigned s_val = (sw_ - SG_G5_P * ST) & ring_mask;
+    const unsigned va = ring_w + s_val + ((nibw0 >> nib_shift) & 15u) * 8u;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) t_cur[d] = lds_f64(va + d * SG_G5_ROW);
+    if (!UNIW) wi_cur = lds_f64(ring_w + 31u * 16u + s_val);
+  }
 #pragma unroll 1
   for (int i = 0; i < N; ++i) {
-    cp_async_wait<SG_G5_Q - 1>();  // all copies but the last Q-1 have landed: iterations <= i-Q
+    cp_async_wait<SG_G5_Q - 1>();  // all copies but the last Q-1 have landed: iterations <= i-Q (patch of beam i+1 included)
     __syncwarp();
-    const unsigned s_adr = (sw_ - SG_G5_Q * SG_G5_STAGE) & ring_mask;                  // records of beam i+P
-    const unsigned s_val = (sw_ - SG_G5_P * SG_G5_STAGE) & ring_mask;                  // patch, weight of beam i
-    const unsigned s_cur = (sw_ - (SG_G5_P + SG_G5_Q) * SG_G5_STAGE) & ring_mask;      // records of beam i
+    // (a) beam i+1: its patch values and weight into registers
+    const unsigned s_nxt = (sw_ + ST - SG_G5_P * ST) & ring_mask;
+    const unsigned va = ring_w + s_nxt + ((nibw_next >> nib_shift) & 15u) * 8u;
+    double t_next[DMAX], wi_next = w0;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) t_next[d] = lds_f64(va + d * SG_G5_ROW);
+    if (!UNIW) wi_next = lds_f64(ring_w + 31u * 16u + s_nxt);
+    // (b) records: column nibbles of beam i+2, new-row mask of beam i+1, patch address of beam i+P
+    const unsigned nibw_nn = lds32(nib_addr + ((sw_ + 2u * ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
+    const unsigned msk_next = lds32(rw_addr + 4u + ((sw_ + ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
+    const unsigned s_adr = (sw_ - SG_G5_Q * ST) & ring_mask;
     const unsigned col0 = lds32(ring_w + 28u * 16u + s_adr);
     const uint2 rw = lds64(rw_addr + s_adr);
-    const unsigned nibw = lds32(nib_addr + s_cur);
-    const unsigned msk = lds32(rw_addr + 4u + s_cur);
+    // (c) this iteration's copy: patch + weight of beam i+P, records of beam i+P+Q
     const unsigned u = is_patch ? rw.x + col0 : uidx;
     uidx += inc;
     cp_async16(my_chunk + sw_, base + (size_t)u * 8u, true);
     cp_async_commit();
-    const unsigned va = ring_w + s_val + ((nibw >> nib_shift) & 15u) * 8u;
-    const double wi = UNIW ? w0 : lds_f64(ring_w + 31u * 16u + s_val);
+    // (d) beam i out of registers
     double t[DMAX];
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(lds_f64(va + d * SG_G5_ROW), wi);
-    add_pattern<DMAX>(msk, acc, t);
-    sw_ = (sw_ + SG_G5_STAGE) & ring_mask;
+    for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(t_cur[d], wi_cur);
+    add_pattern<DMAX>(msk_cur, acc, t);
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) t_cur[d] = t_next[d];
+    wi_cur = wi_next; msk_cur = msk_next; nibw_next = nibw_nn;
+    sw_ = (sw_ + ST) & ring_mask;
   }
   cp_async_wait<0>();
 
@@ -1937,7 +1963,7 @@ int upload_host_trig(slamgpu_ctx *ctx, Candidates &c, const std::vector<double> 
 }
 
 #define SG_LIST_MAX_TABLE_BYTES (1ull << 30)
-#define SG_IDX_SLACK 8  // zeroed beam rows behind the grid index tables (k_score_grid4 prefetches past the last beam)
+#define SG_IDX_SLACK 16  // zeroed beam rows behind the grid index tables (k_score_grid4 prefetches past the last beam)
 
 }  // namespace
 
