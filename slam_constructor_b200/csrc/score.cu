@@ -982,7 +982,11 @@ SG_DEV int grid_axis_cell(double v, double rc, double scale, double inv_scale, i
   return c;
 }
 
+// MODE: bit 0 window tables, 1 packed row words (v2+), 2 TMA block patches (v3), 3 row de-duplication (v4 / v5), 4 column
+// records (v5) -- compile-time so that the per-item loops carry no mode tests
+template <int MODE>
 __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) {
+  constexpr bool M_WIN = (MODE & 1) != 0, M_V2 = (MODE & 2) != 0, M_V3 = (MODE & 4) != 0, M_V4 = (MODE & 8) != 0, M_V5 = (MODE & 16) != 0;
   // grid = (ceil(N / SG_IDX_PAIRS), nt_loc): each block handles SG_IDX_PAIRS beams of one theta; a thread
   // owns one axis value (an x or a y) and walks the beams, so the axis value is loaded once
   extern __shared__ int sh_rows[];  // [SG_IDX_PAIRS][ny] padded LUT rows (v2 packing)
@@ -1001,14 +1005,14 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
   __syncthreads();
   bool unsafe_any = false;
   const long long ti0 = (long long)tl * a.N + i0;
-  const int ny_items = a.v2 ? a.ny : a.nyp;
+  const int ny_items = M_V2 ? a.ny : a.nyp;
   for (int c = threadIdx.x; c < a.nx + ny_items; c += blockDim.x) {
     if (c < a.nx) {
       const double x = a.xs[c];
       int *dst = a.cxp + ti0 * a.nx + c;
       for (int pr = 0; pr < np; ++pr) {
         const double rc = sh_rc[pr];
-        if (a.win) {
+        if (M_WIN) {
           // window_probability (dev_window.cuh): lx = floor((X - hh) / s), rx = floor((X + hh) / s), x outer loop
           const double X = sg::add(x, rc);
           const int lx = grid_axis_cell(sg::sub(X, a.win_hh), rc, a.scale, inv_scale, a.guard, &unsafe_any);
@@ -1021,16 +1025,16 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
         }
         const int cx = grid_axis_cell(sg::add(x, rc), rc, a.scale, inv_scale, a.guard, &unsafe_any);
         const int col = clampi(cx + a.ox, -1, a.w) + SG_LUT_PAD;
-        if (a.v5) sh_rows[SG_IDX_PAIRS * a.ny + pr * a.nx + c] = col;
+        if (M_V5) sh_rows[SG_IDX_PAIRS * a.ny + pr * a.nx + c] = col;
         else dst[(size_t)pr * a.nx] = col;
-        if (a.v3) { atomicMin(&sh_xmin[pr], col); atomicMax(&sh_xmax[pr], col); }
+        if (M_V3) { atomicMin(&sh_xmin[pr], col); atomicMax(&sh_xmax[pr], col); }
       }
     } else {
       const int k = c - a.nx;
       const double y = k < a.ny ? a.ys[k] : 0.0;
       for (int pr = 0; pr < np; ++pr) {
         int prow = 0;  // v1 padding rows point at the ring row 0 (always valid memory)
-        if (a.win) {
+        if (M_WIN) {
           int enc = 0;
           if (k < a.ny) {
             const double rs = sh_rs[pr];
@@ -1050,18 +1054,18 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
           const int cy = grid_axis_cell(sg::add(y, rs), rs, a.scale, inv_scale, a.guard, &unsafe_any);
           prow = clampi(cy + a.oy, -1, a.h) + SG_LUT_PAD;
         }
-        if (a.v2) sh_rows[pr * a.ny + k] = prow;
+        if (M_V2) sh_rows[pr * a.ny + k] = prow;
         else a.cyp[(ti0 + pr) * a.nyp + k] = prow * a.pitch;
       }
     }
   }
-  if (a.v2) {
+  if (M_V2) {
     __syncthreads();
     for (int e = threadIdx.x; e < np * a.ngy; e += blockDim.x) {
       const int pr = e / a.ngy, gy = e - pr * a.ngy;
       const int *rows = sh_rows + pr * a.ny;
       const int k0 = gy * a.R;
-      if (a.v4) {
+      if (M_V4) {
         // k_score_grid4: rows of the group must be base, base + 1, ... (steps of 0 or 1, fewer than dmax distinct ones)
         unsigned mask = 0;
         int prev4 = rows[k0], distinct = 1;
@@ -1090,7 +1094,7 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
       }
       a.cyw[(ti0 + pr) * a.ngy + gy] = word;
     }
-    if (a.v5) {
+    if (M_V5) {
       // k_score_grid5: one record per band of <= 30 consecutive x; a band's 14-column window must hold all its columns
       const int *cols_all = sh_rows + SG_IDX_PAIRS * a.ny;
       for (int e = threadIdx.x; e < np * a.nb; e += blockDim.x) {
@@ -1112,7 +1116,7 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
         dst[1] = make_uint4(nib[0], nib[1], nib[2], nib[3]);
       }
     }
-    if (a.v3) {
+    if (M_V3) {
       for (int e = threadIdx.x; e < np * a.nbt; e += blockDim.x) {
         const int pr = e / a.nbt, b = e - pr * a.nbt;
         const int *rows = sh_rows + pr * a.ny;
@@ -2501,7 +2505,16 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
       {
         const size_t shm = c.grid_v2 ? sizeof(int) * SG_IDX_PAIRS * ((size_t)c.ny + (c.grid_variant == 5 ? c.nx : 0)) : 0;
         dim3 grd((unsigned)((N + SG_IDX_PAIRS - 1) / SG_IDX_PAIRS), (unsigned)nt_loc);
-        k_grid_indices<<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia);
+        const int mode = (ia.win ? 1 : 0) | (ia.v2 ? 2 : 0) | (ia.v3 ? 4 : 0) | (ia.v4 ? 8 : 0) | (ia.v5 ? 16 : 0);
+        switch (mode) {
+          case 0: k_grid_indices<0><<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia); break;
+          case 1: k_grid_indices<1><<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia); break;
+          case 2: k_grid_indices<2><<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia); break;
+          case 6: k_grid_indices<6><<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia); break;
+          case 10: k_grid_indices<10><<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia); break;
+          case 26: k_grid_indices<26><<<grd, SG_IDX_THREADS, shm, ctx->stream>>>(ia); break;
+          default: return sg_fail(ctx, SLAMGPU_E_STATE, "grid index kernel: unexpected mode %d", mode);
+        }
       }
       SG_LAUNCHED(ctx);
     }
@@ -3090,7 +3103,7 @@ extern "C" int slamgpu_match_mc(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan
 #define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
 void sg_preload_score() {
   SG_TOUCH((k_score_grid2<8, false, true>)); SG_TOUCH((k_score_grid2<8, false, false>)); SG_TOUCH((k_score_grid2<4, false, true>));
-  SG_TOUCH((k_score_grid2<2, false, true>)); SG_TOUCH(k_grid_indices); SG_TOUCH(k_trig_table); SG_TOUCH(k_reduce_blocks); SG_TOUCH(k_finalize);
+  SG_TOUCH((k_score_grid2<2, false, true>)); SG_TOUCH(k_grid_indices<0>); SG_TOUCH(k_grid_indices<1>); SG_TOUCH(k_grid_indices<2>); SG_TOUCH(k_grid_indices<6>); SG_TOUCH(k_grid_indices<10>); SG_TOUCH(k_grid_indices<26>); SG_TOUCH(k_trig_table); SG_TOUCH(k_reduce_blocks); SG_TOUCH(k_finalize);
   SG_TOUCH((k_score_list<SLAMGPU_OOPE_OBSTACLE, false, true, false>)); SG_TOUCH((k_point_terms<SLAMGPU_OOPE_OBSTACLE, false, true, false>));
   SG_TOUCH((k_pose_sums<false, false>)); SG_TOUCH((k_pose_sums_chained<false>));
   SG_TOUCH((k_small_fused<SLAMGPU_OOPE_OBSTACLE, false, false>)); SG_TOUCH((k_small_fused<SLAMGPU_OOPE_GMAPPING, false, false>));
