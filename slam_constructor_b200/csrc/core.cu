@@ -253,7 +253,7 @@ extern "C" int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_
     ctx->p2p_timeout_ms = (double)value;
     return SLAMGPU_OK;
   }
-  if (strcmp(name, "warm_l2") == 0) {  // experiment: 0 = no L2 warm-up of the score LUT before big grid launches
+  if (strcmp(name, "warm_l2") == 0) {  // experiment: 1 = stream the score LUT through L2 (side stream) before big grid launches
     ctx->cand.warm_l2 = value != 0;
     return SLAMGPU_OK;
   }

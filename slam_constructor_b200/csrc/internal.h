@@ -72,7 +72,8 @@ struct Candidates {  // a staged candidate set (device resident)
   bool uniform_w = false;
   int64_t shape_key[8] = {0};  // shape of the last grid staging (see slamgpu_stage_grid)
   bool shape_valid = false;
-  bool warm_l2 = true;    // stream the score LUT through L2 before a big grid launch (slamgpu_ctx_set_option "warm_l2")
+  bool warm_l2 = false;   // stream the score LUT through L2 before a big grid launch (slamgpu_ctx_set_option "warm_l2"; off: measured
+                          // 10 us slower per step than letting the scoring kernel pull the LUT in itself)
   // K6: every pose scored against its own particle's map
   bool multi = false;
   DevBuf views, view_id;

@@ -89,6 +89,19 @@ __global__ void k_finalize(const Result *__restrict__ per_rank, int nranks, doub
   out->score = s; out->idx = i; out->guard = guard; out->pad = enc;
 }
 
+// one rank: k_reduce_blocks and k_finalize in one launch (thread 0 holds the reduced result and applies the accept rule)
+__global__ void __launch_bounds__(1024) k_reduce_finalize(const Best *__restrict__ blk, int n, Result *res, double init_score, Result *out) {
+  double s = -INFINITY;
+  long long i = LLONG_MAX;
+  for (int k = threadIdx.x; k < n; k += blockDim.x)
+    if (beats(blk[k].score, blk[k].idx, s, i)) { s = blk[k].score; i = blk[k].idx; }
+  block_argmax(s, i, reinterpret_cast<Best *>(res));
+  if (threadIdx.x != 0) return;
+  s = res->score; i = res->idx;  // written by this thread
+  if (!(init_score < s) || i == LLONG_MAX) { s = init_score; i = -1; }
+  out->score = s; out->idx = i; out->guard = res->guard; out->pad = res->pad;
+}
+
 // The same merge fused with the exchange: instead of ncclAllGather + k_finalize, lane r of one warp stores this
 // rank's result straight into rank r's mailbox (a peer mapping over NVLink; slot = this rank, double-buffered by the
 // parity of the call number), publishes it with a system-scope fence + sequence number, then waits for rank r's result
@@ -919,6 +932,7 @@ struct GridIdxArgs {
   const double *trc, *trs;  // [t*N + i]
   const double *xs, *ys;
   int nx, ny, nyp, N, t_lo, nt_loc;
+  const double *thetas, *range, *angle;  // device trig: r*cos(theta + a), r*sin(theta + a) computed in the kernel (NULL: trc / trs hold a host table)
   int w, h, ox, oy, pitch;
   double scale;
   int guard;
@@ -998,9 +1012,16 @@ __global__ void __launch_bounds__(SG_IDX_THREADS) k_grid_indices(GridIdxArgs a) 
   const int np = min(SG_IDX_PAIRS, a.N - i0);
   const double inv_scale = 1.0 / a.scale;
   if (threadIdx.x < np) {
-    const long long src = (long long)(a.t_lo + tl) * a.N + i0 + threadIdx.x;
-    sh_rc[threadIdx.x] = a.trc[src];
-    sh_rs[threadIdx.x] = a.trs[src];
+    if (a.thetas) {  // device trig: what k_trig_table computes, here (one launch and one table round trip less)
+      double sn, cs;
+      sincos(sg::add(a.thetas[a.t_lo + tl], a.angle[i0 + threadIdx.x]), &sn, &cs);
+      sh_rc[threadIdx.x] = sg::mul(a.range[i0 + threadIdx.x], cs);
+      sh_rs[threadIdx.x] = sg::mul(a.range[i0 + threadIdx.x], sn);
+    } else {         // libm table from the host
+      const long long src = (long long)(a.t_lo + tl) * a.N + i0 + threadIdx.x;
+      sh_rc[threadIdx.x] = a.trc[src];
+      sh_rs[threadIdx.x] = a.trs[src];
+    }
   }
   __syncthreads();
   bool unsafe_any = false;
@@ -2460,8 +2481,8 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
     }
     const int nt_loc = c.t_hi - c.t_lo + 1;
     // big sets: make the score LUT L2-resident while the trig / index kernels run (side stream)
-    static const bool env_warm = [] { const char *e = getenv("SLAMGPU_WARM_L2"); return !e || atoi(e) != 0; }();
-    const bool warm = (long long)Ploc * N >= (1ll << 26) && c.warm_l2 && env_warm && !c.win_mode;
+    static const int env_warm = [] { const char *e = getenv("SLAMGPU_WARM_L2"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool warm = (long long)Ploc * N >= (1ll << 26) && (env_warm >= 0 ? env_warm == 1 : c.warm_l2) && !c.win_mode;
     if (warm) {
       const size_t lut_bytes = (size_t)map->pitch * (map->h + 2 * SG_LUT_PAD) * sizeof(double);
       if (lut_bytes <= (96ull << 20)) {
@@ -2473,19 +2494,12 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
         SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
       }
     }
-    if (device_trig && N > 0) {
-      // only the theta planes of this rank's slice (the table is indexed by the global theta number)
-      long long tot = (long long)nt_loc * N;
-      k_trig_table<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(c.p_ts + c.t_lo, nt_loc, s->d_range, s->d_angle, N, N, 1,
-                                                                            c.trc.as<double>() + (size_t)c.t_lo * N,
-                                                                            c.trs.as<double>() + (size_t)c.t_lo * N);
-      SG_LAUNCHED(ctx);
-    }
     long long threads = (long long)c.n_groups * c.nx;
     nblk = (int)((threads + 127) / 128);
     if (nblk > 0 && N > 0) {
       GridIdxArgs ia;
       ia.trc = c.trc.as<double>(); ia.trs = c.trs.as<double>(); ia.xs = c.p_xs; ia.ys = c.p_ys;
+      ia.thetas = device_trig ? c.p_ts : nullptr; ia.range = s->d_range; ia.angle = s->d_angle;
       ia.nx = c.nx; ia.ny = c.ny; ia.nyp = c.nyp; ia.N = N; ia.t_lo = c.t_lo; ia.nt_loc = nt_loc;
       ia.w = map->w; ia.h = map->h; ia.ox = map->ox; ia.oy = map->oy; ia.pitch = map->pitch; ia.scale = map->scale;
       ia.guard = device_trig ? 1 : 0;
@@ -2615,6 +2629,16 @@ int launch_staged(slamgpu_ctx *ctx, slamgpu_map *map, double init_score) {
   // per-rank best -> res[1] (keeps the guard counter accumulated in res[0].guard)
   Result *local = res + 1;
   const bool p2p = ctx->nranks > 1 && ctx->d_peer_mailbox && !ctx->p2p_broken;
+  if (nblk > 0 && ctx->nranks == 1) {
+    k_reduce_finalize<<<1, 1024, 0, ctx->stream>>>(c.blk_best.as<Best>(), nblk, res, init_score, local);
+    SG_LAUNCHED(ctx);
+    SG_CUDA(ctx, cudaGetLastError());
+    c.stats[6] = 0;
+    c.launched = true;
+    c.init_score = init_score;
+    c.last_map = map;
+    return SLAMGPU_OK;
+  }
   if (nblk > 0 && !p2p) {
     k_reduce_blocks<<<1, 1024, 0, ctx->stream>>>(c.blk_best.as<Best>(), nblk, res);
     SG_LAUNCHED(ctx);
