@@ -199,6 +199,8 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   for (DevBuf *b : bufs) b->release();
   for (DevBuf &b : ctx->scratch) b.release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evk0);

@@ -108,6 +108,8 @@ struct slamgpu_ctx {
   unsigned long long p2p_seq = 0;
   int *d_p2p_status = nullptr;     // set by the kernel when a peer did not answer in time
   bool p2p_broken = false;         // after a timeout: results go through ncclAllGather
+  void *h_slots = nullptr, *h_counters = nullptr;  // small pinned blocks of the scan insertion (map slots up, cell counts down)
+  size_t h_slots_cap = 0, h_counters_cap = 0;
   double p2p_timeout_ms = 20000.0; // slamgpu_ctx_set_option("p2p_timeout_ms")
   double clock_hz = 1.965e9;       // SM clock (cudaDevAttrClockRate) for clock64 deadlines
   cudaStream_t side = nullptr;  // the robot cell's update chain runs here, next to the sort (mapping.cu)

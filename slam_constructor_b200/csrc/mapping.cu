@@ -891,14 +891,38 @@ double est_shift(const slamgpu_estimator &e, double scale, const BeamPlan &plan)
 // K2 for prepared beams (one or several maps): fills scratch[0] (beams), [1] (offsets), [2] (cells), [3] (BeamOut),
 // scratch[7] (MapSlot array, px/py valid; dims are refreshed after the growth check)
 int run_raycast_multi(slamgpu_ctx *ctx, double scale, const BeamRec *beams, int N, const long long *offsets,
-                      long long M, const std::vector<MapSlot> &slots, const slamgpu_estimator &est) {
-  SG_TRY(upload_async(ctx, ctx->scratch[0], beams, sizeof(BeamRec) * N));
-  SG_TRY(upload_async(ctx, ctx->scratch[1], offsets, sizeof(long long) * (N + 1)));
-  // scratch[7]: MapSlot[n] | counters[2n]
+                      long long M, const std::vector<MapSlot> &slots, const slamgpu_estimator &est, bool beams_pinned = false) {
+  // scratch[7]: MapSlot[n] | counters[2n] (zeroed by the same copy)
   const size_t coff = map_counters_offset(slots.size());
-  if (ctx->scratch[7].reserve(coff + 16 * slots.size()) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "map slots");
-  SG_TRY(upload_async(ctx, ctx->scratch[7], slots.data(), sizeof(MapSlot) * slots.size()));
-  SG_CUDA(ctx, cudaMemsetAsync((char *)ctx->scratch[7].p + coff, 0, 16 * slots.size(), ctx->stream));
+  const size_t slot_bytes = coff + 16 * slots.size();
+  const size_t bb = (sizeof(BeamRec) * (size_t)N + 63) & ~(size_t)63, ob = (sizeof(long long) * ((size_t)N + 1) + 63) & ~(size_t)63;
+  if (ctx->scratch[0].reserve(std::max<size_t>(sizeof(BeamRec) * N, 16)) != SLAMGPU_OK ||
+      ctx->scratch[1].reserve(sizeof(long long) * ((size_t)N + 1)) != SLAMGPU_OK || ctx->scratch[7].reserve(slot_bytes) != SLAMGPU_OK)
+    return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast inputs");
+  // everything goes up from pinned memory (a copy from pageable memory is staged by the driver, ~8 us apiece): the slot
+  // block always, beams and offsets unless the caller already assembled them in the ctx's pinned block
+  void *hp;
+  if (beams_pinned) {
+    if (ctx->h_slots_cap < slot_bytes) {
+      if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+      ctx->h_slots = nullptr; ctx->h_slots_cap = 0;
+      SG_CUDA(ctx, cudaMallocHost(&ctx->h_slots, slot_bytes * 2));
+      ctx->h_slots_cap = slot_bytes * 2;
+    }
+    hp = ctx->h_slots;
+  } else {
+    SG_TRY(sg_pinned(ctx, bb + ob + slot_bytes, &hp));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging may still be in flight
+    if (N) memcpy(hp, beams, sizeof(BeamRec) * N);
+    memcpy((char *)hp + bb, offsets, sizeof(long long) * ((size_t)N + 1));
+    beams = (const BeamRec *)hp; offsets = (const long long *)((char *)hp + bb);
+    hp = (char *)hp + bb + ob;
+  }
+  memset(hp, 0, slot_bytes);
+  memcpy(hp, slots.data(), sizeof(MapSlot) * slots.size());
+  if (N) SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0].p, beams, sizeof(BeamRec) * N, cudaMemcpyHostToDevice, ctx->stream));
+  SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[1].p, offsets, sizeof(long long) * ((size_t)N + 1), cudaMemcpyHostToDevice, ctx->stream));
+  SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[7].p, hp, slot_bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (ctx->scratch[2].reserve(std::max<size_t>(M, 1) * sizeof(int2)) != SLAMGPU_OK ||
       ctx->scratch[3].reserve(std::max<size_t>(N, 1) * sizeof(BeamOut)) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast buffers (%lld slots)", M);
@@ -1030,9 +1054,18 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     beams_ptr = all_beams; offs_ptr = all_offs;
   }
   std::vector<MapSlot> slots(n);
-  // Shift_Amount per map, exactly as one call per map would fix it
-  for (int k = 0; k < n; ++k) slots[k] = slot_of(maps[k], plans[k].px, plans[k].py, est_shift(*est, maps[0]->scale, plans[k]), 0);
-  SG_TRY(run_raycast_multi(ctx, maps[0]->scale, beams_ptr, N, offs_ptr, M, slots, *est));
+  // Shift_Amount per map, exactly as one call per map would fix it; key bases and beam ranges as far as they are known
+  // (growth and copy-on-write below may still change a map: then the slots go up a second time)
+  {
+    unsigned long long kb = 0;
+    for (int k = 0; k < n; ++k) {
+      slots[k] = slot_of(maps[k], plans[k].px, plans[k].py, est_shift(*est, maps[0]->scale, plans[k]), (unsigned)std::min<unsigned long long>(kb, 0xFFFFFFFFull));
+      slots[k].beam_begin = (int)beam0[k]; slots[k].beam_end = (int)beam0[k + 1];
+      kb += (unsigned long long)maps[k]->w * maps[k]->h;
+    }
+  }
+  const std::vector<MapSlot> slots_sent = slots;
+  SG_TRY(run_raycast_multi(ctx, maps[0]->scale, beams_ptr, N, offs_ptr, M, slots, *est, n > 1));
 
   // ---- map growth (Q9): only when some beam leaves a map's current bounds; replays the reference's
   // ensure_inside sequence over that map's cells in update order
@@ -1091,7 +1124,18 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     key_total += (unsigned long long)maps[k]->w * maps[k]->h;
   }
   if (key_total >= 0xFFFFFFFFull) return sg_fail(ctx, SLAMGPU_E_NOMEM, "maps too large for 32-bit cell keys (%llu cells): insert in smaller batches", key_total);
-  SG_TRY(upload_async(ctx, ctx->scratch[7], slots.data(), sizeof(MapSlot) * n));
+  if (memcmp(slots.data(), slots_sent.data(), sizeof(MapSlot) * n) != 0) {  // a map grew or cloned tiles since the first upload
+    if (ctx->h_slots_cap < sizeof(MapSlot) * n) {
+      if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+      ctx->h_slots = nullptr; ctx->h_slots_cap = 0;
+      SG_CUDA(ctx, cudaMallocHost(&ctx->h_slots, sizeof(MapSlot) * n * 2));
+      ctx->h_slots_cap = sizeof(MapSlot) * n * 2;
+    } else {
+      SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the first upload may still read the block
+    }
+    memcpy(ctx->h_slots, slots.data(), sizeof(MapSlot) * n);
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[7].p, ctx->h_slots, sizeof(MapSlot) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
 
   // ---- K3a: per-slot AOO + sort keys
   DevBuf &slotbuf = ctx->scratch[4];
@@ -1175,8 +1219,14 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   if (robot_split) SG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   for (int k = 0; k < n; ++k)
     if (plans[k].M > 0) sg_map_invalidate_lut(maps[k]);
-  std::vector<unsigned long long> h_counters((size_t)n * 2);
-  SG_CUDA(ctx, cudaMemcpyAsync(h_counters.data(), counters, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->h_counters_cap < (size_t)n * 16) {
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    ctx->h_counters = nullptr; ctx->h_counters_cap = 0;
+    SG_CUDA(ctx, cudaMallocHost(&ctx->h_counters, (size_t)n * 32));
+    ctx->h_counters_cap = (size_t)n * 32;
+  }
+  unsigned long long *h_counters = (unsigned long long *)ctx->h_counters;
+  SG_CUDA(ctx, cudaMemcpyAsync(h_counters, counters, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
   SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (cells_updated) for (int k = 0; k < n; ++k) cells_updated[k] = (int64_t)h_counters[2 * k];
   if (trace) {
