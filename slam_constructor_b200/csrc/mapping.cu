@@ -588,6 +588,8 @@ struct RobotArgs {
   const double *aoo_p, *aoo_q; // per slot: the occupancy estimate
   int stride, model;
   int ring;                    // half size W of the window of cells around the robot handled here (0: the robot cell only)
+  double *trace_impact, *trace_rec;  // pyramid: per slot, impact and record right after the update (NULL: none)
+  int trace_oie;
 };
 
 // One warp per cell of the (2W+1)^2 window around the robot of each map.  A ray is monotone in x and y, so it can only
@@ -646,6 +648,14 @@ __global__ void __launch_bounds__(128) k_apply_ring(RobotArgs a) {
       else
         sg::cell_update(a.model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
                         __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l));
+      if (!TBM && a.trace_impact) {  // what the pyramid folds upwards: the cell right after this update
+        const long long slot = __shfl_sync(0xffffffffu, rs, l);
+        if (lane == 0) {
+          a.trace_impact[slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+          double *tr = a.trace_rec + (size_t)slot * a.stride;
+          SG_COPY_REC(tr, r, a.stride);
+        }
+      }
     }
   }
   if (dirty) tbm_publish(a.model, r);
@@ -1154,10 +1164,12 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   ea.N = N; ea.M = M; ea.maps = ctx->scratch[7].as<MapSlot>(); ea.scale = maps[0]->scale; ea.est = *est;
   ea.cells = ctx->scratch[2].as<int2>();
   ea.aoo_p = aoo_p; ea.aoo_q = aoo_q; ea.keys = keys; ea.vals = vals; ea.slot_beam = slot_beam; ea.counters = counters;
-  // the cells around the robot leave the sort and run on the side stream (not when a pyramid wants the per-slot trace):
+  // the cells around the robot leave the sort and run on the side stream (with a pyramid's per-slot trace only for non-TBM cells):
   // the robot's own cell always (every ray starts in it: the longest chain of an insertion); for a few maps also the
   // ring of cells around it, whose runs of dozens to hundreds of updates would otherwise follow the sort
-  const bool robot_split = trace == nullptr;
+  const bool tbm_model = maps[0]->model == SLAMGPU_CELL_TBM_CONSISTENT || maps[0]->model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN ||
+                         maps[0]->model == SLAMGPU_CELL_CREDIBILIST;
+  const bool robot_split = trace == nullptr || !tbm_model;  // (TBM chains publish their fields once per run: no per-update trace there)
   static const int ring_env = getenv("SLAMGPU_RING") ? atoi(getenv("SLAMGPU_RING")) : -1;  // experiment: 0..6
   const int ring = !robot_split ? -1 : (ring_env >= 0 && ring_env <= 6 ? ring_env : (n <= 8 ? 6 : 0));  // (k_apply_ring unrolls 2 * 6 + 1 = 13 candidate slots per ray)
   ea.ring = ring;
@@ -1165,8 +1177,11 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   else k_estimate<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
   SG_LAUNCHED(ctx);
   SG_CUDA(ctx, cudaGetLastError());
+  if (trace && ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + maps[0]->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
   if (robot_split) {
     RobotArgs ra;
+    ra.trace_impact = trace ? ctx->scratch[5].as<double>() : nullptr; ra.trace_rec = trace ? ra.trace_impact + M : nullptr;
+    ra.trace_oie = trace ? trace->oie : 0;
     ra.maps = ctx->scratch[7].as<MapSlot>(); ra.n_maps = n; ra.beams = ctx->scratch[0].as<BeamRec>();
     ra.bout = ctx->scratch[3].as<BeamOut>(); ra.offsets = ctx->scratch[1].as<long long>(); ra.cells = ctx->scratch[2].as<int2>();
     ra.aoo_p = aoo_p; ra.aoo_q = aoo_q; ra.stride = maps[0]->stride; ra.model = maps[0]->model; ra.ring = ring;
@@ -1191,10 +1206,7 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   ApplyArgs aa;
   aa.keys = ks; aa.aoo = sorted_aoo; aa.M = M; aa.maps = ctx->scratch[7].as<MapSlot>(); aa.stride = maps[0]->stride; aa.model = maps[0]->model;
   aa.trace_impact = nullptr; aa.trace_rec = nullptr; aa.trace_oie = 0;
-  if (trace) {
-    if (ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + maps[0]->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
-    aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_rec = aa.trace_impact + M; aa.trace_oie = trace->oie;
-  }
+  if (trace) { aa.trace_impact = ctx->scratch[5].as<double>(); aa.trace_rec = aa.trace_impact + M; aa.trace_oie = trace->oie; }  // (reserved above)
   // long-run queue: at most M / SG_LONG_RUN entries, the counter in front
   const size_t lr_bytes = 64 + ((size_t)(M / SG_LONG_RUN) + 1) * sizeof(LongRun);
   if (ctx->scratch[6].reserve(lr_bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "long-run queue");

@@ -207,7 +207,11 @@ struct FoldArgs {
   double *cells;         // this level
   int stride, model, oie;
   unsigned char *alive_next;
+  unsigned *n_long;      // runs of SG_FOLD_LONG updates or more are queued for k_level_fold_long (a warp per run)
+  unsigned *long_runs;   // their first sorted positions
 };
+
+#define SG_FOLD_LONG 64
 
 // M3RSMRescalableGridMap::update_coarser_maps :101-126 for one level, one thread per level cell
 __global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
@@ -216,6 +220,10 @@ __global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
   const unsigned key = a.keys[j];
   if (key == SG_INVALID_KEY) return;
   if (j > 0 && a.keys[j - 1] == key) return;
+  if (j + SG_FOLD_LONG - 1 < a.M && a.keys[j + SG_FOLD_LONG - 1] == key) {  // (sorted: equal ends = one run)
+    a.long_runs[atomicAdd(a.n_long, 1u)] = (unsigned)j;
+    return;
+  }
   double cur[SLAMGPU_MAX_STRIDE];
   double *cell = a.cells + (size_t)key * a.stride;
   SG_COPY_REC(cur, cell, a.stride);
@@ -234,6 +242,51 @@ __global__ void __launch_bounds__(128) k_level_fold(FoldArgs a) {
   }
   if (changed)
     SG_COPY_REC(cell, cur, a.stride);
+}
+
+// The same fold for a long run (the coarse cell under the robot collects an update from every beam), a warp per run.  The
+// fold is a running maximum: an update survives only if it beats the value the cell holds when its turn comes, so in 32
+// consecutive updates few survive.  The lanes test their updates against the current value at once; the first that beats
+// it is the next survivor (everything before it dies, exactly as in the sequential walk), the value moves on to it, and
+// the lanes behind it test again: a handful of ballots per 32 updates instead of 32 dependent steps.
+__global__ void __launch_bounds__(128) k_level_fold_long(FoldArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned n_runs = *a.n_long;
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_runs; w += (gridDim.x * blockDim.x) >> 5) {
+    const long long j = a.long_runs[w];
+    const unsigned key = a.keys[j];
+    double cur[SLAMGPU_MAX_STRIDE];
+    double *cell = a.cells + (size_t)key * a.stride;
+    SG_COPY_REC(cur, cell, a.stride);
+    bool cur_unknown = sg::rec_is_unknown(a.model, cur);
+    double cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
+    bool changed = false;
+    for (long long t0 = j;; t0 += 32) {
+      const long long t = t0 + lane;
+      const bool in = t < a.M && a.keys[t] == key;
+      const double x = in ? a.g_impact[t] : 0.0;
+      const unsigned pending = __ballot_sync(0xffffffffu, in);
+      if (!pending) break;
+      unsigned survivors = 0, rem = pending;
+      while (rem) {
+        const bool beats_cur = ((rem >> lane) & 1u) && (cur_unknown || !sg::less_or_equal(x, cur_impact));
+        const unsigned b = __ballot_sync(0xffffffffu, beats_cur);
+        if (!b) break;
+        const int l = __ffs(b) - 1;
+        survivors |= 1u << l;
+        const double *r = a.g_rec + (size_t)(t0 + l) * a.stride;
+        SG_COPY_REC(cur, r, a.stride);
+        cur_unknown = sg::rec_is_unknown(a.model, cur);
+        cur_impact = sg::cell_impact(a.model, a.oie, cur, 0.0, 0.0);
+        changed = true;
+        rem &= l == 31 ? 0u : ~((2u << l) - 1u);
+      }
+      if (in) a.alive_next[a.vals[t]] = (survivors >> lane) & 1u;
+      if (pending != 0xffffffffu) break;  // the run ended inside this chunk
+    }
+    if (changed && lane == 0)
+      SG_COPY_REC(cell, cur, a.stride);
+  }
 }
 
 // ---------------------------------------------------------------- from-scratch build
@@ -696,7 +749,8 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
   const long long M = tr.M;
   if (M == 0) return SLAMGPU_OK;
   // per-position arrays: ent_slot (i32) coords (int2) keys vals keys_tmp vals_tmp (u32) alive alive_next (u8) counters
-  const size_t bytes = (size_t)M * (4 + 8 + 16 + 2) + 256 + (size_t)M * sizeof(double) * (1 + fine->stride) + 64;
+  const size_t bytes = (size_t)M * (4 + 8 + 16 + 2) + 256 + (size_t)M * sizeof(double) * (1 + fine->stride) + 64 +
+                       ((size_t)(M / SG_FOLD_LONG) + 2) * sizeof(unsigned) + 64;
   if (p->ent.reserve(bytes) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "pyramid update buffers (%lld updates)", M);
   int2 *coords = p->ent.as<int2>();
   int *ent_slot = (int *)(coords + M);
@@ -704,6 +758,7 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
   unsigned char *alive = (unsigned char *)(vals_tmp + M), *alive_next = alive + M;
   unsigned long long *counters = (unsigned long long *)(((uintptr_t)(alive_next + M) + 63) & ~(uintptr_t)63);
   double *g_impact = (double *)(counters + 8), *g_rec = g_impact + M;
+  unsigned *n_long = (unsigned *)(g_rec + (size_t)M * fine->stride), *long_runs = n_long + 16;  // counters[4] is cleared with the level's counters
   const unsigned nblk = (unsigned)((M + 127) / 128);
   OrderArgs oa;
   oa.offsets = tr.d_offsets; oa.bout = tr.d_bout; oa.cells = tr.cells; oa.N = tr.N; oa.M = M;
@@ -713,6 +768,7 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
   for (size_t id = 1; id < p->lv.size(); ++id) {
     slamgpu_map *lvl = p->lv[id];
     SG_CUDA(ctx, cudaMemsetAsync(counters, 0, 32, ctx->stream));
+    SG_CUDA(ctx, cudaMemsetAsync(n_long, 0, 64, ctx->stream));
     CoordArgs ca;
     ca.ent_slot = ent_slot; ca.alive = alive; ca.cells = tr.cells; ca.M = M; ca.fine_scale = fine->scale; ca.scale = lvl->scale;
     ca.w = lvl->w; ca.h = lvl->h; ca.ox = lvl->ox; ca.oy = lvl->oy; ca.coords = coords; ca.counters = counters;
@@ -751,7 +807,10 @@ static int pyramid_propagate(slamgpu_pyramid *p, const AppendTrace &tr) {
     FoldArgs fa;
     fa.keys = ks; fa.vals = vs; fa.M = M; fa.g_impact = g_impact; fa.g_rec = g_rec;
     fa.cells = lvl->d_cells; fa.stride = lvl->stride; fa.model = lvl->model; fa.oie = p->oie; fa.alive_next = alive_next;
+    fa.n_long = n_long; fa.long_runs = long_runs;
     k_level_fold<<<nblk, 128, 0, ctx->stream>>>(fa);
+    k_level_fold_long<<<ctx->sm_count, 128, 0, ctx->stream>>>(fa);
+    SG_LAUNCHED(ctx);
     SG_LAUNCHED(ctx);
     SG_CUDA(ctx, cudaGetLastError());
     sg_map_invalidate_lut(lvl);
@@ -1242,7 +1301,7 @@ extern "C" int slamgpu_debug_m3rsm(double x_limit, double y_limit, double rot_li
 
 #define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
 void sg_preload_pyramid() {  // see sg_preload_score
-  SG_TOUCH(k_order_entries); SG_TOUCH(k_level_coords); SG_TOUCH(k_level_keys); SG_TOUCH(k_level_gather); SG_TOUCH(k_level_fold);
+  SG_TOUCH(k_order_entries); SG_TOUCH(k_level_coords); SG_TOUCH(k_level_keys); SG_TOUCH(k_level_gather); SG_TOUCH(k_level_fold); SG_TOUCH(k_level_fold_long);
   SG_TOUCH(k_build_level); SG_TOUCH(k_build_fused<SLAMGPU_CELL_LWW>); SG_TOUCH(k_build_fused<SLAMGPU_CELL_MEAN>); SG_TOUCH(k_build_fused<SLAMGPU_CELL_TBM_CONSISTENT>); SG_TOUCH(k_build_fused<SLAMGPU_CELL_GMAPPING>); SG_TOUCH(k_fill_level); SG_TOUCH(k_window_terms); SG_TOUCH(k_ordered_sums); SG_TOUCH(k_ordered_sums_staged);
   (void)cudaGetLastError();
 }
