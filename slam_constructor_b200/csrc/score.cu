@@ -1377,8 +1377,8 @@ SG_DEV bool grid4_task(const GridArgs4 &a, int task, int &g, int &j) {
 }
 
 template <int DMAX, bool UNIW>
-__global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_score_grid4(GridArgs4 a) {
-  // 7 blocks of 4 warps per SM (72 registers) hold configs[2]'s 1026 blocks in ONE wave: every task (a warp walking all the
+__global__ void __launch_bounds__(128, DMAX <= 4 ? 9 : (DMAX <= 6 ? 5 : 4)) k_score_grid4(GridArgs4 a) {
+  // configs[2]'s 1030 blocks (7 per SM) must run as ONE wave -- 56 registers leave room for 9 --: every task (a warp walking all the
   // beams) takes the same time, so a second, nearly empty wave would double the kernel time
   // Which 128 candidates-columns this block takes.  Blocks are handed out per SM: the work is cut into one contiguous chunk
   // per SM (neighbouring y-groups of the same theta read the same LUT lines for a given beam), so that the warps resident on
@@ -1430,49 +1430,44 @@ __global__ void __launch_bounds__(128, DMAX <= 4 ? 7 : (DMAX <= 6 ? 5 : 4)) k_sc
   double acc[8];
 #pragma unroll
   for (int m = 0; m < 8; ++m) acc[m] = 0.0;
-  // Software pipeline without register rotation: the beam loop is unrolled by two; index set A serves the odd beams, B the
-  // even ones (each reloaded two beams ahead of its use, right after it was consumed), value sets v0 / v1 alternate.
-  // The index tables carry four zeroed beam rows of slack, so the prefetches past the last beam need no guard.
-  // One beam per loop half; values of beam i in v0 (even) / v1 (odd).  ptxas puts EVERY global load of the loop on one
-  // scoreboard (SB5 in all our kernels), so the first use of any loaded register waits for all loads in flight: the loads
-  // cannot run more than one beam ahead of their use whatever the source says.  Each half therefore does FIRST the products
-  // of its beam (the one place where the warp waits), THEN issues the gathers of the next beam -- their address is made to
-  // depend on a product so that the scheduler cannot hoist them above the wait --, reloads its index set in place (A serves
-  // the odd beams, B the even ones), and only then runs the adds, which overlap the loads' flight.
+  // ptxas puts EVERY global load of the loop on one scoreboard (SB5 in all our kernels), so the first use of any loaded
+  // register waits for all loads in flight: the loads cannot run more than one beam ahead of their use whatever the source
+  // says.  An iteration therefore does FIRST the products of its beam (the one place where the warp waits), THEN issues the
+  // gathers of the next beam -- their address is made to depend on a product so that the scheduler cannot hoist them above
+  // the wait --, reloads the index registers in place for the beam after that, and only then runs the adds, which overlap
+  // the loads' flight.  One value set and one index set are enough for that order (a set is dead once its products / its
+  // address are taken), which keeps the kernel at 56 registers (two sets: 72) and the loop short.
   // (Measured alternatives: gathers issued before the wait 0.67 ms; index pairs through a cp.async ring 0.91 ms -- LDGSTS
-  // costs ~1 cycle per lane here; two beams per wait 0.59 ms; this order 0.50 ms at configs[2].)
-  double v0[DMAX], v1[DMAX];
-  unsigned m0, m1 = 0;
+  // costs ~1 cycle per lane here; two beams per wait 0.59 ms; this order with two register sets, 72 registers 0.517 ms; one set 0.491 ms.)
+  double v[DMAX];
+  unsigned mcur;
   {
     const unsigned cx0 = __ldcg(cxp + ox);
     const uint2 cw0 = __ldcg(cyw + ow);
-    m0 = cw0.y;
+    mcur = cw0.y;
     const unsigned b = cw0.x + cx0;
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) v0[d] = __ldg(rowp[d] + b);
+    for (int d = 0; d < DMAX; ++d) v[d] = __ldg(rowp[d] + b);
   }
   // the index tables are streamed (L2 only: they would only push LUT lines out of L1)
-  unsigned cxA = __ldcg(cxp + (ox + sx)), cxB = __ldcg(cxp + (ox + 2 * sx));
-  uint2 cwA = __ldcg(cyw + (ow + sw)), cwB = __ldcg(cyw + (ow + 2 * sw));
-  ox += 3 * sx; ow += 3 * sw;
-#define SG_G4_HALF(VCUR, VNXT, MCUR, MNXT, CX, CW, I)                                      \
-  {                                                                                       \
-    const double wi = UNIW ? w0 : __ldg(a.w + (I));                                       \
-    double t[DMAX];                                                                       \
-    _Pragma("unroll") for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(VCUR[d], wi);         \
-    const unsigned b = CW.x + CX + ((unsigned)__double2hiint(t[0]) & zero);               \
-    MNXT = CW.y;                                                                          \
-    _Pragma("unroll") for (int d = 0; d < DMAX; ++d) VNXT[d] = __ldg(rowp[d] + b);        \
-    CX = __ldcg(cxp + ox); CW = __ldcg(cyw + ow);                                         \
-    ox += sx; ow += sw;                                                                   \
-    add_pattern<DMAX>(MCUR, acc, t);                                                      \
-  }
+  unsigned cx = __ldcg(cxp + (ox + sx));
+  uint2 cw = __ldcg(cyw + (ow + sw));
+  ox += 2 * sx; ow += 2 * sw;
 #pragma unroll 1
-  for (int i = 0; i < N; i += 2) {
-    SG_G4_HALF(v0, v1, m0, m1, cxA, cwA, i)
-    if (i + 1 < N) SG_G4_HALF(v1, v0, m1, m0, cxB, cwB, i + 1)
+  for (int i = 0; i < N; ++i) {
+    const double wi = UNIW ? w0 : __ldg(a.w + i);
+    double t[DMAX];
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(v[d], wi);
+    const unsigned b = cw.x + cx + ((unsigned)__double2hiint(t[0]) & zero);
+    const unsigned mnext = cw.y;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) v[d] = __ldg(rowp[d] + b);
+    cx = __ldcg(cxp + ox); cw = __ldcg(cyw + ow);
+    ox += sx; ow += sw;
+    add_pattern<DMAX>(mcur, acc, t);
+    mcur = mnext;
   }
-#undef SG_G4_HALF
   double best_s = -INFINITY;
   long long best_i = LLONG_MAX;
   // (group, column) are derived again from the task number rather than kept in registers across the beam loop
