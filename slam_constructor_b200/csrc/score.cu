@@ -1621,49 +1621,51 @@ __global__ void __launch_bounds__(64, 13) k_score_grid5(GridArgs5 a) {
   constexpr unsigned ST = SG_G5_STAGE;
   unsigned sw_ = 0;  // stage offset of slot i % STAGES
   // slots relative to sw_: patch / weight of beam i+k at sw_ + (k-P)*ST, records of beam i+k at sw_ + (k-P-Q)*ST
-  unsigned msk_cur = lds32(rw_addr + 4u + ((sw_ - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
-  unsigned nibw_next = lds32(nib_addr + ((sw_ + ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
-  double t_cur[DMAX], wi_cur = w0;
+  // two register sets, A and B, alternate (the loop is unrolled by two so that nothing has to be moved between them): the
+  // even beams are added out of A while B is loaded for the next beam, the odd ones the other way round
+  unsigned msk_a = lds32(rw_addr + 4u + ((sw_ - (SG_G5_P + SG_G5_Q) * ST) & ring_mask)), msk_b = 0;
+  unsigned nib_b = lds32(nib_addr + ((sw_ + ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask)), nib_a = 0;
+  double t_a[DMAX], t_b[DMAX], wi_a = w0, wi_b = w0;
   {
     const unsigned nibw0 = lds32(nib_addr + ((sw_ - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
     const unsigned s_val = (sw_ - SG_G5_P * ST) & ring_mask;
     const unsigned va = ring_w + s_val + ((nibw0 >> nib_shift) & 15u) * 8u;
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) t_cur[d] = lds_f64(va + d * SG_G5_ROW);
-    if (!UNIW) wi_cur = lds_f64(ring_w + 31u * 16u + s_val);
+    for (int d = 0; d < DMAX; ++d) t_a[d] = lds_f64(va + d * SG_G5_ROW);
+    if (!UNIW) wi_a = lds_f64(ring_w + 31u * 16u + s_val);
+  }
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) t_b[d] = 0.0;
+  // one beam: TC / WC / MC hold beam i; TN / WN / MN receive beam i+1 (its column nibbles are in NC); NN receives the
+  // nibbles of beam i+2
+#define SG_G5_BEAM(TC, WC, MC, TN, WN, MN, NC, NN)                                                                        \
+  {                                                                                                                      \
+    cp_async_wait<SG_G5_Q - 1>(); /* all copies but the last Q-1 have landed: iterations <= i-Q (patch of beam i+1 included) */ \
+    __syncwarp();                                                                                                        \
+    const unsigned s_nxt = (sw_ + ST - SG_G5_P * ST) & ring_mask;                                                         \
+    const unsigned va = ring_w + s_nxt + ((NC >> nib_shift) & 15u) * 8u;                                                  \
+    _Pragma("unroll") for (int d = 0; d < DMAX; ++d) TN[d] = lds_f64(va + d * SG_G5_ROW);                                 \
+    if (!UNIW) WN = lds_f64(ring_w + 31u * 16u + s_nxt);                                                                  \
+    NN = lds32(nib_addr + ((sw_ + 2u * ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));                                      \
+    MN = lds32(rw_addr + 4u + ((sw_ + ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));                                       \
+    const unsigned s_adr = (sw_ - SG_G5_Q * ST) & ring_mask;                                                              \
+    const unsigned col0 = lds32(ring_w + 28u * 16u + s_adr);                                                              \
+    const uint2 rw = lds64(rw_addr + s_adr);                                                                              \
+    const unsigned u = is_patch ? rw.x + col0 : uidx;                                                                     \
+    uidx += inc;                                                                                                          \
+    cp_async16(my_chunk + sw_, base + (size_t)u * 8u, true); /* patch + weight of beam i+P, records of beam i+P+Q */       \
+    cp_async_commit();                                                                                                    \
+    double t[DMAX];                                                                                                       \
+    _Pragma("unroll") for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(TC[d], WC);                                           \
+    add_pattern<DMAX>(MC, acc, t);                                                                                        \
+    sw_ = (sw_ + ST) & ring_mask;                                                                                         \
   }
 #pragma unroll 1
-  for (int i = 0; i < N; ++i) {
-    cp_async_wait<SG_G5_Q - 1>();  // all copies but the last Q-1 have landed: iterations <= i-Q (patch of beam i+1 included)
-    __syncwarp();
-    // (a) beam i+1: its patch values and weight into registers
-    const unsigned s_nxt = (sw_ + ST - SG_G5_P * ST) & ring_mask;
-    const unsigned va = ring_w + s_nxt + ((nibw_next >> nib_shift) & 15u) * 8u;
-    double t_next[DMAX], wi_next = w0;
-#pragma unroll
-    for (int d = 0; d < DMAX; ++d) t_next[d] = lds_f64(va + d * SG_G5_ROW);
-    if (!UNIW) wi_next = lds_f64(ring_w + 31u * 16u + s_nxt);
-    // (b) records: column nibbles of beam i+2, new-row mask of beam i+1, patch address of beam i+P
-    const unsigned nibw_nn = lds32(nib_addr + ((sw_ + 2u * ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
-    const unsigned msk_next = lds32(rw_addr + 4u + ((sw_ + ST - (SG_G5_P + SG_G5_Q) * ST) & ring_mask));
-    const unsigned s_adr = (sw_ - SG_G5_Q * ST) & ring_mask;
-    const unsigned col0 = lds32(ring_w + 28u * 16u + s_adr);
-    const uint2 rw = lds64(rw_addr + s_adr);
-    // (c) this iteration's copy: patch + weight of beam i+P, records of beam i+P+Q
-    const unsigned u = is_patch ? rw.x + col0 : uidx;
-    uidx += inc;
-    cp_async16(my_chunk + sw_, base + (size_t)u * 8u, true);
-    cp_async_commit();
-    // (d) beam i out of registers
-    double t[DMAX];
-#pragma unroll
-    for (int d = 0; d < DMAX; ++d) t[d] = sg::mul(t_cur[d], wi_cur);
-    add_pattern<DMAX>(msk_cur, acc, t);
-#pragma unroll
-    for (int d = 0; d < DMAX; ++d) t_cur[d] = t_next[d];
-    wi_cur = wi_next; msk_cur = msk_next; nibw_next = nibw_nn;
-    sw_ = (sw_ + ST) & ring_mask;
+  for (int i = 0; i < N; i += 2) {
+    SG_G5_BEAM(t_a, wi_a, msk_a, t_b, wi_b, msk_b, nib_b, nib_a)
+    if (i + 1 < N) SG_G5_BEAM(t_b, wi_b, msk_b, t_a, wi_a, msk_a, nib_a, nib_b)
   }
+#undef SG_G5_BEAM
   cp_async_wait<0>();
 
   double best_s = -INFINITY;
