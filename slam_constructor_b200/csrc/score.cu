@@ -1638,10 +1638,12 @@ __global__ void __launch_bounds__(64, 13) k_score_grid5(GridArgs5 a) {
   for (int d = 0; d < DMAX; ++d) t_b[d] = 0.0;
   // one beam: TC / WC / MC hold beam i; TN / WN / MN receive beam i+1 (its column nibbles are in NC); NN receives the
   // nibbles of beam i+2
-#define SG_G5_BEAM(TC, WC, MC, TN, WN, MN, NC, NN)                                                                        \
+#define SG_G5_BEAM(TC, WC, MC, TN, WN, MN, NC, NN, WAIT)                                                                  \
   {                                                                                                                      \
-    cp_async_wait<SG_G5_Q - 1>(); /* all copies but the last Q-1 have landed: iterations <= i-Q (patch of beam i+1 included) */ \
-    __syncwarp();                                                                                                        \
+    if (WAIT) { /* one wait serves both halves: all copies but the last Q-2 have landed, i.e. iterations <= i+1-Q */      \
+      cp_async_wait<SG_G5_Q - 2>();                                                                                      \
+      __syncwarp();                                                                                                      \
+    }                                                                                                                    \
     const unsigned s_nxt = (sw_ + ST - SG_G5_P * ST) & ring_mask;                                                         \
     const unsigned va = ring_w + s_nxt + ((NC >> nib_shift) & 15u) * 8u;                                                  \
     _Pragma("unroll") for (int d = 0; d < DMAX; ++d) TN[d] = lds_f64(va + d * SG_G5_ROW);                                 \
@@ -1662,8 +1664,8 @@ __global__ void __launch_bounds__(64, 13) k_score_grid5(GridArgs5 a) {
   }
 #pragma unroll 1
   for (int i = 0; i < N; i += 2) {
-    SG_G5_BEAM(t_a, wi_a, msk_a, t_b, wi_b, msk_b, nib_b, nib_a)
-    if (i + 1 < N) SG_G5_BEAM(t_b, wi_b, msk_b, t_a, wi_a, msk_a, nib_a, nib_b)
+    SG_G5_BEAM(t_a, wi_a, msk_a, t_b, wi_b, msk_b, nib_b, nib_a, true)
+    if (i + 1 < N) SG_G5_BEAM(t_b, wi_b, msk_b, t_a, wi_a, msk_a, nib_a, nib_b, false)
   }
 #undef SG_G5_BEAM
   cp_async_wait<0>();
