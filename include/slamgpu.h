@@ -139,18 +139,25 @@ int slamgpu_ctx_create(int device, slamgpu_ctx **out);
 /* one rank of an n-rank job (one process per GPU).  `nccl_id` is the 128-byte
  * ncclUniqueId made by slamgpu_nccl_unique_id on rank 0 and shipped to the others by
  * the launcher.  Candidate sets are sharded over ranks by contiguous index range and
- * merged by one 16-byte-per-rank all-gather. */
+ * merged through NVLink peer mailboxes inside the finalize kernel (one 32-byte-per-rank
+ * NCCL all-gather where peer mapping is unavailable). */
 int slamgpu_nccl_unique_id(void *id128);
 int slamgpu_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id128, slamgpu_ctx **out);
 void slamgpu_ctx_destroy(slamgpu_ctx *ctx);
 const char *slamgpu_last_error(const slamgpu_ctx *ctx); /* ctx may be NULL: last create error */
 int slamgpu_sync(slamgpu_ctx *ctx);
 /* tuning knobs (defaults are right for production):
- *   "grid_variant"  highest brute-force grid kernel allowed: 0 = automatic (= 4), 4 = every distinct map row gathered
- *                   once per thread + indexed-branch accumulate (default; needs ascending y, unit point factors and at
- *                   most 8 cell rows under 8 consecutive y, else 2), 2 = packed row words + L1-resident gathers,
- *                   3 = map patches staged in shared memory by TMA bulk copies (kept for comparison: 2.3x slower
- *                   than 2 at configs[2]), 1 = explicit row table
+ *   "grid_variant"  highest brute-force grid kernel allowed: 0 = automatic (5 when the candidate set leaves the GPU
+ *                   partly empty, 4 otherwise); 5 = variant 4's arithmetic behind a per-warp cp.async ring (LUT patches
+ *                   and index records staged in shared memory many beams ahead; needs at most 4 cell rows under 8
+ *                   consecutive y, else 4); 4 = every distinct map row gathered once per thread + indexed-branch
+ *                   accumulate (needs ascending y, unit point factors and at most 8 cell rows under 8 consecutive y,
+ *                   else 2); 2 = packed row words + L1-resident gathers; 3 = map patches staged in shared memory by TMA
+ *                   bulk copies (kept for comparison: 2.3x slower than 2 at configs[2]); 1 = explicit row table.
+ *                   Window OOPEs (max / mean) run on variant 1 over window tables, overlap / GMapping as a pose list.
+ *   "warm_l2"       1 = stream the score LUT through L2 on a side stream before big grid launches (default 0)
+ *   "p2p_timeout_ms" how long a rank waits for its peers' results in the fused exchange before the ctx falls back to
+ *                   NCCL all-gathers (default 20000)
  *   "grid_rows"     rows per thread of variant 2: 0 = automatic, 2 / 4 / 8 */
 int slamgpu_ctx_set_option(slamgpu_ctx *ctx, const char *name, int64_t value);
 /* device-side stop watch on the ctx stream (CUDA events) for bench.py */

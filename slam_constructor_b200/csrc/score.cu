@@ -1497,14 +1497,14 @@ void launch_grid4(slamgpu_ctx *ctx, const GridArgs4 &a, int nblk, bool uniw) {
 // copy pipeline.  ptxas puts EVERY global load of a loop on one scoreboard (SB5 in all our kernels), so the first use of any
 // loaded register waits for all loads in flight: register prefetching cannot run more than one beam ahead, and a warp pays a
 // full L2 round trip per beam (ncu, lone warp: ~700 cycles per beam).  cp.async (LDGSTS) completes per commit group
-// instead, so here each warp issues ONE 16-byte-per-lane copy per beam, two beams ahead of its use:
-//   lanes 0 .. 7*DMAX-1   the LUT patch of beam i+2: DMAX consecutive rows x 14 columns (7 aligned pairs) holding every
+// instead, so here each warp issues ONE 16-byte-per-lane copy per beam, SG_G5_P beams ahead of its use:
+//   lanes 0 .. 7*DMAX-1   the LUT patch of beam i+P: DMAX consecutive rows x 14 columns (7 aligned pairs) holding every
 //                         cell the warp's <= 30 consecutive x can touch in its 8 y;
-//   lanes 28, 29          the column record of beam i+4 {first column, 32 nibbles};
-//   lane 30               the row word pair of beam i+4 {row offset, new-row mask};
-//   lane 31               the point weight pair of beam i+2 (uneven weights only);
-// into a ring of four 512-byte stages private to the warp (no block barrier anywhere).  Every value the loop consumes comes
-// from shared memory (LDS, ~30 cycles); cp.async.wait_group 1 leaves the youngest copy in flight.
+//   lanes 28, 29          the column record of beam i+P+Q {first column, 32 nibbles};
+//   lane 30               the row word pair of beam i+P+Q {row offset, new-row mask};
+//   lane 31               the point weight pair of beam i+P (uneven weights only);
+// into a ring of SG_G5_STAGES 512-byte stages private to the warp (no block barrier anywhere).  Every value the loop
+// consumes comes from shared memory (LDS, ~30 cycles); cp.async.wait_group leaves the youngest copies in flight.
 struct GridArgs5 {
   const double *lut;
   const uint4 *colrec;
