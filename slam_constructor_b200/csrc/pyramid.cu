@@ -1227,13 +1227,14 @@ extern "C" int slamgpu_match_m3rsm(slamgpu_pyramid *p, int32_t n, const double *
         SG_CUDA(ctx, cudaGetLastError());
         // poll the completion flag (a few microseconds cheaper than a stream synchronisation); a failed launch or a
         // device fault never sets it, so look at the stream now and then
+        int idle_seen = 0;
         for (unsigned spins = 0; *h_flag != seq; ++spins) {
           if ((spins & 0xFFFFu) == 0xFFFFu) {
             const cudaError_t q = cudaStreamQuery(ctx->stream);
-            if (q != cudaErrorNotReady && *h_flag != seq) {
-              if (q == cudaSuccess) continue;  // finished between the two looks: the flag is visible on the next read
-              return sg_fail(ctx, SLAMGPU_E_CUDA, "match_m3rsm: %s", cudaGetErrorString(q));
-            }
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) return sg_fail(ctx, SLAMGPU_E_CUDA, "match_m3rsm: %s", cudaGetErrorString(q));
+            // the stream is idle: the flag must be visible by the next look or two
+            if (++idle_seen > 2 && *h_flag != seq) return sg_fail(ctx, SLAMGPU_E_CUDA, "match_m3rsm: the scoring kernel finished without reporting");
           }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
