@@ -42,17 +42,17 @@ struct RayWalker {
     double e_x = add(e, e_x_inc), e_y = add(e, e_y_inc);
     double diff = sub(fabs(e_y), fabs(e_x));
     // are_equal(diff, 0.0) (math_utils.h:10-16) is |diff - 0| <= 1e-7 * max(1, |diff|, 0): for |diff| <= 1 the scale is
-    // 1, above 1 the test fails either way -- so it is exactly |diff| <= 1e-7, without the chain of max / multiply
-    if (fabs(diff) <= 1e-7) {
-      if (px == endx) py += inc_y;
-      else if (py == endy) px += inc_x;
-      else { px += inc_x; py += inc_y; }
-      e = 0;
-    } else if (0 < diff) {
-      px += inc_x; e = e_x;
-    } else {
-      py += inc_y; e = e_y;
-    }
+    // 1, above 1 the test fails either way -- so it is exactly |diff| <= 1e-7, without the chain of max / multiply.
+    // The three-way choice of the reference (diagonal step on a tie -- only along the axis that is left when the other
+    // has arrived --, x step if the error favours it, else y step) is spelled with selects: the lanes of a warp walk
+    // different rays, and as branches the three arms run one after the other for every step.
+    const bool tie = fabs(diff) <= 1e-7;
+    const bool x_wins = 0 < diff;
+    const bool step_x = tie ? px != endx : x_wins;
+    const bool step_y = tie ? (px == endx || py != endy) : !x_wins;
+    e = tie ? 0.0 : (x_wins ? e_x : e_y);
+    px += step_x ? inc_x : 0;
+    py += step_y ? inc_y : 0;
     return true;
   }
 };
