@@ -15,7 +15,7 @@ namespace sg {
 // A resumable walker: next() yields the cells of the segment in the reference's order.
 struct RayWalker {
   int px, py, sx, sy, endx, endy, inc_x, inc_y;
-  long long cells_nm, n;
+  int cells_nm, n;  // (a ray spans at most 2^26 cells per axis: the callers refuse longer ones)
   double e, e_x_inc, e_y_inc;
   bool done;
 
@@ -25,7 +25,8 @@ struct RayWalker {
     px = sx = world_to_cell(bx, scale); py = sy = world_to_cell(by, scale);
     endx = world_to_cell(ex, scale); endy = world_to_cell(ey, scale);
     long long ax = (long long)endx - px, ay = (long long)endy - py;
-    cells_nm = (ax < 0 ? -ax : ax) + (ay < 0 ? -ay : ay) + 1;
+    const long long span = (ax < 0 ? -ax : ax) + (ay < 0 ? -ay : ay) + 1;
+    cells_nm = span > 0x7fffffffll ? 0x7fffffff : (int)span;
     double midx = mul(add((double)px, 0.5), scale), midy = mul(add((double)py, 0.5), scale);
     double mid_seg_y = add(mul(d_x, by), mul(sub(midx, bx), d_y));
     e = sub(mid_seg_y, mul(midy, d_x));
