@@ -597,8 +597,12 @@ struct RobotArgs {
 // are one per beam at most, in beam order -- no sort needed.  The lanes test 32 beams at a time for "does this ray
 // pass through my cell", then the hits are applied in beam order (the chain of dependent updates), W = 0 being the
 // robot's own cell, which every ray starts in.
-template <bool TBM>
+// MODEL: the cell model as a compile-time constant (the update's switch and the operands it does not read drop out of the
+// chain) or -1 for the run-time a.model
+template <bool TBM, int MODEL>
 __global__ void __launch_bounds__(128) k_apply_ring(RobotArgs a) {
+  const int model = MODEL >= 0 ? MODEL : a.model;
+  constexpr bool WANT_XY = MODEL < 0 || MODEL == SLAMGPU_CELL_GMAPPING;  // only the GMapping cell reads the obstacle point
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int side = 2 * a.ring + 1, per_map = side * side;
@@ -646,19 +650,19 @@ __global__ void __launch_bounds__(128) k_apply_ring(RobotArgs a) {
       if (TBM)
         chain_update_tbm(r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, quality, l), fx, lane, &dirty);
       else
-        sg::cell_update(a.model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), __shfl_sync(0xffffffffu, wx, l),
-                        __shfl_sync(0xffffffffu, wy, l), __shfl_sync(0xffffffffu, quality, l));
+        sg::cell_update(model, r, __shfl_sync(0xffffffffu, p, l), __shfl_sync(0xffffffffu, q, l), WANT_XY ? __shfl_sync(0xffffffffu, wx, l) : 0.0,
+                        WANT_XY ? __shfl_sync(0xffffffffu, wy, l) : 0.0, __shfl_sync(0xffffffffu, quality, l));
       if (!TBM && a.trace_impact) {  // what the pyramid folds upwards: the cell right after this update
         const long long slot = __shfl_sync(0xffffffffu, rs, l);
         if (lane == 0) {
-          a.trace_impact[slot] = sg::cell_impact(a.model, a.trace_oie, r, 0.0, 0.0);
+          a.trace_impact[slot] = sg::cell_impact(model, a.trace_oie, r, 0.0, 0.0);
           double *tr = a.trace_rec + (size_t)slot * a.stride;
           SG_COPY_REC(tr, r, a.stride);
         }
       }
     }
   }
-  if (dirty) tbm_publish(a.model, r);
+  if (dirty) tbm_publish(model, r);
   if (any && lane == 0)
     SG_COPY_REC(cell, r, a.stride);
 }
@@ -1189,8 +1193,14 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     SG_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     const bool tbm_cells = ra.model == SLAMGPU_CELL_TBM_CONSISTENT || ra.model == SLAMGPU_CELL_TBM_UNKNOWN_EVEN || ra.model == SLAMGPU_CELL_CREDIBILIST;
     const long long warps = (long long)n * (2 * ring + 1) * (2 * ring + 1);
-    if (tbm_cells) k_apply_ring<true><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
-    else k_apply_ring<false><<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->side>>>(ra);
+    const unsigned rblk = (unsigned)((warps * 32 + 127) / 128);
+    if (tbm_cells) k_apply_ring<true, -1><<<rblk, 128, 0, ctx->side>>>(ra);
+    else switch (ra.model) {
+      case SLAMGPU_CELL_MEAN: k_apply_ring<false, SLAMGPU_CELL_MEAN><<<rblk, 128, 0, ctx->side>>>(ra); break;
+      case SLAMGPU_CELL_AFFINE: k_apply_ring<false, SLAMGPU_CELL_AFFINE><<<rblk, 128, 0, ctx->side>>>(ra); break;
+      case SLAMGPU_CELL_GMAPPING: k_apply_ring<false, SLAMGPU_CELL_GMAPPING><<<rblk, 128, 0, ctx->side>>>(ra); break;
+      default: k_apply_ring<false, -1><<<rblk, 128, 0, ctx->side>>>(ra); break;
+    }
     SG_LAUNCHED(ctx);
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
   }
@@ -1442,6 +1452,7 @@ void sg_preload_mapping() {  // see sg_preload_score
   SG_TOUCH(k_raycast); SG_TOUCH(k_estimate<true>); SG_TOUCH(k_estimate<false>); SG_TOUCH(k_radix_hist); SG_TOUCH(k_radix_scan);
   SG_TOUCH(k_scan_chunks); SG_TOUCH(k_scan_add); SG_TOUCH(k_radix_scatter); SG_TOUCH(k_gather_sorted); SG_TOUCH(k_apply);
   SG_TOUCH((k_apply_long<true, false>)); SG_TOUCH((k_apply_long<false, false>)); SG_TOUCH((k_apply_long<false, true>));
-  SG_TOUCH(k_apply_ring<true>); SG_TOUCH(k_apply_ring<false>); SG_TOUCH(k_copy_block); SG_TOUCH(k_fill);
+  SG_TOUCH((k_apply_ring<true, -1>)); SG_TOUCH((k_apply_ring<false, -1>)); SG_TOUCH((k_apply_ring<false, SLAMGPU_CELL_MEAN>));
+  SG_TOUCH((k_apply_ring<false, SLAMGPU_CELL_AFFINE>)); SG_TOUCH((k_apply_ring<false, SLAMGPU_CELL_GMAPPING>)); SG_TOUCH(k_copy_block); SG_TOUCH(k_fill);
   (void)cudaGetLastError();
 }
