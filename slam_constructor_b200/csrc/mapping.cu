@@ -95,34 +95,13 @@ struct EstimateArgs {
   int *slot_beam;         // per slot
   unsigned long long *counters;  // per map: [2*id+1] updates dropped outside a bounded map ([2*id]: see k_raycast)
   int ring;               // >= 0: cells within this many cells of the robot are taken out of the sort (k_apply_ring)
+  int head;               // k_estimate skips the first `head` cells of every ray (k_estimate_head has done them)
 };
 
 // AREA = false: the const estimator only (a select); the kernel then does not carry the area estimator's registers
+// everything k_estimate does for slot s = cell k of beam i
 template <bool AREA>
-__global__ void __launch_bounds__(128) k_estimate(EstimateArgs a) {
-  const long long s0 = blockIdx.x * (long long)blockDim.x;
-  long long s = s0 + threadIdx.x;
-  // beam of a slot: last i with offsets[i] <= s.  Two threads bracket the block's slots with a full binary search,
-  // the others search inside that bracket (a block rarely spans more than a couple of beams)
-  __shared__ int s_range[2];
-  if (threadIdx.x < 2) {
-    long long t = threadIdx.x == 0 ? s0 : min(s0 + (long long)blockDim.x - 1, a.M - 1);
-    int lo = 0, hi = a.N;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (a.offsets[mid] <= t) lo = mid; else hi = mid;
-    }
-    s_range[threadIdx.x] = lo;
-  }
-  __syncthreads();
-  if (s >= a.M) return;
-  int lo = s_range[0], hi = s_range[1] + 1;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (a.offsets[mid] <= s) lo = mid; else hi = mid;
-  }
-  const int i = lo;
-  const int k = (int)(s - a.offsets[i]);
+SG_DEV void estimate_slot(const EstimateArgs &a, long long s, int i, int k) {
   const BeamOut bo = a.bout[i];
   a.vals[s] = (unsigned)s;
   a.slot_beam[s] = i;
@@ -161,6 +140,47 @@ __global__ void __launch_bounds__(128) k_estimate(EstimateArgs a) {
       a.keys[s] = ms.key_base + (unsigned)iy * (unsigned)ms.w + (unsigned)ix;
     }
   }
+}
+
+template <bool AREA>
+__global__ void __launch_bounds__(128) k_estimate(EstimateArgs a) {
+  const long long s0 = blockIdx.x * (long long)blockDim.x;
+  long long s = s0 + threadIdx.x;
+  // beam of a slot: last i with offsets[i] <= s.  Two threads bracket the block's slots with a full binary search,
+  // the others search inside that bracket (a block rarely spans more than a couple of beams)
+  __shared__ int s_range[2];
+  if (threadIdx.x < 2) {
+    long long t = threadIdx.x == 0 ? s0 : min(s0 + (long long)blockDim.x - 1, a.M - 1);
+    int lo = 0, hi = a.N;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (a.offsets[mid] <= t) lo = mid; else hi = mid;
+    }
+    s_range[threadIdx.x] = lo;
+  }
+  __syncthreads();
+  if (s >= a.M) return;
+  int lo = s_range[0], hi = s_range[1] + 1;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (a.offsets[mid] <= s) lo = mid; else hi = mid;
+  }
+  const int i = lo;
+  const int k = (int)(s - a.offsets[i]);
+  if (k < a.head) return;  // done by k_estimate_head, ahead of the ring kernel
+  estimate_slot<AREA>(a, s, i, k);
+}
+
+// The first `head` cells of every ray, one thread each: all the ring kernel needs (a ray can be inside the window around the
+// robot only during its first 2W+1 cells), so that it can start beside the estimate of the other ~95 % of the slots
+template <bool AREA>
+__global__ void __launch_bounds__(128) k_estimate_head(EstimateArgs a) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int i = (int)(t / a.head), k = (int)(t - (long long)i * a.head);
+  if (i >= a.N) return;
+  const long long s = a.offsets[i] + k;
+  if (s >= a.offsets[i + 1]) return;
+  estimate_slot<AREA>(a, s, i, k);
 }
 
 // ---------------------------------------------------------------- stable LSD radix sort (8-bit digits)
@@ -1177,10 +1197,15 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   static const int ring_env = getenv("SLAMGPU_RING") ? atoi(getenv("SLAMGPU_RING")) : -1;  // experiment: 0..6
   const int ring = !robot_split ? -1 : (ring_env >= 0 && ring_env <= 6 ? ring_env : (n <= 8 ? 6 : 0));  // (k_apply_ring unrolls 2 * 6 + 1 = 13 candidate slots per ray)
   ea.ring = ring;
-  if (est->type == SLAMGPU_EST_AREA) k_estimate<true><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
-  else k_estimate<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
-  SG_LAUNCHED(ctx);
-  SG_CUDA(ctx, cudaGetLastError());
+  // the ring kernel reads only the first 2 * ring + 1 cells of every ray: those are estimated first (one small launch), the
+  // ring forks off, and the other slots are estimated beside it
+  ea.head = robot_split ? 2 * ring + 1 : 0;
+  if (ea.head > 0) {
+    const unsigned hblk = (unsigned)(((long long)N * ea.head + 127) / 128);
+    if (est->type == SLAMGPU_EST_AREA) k_estimate_head<true><<<hblk, 128, 0, ctx->stream>>>(ea);
+    else k_estimate_head<false><<<hblk, 128, 0, ctx->stream>>>(ea);
+    SG_LAUNCHED(ctx);
+  }
   if (trace && ctx->scratch[5].reserve((size_t)M * sizeof(double) * (1 + maps[0]->stride)) != SLAMGPU_OK) return sg_fail(ctx, SLAMGPU_E_NOMEM, "trace buffer");
   if (robot_split) {
     RobotArgs ra;
@@ -1205,6 +1230,10 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
   }
 
+  if (est->type == SLAMGPU_EST_AREA) k_estimate<true><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
+  else k_estimate<false><<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(ea);
+  SG_LAUNCHED(ctx);
+  SG_CUDA(ctx, cudaGetLastError());
   // ---- sort by (map, cell) (stable), then apply each cell's run in order
   unsigned *ks, *vs;
   SG_TRY(sg_radix_sort(ctx, keys, vals, keys_tmp, vals_tmp, M, (unsigned)key_total, &ks, &vs));
@@ -1449,7 +1478,7 @@ extern "C" int slamgpu_estimate_occupancy(slamgpu_ctx *ctx, const slamgpu_estima
 
 #define SG_TOUCH(k) do { cudaFuncAttributes fa_; (void)cudaFuncGetAttributes(&fa_, k); } while (0)
 void sg_preload_mapping() {  // see sg_preload_score
-  SG_TOUCH(k_raycast); SG_TOUCH(k_estimate<true>); SG_TOUCH(k_estimate<false>); SG_TOUCH(k_radix_hist); SG_TOUCH(k_radix_scan);
+  SG_TOUCH(k_raycast); SG_TOUCH(k_estimate<true>); SG_TOUCH(k_estimate<false>); SG_TOUCH(k_estimate_head<true>); SG_TOUCH(k_estimate_head<false>); SG_TOUCH(k_radix_hist); SG_TOUCH(k_radix_scan);
   SG_TOUCH(k_scan_chunks); SG_TOUCH(k_scan_add); SG_TOUCH(k_radix_scatter); SG_TOUCH(k_gather_sorted); SG_TOUCH(k_apply);
   SG_TOUCH((k_apply_long<true, false>)); SG_TOUCH((k_apply_long<false, false>)); SG_TOUCH((k_apply_long<false, true>));
   SG_TOUCH((k_apply_ring<true, -1>)); SG_TOUCH((k_apply_ring<false, -1>)); SG_TOUCH((k_apply_ring<false, SLAMGPU_CELL_MEAN>));
