@@ -508,12 +508,16 @@ SG_DEV void tbm_update_warp(double *r, double p, double q, double quality, int l
   const double tot = add(add(add(tu, te), to), tc);
   const int k = lane & 3;
   double num = k == 0 ? tu : (k == 1 ? te : (k == 2 ? to : tc));
-  double qv = careful ? tbm_div<true>(num, tot, near_one(tot)) : __ddiv_rn(num, tot);
+  // (x / 1 = x exactly: the masses of both sides sum to one up to rounding, so the total is exactly 1.0 for many updates,
+  // and the test is uniform over the warp)
+  double qv = num;
+  if (tot != 1.0) qv = careful ? tbm_div<true>(num, tot, near_one(tot)) : __ddiv_rn(num, tot);
   double ou = __shfl_sync(0xffffffffu, qv, 0), oe = __shfl_sync(0xffffffffu, qv, 1), oo = __shfl_sync(0xffffffffu, qv, 2);
   if (tot == 0.0) { ou = 1.0; oe = 0.0; oo = 0.0; }
   const double w = add(add(ou, oe), oo);  // normalize_conflict
   num = k == 0 ? ou : (k == 1 ? oe : oo);
-  qv = careful ? tbm_div<true>(num, w, near_one(w)) : __ddiv_rn(num, w);
+  qv = num;
+  if (w != 1.0) qv = careful ? tbm_div<true>(num, w, near_one(w)) : __ddiv_rn(num, w);
   double nu = __shfl_sync(0xffffffffu, qv, 0), ne = __shfl_sync(0xffffffffu, qv, 1), no = __shfl_sync(0xffffffffu, qv, 2);
   if (w == 0.0) { nu = 1.0; ne = 0.0; no = 0.0; }
   r[2] = nu; r[3] = ne; r[4] = no;
