@@ -1043,9 +1043,11 @@ int m3rsm_search(const std::vector<M3Rot> &rots, double x_limit, double y_limit,
     }
   };
   std::unordered_map<Key, double, KeyHash> known;
+  known.reserve(8192);  // a match scores ~1000 windows: no rehash on the way
   auto key_of = [](const HMatch &m) { return Key{m.scan_id, m.bot, m.top, m.left, m.right}; };
   std::vector<HMatch> heap;  // std::priority_queue's own algorithm (push_heap / pop_heap), kept open for peeking
   std::vector<HMatch> ask, spec;
+  heap.reserve(2048); ask.reserve(1024); spec.reserve(4096);
   // (a call costs ~25 us however many matches it carries up to a few thousand: 768 / 96 halves the calls of 192 / 12)
   const size_t kSpeculate = 768, kPeek = 96;
   auto score = [&](std::vector<HMatch> &ms) -> int {
