@@ -205,6 +205,7 @@ extern "C" void slamgpu_ctx_destroy(slamgpu_ctx *ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evk0);
   cudaEventDestroy(ctx->evk1);
+  if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->side);

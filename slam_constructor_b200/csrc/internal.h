@@ -114,6 +114,8 @@ struct slamgpu_ctx {
   double clock_hz = 1.965e9;       // SM clock (cudaDevAttrClockRate) for clock64 deadlines
   cudaStream_t side = nullptr;  // the robot cell's update chain runs here, next to the sort (mapping.cu)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_staged = nullptr;  // recorded behind the uploads of a deferred batched insertion (sg_append_plans): the next batch
+  bool staged_pending = false;      // may refill the pinned staging block once it has fired, while the kernels still run
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // around the dominant kernel of the last call
   bool evk_valid = false;

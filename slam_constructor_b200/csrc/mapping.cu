@@ -947,6 +947,7 @@ int run_raycast_multi(slamgpu_ctx *ctx, double scale, const BeamRec *beams, int 
       SG_CUDA(ctx, cudaMallocHost(&ctx->h_slots, slot_bytes * 2));
       ctx->h_slots_cap = slot_bytes * 2;
     }
+    if (ctx->staged_pending) { SG_CUDA(ctx, cudaEventSynchronize(ctx->ev_staged)); ctx->staged_pending = false; }  // (the slot block of the batch before)
     hp = ctx->h_slots;
   } else {
     SG_TRY(sg_pinned(ctx, bb + ob + slot_bytes, &hp));
@@ -961,6 +962,11 @@ int run_raycast_multi(slamgpu_ctx *ctx, double scale, const BeamRec *beams, int 
   if (N) SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0].p, beams, sizeof(BeamRec) * N, cudaMemcpyHostToDevice, ctx->stream));
   SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[1].p, offsets, sizeof(long long) * ((size_t)N + 1), cudaMemcpyHostToDevice, ctx->stream));
   SG_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[7].p, hp, slot_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (beams_pinned) {
+    if (!ctx->ev_staged) SG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev_staged, ctx->stream));
+    ctx->staged_pending = true;
+  }
   if (ctx->scratch[2].reserve(std::max<size_t>(M, 1) * sizeof(int2)) != SLAMGPU_OK ||
       ctx->scratch[3].reserve(std::max<size_t>(N, 1) * sizeof(BeamOut)) != SLAMGPU_OK)
     return sg_fail(ctx, SLAMGPU_E_NOMEM, "ray-cast buffers (%lld slots)", M);
@@ -1053,7 +1059,7 @@ int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, con
 // pose): one ray-cast launch, one estimate launch, ONE sort over (map, cell) keys and one apply launch for all of
 // them.  Maps must share cell model, cell size and ctx.  `trace` is only available for n == 1.
 int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *plans, int n, const slamgpu_estimator *est,
-                    int64_t *cells_updated, AppendTrace *trace) {
+                    int64_t *cells_updated, AppendTrace *trace, unsigned long long *deferred) {
   if (!ctx || !maps || !plans || n <= 0 || !est) return sg_fail(ctx, SLAMGPU_E_INVALID, "append: NULL argument");
   if (est->type != SLAMGPU_EST_CONST && est->type != SLAMGPU_EST_AREA) return sg_fail(ctx, SLAMGPU_E_INVALID, "bad estimator type");
   if (trace && n != 1) return sg_fail(ctx, SLAMGPU_E_INVALID, "append: a trace needs a single map");
@@ -1078,7 +1084,10 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
     const size_t bb = (sizeof(BeamRec) * (size_t)N + 63) & ~(size_t)63;
     void *hp;
     SG_TRY(sg_pinned(ctx, bb + sizeof(long long) * ((size_t)N + 1), &hp));
-    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging may still be in flight
+    // the pinned staging block may still be in flight: behind a deferred batch only its uploads have to be over (their
+    // event), not its kernels
+    if (ctx->staged_pending) { SG_CUDA(ctx, cudaEventSynchronize(ctx->ev_staged)); ctx->staged_pending = false; }
+    else SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     BeamRec *all_beams = (BeamRec *)hp;
     long long *all_offs = (long long *)((char *)hp + bb);
     for (int k = 0; k < n; ++k) {
@@ -1274,6 +1283,11 @@ int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *
   if (robot_split) SG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   for (int k = 0; k < n; ++k)
     if (plans[k].M > 0) sg_map_invalidate_lut(maps[k]);
+  if (deferred) {
+    SG_CUDA(ctx, cudaMemcpyAsync(deferred, counters, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    return SLAMGPU_OK;
+  }
+  ctx->staged_pending = false;  // (the synchronisation below covers the uploads too)
   if (ctx->h_counters_cap < (size_t)n * 16) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     ctx->h_counters = nullptr; ctx->h_counters_cap = 0;

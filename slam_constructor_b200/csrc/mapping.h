@@ -62,8 +62,10 @@ int sg_prepare_beams(const slamgpu_map *m, const slamgpu_scan *s, const double p
                      double blur, double max_range, const double *point_quality, bool gate, BeamPlan *plan);
 int sg_plan_from_beams(slamgpu_ctx *ctx, const slamgpu_map *map, int32_t n, const double *beams, const uint8_t *is_occ,
                        const double *quality, double blur, double max_range, BeamPlan *out);
+// deferred (optional, pinned, 2 values per map): the call returns with its work queued -- the cell counts land there when the
+// stream gets to them, the caller synchronises -- so that the host work of the next batch overlaps this batch's kernels
 int sg_append_plans(slamgpu_ctx *ctx, slamgpu_map *const *maps, const BeamPlan *plans, int n, const slamgpu_estimator *est,
-                    int64_t *cells_updated, AppendTrace *trace);
+                    int64_t *cells_updated, AppendTrace *trace, unsigned long long *deferred = nullptr);
 int sg_append_plan(slamgpu_ctx *ctx, slamgpu_map *map, const BeamPlan &plan, const slamgpu_estimator *est,
                    int64_t *cells_updated, AppendTrace *trace);
 int sg_append_scan_impl(slamgpu_ctx *ctx, slamgpu_map *map, slamgpu_scan *scan, const double pose[3], double scan_quality,

@@ -36,6 +36,8 @@ struct slamgpu_particles {
   std::vector<slamgpu_map *> maps;
   // GROW_TILED particle maps (UnboundedLazyTiledGridMap upstream) share copy-on-write tiles out of this pool; NULL: dense maps
   SgTilePool *pool = nullptr;
+  unsigned long long *h_counts = nullptr;  // pinned: per local particle {cells updated, dropped} of the last insertion
+  size_t h_counts_cap = 0;
   int64_t resample_bytes = 0, resample_tiles_shared = 0;  // of the last resampling
   double resample_ms = 0;
   int lo = 0, hi = 0, chunk = 0;
@@ -75,6 +77,7 @@ extern "C" void slamgpu_particles_destroy(slamgpu_particles *p) {
   for (slamgpu_map *m : p->maps)
     if (m) slamgpu_map_destroy(m);
   sg_pool_destroy(p->pool);
+  if (p->h_counts) cudaFreeHost(p->h_counts);
   delete p;
 }
 
@@ -362,7 +365,14 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
     if (rc[k] != SLAMGPU_OK) return publish(sg_fail(ctx, SLAMGPU_E_INVALID, "particle %d: a beam spans more than 2^26 cells", who[k]));
   // batches bounded by the 32-bit (map, cell) key space and 2^30 cell slots
   std::vector<slamgpu_map *> maps;
-  std::vector<int64_t> counts;
+  if (p->h_counts_cap < (size_t)m * 2) {
+    if (p->h_counts) cudaFreeHost(p->h_counts);
+    p->h_counts = nullptr; p->h_counts_cap = 0;
+    if (cudaMallocHost(&p->h_counts, sizeof(unsigned long long) * 2 * (size_t)p->chunk) != cudaSuccess)
+      return publish(sg_fail(ctx, SLAMGPU_E_NOMEM, "particles_append_scan: pinned counters"));
+    p->h_counts_cap = 2 * (size_t)p->chunk;
+  }
+  unsigned long long *h_counts = p->h_counts;
   for (int k0 = 0; k0 < m;) {
     unsigned long long keys = 0;
     long long slots = 0;
@@ -375,12 +385,18 @@ extern "C" int slamgpu_particles_append_scan(slamgpu_particles *p, slamgpu_scan 
     }
     maps.clear();
     for (int k = k0; k < k1; ++k) maps.push_back(p->maps[who[k]]);
-    counts.assign(k1 - k0, 0);
-    const int arc = sg_append_plans(ctx, maps.data(), plans.data() + k0, k1 - k0, est, counts.data(), nullptr);
-    if (arc != SLAMGPU_OK) return publish(arc);
-    for (int k = k0; k < k1; ++k) count_of(who[k]) = counts[k - k0];
+    // deferred: the batch is queued and the loop goes on to prepare the next one while its kernels run; the cell counts
+    // of every batch land in one pinned array, read after the one synchronisation below
+    const int arc = sg_append_plans(ctx, maps.data(), plans.data() + k0, k1 - k0, est, nullptr, nullptr, h_counts + 2 * (size_t)k0);
+    if (arc != SLAMGPU_OK) { cudaStreamSynchronize(ctx->stream); ctx->staged_pending = false; return publish(arc); }
     k0 = k1;
   }
+  {
+    const cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    ctx->staged_pending = false;
+    if (se != cudaSuccess) return publish(sg_fail(ctx, SLAMGPU_E_CUDA, "particles_append_scan: %s", cudaGetErrorString(se)));
+  }
+  for (int k = 0; k < m; ++k) count_of(who[k]) = (int64_t)h_counts[2 * (size_t)k];
   return publish(SLAMGPU_OK);
 }
 
